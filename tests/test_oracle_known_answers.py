@@ -1,0 +1,225 @@
+"""Pins oracle/agref.py against every exact known-answer vector the reference holds for the hot
+path.  Citations: file:line under /root/reference."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import agref as ag
+from oracle.agref import Param, diff, grad, gradloss, value, Sparse, full
+
+
+def F(a):
+    return np.asfortranarray(np.array(a, dtype=np.float64))
+
+
+def test_readme_sum_abs2():
+    # README.md:37-44 / src/AutoGrad.jl:17-19
+    x = Param(F([1, 2, 3]))
+    y = diff(lambda: ag.sumabs2(x))
+    assert value(y) == 14
+    assert np.array_equal(grad(y, x), [2, 4, 6])
+
+
+def test_gradloss():
+    # src/AutoGrad.jl:38-42
+    g, l = gradloss(lambda x: ag.sumabs2(x))(F([[1, 2, 3]]))
+    assert l == 14 and np.array_equal(g, [[2, 4, 6]])
+
+
+def test_power_rules_exact():
+    # test/base.jl:94-110
+    assert grad(lambda x: x ** 2)(1) == 2
+    assert np.array_equal(grad(lambda x: ag.sum_(x ** 2))(F([1, 2, 3])), [2, 4, 6])
+    assert np.array_equal(grad(lambda x: ag.sum_(x ** 2.0))(F([1, 2, 3])), [2., 4., 6.])
+    r = F([[1, 2], [3, 4]])
+    assert np.array_equal(grad(lambda x: ag.sum_(x ** 2))(r), [[2, 4], [6, 8]])
+    assert np.array_equal(grad(lambda x: ag.sum_(x ** 2.0))(r), [[2, 4], [6, 8]])
+    with pytest.raises(RuntimeError):
+        grad(lambda x: ag.sum_(ag.matpow(x, 2)))(r)
+    assert grad(lambda x: ag.sum_(x ** 3.1))(r).dtype == np.float64
+
+
+def test_core_known_answers():
+    # test/core.jl:35
+    x = Param(1)
+    assert grad(diff(lambda: ag.sin(ag.sqrt(x))), x) == math.cos(1) / 2
+    # :40 (Issue 101.1) identity on a Param
+    x = Param(1.0)
+    assert grad(diff(lambda: x), x) == 1
+    # :44 (Issue 101.2)
+    x = Param(F([1., 2.]))
+    assert np.array_equal(grad(diff(lambda: ag.sum_(1 * x)), x), [1.0, 1.0])
+    # :48-49 (Issue 103)
+    assert grad(lambda x: ag.exp(x))(1.) == math.exp(1.)
+    assert np.array_equal(grad(lambda x: ag.sum_(ag.exp(x)))(F([1.])), [math.exp(1.)])
+    # :65-68 result not last on tape
+    x = Param(np.asfortranarray(np.random.default_rng(0).random((2, 3))))
+
+    def f(x):
+        x1 = ag.sum_(x)
+        x2 = 2 * x  # noqa: F841 recorded after the result
+        return x1
+    assert np.array_equal(grad(diff(lambda: f(x)), x), np.ones((2, 3)))
+
+
+def test_highorder_sin_cycle():
+    # test/highorder.jl:6-14 -- exact equality through order 9
+    g = ag.sin
+    expect = [math.cos(1), -math.sin(1), -math.cos(1), math.sin(1)]
+    for k in range(9):
+        g = grad(g)
+        assert g(1) == expect[k % 4], k
+
+
+def test_highorder_exp_tanh():
+    # test/highorder.jl:28-34
+    assert math.exp(1) == grad(ag.exp)(1) == grad(grad(ag.exp))(1)
+    f = lambda x: ag.exp(x * x)  # noqa: E731
+    assert np.isclose(f(1), grad(f)(1) / 2) and np.isclose(f(1), grad(grad(f))(1) / 6)
+    t = math.tanh(1)
+    assert grad(ag.tanh)(1) == 1 - t ** 2
+    assert np.isclose(grad(grad(ag.tanh))(1), -2 * t * (1 - t ** 2), rtol=1e-15)
+    # PR #75 (test/highorder.jl:19)
+    assert grad(lambda x: x * grad(lambda y: x + y)(1 * x))(5.0) == 1
+
+
+def test_getindex_size_known_answer():
+    # test/getindex.jl:51-58
+    g = grad(lambda x: ag.size(x, 0) * ag.sumabs2(x))(np.ones((3, 3), order="F"))
+    assert np.array_equal(g, np.full((3, 3), 6.0))
+
+
+def test_sparse_known_answers():
+    # test/sparse.jl:7-16 (indices shifted to 0-based)
+    a = Sparse(np.zeros((3, 4), order="F"), [F([1., 1.]), F([1., 1.]), 1., 1.],
+               [([0, 1],), (range(2, 4),), (1, 1), (0,)])
+    fa = full(a)
+    lin = fa.reshape(-1, order="F")
+    assert list(lin[:5]) == [2, 1, 1, 1, 1] and not lin[5:].any()
+    b = a + a
+    assert isinstance(b, Sparse)
+    assert np.array_equal(full(b), full(a) + full(a))
+    ag.addto(a, Sparse(a.container, list(a.values), list(a.indices)))
+    assert isinstance(a, Sparse)
+    assert np.array_equal(full(a), full(b))
+    # lmul! stays Sparse (test/sparse.jl:18-23)
+    w = Param(np.asfortranarray(np.random.default_rng(1).standard_normal((2, 2))))
+
+    def foo(w):
+        s = 0.0
+        for i in range(4):
+            s = s + w[i]
+        return s
+    J = diff(lambda: foo(w))
+    assert isinstance(ag.lmul(0.5, grad(J, w)), Sparse)
+    assert np.array_equal(full(grad(J, w)), np.ones((2, 2)))
+
+
+def test_tape_node_order_readme():
+    # README.md:116-125 pins the node order for sum(abs2, w*x .+ b - y)
+    rng = np.random.default_rng(0)
+    w, b = Param(F(rng.standard_normal((2, 3)))), Param(F(rng.standard_normal(2)))
+    x, y = F(rng.standard_normal((3, 4))), F(rng.standard_normal((2, 4)))
+    J = diff(lambda: ag.sumabs2((w @ x + b) - y))
+    names = [("P" if isinstance(n.Value, Param) else n.Value.func.name) for n in J.list]
+    assert names == ["P", "*", "P", "+", "-", "sum(abs2,·)"]
+    assert J.list[0].Value is w and J.list[2].Value is b
+
+
+def test_relu_tie_passes_gradient():
+    # src/math.jl:54: dy.*(y.==xi) -> derivative 1 at 0
+    g = grad(lambda x: ag.sum_(ag.relu(x)))(F([-1., 0., 2.]))
+    assert np.array_equal(g, [0., 1., 1.])
+    g = grad(lambda x: ag.sum_(ag.abs_(x)))(F([-1., 0., 2.]))
+    assert np.array_equal(g, [-1., 0., 1.])
+
+
+def test_getindex_kinds_gradcheck():
+    # test/getindex.jl:8-26 index kinds, repeated indices summed
+    rng = np.random.default_rng(3)
+    a = F(rng.standard_normal((3, 4)))
+    for idx in [(slice(None),), (0,), (range(0, 2),), (range(0, 3, 2),), ([0, 1],), ([1, 1],), ([],),
+                (np.array([True, False, True] * 4),), (0, 1), (slice(None), [1, 1, 3]),
+                ([0, 2], range(1, 3)), (np.array([[0, 1], [2, 3]]),)]:
+        assert ag.gradcheck(lambda x: ag.getindex(x, *idx), a), idx
+    g = grad(lambda x: ag.sum_(ag.getindex(x, [1, 1])))(a)
+    assert g.reshape(-1, order="F")[1] == 2.0
+
+
+def test_unbroadcast_shapes():
+    # test/base.jl:46-58 shapes (2,3,5)/(1,3,5) and (2,3,5,4)/(2,3,1,4)
+    rng = np.random.default_rng(4)
+    for s1, s2 in [((2, 3, 5), (1, 3, 5)), ((2, 3, 5, 4), (2, 3, 1, 4)), ((64, 7), (64,)), ((5, 7), (1, 7)), ((5, 7), ())]:
+        a = F(rng.standard_normal(s1))
+        b = F(rng.standard_normal(s2)) if s2 else float(rng.standard_normal())
+        for op in (ag.add, ag.sub, ag.mul, ag.div):
+            assert ag.gradcheck(lambda p, q: op(p, q), a, b), (s1, s2, op)
+            assert ag.gradcheck(lambda p, q: op(q, p), a, b), (s1, s2, op)
+    x = Param(F(rng.standard_normal(64)))
+    J = diff(lambda: ag.sum_(F(rng.standard_normal((64, 5))) + x))
+    assert grad(J, x).shape == (64,)
+    with pytest.raises(ValueError):
+        ag.unbroadcast(np.zeros((3, 2)), np.zeros((3, 4)))
+
+
+def test_every_rule_gradcheck():
+    # test/math.jl:21-87, test/base.jl:28-89, test/statistics.jl:9-21, test/cat.jl, test/linearalgebra.jl:57
+    rng = np.random.default_rng(5)
+    x = F(rng.standard_normal((3, 4)))
+    xp = np.abs(x) + 0.5
+    for f, a in [(ag.exp, x), (ag.log, xp), (ag.tanh, x), (ag.sin, x), (ag.cos, x), (ag.sqrt, xp), (ag.sigm, x),
+                 (ag.abs_, x), (ag.abs2, x), (ag.neg, x), (ag.relu, x), (ag.vec, x), (ag.copy, x), (ag.adjoint, x)]:
+        assert ag.gradcheck(f, a), f
+    for f in (ag.sum_, ag.sumabs2, ag.sumabs, ag.mean, ag.meanabs2, ag.maximum, ag.minimum, ag.prod):
+        assert ag.gradcheck(f, x), f
+        for d in (0, 1, (0, 1)):
+            assert ag.gradcheck(lambda a: f(a, dims=d), x), (f, d)
+    w = F(rng.standard_normal((2, 3)))
+    assert ag.gradcheck(ag.matmul, w, x)
+    assert ag.gradcheck(lambda a, b: ag.matmul(a, ag.adjoint(b)), x, x.copy(order="F"))
+    assert ag.gradcheck(ag.max_, x, F(rng.standard_normal((3, 4))))
+    assert ag.gradcheck(ag.min_, x, F(rng.standard_normal((3, 1))))
+    assert ag.gradcheck(lambda a: a ** 3, xp) and ag.gradcheck(lambda a, b: a ** b, xp, xp.copy(order="F"))
+    assert ag.gradcheck(ag.vcat, x, x.copy(order="F")) and ag.gradcheck(ag.hcat, x, F(rng.standard_normal((3, 2))))
+    assert ag.gradcheck(lambda a, b: ag.cat1d(a, b), x, w)
+    assert ag.gradcheck(lambda a: ag.reshape(a, (4, 3)), x)
+    assert ag.gradcheck(lambda a: ag.permutedims(a, (1, 0)), x)
+
+
+def test_neuralnet_first_and_second_order():
+    # test/neuralnet.jl:4-18 (2-layer relu MLP); test/highorder.jl:36-42 (hessian shapes)
+    rng = np.random.default_rng(6)
+    w1, b1, w2, b2 = (F(rng.standard_normal(s)) for s in [(4, 3), (4,), (2, 4), (2,)])
+    x, y = F(rng.standard_normal((3, 5))), F(rng.standard_normal((2, 5)))
+
+    def loss(w1, b1, w2, b2):
+        h = ag.relu(ag.add(ag.matmul(w1, x), b1))
+        return ag.sumabs2(ag.sub(ag.add(ag.matmul(w2, h), b2), y))
+    assert ag.gradcheck(loss, w1, b1, w2, b2)
+
+    def nll(p):
+        p = ag.exp(p)
+        p = ag.div(p, ag.sum_(p, dims=0))
+        p = ag.getindex(p, 0, slice(None))
+        return ag.mean(ag.neg(ag.log(p)))
+    w, b, x = F(rng.standard_normal((2, 3))), F(rng.standard_normal(2)), F(rng.standard_normal((3, 4)))
+    hess = lambda f: grad(lambda a: ag.sum_(grad(f)(a)))  # noqa: E731
+    assert hess(lambda w_: nll(ag.add(ag.matmul(w_, x), b)))(w).shape == w.shape
+    assert hess(lambda b_: nll(ag.add(ag.matmul(w, x), b_)))(b).shape == b.shape
+    # second-order gradient checked numerically
+    assert ag.gradcheck(lambda w_: ag.sum_(grad(lambda a: nll(ag.add(ag.matmul(a, x), b)))(w_)), w)
+
+
+def test_softmax_xent_identity():
+    # analytic identity (SURVEY 8c "additional"): d/dp of -sum(y.*(p .- log(sum(exp(p),dims=1))))/B = (softmax(p)-y)/B
+    rng = np.random.default_rng(7)
+    p = F(rng.standard_normal((10, 6)))
+    y = np.zeros((10, 6), order="F")
+    y[rng.integers(0, 10, 6), np.arange(6)] = 1
+
+    def loss(p):
+        return ag.div(ag.neg(ag.sum_(ag.mul(y, ag.sub(p, ag.log(ag.sum_(ag.exp(p), dims=0)))))), 6)
+    g = grad(loss)(p)
+    sm = np.exp(p) / np.exp(p).sum(0, keepdims=True)
+    assert np.allclose(g, (sm - y) / 6, rtol=1e-13, atol=1e-15)
