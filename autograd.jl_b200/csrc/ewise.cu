@@ -1,0 +1,606 @@
+// ewise.cu -- elementwise forward kernels and the fused gradient kernels `dx = dy .* g(x,y)`.
+//
+// Reference: every rule of src/math.jl:9-74 and src/base.jl:20-49,73-74 is a Julia broadcast
+// expression evaluated by Base on the CPU, one pass per dotted call (src/core.jl:68-70 stops
+// fusion).  Here each rule is ONE kernel: 128-bit vector loads/stores, 4 vectors in flight per
+// thread, exact grids (HBM-bound: algorithmic bytes 3*N*s for a unary gradient).
+#include "common.cuh"
+
+namespace agb {
+
+template <typename T>
+struct alignas(16) Pack {
+  static constexpr int N = 16 / sizeof(T);
+  T v[N];
+};
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+// ---- unary op table -----------------------------------------------------------------------------
+template <int OP, typename T>
+struct U;
+
+#define AG_DEF_U(OP, NX, NY, FEXPR, GEXPR)                         \
+  template <typename T>                                            \
+  struct U<OP, T> {                                                \
+    static constexpr bool needs_x = NX, needs_y = NY;              \
+    static __device__ __forceinline__ T f(T x) { return FEXPR; }   \
+    static __device__ __forceinline__ T g(T x, T y) { return GEXPR; } \
+  };
+
+template <typename T>
+__device__ __forceinline__ T sgn(T x) {
+  return x > T(0) ? T(1) : (x < T(0) ? T(-1) : x);  // sign(0)=0, sign(NaN)=NaN like Julia
+}
+template <typename T>
+__device__ __forceinline__ T relu(T x) {
+  return x > T(0) ? x : (x != x ? x : T(0));
+}
+
+//        op            x?     y?     f(x)                          g(x,y)
+AG_DEF_U(AG_U_IDENTITY, false, false, x, T(1))
+AG_DEF_U(AG_U_NEG, false, false, -x, T(-1))
+AG_DEF_U(AG_U_ABS, true, false, fabs(x), sgn(x))
+AG_DEF_U(AG_U_ABS2, true, false, x* x, T(2) * x)
+AG_DEF_U(AG_U_EXP, false, true, exp(x), y)
+AG_DEF_U(AG_U_LOG, true, false, log(x), T(1) / x)
+AG_DEF_U(AG_U_TANH, false, true, tanh(x), T(1) - y * y)
+AG_DEF_U(AG_U_SIGM, false, true, T(1) / (T(1) + exp(-x)), y*(T(1) - y))
+AG_DEF_U(AG_U_SQRT, false, true, sqrt(x), T(1) / (T(2) * y))
+AG_DEF_U(AG_U_SIN, true, false, sin(x), cos(x))
+AG_DEF_U(AG_U_COS, true, false, cos(x), -sin(x))
+AG_DEF_U(AG_U_TAN, false, true, tan(x), T(1) + y * y)
+AG_DEF_U(AG_U_SINH, true, false, sinh(x), cosh(x))
+AG_DEF_U(AG_U_COSH, true, false, cosh(x), sinh(x))
+AG_DEF_U(AG_U_ASIN, true, false, asin(x), T(1) / sqrt(T(1) - x * x))
+AG_DEF_U(AG_U_ACOS, true, false, acos(x), T(-1) / sqrt(T(1) - x * x))
+AG_DEF_U(AG_U_ATAN, true, false, atan(x), T(1) / (T(1) + x * x))
+AG_DEF_U(AG_U_ASINH, true, false, asinh(x), T(1) / sqrt(T(1) + x * x))
+AG_DEF_U(AG_U_ACOSH, true, false, acosh(x), T(1) / sqrt(x * x - T(1)))
+AG_DEF_U(AG_U_ATANH, true, false, atanh(x), T(1) / (T(1) - x * x))
+AG_DEF_U(AG_U_EXP2, false, true, exp2(x), y* T(0.69314718055994530942))
+AG_DEF_U(AG_U_EXP10, false, true, exp10(x), y* T(2.30258509299404568402))
+AG_DEF_U(AG_U_EXPM1, false, true, expm1(x), T(1) + y)
+AG_DEF_U(AG_U_LOG2, true, false, log2(x), T(1) / (T(0.69314718055994530942) * x))
+AG_DEF_U(AG_U_LOG10, true, false, log10(x), T(1) / (T(2.30258509299404568402) * x))
+AG_DEF_U(AG_U_LOG1P, true, false, log1p(x), T(1) / (T(1) + x))
+AG_DEF_U(AG_U_CBRT, false, true, cbrt(x), T(1) / (T(3) * y * y))
+AG_DEF_U(AG_U_SIGN, false, false, sgn(x), T(0))
+AG_DEF_U(AG_U_RELU, true, false, relu(x), (x >= T(0) ? T(1) : T(0)))
+AG_DEF_U(AG_U_ONE, false, false, T(1), T(0))
+
+template <typename T>
+__device__ __forceinline__ Pack<T> load_pack(const T* __restrict__ p, int64_t i, bool vec) {
+  Pack<T> r;
+  if (vec) {
+    r = *reinterpret_cast<const Pack<T>*>(p + i);
+  } else {
+#pragma unroll
+    for (int j = 0; j < Pack<T>::N; ++j) r.v[j] = p[i + j];
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void store_pack(T* __restrict__ p, int64_t i, const Pack<T>& r, bool vec) {
+  if (vec) {
+    *reinterpret_cast<Pack<T>*>(p + i) = r;
+  } else {
+#pragma unroll
+    for (int j = 0; j < Pack<T>::N; ++j) p[i + j] = r.v[j];
+  }
+}
+
+template <int OP, typename T>
+__global__ void __launch_bounds__(kThreads) k_unary_fwd(const T* __restrict__ x, T* __restrict__ y,
+                                                        int64_t n, bool vec) {
+  constexpr int N = Pack<T>::N;
+  const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll * N);
+  Pack<T> in[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    int64_t i = base + ((int64_t)u * kThreads + threadIdx.x) * N;
+    if (i + N <= n) in[u] = load_pack(x, i, vec);
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    int64_t i = base + ((int64_t)u * kThreads + threadIdx.x) * N;
+    if (i + N <= n) {
+      Pack<T> o;
+#pragma unroll
+      for (int j = 0; j < N; ++j) o.v[j] = U<OP, T>::f(in[u].v[j]);
+      store_pack(y, i, o, vec);
+    } else {
+      for (; i < n; ++i) y[i] = U<OP, T>::f(x[i]);
+    }
+  }
+}
+
+// dx = dy .* g(x, y);  DYARR: dy is a full array, else a scalar (device scalar or immediate)
+template <int OP, typename T, bool DYARR>
+__global__ void __launch_bounds__(kThreads)
+    k_unary_bwd(const T* __restrict__ dy, T dy_imm, bool dy_dev_scalar, const T* __restrict__ x,
+                const T* __restrict__ y, T* __restrict__ dx, int64_t n, bool vec) {
+  constexpr int N = Pack<T>::N;
+  constexpr bool NX = U<OP, T>::needs_x, NY = U<OP, T>::needs_y;
+  const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll * N);
+  T dys = dy_imm;
+  if (!DYARR && dy_dev_scalar) dys = dy[0];
+  Pack<T> vdy[kUnroll], vx[kUnroll], vy[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    int64_t i = base + ((int64_t)u * kThreads + threadIdx.x) * N;
+    if (i + N <= n) {
+      if (DYARR) vdy[u] = load_pack(dy, i, vec);
+      if (NX) vx[u] = load_pack(x, i, vec);
+      if (NY) vy[u] = load_pack(y, i, vec);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    int64_t i = base + ((int64_t)u * kThreads + threadIdx.x) * N;
+    if (i + N <= n) {
+      Pack<T> o;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        T d = DYARR ? vdy[u].v[j] : dys;
+        o.v[j] = d * U<OP, T>::g(NX ? vx[u].v[j] : T(0), NY ? vy[u].v[j] : T(0));
+      }
+      store_pack(dx, i, o, vec);
+    } else {
+      for (; i < n; ++i) {
+        T d = DYARR ? dy[i] : dys;
+        dx[i] = d * U<OP, T>::g(NX ? x[i] : T(0), NY ? y[i] : T(0));
+      }
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <int OP, typename T>
+static ag_status launch_unary_fwd(const void* x, void* y, int64_t n) {
+  Context& c = ctx();
+  constexpr int N = Pack<T>::N;
+  int64_t blocks = cdiv(n, (int64_t)kThreads * kUnroll * N);
+  bool vec = aligned16(x) && aligned16(y);
+  k_unary_fwd<OP, T><<<(unsigned)blocks, kThreads, 0, c.stream>>>((const T*)x, (T*)y, n, vec);
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+template <int OP, typename T>
+static ag_status launch_unary_bwd(const void* dy, int dy_mode, double dy_scalar, const void* x,
+                                  const void* y, void* dx, int64_t n) {
+  Context& c = ctx();
+  constexpr int N = Pack<T>::N;
+  if (U<OP, T>::needs_x && !x) {
+    set_error("ag_unary_bwd: op %d needs x", OP);
+    return AG_EINVAL;
+  }
+  if (U<OP, T>::needs_y && !y) {
+    set_error("ag_unary_bwd: op %d needs y", OP);
+    return AG_EINVAL;
+  }
+  int64_t blocks = cdiv(n, (int64_t)kThreads * kUnroll * N);
+  bool vec = aligned16(dx) && (!U<OP, T>::needs_x || aligned16(x)) &&
+             (!U<OP, T>::needs_y || aligned16(y)) && (dy_mode != 0 || aligned16(dy));
+  if (dy_mode == 0)
+    k_unary_bwd<OP, T, true><<<(unsigned)blocks, kThreads, 0, c.stream>>>(
+        (const T*)dy, T(0), false, (const T*)x, (const T*)y, (T*)dx, n, vec);
+  else
+    k_unary_bwd<OP, T, false><<<(unsigned)blocks, kThreads, 0, c.stream>>>(
+        (const T*)dy, (T)dy_scalar, dy_mode == 1, (const T*)x, (const T*)y, (T*)dx, n, vec);
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+#define AG_FOR_UNARY(X)                                                                          \
+  X(AG_U_IDENTITY) X(AG_U_NEG) X(AG_U_ABS) X(AG_U_ABS2) X(AG_U_EXP) X(AG_U_LOG) X(AG_U_TANH)     \
+  X(AG_U_SIGM) X(AG_U_SQRT) X(AG_U_SIN) X(AG_U_COS) X(AG_U_TAN) X(AG_U_SINH) X(AG_U_COSH)        \
+  X(AG_U_ASIN) X(AG_U_ACOS) X(AG_U_ATAN) X(AG_U_ASINH) X(AG_U_ACOSH) X(AG_U_ATANH) X(AG_U_EXP2)  \
+  X(AG_U_EXP10) X(AG_U_EXPM1) X(AG_U_LOG2) X(AG_U_LOG10) X(AG_U_LOG1P) X(AG_U_CBRT) X(AG_U_SIGN) \
+  X(AG_U_RELU) X(AG_U_ONE)
+
+// ---- n-ary broadcast map -------------------------------------------------------------------------
+// out[i0,i1,i2,i3] = F(in0[...], in1[...], in2[...]) over a (collapsed) <=4-d column-major shape;
+// each operand has per-dimension element strides (0 = broadcast) or is an immediate.
+struct Opnd {
+  const void* p;
+  double imm;
+  int64_t s[4];
+  int mode;  // 0 immediate, 1 unit stride along dim0 (vectorisable), 2 broadcast along dim0, 3 strided
+};
+
+template <int NIN>
+struct MapArgs {
+  Opnd in[NIN];
+  void* out;
+  int64_t shape[4];
+  int64_t n;
+  int nd;
+  bool big;  // n >= 2^31: 64-bit index arithmetic
+};
+
+template <typename T, int NIN, typename F, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_map(const MapArgs<NIN> a) {
+  constexpr int N = VEC ? Pack<T>::N : 1;
+  // element index of this thread's first item in each unrolled slot
+  const int64_t base = ((int64_t)blockIdx.x * kUnroll * kThreads + threadIdx.x) * N;
+  T* __restrict__ out = (T*)a.out;
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const int64_t i = base + (int64_t)u * kThreads * N;
+    if (i >= a.n) break;
+    // decompose i into (i0, i1, i2, i3)
+    int64_t idx[4] = {i, 0, 0, 0};
+    if (a.nd > 1) {
+      if (a.big) {
+        int64_t r = i;
+        for (int d = 0; d < a.nd - 1; ++d) {
+          int64_t q = r / a.shape[d];
+          idx[d] = r - q * a.shape[d];
+          r = q;
+        }
+        idx[a.nd - 1] = r;
+      } else {
+        uint32_t r = (uint32_t)i;
+        for (int d = 0; d < a.nd - 1; ++d) {
+          uint32_t sd = (uint32_t)a.shape[d];
+          uint32_t q = r / sd;
+          idx[d] = r - q * sd;
+          r = q;
+        }
+        idx[a.nd - 1] = r;
+      }
+    }
+    T v[NIN][N];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) {
+      const Opnd& o = a.in[k];
+      if (o.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[k][j] = (T)o.imm;
+      } else {
+        const T* __restrict__ p = (const T*)o.p;
+        int64_t off = idx[0] * o.s[0];
+        for (int d = 1; d < a.nd; ++d) off += idx[d] * o.s[d];
+        if (VEC && o.mode == 1) {
+          Pack<T> t = *reinterpret_cast<const Pack<T>*>(p + off);
+#pragma unroll
+          for (int j = 0; j < N; ++j) v[k][j] = t.v[j];
+        } else if (o.mode == 2) {
+          T t = p[off];
+#pragma unroll
+          for (int j = 0; j < N; ++j) v[k][j] = t;
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) v[k][j] = p[off + j * o.s[0]];
+        }
+      }
+    }
+    if (VEC) {
+      Pack<T> r;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        T in[NIN];
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) in[k] = v[k][j];
+        r.v[j] = F::apply(in);
+      }
+      *reinterpret_cast<Pack<T>*>(out + i) = r;
+    } else {
+      T in[NIN];
+#pragma unroll
+      for (int k = 0; k < NIN; ++k) in[k] = v[k][0];
+      out[i] = F::apply(in);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T jmax(T a, T b) {  // Julia max: NaN-propagating
+  return (a != a || b != b) ? (a + b) : (a > b ? a : (b > a ? b : (signbit(a) ? b : a)));
+}
+template <typename T>
+__device__ __forceinline__ T jmin(T a, T b) {
+  return (a != a || b != b) ? (a + b) : (a < b ? a : (b < a ? b : (signbit(a) ? a : b)));
+}
+
+#define AG_DEF_F(NAME, EXPR)                                          \
+  template <typename T>                                               \
+  struct NAME {                                                       \
+    static __device__ __forceinline__ T apply(const T* in) {          \
+      const T a = in[0], b = in[1];                                   \
+      (void)a; (void)b;                                               \
+      return EXPR;                                                    \
+    }                                                                 \
+  };
+AG_DEF_F(FAdd, a + b)
+AG_DEF_F(FSub, a - b)
+AG_DEF_F(FMul, a* b)
+AG_DEF_F(FDiv, a / b)
+AG_DEF_F(FMax, jmax(a, b))
+AG_DEF_F(FMin, jmin(a, b))
+AG_DEF_F(FPow, pow(a, b))
+AG_DEF_F(FEq, (a == b ? T(1) : T(0)))
+AG_DEF_F(FLt, (a < b ? T(1) : T(0)))
+AG_DEF_F(FLe, (a <= b ? T(1) : T(0)))
+AG_DEF_F(FGt, (a > b ? T(1) : T(0)))
+AG_DEF_F(FGe, (a >= b ? T(1) : T(0)))
+AG_DEF_F(FAtan2, atan2(a, b))
+AG_DEF_F(FHypot, hypot(a, b))
+
+// ternary gradient maps: in[0] = dy, in[1] = p, in[2] = q
+#define AG_DEF_F3(NAME, EXPR)                                         \
+  template <typename T>                                               \
+  struct NAME {                                                       \
+    static __device__ __forceinline__ T apply(const T* in) {          \
+      const T dy = in[0], p = in[1], q = in[2];                       \
+      return EXPR;                                                    \
+    }                                                                 \
+  };
+AG_DEF_F3(GDiv2, -dy* p / (q * q))               // ./ arg2: -dy.*x1./abs2.(x2)   base.jl:33  (p=x1,q=x2)
+AG_DEF_F3(GEqMask, dy*(p == q ? T(1) : T(0)))    // max/min: dy.*(y.==xi)         math.jl:54-55 (p=y,q=xi)
+AG_DEF_F3(GPow1, dy* q* pow(p, q - T(1)))        // .^ arg1: dy.*x2.*x1.^(x2-1)   base.jl:49  (p=x1,q=x2)
+AG_DEF_F3(GPow2, dy* p* log(q))                  // .^ arg2: dy.*y.*log.(x1)      base.jl:45  (p=y,q=x1)
+AG_DEF_F3(GAtan1, dy* q / (p * p + q * q))       // atan arg1                     math.jl:24  (p=x1,q=x2)
+AG_DEF_F3(GAtan2, dy*(-p) / (p * p + q * q))     // atan arg2
+AG_DEF_F3(GHypot, dy* p / q)                     // hypot: dy.*(xi./y)            math.jl:48  (p=xi,q=y)
+
+template <typename T, int NIN, typename F>
+static ag_status launch_map(MapArgs<NIN>& a) {
+  Context& c = ctx();
+  constexpr int N = Pack<T>::N;
+  // vectorise along dim0 when every N-run stays inside dim0 and every operand is either
+  // unit-stride + aligned, broadcast, or immediate
+  bool vec = (a.shape[0] % N == 0) && aligned16(a.out);
+  for (int k = 0; k < NIN; ++k) {
+    Opnd& o = a.in[k];
+    if (!o.p) {
+      o.mode = 0;
+      continue;
+    }
+    if (o.s[0] == 0) {
+      o.mode = 2;
+    } else if (o.s[0] == 1) {
+      o.mode = 1;
+      bool ok = aligned16(o.p);
+      for (int d = 1; d < a.nd; ++d) ok = ok && (o.s[d] % N == 0);
+      if (!ok) o.mode = 3;
+    } else {
+      o.mode = 3;
+    }
+  }
+  a.big = a.n >= ((int64_t)1 << 31);
+  if (vec) {
+    int64_t blocks = cdiv(a.n, (int64_t)kThreads * kUnroll * N);
+    k_map<T, NIN, F, true><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
+  } else {
+    for (int k = 0; k < NIN; ++k)
+      if (a.in[k].mode == 1) a.in[k].mode = 3;
+    int64_t blocks = cdiv(a.n, (int64_t)kThreads * kUnroll);
+    k_map<T, NIN, F, false><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
+  }
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+static ag_status fill_shape(int32_t ndims, const int64_t* shape, int64_t* out_shape, int64_t* n) {
+  AG_CHECK(ndims >= 1 && ndims <= 4 && shape, AG_EUNSUPPORTED,
+           "broadcast map: ndims=%d (collapse to <=4 dims on the host)", ndims);
+  int64_t total = 1;
+  for (int d = 0; d < 4; ++d) {
+    out_shape[d] = d < ndims ? shape[d] : 1;
+    AG_CHECK(out_shape[d] >= 0, AG_EINVAL, "broadcast map: negative extent");
+    total *= out_shape[d];
+  }
+  *n = total;
+  return AG_OK;
+}
+
+static void set_opnd(Opnd& o, const void* p, double imm, const int64_t* strides, int nd) {
+  o.p = p;
+  o.imm = imm;
+  for (int d = 0; d < 4; ++d) o.s[d] = (p && strides && d < nd) ? strides[d] : 0;
+  o.mode = 0;
+}
+
+template <typename T>
+static ag_status binary_dispatch(int32_t op, MapArgs<2>& a) {
+  switch (op) {
+    case AG_B_ADD: return launch_map<T, 2, FAdd<T>>(a);
+    case AG_B_SUB: return launch_map<T, 2, FSub<T>>(a);
+    case AG_B_MUL: return launch_map<T, 2, FMul<T>>(a);
+    case AG_B_DIV: return launch_map<T, 2, FDiv<T>>(a);
+    case AG_B_MAX: return launch_map<T, 2, FMax<T>>(a);
+    case AG_B_MIN: return launch_map<T, 2, FMin<T>>(a);
+    case AG_B_POW: return launch_map<T, 2, FPow<T>>(a);
+    case AG_B_EQ: return launch_map<T, 2, FEq<T>>(a);
+    case AG_B_LT: return launch_map<T, 2, FLt<T>>(a);
+    case AG_B_LE: return launch_map<T, 2, FLe<T>>(a);
+    case AG_B_GT: return launch_map<T, 2, FGt<T>>(a);
+    case AG_B_GE: return launch_map<T, 2, FGe<T>>(a);
+    case AG_B_ATAN2: return launch_map<T, 2, FAtan2<T>>(a);
+    case AG_B_HYPOT: return launch_map<T, 2, FHypot<T>>(a);
+  }
+  set_error("ag_binary_fwd: unknown op %d", op);
+  return AG_EUNSUPPORTED;
+}
+
+template <typename T>
+static ag_status ternary_dispatch(int which, MapArgs<3>& a) {
+  switch (which) {
+    case 0: return launch_map<T, 3, GDiv2<T>>(a);
+    case 1: return launch_map<T, 3, GEqMask<T>>(a);
+    case 2: return launch_map<T, 3, GPow1<T>>(a);
+    case 3: return launch_map<T, 3, GPow2<T>>(a);
+    case 4: return launch_map<T, 3, GAtan1<T>>(a);
+    case 5: return launch_map<T, 3, GAtan2<T>>(a);
+    case 6: return launch_map<T, 3, GHypot<T>>(a);
+  }
+  return AG_EUNSUPPORTED;
+}
+
+}  // namespace agb
+
+using namespace agb;
+
+extern "C" {
+
+ag_status ag_unary_fwd(int32_t op, int32_t dtype, const void* x, void* y, int64_t n) {
+  AG_REQUIRE_INIT();
+  if (n == 0) return AG_OK;
+  AG_CHECK(x && y && n > 0, AG_EINVAL, "ag_unary_fwd: bad arguments");
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_unary_fwd: dtype %d", dtype);
+#define X(OP)                                                                  \
+  case OP:                                                                     \
+    return dtype == AG_F32 ? launch_unary_fwd<OP, float>(x, y, n)              \
+                           : launch_unary_fwd<OP, double>(x, y, n);
+  switch (op) { AG_FOR_UNARY(X) }
+#undef X
+  set_error("ag_unary_fwd: unknown op %d", op);
+  return AG_EUNSUPPORTED;
+}
+
+ag_status ag_unary_bwd(int32_t op, int32_t dtype, const void* dy, int32_t dy_mode, double dy_scalar,
+                       const void* x, const void* y, void* dx, int64_t n) {
+  AG_REQUIRE_INIT();
+  if (n == 0) return AG_OK;
+  AG_CHECK(dx && n > 0, AG_EINVAL, "ag_unary_bwd: bad arguments");
+  AG_CHECK(dy_mode >= 0 && dy_mode <= 2, AG_EINVAL, "ag_unary_bwd: dy_mode %d", dy_mode);
+  AG_CHECK(dy_mode == 2 || dy, AG_EINVAL, "ag_unary_bwd: dy is null");
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_unary_bwd: dtype %d", dtype);
+#define X(OP)                                                                                  \
+  case OP:                                                                                     \
+    return dtype == AG_F32 ? launch_unary_bwd<OP, float>(dy, dy_mode, dy_scalar, x, y, dx, n)  \
+                           : launch_unary_bwd<OP, double>(dy, dy_mode, dy_scalar, x, y, dx, n);
+  switch (op) { AG_FOR_UNARY(X) }
+#undef X
+  set_error("ag_unary_bwd: unknown op %d", op);
+  return AG_EUNSUPPORTED;
+}
+
+ag_status ag_binary_fwd(int32_t op, int32_t dtype, const void* a, double a_scalar,
+                        const int64_t* a_strides, const void* b, double b_scalar,
+                        const int64_t* b_strides, void* y, int32_t ndims, const int64_t* shape) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_binary_fwd: dtype %d", dtype);
+  MapArgs<2> m;
+  ag_status s = fill_shape(ndims, shape, m.shape, &m.n);
+  if (s != AG_OK) return s;
+  if (m.n == 0) return AG_OK;
+  AG_CHECK(y, AG_EINVAL, "ag_binary_fwd: null output");
+  AG_CHECK((!a || a_strides) && (!b || b_strides), AG_EINVAL, "ag_binary_fwd: missing strides");
+  m.nd = ndims;
+  m.out = y;
+  set_opnd(m.in[0], a, a_scalar, a_strides, ndims);
+  set_opnd(m.in[1], b, b_scalar, b_strides, ndims);
+  return dtype == AG_F32 ? binary_dispatch<float>(op, m) : binary_dispatch<double>(op, m);
+}
+
+ag_status ag_binary_bwd(int32_t op, int32_t argno, int32_t dtype, const void* dy,
+                        const int64_t* dy_strides, const void* x1, double x1_scalar,
+                        const int64_t* x1_strides, const void* x2, double x2_scalar,
+                        const int64_t* x2_strides, const void* y, const int64_t* y_strides,
+                        void* dx, int32_t ndims, const int64_t* shape) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_binary_bwd: dtype %d", dtype);
+  AG_CHECK(argno == 1 || argno == 2, AG_EINVAL, "ag_binary_bwd: argno %d", argno);
+  AG_CHECK(dy && dy_strides, AG_EINVAL, "ag_binary_bwd: dy must be a device array");
+  AG_CHECK((!x1 || x1_strides) && (!x2 || x2_strides) && (!y || y_strides), AG_EINVAL,
+           "ag_binary_bwd: missing strides");
+  int64_t shp[4], n;
+  ag_status s = fill_shape(ndims, shape, shp, &n);
+  if (s != AG_OK) return s;
+  if (n == 0) return AG_OK;
+  AG_CHECK(dx, AG_EINVAL, "ag_binary_bwd: null output");
+
+  // two-operand gradients reuse the forward map: dx = dy (op') other
+  int bop = -1;
+  const void* o_p = nullptr;
+  double o_imm = 0;
+  const int64_t* o_s = nullptr;
+  switch (op) {
+    case AG_B_ADD: bop = AG_B_MUL; o_imm = 1.0; break;                       // base.jl:21
+    case AG_B_SUB: bop = AG_B_MUL; o_imm = argno == 1 ? 1.0 : -1.0; break;   // base.jl:23
+    case AG_B_MUL:                                                           // base.jl:27
+      bop = AG_B_MUL;
+      if (argno == 1) { o_p = x2; o_imm = x2_scalar; o_s = x2_strides; }
+      else { o_p = x1; o_imm = x1_scalar; o_s = x1_strides; }
+      break;
+    case AG_B_DIV:                                                           // base.jl:33
+      if (argno == 1) { bop = AG_B_DIV; o_p = x2; o_imm = x2_scalar; o_s = x2_strides; }
+      break;
+    default: break;
+  }
+  if (bop >= 0) {
+    MapArgs<2> m;
+    for (int d = 0; d < 4; ++d) m.shape[d] = shp[d];
+    m.n = n;
+    m.nd = ndims;
+    m.out = dx;
+    set_opnd(m.in[0], dy, 0, dy_strides, ndims);
+    set_opnd(m.in[1], o_p, o_imm, o_s, ndims);
+    return dtype == AG_F32 ? binary_dispatch<float>(bop, m) : binary_dispatch<double>(bop, m);
+  }
+
+  MapArgs<3> m;
+  for (int d = 0; d < 4; ++d) m.shape[d] = shp[d];
+  m.n = n;
+  m.nd = ndims;
+  m.out = dx;
+  set_opnd(m.in[0], dy, 0, dy_strides, ndims);
+  int which = -1;
+  const void* xi = argno == 1 ? x1 : x2;
+  double xi_imm = argno == 1 ? x1_scalar : x2_scalar;
+  const int64_t* xi_s = argno == 1 ? x1_strides : x2_strides;
+  switch (op) {
+    case AG_B_DIV:  // arg2
+      which = 0;
+      set_opnd(m.in[1], x1, x1_scalar, x1_strides, ndims);
+      set_opnd(m.in[2], x2, x2_scalar, x2_strides, ndims);
+      break;
+    case AG_B_MAX:
+    case AG_B_MIN:
+      AG_CHECK(y, AG_EINVAL, "ag_binary_bwd: max/min need y");
+      which = 1;
+      set_opnd(m.in[1], y, 0, y_strides, ndims);
+      set_opnd(m.in[2], xi, xi_imm, xi_s, ndims);
+      break;
+    case AG_B_POW:
+      if (argno == 1) {
+        which = 2;
+        set_opnd(m.in[1], x1, x1_scalar, x1_strides, ndims);
+        set_opnd(m.in[2], x2, x2_scalar, x2_strides, ndims);
+      } else {
+        AG_CHECK(y, AG_EINVAL, "ag_binary_bwd: pow arg2 needs y");
+        which = 3;
+        set_opnd(m.in[1], y, 0, y_strides, ndims);
+        set_opnd(m.in[2], x1, x1_scalar, x1_strides, ndims);
+      }
+      break;
+    case AG_B_ATAN2:
+      which = argno == 1 ? 4 : 5;
+      set_opnd(m.in[1], x1, x1_scalar, x1_strides, ndims);
+      set_opnd(m.in[2], x2, x2_scalar, x2_strides, ndims);
+      break;
+    case AG_B_HYPOT:
+      AG_CHECK(y, AG_EINVAL, "ag_binary_bwd: hypot needs y");
+      which = 6;
+      set_opnd(m.in[1], xi, xi_imm, xi_s, ndims);
+      set_opnd(m.in[2], y, 0, y_strides, ndims);
+      break;
+    default:
+      set_error("ag_binary_bwd: op %d has no gradient (zerograd)", op);
+      return AG_EUNSUPPORTED;
+  }
+  return dtype == AG_F32 ? ternary_dispatch<float>(which, m) : ternary_dispatch<double>(which, m);
+}
+
+ag_status ag_add(int32_t dtype, const void* a, const void* b, void* out, int64_t n) {
+  int64_t st = 1, shape = n;
+  return ag_binary_fwd(AG_B_ADD, dtype, a, 0, &st, b, 0, &st, out, 1, &shape);
+}
+
+}  // extern "C"

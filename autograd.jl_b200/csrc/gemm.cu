@@ -1,0 +1,225 @@
+// gemm.cu -- C = alpha*op(A)*op(B) + beta*C, column-major BLAS convention.
+//
+// Reference: forward `*` (src/core.jl:66 -> LinearAlgebra/OpenBLAS) and the rules
+// `@primitive1 *(x1,x2),dy (dy*x2') (x1'*dy)` (src/base.jl:26; lazy adjoint src/linearalgebra.jl:16),
+// i.e. NN forward, NT for dA and TN for dB.
+//
+// Engines: "tcgen05" (gemm_tc.cu: TMA + tcgen05.mma kind::tf32, 3xTF32 error compensation, fp32
+// TMEM accumulators, split-K) for qualifying Float32 shapes; "ffma"/"dfma" (this file): a
+// shared-memory tiled CUDA-core kernel with deterministic split-K for everything else (Float64
+// has no tcgen05 kind).
+#include "common.cuh"
+
+namespace agb {
+
+constexpr int BM = 64, BN = 64, BK = 16, GT = 256, PADM = 4;
+
+// Partial product over k in [k0,k1) of one 64x64 tile.  SPLIT: write raw partial sums to `ws`
+// ([split][N][M] column-major tiles of the full MxN), else apply alpha/beta and write C.
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(GT)
+    k_gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t K, T alpha,
+                const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb, T beta,
+                T* __restrict__ C, int64_t ldc, int64_t kchunk, T* __restrict__ ws) {
+  __shared__ T As[BK][BM + PADM];
+  __shared__ T Bs[BK][BN + PADM];
+  const int t = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * kchunk;
+  int64_t kend = kbeg + kchunk;
+  if (kend > K) kend = K;
+  const int tx = t % 16, ty = t / 16;  // thread computes rows tx*4.., cols ty*4..
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+
+  for (int64_t kk = kbeg; kk < kend; kk += BK) {
+    // ---- stage A tile (BM x BK) as As[k][m]
+    if (!transA) {  // A[m + k*lda]: m contiguous
+      const int m = t % BM, kq = t / BM;  // kq in 0..3
+#pragma unroll
+      for (int j = 0; j < BK / 4; ++j) {
+        int k = kq + 4 * j;
+        int64_t gm = m0 + m, gk = kk + k;
+        As[k][m] = (gm < M && gk < kend) ? A[gm + gk * lda] : T(0);
+      }
+    } else {  // A[k + m*lda]: k contiguous
+      const int k = t % BK, mq = t / BK;  // mq in 0..15
+#pragma unroll
+      for (int j = 0; j < BM / 16; ++j) {
+        int m = mq + 16 * j;
+        int64_t gm = m0 + m, gk = kk + k;
+        As[k][m] = (gm < M && gk < kend) ? A[gk + gm * lda] : T(0);
+      }
+    }
+    // ---- stage B tile (BK x BN) as Bs[k][n]
+    if (!transB) {  // B[k + n*ldb]: k contiguous
+      const int k = t % BK, nq = t / BK;
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        int n = nq + 16 * j;
+        int64_t gn = n0 + n, gk = kk + k;
+        Bs[k][n] = (gn < N && gk < kend) ? B[gk + gn * ldb] : T(0);
+      }
+    } else {  // B[n + k*ldb]: n contiguous
+      const int n = t % BN, kq = t / BN;
+#pragma unroll
+      for (int j = 0; j < BK / 4; ++j) {
+        int k = kq + 4 * j;
+        int64_t gn = n0 + n, gk = kk + k;
+        Bs[k][n] = (gn < N && gk < kend) ? B[gn + gk * ldb] : T(0);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][tx * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][ty * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int64_t gn = n0 + ty * 4 + j;
+    if (gn >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int64_t gm = m0 + tx * 4 + i;
+      if (gm >= M) continue;
+      if (SPLIT) {
+        ws[((int64_t)blockIdx.z * N + gn) * M + gm] = acc[i][j];
+      } else {
+        T* c = C + gm + gn * ldc;
+        *c = beta == T(0) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*c);
+      }
+    }
+  }
+}
+
+// C = alpha * sum_s ws[s] + beta*C, fixed summation order (deterministic split-K)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_splitk_reduce(const T* __restrict__ ws, int splits, int64_t M, int64_t N, T alpha, T beta,
+                    T* __restrict__ C, int64_t ldc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  int64_t m = i % M, n = i / M;
+  double s = 0;
+  for (int k = 0; k < splits; ++k) s += (double)ws[(int64_t)k * M * N + i];
+  T* c = C + m + n * ldc;
+  *c = beta == T(0) ? (T)(alpha * s) : (T)(alpha * s + (double)beta * (double)(*c));
+}
+
+template <typename T>
+static ag_status gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                           const void* A, int64_t lda, const void* B, int64_t ldb, double beta,
+                           void* C, int64_t ldc) {
+  Context& c = ctx();
+  int64_t tm = cdiv(M, BM), tn = cdiv(N, BN);
+  AG_CHECK(tn <= 65535, AG_EUNSUPPORTED, "ag_gemm: N=%lld too large for the CUDA-core engine",
+           (long long)N);
+  int64_t tiles = tm * tn;
+  int64_t splits = 1;
+  if (tiles < 2 * c.num_sms && K >= 512) {
+    splits = cdiv(2 * (int64_t)c.num_sms, tiles);
+    int64_t maxs = cdiv(K, 256);
+    if (splits > maxs) splits = maxs;
+    if (splits > 512) splits = 512;
+  }
+  int64_t kchunk = BK;
+  if (K > 0) {
+    kchunk = cdiv(cdiv(K, splits), BK) * BK;
+    splits = cdiv(K, kchunk);
+  } else {
+    splits = 1;
+  }
+  dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
+  if (splits == 1) {
+    k_gemm_simt<T, false><<<grid, GT, 0, c.stream>>>(transA, transB, M, N, K, (T)alpha, (const T*)A,
+                                                     lda, (const T*)B, ldb, (T)beta, (T*)C, ldc,
+                                                     kchunk, nullptr);
+    AG_LAUNCHED();
+    return AG_OK;
+  }
+  T* ws = (T*)workspace((size_t)(splits * M * N) * sizeof(T));
+  if (!ws) return AG_ENOMEM;
+  k_gemm_simt<T, true><<<grid, GT, 0, c.stream>>>(transA, transB, M, N, K, (T)alpha, (const T*)A, lda,
+                                                  (const T*)B, ldb, (T)beta, (T*)C, ldc, kchunk, ws);
+  AG_LAUNCHED();
+  k_splitk_reduce<T><<<(unsigned)cdiv(M * N, 256), 256, 0, c.stream>>>(ws, (int)splits, M, N, (T)alpha,
+                                                                       (T)beta, (T*)C, ldc);
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+// gemm_tc.cu
+bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A,
+                       int64_t lda, const void* B, int64_t ldb, const void* C, int64_t ldc);
+ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                  const void* A, int64_t lda, const void* B, int64_t ldb, double beta, void* C,
+                  int64_t ldc);
+
+static int g_engine = 0;
+static const char* g_last_engine = "none";
+
+}  // namespace agb
+
+using namespace agb;
+
+extern "C" {
+
+ag_status ag_gemm_set_engine(int32_t engine) {
+  AG_CHECK(engine >= 0 && engine <= 2, AG_EINVAL, "ag_gemm_set_engine: %d", engine);
+  g_engine = engine;
+  return AG_OK;
+}
+
+ag_status ag_gemm_last_engine(char* buf, int64_t buflen) {
+  if (!buf || buflen <= 0) return AG_EINVAL;
+  strncpy(buf, g_last_engine, (size_t)buflen - 1);
+  buf[buflen - 1] = 0;
+  return AG_OK;
+}
+
+ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                  double alpha, const void* A, int64_t lda, const void* B, int64_t ldb, double beta,
+                  void* C, int64_t ldc) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_gemm: dtype %d", dtype);
+  AG_CHECK(M >= 0 && N >= 0 && K >= 0, AG_EINVAL, "ag_gemm: negative dimension");
+  AG_CHECK((transA == 0 || transA == 1) && (transB == 0 || transB == 1), AG_EINVAL,
+           "ag_gemm: trans flags must be 0 or 1");
+  if (M == 0 || N == 0) return AG_OK;
+  AG_CHECK(C && ldc >= M, AG_EINVAL, "ag_gemm: bad C/ldc (DimensionMismatch)");
+  if (K > 0) {
+    AG_CHECK(A && B, AG_EINVAL, "ag_gemm: null operand");
+    AG_CHECK(lda >= (transA ? K : M) && ldb >= (transB ? N : K), AG_EINVAL,
+             "ag_gemm: leading dimension too small (DimensionMismatch)");
+  }
+  if (dtype == AG_F64) {
+    g_last_engine = "dfma";
+    return gemm_simt<double>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  }
+  bool tc_ok = K > 0 && gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
+  if (g_engine == 2) {
+    AG_CHECK(tc_ok, AG_EUNSUPPORTED, "ag_gemm: shape does not qualify for the tcgen05 engine");
+  }
+  if (tc_ok && g_engine != 1) {
+    g_last_engine = "tcgen05";
+    return gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  }
+  g_last_engine = "ffma";
+  return gemm_simt<float>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+// reduce.cu -- sum reductions: sum(x), sum(abs2,x), sum(x;dims) and the reductions inside
+// unbroadcast (src/unbroadcast.jl:9-26; rules src/base.jl:245-247).
+//
+// All reductions are deterministic (fixed tree, no float atomics): phase 1 writes per-block partials
+// to the workspace, phase 2 reduces the partials.  Per-thread accumulation is in T with several
+// independent accumulators (pairwise-like error growth); block/partial combination is in double.
+// HBM-bound: algorithmic bytes N*s + n_out*s.
+#include "common.cuh"
+
+namespace agb {
+
+constexpr int kRT = 256;  // threads per reduction block
+
+template <int MAP, typename T>
+__device__ __forceinline__ T premap(T v) {
+  if (MAP == AG_R_ABS2) return v * v;
+  if (MAP == AG_R_ABS) return fabs(v);
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum of `v` over the block (kRT threads); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sm[kRT / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < kRT / 32 ? sm[threadIdx.x] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// ---- contiguous segments: out[o] = sum_r map(x[r + red*o]) -----------------------------------
+// grid (outer, nchunks); chunk c of segment o covers [c*chunk, min(red,(c+1)*chunk))
+template <int MAP, typename T, typename TO>
+__global__ void __launch_bounds__(kRT)
+    k_seg_block(const T* __restrict__ x, int64_t red, int64_t chunk, TO* __restrict__ out) {
+  const int64_t o = blockIdx.x, c = blockIdx.y;
+  const T* __restrict__ p = x + o * red;
+  int64_t lo = c * chunk, hi = lo + chunk;
+  if (hi > red) hi = red;
+  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  // 128-bit loads over the aligned middle of [lo,hi)
+  constexpr int N = 16 / sizeof(T);
+  int64_t head = lo;
+  while (head < hi && (((uintptr_t)(p + head)) & 15)) ++head;
+  if (threadIdx.x == 0)
+    for (int64_t i = lo; i < head; ++i) a0 += premap<MAP>(p[i]);
+  int64_t nvec = (hi - head) / N;
+  const T* __restrict__ pv = p + head;
+  for (int64_t v = threadIdx.x; v < nvec; v += 2 * kRT) {
+    if constexpr (N == 4) {
+      float4 q = *reinterpret_cast<const float4*>(pv + v * N);
+      a0 += premap<MAP>((T)q.x); a1 += premap<MAP>((T)q.y);
+      a2 += premap<MAP>((T)q.z); a3 += premap<MAP>((T)q.w);
+      if (v + kRT < nvec) {
+        float4 q2 = *reinterpret_cast<const float4*>(pv + (v + kRT) * N);
+        a0 += premap<MAP>((T)q2.x); a1 += premap<MAP>((T)q2.y);
+        a2 += premap<MAP>((T)q2.z); a3 += premap<MAP>((T)q2.w);
+      }
+    } else {
+      double2 q = *reinterpret_cast<const double2*>(pv + v * N);
+      a0 += premap<MAP>((T)q.x); a1 += premap<MAP>((T)q.y);
+      if (v + kRT < nvec) {
+        double2 q2 = *reinterpret_cast<const double2*>(pv + (v + kRT) * N);
+        a2 += premap<MAP>((T)q2.x); a3 += premap<MAP>((T)q2.y);
+      }
+    }
+  }
+  if (threadIdx.x == 0)
+    for (int64_t i = head + nvec * N; i < hi; ++i) a1 += premap<MAP>(p[i]);
+  double s = block_sum(((double)a0 + (double)a1) + ((double)a2 + (double)a3));
+  if (threadIdx.x == 0) out[o * gridDim.y + c] = (TO)s;
+}
+
+// short segments: one thread per segment (red <= 64)
+template <int MAP, typename T, typename TI>
+__global__ void __launch_bounds__(kRT)
+    k_seg_thread(const TI* __restrict__ x, int64_t red, int64_t outer, T* __restrict__ out) {
+  int64_t o = (int64_t)blockIdx.x * kRT + threadIdx.x;
+  if (o >= outer) return;
+  const TI* __restrict__ p = x + o * red;
+  double s = 0;
+  for (int64_t r = 0; r < red; ++r) s += (double)premap<MAP>(p[r]);
+  out[o] = (T)s;
+}
+
+// ---- strided: out[i,o] = sum_r map(x[i + inner*(r + red*o)]), inner <= kRT ---------------------
+// The (inner x red) slab of one `o` is contiguous: thread t walks it with a stride S that is a
+// multiple of inner, so it always sees the same i and every warp load is fully coalesced.
+// grid (outer, nchunks); partial/out layout [o][c][i].
+template <int MAP, typename T, typename TI, typename TO>
+__global__ void __launch_bounds__(kRT)
+    k_strided_small(const TI* __restrict__ x, int64_t inner, int64_t red, int64_t rows_per_chunk,
+                    TO* __restrict__ out) {
+  __shared__ double sm[kRT];
+  const int64_t o = blockIdx.x, c = blockIdx.y;
+  const int S = (kRT / (int)inner) * (int)inner;
+  const int t = threadIdx.x;
+  int64_t r0 = c * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > red) r1 = red;
+  const TI* __restrict__ p = x + o * inner * red;
+  const int64_t lo = r0 * inner, hi = r1 * inner;
+  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (t < S) {
+    int64_t q = lo + t;
+    for (; q + 3 * (int64_t)S < hi; q += 4 * (int64_t)S) {
+      T v0 = (T)p[q], v1 = (T)p[q + S], v2 = (T)p[q + 2 * (int64_t)S], v3 = (T)p[q + 3 * (int64_t)S];
+      a0 += premap<MAP>(v0); a1 += premap<MAP>(v1); a2 += premap<MAP>(v2); a3 += premap<MAP>(v3);
+    }
+    for (; q < hi; q += S) a0 += premap<MAP>((T)p[q]);
+  }
+  sm[t] = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+  __syncthreads();
+  if (t < inner) {
+    double s = 0;
+    for (int j = t; j < S; j += (int)inner) s += sm[j];
+    out[(o * gridDim.y + c) * inner + t] = (TO)s;
+  }
+}
+
+// inner > kRT: thread per i, loop over the chunk's rows.  grid (outer, nchunks, itiles)
+template <int MAP, typename T, typename TI, typename TO>
+__global__ void __launch_bounds__(kRT)
+    k_strided_large(const TI* __restrict__ x, int64_t inner, int64_t red, int64_t rows_per_chunk,
+                    TO* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.z * kRT + threadIdx.x;
+  const int64_t c = blockIdx.y, o = blockIdx.x;
+  if (i >= inner) return;
+  int64_t r0 = c * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > red) r1 = red;
+  const TI* __restrict__ p = x + o * inner * red + i;
+  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    T v0 = (T)p[r * inner], v1 = (T)p[(r + 1) * inner], v2 = (T)p[(r + 2) * inner],
+      v3 = (T)p[(r + 3) * inner];
+    a0 += premap<MAP>(v0); a1 += premap<MAP>(v1); a2 += premap<MAP>(v2); a3 += premap<MAP>(v3);
+  }
+  for (; r < r1; ++r) a0 += premap<MAP>((T)p[r * inner]);
+  double s = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+  out[(o * gridDim.y + c) * inner + i] = (TO)s;
+}
+
+// Partials are kept in double in the workspace so the second phase loses nothing.
+template <int MAP, typename T>
+static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t outer, T* out) {
+  Context& c = ctx();
+  const int64_t target_blocks = (int64_t)c.num_sms * 8;
+  if (inner == 1) {
+    if (red <= 64) {
+      k_seg_thread<MAP, T, T><<<(unsigned)cdiv(outer, kRT), kRT, 0, c.stream>>>(x, red, outer, out);
+      AG_LAUNCHED();
+      return AG_OK;
+    }
+    int64_t nchunks = 1;
+    if (outer < target_blocks) {
+      nchunks = cdiv(target_blocks, outer);
+      int64_t maxc = cdiv(red, (int64_t)kRT * 16);  // >= 4096 elements per block
+      if (nchunks > maxc) nchunks = maxc;
+      if (nchunks > 1024) nchunks = 1024;
+      if (nchunks < 1) nchunks = 1;
+    }
+    int64_t chunk = cdiv(red, nchunks);
+    chunk = cdiv(chunk, 4) * 4;
+    nchunks = cdiv(red, chunk);
+    dim3 grid((unsigned)outer, (unsigned)nchunks);
+    if (nchunks == 1) {
+      k_seg_block<MAP, T, T><<<grid, kRT, 0, c.stream>>>(x, red, chunk, out);
+      AG_LAUNCHED();
+      return AG_OK;
+    }
+    double* part = (double*)workspace((size_t)(nchunks * outer) * sizeof(double));
+    if (!part) return AG_ENOMEM;
+    k_seg_block<MAP, T, double><<<grid, kRT, 0, c.stream>>>(x, red, chunk, part);
+    AG_LAUNCHED();
+    if (nchunks <= 64) {
+      k_seg_thread<AG_R_ID, T, double><<<(unsigned)cdiv(outer, kRT), kRT, 0, c.stream>>>(
+          part, nchunks, outer, out);
+    } else {
+      k_seg_block<AG_R_ID, double, T><<<dim3((unsigned)outer, 1), kRT, 0, c.stream>>>(
+          part, nchunks, nchunks, out);
+    }
+    AG_LAUNCHED();
+    return AG_OK;
+  }
+
+  // strided
+  const bool small = inner <= kRT;
+  const int64_t itiles = small ? 1 : cdiv(inner, kRT);
+  AG_CHECK(itiles <= 65535, AG_EUNSUPPORTED, "ag_sum_dim: inner extent %lld too large",
+           (long long)inner);
+  const int64_t rows_per_iter = small ? (kRT / inner) : 1;
+  int64_t nchunks = 1;
+  if (outer * itiles < target_blocks && red > 256) {
+    nchunks = cdiv(target_blocks, outer * itiles);
+    int64_t maxc = cdiv(red, rows_per_iter * 16);
+    if (nchunks > maxc) nchunks = maxc;
+    if (nchunks > 256) nchunks = 256;
+    if (nchunks < 1) nchunks = 1;
+  }
+  int64_t rows = cdiv(red, nchunks);
+  nchunks = cdiv(red, rows);
+  if (nchunks == 1) {
+    if (small)
+      k_strided_small<MAP, T, T, T><<<dim3((unsigned)outer, 1), kRT, 0, c.stream>>>(x, inner, red, rows, out);
+    else
+      k_strided_large<MAP, T, T, T><<<dim3((unsigned)outer, 1, (unsigned)itiles), kRT, 0, c.stream>>>(
+          x, inner, red, rows, out);
+    AG_LAUNCHED();
+    return AG_OK;
+  }
+  double* part = (double*)workspace((size_t)(nchunks * outer * inner) * sizeof(double));
+  if (!part) return AG_ENOMEM;
+  if (small)
+    k_strided_small<MAP, T, T, double><<<dim3((unsigned)outer, (unsigned)nchunks), kRT, 0, c.stream>>>(
+        x, inner, red, rows, part);
+  else
+    k_strided_large<MAP, T, T, double><<<dim3((unsigned)outer, (unsigned)nchunks, (unsigned)itiles), kRT, 0,
+                                          c.stream>>>(x, inner, red, rows, part);
+  AG_LAUNCHED();
+  // phase 2: partials (inner, nchunks, outer) -> out (inner, outer); nchunks <= 256 so one chunk
+  if (small)
+    k_strided_small<AG_R_ID, double, double, T><<<dim3((unsigned)outer, 1), kRT, 0, c.stream>>>(
+        part, inner, nchunks, nchunks, out);
+  else
+    k_strided_large<AG_R_ID, double, double, T><<<dim3((unsigned)outer, 1, (unsigned)itiles), kRT, 0,
+                                                  c.stream>>>(part, inner, nchunks, nchunks, out);
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+template <typename T>
+static ag_status sum_dim_map(int32_t map, const void* x, int64_t inner, int64_t red, int64_t outer,
+                             void* out) {
+  switch (map) {
+    case AG_R_ID: return sum_dim_impl<AG_R_ID, T>((const T*)x, inner, red, outer, (T*)out);
+    case AG_R_ABS2: return sum_dim_impl<AG_R_ABS2, T>((const T*)x, inner, red, outer, (T*)out);
+    case AG_R_ABS: return sum_dim_impl<AG_R_ABS, T>((const T*)x, inner, red, outer, (T*)out);
+  }
+  set_error("ag_sum: unknown map %d", map);
+  return AG_EUNSUPPORTED;
+}
+
+}  // namespace agb
+
+using namespace agb;
+
+extern "C" {
+
+ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, int64_t red,
+                     int64_t outer, void* out) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_sum_dim: dtype %d", dtype);
+  AG_CHECK(inner >= 0 && red >= 0 && outer >= 0, AG_EINVAL, "ag_sum_dim: negative extent");
+  if (inner * outer == 0) return AG_OK;
+  AG_CHECK(out, AG_EINVAL, "ag_sum_dim: null output");
+  if (red == 0) return ag_fill(out, inner * outer, dtype, 0.0);
+  AG_CHECK(x, AG_EINVAL, "ag_sum_dim: null input");
+  return dtype == AG_F32 ? sum_dim_map<float>(map, x, inner, red, outer, out)
+                         : sum_dim_map<double>(map, x, inner, red, outer, out);
+}
+
+ag_status ag_sum_all(int32_t map, int32_t dtype, const void* x, int64_t n, void* out_scalar) {
+  return ag_sum_dim(map, dtype, x, 1, n, 1, out_scalar);
+}
+
+}  // extern "C"

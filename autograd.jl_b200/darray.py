@@ -1,0 +1,565 @@
+"""DArray -- the device array type that sits inside Param/Result, and the raw (unboxed) array
+operations the tape runtime dispatches to.
+
+In the reference this layer is Julia Base broadcast / mapreduce / LinearAlgebra on `Array`
+(SURVEY.md layer L0; src/core.jl:66 calls `f(novalue...)` on the unboxed values).  Here every
+operation is one call into libagb200.so.  Layout is COLUMN-MAJOR with Julia's broadcasting rule
+(align leading dimensions, pad trailing 1s).  A 0-dimensional DArray is a device scalar: `sum(x)`
+stays on the device so a whole step can be enqueued (and graph-captured) without a host sync.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import lib, check
+
+_DT = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64}
+
+# op ids (include/agb200.h)
+U = dict(identity=0, neg=1, abs=2, abs2=3, exp=4, log=5, tanh=6, sigm=7, sqrt=8, sin=9, cos=10, tan=11,
+         sinh=12, cosh=13, asin=14, acos=15, atan=16, asinh=17, acosh=18, atanh=19, exp2=20, exp10=21,
+         expm1=22, log2=23, log10=24, log1p=25, cbrt=26, sign=27, relu=28, one=29)
+B = dict(add=0, sub=1, mul=2, div=3, max=4, min=5, pow=6, eq=7, lt=8, le=9, gt=10, ge=11, atan2=12, hypot=13)
+R = dict(id=0, abs2=1, abs=2)
+
+_initialised = [False]
+
+
+def init(device=0):
+    check(lib.ag_init(int(device)))
+    _initialised[0] = True
+
+
+def _require_init():
+    if not _initialised[0]:
+        init(0)
+
+
+def sync():
+    check(lib.ag_sync())
+
+
+def launch_count():
+    n = C.c_int64()
+    check(lib.ag_launch_count(C.byref(n)))
+    return n.value
+
+
+def device_info():
+    a = (C.c_int64 * 8)()
+    check(lib.ag_device_info(a))
+    k = ["device", "sms", "cc_major", "cc_minor", "total_bytes", "free_bytes", "pool_bytes", "live_bytes"]
+    return dict(zip(k, list(a)))
+
+
+class _Buffer:
+    """Owns one pool block; freed (stream-ordered, no sync) when the last view dies."""
+    __slots__ = ("ptr", "nbytes")
+
+    def __init__(self, nbytes):
+        _require_init()
+        p = C.c_void_p()
+        check(lib.ag_alloc(int(nbytes), C.byref(p)))
+        self.ptr = p.value or 0
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib.ag_free(C.c_void_p(self.ptr))
+                self.ptr = 0
+        except Exception:
+            pass
+
+
+def isnum(x):
+    return isinstance(x, (int, float, np.floating, np.integer)) and not isinstance(x, (bool, np.bool_))
+
+
+def _prod(s):
+    n = 1
+    for v in s:
+        n *= int(v)
+    return n
+
+
+class DArray:
+    """Dense column-major device array (Float32/Float64).  `tr=True` marks a lazy adjoint of a
+    2-d array (src/linearalgebra.jl:16): storage is that of the parent, `shape` is the logical
+    (transposed) shape, and only matmul / materialize understand it."""
+    __slots__ = ("buf", "ptr", "shape", "dtype", "tr", "__weakref__")
+    __array_priority__ = 2000
+
+    def __init__(self, buf, ptr, shape, dtype, tr=False):
+        self.buf, self.ptr, self.shape, self.dtype, self.tr = buf, ptr, tuple(int(s) for s in shape), np.dtype(dtype), tr
+
+    # ---- construction / transfer
+    @staticmethod
+    def empty(shape, dtype):
+        dtype = np.dtype(dtype)
+        if dtype not in _DT:
+            raise L.UnsupportedOnDevice("DArray eltype %s (Float32/Float64 only)" % dtype)
+        shape = tuple(int(s) for s in shape)
+        buf = _Buffer(max(_prod(shape), 1) * dtype.itemsize)
+        return DArray(buf, buf.ptr, shape, dtype)
+
+    @staticmethod
+    def from_numpy(a, dtype=None):
+        a = np.asarray(a, dtype=dtype)
+        if a.dtype not in _DT:
+            a = a.astype(np.float64)
+        out = DArray.empty(a.shape, a.dtype)
+        if a.size:
+            flat = np.ascontiguousarray(a.reshape(-1, order="F"))
+            check(lib.ag_copy_h2d(C.c_void_p(out.ptr), flat.ctypes.data_as(C.c_void_p), flat.nbytes))
+            sync()   # `flat` is pageable and about to be released
+        return out
+
+    def copy_from_host(self, host_ptr, nbytes):
+        """Async h2d from a pinned staging buffer (ag_host_alloc)."""
+        check(lib.ag_copy_h2d(C.c_void_p(self.ptr), C.c_void_p(host_ptr), int(nbytes)))
+
+    def to_numpy(self):
+        src = materialize(self)
+        out = np.empty(src.size, dtype=src.dtype)
+        if src.size:
+            check(lib.ag_copy_d2h(out.ctypes.data_as(C.c_void_p), C.c_void_p(src.ptr), out.nbytes))
+        if src.shape == ():
+            return out.reshape(())
+        return out.reshape(src.shape, order="F")
+
+    def item(self):
+        return self.to_numpy().reshape(-1)[0]
+
+    def __float__(self):
+        if self.size != 1:
+            raise TypeError("only size-1 DArrays convert to a Number")
+        return float(self.item())
+
+    # ---- metadata
+    @property
+    def size(self):
+        return _prod(self.shape)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
+
+    @property
+    def dt(self):
+        return _DT[self.dtype]
+
+    def __repr__(self):
+        return "DArray{%s}%s%s@0x%x" % (self.dtype.name, self.shape, "'" if self.tr else "", self.ptr)
+
+    def reshape(self, shape):
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        src = materialize(self)
+        if _prod(shape) != src.size:
+            raise L.DimensionMismatch("reshape %s -> %s" % (src.shape, shape))
+        return DArray(src.buf, src.ptr, shape, src.dtype)
+
+    # raw arithmetic sugar (the unboxed array also supports + - .* ./ like a Julia Array)
+    def __add__(self, o): return _ops().add(self, o)
+    def __radd__(self, o): return _ops().add(o, self)
+    def __sub__(self, o): return _ops().sub(self, o)
+    def __rsub__(self, o): return _ops().sub(o, self)
+    def __mul__(self, o): return _ops().mul(self, o)
+    def __rmul__(self, o): return _ops().mul(o, self)
+    def __truediv__(self, o): return _ops().div(self, o)
+    def __rtruediv__(self, o): return _ops().div(o, self)
+    def __pow__(self, o): return _ops().pow_(self, o)
+    def __neg__(self): return _ops().neg(self)
+    def __matmul__(self, o): return _ops().matmul(self, o)
+    def __rmatmul__(self, o): return _ops().matmul(o, self)
+    def __getitem__(self, i): return _ops().getindex(self, *(i if isinstance(i, tuple) else (i,)))
+
+    @property
+    def T(self): return _ops().adjoint(self)
+
+
+def _ops():
+    from . import rules
+    return rules
+
+
+def vptr(x):
+    return C.c_void_p(x.ptr if x is not None else None)
+
+
+def zeros(shape, dtype):
+    out = DArray.empty(shape, dtype)
+    if out.size:
+        check(lib.ag_fill(vptr(out), out.size, out.dt, 0.0))
+    return out
+
+
+def full_like_shape(shape, dtype, v):
+    out = DArray.empty(shape, dtype)
+    if out.size:
+        check(lib.ag_fill(vptr(out), out.size, out.dt, float(v)))
+    return out
+
+
+def materialize(x):
+    """Resolve a lazy adjoint into dense storage (permutedims)."""
+    if not x.tr:
+        return x
+    cols, rows = x.shape           # logical shape of the adjoint; storage is (rows x cols)^T = (cols', rows')
+    out = DArray.empty(x.shape, x.dtype)
+    # storage holds parent P of shape (rows_p, cols_p) = (x.shape[1], x.shape[0])
+    check(lib.ag_transpose(x.dt, vptr(x), x.shape[1], x.shape[0], vptr(out)))
+    return out
+
+
+def copy(x):
+    x = materialize(x)
+    out = DArray.empty(x.shape, x.dtype)
+    check(lib.ag_copy_d2d(vptr(out), vptr(x), x.nbytes))
+    return out
+
+
+# ---- elementwise ---------------------------------------------------------------------------------
+
+def unary_fwd(op, x):
+    x = materialize(x)
+    y = DArray.empty(x.shape, x.dtype)
+    check(lib.ag_unary_fwd(U[op], x.dt, vptr(x), vptr(y), x.size))
+    return y
+
+
+def unary_bwd(op, dy, x, y, shape=None, dtype=None):
+    """dx = dy .* g(x, y).  dy: DArray of the full shape, 0-dim DArray, or host Number."""
+    ref = x if x is not None else y
+    if ref is None:
+        ref = dy
+    shape = ref.shape if shape is None else shape
+    dtype = ref.dtype if dtype is None else dtype
+    dx = DArray.empty(shape, dtype)
+    n = dx.size
+    if isnum(dy):
+        mode, dyp, dys = 2, None, float(dy)
+    elif dy.size == 1 and n != 1:
+        mode, dyp, dys = 1, dy, 0.0
+    else:
+        if dy.size != n:
+            raise L.DimensionMismatch("unary_bwd: dy %s vs %s" % (dy.shape, shape))
+        mode, dyp, dys = 0, materialize(dy), 0.0
+    check(lib.ag_unary_bwd(U[op], _DT[np.dtype(dtype)], vptr(dyp), mode, dys,
+                           vptr(materialize(x)) if x is not None else None,
+                           vptr(materialize(y)) if y is not None else None, vptr(dx), n))
+    return dx
+
+
+def shape_of(x):
+    return () if isnum(x) else x.shape
+
+
+def bcast_shape(*shapes):
+    nd = max((len(s) for s in shapes), default=0)
+    out = [1] * nd
+    for s in shapes:
+        for d, e in enumerate(s):
+            if e != 1:
+                if out[d] != 1 and out[d] != e:
+                    raise L.DimensionMismatch("arrays could not be broadcast to a common size: %s" % (shapes,))
+                out[d] = e
+    # an extent-0 dimension broadcast against 1 stays 0
+    for s in shapes:
+        for d, e in enumerate(s):
+            if e == 0:
+                out[d] = 0
+    return tuple(out)
+
+
+def _strides_for(shape, out_shape):
+    """Column-major element strides of an operand of `shape` viewed in `out_shape` (0 = broadcast)."""
+    st, acc = [], 1
+    for d in range(len(out_shape)):
+        e = shape[d] if d < len(shape) else 1
+        st.append(0 if (e == 1 and out_shape[d] != 1) else acc)
+        acc *= e
+    return st
+
+
+def collapse(out_shape, strides_list):
+    """Drop extent-1 dims and merge adjacent dims that every operand traverses contiguously."""
+    dims = [d for d in range(len(out_shape)) if out_shape[d] != 1]
+    if not dims:
+        return [1], [[0] for _ in strides_list]
+    shp = [out_shape[dims[0]]]
+    sts = [[s[dims[0]]] for s in strides_list]
+    for d in dims[1:]:
+        e = out_shape[d]
+        if all(s[d] == st[-1] * shp[-1] for s, st in zip(strides_list, sts)):
+            shp[-1] *= e
+        else:
+            shp.append(e)
+            for s, st in zip(strides_list, sts):
+                st.append(s[d])
+    return shp, sts
+
+
+def _i64arr(v):
+    return (C.c_int64 * len(v))(*[int(x) for x in v])
+
+
+def _common_dtype(*xs):
+    dts = {x.dtype for x in xs if isinstance(x, DArray)}
+    if len(dts) != 1:
+        raise L.UnsupportedOnDevice("mixed or missing device eltypes %s" % (dts,))
+    return dts.pop()
+
+
+def binary_fwd(op, a, b):
+    """op.(a, b) with Julia broadcasting; a, b: DArray or host Number (at least one DArray)."""
+    a = materialize(a) if isinstance(a, DArray) else a
+    b = materialize(b) if isinstance(b, DArray) else b
+    dtype = _common_dtype(a, b)
+    out_shape = bcast_shape(shape_of(a), shape_of(b))
+    y = DArray.empty(out_shape, dtype)
+    if y.size == 0:
+        return y
+    sl = [_strides_for(shape_of(x), out_shape) if isinstance(x, DArray) else [0] * len(out_shape) for x in (a, b)]
+    oshape = list(out_shape) if out_shape else [1]
+    if not out_shape:
+        sl = [[0], [0]]
+    shp, sts = collapse(oshape, sl + [_strides_for(out_shape, out_shape) if out_shape else [0]])
+    if len(shp) > 4:
+        raise L.UnsupportedOnDevice("broadcast needs %d collapsed dims (max 4)" % len(shp))
+    check(lib.ag_binary_fwd(B[op], _DT[dtype],
+                            vptr(a) if isinstance(a, DArray) else None, 0.0 if isinstance(a, DArray) else float(a), _i64arr(sts[0]),
+                            vptr(b) if isinstance(b, DArray) else None, 0.0 if isinstance(b, DArray) else float(b), _i64arr(sts[1]),
+                            vptr(y), len(shp), _i64arr(shp)))
+    return y
+
+
+def binary_bwd(op, argno, dy, x1, x2, y):
+    """dy .* d(op)/d(x_argno), full broadcast shape (before unbroadcast)."""
+    arrs = [materialize(v) if isinstance(v, DArray) else v for v in (dy, x1, x2, y)]
+    dy, x1, x2, y = arrs
+    dtype = _common_dtype(*[v for v in arrs if v is not None])
+    out_shape = bcast_shape(*[shape_of(v) for v in arrs if v is not None])
+    dx = DArray.empty(out_shape, dtype)
+    if dx.size == 0:
+        return dx
+    if isnum(dy):
+        dy = full_like_shape((), dtype, dy)
+    oshape = list(out_shape) if out_shape else [1]
+
+    def st(v):
+        if isinstance(v, DArray):
+            return _strides_for(v.shape, out_shape) if out_shape else [0]
+        return [0] * len(oshape)
+    sl = [st(dy), st(x1), st(x2), st(y), (_strides_for(out_shape, out_shape) if out_shape else [0])]
+    shp, sts = collapse(oshape, sl)
+    if len(shp) > 4:
+        raise L.UnsupportedOnDevice("broadcast needs %d collapsed dims (max 4)" % len(shp))
+
+    def pv(v):
+        return vptr(v) if isinstance(v, DArray) else None
+
+    def sv(v):
+        return float(v) if isnum(v) else 0.0
+    check(lib.ag_binary_bwd(B[op], argno, _DT[dtype], pv(dy), _i64arr(sts[0]),
+                            pv(x1), sv(x1), _i64arr(sts[1]), pv(x2), sv(x2), _i64arr(sts[2]),
+                            pv(y), _i64arr(sts[3]), vptr(dx), len(shp), _i64arr(shp)))
+    return dx
+
+
+# ---- reductions -------------------------------------------------------------------------------------
+
+def sum_all(x, mapname="id"):
+    x = materialize(x)
+    out = DArray.empty((), x.dtype)
+    if x.size == 0:
+        check(lib.ag_fill(vptr(out), 1, out.dt, 0.0))
+        return out
+    check(lib.ag_sum_all(R[mapname], x.dt, vptr(x), x.size, vptr(out)))
+    return out
+
+
+def sum_dims(x, dims, mapname="id"):
+    """sum(map, x; dims) keeping reduced dims with extent 1 (Julia).  dims: iterable of 0-based dims."""
+    x = materialize(x)
+    dims = sorted({int(d) for d in dims if int(d) < x.ndim})
+    shape = list(x.shape)
+    out_shape = [1 if d in dims else e for d, e in enumerate(shape)]
+    if not dims or all(shape[d] == 1 for d in dims):
+        if mapname == "id":
+            return x.reshape(out_shape) if dims else x
+        return unary_fwd(mapname, x).reshape(out_shape)
+    # maximal runs of consecutive reduced dims -> one ag_sum_dim each
+    runs, i = [], 0
+    while i < len(dims):
+        j = i
+        while j + 1 < len(dims) and dims[j + 1] == dims[j] + 1:
+            j += 1
+        runs.append((dims[i], dims[j]))
+        i = j + 1
+    cur, cur_shape, m = x, shape, mapname
+    for lo, hi in runs:
+        inner = _prod(cur_shape[:lo])
+        red = _prod(cur_shape[lo:hi + 1])
+        outer = _prod(cur_shape[hi + 1:])
+        new_shape = [1 if lo <= d <= hi else e for d, e in enumerate(cur_shape)]
+        out = DArray.empty(new_shape, x.dtype)
+        if out.size:
+            check(lib.ag_sum_dim(R[m], x.dt, vptr(cur), inner, red, outer, vptr(out)))
+        cur, cur_shape, m = out, new_shape, "id"
+    return cur
+
+
+def add(a, b):
+    if a.shape != b.shape:
+        raise L.DimensionMismatch("addto!: %s vs %s" % (a.shape, b.shape))
+    a, b = materialize(a), materialize(b)
+    if a.dtype != b.dtype:
+        raise L.UnsupportedOnDevice("addto!: eltypes %s, %s" % (a.dtype, b.dtype))
+    out = DArray.empty(a.shape, a.dtype)
+    check(lib.ag_add(a.dt, vptr(a), vptr(b), vptr(out), a.size))
+    return out
+
+
+def axpy_(alpha, x, y):
+    """y .+= alpha .* x in place (dense)."""
+    x = materialize(x)
+    if x.size != y.size:
+        raise L.DimensionMismatch("axpy!: %s vs %s" % (x.shape, y.shape))
+    if y.tr:
+        raise L.UnsupportedOnDevice("axpy! into a lazy adjoint")
+    check(lib.ag_axpy(y.dt, float(alpha), vptr(x), vptr(y), y.size))
+    return y
+
+
+def scale_(alpha, x):
+    check(lib.ag_scale(x.dt, float(alpha), vptr(x), x.size))
+    return x
+
+
+# ---- matmul ---------------------------------------------------------------------------------------
+
+def _as_matrix(x, left):
+    """(storage DArray, trans flag, rows, cols, ld) of a matmul operand."""
+    if x.ndim == 2:
+        if x.tr:
+            return x, 1, x.shape[0], x.shape[1], x.shape[1]   # storage is (cols x rows)
+        return x, 0, x.shape[0], x.shape[1], max(x.shape[0], 1)
+    if x.ndim == 1:
+        return x, 0, x.shape[0], 1, max(x.shape[0], 1)
+    raise L.DimensionMismatch("matmul operand with %d dims" % x.ndim)
+
+
+def matmul(a, b):
+    """a*b for matrices/vectors (src/base.jl:26 forward and both of its gradient products)."""
+    dtype = _common_dtype(a, b)
+    A, ta, m, ka, lda = _as_matrix(a, True)
+    Bm, tb, kb, n, ldb = _as_matrix(b, False)
+    if ka != kb:
+        raise L.DimensionMismatch("matmul: A has dimensions (%d,%d) but B has dimensions (%d,%d)" % (m, ka, kb, n))
+    out_shape = (m,) if (b.ndim == 1) else (m, n)
+    if a.ndim == 1 and b.ndim == 2:
+        out_shape = (m, n)
+    c = DArray.empty(out_shape, dtype)
+    if c.size == 0:
+        return c
+    if ka == 0:
+        check(lib.ag_fill(vptr(c), c.size, c.dt, 0.0))
+        return c
+    check(lib.ag_gemm(_DT[dtype], ta, tb, m, n, ka, 1.0, vptr(A), lda, vptr(Bm), ldb, 0.0, vptr(c), max(m, 1)))
+    return c
+
+
+def gemm_engine():
+    buf = C.create_string_buffer(32)
+    check(lib.ag_gemm_last_engine(buf, 32))
+    return buf.value.decode()
+
+
+def set_gemm_engine(e):
+    check(lib.ag_gemm_set_engine({"auto": 0, "ffma": 1, "tcgen05": 2}[e]))
+
+
+def adjoint(x):
+    if x.ndim == 1:
+        return DArray(x.buf, x.ptr, (1, x.shape[0]), x.dtype)
+    if x.ndim != 2:
+        raise L.DimensionMismatch("adjoint of a %d-d array" % x.ndim)
+    if x.shape[0] == 1 or x.shape[1] == 1:
+        src = materialize(x)
+        return DArray(src.buf, src.ptr, (x.shape[1], x.shape[0]), x.dtype)
+    return DArray(x.buf, x.ptr, (x.shape[1], x.shape[0]), x.dtype, tr=not x.tr)
+
+
+# ---- indexing ---------------------------------------------------------------------------------------
+
+def index_to_device(idx):
+    """int64 numpy index vector -> device buffer (returned as a raw _Buffer)."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    buf = _Buffer(max(idx.nbytes, 8))
+    if idx.size:
+        check(lib.ag_copy_h2d(C.c_void_p(buf.ptr), idx.ctypes.data_as(C.c_void_p), idx.nbytes))
+        sync()
+    return buf
+
+
+def gather(x, flat_idx, out_shape):
+    x = materialize(x)
+    out = DArray.empty(out_shape, x.dtype)
+    if out.size:
+        ib = index_to_device(flat_idx)
+        check(lib.ag_gather(x.dt, vptr(x), C.c_void_p(ib.ptr), vptr(out), out.size))
+    return out
+
+
+def gather_cols(x, cols):
+    x = materialize(x)
+    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    out = DArray.empty((x.shape[0], cols.size), x.dtype)
+    if out.size:
+        ib = index_to_device(cols)
+        check(lib.ag_gather_cols(x.dt, vptr(x), x.shape[0], C.c_void_p(ib.ptr), vptr(out), cols.size))
+    return out
+
+
+def scatter_add_(dest, flat_idx, vals, block=1):
+    """dest[flat_idx[j]*block .. +block) += vals[j*block .. +block), repeated indices summed."""
+    flat_idx = np.ascontiguousarray(flat_idx, dtype=np.int64)
+    n = flat_idx.size
+    if n == 0:
+        return dest
+    vals = materialize(vals)
+    if vals.size != n * block:
+        raise L.DimensionMismatch("scatter-add: %d values for %d destinations" % (vals.size, n * block))
+    if flat_idx.min() < 0 or (flat_idx.max() + 1) * block > dest.size:
+        raise IndexError("BoundsError")
+    ib = index_to_device(flat_idx)
+    check(lib.ag_scatter_add(dest.dt, vptr(dest), dest.size, C.c_void_p(ib.ptr), vptr(vals), n, block))
+    return dest
+
+
+def slab_copy(src, src_red, src_off, dst, dst_red, dst_off, inner, length, outer):
+    check(lib.ag_slab_copy(src.dt, vptr(src), src_red, src_off, vptr(dst), dst_red, dst_off, inner, length, outer))
+    return dst
+
+
+# ---- host scalar math (Numbers never touch the device) ----------------------------------------------
+HOST_UNARY = dict(
+    identity=lambda x: x, neg=lambda x: -x, abs=abs, abs2=lambda x: x * x, exp=math.exp, log=math.log,
+    tanh=math.tanh, sigm=lambda x: 1.0 / (1.0 + math.exp(-x)), sqrt=math.sqrt, sin=math.sin, cos=math.cos,
+    tan=math.tan, sinh=math.sinh, cosh=math.cosh, asin=math.asin, acos=math.acos, atan=math.atan,
+    asinh=math.asinh, acosh=math.acosh, atanh=math.atanh, exp2=lambda x: 2.0 ** x, exp10=lambda x: 10.0 ** x,
+    expm1=math.expm1, log2=math.log2, log10=math.log10, log1p=math.log1p,
+    cbrt=lambda x: math.copysign(abs(x) ** (1.0 / 3.0), x), sign=lambda x: (x > 0) - (x < 0),
+    relu=lambda x: x if x > 0 else 0 * x, one=lambda x: type(x)(1))
+HOST_BINARY = dict(
+    add=lambda a, b: a + b, sub=lambda a, b: a - b, mul=lambda a, b: a * b, div=lambda a, b: a / b,
+    max=max, min=min, pow=lambda a, b: a ** b, eq=lambda a, b: float(a == b), lt=lambda a, b: float(a < b),
+    le=lambda a, b: float(a <= b), gt=lambda a, b: float(a > b), ge=lambda a, b: float(a >= b),
+    atan2=math.atan2, hypot=math.hypot)

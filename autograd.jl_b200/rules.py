@@ -1,0 +1,705 @@
+"""Primitive catalogue: forward methods and gradient rules on device arrays.
+
+Mirrors the reference's operator API (file:line under /root/reference):
+  @primitive / @zerograd surface .......... src/macros.jl:88-194
+  + - .* ./ .^ abs abs2 ..................... src/base.jl:20-49,73-74
+  exp log tanh ... max min ................... src/math.jl:9-74
+  sum / sum(abs2,.) / sum(abs,.) / mean ..... src/base.jl:245-247, src/statistics.jl:20-22
+  * (matmul) and adjoint ..................... src/base.jl:26, src/linearalgebra.jl:16
+  reshape / vec / copy / identity ............ src/base.jl:217-224,250,338,341
+  unbroadcast ................................ src/unbroadcast.jl:9-26
+  addto! ..................................... src/addto.jl:14-31,41-52,91-98
+  getindex / ungetindex ...................... src/getindex.jl:32-33,61-79,91-95
+  cat / uncat / cat1d ........................ src/cat.jl:27-31,46-92,122-123,150-182
+
+Every rule has two forms.  When no outer tape is recording, the rule calls ONE fused kernel
+(`dx = dy .* g(x,y)`).  Under an outer tape (higher-order gradients) the rule is the
+reference's own expression over primitives, so that it records itself and stays differentiable.
+"""
+import math
+
+import numpy as np
+
+from . import darray as D
+from ._lib import DimensionMismatch, UnsupportedOnDevice
+from .core import Result, Tracked, Value, forw, recording, value
+from .darray import DArray, isnum
+from .sparse import Sparse, flat_dest
+
+# ---------------------------------------------------------------------------------------------------
+# definition helpers (src/macros.jl:88-194)
+# ---------------------------------------------------------------------------------------------------
+
+
+class Primitive:
+    """`@primitive f(args...),dy,y  rule1 rule2 ...`: a callable that records itself on the active
+    tapes when any argument is boxed."""
+
+    def __init__(self, name, fwd, backs=(), only_first=False):
+        self.name, self.fwd, self.backs, self.only_first = name, fwd, tuple(backs), only_first
+
+    def __call__(self, *args, **kwargs):
+        for a in args:
+            if isinstance(a, Value):
+                return forw(self, *args, **kwargs)
+        return self.fwd(*args, **kwargs)
+
+    def __repr__(self):
+        return self.name
+
+
+def primitive(name, fwd, *backs, **kw):
+    return Primitive(name, fwd, backs, **kw)
+
+
+def zerograd(name, fwd):
+    """`@zerograd f(x)`: unbox, compute, never record (src/macros.jl:158-170)."""
+    def z(*args, **kwargs):
+        return fwd(*(value(a) for a in args), **kwargs)
+    z.__name__ = name
+    return z
+
+
+def back(f, i, dy, y, *args, **kwargs):
+    """back(f, Arg{i+1}, dy, y, args...; kwargs...)  (src/core.jl:165,174)."""
+    vb = getattr(f, "vback", None)
+    if vb is not None:
+        return vb(i, dy, y, *args, **kwargs)
+    rule = f.backs[i] if i < len(f.backs) else None
+    if rule is None:
+        if f.only_first or i < len(f.backs):
+            return None
+        raise TypeError("MethodError: no method matching back(%s, Arg{%d}, ...)" % (f.name, i + 1))
+    return rule(dy, y, *args, **kwargs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# size helpers (all @zerograd in the reference, src/base.jl:221-232)
+# ---------------------------------------------------------------------------------------------------
+
+def size(x, d=None):
+    v = value(x)
+    if isinstance(v, Sparse):
+        v = v.container
+    s = () if isnum(v) else tuple(v.shape)
+    if d is None:
+        return s
+    return s[d] if d < len(s) else 1
+
+
+def ndims(x):
+    return len(size(x))
+
+
+def length(x):
+    n = 1
+    for e in size(x):
+        n *= e
+    return n
+
+
+def _isnumv(x):
+    return isnum(value(x))
+
+
+def _fusable(*xs):
+    """Fused gradient kernels are legal only when nothing is being recorded."""
+    return not recording()
+
+
+# ---------------------------------------------------------------------------------------------------
+# unbroadcast (src/unbroadcast.jl:9-26)
+# ---------------------------------------------------------------------------------------------------
+
+def unbroadcast(x, dx):
+    sx, sdx = size(x), size(dx)
+    if sx == sdx:
+        return dx
+    if _isnumv(x):
+        return sum_(dx)
+    if _isnumv(dx):
+        return fill_like(value(x), dx)
+    d = []
+    for i in range(len(sdx)):
+        if size(x, i) == sdx[i] and sdx[i] > 1:
+            continue
+        if size(x, i) != 1:
+            raise DimensionMismatch("unbroadcast: %s vs %s" % (sx, sdx))
+        d.append(i)
+    return reshape(sum_(dx, dims=tuple(d)), sx)
+
+
+def _fill_like_fwd(xv, v):
+    if isinstance(v, DArray):      # device scalar
+        return D.unary_bwd("identity", v, None, None, shape=xv.shape, dtype=xv.dtype)
+    return D.full_like_shape(xv.shape, xv.dtype, v)
+
+
+fill_like = primitive("fill!", _fill_like_fwd, None, lambda dy, y, x, v: sum_(dy))
+
+# ---------------------------------------------------------------------------------------------------
+# addto! (src/addto.jl:14-31,41-52,91-98)
+# ---------------------------------------------------------------------------------------------------
+
+
+def matches(a, b):
+    if isnum(a) and isnum(b):
+        return True
+    if isinstance(a, DArray) and isinstance(b, DArray):
+        return a.shape == b.shape
+    if isinstance(a, DArray) and a.shape == () and isnum(b) or isinstance(b, DArray) and b.shape == () and isnum(a):
+        return True
+    return False
+
+
+def _addto_fwd(a, b):
+    if a is None:
+        return b
+    if b is None:
+        return a
+    if isinstance(a, Sparse) and isinstance(b, Sparse):
+        assert a.container.shape == b.container.shape, "addto!: Sparse containers differ"
+        a.values.extend(b.values)          # mutates the first argument (src/addto.jl:41-46)
+        a.indices.extend(b.indices)
+        return a
+    if isinstance(a, Sparse):
+        a, b = b, a
+    if isinstance(b, Sparse):
+        if isnum(a):
+            for v in b.values:
+                a = a + v
+            return a
+        assert a.shape == b.container.shape, "addto!: accumulator does not match the Sparse container"
+        return b.addto_dense(a, inplace=not recording())   # copy first under an outer tape (:93)
+    if isinstance(a, DArray) and isinstance(b, DArray):
+        return D.add(a, b)                 # out of place: rules may alias dy (src/addto.jl:23)
+    if isinstance(a, DArray) or isinstance(b, DArray):
+        arr, num = (a, b) if isinstance(a, DArray) else (b, a)
+        if arr.shape != ():
+            raise DimensionMismatch("addto!: array %s vs Number" % (arr.shape,))
+        return D.binary_fwd("add", arr, num)
+    return a + b
+
+
+class _AddTo(Primitive):
+    def __call__(self, a, b):
+        if isinstance(a, Value) or isinstance(b, Value):
+            return forw(self, a, b)
+        return _addto_fwd(a, b)
+
+
+addto = _AddTo("addto!", _addto_fwd, (lambda dy, y, a, b: dy, lambda dy, y, a, b: dy))
+
+
+def full(b):
+    """full(::Sparse) densifies (src/sparse.jl:57); everything else passes through."""
+    if isinstance(b, Sparse):
+        return b.full()
+    return b
+
+
+# ---------------------------------------------------------------------------------------------------
+# elementwise primitives
+# ---------------------------------------------------------------------------------------------------
+
+def _bin_fwd(op):
+    def fwd(a, b):
+        if isnum(a) and isnum(b):
+            return D.HOST_BINARY[op](a, b)
+        return D.binary_fwd(op, a, b)
+    return fwd
+
+
+_HOST_OK = {("mul", 1): 2, ("mul", 2): 1, ("div", 1): 2}   # (op, argno) -> the only operand the rule reads
+
+
+def _bin_back(op, argno, composite):
+    """Gradient of a broadcasting binary op w.r.t. argument `argno`: fused kernel + unbroadcast."""
+    def rule(dy, y, x1, x2):
+        xi = x1 if argno == 1 else x2
+        other = _HOST_OK.get((op, argno))
+        if other is not None and isnum(value(dy)) and isnum(value(x1 if other == 1 else x2)):
+            return unbroadcast(xi, composite(dy, y, x1, x2))     # pure host-scalar arithmetic
+        if _fusable() and (isinstance(value(x1), DArray) or isinstance(value(x2), DArray)
+                           or isinstance(value(dy), DArray)):
+            g = D.binary_bwd(op, argno, value(dy), value(x1), value(x2), value(y))
+            return unbroadcast(xi, g)
+        return unbroadcast(xi, composite(dy, y, x1, x2))
+    return rule
+
+
+def _mask(a, b):
+    """`a .== b` as a non-differentiable 0/1 array (== is @zerograd, src/base.jl:57)."""
+    a, b = value(a), value(b)
+    if isnum(a) and isnum(b):
+        return float(a == b)
+    return D.binary_fwd("eq", a, b)
+
+
+def _passthru(argno, negate=False):
+    def rule(dy, y, x1, x2):
+        xi = x1 if argno == 1 else x2
+        if not negate:
+            return unbroadcast(xi, dy)
+        if _fusable() and isinstance(value(dy), DArray) and size(xi) != size(dy) and not _isnumv(xi):
+            return neg(unbroadcast(xi, dy))      # -(sum dy) == sum(-dy) bit for bit, one pass less
+        return unbroadcast(xi, neg(dy))
+    return rule
+
+
+add = primitive("+", _bin_fwd("add"), _passthru(1), _passthru(2))
+sub = primitive("-", _bin_fwd("sub"), _passthru(1), _passthru(2, negate=True))
+mul = primitive(".*", _bin_fwd("mul"),
+                _bin_back("mul", 1, lambda dy, y, x1, x2: mul(dy, x2)),
+                _bin_back("mul", 2, lambda dy, y, x1, x2: mul(x1, dy)))
+div = primitive("./", _bin_fwd("div"),
+                _bin_back("div", 1, lambda dy, y, x1, x2: div(dy, x2)),
+                _bin_back("div", 2, lambda dy, y, x1, x2: div(mul(neg(dy), x1), abs2(x2))))
+
+
+def dxndx(x1, x2, dy):
+    """src/base.jl:49."""
+    if _isnumv(x2):
+        p = value(x2)
+        if p == 0:
+            return mul(dy, 0)
+        if p == 1:
+            return dy
+        if p == 2:
+            return mul(mul(2, x1), dy)
+    return mul(mul(dy, x2), pow_(x1, sub(x2, 1)))
+
+
+def _pow_back1(dy, y, x1, x2):
+    if _isnumv(x2) and value(x2) in (0, 1, 2):
+        return unbroadcast(x1, dxndx(x1, x2, dy))
+    return _bin_back("pow", 1, lambda dy, y, x1, x2: dxndx(x1, x2, dy))(dy, y, x1, x2)
+
+
+pow_ = primitive(".^", _bin_fwd("pow"), _pow_back1,
+                 _bin_back("pow", 2, lambda dy, y, x1, x2: mul(mul(dy, y), log(x1))))
+max_ = primitive("max", _bin_fwd("max"),
+                 _bin_back("max", 1, lambda dy, y, x1, x2: mul(dy, _mask(y, x1))),
+                 _bin_back("max", 2, lambda dy, y, x1, x2: mul(dy, _mask(y, x2))))
+min_ = primitive("min", _bin_fwd("min"),
+                 _bin_back("min", 1, lambda dy, y, x1, x2: mul(dy, _mask(y, x1))),
+                 _bin_back("min", 2, lambda dy, y, x1, x2: mul(dy, _mask(y, x2))))
+atan2 = primitive("atan", _bin_fwd("atan2"),
+                  _bin_back("atan2", 1, lambda dy, y, x1, x2: mul(dy, div(x2, add(abs2(x1), abs2(x2))))),
+                  _bin_back("atan2", 2, lambda dy, y, x1, x2: mul(dy, div(neg(x1), add(abs2(x1), abs2(x2))))))
+hypot = primitive("hypot", _bin_fwd("hypot"),
+                  _bin_back("hypot", 1, lambda dy, y, x1, x2: mul(dy, div(x1, y))),
+                  _bin_back("hypot", 2, lambda dy, y, x1, x2: mul(dy, div(x2, y))))
+
+# comparison masks are @zerograd (src/base.jl:52-60)
+eq = zerograd("==", _bin_fwd("eq"))
+lt = zerograd("<", _bin_fwd("lt"))
+le = zerograd("<=", _bin_fwd("le"))
+gt = zerograd(">", _bin_fwd("gt"))
+ge = zerograd(">=", _bin_fwd("ge"))
+
+
+def relu(x):
+    """`max.(0, x)` (examples/mnist.jl:32)."""
+    return max_(0, x)
+
+
+def _un_fwd(op):
+    def fwd(x):
+        if isnum(x):
+            return D.HOST_UNARY[op](x)
+        return D.unary_fwd(op, x)
+    return fwd
+
+
+def _un_back(op, composite, needs_x, needs_y):
+    def rule(dy, y, x):
+        if _fusable() and isinstance(value(x), DArray):
+            dyv = value(dy)
+            xv, yv = value(x), value(y)
+            if isnum(dyv) and not needs_x and not needs_y and xv.size == 1:
+                return composite(dy, y, x)                       # scalar chain stays on the host
+            if isnum(dyv) or dyv.size == xv.size or dyv.shape == ():
+                return D.unary_bwd(op, dyv, xv if needs_x else None, yv if needs_y else None,
+                                   shape=xv.shape, dtype=xv.dtype)
+        return composite(dy, y, x)
+    return rule
+
+
+def _unary(name, op, composite, needs_x, needs_y):
+    return primitive(name, _un_fwd(op), _un_back(op, composite, needs_x, needs_y))
+
+
+_LN2, _LN10 = math.log(2.0), math.log(10.0)
+
+sign = zerograd("sign", _un_fwd("sign"))
+one = zerograd("one", _un_fwd("one"))
+identity = primitive("identity", lambda x: x, lambda dy, y, x: dy)
+neg = _unary("-", "neg", lambda dy, y, x: neg(dy), False, False)
+abs_ = _unary("abs", "abs", lambda dy, y, x: mul(dy, sign(x)), True, False)
+abs2 = _unary("abs2", "abs2", lambda dy, y, x: mul(dy, mul(2, x)), True, False)
+exp = _unary("exp", "exp", lambda dy, y, x: mul(dy, y), False, True)
+log = _unary("log", "log", lambda dy, y, x: mul(dy, div(1, x)), True, False)
+tanh = _unary("tanh", "tanh", lambda dy, y, x: mul(dy, sub(1, abs2(y))), False, True)
+sigm = _unary("sigm", "sigm", lambda dy, y, x: mul(mul(dy, y), sub(1, y)), False, True)
+sqrt = _unary("sqrt", "sqrt", lambda dy, y, x: mul(dy, div(1, mul(2, y))), False, True)
+sin = _unary("sin", "sin", lambda dy, y, x: mul(dy, cos(x)), True, False)
+cos = _unary("cos", "cos", lambda dy, y, x: mul(dy, neg(sin(x))), True, False)
+tan = _unary("tan", "tan", lambda dy, y, x: mul(dy, add(1, abs2(y))), False, True)
+sinh = _unary("sinh", "sinh", lambda dy, y, x: mul(dy, cosh(x)), True, False)
+cosh = _unary("cosh", "cosh", lambda dy, y, x: mul(dy, sinh(x)), True, False)
+asin = _unary("asin", "asin", lambda dy, y, x: mul(dy, div(1, sqrt(sub(1, abs2(x))))), True, False)
+acos = _unary("acos", "acos", lambda dy, y, x: mul(dy, div(-1, sqrt(sub(1, abs2(x))))), True, False)
+atan = _unary("atan", "atan", lambda dy, y, x: mul(dy, div(1, add(1, abs2(x)))), True, False)
+asinh = _unary("asinh", "asinh", lambda dy, y, x: mul(dy, div(1, sqrt(add(1, abs2(x))))), True, False)
+acosh = _unary("acosh", "acosh", lambda dy, y, x: mul(dy, div(1, sqrt(sub(abs2(x), 1)))), True, False)
+atanh = _unary("atanh", "atanh", lambda dy, y, x: mul(dy, div(1, sub(1, abs2(x)))), True, False)
+exp2 = _unary("exp2", "exp2", lambda dy, y, x: mul(dy, mul(y, _LN2)), False, True)
+exp10 = _unary("exp10", "exp10", lambda dy, y, x: mul(dy, mul(y, _LN10)), False, True)
+expm1 = _unary("expm1", "expm1", lambda dy, y, x: mul(dy, add(1, y)), False, True)
+log2 = _unary("log2", "log2", lambda dy, y, x: mul(dy, div(1, mul(_LN2, x))), True, False)
+log10 = _unary("log10", "log10", lambda dy, y, x: mul(dy, div(1, mul(_LN10, x))), True, False)
+log1p = _unary("log1p", "log1p", lambda dy, y, x: mul(dy, div(1, add(1, x))), True, False)
+cbrt = _unary("cbrt", "cbrt", lambda dy, y, x: mul(dy, div(1, mul(3, abs2(y)))), False, True)
+
+
+def _copy_fwd(x):
+    return D.copy(x) if isinstance(x, DArray) else x
+
+
+copy = primitive("copy", _copy_fwd, lambda dy, y, x: dy)
+
+# ---------------------------------------------------------------------------------------------------
+# reductions (src/base.jl:245-247; src/statistics.jl:20-22)
+# ---------------------------------------------------------------------------------------------------
+
+
+def _dims(dims):
+    if dims is None:
+        return None
+    return (int(dims),) if isinstance(dims, (int, np.integer)) else tuple(int(d) for d in dims)
+
+
+def _sum_fwd_map(mapname):
+    def fwd(x, dims=None):
+        if isnum(x):
+            return D.HOST_UNARY[mapname](x) if mapname != "id" else x
+        if dims is None:
+            return D.sum_all(x, mapname)
+        return D.sum_dims(x, _dims(dims), mapname)
+    return fwd
+
+
+def _expand_to(dy, x):
+    """dy .* one.(x): broadcast dy (Number, device scalar or keep-dims array) to x's shape."""
+    dyv, xv = value(dy), value(x)
+    if isnum(xv):
+        return dyv
+    if isnum(dyv):
+        return D.full_like_shape(xv.shape, xv.dtype, dyv)
+    if dyv.shape == xv.shape:
+        return dyv
+    if dyv.size == 1:
+        return D.unary_bwd("identity", dyv.reshape(()), None, None, shape=xv.shape, dtype=xv.dtype)
+    return _bcast_to(dyv, xv.shape)
+
+
+def _bcast_to(a, shape):
+    # broadcast-copy through the binary map: a .* 1 evaluated on the target shape
+    out = D.DArray.empty(shape, a.dtype)
+    if out.size == 0:
+        return out
+    st_a = D._strides_for(a.shape, shape)
+    shp, sts = D.collapse(list(shape), [st_a, D._strides_for(shape, shape)])
+    if len(shp) > 4:
+        raise UnsupportedOnDevice("broadcast needs %d collapsed dims (max 4)" % len(shp))
+    D.check(D.lib.ag_binary_fwd(D.B["mul"], a.dt, D.vptr(a), 0.0, D._i64arr(sts[0]), None, 1.0,
+                                D._i64arr([0] * len(shp)), D.vptr(out), len(shp), D._i64arr(shp)))
+    return out
+
+
+def _sum_back(dy, y, x, dims=None):
+    if _fusable():
+        return _expand_to(dy, x)
+    return mul(dy, one(x))
+
+
+def _sumabs2_back(dy, y, x, dims=None):
+    if _fusable() and isinstance(value(x), DArray):
+        dyv, xv = value(dy), value(x)
+        if isnum(dyv) or dyv.size == 1:
+            return D.unary_bwd("abs2", dyv if isnum(dyv) else dyv.reshape(()), xv, None)
+        return D.binary_fwd("mul", dyv, D.binary_fwd("mul", 2.0, xv))
+    return mul(dy, mul(2, x))
+
+
+def _sumabs_back(dy, y, x, dims=None):
+    if _fusable() and isinstance(value(x), DArray):
+        dyv, xv = value(dy), value(x)
+        if isnum(dyv) or dyv.size == 1:
+            return D.unary_bwd("abs", dyv if isnum(dyv) else dyv.reshape(()), xv, None)
+    return mul(dy, sign(x))
+
+
+sum_ = primitive("sum", _sum_fwd_map("id"), _sum_back)
+sumabs2 = primitive("sum(abs2,·)", _sum_fwd_map("abs2"), _sumabs2_back)
+sumabs = primitive("sum(abs,·)", _sum_fwd_map("abs"), _sumabs_back)
+
+
+def _mean_fwd(x, dims=None):
+    s = _sum_fwd_map("id")(x, dims)
+    return div.fwd(s, length(x) // max(length(s), 1))
+
+
+mean = primitive("mean", _mean_fwd,
+                 lambda dy, y, x, dims=None: div(_sum_back(dy, y, x, dims), length(x) // length(dy)))
+
+# ---------------------------------------------------------------------------------------------------
+# linear algebra (src/base.jl:26; src/linearalgebra.jl:16,87)
+# ---------------------------------------------------------------------------------------------------
+
+
+def _matmul_fwd(a, b):
+    if isnum(a) or isnum(b) or (isinstance(a, DArray) and a.shape == ()) or (isinstance(b, DArray) and b.shape == ()):
+        return _bin_fwd("mul")(a, b)
+    return D.matmul(a, b)
+
+
+def _scalarish(x):
+    v = value(x)
+    return isnum(v) or (isinstance(v, DArray) and v.shape == ())
+
+
+def _matmul_back1(dy, y, x1, x2):
+    if _scalarish(x1) or _scalarish(x2):
+        return unbroadcast(x1, mul(dy, x2))
+    return matmul(dy, adjoint(x2))
+
+
+def _matmul_back2(dy, y, x1, x2):
+    if _scalarish(x1) or _scalarish(x2):
+        return unbroadcast(x2, mul(x1, dy))
+    return matmul(adjoint(x1), dy)
+
+
+matmul = primitive("*", _matmul_fwd, _matmul_back1, _matmul_back2)
+
+
+def _adjoint_fwd(x):
+    return x if isnum(x) else D.adjoint(x)
+
+
+adjoint = primitive("adjoint", _adjoint_fwd,
+                    lambda dy, y, x: reshape(adjoint(dy), size(x)) if ndims(x) == 1 else adjoint(dy))
+transpose = adjoint
+
+
+def matpow(x, p):
+    """`A^p` on a matrix has no gradient by design (src/base.jl:44)."""
+    if isinstance(x, Value) and ndims(x) >= 1:
+        raise RuntimeError("A^B grad undefined")
+    raise UnsupportedOnDevice("matrix power on device")
+
+
+# ---------------------------------------------------------------------------------------------------
+# shape rules (src/base.jl:217-224,250)
+# ---------------------------------------------------------------------------------------------------
+
+def _reshape_fwd(x, shape):
+    shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    if isnum(x):
+        return x
+    return x.reshape(shape)
+
+
+reshape = primitive("reshape", _reshape_fwd, lambda dy, y, x, shape: reshape(dy, size(x)))
+vec = primitive("vec", lambda x: x.reshape((x.size,)), lambda dy, y, x: reshape(dy, size(x)))
+
+# ---------------------------------------------------------------------------------------------------
+# getindex / ungetindex (src/getindex.jl:32-33,61-79,91-95)
+# ---------------------------------------------------------------------------------------------------
+
+
+def _col_index(x, idx):
+    """(Colon, Vector{Int}) on a matrix -> the column ids, else None (embedding lookup fast path)."""
+    if x.ndim == 2 and len(idx) == 2 and isinstance(idx[0], slice) and idx[0] == slice(None):
+        j = idx[1]
+        if isinstance(j, (list, np.ndarray)) and np.asarray(j).dtype != np.bool_ and np.asarray(j).ndim == 1:
+            return np.asarray(j, dtype=np.int64)
+    return None
+
+
+def _getindex_fwd(x, *idx):
+    if isnum(x):
+        return x
+    cols = _col_index(x, idx)
+    if cols is not None:
+        if cols.size and (cols.min() < 0 or cols.max() >= x.shape[1]):
+            raise IndexError("BoundsError")
+        return D.gather_cols(x, cols)
+    dest, outshape = flat_dest(x.shape, idx)
+    return D.gather(x, dest, outshape)
+
+
+def _ungetindex_dense(x, dxi, idx):
+    return Sparse(x, [dxi], [idx]).full()
+
+
+def ungetindex(x, dxi, idx):
+    """src/getindex.jl:61-79 (Array branch), :91-92 (Value unboxing)."""
+    x = value(x)
+    if isinstance(dxi, Value):
+        if isnum(x):
+            return dxi
+        return forw(addto, D.zeros(x.shape, x.dtype), forw(_ungetindex_p, x, dxi, idx))
+    if isnum(x):
+        return dxi
+    if recording():
+        return _ungetindex_dense(x, dxi, idx)
+    return Sparse(x, [dxi], [idx])
+
+
+_ungetindex_p = primitive("ungetindex", _ungetindex_dense, None,
+                          lambda ddx, dx, x, dxi, idx: getindex(ddx, *idx), None)
+getindex = primitive("getindex", _getindex_fwd, lambda dxi, xi, x, *idx: ungetindex(x, dxi, idx),
+                     only_first=True)
+
+# ---------------------------------------------------------------------------------------------------
+# cat / uncat (src/cat.jl:27-31,46-92,122-123) and cat1d (src/cat.jl:150-182)
+# ---------------------------------------------------------------------------------------------------
+
+
+def _shape_nd(x, nd):
+    s = size(x)
+    if s == () and isnum(value(x)):
+        s = (1,)
+    return tuple(s) + (1,) * (nd - len(s))
+
+
+def _cat_fwd(*xs, dims):
+    arrs = [x for x in xs if isinstance(x, DArray)]
+    if not arrs:
+        raise UnsupportedOnDevice("cat of host Numbers only")
+    dtype = arrs[0].dtype
+    nd = max(max(ndims(x) for x in xs), dims + 1)
+    shapes = [_shape_nd(x, nd) for x in xs]
+    for s in shapes:
+        for d in range(nd):
+            if d != dims and s[d] != shapes[0][d]:
+                raise DimensionMismatch("cat: mismatch in dimension %d" % (d + 1))
+    tot = sum(s[dims] for s in shapes)
+    out_shape = tuple(tot if d == dims else shapes[0][d] for d in range(nd))
+    out = D.DArray.empty(out_shape, dtype)
+    inner = D._prod(out_shape[:dims])
+    outer = D._prod(out_shape[dims + 1:])
+    off = 0
+    for x, s in zip(xs, shapes):
+        if isnum(x):
+            x = D.full_like_shape((1,), dtype, x)
+        x = D.materialize(x)
+        if s[dims]:
+            D.slab_copy(x, s[dims], 0, out, tot, off, inner, s[dims], outer)
+        off += s[dims]
+    return out
+
+
+def _uncat_range(y1, argn, dims, xs):
+    lo = 0
+    for j in range(argn):
+        lo += size(xs[j], dims) if ndims(xs[j]) > dims or not _isnumv(xs[j]) else 1
+    ln = size(xs[argn], dims) if not _isnumv(xs[argn]) else 1
+    return lo, ln
+
+
+def _uncat_fwd(y1, argn, dims, *xs):
+    lo, ln = _uncat_range(y1, argn, dims, xs)
+    shp = y1.shape + (1,) * (dims + 1 - y1.ndim)
+    inner, tot, outer = D._prod(shp[:dims]), shp[dims], D._prod(shp[dims + 1:])
+    target = size(xs[argn]) if not _isnumv(xs[argn]) else (1,)
+    out = D.DArray.empty(target, y1.dtype)
+    if out.size:
+        D.slab_copy(D.materialize(y1), tot, lo, out, ln, 0, inner, ln, outer)
+    return out
+
+
+def _uncat1_fwd(x2, y1, argn, dims, *xs):
+    lo, ln = _uncat_range(y1, argn, dims, xs)
+    shp = y1.shape + (1,) * (dims + 1 - y1.ndim)
+    inner, tot, outer = D._prod(shp[:dims]), shp[dims], D._prod(shp[dims + 1:])
+    out = D.zeros(y1.shape, y1.dtype)
+    if isinstance(x2, DArray) and x2.size:
+        D.slab_copy(D.materialize(x2), ln, 0, out, tot, lo, inner, ln, outer)
+    return out
+
+
+uncat = primitive("uncat", _uncat_fwd,
+                  lambda x2, x1, y1, argn, dims, *xs: uncat1(x2, y1, argn, dims, *xs), only_first=True)
+uncat1 = primitive("uncat1", _uncat1_fwd,
+                   lambda y3, y2, x2, y1, argn, dims, *xs: uncat(y3, argn, dims, *xs), only_first=True)
+
+
+class _Cat(Primitive):
+    def __call__(self, *args, dims):
+        for a in args:
+            if isinstance(a, Value):
+                return forw(self, *args, dims=dims)
+        return self.fwd(*args, dims=dims)
+
+    @staticmethod
+    def vback(i, dy, y, *xs, dims):
+        return uncat(dy, i, dims, *xs)
+
+
+cat = _Cat("cat", _cat_fwd)
+
+
+def vcat(*xs):
+    return cat(*xs, dims=0)
+
+
+def hcat(*xs):
+    return cat(*xs, dims=1)
+
+
+def _cat1d_fwd(*xs):
+    arrs = [D.materialize(x) if isinstance(x, DArray) else x for x in xs]
+    dtype = next(a.dtype for a in arrs if isinstance(a, DArray))
+    tot = sum(length(a) for a in arrs)
+    out = D.DArray.empty((tot,), dtype)
+    off = 0
+    for a in arrs:
+        if isnum(a):
+            a = D.full_like_shape((1,), dtype, a)
+        if a.size:
+            D.slab_copy(a, a.size, 0, out, tot, off, 1, a.size, 1)
+        off += a.size
+    return out
+
+
+class _Cat1d(Primitive):
+    @staticmethod
+    def vback(i, y1, y, *xs):
+        off2 = 0
+        for j in range(i + 1):
+            off2 += length(xs[j])
+        off1 = off2 - length(xs[i])
+        return reshape(getindex(y1, slice(off1, off2)), size(xs[i]))
+
+
+cat1d = _Cat1d("cat1d", _cat1d_fwd)
+
+# ---------------------------------------------------------------------------------------------------
+# update (README.md:70-77; src/sparse.jl:50-54; src/core.jl:55)
+# ---------------------------------------------------------------------------------------------------
+
+
+def axpy(a, x, y):
+    """axpy!(a, x, y): y .+= a .* x in place; y may be a Param; x may be Sparse (src/sparse.jl:50)."""
+    yv = value(y)
+    if x is None:
+        return y
+    if isinstance(x, Sparse):
+        (x * a).addto_dense(yv, inplace=True)
+    else:
+        D.axpy_(a, x, yv)
+    return y

@@ -1,0 +1,250 @@
+/* agb200.h -- C ABI of libagb200.so: the B200 (sm_100a) array hot path behind AutoGrad.jl's
+ * operator API.
+ *
+ * AutoGrad.jl (reference, /root/reference) has no FFI: its extension point is Julia multiple
+ * dispatch on the *unboxed array type* that sits inside Param/Result (src/core.jl:66 calls
+ * f(novalue...); gradient rules in src/base.jl, src/math.jl call generic array functions).  A device
+ * array type plugs in by giving those generic functions methods that `ccall` into this library.
+ * Every entry point below names the reference call site(s) it replaces.  See INTEGRATION.md for the
+ * Julia-side binding.
+ *
+ * Conventions
+ *   - plain C, `extern "C"`; every function returns ag_status (0 = ok); the message of the last
+ *     failure on this thread is read with ag_last_error().  Nothing throws, nothing aborts.
+ *   - arrays are raw device pointers to COLUMN-MAJOR (Julia layout) dense storage; sizes, strides
+ *     and indices are int64_t (Julia Int); strides are in elements; index vectors handed to the
+ *     gather/scatter entry points are 0-based flat column-major offsets (the Julia wrapper
+ *     subtracts 1 when it normalises an index tuple, src/addto.jl:95).
+ *   - dtype: AG_F32 / AG_F64.  Scalars cross the ABI as double and are narrowed on device.
+ *   - all work is enqueued on ONE library stream (ag_stream()); only ag_sync, ag_copy_d2h,
+ *     ag_event_elapsed and ag_graph_end block the host.  There is no CPU fallback: an unsupported
+ *     request returns AG_EUNSUPPORTED.
+ */
+#ifndef AGB200_H
+#define AGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t ag_status;
+
+enum {
+  AG_OK = 0,
+  AG_EINVAL = 1,       /* bad argument / shape mismatch  -> Julia DimensionMismatch / ArgumentError */
+  AG_ENOMEM = 2,       /* device or pinned allocation failed -> OutOfMemoryError */
+  AG_ECUDA = 3,        /* a CUDA runtime/driver call failed */
+  AG_ENCCL = 4,        /* an NCCL call failed */
+  AG_EUNSUPPORTED = 5, /* dtype/op/rank not implemented on device -> MethodError (no CPU fallback) */
+  AG_ESTATE = 6        /* call order violated (not initialised, graph capture state, ...) */
+};
+
+enum { AG_F32 = 0, AG_F64 = 1 };
+
+/* ------------------------------------------------------------------------------------------------
+ * Unary elementwise primitives.  fwd: y = f(x).  bwd: dx = dy .* g(x, y) -- the
+ * `@primitive f(x),dy,y (dy.*(g))` rules of src/math.jl:9-74 and src/base.jl:73-74, plus the user
+ * primitive `sigm` of examples/charlm.jl:46-47.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  AG_U_IDENTITY = 0, /* +(x): dy                      src/base.jl:20 */
+  AG_U_NEG = 1,      /* -(x): -dy                     src/base.jl:22 */
+  AG_U_ABS = 2,      /* dy.*sign.(x)                  src/base.jl:73 */
+  AG_U_ABS2 = 3,     /* dy.*(2x)                      src/base.jl:74 */
+  AG_U_EXP = 4,      /* dy.*y                         src/math.jl:42 */
+  AG_U_LOG = 5,      /* dy.*(1 ./ x)                  src/math.jl:50 */
+  AG_U_TANH = 6,     /* dy.*(1 .- abs2.(y))           src/math.jl:74 */
+  AG_U_SIGM = 7,     /* dy.*y.*(1 .- y)               examples/charlm.jl:47 */
+  AG_U_SQRT = 8,     /* dy.*(1 ./ (2 .* y))           src/math.jl:71 */
+  AG_U_SIN = 9,      /* dy.*cos.(x)                   src/math.jl:65 */
+  AG_U_COS = 10,     /* dy.*(-sin.(x))                src/math.jl:30 */
+  AG_U_TAN = 11,     /* dy.*(1 .+ abs2.(y))           src/math.jl:72 */
+  AG_U_SINH = 12,    /* dy.*cosh.(x)                  src/math.jl:68 */
+  AG_U_COSH = 13,    /* dy.*sinh.(x)                  src/math.jl:33 */
+  AG_U_ASIN = 14,    /* dy./sqrt(1-x^2)               src/math.jl:21 */
+  AG_U_ACOS = 15,    /* -dy./sqrt(1-x^2)              src/math.jl:9 */
+  AG_U_ATAN = 16,    /* dy./(1+x^2)                   src/math.jl:24 */
+  AG_U_ASINH = 17,   /* dy./sqrt(1+x^2)               src/math.jl:23 */
+  AG_U_ACOSH = 18,   /* dy./sqrt(x^2-1)               src/math.jl:11 */
+  AG_U_ATANH = 19,   /* dy./(1-x^2)                   src/math.jl:26 */
+  AG_U_EXP2 = 20,    /* dy.*y.*log(2)                 src/math.jl:44 */
+  AG_U_EXP10 = 21,   /* dy.*y.*log(10)                src/math.jl:43 */
+  AG_U_EXPM1 = 22,   /* dy.*(1 .+ y)                  src/math.jl:45 */
+  AG_U_LOG2 = 23,    /* dy./(log(2).*x)               src/math.jl:53 */
+  AG_U_LOG10 = 24,   /* dy./(log(10).*x)              src/math.jl:51 */
+  AG_U_LOG1P = 25,   /* dy./(1 .+ x)                  src/math.jl:52 */
+  AG_U_CBRT = 26,    /* dy./(3 .* abs2.(y))           src/math.jl:27 */
+  AG_U_SIGN = 27,    /* @zerograd sign                src/base.jl (zero gradient; fwd only) */
+  AG_U_RELU = 28,    /* max.(0,x): dy.*(y.==x)        src/math.jl:54 with x1 = 0 (examples/mnist.jl:32) */
+  AG_U_ONE = 29,     /* one.(x) (fwd only; used by dy.*one.(x), src/base.jl:245) */
+  AG_U_COUNT = 30
+};
+
+/* Binary broadcasting primitives (src/base.jl:21-49, src/math.jl:24,48,54-55). */
+enum {
+  AG_B_ADD = 0,
+  AG_B_SUB = 1,
+  AG_B_MUL = 2,
+  AG_B_DIV = 3,
+  AG_B_MAX = 4,
+  AG_B_MIN = 5,
+  AG_B_POW = 6,
+  AG_B_EQ = 7,     /* (a .== b) as 1.0/0.0 in the operand dtype: the mask in dy.*(y.==xi) */
+  AG_B_LT = 8,     /* comparison masks (@zerograd, src/base.jl:52-60) */
+  AG_B_LE = 9,
+  AG_B_GT = 10,
+  AG_B_GE = 11,
+  AG_B_ATAN2 = 12, /* atan(x1,x2)  src/math.jl:24 */
+  AG_B_HYPOT = 13, /* hypot        src/math.jl:48 */
+  AG_B_COUNT = 14
+};
+
+/* Reduction pre-maps: sum(x), sum(abs2,x), sum(abs,x)  (src/base.jl:245-247). */
+enum { AG_R_ID = 0, AG_R_ABS2 = 1, AG_R_ABS = 2 };
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+/* Bind this process to one GPU, create the library stream and the caching pool.  Idempotent for the
+ * same device.  Replaces nothing in the reference (CPU only); one rank == one process == one GPU. */
+ag_status ag_init(int32_t device);
+ag_status ag_shutdown(void);
+/* cudaStreamSynchronize on the library stream: the `@gs` hook, src/AutoGrad.jl:11. */
+ag_status ag_sync(void);
+/* Copies the calling thread's last error message (NUL terminated) into buf. */
+ag_status ag_last_error(char* buf, int64_t buflen);
+/* info[0]=device, [1]=SM count, [2]=cc major, [3]=cc minor, [4]=total bytes, [5]=free bytes,
+ * [6]=bytes held by the pool, [7]=bytes handed out. */
+ag_status ag_device_info(int64_t* info8);
+/* The library's cudaStream_t, as an integer, for interop (torch.cuda.ExternalStream, NCCL). */
+ag_status ag_stream(uint64_t* stream_out);
+/* Number of kernels this library has launched since ag_init (bench.py's gpu_launches). */
+ag_status ag_launch_count(int64_t* count_out);
+
+/* ---- memory: the storage behind the device array type --------------------------------------- */
+/* Stream-ordered caching allocator.  ag_free never synchronises and is safe from a finalizer
+ * (Julia GC) and from the gcnode hook (src/core.jl:168,235-237). */
+ag_status ag_alloc(int64_t bytes, void** ptr_out);
+ag_status ag_free(void* ptr);
+ag_status ag_pool_trim(void);
+/* Pinned host staging buffers for the h2d/d2h copies. */
+ag_status ag_host_alloc(int64_t bytes, void** ptr_out);
+ag_status ag_host_free(void* ptr);
+ag_status ag_copy_h2d(void* dst_dev, const void* src_host, int64_t bytes); /* async on the stream */
+ag_status ag_copy_d2h(void* dst_host, const void* src_dev, int64_t bytes); /* blocks until done */
+ag_status ag_copy_d2h_async(void* dst_host, const void* src_dev, int64_t bytes);
+ag_status ag_copy_d2d(void* dst_dev, const void* src_dev, int64_t bytes);  /* copy(x), src/base.jl:338 */
+/* fill!(similar(x), v): unbroadcast's scalar branch (src/unbroadcast.jl:14-15), zero(x), ones. */
+ag_status ag_fill(void* dst, int64_t n, int32_t dtype, double value);
+
+/* ---- timing / graphs ---------------------------------------------------------------------------- */
+ag_status ag_event_create(uint64_t* ev_out);
+ag_status ag_event_record(uint64_t ev);
+ag_status ag_event_elapsed_ms(uint64_t ev_start, uint64_t ev_stop, float* ms_out); /* syncs on stop */
+ag_status ag_event_destroy(uint64_t ev);
+/* Capture everything enqueued between begin/end (one recorded tape's forward+backward+update)
+ * into a CUDA graph and replay it.  Pool blocks handed out during capture stay owned by the graph
+ * until ag_graph_destroy.  Replaces the per-op dispatch of src/core.jl:64-79,156-169 on replay. */
+ag_status ag_graph_begin(void);
+ag_status ag_graph_end(uint64_t* graph_out);
+ag_status ag_graph_launch(uint64_t graph);
+ag_status ag_graph_destroy(uint64_t graph);
+
+/* ---- elementwise ------------------------------------------------------------------------------ */
+/* y[i] = f(x[i]), i < n.  Forward of every `f.(x)` node (src/core.jl:66-70 materialises it). */
+ag_status ag_unary_fwd(int32_t op, int32_t dtype, const void* x, void* y, int64_t n);
+/* dx[i] = dy[i] * g(x[i], y[i]).  dy: device array (dy_mode 0), device scalar (1), or the
+ * immediate dy_scalar (2).  x / y may be NULL when g does not use them.
+ * Replaces the broadcast expression in each rule of src/math.jl:9-74. */
+ag_status ag_unary_bwd(int32_t op, int32_t dtype, const void* dy, int32_t dy_mode, double dy_scalar,
+                       const void* x, const void* y, void* dx, int64_t n);
+/* y = op.(a, b) with Julia broadcasting.  shape[ndims] (ndims <= 4) is the result shape after the
+ * caller has collapsed adjacent dimensions; a_strides/b_strides give each operand's element
+ * stride per dimension (0 = broadcast along it).  a == NULL (b == NULL) means the operand is the
+ * immediate a_scalar (b_scalar).  Forward of `+ - .* ./ max min .^` nodes (src/base.jl:21-45,
+ * src/math.jl:54-55) and the building block of the unfused (higher-order-safe) gradient path. */
+ag_status ag_binary_fwd(int32_t op, int32_t dtype, const void* a, double a_scalar,
+                        const int64_t* a_strides, const void* b, double b_scalar,
+                        const int64_t* b_strides, void* y, int32_t ndims, const int64_t* shape);
+/* Fused gradient of a binary node w.r.t. argument argno (1 or 2), BEFORE unbroadcast:
+ *   dx = dy .* d(op)/d(x_argno)(x1, x2, y), all operands broadcast to `shape` through strides
+ * (x1/x2 may be immediates as above; y may be NULL where unused).  Only valid when no outer tape
+ * is recording (src/core.jl:60-61), see SURVEY.md 3.4. */
+ag_status ag_binary_bwd(int32_t op, int32_t argno, int32_t dtype, const void* dy,
+                        const int64_t* dy_strides, const void* x1, double x1_scalar,
+                        const int64_t* x1_strides, const void* x2, double x2_scalar,
+                        const int64_t* x2_strides, const void* y, const int64_t* y_strides,
+                        void* dx, int32_t ndims, const int64_t* shape);
+
+/* ---- reductions -------------------------------------------------------------------------------- */
+/* out[0] = sum(map.(x)) over n elements; deterministic two-phase tree.  sum(x), sum(abs2,x),
+ * sum(abs,x) forward (rules at src/base.jl:245-247); unbroadcast's Number branch
+ * (src/unbroadcast.jl:12-13). */
+ag_status ag_sum_all(int32_t map, int32_t dtype, const void* x, int64_t n, void* out_scalar);
+/* x viewed as (inner, red, outer) column-major; out[i,o] = sum_r map(x[i,r,o]), out is
+ * (inner, outer).  One call per reduced dimension: sum(x;dims=d) and the general branch of
+ * unbroadcast (src/unbroadcast.jl:17-24). */
+ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, int64_t red,
+                     int64_t outer, void* out);
+
+/* ---- accumulation / update ---------------------------------------------------------------------- */
+/* out = a + b (out may alias a or b).  addto!(a::AbstractArray,b) = a+b, src/addto.jl:23. */
+ag_status ag_add(int32_t dtype, const void* a, const void* b, void* out, int64_t n);
+/* y += alpha*x.  LinearAlgebra.axpy! in the SGD loop (README.md:70-77; src/core.jl:55). */
+ag_status ag_axpy(int32_t dtype, double alpha, const void* x, void* y, int64_t n);
+/* x *= alpha (lmul!, gradient clipping examples/charlm.jl:148-149). */
+ag_status ag_scale(int32_t dtype, double alpha, void* x, int64_t n);
+
+/* ---- matrix product ------------------------------------------------------------------------------ */
+/* C = alpha*op(A)*op(B) + beta*C, column-major BLAS convention, op = N (0) or T (1).
+ * Forward `*` (src/core.jl:66 -> LinearAlgebra) and its rules dy*x2' (NT) and x1'*dy (TN),
+ * src/base.jl:26 with the lazy adjoint of src/linearalgebra.jl:16.  Float32 uses tcgen05
+ * (3xTF32 error-compensated, fp32 TMEM accumulation) where the shape qualifies and an FFMA
+ * kernel otherwise; Float64 uses DFMA. */
+ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                  double alpha, const void* A, int64_t lda, const void* B, int64_t ldb, double beta,
+                  void* C, int64_t ldc);
+/* Select the Float32 GEMM engine: 0 = auto, 1 = force FFMA, 2 = force tcgen05 (error if the
+ * shape does not qualify).  Test hook. */
+ag_status ag_gemm_set_engine(int32_t engine);
+/* Name of the engine the last ag_gemm call used ("ffma", "dfma", "tcgen05"). */
+ag_status ag_gemm_last_engine(char* buf, int64_t buflen);
+
+/* ---- indexing: getindex / Sparse / addtoindex! ------------------------------------------------- */
+/* out[j] = x[idx[j]], j < n; idx are 0-based flat offsets on device.  getindex forward,
+ * src/getindex.jl:32. */
+ag_status ag_gather(int32_t dtype, const void* x, const int64_t* idx, void* out, int64_t n);
+/* Blocked gather: out[:, j] = x[:, col[j]] for (rows x ncols_out); the W[:, ids] embedding lookup. */
+ag_status ag_gather_cols(int32_t dtype, const void* x, int64_t rows, const int64_t* col,
+                         void* out, int64_t ncols_out);
+/* dest[idx[j]] += vals[j] for j < n with repeated indices summed (addtoindex!,
+ * src/addto.jl:107-129; addto!(dense, Sparse), src/addto.jl:91-98; full(), src/sparse.jl:57).
+ * Deterministic: stable radix sort by destination + segmented reduce in source order, one
+ * read-modify-write per touched destination.  block > 1 treats idx as block-granular: value j
+ * covers dest[idx[j]*block .. +block) (column indices of an (rows x cols) container with
+ * block = rows). */
+ag_status ag_scatter_add(int32_t dtype, void* dest, int64_t dest_len, const int64_t* idx,
+                         const void* vals, int64_t n, int64_t block);
+
+/* ---- cat / uncat ---------------------------------------------------------------------------------- */
+/* Copy a (inner, len, outer) slab: dst[i, dst_off + r, o] = src[i, src_off + r, o] where src has
+ * middle extent src_red and dst has dst_red.  cat forward / uncat gradient slices,
+ * src/cat.jl:27-31,46-67; also getindex/ungetindex with range indices. */
+ag_status ag_slab_copy(int32_t dtype, const void* src, int64_t src_red, int64_t src_off, void* dst,
+                       int64_t dst_red, int64_t dst_off, int64_t inner, int64_t len, int64_t outer);
+/* permutedims(x, (2,1)) materialised: out (cols x rows) = transpose of x (rows x cols). */
+ag_status ag_transpose(int32_t dtype, const void* x, int64_t rows, int64_t cols, void* out);
+
+/* ---- data-parallel exchange (no reference counterpart: BASELINE.json north_star) --------------- */
+/* NCCL communicator over the ranks of one node; id is the 128-byte ncclUniqueId produced on rank
+ * 0 by ag_comm_unique_id and distributed by the host launcher. */
+ag_status ag_comm_unique_id(uint8_t* id128);
+ag_status ag_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128);
+ag_status ag_comm_destroy(void);
+/* In-place sum-allreduce of a flat gradient bucket on the library stream. */
+ag_status ag_allreduce_sum(int32_t dtype, void* buf, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGB200_H */

@@ -1,0 +1,325 @@
+"""TEST INFRASTRUCTURE ONLY: a numpy stand-in for libagb200.so's C ABI so the HOST logic (tape runtime,
+rule dispatch, broadcast stride collapsing, index bookkeeping, data-parallel bucketing) can be
+exercised on a machine without a GPU.  It is installed by the `hostlib` fixture in conftest.py by
+swapping the `lib` object inside the product modules; nothing under autograd.jl_b200/ knows about
+it.  GPU parity tests (-m gpu) never use it.
+
+Each function documents the contract of the C entry point of the same name (include/agb200.h).
+"""
+import ctypes as C
+
+import numpy as np
+
+_DT = {0: np.float32, 1: np.float64}
+
+
+def _p(x):
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "value"):
+        return x.value or 0
+    return C.cast(x, C.c_void_p).value or 0
+
+
+def _arr(ptr, n, dtype):
+    ptr = _p(ptr)
+    dtype = np.dtype(dtype)
+    if n == 0:
+        return np.empty(0, dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+def _out(ref):
+    return ref._obj
+
+
+_U = {
+    0: (lambda x: x, lambda x, y: 1.0), 1: (lambda x: -x, lambda x, y: -1.0),
+    2: (np.abs, lambda x, y: np.sign(x)), 3: (lambda x: x * x, lambda x, y: 2 * x),
+    4: (np.exp, lambda x, y: y), 5: (np.log, lambda x, y: 1 / x), 6: (np.tanh, lambda x, y: 1 - y * y),
+    7: (lambda x: 1 / (1 + np.exp(-x)), lambda x, y: y * (1 - y)), 8: (np.sqrt, lambda x, y: 1 / (2 * y)),
+    9: (np.sin, lambda x, y: np.cos(x)), 10: (np.cos, lambda x, y: -np.sin(x)),
+    11: (np.tan, lambda x, y: 1 + y * y), 12: (np.sinh, lambda x, y: np.cosh(x)),
+    13: (np.cosh, lambda x, y: np.sinh(x)), 14: (np.arcsin, lambda x, y: 1 / np.sqrt(1 - x * x)),
+    15: (np.arccos, lambda x, y: -1 / np.sqrt(1 - x * x)), 16: (np.arctan, lambda x, y: 1 / (1 + x * x)),
+    17: (np.arcsinh, lambda x, y: 1 / np.sqrt(1 + x * x)), 18: (np.arccosh, lambda x, y: 1 / np.sqrt(x * x - 1)),
+    19: (np.arctanh, lambda x, y: 1 / (1 - x * x)), 20: (np.exp2, lambda x, y: y * np.log(2.0)),
+    21: (lambda x: 10.0 ** x, lambda x, y: y * np.log(10.0)), 22: (np.expm1, lambda x, y: 1 + y),
+    23: (np.log2, lambda x, y: 1 / (np.log(2.0) * x)), 24: (np.log10, lambda x, y: 1 / (np.log(10.0) * x)),
+    25: (np.log1p, lambda x, y: 1 / (1 + x)), 26: (np.cbrt, lambda x, y: 1 / (3 * y * y)),
+    27: (np.sign, lambda x, y: 0.0), 28: (lambda x: np.maximum(x, 0), lambda x, y: (x >= 0).astype(x.dtype)),
+    29: (np.ones_like, lambda x, y: 0.0),
+}
+_B = {
+    0: np.add, 1: np.subtract, 2: np.multiply, 3: np.divide, 4: np.maximum, 5: np.minimum, 6: np.power,
+    7: lambda a, b: (a == b), 8: lambda a, b: (a < b), 9: lambda a, b: (a <= b), 10: lambda a, b: (a > b),
+    11: lambda a, b: (a >= b), 12: np.arctan2, 13: np.hypot,
+}
+
+
+_BLOCKS = {}   # shared by all instances: late finalizers of an earlier test must find their own block
+
+
+class FakeLib:
+    def __init__(self, allreduce=None):
+        self.blocks = _BLOCKS
+        self.launches = 0
+        self.err = b""
+        self.allreduce = allreduce
+        self.nranks = 1
+
+    # ---- helpers
+    def _fail(self, code, msg):
+        self.err = msg.encode()
+        return code
+
+    def _view(self, ptr, strides, shape, dtype):
+        """Strided (possibly broadcast) view of an operand over the collapsed shape."""
+        strides = [int(s) for s in strides][:len(shape)]
+        span = 1 + sum((e - 1) * s for e, s in zip(shape, strides))
+        flat = _arr(ptr, span, dtype)
+        return np.lib.stride_tricks.as_strided(flat, shape=shape, strides=[s * flat.itemsize for s in strides])
+
+    # ---- lifecycle / memory
+    def ag_init(self, dev): return 0
+    def ag_shutdown(self): return 0
+    def ag_sync(self): return 0
+
+    def ag_last_error(self, buf, n):
+        buf.value = self.err[:n - 1]
+        return 0
+
+    def ag_launch_count(self, ref):
+        _out(ref).value = self.launches
+        return 0
+
+    def ag_alloc(self, nbytes, ref):
+        b = C.create_string_buffer(max(int(nbytes), 1) + 64)
+        addr = (C.addressof(b) + 63) & ~63
+        self.blocks[addr] = b
+        _out(ref).value = addr
+        return 0
+
+    def ag_free(self, p):
+        self.blocks.pop(_p(p), None)
+        return 0
+
+    ag_host_alloc = ag_alloc
+    ag_host_free = ag_free
+
+    def _copy(self, dst, src, nbytes):
+        C.memmove(_p(dst), _p(src), int(nbytes))
+        return 0
+
+    ag_copy_h2d = ag_copy_d2h = ag_copy_d2h_async = ag_copy_d2d = _copy
+
+    def ag_fill(self, dst, n, dtype, v):
+        _arr(dst, n, _DT[dtype])[:] = v
+        return 0
+
+    def ag_event_create(self, ref):
+        _out(ref).value = 1
+        return 0
+
+    def ag_event_record(self, ev): return 0
+
+    def ag_event_elapsed_ms(self, a, b, ref):
+        _out(ref).value = 0.0
+        return 0
+
+    def ag_event_destroy(self, ev): return 0
+    def ag_graph_begin(self): return self._fail(5, "fake ABI: no graphs")
+
+    # ---- elementwise
+    def ag_unary_fwd(self, op, dtype, x, y, n):
+        self.launches += 1
+        with np.errstate(all="ignore"):
+            _arr(y, n, _DT[dtype])[:] = _U[op][0](_arr(x, n, _DT[dtype]))
+        return 0
+
+    def ag_unary_bwd(self, op, dtype, dy, mode, dys, x, y, dx, n):
+        self.launches += 1
+        T = _DT[dtype]
+        d = _arr(dy, n, T) if mode == 0 else (_arr(dy, 1, T)[0] if mode == 1 else T(dys))
+        xv = _arr(x, n, T) if _p(x) else np.zeros(n, T)
+        yv = _arr(y, n, T) if _p(y) else np.zeros(n, T)
+        with np.errstate(all="ignore"):
+            _arr(dx, n, T)[:] = d * _U[op][1](xv, yv)
+        return 0
+
+    def _operand(self, p, imm, strides, shape, T):
+        if not _p(p):
+            return T(imm)
+        return self._view(p, strides, shape, T)
+
+    def ag_binary_fwd(self, op, dtype, a, ai, ast, b, bi, bst, y, nd, shape):
+        self.launches += 1
+        T = _DT[dtype]
+        shape = [int(s) for s in shape][:nd]
+        if nd > 4:
+            return self._fail(5, "ndims>4")
+        av, bv = self._operand(a, ai, ast, shape, T), self._operand(b, bi, bst, shape, T)
+        with np.errstate(all="ignore"):
+            r = np.broadcast_to(_B[op](av, bv), shape).astype(T)
+        _arr(y, int(np.prod(shape)), T)[:] = r.reshape(-1, order="F")
+        return 0
+
+    def ag_binary_bwd(self, op, argno, dtype, dy, dyst, x1, x1i, x1st, x2, x2i, x2st, y, yst, dx, nd, shape):
+        self.launches += 1
+        T = _DT[dtype]
+        shape = [int(s) for s in shape][:nd]
+        d = self._view(dy, dyst, shape, T)
+        a, b = self._operand(x1, x1i, x1st, shape, T), self._operand(x2, x2i, x2st, shape, T)
+        yv = self._view(y, yst, shape, T) if _p(y) else None
+        with np.errstate(all="ignore"):
+            if op == 0: r = d * 1
+            elif op == 1: r = d * (1 if argno == 1 else -1)
+            elif op == 2: r = d * (b if argno == 1 else a)
+            elif op == 3: r = d / b if argno == 1 else -d * a / (b * b)
+            elif op in (4, 5): r = d * (yv == (a if argno == 1 else b))
+            elif op == 6: r = d * b * np.power(a, b - 1) if argno == 1 else d * yv * np.log(a)
+            elif op == 12: r = d * b / (a * a + b * b) if argno == 1 else d * (-a) / (a * a + b * b)
+            elif op == 13: r = d * (a if argno == 1 else b) / yv
+            else: return self._fail(5, "zerograd op")
+        r = np.broadcast_to(r, shape).astype(T)
+        _arr(dx, int(np.prod(shape)), T)[:] = r.reshape(-1, order="F")
+        return 0
+
+    # ---- reductions
+    @staticmethod
+    def _map(m, v):
+        return v if m == 0 else (v * v if m == 1 else np.abs(v))
+
+    def ag_sum_all(self, m, dtype, x, n, out):
+        return self.ag_sum_dim(m, dtype, x, 1, n, 1, out)
+
+    def ag_sum_dim(self, m, dtype, x, inner, red, outer, out):
+        self.launches += 1
+        T = _DT[dtype]
+        v = _arr(x, inner * red * outer, T).reshape((inner, red, outer), order="F")
+        r = self._map(m, v.astype(np.float64)).sum(axis=1)
+        _arr(out, inner * outer, T)[:] = r.astype(T).reshape(-1, order="F")
+        return 0
+
+    def ag_add(self, dtype, a, b, out, n):
+        self.launches += 1
+        T = _DT[dtype]
+        _arr(out, n, T)[:] = _arr(a, n, T) + _arr(b, n, T)
+        return 0
+
+    def ag_axpy(self, dtype, alpha, x, y, n):
+        self.launches += 1
+        T = _DT[dtype]
+        yv = _arr(y, n, T)
+        yv[:] = yv + T(alpha) * _arr(x, n, T)
+        return 0
+
+    def ag_scale(self, dtype, alpha, x, n):
+        self.launches += 1
+        T = _DT[dtype]
+        xv = _arr(x, n, T)
+        xv[:] = xv * T(alpha)
+        return 0
+
+    # ---- gemm
+    def ag_gemm(self, dtype, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cp, ldc):
+        self.launches += 1
+        T = _DT[dtype]
+
+        def mat(p, rows, cols, ld):
+            flat = _arr(p, ld * cols, T)
+            return np.lib.stride_tricks.as_strided(flat, (rows, cols), (flat.itemsize, ld * flat.itemsize))
+        a = mat(A, K, M, lda).T if ta else mat(A, M, K, lda)
+        b = mat(B, N, K, ldb).T if tb else mat(B, K, N, ldb)
+        c = mat(Cp, M, N, ldc)
+        r = alpha * (a.astype(np.float64) @ b.astype(np.float64))
+        c[:] = (r + (beta * c if beta != 0 else 0)).astype(T)
+        return 0
+
+    def ag_gemm_set_engine(self, e): return 0
+
+    def ag_gemm_last_engine(self, buf, n):
+        buf.value = b"fake"
+        return 0
+
+    # ---- indexing
+    def ag_gather(self, dtype, x, idx, out, n):
+        self.launches += 1
+        T = _DT[dtype]
+        ii = _arr(idx, n, np.int64)
+        src = _arr(x, int(ii.max()) + 1 if n else 0, T)
+        _arr(out, n, T)[:] = src[ii]
+        return 0
+
+    def ag_gather_cols(self, dtype, x, rows, col, out, nc):
+        self.launches += 1
+        T = _DT[dtype]
+        cc = _arr(col, nc, np.int64)
+        src = _arr(x, rows * (int(cc.max()) + 1), T).reshape((rows, -1), order="F")
+        _arr(out, rows * nc, T)[:] = src[:, cc].reshape(-1, order="F")
+        return 0
+
+    def ag_scatter_add(self, dtype, dest, dest_len, idx, vals, n, block):
+        self.launches += 1
+        T = _DT[dtype]
+        ii = _arr(idx, n, np.int64)
+        if n and (ii.min() < 0 or (ii.max() + 1) * block > dest_len):
+            return self._fail(1, "BoundsError")
+        d = _arr(dest, dest_len, T).reshape((block, -1), order="F")
+        v = _arr(vals, n * block, T).reshape((block, n), order="F")
+        np.add.at(d, (slice(None), ii), v)
+        return 0
+
+    def ag_slab_copy(self, dtype, src, sred, soff, dst, dred, doff, inner, ln, outer):
+        self.launches += 1
+        T = _DT[dtype]
+        s = _arr(src, inner * sred * outer, T).reshape((inner, sred, outer), order="F")
+        d = _arr(dst, inner * dred * outer, T).reshape((inner, dred, outer), order="F")
+        d[:, doff:doff + ln, :] = s[:, soff:soff + ln, :]
+        return 0
+
+    def ag_transpose(self, dtype, x, rows, cols, out):
+        self.launches += 1
+        T = _DT[dtype]
+        s = _arr(x, rows * cols, T).reshape((rows, cols), order="F")
+        _arr(out, rows * cols, T)[:] = s.T.reshape(-1, order="F")
+        return 0
+
+    # ---- comm: the collective is delegated to the test (gloo) through `allreduce`
+    def ag_comm_unique_id(self, idbuf):
+        return 0
+
+    def ag_comm_init(self, nranks, rank, idbuf):
+        self.nranks = nranks
+        return 0
+
+    def ag_comm_destroy(self): return 0
+
+    def ag_allreduce_sum(self, dtype, buf, n):
+        if self.nranks > 1:
+            v = _arr(buf, n, _DT[dtype])
+            v[:] = self.allreduce(v)
+        return 0
+
+
+def install(ag, fake=None):
+    """Swap the ctypes library object inside the product modules for the numpy stand-in."""
+    import sys
+    fake = fake or FakeLib()
+    saved = {}
+    for name in ("agb200._lib", "agb200.darray", "agb200.graph", "agb200.comm"):
+        mod = sys.modules[name]
+        saved[name] = mod.lib
+        mod.lib = fake
+    D = sys.modules["agb200.darray"]
+    saved_sync = D._initialised[0]
+    D._initialised[0] = True
+
+    def restore():
+        for name, l in saved.items():
+            sys.modules[name].lib = l
+        D._initialised[0] = saved_sync
+    return fake, restore

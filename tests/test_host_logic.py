@@ -1,0 +1,217 @@
+"""CPU tests of the HOST side of the product (tape runtime, rule dispatch, stride collapsing, index
+bookkeeping) against the oracle, with the C ABI replaced by tests/fake_abi.py.  The real kernels are
+checked by the -m gpu tests."""
+import numpy as np
+import pytest
+
+
+def to_dev(ag, a):
+    return ag.DArray.from_numpy(a)
+
+
+def relerr(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
+
+
+def run_both(hostlib, oracle, loss, params_np, consts_np, dtype):
+    """loss(m, params, *consts) on oracle (float64) and on the device path; returns (loss, grads) x2."""
+    ag = hostlib
+    po = [oracle.Param(np.asfortranarray(p.astype(np.float64))) for p in params_np]
+    co = [np.asfortranarray(c.astype(np.float64)) if isinstance(c, np.ndarray) and c.dtype.kind == "f" else c
+          for c in consts_np]
+    to = oracle.diff(lambda: loss(oracle, po, *co))
+    go = [oracle.full(oracle.grad(to, p)) for p in po]
+    pd = [ag.Param(to_dev(ag, p.astype(dtype))) for p in params_np]
+    cd = [to_dev(ag, c.astype(dtype)) if isinstance(c, np.ndarray) and c.dtype.kind == "f" else c
+          for c in consts_np]
+    td = ag.diff(lambda: loss(ag, pd, *cd))
+    gd = [ag.full(ag.grad(td, p)) for p in pd]
+    gd = [None if g is None else (g if isinstance(g, float) else g.to_numpy()) for g in gd]
+    return float(oracle.value(to)), go, float(ag.value(td)), gd
+
+
+def test_readme_known_answer(hostlib):
+    ag = hostlib
+    x = ag.Param(to_dev(ag, np.array([1.0, 2.0, 3.0])))
+    t = ag.diff(lambda: ag.sumabs2(x))
+    assert float(ag.value(t)) == 14.0
+    assert np.array_equal(ag.grad(t, x).to_numpy(), [2.0, 4.0, 6.0])
+    g = ag.grad(lambda v: ag.sum_(ag.pow_(v, 2)))(to_dev(ag, np.array([[1.0, 2.0], [3.0, 4.0]])))
+    assert np.array_equal(g.to_numpy(), [[2.0, 4.0], [6.0, 8.0]])
+
+
+def test_tape_order_matches_readme(hostlib):
+    """README.md:116-125 pins the node order of sum(abs2, w*x .+ b - y)."""
+    ag = hostlib
+    rng = np.random.default_rng(0)
+    w = ag.Param(to_dev(ag, rng.standard_normal((1, 3))))
+    b = ag.Param(to_dev(ag, np.zeros((1, 1))))
+    x, y = to_dev(ag, rng.standard_normal((3, 4))), to_dev(ag, rng.standard_normal((1, 4)))
+    t = ag.diff(lambda: ag.sumabs2(ag.sub(ag.add(ag.matmul(w, x), b), y)))
+    names = [("P" if isinstance(n.Value, ag.Param) else n.Value.func.name) for n in t.list]
+    assert names == ["P", "*", "P", "+", "-", "sum(abs2,·)"]
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_housing(hostlib, oracle, dtype, tol):
+    W = hostlib.workloads
+    w, x, y = W.housing_init(np.random.default_rng(1))
+    lo, go, ld, gd = run_both(hostlib, oracle, W.housing_loss, w, [x, y], dtype)
+    assert abs(lo - ld) <= tol * 10 * max(abs(lo), 1)
+    for a, b in zip(gd, go):
+        assert relerr(a, b) <= tol * 10
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_mnist_mlp(hostlib, oracle, dtype, tol):
+    W = hostlib.workloads
+    w, x, y = W.mnist_init(np.random.default_rng(2), 100)
+    lo, go, ld, gd = run_both(hostlib, oracle, W.mnist_loss, w, [x, y], dtype)
+    assert abs(lo - ld) <= tol * 10 * max(abs(lo), 1)
+    for a, b in zip(gd, go):
+        assert a.shape == b.shape
+        assert relerr(a, b) <= tol * 10
+
+
+def test_sweep(hostlib, oracle):
+    W = hostlib.workloads
+    x, brow, bcol = W.sweep_init(np.random.default_rng(3), 64, 48)
+
+    def loss(m, p):
+        return W.sweep_loss(m, p[0], p[1], p[2])
+    lo, go, ld, gd = run_both(hostlib, oracle, loss, [x, brow, bcol], [], np.float64)
+    assert abs(lo - ld) <= 1e-11 * abs(lo)
+    for a, b in zip(gd, go):
+        assert a.shape == b.shape and relerr(a, b) <= 1e-11
+
+
+def test_lstm_small(hostlib, oracle):
+    W = hostlib.workloads
+    rng = np.random.default_rng(4)
+    H, E, V, B, T = 16, 8, 12, 6, 3
+    w = W.lstm_init(rng, H, E, V, np.float64)
+    keys = list(w)
+    ids = [rng.integers(0, V, B) for _ in range(T)]
+    ids[0][1] = ids[0][0]                       # repeated index inside one step
+    tg = []
+    for t in range(T):
+        oh = np.zeros((V, B))
+        oh[rng.integers(0, V, B), np.arange(B)] = 1
+        tg.append(np.asfortranarray(oh))
+    h0, c0 = np.zeros((H, B)), np.zeros((H, B))
+
+    def loss(m, p, h0, c0, *tg):
+        return W.lstm_loss(m, dict(zip(keys, p)), ids, list(tg), h0, c0)
+    lo, go, ld, gd = run_both(hostlib, oracle, loss, [w[k] for k in keys], [h0, c0] + tg, np.float64)
+    assert abs(lo - ld) <= 1e-11 * abs(lo)
+    for k, a, b in zip(keys, gd, go):
+        assert a.shape == b.shape, k
+        assert relerr(a, b) <= 1e-11, k
+
+
+def test_sparse_known_answer(hostlib):
+    """test/sparse.jl:7-16."""
+    ag = hostlib
+    z = to_dev(ag, np.zeros((3, 4)))
+    one2 = to_dev(ag, np.array([1.0, 1.0]))
+    a = ag.Sparse(z, [one2, one2, 1.0, 1.0], [([0, 1],), (range(2, 4),), (1, 1), (0,)])
+    fa = a.full().to_numpy()
+    exp = np.zeros(12)
+    exp[:5] = [2, 1, 1, 1, 1]
+    assert np.array_equal(fa.reshape(-1, order="F"), exp)
+    assert np.array_equal((a + a).full().to_numpy(), 2 * fa)
+    assert isinstance(ag.addto(a, a), ag.Sparse)
+
+
+def test_flat_dest_matches_oracle(hostlib, oracle):
+    """Index bookkeeping must be bit-exact: every index kind of test/getindex.jl:8-26."""
+    ag = hostlib
+    shape = (3, 4)
+    mask = np.zeros(shape, bool)
+    mask[1, 2] = mask[0, 0] = True
+    kinds = [(slice(None),), (0,), (range(0, 2),), (range(0, 3, 2),), ([0, 1],), ([1, 1],), ([],),
+             (mask,), (slice(None), 1), (1, slice(None)), ([0, 2], [1, 1, 3]), (np.array([[0, 1], [2, 2]]),),
+             ((1, 2),), (slice(None), np.array([True, False, True, False]))]
+    for idx in kinds:
+        d1, s1 = ag.flat_dest(shape, idx)
+        d2, s2 = oracle.flat_dest(shape, idx)
+        assert s1 == s2 and d1.dtype == np.int64 and np.array_equal(d1, d2), idx
+
+
+def test_getindex_grads(hostlib, oracle):
+    ag = hostlib
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 4))
+    for idx in [(slice(None), [1, 1, 3]), ([1, 1],), (range(0, 2), 2), (slice(None), 1), (5,)]:
+        go = oracle.grad(lambda v: oracle.sumabs2(oracle.getindex(v, *idx)))(np.asfortranarray(x.copy()))
+        gd = ag.grad(lambda v: ag.sumabs2(ag.getindex(v, *idx)))(to_dev(ag, x))
+        assert relerr(gd.to_numpy(), go) <= 1e-14, idx
+
+
+def test_highorder_tanh(hostlib):
+    """test/highorder.jl:33-34 on a 1-element device array."""
+    ag = hostlib
+    x = to_dev(ag, np.array([1.0]))
+    g1 = ag.grad(lambda v: ag.sum_(ag.tanh(v)))
+    g2 = ag.grad(lambda v: ag.sum_(g1(v)))
+    t = np.tanh(1.0)
+    assert abs(g1(x).to_numpy()[0] - (1 - t * t)) < 1e-15
+    assert abs(g2(x).to_numpy()[0] - (-2 * t * (1 - t * t))) < 1e-15
+
+
+def test_neuralnet_hessian_vs_oracle(hostlib, oracle):
+    """test/neuralnet.jl + test/highorder.jl:36-42: grad of (sum of squared grad) through relu MLP."""
+    rng = np.random.default_rng(6)
+    w1, w2 = rng.standard_normal((5, 4)), rng.standard_normal((2, 5))
+    x, y = rng.standard_normal((4, 7)), rng.standard_normal((2, 7))
+
+    def make(m, dev):
+        X, Y, W2 = dev(x), dev(y), dev(w2)
+
+        def loss(w):
+            return m.sumabs2(m.sub(m.matmul(W2, m.tanh(m.matmul(w, X))), Y))
+        inner = m.grad(loss)
+        return m.grad(lambda w: m.sumabs2(inner(w)))
+    go = make(oracle, lambda a: np.asfortranarray(a.copy()))(np.asfortranarray(w1.copy()))
+    gd = make(hostlib, lambda a: to_dev(hostlib, a))(to_dev(hostlib, w1))
+    assert relerr(gd.to_numpy(), go) <= 1e-12
+
+
+def test_unbroadcast_shapes(hostlib, oracle):
+    """test/base.jl:46-58 shapes: (2,3,5) with (1,3,5), (2,3,5,4) with (2,3,1,4), vectors."""
+    rng = np.random.default_rng(7)
+    for sa, sb in [((2, 3, 5), (1, 3, 5)), ((2, 3, 5, 4), (2, 3, 1, 4)), ((4, 6), (4,)), ((4, 6), (1, 6)),
+                   ((4, 6), (1, 1)), ((3,), (3, 5))]:
+        a, b = rng.standard_normal(sa), rng.standard_normal(sb)
+        for name in ("add", "sub", "mul", "div", "max_", "min_"):
+            def loss(m, p):
+                return m.sumabs2(getattr(m, name)(p[0], p[1]))
+            lo, go, ld, gd = run_both(hostlib, oracle, loss, [a, b], [], np.float64)
+            assert abs(lo - ld) <= 1e-12 * max(abs(lo), 1), (name, sa, sb)
+            for u, v in zip(gd, go):
+                assert np.shape(u) == np.shape(v), (name, sa, sb)
+                assert relerr(u, v) <= 1e-12, (name, sa, sb)
+
+
+def test_gradcheck_unary(hostlib):
+    ag = hostlib
+    rng = np.random.default_rng(8)
+    x = rng.uniform(0.2, 0.8, (3, 2))
+    for name in ["exp", "log", "tanh", "sigm", "sqrt", "sin", "cos", "tan", "sinh", "cosh", "asin", "acos",
+                 "atan", "asinh", "atanh", "exp2", "exp10", "expm1", "log2", "log10", "log1p", "cbrt", "abs_",
+                 "abs2", "neg"]:
+        assert ag.gradcheck(getattr(ag, name), to_dev(ag, x)), name
+    assert ag.gradcheck(ag.acosh, to_dev(ag, x + 1.5))
+
+
+def test_cat(hostlib, oracle):
+    rng = np.random.default_rng(9)
+    a, b = rng.standard_normal((2, 3)), rng.standard_normal((4, 3))
+
+    def loss(m, p):
+        return m.sumabs2(m.mul(m.vcat(p[0], p[1]), 2.0))
+    lo, go, ld, gd = run_both(hostlib, oracle, loss, [a, b], [], np.float64)
+    assert abs(lo - ld) <= 1e-12 * abs(lo)
+    for u, v in zip(gd, go):
+        assert relerr(u, v) <= 1e-13
