@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: `@diff`+`grad` steps/sec and backward HBM GB/s on the MNIST-shape MLP
+(examples/mnist.jl, 784-64-10, Float32) at batch 65536 per GPU, data-parallel over N B200s.
+
+One "step" = forward recording + backward sweep (+ NCCL allreduce of the Param gradients when N > 1) +
+axpy! update of all four Params, on one 65536-column batch shard per rank (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`--impl reference` times the CPU restatement of the reference (oracle/agref.py, numpy + OpenBLAS on
+all host threads; Julia is not installed in this image) on the same config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 65536
+LR = 0.1
+METRIC = "@diff+grad steps/sec (MNIST-shape MLP 784-64-10, Float32, batch 65536 per GPU)"
+UNIT = "steps/s"
+
+
+def algo_bytes(B, s=4):
+    """Algorithmic bytes of the unfused tape: (forward, backward)."""
+    N1, N2, NX = 64 * B, 10 * B, 784 * B
+    return s * (NX + 6 * N1 + 12 * N2 + 4 * B), s * (15 * N2 + 5 * B + 7 * N1 + NX)
+
+
+class Clocks:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if (t0 is None or ts >= t0 - 0.05) and (t1 is None or ts <= t1 + 0.15)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(steps, warmup, budget_s=20.0):
+    """The CPU restatement of the reference on the host cores: same tape, same temporaries."""
+    from oracle import agref
+    import __graft_entry__ as ge
+    W = ge.load_package().workloads        # workload definitions only (pure Python, no device call)
+    rng = np.random.default_rng(1)
+    w, _, _ = W.mnist_init(rng, 1)
+    _, x, y = W.mnist_init(np.random.default_rng(1000), BATCH)
+    params = [agref.Param(np.asfortranarray(a)) for a in w]
+
+    def step():
+        tape = agref.diff(lambda: W.mnist_loss(agref, params, x, y))
+        for p in params:
+            agref.axpy(-LR, agref.grad(tape, p), p)
+        return float(agref.value(tape))
+    for _ in range(warmup):
+        step()
+    times, t_start = [], time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 3:
+            break
+    mean = sum(times) / len(times)
+    return {"value": 1.0 / mean, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d full steps (forward+backward+axpy!) at batch %d Float32, numpy/OpenBLAS, all host threads"
+                      % (len(times), BATCH), "ms_per_step": mean * 1e3}, len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cb, done = cpu_reference_run(args.steps, min(args.warmup, 2), budget_s=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "examples/mnist.jl MLP 784-64-10 softmax, batch 65536, Float32, "
+                                   "@diff + grad + axpy! (CPU restatement of the reference; Julia absent)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="agb200")
+    ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    W_ = max(args.warmup, 3)
+    K = args.steps
+    B = args.batch
+
+    import __graft_entry__ as ge
+    ag = ge.load_package()
+    ag.init(local)
+    Wl = ag.workloads
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+        def bcast(payload):
+            obj = [payload]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+        dp = ag.DataParallel(rank, world, bcast)
+    else:
+        dp = ag.DataParallel(0, 1)
+
+    def barrier():
+        ag.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # identical Params on every rank, per-rank batch shard
+    w_np, _, _ = Wl.mnist_init(np.random.default_rng(1), 1)
+    _, x_np, y_np = Wl.mnist_init(np.random.default_rng(1000 + rank), B)
+    params = [ag.Param(ag.DArray.from_numpy(a)) for a in w_np]
+    xd, yd = ag.DArray.empty(x_np.shape, np.float32), ag.DArray.empty(y_np.shape, np.float32)
+    xh, yh = ag.pinned_empty(x_np.shape, np.float32), ag.pinned_empty(y_np.shape, np.float32)
+    xh[...] = x_np
+    yh[...] = y_np
+    loss_h = ag.pinned_empty((1,), np.float32)
+    xd.copy_from_host(xh.host_ptr, xh.nbytes)
+    yd.copy_from_host(yh.host_ptr, yh.nbytes)
+    ag.sync()
+    gB = B * world
+    state = {}
+
+    def fwd_bwd():
+        t = ag.diff(lambda: Wl.mnist_loss(ag, params, xd, yd, global_batch=gB))
+        state["loss"] = ag.value(t)
+        state["grads"] = [ag.grad(t, p) for p in params]
+        return t
+
+    def exchange():
+        state["grads"] = dp.allreduce_grads(state["grads"])
+
+    def update():
+        for p, g in zip(params, state["grads"]):
+            ag.axpy(-LR, g, p)
+
+    def eager_step():
+        fwd_bwd()
+        exchange()
+        update()
+
+    # eager warm-up populates the pool / workspace, then capture the step
+    for _ in range(2):
+        eager_step()
+    ag.sync()
+    if world == 1:
+        with ag.StepGraph() as g_all:
+            eager_step()
+        graphs = [g_all]
+
+        def step():
+            g_all.launch()
+    else:
+        with ag.StepGraph() as g_a:
+            fwd_bwd()
+        pre = state["grads"]
+        exchange()                       # eager once: fixes the bucket views
+        with ag.StepGraph() as g_b:
+            update()
+        graphs = [g_a, g_b]
+
+        def step():
+            g_a.launch()
+            state["grads"] = pre
+            exchange()
+            g_b.launch()
+
+    for _ in range(W_):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident inputs (x = 205 MB > 126 MB L2, so no L2 flush needed)
+    clocks = Clocks(local)
+    time.sleep(0.3)
+    l0 = ag.launch_count()
+    e0, e1 = ag.Event(), ag.Event()
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    ms = e1.elapsed_ms_since(e0)
+    barrier()
+    t_wall1 = time.time()
+    launches = ag.launch_count() - l0
+    clk = clocks.stop(t_wall0, t_wall1)
+
+    # ---- forward / backward split (two graphs, events between them), N-independent
+    with ag.StepGraph() as g_f:
+        loss_t = Wl.mnist_loss(ag, [p.value for p in params], xd, yd, global_batch=gB)
+    ef0, ef1 = ag.Event(), ag.Event()
+    ef0.record()
+    for _ in range(K):
+        g_f.launch()
+    ef1.record()
+    fwd_ms = ef1.elapsed_ms_since(ef0) / K
+    g_f.destroy()
+
+    # ---- end to end through the public API with HOST buffers: h2d of the batch + step + d2h of the loss
+    C_ = __import__("ctypes")
+
+    def e2e_step():
+        xd.copy_from_host(xh.host_ptr, xh.nbytes)
+        yd.copy_from_host(yh.host_ptr, yh.nbytes)
+        step()
+        ag._lib.check(ag._lib.lib.ag_copy_d2h(C_.c_void_p(loss_h.host_ptr), C_.c_void_p(state["loss"].ptr), 4))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    Ke = max(3, min(K, 20))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    ag.sync()
+    e2e_s = (time.perf_counter() - t0) / Ke
+    barrier()
+
+    # ---- dominant kernel, timed alone on the library stream (inputs > L2)
+    cand = {}
+    a1 = ag.matmul(params[0].value, xd)
+    dy1 = ag.DArray.empty(a1.shape, np.float32)
+    ag._lib.check(ag._lib.lib.ag_fill(C_.c_void_p(dy1.ptr), dy1.size, 0, 0.001))
+
+    def time_op(fn, reps=max(5, min(K, 30))):
+        for _ in range(3):
+            fn()
+        a, b = ag.Event(), ag.Event()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        return b.elapsed_ms_since(a) / reps
+    s = 4
+    cand["gemm_fwd w1*x (64x784 * 784xB, NN)"] = (time_op(lambda: ag.matmul(params[0].value, xd)),
+                                                   s * (64 * 784 + 784 * B + 64 * B), 2.0 * 64 * 784 * B)
+    eng_f = ag.gemm_engine()
+    cand["gemm_dw1 dy*x' (64xB * Bx784, NT)"] = (time_op(lambda: ag.matmul(dy1, ag.adjoint(xd))),
+                                                  s * (64 * B + 784 * B + 64 * 784), 2.0 * 64 * 784 * B)
+    eng_b = ag.gemm_engine()
+    top = max(cand, key=lambda k: cand[k][0])
+    t_ms, bytes_, flops = cand[top]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"kernel": top, "engine": eng_b if "dw1" in top else eng_f, "bound": "hbm",
+                "achieved": bytes_ / (t_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_ / (t_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                "ms_per_launch": t_ms, "tflops": flops / (t_ms * 1e-3) / 1e12,
+                "all": {k: {"ms": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9} for k, v in cand.items()}}
+
+    # ---- max over ranks
+    ms_all, e2e_all = ms, e2e_s
+    if dist is not None:
+        import torch
+        tt = torch.tensor([ms, e2e_s, fwd_ms], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_all, e2e_all, fwd_ms = tt.tolist()
+    ms_per_step = ms_all / K
+    fb, bb = algo_bytes(B)
+    bwd_ms = max(ms_per_step - fwd_ms, 1e-9)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_run(1000, 1, budget_s=15.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": world * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W_, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "examples/mnist.jl MLP 784-64-10 softmax (configs[1]), batch %d per GPU, Float32, "
+                                   "@diff + grad + allreduce + axpy!; value counts one per-rank step per rank" % B,
+                       "global_batch": gB, "parallelism": "dp%d" % world, "replay": "CUDA graph",
+                       "l2": "inputs (x = %.0f MB per rank) larger than the 126 MB L2; no flush" % (x_np.nbytes / 1e6)},
+            "forward_ms": fwd_ms, "backward_update_ms": bwd_ms,
+            "backward_hbm_gbs": bb / (bwd_ms * 1e-3) / 1e9,
+            "step_hbm_gbs": (fb + bb) / (ms_per_step * 1e-3) / 1e9,
+            "algorithmic_bytes": {"forward": fb, "backward": bb},
+            "clocks": clk,
+            "e2e": {"value": world / e2e_all, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes + yh.nbytes),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_all * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    for g in graphs:
+        g.destroy()
+    if dist is not None:
+        dist.barrier()
+        dp.close()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

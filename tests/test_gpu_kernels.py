@@ -1,0 +1,246 @@
+"""GPU parity tests: every kernel family of libagb200.so, called through the C ABI (ctypes binding),
+against the numpy oracle on the same seeded inputs.  Tolerances (BASELINE.json north_star): Float32
+1e-5, Float64 1e-12, norm-wise against the float64 oracle; index bookkeeping bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: 1e-5, np.float64: 1e-12}
+
+
+def relerr(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0
+    return np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
+
+
+UNARY = ["neg", "abs_", "abs2", "exp", "log", "tanh", "sigm", "sqrt", "sin", "cos", "tan", "sinh", "cosh",
+         "asin", "acos", "atan", "asinh", "acosh", "atanh", "exp2", "exp10", "expm1", "log2", "log10", "log1p",
+         "cbrt"]
+NP_F = dict(neg=lambda x: -x, abs_=np.abs, abs2=lambda x: x * x, exp=np.exp, log=np.log, tanh=np.tanh,
+            sigm=lambda x: 1 / (1 + np.exp(-x)), sqrt=np.sqrt, sin=np.sin, cos=np.cos, tan=np.tan, sinh=np.sinh,
+            cosh=np.cosh, asin=np.arcsin, acos=np.arccos, atan=np.arctan, asinh=np.arcsinh, acosh=np.arccosh,
+            atanh=np.arctanh, exp2=np.exp2, exp10=lambda x: 10.0 ** x, expm1=np.expm1, log2=np.log2,
+            log10=np.log10, log1p=np.log1p, cbrt=np.cbrt)
+NP_G = dict(neg=lambda x, y: -1 + 0 * x, abs_=lambda x, y: np.sign(x), abs2=lambda x, y: 2 * x, exp=lambda x, y: y,
+            log=lambda x, y: 1 / x, tanh=lambda x, y: 1 - y * y, sigm=lambda x, y: y * (1 - y),
+            sqrt=lambda x, y: 1 / (2 * y), sin=lambda x, y: np.cos(x), cos=lambda x, y: -np.sin(x),
+            tan=lambda x, y: 1 + y * y, sinh=lambda x, y: np.cosh(x), cosh=lambda x, y: np.sinh(x),
+            asin=lambda x, y: 1 / np.sqrt(1 - x * x), acos=lambda x, y: -1 / np.sqrt(1 - x * x),
+            atan=lambda x, y: 1 / (1 + x * x), asinh=lambda x, y: 1 / np.sqrt(1 + x * x),
+            acosh=lambda x, y: 1 / np.sqrt(x * x - 1), atanh=lambda x, y: 1 / (1 - x * x),
+            exp2=lambda x, y: y * np.log(2), exp10=lambda x, y: y * np.log(10), expm1=lambda x, y: 1 + y,
+            log2=lambda x, y: 1 / (np.log(2) * x), log10=lambda x, y: 1 / (np.log(10) * x),
+            log1p=lambda x, y: 1 / (1 + x), cbrt=lambda x, y: 1 / (3 * y * y))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 1023, 4096, 100003])
+def test_unary_fwd_bwd(ag, dtype, n):
+    rng = np.random.default_rng(n)
+    x = rng.uniform(0.15, 0.85, n).astype(dtype)
+    dy = rng.standard_normal(n).astype(dtype)
+    for name in UNARY:
+        xx = x + 1.5 if name == "acosh" else x
+        x64, dy64 = xx.astype(np.float64), dy.astype(np.float64)
+        f = getattr(ag, name)
+        xd = ag.DArray.from_numpy(xx)
+        y = f(xd)
+        yref = NP_F[name](x64)
+        assert relerr(y.to_numpy(), yref) <= TOL[dtype], (name, "fwd")
+        # gradient through the tape: d/dx sum(dy .* f(x)) = dy .* g(x,y)
+        p = ag.Param(xd)
+        dyd = ag.DArray.from_numpy(dy)
+        t = ag.diff(lambda: ag.sum_(ag.mul(dyd, f(p))))
+        g = ag.grad(t, p).to_numpy()
+        gref = dy64 * NP_G[name](x64, yref)
+        assert relerr(g, gref) <= 4 * TOL[dtype], (name, "bwd")
+
+
+def test_unary_misaligned_view(ag):
+    """A reshape/slice view that is not 16-byte aligned must take the scalar path and stay correct."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(1001).astype(np.float32)
+    xd = ag.DArray.from_numpy(x)
+    v = ag.DArray(xd.buf, xd.ptr + 4, (1000,), xd.dtype)
+    assert relerr(ag.tanh(v).to_numpy(), np.tanh(x[1:].astype(np.float64))) <= 1e-6
+    assert relerr(ag.add(v, v).to_numpy(), 2 * x[1:].astype(np.float64)) == 0
+    assert relerr(ag.sum_(v).to_numpy(), x[1:].astype(np.float64).sum()) <= 1e-6
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_relu_ties(ag, dtype):
+    """max.(0,x): relu'(0) = 1 (src/math.jl:54)."""
+    x = np.array([-1.0, -0.0, 0.0, 2.0, 5.0, -3.0, 0.0, 1.0], dtype)
+    p = ag.Param(ag.DArray.from_numpy(x))
+    t = ag.diff(lambda: ag.sum_(ag.relu(p)))
+    assert np.array_equal(ag.grad(t, p).to_numpy(), np.array([0, 1, 1, 1, 1, 0, 1, 1], dtype))
+    a = ag.Param(ag.DArray.from_numpy(np.array([1.0, 2.0, 3.0], dtype)))
+    b = ag.Param(ag.DArray.from_numpy(np.array([1.0, 5.0, 0.0], dtype)))
+    t = ag.diff(lambda: ag.sum_(ag.max_(a, b)))
+    assert np.array_equal(ag.grad(t, a).to_numpy(), [1, 0, 1])
+    assert np.array_equal(ag.grad(t, b).to_numpy(), [1, 1, 0])
+
+
+SHAPES = [((2, 3, 5), (1, 3, 5)), ((2, 3, 5, 4), (2, 3, 1, 4)), ((64, 100), (64,)), ((10, 100), (1, 100)),
+          ((7, 9), (1, 1)), ((3,), (3, 5)), ((128, 257), (128, 257)), ((4, 1, 6), (1, 5, 1)), ((1000,), (1000,)),
+          ((5, 3, 2, 4, 3), (5, 3, 1, 4, 3))]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("sa,sb", SHAPES)
+def test_binary_broadcast_fwd_bwd(ag, oracle, dtype, sa, sb):
+    rng = np.random.default_rng(len(sa) * 100 + len(sb))
+    a = rng.uniform(0.5, 2.0, sa).astype(dtype)
+    b = rng.uniform(0.5, 2.0, sb).astype(dtype)
+    for name in ("add", "sub", "mul", "div", "max_", "min_", "pow_", "atan2", "hypot"):
+        if not hasattr(oracle, name):
+            continue
+        po = [oracle.Param(np.asfortranarray(a.astype(np.float64))), oracle.Param(np.asfortranarray(b.astype(np.float64)))]
+        to = oracle.diff(lambda: oracle.sumabs2(getattr(oracle, name)(po[0], po[1])))
+        pd = [ag.Param(ag.DArray.from_numpy(a)), ag.Param(ag.DArray.from_numpy(b))]
+        td = ag.diff(lambda: ag.sumabs2(getattr(ag, name)(pd[0], pd[1])))
+        lo, ld = float(oracle.value(to)), float(ag.value(td))
+        assert abs(lo - ld) <= 4 * TOL[dtype] * abs(lo), (name, sa, sb)
+        for q, r in zip(pd, po):
+            assert relerr(ag.grad(td, q).to_numpy(), oracle.grad(to, r)) <= 4 * TOL[dtype], (name, sa, sb)
+
+
+def test_binary_scalar_operands(ag):
+    x = np.linspace(-2, 2, 37).astype(np.float32)
+    xd = ag.DArray.from_numpy(x)
+    assert relerr(ag.mul(0.1, xd).to_numpy(), np.float32(0.1) * x) <= 1e-7
+    assert relerr(ag.sub(1, xd).to_numpy(), 1 - x) == 0
+    assert relerr(ag.div(xd, 4).to_numpy(), x / 4) == 0
+    assert np.array_equal(ag.relu(xd).to_numpy(), np.maximum(x, 0))
+    s = ag.sum_(xd)                                    # device scalar
+    assert s.shape == ()
+    assert relerr(ag.mul(xd, s).to_numpy(), x * x.sum(dtype=np.float64)) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 5, 4096, 4097, 1 << 20, (1 << 22) + 3])
+def test_sum_all(ag, dtype, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n).astype(dtype)
+    xd = ag.DArray.from_numpy(x)
+    x64 = x.astype(np.float64)
+    for f, ref in ((ag.sum_, x64.sum()), (ag.sumabs2, (x64 * x64).sum()), (ag.sumabs, np.abs(x64).sum())):
+        got = float(f(xd))
+        scale = np.abs(x64).sum() if f is ag.sum_ else abs(ref)
+        assert abs(got - ref) <= TOL[dtype] * max(scale, 1e-30), (f, n)
+
+
+RED = [((10, 1000), 0), ((10, 1000), 1), ((64, 5000), 1), ((64, 5000), 0), ((1, 777), 1), ((300, 50), 1),
+       ((1000, 33), 1), ((1000, 33), 0), ((100, 7, 13), 1), ((2, 3, 5), (0, 2)), ((2, 3, 5), (0, 1)),
+       ((6, 4, 5, 3), (1, 2)), ((5000, 3), 0), ((3, 100000), 1), ((100000, 3), 0), ((17, 1), 1)]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,dims", RED)
+def test_sum_dims(ag, dtype, shape, dims):
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal(shape).astype(dtype)
+    xd = ag.DArray.from_numpy(x)
+    ax = dims if isinstance(dims, tuple) else (dims,)
+    ref = x.astype(np.float64).sum(axis=ax, keepdims=True)
+    got = ag.sum_(xd, dims=dims).to_numpy()
+    absref = np.abs(x.astype(np.float64)).sum(axis=ax, keepdims=True)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / absref) <= TOL[dtype]
+    got2 = ag.sumabs2(xd, dims=dims).to_numpy()
+    assert relerr(got2, (x.astype(np.float64) ** 2).sum(axis=ax, keepdims=True)) <= TOL[dtype]
+
+
+GEMM = [(64, 784, 1000, 0, 0), (64, 1000, 784, 0, 1), (64, 10, 1000, 1, 0), (10, 64, 3000, 0, 1),
+        (1, 13, 506, 0, 0), (1, 506, 13, 0, 1), (130, 70, 33, 0, 0), (130, 70, 33, 1, 1), (5, 1, 7, 0, 0),
+        (512, 640, 256, 0, 0), (512, 256, 640, 0, 1), (640, 512, 256, 1, 0), (128, 128, 4096, 0, 1)]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("M,K,N,ta,tb", GEMM)
+def test_gemm(ag, dtype, M, K, N, ta, tb):
+    """op(A) (MxK) * op(B) (KxN); exercises NN forward, NT (dy*x') and TN (w'*dy) of src/base.jl:26."""
+    rng = np.random.default_rng(M * 7 + N)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(dtype)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(dtype)
+    ad, bd = ag.DArray.from_numpy(a), ag.DArray.from_numpy(b)
+    A = ag.adjoint(ad) if ta else ad
+    Bm = ag.adjoint(bd) if tb else bd
+    c = ag.matmul(A, Bm).to_numpy()
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    ref = (a64.T if ta else a64) @ (b64.T if tb else b64)
+    # norm-wise against the magnitude of the accumulated products
+    mag = (np.abs(a64.T if ta else a64) @ np.abs(b64.T if tb else b64)).max()
+    assert c.shape == ref.shape
+    assert np.max(np.abs(c - ref)) <= TOL[dtype] * mag, ag.gemm_engine()
+
+
+def test_gemm_vector_and_errors(ag):
+    rng = np.random.default_rng(1)
+    a, v = rng.standard_normal((5, 7)), rng.standard_normal(7)
+    r = ag.matmul(ag.DArray.from_numpy(a), ag.DArray.from_numpy(v))
+    assert r.shape == (5,) and relerr(r.to_numpy(), a @ v) <= 1e-14
+    with pytest.raises(ag.DimensionMismatch):
+        ag.matmul(ag.DArray.from_numpy(a), ag.DArray.from_numpy(a))
+    with pytest.raises(ag.DimensionMismatch):
+        ag.add(ag.DArray.from_numpy(a), ag.DArray.from_numpy(v))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_scatter_add_and_gather(ag, oracle, dtype):
+    rng = np.random.default_rng(3)
+    E, V, Bn, T = 32, 50, 64, 5
+    W = rng.standard_normal((E, V)).astype(dtype)
+    Wd = ag.DArray.from_numpy(W)
+    ids = [rng.integers(0, V, Bn) for _ in range(T)]
+    ids[0][:8] = 7                                     # heavy repeats
+    vals = [rng.standard_normal((E, Bn)).astype(dtype) for _ in range(T)]
+    # gather
+    assert np.array_equal(ag.getindex(Wd, slice(None), ids[0]).to_numpy(), W[:, ids[0]])
+    # Sparse with T blocks -> one batched scatter-add (column-block path)
+    sp = ag.Sparse(Wd, [ag.DArray.from_numpy(v) for v in vals], [(slice(None), i) for i in ids])
+    ref = oracle.full(oracle.Sparse(np.asfortranarray(W.astype(np.float64)),
+                                    [np.asfortranarray(v.astype(np.float64)) for v in vals],
+                                    [(slice(None), i) for i in ids]))
+    got = sp.full().to_numpy()
+    assert relerr(got, ref) <= TOL[dtype]
+    # determinism: bit-identical on repeat
+    assert np.array_equal(got, sp.full().to_numpy())
+    # untouched destinations stay exactly zero; touched set is bit-exact
+    assert np.array_equal(got != 0, ref != 0)
+    # generic (element-granular) path with mixed index kinds
+    x = rng.standard_normal((6, 7)).astype(dtype)
+    for idx in [([1, 1, 3], [0, 2]), ([5, 5, 5],), (range(0, 4, 2), slice(None)), (3, 4)]:
+        go = oracle.grad(lambda v: oracle.sumabs2(oracle.getindex(v, *idx)))(np.asfortranarray(x.astype(np.float64)))
+        gd = ag.grad(lambda v: ag.sumabs2(ag.getindex(v, *idx)))(ag.DArray.from_numpy(x))
+        assert relerr(gd.to_numpy(), go) <= TOL[dtype], idx
+
+
+def test_scatter_out_of_range_is_an_error(ag):
+    z = ag.zeros((4, 4), np.float32)
+    with pytest.raises(IndexError):
+        ag.Sparse(z, [ag.DArray.from_numpy(np.ones((4, 1), np.float32))], [(slice(None), [9])]).full()
+
+
+def test_cat_transpose_copy(ag):
+    rng = np.random.default_rng(4)
+    a, b = rng.standard_normal((128, 33)).astype(np.float32), rng.standard_normal((512, 33)).astype(np.float32)
+    ad, bd = ag.DArray.from_numpy(a), ag.DArray.from_numpy(b)
+    assert np.array_equal(ag.vcat(ad, bd).to_numpy(), np.vstack([a, b]))
+    assert np.array_equal(ag.hcat(ad, ad).to_numpy(), np.hstack([a, a]))
+    assert np.array_equal(ag.adjoint(bd).to_numpy(), b.T)
+    assert np.array_equal(ag.copy(ad).to_numpy(), a)
+    assert np.array_equal(ag.cat1d(ad, bd).to_numpy(), np.concatenate([a.reshape(-1, order="F"), b.reshape(-1, order="F")]))
+
+
+def test_axpy_and_fill(ag):
+    x = np.arange(1001, dtype=np.float32)
+    y = np.ones(1001, dtype=np.float32)
+    yd = ag.DArray.from_numpy(y)
+    ag.axpy(-0.5, ag.DArray.from_numpy(x), yd)
+    assert np.array_equal(yd.to_numpy(), y - np.float32(0.5) * x)
+    assert np.array_equal(ag.zeros((3, 5), np.float64).to_numpy(), np.zeros((3, 5)))

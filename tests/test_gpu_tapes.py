@@ -1,0 +1,218 @@
+"""GPU parity of whole tapes (forward + backward sweep + update) for the BASELINE.json configs against
+the oracle, plus size-independent properties at the full bench size."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
+
+
+def both(ag, oracle, loss, params_np, consts_np, dtype):
+    po = [oracle.Param(np.asfortranarray(p.astype(np.float64))) for p in params_np]
+    co = [np.asfortranarray(c.astype(np.float64)) if isinstance(c, np.ndarray) and c.dtype.kind == "f" else c
+          for c in consts_np]
+    to = oracle.diff(lambda: loss(oracle, po, *co))
+    go = [oracle.full(oracle.grad(to, p)) for p in po]
+    pd = [ag.Param(ag.DArray.from_numpy(p.astype(dtype))) for p in params_np]
+    cd = [ag.DArray.from_numpy(c.astype(dtype)) if isinstance(c, np.ndarray) and c.dtype.kind == "f" else c
+          for c in consts_np]
+    td = ag.diff(lambda: loss(ag, pd, *cd))
+    gd = [ag.full(ag.grad(td, p)).to_numpy() for p in pd]
+    return float(oracle.value(to)), go, float(ag.value(td)), gd
+
+
+def test_readme_known_answers(ag):
+    x = ag.Param(ag.DArray.from_numpy(np.array([1.0, 2.0, 3.0])))
+    t = ag.diff(lambda: ag.sumabs2(x))
+    assert float(ag.value(t)) == 14.0
+    assert np.array_equal(ag.grad(t, x).to_numpy(), [2.0, 4.0, 6.0])
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_housing(ag, oracle, dtype, tol):
+    W = ag.workloads
+    w, x, y = W.housing_init(np.random.default_rng(1))
+    lo, go, ld, gd = both(ag, oracle, W.housing_loss, w, [x, y], dtype)
+    assert abs(lo - ld) <= tol * abs(lo)
+    for a, b in zip(gd, go):
+        assert relerr(a, b) <= tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+@pytest.mark.parametrize("batch", [100, 4096])
+def test_mnist_mlp(ag, oracle, dtype, tol, batch):
+    W = ag.workloads
+    w, x, y = W.mnist_init(np.random.default_rng(2), batch)
+    lo, go, ld, gd = both(ag, oracle, W.mnist_loss, w, [x, y], dtype)
+    assert abs(lo - ld) <= tol * abs(lo)
+    for a, b in zip(gd, go):
+        assert relerr(a, b) <= tol
+
+
+def test_mnist_sgd_trajectory(ag, oracle):
+    """5 steps of @diff + grad + axpy! stay within tolerance of the oracle's trajectory."""
+    W = ag.workloads
+    w, x, y = W.mnist_init(np.random.default_rng(5), 512)
+    po = [oracle.Param(np.asfortranarray(p.astype(np.float64))) for p in w]
+    pd = [ag.Param(ag.DArray.from_numpy(p)) for p in w]
+    xo, yo = x.astype(np.float64), y.astype(np.float64)
+    xd, yd = ag.DArray.from_numpy(x), ag.DArray.from_numpy(y)
+    for _ in range(5):
+        to = oracle.diff(lambda: W.mnist_loss(oracle, po, xo, yo))
+        for p in po:
+            oracle.axpy(-0.1, oracle.grad(to, p), p)
+        td = ag.diff(lambda: W.mnist_loss(ag, pd, xd, yd))
+        for p in pd:
+            ag.axpy(-0.1, ag.grad(td, p), p)
+    assert abs(float(ag.value(td)) - float(oracle.value(to))) <= 1e-5 * abs(float(oracle.value(to)))
+    for a, b in zip(pd, po):
+        assert relerr(a.value.to_numpy(), b.value) <= 2e-5
+
+
+@pytest.mark.parametrize("rows,cols", [(1024, 1024), (64, 4096), (4096, 64)])
+def test_sweep(ag, oracle, rows, cols):
+    W = ag.workloads
+    x, brow, bcol = W.sweep_init(np.random.default_rng(3), rows, cols)
+    lo, go, ld, gd = both(ag, oracle, lambda m, p: W.sweep_loss(m, p[0], p[1], p[2]), [x, brow, bcol], [], np.float32)
+    assert abs(lo - ld) <= 1e-5 * abs(lo)
+    for a, b in zip(gd, go):
+        assert relerr(a, b) <= 1e-5
+
+
+def test_lstm(ag, oracle):
+    W = ag.workloads
+    rng = np.random.default_rng(4)
+    H, E, V, B, T = 64, 32, 40, 48, 4
+    w = W.lstm_init(rng, H, E, V, np.float32)
+    keys = list(w)
+    ids = [rng.integers(0, V, B) for _ in range(T)]
+    tg = []
+    for t in range(T):
+        oh = np.zeros((V, B), np.float32)
+        oh[rng.integers(0, V, B), np.arange(B)] = 1
+        tg.append(np.asfortranarray(oh))
+    h0, c0 = np.zeros((H, B), np.float32), np.zeros((H, B), np.float32)
+
+    def loss(m, p, h0, c0, *tg):
+        return W.lstm_loss(m, dict(zip(keys, p)), ids, list(tg), h0, c0)
+    lo, go, ld, gd = both(ag, oracle, loss, [w[k] for k in keys], [h0, c0] + tg, np.float32)
+    assert abs(lo - ld) <= 1e-5 * abs(lo)
+    for k, a, b in zip(keys, gd, go):
+        assert relerr(a, b) <= 2e-5, k
+
+
+def test_rnn_grad_of_grad(ag, oracle):
+    """Config 5 pattern (test/highorder.jl:36-42): d/dW_hh of sum(abs2, d loss / d W_hh)."""
+    W = ag.workloads
+    rng = np.random.default_rng(6)
+    H, V, B, T = 16, 10, 32, 3
+    w = W.rnn_init(rng, H, V, np.float64)
+    xs = []
+    for t in range(T):
+        oh = np.zeros((V, B))
+        oh[rng.integers(0, V, B), np.arange(B)] = 1
+        xs.append(np.asfortranarray(oh))
+    y = np.zeros((V, B))
+    y[rng.integers(0, V, B), np.arange(B)] = 1
+    h0 = np.zeros((H, B))
+
+    def make(m, dev):
+        wd = [dev(a) for a in w]
+        xd, yd, hd = [dev(a) for a in xs], dev(y), dev(h0)
+
+        def loss(whh):
+            return W.rnn_loss(m, [wd[0], whh, wd[2], wd[3], wd[4]], xd, yd, hd)
+        inner = m.grad(loss)
+        return m.grad(lambda whh: m.sumabs2(inner(whh))), wd[1]
+    fo, wo = make(oracle, lambda a: np.asfortranarray(a.copy()))
+    fd, wdv = make(ag, ag.DArray.from_numpy)
+    assert relerr(fd(wdv).to_numpy(), fo(wo)) <= 1e-10
+
+
+def test_highorder_tanh(ag):
+    x = ag.DArray.from_numpy(np.array([1.0]))
+    g1 = ag.grad(lambda v: ag.sum_(ag.tanh(v)))
+    g2 = ag.grad(lambda v: ag.sum_(g1(v)))
+    t = np.tanh(1.0)
+    assert abs(g1(x).to_numpy()[0] - (1 - t * t)) < 1e-15
+    assert abs(g2(x).to_numpy()[0] - (-2 * t * (1 - t * t))) < 1e-14
+
+
+def test_gradcheck_primitives(ag):
+    """test/gradcheck.jl on device for the hot-path primitives (reference tolerances)."""
+    rng = np.random.default_rng(8)
+    x = ag.DArray.from_numpy(rng.uniform(0.2, 0.8, (3, 2)))
+    for name in ["exp", "log", "tanh", "sigm", "sqrt", "sin", "cos", "abs2", "abs_", "neg", "relu"]:
+        assert ag.gradcheck(getattr(ag, name), x), name
+    a = ag.DArray.from_numpy(rng.standard_normal((4, 3)))
+    b = ag.DArray.from_numpy(rng.standard_normal((3, 5)))
+    assert ag.gradcheck(ag.matmul, a, b)
+    v = ag.DArray.from_numpy(rng.uniform(0.5, 1.5, (4, 1)))
+    for name in ["add", "sub", "mul", "div", "max_", "min_"]:
+        assert ag.gradcheck(getattr(ag, name), a, v), name
+    assert ag.gradcheck(lambda z: ag.sum_(z, dims=1), a)
+    assert ag.gradcheck(lambda z: ag.getindex(z, slice(None), [1, 1, 2]), a)
+    assert ag.gradcheck(lambda p, q: ag.vcat(p, q), a, ag.DArray.from_numpy(rng.standard_normal((2, 3))))
+
+
+def test_graph_replay_matches_eager(ag):
+    """CUDA-graph replay of a whole step gives bit-identical parameters to the eager step."""
+    W = ag.workloads
+    w, x, y = W.mnist_init(np.random.default_rng(9), 2048)
+    xd, yd = ag.DArray.from_numpy(x), ag.DArray.from_numpy(y)
+
+    def step(params):
+        t = ag.diff(lambda: W.mnist_loss(ag, params, xd, yd))
+        for p in params:
+            ag.axpy(-0.1, ag.grad(t, p), p)
+        return ag.value(t)
+    pe = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    pg = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    for _ in range(3):
+        le = step(pe)
+    step(pg)                                   # eager warm-up populates pool and workspace
+    with ag.StepGraph() as g:
+        lg = step(pg)
+    g.launch()                                 # the capture itself did not execute: 2nd and 3rd step
+    g.launch()
+    ag.sync()
+    for a, b in zip(pe, pg):
+        assert np.array_equal(a.value.to_numpy(), b.value.to_numpy())
+    assert float(le) == float(lg)
+    g.destroy()
+
+
+def test_full_size_properties(ag):
+    """BASELINE config 2 at the bench size (B = 65536): properties that need no oracle.
+    (a) softmax cross-entropy: column sums of d loss / d logits are 0, so grad(b2) sums to ~0;
+    (b) linearity: grads of 2*loss are exactly 2x; (c) grad(b1) == row sums of the relu-masked dy."""
+    W = ag.workloads
+    B = 65536
+    w, x, y = W.mnist_init(np.random.default_rng(10), B)
+    pd = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    xd, yd = ag.DArray.from_numpy(x), ag.DArray.from_numpy(y)
+    t1 = ag.diff(lambda: W.mnist_loss(ag, pd, xd, yd))
+    g1 = [ag.grad(t1, p).to_numpy() for p in pd]
+    assert abs(g1[3].astype(np.float64).sum()) <= 1e-5
+    t2 = ag.diff(lambda: ag.mul(2.0, W.mnist_loss(ag, pd, xd, yd)))
+    g2 = [ag.grad(t2, p).to_numpy() for p in pd]
+    for a, b in zip(g1, g2):
+        assert np.array_equal(2 * a, b)
+    # against a float64 numpy evaluation of the same formula (cheap: one pass on the host)
+    w64 = [a.astype(np.float64) for a in w]
+    a2 = w64[0] @ x.astype(np.float64) + w64[1][:, None]
+    a3 = np.maximum(a2, 0)
+    p = w64[2] @ a3 + w64[3][:, None]
+    sm = np.exp(p - p.max(0))
+    sm /= sm.sum(0)
+    dp = (sm - y) / B
+    assert relerr(g1[3], dp.sum(1)) <= 1e-5
+    assert relerr(g1[2], dp @ a3.T) <= 1e-5
+    da2 = (w64[2].T @ dp) * (a2 >= 0)
+    assert relerr(g1[1], da2.sum(1)) <= 1e-5
+    assert relerr(g1[0], da2 @ x.astype(np.float64).T) <= 1e-5
