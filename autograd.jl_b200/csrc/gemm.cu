@@ -12,6 +12,13 @@
 
 namespace agb {
 
+ag_status gemm_skinny(int dtype, int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                      const void* A, int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc,
+                      bool* done);
+template <typename T>
+ag_status reduce_partials(const T* part, int nparts, int64_t M, int64_t N, double alpha, double beta, T* C,
+                          int64_t ldc);
+
 constexpr int BM = 64, BN = 64, BK = 16, GT = 256, PADM = 4;
 
 // Partial product over k in [k0,k1) of one 64x64 tile.  SPLIT: write raw partial sums to `ws`
@@ -156,10 +163,7 @@ static ag_status gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t
   k_gemm_simt<T, true><<<grid, GT, 0, c.stream>>>(transA, transB, M, N, K, (T)alpha, (const T*)A, lda,
                                                   (const T*)B, ldb, (T)beta, (T*)C, ldc, kchunk, ws);
   AG_LAUNCHED();
-  k_splitk_reduce<T><<<(unsigned)cdiv(M * N, 256), 256, 0, c.stream>>>(ws, (int)splits, M, N, (T)alpha,
-                                                                       (T)beta, (T*)C, ldc);
-  AG_LAUNCHED();
-  return AG_OK;
+  return reduce_partials<T>(ws, (int)splits, M, N, alpha, beta, (T*)C, ldc);
 }
 
 // gemm_tc.cu
@@ -205,6 +209,15 @@ ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int6
     AG_CHECK(A && B, AG_EINVAL, "ag_gemm: null operand");
     AG_CHECK(lda >= (transA ? K : M) && ldb >= (transB ? N : K), AG_EINVAL,
              "ag_gemm: leading dimension too small (DimensionMismatch)");
+  }
+  if (K > 0 && g_engine != 2) {
+    bool done = false;
+    ag_status st = gemm_skinny(dtype, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &done);
+    if (st != AG_OK) return st;
+    if (done) {
+      g_last_engine = "skinny";
+      return AG_OK;
+    }
   }
   if (dtype == AG_F64) {
     g_last_engine = "dfma";

@@ -1,18 +1,516 @@
-// gemm_tc.cu -- tcgen05 (TMA + TMEM) Float32 GEMM engine.  Placeholder until the kernel lands:
-// reports "not supported" so ag_gemm uses the CUDA-core engine.
+// gemm_tc.cu -- the Float32 matrix product on the 5th-generation tensor cores.
+//
+// Reference: forward `*` and its gradient products `dy*x2'` (NT) and `x1'*dy` (TN), src/base.jl:26,
+// which the reference hands to OpenBLAS sgemm.
+//
+// Design (sm_100a):
+//   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread),
+//     warps 2-5 = operand splitters, warps 6-9 = epilogue.  One CTA per SM, 4-stage smem ring.
+//   * operands are fed by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) straight from the caller's
+//     column-major arrays; either operand may be K-major or MN-major, so NN / NT / TN / TT all map onto
+//     the same kernel without a transpose pass (the instruction descriptor carries the majors).
+//   * Float32 accuracy on a TF32 pipe: each fp32 operand tile is split in shared memory into
+//     hi = rna_tf32(x) and lo = rna_tf32(x - hi); D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi with fp32
+//     accumulation in TMEM (3xTF32).  Dropped term lo*lo ~ 2^-22 relative.
+//   * D tile = 128 (mm) x 64 (nn) fp32 in TMEM, double buffered (2 x 64 columns) so the epilogue of
+//     one tile overlaps the main loop of the next.  The large extent of C is mapped to mm.
+//   * split-K for small outputs with a huge contraction (dW = dy*x', K = batch): partials go to the
+//     workspace and are summed in a fixed order (deterministic).
+// Roofline: for the MNIST-MLP shapes (M = 64) the products are HBM-bound:
+// algorithmic bytes (MK + KN + MN)*4.
 #include "common.cuh"
+
+#include <cuda.h>
 
 namespace agb {
 
-bool gemm_tc_supported(int, int, int64_t, int64_t, int64_t, const void*, int64_t, const void*,
-                       int64_t, const void*, int64_t) {
-  return false;
+constexpr int TC_BM = 128;      // mm tile (TMEM lanes)
+constexpr int TC_BN = 64;       // nn tile (TMEM columns per accumulator)
+constexpr int TC_BK = 32;       // k block: 32 floats = one 128-byte swizzle row
+constexpr int TC_RAW_STAGES = 6;   // TMA ring (fp32 tiles as loaded; the tensor core truncates them to tf32 = "hi")
+constexpr int TC_LO_STAGES = 3;    // ring of the error-compensation tiles ("lo")
+constexpr int TC_FLUSH_KB = 8;     // k-blocks accumulated in TMEM before the partial is promoted to registers
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   //  8 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_THREADS = 320;
+constexpr int TC_NBARS = 2 * TC_RAW_STAGES + 2 * TC_LO_STAGES + 4;
+constexpr int TC_SMEM = (TC_RAW_STAGES + TC_LO_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+  int mm_tiles, nn_tiles, splits;
+  int kblocks_total, kblocks_per_split;
+  int64_t MM, NN;          // extents along mm / nn
+  float* out;              // C, or the split-K workspace
+  int64_t ld_out;          // leading dimension of out (elements)
+  int64_t split_stride;    // elements between consecutive split partials
+  int transposed;          // 1: mm runs along C's columns (out[nn + ld*mm]); 0: out[mm + ld*nn]
+  float alpha;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin) {
+    if (spin > (1u << 24)) {
+      printf("libagb200 gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 
-ag_status gemm_tc(int, int, int64_t, int64_t, int64_t, double, const void*, int64_t, const void*,
-                  int64_t, double, void*, int64_t) {
-  set_error("tcgen05 GEMM engine not built");
-  return AG_EUNSUPPORTED;
+// shared-memory matrix descriptor, Blackwell version field = 1.
+// K-major operands use SWIZZLE_128B (layout type 2, 16-byte atoms, 8-row groups of 1024 B).
+// MN-major tf32 operands must use SWIZZLE_128B_BASE32B (layout type 1: 32-byte atoms, the pattern
+// repeats every 4 k-rows = 512 B); TMA counterpart: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t lo_base = smem_base + TC_RAW_STAGES * TC_STAGE_BYTES;
+  const uint32_t bars = lo_base + TC_LO_STAGES * TC_STAGE_BYTES;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (TC_RAW_STAGES + s); };
+  auto lo_ready = [&](int s) { return bars + 8u * (2 * TC_RAW_STAGES + s); };
+  auto lo_empty = [&](int s) { return bars + 8u * (2 * TC_RAW_STAGES + TC_LO_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_RAW_STAGES + 2 * TC_LO_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_RAW_STAGES + 2 * TC_LO_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * TC_NBARS;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + (TC_RAW_STAGES + TC_LO_STAGES) * TC_STAGE_BYTES + 8 * TC_NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_work = p.mm_tiles * p.nn_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < TC_RAW_STAGES; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(raw_empty(s), 1);
+    }
+    for (int s = 0; s < TC_LO_STAGES; ++s) {
+      mbar_init(lo_ready(s), 128);
+      mbar_init(lo_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: 2 accumulators x 64 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // work item -> (mm tile, nn tile, split)
+  auto decode = [&](int w, int& mt, int& nt, int& kb0, int& kb1) {
+    mt = w % p.mm_tiles;
+    int r = w / p.mm_tiles;
+    nt = r % p.nn_tiles;
+    int sp = r / p.nn_tiles;
+    kb0 = sp * p.kblocks_per_split;
+    kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+    return sp;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int mt, nt, kb0, kb1;
+        decode(w, mt, nt, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(raw_empty(s), ph ^ 1);
+          const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+          mbar_expect_tx(raw_full(s), TC_STAGE_BYTES);
+          if (A_KMAJOR) {
+            tma_load_2d(st, &tmA, raw_full(s), kb * TC_BK, mt * TC_BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 32; ++c)
+              tma_load_2d(st + c * 4096, &tmA, raw_full(s), mt * TC_BM + c * 32, kb * TC_BK);
+          }
+          const uint32_t sb = st + TC_A_BYTES;
+          if (B_KMAJOR) {
+            tma_load_2d(sb, &tmB, raw_full(s), kb * TC_BK, nt * TC_BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BN / 32; ++c)
+              tma_load_2d(sb + c * 4096, &tmB, raw_full(s), nt * TC_BN + c * 32, kb * TC_BK);
+          }
+          if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, majors, N, M
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
+                             ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t a_lbo = A_KMAJOR ? 16u : 4096u, b_lbo = B_KMAJOR ? 16u : 4096u;
+      const uint32_t a_kstep = A_KMAJOR ? 32u : 1024u, b_kstep = B_KMAJOR ? 32u : 1024u;   // bytes per UMMA_K = 8
+      const uint32_t a_sbo = A_KMAJOR ? 1024u : 512u, b_sbo = B_KMAJOR ? 1024u : 512u;
+      const uint32_t a_lt = A_KMAJOR ? 2u : 1u, b_lt = B_KMAJOR ? 2u : 1u;
+      int s = 0, l = 0, ci = 0;   // raw stage, lo stage, chunk counter (selects the TMEM accumulator)
+      uint32_t ph = 0, lph = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int mt, nt, kb0, kb1;
+        decode(w, mt, nt, kb0, kb1);
+        for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
+          const int kc1 = min(kc0 + TC_FLUSH_KB, kb1);
+          const int acc = ci & 1;
+          mbar_wait(tempty_bar(acc), ((ci >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * TC_BN;
+          for (int kb = kc0; kb < kc1; ++kb) {
+            mbar_wait(raw_full(s), ph);
+            mbar_wait(lo_ready(l), lph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_base + s * TC_STAGE_BYTES, b_hi = a_hi + TC_A_BYTES;
+            const uint32_t a_lo = lo_base + l * TC_STAGE_BYTES, b_lo = a_lo + TC_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint64_t dah = make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t dal = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t dbh = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
+              const uint64_t dbl = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
+              umma_tf32(d_tmem, dah, dbl, idesc, (kb > kc0 || k > 0) ? 1u : 0u);   // small terms first
+              umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            }
+            umma_commit(raw_empty(s));        // both rings are reusable when these MMAs retire
+            umma_commit(lo_empty(l));
+            if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
+            if (++l == TC_LO_STAGES) { l = 0; lph ^= 1; }
+          }
+          umma_commit(tfull_bar(acc));        // chunk partial complete
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== operand splitters: the tensor core reads hi = trunc_tf32(x) straight from the TMA tile;
+    //       these warps produce lo = rna_tf32(x - trunc_tf32(x)) into the lo ring =====
+    const int tid = threadIdx.x - 64;   // 0..127
+    int s = 0, l = 0;
+    uint32_t ph = 0, lph = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int mt, nt, kb0, kb1;
+      decode(w, mt, nt, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(raw_full(s), ph);
+        mbar_wait(lo_empty(l), lph ^ 1);
+        const float4* raw = reinterpret_cast<const float4*>(smem_gen + s * TC_STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem_gen + (TC_RAW_STAGES + l) * TC_STAGE_BYTES);
+        float4 v[TC_STAGE_BYTES / 16 / 128];
+#pragma unroll
+        for (int i = 0; i < TC_STAGE_BYTES / 16 / 128; ++i) v[i] = raw[tid + i * 128];
+#pragma unroll
+        for (int i = 0; i < TC_STAGE_BYTES / 16 / 128; ++i) {
+          float4 r;
+          r.x = rna_tf32(v[i].x - trunc_tf32(v[i].x));
+          r.y = rna_tf32(v[i].y - trunc_tf32(v[i].y));
+          r.z = rna_tf32(v[i].z - trunc_tf32(v[i].z));
+          r.w = rna_tf32(v[i].w - trunc_tf32(v[i].w));
+          lo[tid + i * 128] = r;
+        }
+        fence_async_smem();                 // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(lo_ready(l));
+        if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
+        if (++l == TC_LO_STAGES) { l = 0; lph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: promote each chunk partial TMEM -> registers (fp32 RN adds), write the tile =====
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    int ci = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int mt, nt, kb0, kb1;
+      const int sp = decode(w, mt, nt, kb0, kb1);
+      float accv[TC_BN];
+#pragma unroll
+      for (int j = 0; j < TC_BN; ++j) accv[j] = 0.f;
+      for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
+        const int acc = ci & 1;
+        mbar_wait(tfull_bar(acc), (ci >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) accv[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      const int64_t mm = (int64_t)mt * TC_BM + q * 32 + lane;
+      const int64_t nn0 = (int64_t)nt * TC_BN;
+      float* __restrict__ out = p.out + (int64_t)sp * p.split_stride;
+      if (mm < p.MM) {
+        if (p.transposed) {
+          // this thread owns 64 consecutive elements of one column of C
+          float* dst = out + nn0 + p.ld_out * mm;
+          if (nn0 + TC_BN <= p.NN && (p.ld_out & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < TC_BN; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(p.alpha * accv[j], p.alpha * accv[j + 1],
+                                                                p.alpha * accv[j + 2], p.alpha * accv[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BN; ++j)
+              if (nn0 + j < p.NN) dst[j] = p.alpha * accv[j];
+          }
+        } else {
+          // lanes hold consecutive rows of C: coalesced per column
+#pragma unroll
+          for (int j = 0; j < TC_BN; ++j)
+            if (nn0 + j < p.NN) out[mm + p.ld_out * (nn0 + j)] = p.alpha * accv[j];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+// C = alpha * sum_s ws[s] + beta*C in a fixed order (deterministic split-K)
+__global__ void __launch_bounds__(256)
+    k_tc_splitk_reduce(const float* __restrict__ ws, int splits, int64_t M, int64_t N, float alpha, float beta,
+                       float* __restrict__ C, int64_t ldc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  int64_t m = i % M, n = i / M;
+  float s0 = 0.f, s1 = 0.f;
+  int k = 0;
+  for (; k + 1 < splits; k += 2) {
+    s0 += ws[(int64_t)k * M * N + i];
+    s1 += ws[(int64_t)(k + 1) * M * N + i];
+  }
+  if (k < splits) s0 += ws[(int64_t)k * M * N + i];
+  float* c = C + m + n * ldc;
+  float r = alpha * (s0 + s1);
+  *c = beta == 0.f ? r : r + beta * (*c);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-d fp32 tensor map: inner (contiguous) extent d0, outer extent d1 with `ld` elements between rows
+static bool make_map(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t ld, int box0, int box1,
+                     bool kmajor) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                       const void* B, int64_t ldb, const void* C, int64_t ldc) {
+  (void)transA; (void)transB;
+  if (!encode_fn()) return false;
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return false;
+  if ((lda | ldb | ldc) & 3) return false;                 // TMA strides are multiples of 16 bytes
+  if (M < 8 || N < 8 || K < 8) return false;
+  if (M >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31)) return false;
+  if (2.0 * (double)M * (double)N * (double)K < 3.0e7) return false;   // tiny: launch-bound either way
+  return true;
+}
+
+ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const void* A,
+                  int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc) {
+  Context& c = ctx();
+  // Map the larger extent of C onto the 128-row mm tile.
+  //   normal     : mm = row index m of C,    Aop = op(A) (M x K),  Bop = op(B)^T (N x K)
+  //   transposed : mm = column index n of C, Aop = op(B)^T (N x K), Bop = op(A) (M x K)
+  const bool transposed = N > M;
+  // op(A)[m,k]: transA ? A[k + m*lda] (K-major) : A[m + k*lda] (MN-major)
+  // op(B)^T[n,k] = op(B)[k,n]: transB ? B[n + k*ldb] (MN-major) : B[k + n*ldb] (K-major)
+  const bool a_kmajor = transA != 0, b_kmajor = transB == 0;
+  const void *pa, *pb;
+  int64_t MM, NN, lda_, ldb_;
+  bool ak, bk;
+  if (!transposed) { pa = A; ak = a_kmajor; lda_ = lda; MM = M; pb = B; bk = b_kmajor; ldb_ = ldb; NN = N; }
+  else { pa = B; ak = b_kmajor; lda_ = ldb; MM = N; pb = A; bk = a_kmajor; ldb_ = lda; NN = M; }
+
+  CUtensorMap tmA, tmB;
+  bool ok;
+  if (ak) ok = make_map(&tmA, pa, K, MM, lda_, TC_BK, TC_BM, true);
+  else ok = make_map(&tmA, pa, MM, K, lda_, 32, TC_BK, false);
+  if (bk) ok = ok && make_map(&tmB, pb, K, NN, ldb_, TC_BK, TC_BN, true);
+  else ok = ok && make_map(&tmB, pb, NN, K, ldb_, 32, TC_BK, false);
+  AG_CHECK(ok, AG_ECUDA, "ag_gemm: cuTensorMapEncodeTiled failed");
+
+  TcParams p;
+  p.mm_tiles = (int)cdiv(MM, TC_BM);
+  p.nn_tiles = (int)cdiv(NN, TC_BN);
+  p.kblocks_total = (int)cdiv(K, TC_BK);
+  const int64_t tiles = (int64_t)p.mm_tiles * p.nn_tiles;
+  int splits = 1;
+  if (tiles < c.num_sms && p.kblocks_total >= 16) {
+    splits = (int)cdiv(2 * (int64_t)c.num_sms, tiles);
+    int maxs = p.kblocks_total / 8;     // >= 8 k-blocks (256 k) per split
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+  }
+  p.kblocks_per_split = (int)cdiv(p.kblocks_total, splits);
+  splits = (int)cdiv(p.kblocks_total, p.kblocks_per_split);
+  const bool via_ws = splits > 1 || beta != 0.0;
+  p.splits = splits;
+  p.MM = MM;
+  p.NN = NN;
+  p.transposed = transposed ? 1 : 0;
+  if (via_ws) {
+    float* ws = (float*)workspace((size_t)splits * (size_t)(M * N) * sizeof(float));
+    if (!ws) return AG_ENOMEM;
+    p.out = ws;
+    p.ld_out = M;
+    p.split_stride = M * N;
+    p.alpha = 1.0f;
+  } else {
+    p.out = (float*)C;
+    p.ld_out = ldc;
+    p.split_stride = 0;
+    p.alpha = (float)alpha;
+  }
+  const int64_t work = tiles * splits;
+  const unsigned grid = (unsigned)(work < c.num_sms ? work : c.num_sms);
+
+#define LAUNCH(AK, BK_)                                                                              \
+  do {                                                                                               \
+    static bool attr_set = false;                                                                    \
+    if (!attr_set) {                                                                                 \
+      AG_CUDA(cudaFuncSetAttribute(k_gemm_tc<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                   TC_SMEM));                                                        \
+      attr_set = true;                                                                               \
+    }                                                                                                \
+    k_gemm_tc<AK, BK_><<<grid, TC_THREADS, TC_SMEM, c.stream>>>(tmA, tmB, p);                        \
+  } while (0)
+  if (ak && bk) LAUNCH(true, true);
+  else if (ak && !bk) LAUNCH(true, false);
+  else if (!ak && bk) LAUNCH(false, true);
+  else LAUNCH(false, false);
+#undef LAUNCH
+  AG_LAUNCHED();
+  if (via_ws) {
+    k_tc_splitk_reduce<<<(unsigned)cdiv(M * N, 256), 256, 0, c.stream>>>(p.out, splits, M, N, (float)alpha,
+                                                                        (float)beta, (float*)C, ldc);
+    AG_LAUNCHED();
+  }
+  return AG_OK;
 }
 
 }  // namespace agb

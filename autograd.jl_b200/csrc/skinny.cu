@@ -1,0 +1,221 @@
+// skinny.cu -- CUDA-core matrix products for the "tiny matrix x very wide matrix" shapes of the tape:
+//   S1  C[MxN] = op(A)[MxK] * B[KxN],  M,K <= 64, N huge      forward  w2*a3  (10x64 * 64xB)  and the
+//                                                              gradient w2'*dy (64x10 * 10xB), src/base.jl:26
+//   S2  C[MxN] = A[MxK] * B[NxK]',     M,N <= 64, K huge      gradient dy*a3' (10xB * Bx64)
+// These are HBM/L2-bound streaming passes over the wide operand (algorithmic bytes (MK+KN+MN)*s); the
+// tiny operand lives in shared memory.  A 128-row tensor-core tile would waste >= 84 % of its rows on
+// M = 10 and TMA cannot address a 40-byte leading dimension, so they stay on the FFMA/DFMA pipe.
+// Reductions over K are deterministic (per-block partials, fixed-order second phase).
+#include "common.cuh"
+
+namespace agb {
+
+constexpr int SK_T = 256;     // threads
+constexpr int SK_COLS = 64;   // columns of the wide operand per block (S1)
+constexpr int SK_MAXD = 64;   // max extent of the small dims
+
+// ---- S1 ---------------------------------------------------------------------------------------------
+template <typename T, int NJ>
+__global__ void __launch_bounds__(SK_T)
+    k_skinny_left(int transA, int M, int64_t N, int K, T alpha, const T* __restrict__ A, int64_t lda,
+                  const T* __restrict__ B, int64_t ldb, T beta, T* __restrict__ C, int64_t ldc) {
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  T* As = reinterpret_cast<T*>(sk_smem);        // As[m*(K+1) + k]
+  T* Bs = As + M * (K + 1);                     // Bs[col*SKs + k]; reused for the output tile [col][M]
+  const int t = threadIdx.x;
+  const int SKs = K | 1;                        // odd stride: conflict-free column access
+  const int64_t n0 = (int64_t)blockIdx.x * SK_COLS;
+  const int ncols = (int)min((int64_t)SK_COLS, N - n0);
+  for (int i = t; i < M * K; i += SK_T) {
+    int m, k;
+    if (transA) { k = i % K; m = i / K; As[m * (K + 1) + k] = A[k + (int64_t)m * lda]; }
+    else { m = i % M; k = i / M; As[m * (K + 1) + k] = A[m + (int64_t)k * lda]; }
+  }
+  if (ldb == K) {   // the tile is one contiguous run
+    const T* __restrict__ src = B + n0 * ldb;
+    for (int i = t; i < ncols * K; i += SK_T) Bs[(i / K) * SKs + (i % K)] = src[i];
+  } else {
+    for (int i = t; i < ncols * K; i += SK_T) {
+      int col = i / K, k = i % K;
+      Bs[col * SKs + k] = B[k + (n0 + col) * ldb];
+    }
+  }
+  __syncthreads();
+  const int col = t % SK_COLS, mg = t / SK_COLS;   // 4 row groups
+  T acc[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) acc[j] = T(0);
+  if (col < ncols) {
+    for (int k = 0; k < K; ++k) {
+      const T b = Bs[col * SKs + k];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int m = mg + 4 * j;
+        if (m < M) acc[j] = fma(As[m * (K + 1) + k], b, acc[j]);
+      }
+    }
+  }
+  __syncthreads();
+  T* Cs = Bs;   // output tile [col][M], odd row stride against bank conflicts
+  const int MS = M | 1;
+  if (col < ncols) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int m = mg + 4 * j;
+      if (m < M) Cs[col * MS + m] = alpha * acc[j];
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < ncols * M; i += SK_T) {
+    const int c = i / M, m = i % M;
+    T* dst = C + m + (n0 + c) * ldc;
+    const T v = Cs[c * MS + m];
+    *dst = beta == T(0) ? v : v + beta * (*dst);
+  }
+}
+
+// ---- S2 ---------------------------------------------------------------------------------------------
+// block b handles k in [b*kc, min(K,(b+1)*kc)); part[b][m + M*n] = sum_k A[m,k]*B[n,k]
+template <typename T, int NJ>
+__global__ void __launch_bounds__(SK_T)
+    k_skinny_nt(int M, int N, int64_t K, int64_t kc, const T* __restrict__ A, int64_t lda,
+                const T* __restrict__ B, int64_t ldb, T* __restrict__ part) {
+  constexpr int KT = 32;
+  __shared__ T At[KT * SK_MAXD];   // At[k*M + m]
+  __shared__ T Bt[KT * SK_MAXD];   // Bt[k*N + n]
+  const int t = threadIdx.x;
+  const int n = t % SK_COLS, mg = t / SK_COLS;
+  const int64_t k0 = (int64_t)blockIdx.x * kc;
+  const int64_t k1 = min(K, k0 + kc);
+  T acc[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) acc[j] = T(0);
+  for (int64_t kk = k0; kk < k1; kk += KT) {
+    const int kt = (int)min((int64_t)KT, k1 - kk);
+    if (lda == M) {
+      const T* __restrict__ src = A + kk * lda;
+      for (int i = t; i < kt * M; i += SK_T) At[i] = src[i];
+    } else {
+      for (int i = t; i < kt * M; i += SK_T) At[i] = A[(i % M) + (kk + i / M) * lda];
+    }
+    if (ldb == N) {
+      const T* __restrict__ src = B + kk * ldb;
+      for (int i = t; i < kt * N; i += SK_T) Bt[i] = src[i];
+    } else {
+      for (int i = t; i < kt * N; i += SK_T) Bt[i] = B[(i % N) + (kk + i / N) * ldb];
+    }
+    __syncthreads();
+    if (n < N) {
+      for (int k = 0; k < kt; ++k) {
+        const T b = Bt[k * N + n];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int m = mg + 4 * j;
+          if (m < M) acc[j] = fma(At[k * M + m], b, acc[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (n < N) {
+    T* __restrict__ dst = part + (int64_t)blockIdx.x * M * N;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int m = mg + 4 * j;
+      if (m < M) dst[m + M * n] = acc[j];
+    }
+  }
+}
+
+// C[m + ldc*n] = alpha * sum_p part[p][i] (+ beta*C), i = m + M*n; 16 x 16 threads: 16 outputs per block,
+// 16 lanes each summing every 16th partial, then a fixed-order combine (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_reduce_partials(const T* __restrict__ part, int nparts, int64_t len, T alpha, T beta, T* __restrict__ C,
+                      int64_t M, int64_t ldc) {
+  __shared__ double sm[16][17];
+  const int li = threadIdx.x % 16, g = threadIdx.x / 16;
+  const int64_t i = (int64_t)blockIdx.x * 16 + li;
+  double s = 0;
+  if (i < len)
+    for (int p = g; p < nparts; p += 16) s += (double)part[(int64_t)p * len + i];
+  sm[g][li] = s;
+  __syncthreads();
+  if (g == 0 && i < len) {
+    double r = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) r += sm[q][li];
+    T* dst = C + (i % M) + (i / M) * ldc;
+    *dst = beta == T(0) ? (T)(alpha * r) : (T)(alpha * r + (double)beta * (double)(*dst));
+  }
+}
+
+template <typename T>
+ag_status reduce_partials(const T* part, int nparts, int64_t M, int64_t N, double alpha, double beta, T* C,
+                          int64_t ldc) {
+  Context& c = ctx();
+  k_reduce_partials<T><<<(unsigned)cdiv(M * N, 16), 256, 0, c.stream>>>(part, nparts, M * N, (T)alpha, (T)beta, C,
+                                                                       M, ldc);
+  AG_LAUNCHED();
+  return AG_OK;
+}
+template ag_status reduce_partials<float>(const float*, int, int64_t, int64_t, double, double, float*, int64_t);
+template ag_status reduce_partials<double>(const double*, int, int64_t, int64_t, double, double, double*, int64_t);
+
+template <typename T>
+static ag_status skinny_impl(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const T* A,
+                             int64_t lda, const T* B, int64_t ldb, double beta, T* C, int64_t ldc, bool* done) {
+  Context& c = ctx();
+  *done = false;
+  if (!transB && M <= SK_MAXD && K <= SK_MAXD && N >= 512 && cdiv(N, SK_COLS) < ((int64_t)1 << 31)) {
+    const int sks = (int)K | 1, ms = (int)M | 1;
+    const size_t smem = ((size_t)M * (K + 1) + (size_t)SK_COLS * (sks > ms ? sks : ms)) * sizeof(T);
+    const unsigned grid = (unsigned)cdiv(N, SK_COLS);
+#define SK_LEFT(NJ_)                                                                                        \
+  do {                                                                                                      \
+    static bool attr_set = false;                                                                           \
+    if (!attr_set) {                                                                                        \
+      AG_CUDA(cudaFuncSetAttribute(k_skinny_left<T, NJ_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                   80 * 1024));                                                             \
+      attr_set = true;                                                                                      \
+    }                                                                                                       \
+    k_skinny_left<T, NJ_><<<grid, SK_T, smem, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B,   \
+                                                         ldb, (T)beta, C, ldc);                             \
+  } while (0)
+    const int nj = (int)cdiv(M, 4);
+    if (nj <= 1) SK_LEFT(1); else if (nj <= 2) SK_LEFT(2); else if (nj <= 3) SK_LEFT(3);
+    else if (nj <= 4) SK_LEFT(4); else if (nj <= 8) SK_LEFT(8); else if (nj <= 12) SK_LEFT(12); else SK_LEFT(16);
+#undef SK_LEFT
+    AG_LAUNCHED();
+    *done = true;
+    return AG_OK;
+  }
+  if (!transA && transB && M <= SK_MAXD && N <= SK_MAXD && K >= 2048) {
+    int64_t nblk = 2 * (int64_t)c.num_sms;
+    int64_t kc = cdiv(cdiv(K, nblk), 32) * 32;
+    nblk = cdiv(K, kc);
+    T* part = (T*)workspace((size_t)(nblk * M * N) * sizeof(T));
+    if (!part) return AG_ENOMEM;
+#define SK_NT(NJ_) k_skinny_nt<T, NJ_><<<(unsigned)nblk, SK_T, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part)
+    const int nj = (int)cdiv(M, 4);
+    if (nj <= 1) SK_NT(1); else if (nj <= 2) SK_NT(2); else if (nj <= 3) SK_NT(3);
+    else if (nj <= 4) SK_NT(4); else if (nj <= 8) SK_NT(8); else if (nj <= 12) SK_NT(12); else SK_NT(16);
+#undef SK_NT
+    AG_LAUNCHED();
+    *done = true;
+    return reduce_partials<T>(part, (int)nblk, M, N, alpha, beta, C, ldc);
+  }
+  return AG_OK;
+}
+
+ag_status gemm_skinny(int dtype, int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                      const void* A, int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc,
+                      bool* done) {
+  if (dtype == AG_F32)
+    return skinny_impl<float>(transA, transB, M, N, K, alpha, (const float*)A, lda, (const float*)B, ldb, beta,
+                              (float*)C, ldc, done);
+  return skinny_impl<double>(transA, transB, M, N, K, alpha, (const double*)A, lda, (const double*)B, ldb, beta,
+                             (double*)C, ldc, done);
+}
+
+}  // namespace agb
