@@ -5,13 +5,14 @@
 //
 // Design (sm_100a):
 //   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread),
-//     warps 2-5 = operand splitters, warps 6-9 = epilogue.  One CTA per SM, 4-stage smem ring.
+//     warps 2-9 = operand splitters, warps 10-13 = epilogue.  One CTA per SM; 6-stage TMA ring + 3-stage lo ring.
 //   * operands are fed by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) straight from the caller's
 //     column-major arrays; either operand may be K-major or MN-major, so NN / NT / TN / TT all map onto
 //     the same kernel without a transpose pass (the instruction descriptor carries the majors).
-//   * Float32 accuracy on a TF32 pipe: each fp32 operand tile is split in shared memory into
-//     hi = rna_tf32(x) and lo = rna_tf32(x - hi); D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi with fp32
-//     accumulation in TMEM (3xTF32).  Dropped term lo*lo ~ 2^-22 relative.
+//   * Float32 accuracy on a TF32 pipe (3xTF32): the tensor core reads the fp32 tile as loaded and truncates
+//     it to tf32 (hi); the splitter warps write lo = rna_tf32(x - hi) to a second ring;
+//     D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi with fp32 accumulation in TMEM, promoted to registers every
+//     8 k-blocks.  Dropped term lo*lo ~ 2^-22 relative.  Measured error ~2e-6 of max|C| (tests/probe_gemm_accuracy.py).
 //   * D tile = 128 (mm) x 64 (nn) fp32 in TMEM, double buffered (2 x 64 columns) so the epilogue of
 //     one tile overlaps the main loop of the next.  The large extent of C is mapped to mm.
 //   * split-K for small outputs with a huge contraction (dW = dy*x', K = batch): partials go to the
@@ -33,7 +34,8 @@ constexpr int TC_FLUSH_KB = 8;     // k-blocks accumulated in TMEM before the pa
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   //  8 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_THREADS = 320;
+constexpr int TC_SPLIT_THREADS = 256;   // 8 operand-splitter warps
+constexpr int TC_THREADS = 64 + TC_SPLIT_THREADS + 128;
 constexpr int TC_NBARS = 2 * TC_RAW_STAGES + 2 * TC_LO_STAGES + 4;
 constexpr int TC_SMEM = (TC_RAW_STAGES + TC_LO_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -103,6 +105,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// lo = x - trunc_tf32(x) (exact in fp32), then +half-ulp(tf32) on the bit pattern: the tensor core's own
+// truncation of the operand then yields round-to-nearest (ties away) -- integer ops instead of cvt.rna.tf32.
+__device__ __forceinline__ float lo_tf32(float x) {
+  const float d = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(d) + 0x1000u);
+}
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(raw_empty(s), 1);
     }
     for (int s = 0; s < TC_LO_STAGES; ++s) {
-      mbar_init(lo_ready(s), 128);
+      mbar_init(lo_ready(s), TC_SPLIT_THREADS);
       mbar_init(lo_empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -261,10 +269,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + TC_SPLIT_THREADS / 32) {
     // ===== operand splitters: the tensor core reads hi = trunc_tf32(x) straight from the TMA tile;
     //       these warps produce lo = rna_tf32(x - trunc_tf32(x)) into the lo ring =====
-    const int tid = threadIdx.x - 64;   // 0..127
+    const int tid = threadIdx.x - 64;   // 0..TC_SPLIT_THREADS-1
     int s = 0, l = 0;
     uint32_t ph = 0, lph = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -275,17 +283,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(lo_empty(l), lph ^ 1);
         const float4* raw = reinterpret_cast<const float4*>(smem_gen + s * TC_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem_gen + (TC_RAW_STAGES + l) * TC_STAGE_BYTES);
-        float4 v[TC_STAGE_BYTES / 16 / 128];
+        constexpr int NV = TC_STAGE_BYTES / 16 / TC_SPLIT_THREADS;
+        float4 v[NV];
 #pragma unroll
-        for (int i = 0; i < TC_STAGE_BYTES / 16 / 128; ++i) v[i] = raw[tid + i * 128];
+        for (int i = 0; i < NV; ++i) v[i] = raw[tid + i * TC_SPLIT_THREADS];
 #pragma unroll
-        for (int i = 0; i < TC_STAGE_BYTES / 16 / 128; ++i) {
+        for (int i = 0; i < NV; ++i) {
           float4 r;
-          r.x = rna_tf32(v[i].x - trunc_tf32(v[i].x));
-          r.y = rna_tf32(v[i].y - trunc_tf32(v[i].y));
-          r.z = rna_tf32(v[i].z - trunc_tf32(v[i].z));
-          r.w = rna_tf32(v[i].w - trunc_tf32(v[i].w));
-          lo[tid + i * 128] = r;
+          r.x = lo_tf32(v[i].x); r.y = lo_tf32(v[i].y); r.z = lo_tf32(v[i].z); r.w = lo_tf32(v[i].w);
+          lo[tid + i * TC_SPLIT_THREADS] = r;
         }
         fence_async_smem();                 // generic-proxy writes -> visible to the tensor core
         mbar_arrive(lo_ready(l));
