@@ -1,0 +1,89 @@
+"""CPU test of the data-parallel path at world size 2 (gloo): each rank runs its own tape on a contiguous
+column shard, gradients are bucketed and all-reduced, and must equal the single-process full-batch
+gradient of the oracle.  The device ABI is replaced by tests/fake_abi.py; the collective inside
+ag_allreduce_sum is delegated to gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    import __graft_entry__ as ge
+    import fake_abi
+    ag = ge.load_package()
+
+    def allreduce(v):
+        t = torch.from_numpy(np.array(v, copy=True))
+        dist.all_reduce(t)
+        return t.numpy()
+    fake_abi.install(ag, fake_abi.FakeLib(allreduce=allreduce))
+
+    def bcast(payload):
+        obj = [payload]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    dp = ag.DataParallel(rank, world, bcast)
+    W = ag.workloads
+    B = 96
+    w, x, y = W.mnist_init(np.random.default_rng(11), B, np.float64)
+    lo, hi = dp.shard_columns(B, rank, world)
+    params = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    xd, yd = ag.DArray.from_numpy(x[:, lo:hi]), ag.DArray.from_numpy(y[:, lo:hi])
+    t = ag.diff(lambda: W.mnist_loss(ag, params, xd, yd, global_batch=B))
+    grads = dp.allreduce_grads([ag.grad(t, p) for p in params])
+    for p, g in zip(params, grads):
+        ag.axpy(-0.1, g, p)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *[p.value.to_numpy() for p in params],
+             *[g.to_numpy() for g in grads])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradients_match_full_batch(tmp_path, oracle):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    W = ge.load_package().workloads
+    B = 96
+    w, x, y = W.mnist_init(np.random.default_rng(11), B, np.float64)
+    po = [oracle.Param(np.asfortranarray(a)) for a in w]
+    to = oracle.diff(lambda: W.mnist_loss(oracle, po, x, y))
+    gref = [oracle.grad(to, p) for p in po]
+    r0 = np.load(os.path.join(str(tmp_path), "rank0.npz"))
+    r1 = np.load(os.path.join(str(tmp_path), "rank1.npz"))
+    for i, g in enumerate(gref):
+        got0, got1 = r0["arr_%d" % (4 + i)], r1["arr_%d" % (4 + i)]
+        assert np.array_equal(got0, got1)                       # every rank holds the same reduced gradient
+        assert np.max(np.abs(got0 - g)) <= 1e-12 * max(np.max(np.abs(g)), 1e-30)
+        want = w[i] - 0.1 * g                                   # identical axpy! on every rank
+        assert np.max(np.abs(r0["arr_%d" % i] - want)) <= 1e-12
+        assert np.array_equal(r0["arr_%d" % i], r1["arr_%d" % i])
+
+
+def test_shard_columns_cover_the_batch(agpkg):
+    for n in (1, 7, 64, 65536):
+        for world in (1, 2, 4, 8):
+            spans = [agpkg.DataParallel.shard_columns(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
