@@ -22,6 +22,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace agb {
 
@@ -48,6 +49,10 @@ struct TcParams {
   int64_t split_stride;    // elements between consecutive split partials
   int transposed;          // 1: mm runs along C's columns (out[nn + ld*mm]); 0: out[mm + ld*nn]
   float alpha;
+  int dbg_mmas;            // experiment knob (AGB_TC_MMAS): MMAs issued per k-step (3 = product)
+  int dbg_nosplit;         // experiment knob (AGB_TC_NOSPLIT): splitter warps skip the smem work
+  int dbg_load;            // experiment knob (AGB_TC_LOAD): 1 = A only, 2 = B only, 3 = both (product)
+  long long* dbg_t;        // AGB_TC_TIMING: per-role wait-cycle counters of block 0
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -89,6 +94,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// One lane of a fully converged warp.  Keeping the TMA / MMA roles warp-uniform (every lane runs the loop, only
+// the instruction itself is predicated on the elected lane) lets ptxas keep descriptors and barrier addresses
+// in uniform registers; wrapping the whole role in `if (lane == 0)` instead costs a serialising ELECT/R2UR loop
+// around every UTCHMMA/UTMALDG (measured: ~1000 cycles of issue time per k-block).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -132,6 +146,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+#define TWAIT(slot, bar, par)                                         \
+  do {                                                               \
+    long long _t0 = clock64();                                       \
+    mbar_wait(bar, par);                                             \
+    tacc[slot] += clock64() - _t0;                                   \
+  } while (0)
+
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -153,6 +174,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = p.mm_tiles * p.nn_tiles * p.splits;
+  long long tacc[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -162,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(raw_empty(s), 1);
     }
     for (int s = 0; s < TC_LO_STAGES; ++s) {
-      mbar_init(lo_ready(s), TC_SPLIT_THREADS);
+      mbar_init(lo_ready(s), TC_SPLIT_THREADS / 32);   // one elected arrival per splitter warp
       mbar_init(lo_empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -192,18 +215,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (warp-uniform; one elected lane issues) =====
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         int mt, nt, kb0, kb1;
         decode(w, mt, nt, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(raw_empty(s), ph ^ 1);
+          TWAIT(0, raw_empty(s), ph ^ 1);
           const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-          mbar_expect_tx(raw_full(s), TC_STAGE_BYTES);
-          if (A_KMAJOR) {
+          if (elect_one()) {
+          mbar_expect_tx(raw_full(s), ((p.dbg_load & 1) ? TC_A_BYTES : 0) + ((p.dbg_load & 2) ? TC_B_BYTES : 0));
+          if (!(p.dbg_load & 1)) {
+          } else if (A_KMAJOR) {
             tma_load_2d(st, &tmA, raw_full(s), kb * TC_BK, mt * TC_BM);
           } else {
 #pragma unroll
@@ -211,20 +236,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               tma_load_2d(st + c * 4096, &tmA, raw_full(s), mt * TC_BM + c * 32, kb * TC_BK);
           }
           const uint32_t sb = st + TC_A_BYTES;
-          if (B_KMAJOR) {
+          if (!(p.dbg_load & 2)) {
+          } else if (B_KMAJOR) {
             tma_load_2d(sb, &tmB, raw_full(s), kb * TC_BK, nt * TC_BN);
           } else {
 #pragma unroll
             for (int c = 0; c < TC_BN / 32; ++c)
               tma_load_2d(sb + c * 4096, &tmB, raw_full(s), nt * TC_BN + c * 32, kb * TC_BK);
           }
+          }
+          __syncwarp();
           if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
         }
       }
+      if (p.dbg_t && blockIdx.x == 0 && lane == 0) { p.dbg_t[0] = tacc[0]; p.dbg_t[1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (warp-uniform; one elected lane issues) =====
+    {
       // instruction descriptor: D=f32, A=B=tf32, majors, N, M
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
                              ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
@@ -233,6 +262,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t a_kstep = A_KMAJOR ? 32u : 1024u, b_kstep = B_KMAJOR ? 32u : 1024u;   // bytes per UMMA_K = 8
       const uint32_t a_sbo = A_KMAJOR ? 1024u : 512u, b_sbo = B_KMAJOR ? 1024u : 512u;
       const uint32_t a_lt = A_KMAJOR ? 2u : 1u, b_lt = B_KMAJOR ? 2u : 1u;
+      // descriptor words (see make_desc): hi = SBO | version<<14 | layout<<29 ; lo = addr>>4 | (LBO>>4)<<16
+      const uint32_t desc_hi_a = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (a_lt << 29);
+      const uint32_t desc_hi_b = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (b_lt << 29);
+      const uint32_t desc_lo_a = ((smem_base >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
+      const uint32_t desc_lbo_delta_b = ((b_lbo >> 4) << 16) - ((a_lbo >> 4) << 16);   // B's LBO field relative to A's
       int s = 0, l = 0, ci = 0;   // raw stage, lo stage, chunk counter (selects the TMEM accumulator)
       uint32_t ph = 0, lph = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -241,33 +275,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
           const int kc1 = min(kc0 + TC_FLUSH_KB, kb1);
           const int acc = ci & 1;
-          mbar_wait(tempty_bar(acc), ((ci >> 1) & 1) ^ 1);
+          TWAIT(0, tempty_bar(acc), ((ci >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TC_BN;
           for (int kb = kc0; kb < kc1; ++kb) {
-            mbar_wait(raw_full(s), ph);
-            mbar_wait(lo_ready(l), lph);
+            TWAIT(1, raw_full(s), ph);
+            TWAIT(2, lo_ready(l), lph);
             tc_fence_after();
-            const uint32_t a_hi = smem_base + s * TC_STAGE_BYTES, b_hi = a_hi + TC_A_BYTES;
-            const uint32_t a_lo = lo_base + l * TC_STAGE_BYTES, b_lo = a_lo + TC_A_BYTES;
+            // descriptors live in uniform registers: constant high word per operand, low word = start
+            // address field advanced by one add per stage / k-step (the uniform datapath is slow)
+            const uint32_t ra = desc_lo_a + (uint32_t)s * (TC_STAGE_BYTES >> 4);            // A_hi (raw ring)
+            const uint32_t rb = ra + (TC_A_BYTES >> 4);                                       // B_hi
+            const uint32_t la = desc_lo_a + (uint32_t)(TC_RAW_STAGES + l) * (TC_STAGE_BYTES >> 4);   // A_lo
+            const uint32_t lb = la + (TC_A_BYTES >> 4);                                       // B_lo
+            uint64_t dah[TC_BK / 8], dal[TC_BK / 8], dbh[TC_BK / 8], dbl[TC_BK / 8];
 #pragma unroll
             for (int k = 0; k < TC_BK / 8; ++k) {
-              const uint64_t dah = make_desc(a_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
-              const uint64_t dal = make_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
-              const uint64_t dbh = make_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
-              const uint64_t dbl = make_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
-              umma_tf32(d_tmem, dah, dbl, idesc, (kb > kc0 || k > 0) ? 1u : 0u);   // small terms first
-              umma_tf32(d_tmem, dal, dbh, idesc, 1u);
-              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+              dah[k] = ((uint64_t)desc_hi_a << 32) | (uint64_t)(ra + k * (a_kstep >> 4));
+              dal[k] = ((uint64_t)desc_hi_a << 32) | (uint64_t)(la + k * (a_kstep >> 4));
+              dbh[k] = ((uint64_t)desc_hi_b << 32) | (uint64_t)(rb + k * (b_kstep >> 4) + desc_lbo_delta_b);
+              dbl[k] = ((uint64_t)desc_hi_b << 32) | (uint64_t)(lb + k * (b_kstep >> 4) + desc_lbo_delta_b);
             }
-            umma_commit(raw_empty(s));        // both rings are reusable when these MMAs retire
-            umma_commit(lo_empty(l));
+            const uint32_t first = kb > kc0 ? 1u : 0u;
+            const uint32_t bar_raw = raw_empty(s), bar_lo = lo_empty(l);
+            const long long t_i0 = clock64();
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 8; ++k) {
+                if (p.dbg_mmas >= 3) {
+                  umma_tf32(d_tmem, dah[k], dbl[k], idesc, k > 0 ? 1u : first);   // small terms first
+                  umma_tf32(d_tmem, dal[k], dbh[k], idesc, 1u);
+                  umma_tf32(d_tmem, dah[k], dbh[k], idesc, 1u);
+                } else if (p.dbg_mmas == 2) {
+                  umma_tf32(d_tmem, dal[k], dbh[k], idesc, k > 0 ? 1u : first);
+                  umma_tf32(d_tmem, dah[k], dbh[k], idesc, 1u);
+                } else {
+                  umma_tf32(d_tmem, dah[k], dbh[k], idesc, k > 0 ? 1u : first);
+                }
+              }
+            }
+            const long long t_i1 = clock64();
+            if (elect_one()) {
+              umma_commit(bar_raw);           // both rings are reusable when these MMAs retire
+              umma_commit(bar_lo);
+            }
+            const long long t_i2 = clock64();
+            tacc[3] += t_i1 - t_i0;
+            tacc[4] += t_i2 - t_i1;
+            __syncwarp();
             if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
             if (++l == TC_LO_STAGES) { l = 0; lph ^= 1; }
           }
-          umma_commit(tfull_bar(acc));        // chunk partial complete
+          if (elect_one()) umma_commit(tfull_bar(acc));        // chunk partial complete
+          __syncwarp();
         }
       }
+      if (p.dbg_t && blockIdx.x == 0 && lane == 0) { p.dbg_t[2] = tacc[0]; p.dbg_t[3] = tacc[1]; p.dbg_t[4] = tacc[2]; p.dbg_t[5] = clock64() - t_begin; p.dbg_t[11] = tacc[3]; p.dbg_t[12] = tacc[4]; }
     }
   } else if (warp < 2 + TC_SPLIT_THREADS / 32) {
     // ===== operand splitters: the tensor core reads hi = trunc_tf32(x) straight from the TMA tile;
@@ -279,12 +342,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       int mt, nt, kb0, kb1;
       decode(w, mt, nt, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(raw_full(s), ph);
-        mbar_wait(lo_empty(l), lph ^ 1);
+        TWAIT(0, raw_full(s), ph);
+        TWAIT(1, lo_empty(l), lph ^ 1);
         const float4* raw = reinterpret_cast<const float4*>(smem_gen + s * TC_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem_gen + (TC_RAW_STAGES + l) * TC_STAGE_BYTES);
         constexpr int NV = TC_STAGE_BYTES / 16 / TC_SPLIT_THREADS;
         float4 v[NV];
+        if (!p.dbg_nosplit) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = raw[tid + i * TC_SPLIT_THREADS];
 #pragma unroll
@@ -293,12 +357,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           r.x = lo_tf32(v[i].x); r.y = lo_tf32(v[i].y); r.z = lo_tf32(v[i].z); r.w = lo_tf32(v[i].w);
           lo[tid + i * TC_SPLIT_THREADS] = r;
         }
+        }
         fence_async_smem();                 // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(lo_ready(l));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lo_ready(l));
         if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
         if (++l == TC_LO_STAGES) { l = 0; lph ^= 1; }
       }
     }
+    if (p.dbg_t && blockIdx.x == 0 && tid == 0) { p.dbg_t[6] = tacc[0]; p.dbg_t[7] = tacc[1]; p.dbg_t[8] = clock64() - t_begin; }
   } else {
     // ===== epilogue: promote each chunk partial TMEM -> registers (fp32 RN adds), write the tile =====
     const int q = warp & 3;              // TMEM lane quarter this warp may read
@@ -311,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int j = 0; j < TC_BN; ++j) accv[j] = 0.f;
       for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
         const int acc = ci & 1;
-        mbar_wait(tfull_bar(acc), (ci >> 1) & 1);
+        TWAIT(0, tfull_bar(acc), (ci >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
@@ -361,6 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   }
 
+  if (p.dbg_t && blockIdx.x == 0 && threadIdx.x == TC_THREADS - 128) { p.dbg_t[9] = tacc[0]; p.dbg_t[10] = clock64() - t_begin; }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -492,6 +560,15 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
     p.split_stride = 0;
     p.alpha = (float)alpha;
   }
+  p.dbg_mmas = getenv("AGB_TC_MMAS") ? atoi(getenv("AGB_TC_MMAS")) : 3;
+  p.dbg_nosplit = getenv("AGB_TC_NOSPLIT") ? 1 : 0;
+  p.dbg_load = getenv("AGB_TC_LOAD") ? atoi(getenv("AGB_TC_LOAD")) : 3;
+  static long long* dbg_t_dev = nullptr;
+  p.dbg_t = nullptr;
+  if (getenv("AGB_TC_TIMING")) {
+    if (!dbg_t_dev) cudaMalloc(&dbg_t_dev, 16 * 8);
+    p.dbg_t = dbg_t_dev;
+  }
   const int64_t work = tiles * splits;
   const unsigned grid = (unsigned)(work < c.num_sms ? work : c.num_sms);
 
@@ -511,6 +588,13 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
   else LAUNCH(false, false);
 #undef LAUNCH
   AG_LAUNCHED();
+  if (p.dbg_t) {
+    long long h[16];
+    cudaStreamSynchronize(c.stream);
+    cudaMemcpy(h, p.dbg_t, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "tc timing (block 0, cycles): work=%lld kb/tile=%d | producer wait_empty=%lld total=%lld | mma wait_tempty=%lld wait_full=%lld wait_lo=%lld total=%lld | split wait_full=%lld wait_loempty=%lld total=%lld | epi wait_tfull=%lld total=%lld | mma issue=%lld commit=%lld\n",
+            (long long)((work + grid - 1) / grid), p.kblocks_per_split, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
+  }
   if (via_ws) {
     k_tc_splitk_reduce<<<(unsigned)cdiv(M * N, 256), 256, 0, c.stream>>>(p.out, splits, M, N, (float)alpha,
                                                                         (float)beta, (float*)C, ldc);
