@@ -29,16 +29,18 @@ namespace agb {
 constexpr int TC_BM = 128;      // mm tile (TMEM lanes)
 constexpr int TC_BN = 64;       // nn tile (TMEM columns per accumulator)
 constexpr int TC_BK = 32;       // k block: 32 floats = one 128-byte swizzle row
-constexpr int TC_RAW_STAGES = 6;   // TMA ring (fp32 tiles as loaded; the tensor core truncates them to tf32 = "hi")
-constexpr int TC_LO_STAGES = 3;    // ring of the error-compensation tiles ("lo")
-constexpr int TC_FLUSH_KB = 8;     // k-blocks accumulated in TMEM before the partial is promoted to registers
+constexpr int TC_STAGES = 6;    // one ring: TMA tiles (smem), B_lo (smem), A hi/lo (TMEM)
+constexpr int TC_FLUSH_KB = 8;  // k-blocks accumulated in TMEM before the partial is promoted to registers
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   //  8 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SPLIT_THREADS = 256;   // 8 operand-splitter warps
+constexpr int TC_RAW_BYTES = TC_A_BYTES + TC_B_BYTES;          // TMA stage: A and B as loaded (fp32)
+constexpr int TC_SPLIT_THREADS = 256;                          // 8 operand-splitter warps
 constexpr int TC_THREADS = 64 + TC_SPLIT_THREADS + 128;
-constexpr int TC_NBARS = 2 * TC_RAW_STAGES + 2 * TC_LO_STAGES + 4;
-constexpr int TC_SMEM = (TC_RAW_STAGES + TC_LO_STAGES) * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_NBARS = 3 * TC_STAGES + 4;
+constexpr int TC_SMEM = TC_STAGES * (TC_RAW_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_TMEM_ACC = 2 * TC_BN;          // columns [0,128): two accumulators
+constexpr int TC_TMEM_ASTAGE = 2 * TC_BK;       // per stage: 32 columns A_hi + 32 columns A_lo
+constexpr int TC_TMEM_COLS = 512;               // 128 + 6*64 = 512: the whole tensor memory of the SM
 
 struct TcParams {
   int mm_tiles, nn_tiles, splits;
@@ -49,10 +51,7 @@ struct TcParams {
   int64_t split_stride;    // elements between consecutive split partials
   int transposed;          // 1: mm runs along C's columns (out[nn + ld*mm]); 0: out[mm + ld*nn]
   float alpha;
-  int dbg_mmas;            // experiment knob (AGB_TC_MMAS): MMAs issued per k-step (3 = product)
-  int dbg_nosplit;         // experiment knob (AGB_TC_NOSPLIT): splitter warps skip the smem work
-  int dbg_load;            // experiment knob (AGB_TC_LOAD): 1 = A only, 2 = B only, 3 = both (product)
-  long long* dbg_t;        // AGB_TC_TIMING: per-role wait-cycle counters of block 0
+  long long* dbg_t;        // AGB_TC_TIMING: per-role wait-cycle counters of block 0 (nullptr in production)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -146,13 +145,50 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// TS-mode MMA: A (128 x 8 tf32) from tensor memory, B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> tensor memory: this thread's TMEM lane, 16 consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// exact tf32 split of an fp32 value: hi = trunc_tf32(x), lo = rna_tf32(x - hi) (integer rounding)
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = x & 0xFFFFE000u;
+  const float d = __uint_as_float(x) - __uint_as_float(hi);
+  lo = (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
+}
+
+// Per-role wait-cycle instrumentation (block 0), compiled in only with -DAGB_TC_TIMING: the clock reads
+// themselves cost ~150 cycles per k-block in the MMA warp.
+#ifdef AGB_TC_TIMING
 #define TWAIT(slot, bar, par)                                         \
   do {                                                               \
     long long _t0 = clock64();                                       \
     mbar_wait(bar, par);                                             \
     tacc[slot] += clock64() - _t0;                                   \
   } while (0)
+#define TCLOCK() clock64()
+#else
+#define TWAIT(slot, bar, par) mbar_wait(bar, par)
+#define TCLOCK() 0ll
+#endif
 
+// A_KMAJOR / B_KMAJOR: memory major of the two operands (K contiguous or mm/nn contiguous).
+// B is consumed from shared memory through a UMMA descriptor in either major; A is consumed from TENSOR
+// MEMORY (TS mode): with N = 64 an SS-mode MMA re-reads a 4 KB A slice from smem for 32 cycles of math
+// (measured 42-50 cycles per UTCHMMA, smem-port bound), so the splitter warps stage A_hi / A_lo into TMEM.
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -160,33 +196,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t lo_base = smem_base + TC_RAW_STAGES * TC_STAGE_BYTES;
-  const uint32_t bars = lo_base + TC_LO_STAGES * TC_STAGE_BYTES;
-  auto raw_full = [&](int s) { return bars + 8u * s; };
-  auto raw_empty = [&](int s) { return bars + 8u * (TC_RAW_STAGES + s); };
-  auto lo_ready = [&](int s) { return bars + 8u * (2 * TC_RAW_STAGES + s); };
-  auto lo_empty = [&](int s) { return bars + 8u * (2 * TC_RAW_STAGES + TC_LO_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_RAW_STAGES + 2 * TC_LO_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_RAW_STAGES + 2 * TC_LO_STAGES + 2 + a); };
+  const uint32_t blo_base = smem_base + TC_STAGES * TC_RAW_BYTES;          // B_lo ring
+  const uint32_t bars = blo_base + TC_STAGES * TC_B_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };                     // TMA bytes landed
+  auto ready_bar = [&](int s) { return bars + 8u * (TC_STAGES + s); };      // A in TMEM, B_lo in smem
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };  // MMAs of the stage retired
+  auto tfull_bar = [&](int a) { return bars + 8u * (3 * TC_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (3 * TC_STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * TC_NBARS;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + (TC_RAW_STAGES + TC_LO_STAGES) * TC_STAGE_BYTES + 8 * TC_NBARS);
+      smem_gen + TC_STAGES * (TC_RAW_BYTES + TC_B_BYTES) + 8 * TC_NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = p.mm_tiles * p.nn_tiles * p.splits;
   long long tacc[6] = {0, 0, 0, 0, 0, 0};
-  const long long t_begin = clock64();
+  const long long t_begin = TCLOCK();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < TC_RAW_STAGES; ++s) {
-      mbar_init(raw_full(s), 1);
-      mbar_init(raw_empty(s), 1);
-    }
-    for (int s = 0; s < TC_LO_STAGES; ++s) {
-      mbar_init(lo_ready(s), TC_SPLIT_THREADS / 32);   // one elected arrival per splitter warp
-      mbar_init(lo_empty(s), 1);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), TC_SPLIT_THREADS / 32);   // one elected arrival per splitter warp
+      mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -194,8 +226,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 2 accumulators x 64 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128));
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -216,156 +249,162 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform; one elected lane issues) =====
-    {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        int mt, nt, kb0, kb1;
-        decode(w, mt, nt, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          TWAIT(0, raw_empty(s), ph ^ 1);
-          const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-          if (elect_one()) {
-          mbar_expect_tx(raw_full(s), ((p.dbg_load & 1) ? TC_A_BYTES : 0) + ((p.dbg_load & 2) ? TC_B_BYTES : 0));
-          if (!(p.dbg_load & 1)) {
-          } else if (A_KMAJOR) {
-            tma_load_2d(st, &tmA, raw_full(s), kb * TC_BK, mt * TC_BM);
-          } else {
-#pragma unroll
-            for (int c = 0; c < TC_BM / 32; ++c)
-              tma_load_2d(st + c * 4096, &tmA, raw_full(s), mt * TC_BM + c * 32, kb * TC_BK);
-          }
-          const uint32_t sb = st + TC_A_BYTES;
-          if (!(p.dbg_load & 2)) {
-          } else if (B_KMAJOR) {
-            tma_load_2d(sb, &tmB, raw_full(s), kb * TC_BK, nt * TC_BN);
-          } else {
-#pragma unroll
-            for (int c = 0; c < TC_BN / 32; ++c)
-              tma_load_2d(sb + c * 4096, &tmB, raw_full(s), nt * TC_BN + c * 32, kb * TC_BK);
-          }
-          }
-          __syncwarp();
-          if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-      if (p.dbg_t && blockIdx.x == 0 && lane == 0) { p.dbg_t[0] = tacc[0]; p.dbg_t[1] = clock64() - t_begin; }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform; one elected lane issues) =====
-    {
-      // instruction descriptor: D=f32, A=B=tf32, majors, N, M
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
-                             ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
-                             ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t a_lbo = A_KMAJOR ? 16u : 4096u, b_lbo = B_KMAJOR ? 16u : 4096u;
-      const uint32_t a_kstep = A_KMAJOR ? 32u : 1024u, b_kstep = B_KMAJOR ? 32u : 1024u;   // bytes per UMMA_K = 8
-      const uint32_t a_sbo = A_KMAJOR ? 1024u : 512u, b_sbo = B_KMAJOR ? 1024u : 512u;
-      const uint32_t a_lt = A_KMAJOR ? 2u : 1u, b_lt = B_KMAJOR ? 2u : 1u;
-      // descriptor words (see make_desc): hi = SBO | version<<14 | layout<<29 ; lo = addr>>4 | (LBO>>4)<<16
-      const uint32_t desc_hi_a = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (a_lt << 29);
-      const uint32_t desc_hi_b = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (b_lt << 29);
-      const uint32_t desc_lo_a = ((smem_base >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
-      const uint32_t desc_lbo_delta_b = ((b_lbo >> 4) << 16) - ((a_lbo >> 4) << 16);   // B's LBO field relative to A's
-      int s = 0, l = 0, ci = 0;   // raw stage, lo stage, chunk counter (selects the TMEM accumulator)
-      uint32_t ph = 0, lph = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        int mt, nt, kb0, kb1;
-        decode(w, mt, nt, kb0, kb1);
-        for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
-          const int kc1 = min(kc0 + TC_FLUSH_KB, kb1);
-          const int acc = ci & 1;
-          TWAIT(0, tempty_bar(acc), ((ci >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * TC_BN;
-          for (int kb = kc0; kb < kc1; ++kb) {
-            TWAIT(1, raw_full(s), ph);
-            TWAIT(2, lo_ready(l), lph);
-            tc_fence_after();
-            // descriptors live in uniform registers: constant high word per operand, low word = start
-            // address field advanced by one add per stage / k-step (the uniform datapath is slow)
-            const uint32_t ra = desc_lo_a + (uint32_t)s * (TC_STAGE_BYTES >> 4);            // A_hi (raw ring)
-            const uint32_t rb = ra + (TC_A_BYTES >> 4);                                       // B_hi
-            const uint32_t la = desc_lo_a + (uint32_t)(TC_RAW_STAGES + l) * (TC_STAGE_BYTES >> 4);   // A_lo
-            const uint32_t lb = la + (TC_A_BYTES >> 4);                                       // B_lo
-            uint64_t dah[TC_BK / 8], dal[TC_BK / 8], dbh[TC_BK / 8], dbl[TC_BK / 8];
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
-              dah[k] = ((uint64_t)desc_hi_a << 32) | (uint64_t)(ra + k * (a_kstep >> 4));
-              dal[k] = ((uint64_t)desc_hi_a << 32) | (uint64_t)(la + k * (a_kstep >> 4));
-              dbh[k] = ((uint64_t)desc_hi_b << 32) | (uint64_t)(rb + k * (b_kstep >> 4) + desc_lbo_delta_b);
-              dbl[k] = ((uint64_t)desc_hi_b << 32) | (uint64_t)(lb + k * (b_kstep >> 4) + desc_lbo_delta_b);
-            }
-            const uint32_t first = kb > kc0 ? 1u : 0u;
-            const uint32_t bar_raw = raw_empty(s), bar_lo = lo_empty(l);
-            const long long t_i0 = clock64();
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < TC_BK / 8; ++k) {
-                if (p.dbg_mmas >= 3) {
-                  umma_tf32(d_tmem, dah[k], dbl[k], idesc, k > 0 ? 1u : first);   // small terms first
-                  umma_tf32(d_tmem, dal[k], dbh[k], idesc, 1u);
-                  umma_tf32(d_tmem, dah[k], dbh[k], idesc, 1u);
-                } else if (p.dbg_mmas == 2) {
-                  umma_tf32(d_tmem, dal[k], dbh[k], idesc, k > 0 ? 1u : first);
-                  umma_tf32(d_tmem, dah[k], dbh[k], idesc, 1u);
-                } else {
-                  umma_tf32(d_tmem, dah[k], dbh[k], idesc, k > 0 ? 1u : first);
-                }
-              }
-            }
-            const long long t_i1 = clock64();
-            if (elect_one()) {
-              umma_commit(bar_raw);           // both rings are reusable when these MMAs retire
-              umma_commit(bar_lo);
-            }
-            const long long t_i2 = clock64();
-            tacc[3] += t_i1 - t_i0;
-            tacc[4] += t_i2 - t_i1;
-            __syncwarp();
-            if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
-            if (++l == TC_LO_STAGES) { l = 0; lph ^= 1; }
-          }
-          if (elect_one()) umma_commit(tfull_bar(acc));        // chunk partial complete
-          __syncwarp();
-        }
-      }
-      if (p.dbg_t && blockIdx.x == 0 && lane == 0) { p.dbg_t[2] = tacc[0]; p.dbg_t[3] = tacc[1]; p.dbg_t[4] = tacc[2]; p.dbg_t[5] = clock64() - t_begin; p.dbg_t[11] = tacc[3]; p.dbg_t[12] = tacc[4]; }
-    }
-  } else if (warp < 2 + TC_SPLIT_THREADS / 32) {
-    // ===== operand splitters: the tensor core reads hi = trunc_tf32(x) straight from the TMA tile;
-    //       these warps produce lo = rna_tf32(x - trunc_tf32(x)) into the lo ring =====
-    const int tid = threadIdx.x - 64;   // 0..TC_SPLIT_THREADS-1
-    int s = 0, l = 0;
-    uint32_t ph = 0, lph = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int mt, nt, kb0, kb1;
       decode(w, mt, nt, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb) {
-        TWAIT(0, raw_full(s), ph);
-        TWAIT(1, lo_empty(l), lph ^ 1);
-        const float4* raw = reinterpret_cast<const float4*>(smem_gen + s * TC_STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem_gen + (TC_RAW_STAGES + l) * TC_STAGE_BYTES);
-        constexpr int NV = TC_STAGE_BYTES / 16 / TC_SPLIT_THREADS;
-        float4 v[NV];
-        if (!p.dbg_nosplit) {
+        TWAIT(0, empty_bar(s), ph ^ 1);
+        const uint32_t st = smem_base + s * TC_RAW_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), TC_RAW_BYTES);
+          if (A_KMAJOR) {
+            tma_load_2d(st, &tmA, full_bar(s), kb * TC_BK, mt * TC_BM);
+          } else {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = raw[tid + i * TC_SPLIT_THREADS];
+            for (int c = 0; c < TC_BM / 32; ++c)
+              tma_load_2d(st + c * 4096, &tmA, full_bar(s), mt * TC_BM + c * 32, kb * TC_BK);
+          }
+          const uint32_t sb = st + TC_A_BYTES;
+          if (B_KMAJOR) {
+            tma_load_2d(sb, &tmB, full_bar(s), kb * TC_BK, nt * TC_BN);
+          } else {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          float4 r;
-          r.x = lo_tf32(v[i].x); r.y = lo_tf32(v[i].y); r.z = lo_tf32(v[i].z); r.w = lo_tf32(v[i].w);
-          lo[tid + i * TC_SPLIT_THREADS] = r;
+            for (int c = 0; c < TC_BN / 32; ++c)
+              tma_load_2d(sb + c * 4096, &tmB, full_bar(s), nt * TC_BN + c * 32, kb * TC_BK);
+          }
         }
-        }
-        fence_async_smem();                 // generic-proxy writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) mbar_arrive(lo_ready(l));
-        if (++s == TC_RAW_STAGES) { s = 0; ph ^= 1; }
-        if (++l == TC_LO_STAGES) { l = 0; lph ^= 1; }
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       }
     }
-    if (p.dbg_t && blockIdx.x == 0 && tid == 0) { p.dbg_t[6] = tacc[0]; p.dbg_t[7] = tacc[1]; p.dbg_t[8] = clock64() - t_begin; }
+    if (p.dbg_t && blockIdx.x == 0 && lane == 0) { p.dbg_t[0] = tacc[0]; p.dbg_t[1] = TCLOCK() - t_begin; }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform; one elected lane issues) =====
+    // instruction descriptor: D=f32, A=B=tf32, A K-major (TMEM), B major, N, M
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_KMAJOR ? 0u : 1u) << 16) |
+                           ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t b_lbo = B_KMAJOR ? 16u : 4096u;
+    const uint32_t b_kstep = B_KMAJOR ? 32u : 1024u;   // bytes per UMMA_K = 8
+    const uint32_t b_sbo = B_KMAJOR ? 1024u : 512u;
+    const uint32_t b_lt = B_KMAJOR ? 2u : 1u;
+    // descriptor words (see make_desc): hi = SBO | version<<14 | layout<<29 ; lo = addr>>4 | (LBO>>4)<<16
+    const uint32_t desc_hi_b = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (b_lt << 29);
+    const uint32_t desc_lo_bhi = (((smem_base + TC_A_BYTES) >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
+    const uint32_t desc_lo_blo = ((blo_base >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
+    int s = 0, ci = 0;   // stage, chunk counter (selects the TMEM accumulator)
+    uint32_t ph = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int mt, nt, kb0, kb1;
+      decode(w, mt, nt, kb0, kb1);
+      for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
+        const int kc1 = min(kc0 + TC_FLUSH_KB, kb1);
+        const int acc = ci & 1;
+        TWAIT(0, tempty_bar(acc), ((ci >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_BN;
+        for (int kb = kc0; kb < kc1; ++kb) {
+          TWAIT(1, ready_bar(s), ph);
+          tc_fence_after();
+          // operands: A_hi / A_lo in TMEM (columns), B_hi in the TMA stage, B_lo in the B_lo ring
+          const uint32_t a_t = tmem_base + TC_TMEM_ACC + (uint32_t)s * TC_TMEM_ASTAGE;
+          const uint32_t rb = desc_lo_bhi + (uint32_t)s * (TC_RAW_BYTES >> 4);
+          const uint32_t lb = desc_lo_blo + (uint32_t)s * (TC_B_BYTES >> 4);
+          uint64_t dbh[TC_BK / 8], dbl[TC_BK / 8];
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            dbh[k] = ((uint64_t)desc_hi_b << 32) | (uint64_t)(rb + k * (b_kstep >> 4));
+            dbl[k] = ((uint64_t)desc_hi_b << 32) | (uint64_t)(lb + k * (b_kstep >> 4));
+          }
+          const uint32_t first = kb > kc0 ? 1u : 0u;
+          const uint32_t bar_e = empty_bar(s);
+          const long long t_i0 = TCLOCK();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+              const uint32_t a_hi = a_t + k * 8, a_lo = a_t + TC_BK + k * 8;
+              umma_tf32_ts(d_tmem, a_hi, dbl[k], idesc, k > 0 ? 1u : first);   // small terms first
+              umma_tf32_ts(d_tmem, a_lo, dbh[k], idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi, dbh[k], idesc, 1u);
+            }
+            umma_commit(bar_e);               // stage (smem + TMEM) reusable when these MMAs retire
+          }
+          tacc[3] += TCLOCK() - t_i0;
+          __syncwarp();
+          if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) umma_commit(tfull_bar(acc));        // chunk partial complete
+        __syncwarp();
+      }
+    }
+    if (p.dbg_t && blockIdx.x == 0 && lane == 0) {
+      p.dbg_t[2] = tacc[0]; p.dbg_t[3] = tacc[1]; p.dbg_t[4] = 0; p.dbg_t[5] = TCLOCK() - t_begin;
+      p.dbg_t[11] = tacc[3]; p.dbg_t[12] = 0;
+    }
+  } else if (warp < 2 + TC_SPLIT_THREADS / 32) {
+    // ===== operand splitters =====
+    // A: each thread owns one tile row (= its TMEM lane) and half of the k-block: reads 16 fp32 from the TMA
+    //    tile, writes hi and lo (exact tf32 values) to tensor memory with tcgen05.st.
+    // B: lo = rna_tf32(x - trunc_tf32(x)) to the B_lo ring in shared memory (the tensor core truncates B_hi itself).
+    const int tid = threadIdx.x - 64;          // 0..255
+    const int q = warp & 3;                    // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;          // which 16 k of the 32
+    const int row = q * 32 + lane;             // tile row
+    int s = 0;
+    uint32_t ph = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int mt, nt, kb0, kb1;
+      decode(w, mt, nt, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        TWAIT(0, full_bar(s), ph);
+        tc_fence_after();                   // order the TMEM stores below after the stage hand-over
+        const uint8_t* rawA = smem_gen + s * TC_RAW_BYTES;
+        uint32_t v[16];
+        if (A_KMAJOR) {
+          // row r at r*128 B, 16-byte chunk c stored at c ^ (r & 7)   (SWIZZLE_128B)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = (half * 4 + c) ^ (row & 7);
+            const uint4 t4 = *reinterpret_cast<const uint4*>(rawA + row * 128 + chunk * 16);
+            v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+          }
+        } else {
+          // 32-row (mm) chunks of 4 KB; inside: k-row at k*128 B, 32-byte atom a stored at a ^ (k & 3)
+          // (SWIZZLE_128B_ATOM_32B); this thread's mm = row -> chunk q, position lane
+          const uint8_t* base = rawA + q * 4096 + (lane & 7) * 4;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = half * 16 + j;
+            const int atom = (lane >> 3) ^ (k & 3);
+            v[j] = *reinterpret_cast<const uint32_t*>(base + k * 128 + atom * 32);
+          }
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_tf32(v[j], hi[j], lo[j]);
+        const uint32_t a_t = tmem_base + ((uint32_t)(q * 32) << 16) + TC_TMEM_ACC + (uint32_t)s * TC_TMEM_ASTAGE;
+        tmem_st16(a_t + half * 16, hi);
+        tmem_st16(a_t + TC_BK + half * 16, lo);
+        // B_lo: 512 float4 per stage, 2 per thread
+        const float4* rawB = reinterpret_cast<const float4*>(smem_gen + s * TC_RAW_BYTES + TC_A_BYTES);
+        float4* blo = reinterpret_cast<float4*>(smem_gen + TC_STAGES * TC_RAW_BYTES + s * TC_B_BYTES);
+#pragma unroll
+        for (int i = 0; i < TC_B_BYTES / 16 / TC_SPLIT_THREADS; ++i) {
+          const float4 x4 = rawB[tid + i * TC_SPLIT_THREADS];
+          float4 r;
+          r.x = lo_tf32(x4.x); r.y = lo_tf32(x4.y); r.z = lo_tf32(x4.z); r.w = lo_tf32(x4.w);
+          blo[tid + i * TC_SPLIT_THREADS] = r;
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        fence_async_smem();                 // generic-proxy smem writes -> visible to the tensor core
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(s));
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    if (p.dbg_t && blockIdx.x == 0 && tid == 0) { p.dbg_t[6] = tacc[0]; p.dbg_t[7] = 0; p.dbg_t[8] = TCLOCK() - t_begin; }
   } else {
     // ===== epilogue: promote each chunk partial TMEM -> registers (fp32 RN adds), write the tile =====
     const int q = warp & 3;              // TMEM lane quarter this warp may read
@@ -426,14 +465,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
+    if (p.dbg_t && blockIdx.x == 0 && threadIdx.x == TC_THREADS - 128) { p.dbg_t[9] = tacc[0]; p.dbg_t[10] = TCLOCK() - t_begin; }
   }
 
-  if (p.dbg_t && blockIdx.x == 0 && threadIdx.x == TC_THREADS - 128) { p.dbg_t[9] = tacc[0]; p.dbg_t[10] = clock64() - t_begin; }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
   }
 }
 
@@ -535,7 +574,8 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
   const int64_t tiles = (int64_t)p.mm_tiles * p.nn_tiles;
   int splits = 1;
   if (tiles < c.num_sms && p.kblocks_total >= 16) {
-    splits = (int)cdiv(2 * (int64_t)c.num_sms, tiles);
+    splits = (int)(c.num_sms / tiles);  // one work item per CTA: tiles*splits <= SMs (a second partial wave
+                                        // would leave most SMs idle for a whole item)
     int maxs = p.kblocks_total / 8;     // >= 8 k-blocks (256 k) per split
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
@@ -560,9 +600,6 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
     p.split_stride = 0;
     p.alpha = (float)alpha;
   }
-  p.dbg_mmas = getenv("AGB_TC_MMAS") ? atoi(getenv("AGB_TC_MMAS")) : 3;
-  p.dbg_nosplit = getenv("AGB_TC_NOSPLIT") ? 1 : 0;
-  p.dbg_load = getenv("AGB_TC_LOAD") ? atoi(getenv("AGB_TC_LOAD")) : 3;
   static long long* dbg_t_dev = nullptr;
   p.dbg_t = nullptr;
   if (getenv("AGB_TC_TIMING")) {
@@ -588,13 +625,15 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
   else LAUNCH(false, false);
 #undef LAUNCH
   AG_LAUNCHED();
+#ifdef AGB_TC_TIMING
   if (p.dbg_t) {
     long long h[16];
     cudaStreamSynchronize(c.stream);
     cudaMemcpy(h, p.dbg_t, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "tc timing (block 0, cycles): work=%lld kb/tile=%d | producer wait_empty=%lld total=%lld | mma wait_tempty=%lld wait_full=%lld wait_lo=%lld total=%lld | split wait_full=%lld wait_loempty=%lld total=%lld | epi wait_tfull=%lld total=%lld | mma issue=%lld commit=%lld\n",
+    fprintf(stderr, "tc timing (block 0, cycles): work=%lld kb/tile=%d | producer wait_empty=%lld total=%lld | mma wait_tempty=%lld wait_full=%lld wait_lo=%lld total=%lld | split wait_full=%lld (unused)=%lld total=%lld | epi wait_tfull=%lld total=%lld | mma issue=%lld commit=%lld\n",
             (long long)((work + grid - 1) / grid), p.kblocks_per_split, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
   }
+#endif
   if (via_ws) {
     k_tc_splitk_reduce<<<(unsigned)cdiv(M * N, 256), 256, 0, c.stream>>>(p.out, splits, M, N, (float)alpha,
                                                                         (float)beta, (float*)C, ldc);
