@@ -222,77 +222,75 @@ struct MapArgs {
   bool big;  // n >= 2^31: 64-bit index arithmetic
 };
 
-template <typename T, int NIN, typename F, bool VEC>
+// ND = 2: at most two collapsed dims (one division per item, none when shape[1] == 1); ND = 4: general.
+// All loads of the kUnroll items of a thread are issued before any arithmetic (memory-level parallelism).
+template <typename T, int NIN, typename F, bool VEC, int ND>
 __global__ void __launch_bounds__(kThreads) k_map(const MapArgs<NIN> a) {
   constexpr int N = VEC ? Pack<T>::N : 1;
-  // element index of this thread's first item in each unrolled slot
   const int64_t base = ((int64_t)blockIdx.x * kUnroll * kThreads + threadIdx.x) * N;
   T* __restrict__ out = (T*)a.out;
+  T v[kUnroll][NIN][N];
+  bool ok[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u) {
     const int64_t i = base + (int64_t)u * kThreads * N;
-    if (i >= a.n) break;
-    // decompose i into (i0, i1, i2, i3)
-    int64_t idx[4] = {i, 0, 0, 0};
-    if (a.nd > 1) {
-      if (a.big) {
-        int64_t r = i;
-        for (int d = 0; d < a.nd - 1; ++d) {
-          int64_t q = r / a.shape[d];
-          idx[d] = r - q * a.shape[d];
-          r = q;
-        }
-        idx[a.nd - 1] = r;
-      } else {
-        uint32_t r = (uint32_t)i;
-        for (int d = 0; d < a.nd - 1; ++d) {
-          uint32_t sd = (uint32_t)a.shape[d];
-          uint32_t q = r / sd;
-          idx[d] = r - q * sd;
-          r = q;
-        }
-        idx[a.nd - 1] = r;
+    ok[u] = i < a.n;
+    if (!ok[u]) continue;
+    int64_t i0 = i, i1 = 0, i2 = 0, i3 = 0;
+    if (ND == 2) {
+      if (a.shape[1] != 1) {
+        if (a.big) { i1 = i / a.shape[0]; i0 = i - i1 * a.shape[0]; }
+        else { uint32_t q = (uint32_t)i / (uint32_t)a.shape[0]; i1 = q; i0 = (uint32_t)i - q * (uint32_t)a.shape[0]; }
       }
+    } else {
+      int64_t r = i;
+      int64_t q = r / a.shape[0]; i0 = r - q * a.shape[0]; r = q;
+      q = r / a.shape[1]; i1 = r - q * a.shape[1]; r = q;
+      q = r / a.shape[2]; i2 = r - q * a.shape[2]; i3 = q;
     }
-    T v[NIN][N];
 #pragma unroll
     for (int k = 0; k < NIN; ++k) {
       const Opnd& o = a.in[k];
       if (o.mode == 0) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) v[k][j] = (T)o.imm;
+        for (int j = 0; j < N; ++j) v[u][k][j] = (T)o.imm;
       } else {
         const T* __restrict__ p = (const T*)o.p;
-        int64_t off = idx[0] * o.s[0];
-        for (int d = 1; d < a.nd; ++d) off += idx[d] * o.s[d];
+        int64_t off = i0 * o.s[0] + i1 * o.s[1];
+        if (ND > 2) off += i2 * o.s[2] + i3 * o.s[3];
         if (VEC && o.mode == 1) {
-          Pack<T> t = *reinterpret_cast<const Pack<T>*>(p + off);
+          const Pack<T> t = *reinterpret_cast<const Pack<T>*>(p + off);
 #pragma unroll
-          for (int j = 0; j < N; ++j) v[k][j] = t.v[j];
+          for (int j = 0; j < N; ++j) v[u][k][j] = t.v[j];
         } else if (o.mode == 2) {
-          T t = p[off];
+          const T t = p[off];
 #pragma unroll
-          for (int j = 0; j < N; ++j) v[k][j] = t;
+          for (int j = 0; j < N; ++j) v[u][k][j] = t;
         } else {
 #pragma unroll
-          for (int j = 0; j < N; ++j) v[k][j] = p[off + j * o.s[0]];
+          for (int j = 0; j < N; ++j) v[u][k][j] = p[off + j * o.s[0]];
         }
       }
     }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    if (!ok[u]) continue;
+    const int64_t i = base + (int64_t)u * kThreads * N;
     if (VEC) {
       Pack<T> r;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         T in[NIN];
 #pragma unroll
-        for (int k = 0; k < NIN; ++k) in[k] = v[k][j];
+        for (int k = 0; k < NIN; ++k) in[k] = v[u][k][j];
         r.v[j] = F::apply(in);
       }
       *reinterpret_cast<Pack<T>*>(out + i) = r;
     } else {
       T in[NIN];
 #pragma unroll
-      for (int k = 0; k < NIN; ++k) in[k] = v[k][0];
+      for (int k = 0; k < NIN; ++k) in[k] = v[u][k][0];
       out[i] = F::apply(in);
     }
   }
@@ -373,14 +371,18 @@ static ag_status launch_map(MapArgs<NIN>& a) {
     }
   }
   a.big = a.n >= ((int64_t)1 << 31);
+  for (int d = a.nd; d < 4; ++d) a.shape[d] = 1;
+  const bool nd2 = a.nd <= 2;
   if (vec) {
     int64_t blocks = cdiv(a.n, (int64_t)kThreads * kUnroll * N);
-    k_map<T, NIN, F, true><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
+    if (nd2) k_map<T, NIN, F, true, 2><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
+    else k_map<T, NIN, F, true, 4><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
   } else {
     for (int k = 0; k < NIN; ++k)
       if (a.in[k].mode == 1) a.in[k].mode = 3;
     int64_t blocks = cdiv(a.n, (int64_t)kThreads * kUnroll);
-    k_map<T, NIN, F, false><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
+    if (nd2) k_map<T, NIN, F, false, 2><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
+    else k_map<T, NIN, F, false, 4><<<(unsigned)blocks, kThreads, 0, c.stream>>>(a);
   }
   AG_LAUNCHED();
   return AG_OK;

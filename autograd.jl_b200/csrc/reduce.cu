@@ -128,6 +128,52 @@ __global__ void __launch_bounds__(kRT)
   }
 }
 
+// Vector variant of the above for inner | kRT*N (N = elements per 16 bytes): every thread streams 128-bit
+// loads with stride kRT*N elements, so its N lanes always belong to the same N consecutive i.
+// grid (outer, nchunks); partial/out layout [o][c][i].
+template <int MAP, typename T, typename TO>
+__global__ void __launch_bounds__(kRT)
+    k_strided_vec(const T* __restrict__ x, int64_t inner, int64_t red, int64_t rows_per_chunk,
+                  TO* __restrict__ out) {
+  constexpr int N = 16 / sizeof(T);
+  struct alignas(16) V { T v[N]; };
+  __shared__ double sm[kRT * N];
+  const int64_t o = blockIdx.x, c = blockIdx.y;
+  const int t = threadIdx.x;
+  int64_t r0 = c * rows_per_chunk, r1 = r0 + rows_per_chunk;
+  if (r1 > red) r1 = red;
+  const T* __restrict__ p = x + o * inner * red;
+  const int64_t lo = r0 * inner, hi = r1 * inner, S = (int64_t)kRT * N;
+  T a0[N], a1[N], a2[N], a3[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) a0[j] = a1[j] = a2[j] = a3[j] = T(0);
+  int64_t q = lo + (int64_t)t * N;
+  for (; q + 3 * S < hi; q += 4 * S) {
+    const V v0 = *reinterpret_cast<const V*>(p + q), v1 = *reinterpret_cast<const V*>(p + q + S),
+            v2 = *reinterpret_cast<const V*>(p + q + 2 * S), v3 = *reinterpret_cast<const V*>(p + q + 3 * S);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      a0[j] += premap<MAP>(v0.v[j]); a1[j] += premap<MAP>(v1.v[j]);
+      a2[j] += premap<MAP>(v2.v[j]); a3[j] += premap<MAP>(v3.v[j]);
+    }
+  }
+  for (; q < hi; q += S) {
+    const V v0 = *reinterpret_cast<const V*>(p + q);
+#pragma unroll
+    for (int j = 0; j < N; ++j) a0[j] += premap<MAP>(v0.v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) sm[t * N + j] = ((double)a0[j] + (double)a1[j]) + ((double)a2[j] + (double)a3[j]);
+  __syncthreads();
+  if (t < inner) {
+    double s = 0;
+    const int groups = (int)(S / inner);       // threads per i-group
+    const int gstride = (int)(inner / N);      // thread distance between members of a group
+    for (int m = 0; m < groups; ++m) s += sm[((t / N) + m * gstride) * N + (t % N)];
+    out[(o * gridDim.y + c) * inner + t] = (TO)s;
+  }
+}
+
 // inner > kRT: thread per i, loop over the chunk's rows.  grid (outer, nchunks, itiles)
 template <int MAP, typename T, typename TI, typename TO>
 __global__ void __launch_bounds__(kRT)
@@ -149,6 +195,28 @@ __global__ void __launch_bounds__(kRT)
   for (; r < r1; ++r) a0 += premap<MAP>((T)p[r * inner]);
   double s = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
   out[(o * gridDim.y + c) * inner + i] = (TO)s;
+}
+
+// phase 2 of the strided reductions: out[i,o] = sum_c part[o][c][i]; 16 outputs x 16 lanes per block, each lane
+// sums every 16th partial, fixed-order combine (deterministic).  grid (ceil(inner/16), outer)
+template <typename TO>
+__global__ void __launch_bounds__(256)
+    k_partials_reduce(const double* __restrict__ part, int nchunks, int64_t inner, TO* __restrict__ out) {
+  __shared__ double sm[16][17];
+  const int li = threadIdx.x % 16, g = threadIdx.x / 16;
+  const int64_t i = (int64_t)blockIdx.x * 16 + li, o = blockIdx.y;
+  const double* __restrict__ p = part + o * nchunks * inner;
+  double s = 0;
+  if (i < inner)
+    for (int c = g; c < nchunks; c += 16) s += p[(int64_t)c * inner + i];
+  sm[g][li] = s;
+  __syncthreads();
+  if (g == 0 && i < inner) {
+    double r = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) r += sm[q][li];
+    out[o * inner + i] = (TO)r;
+  }
 }
 
 // Partials are kept in double in the workspace so the second phase loses nothing.
@@ -195,6 +263,33 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
   }
 
   // strided
+  constexpr int VN = 16 / sizeof(T);
+  const bool vecok = inner <= kRT && inner % VN == 0 && ((int64_t)kRT * VN) % inner == 0 &&
+                     (((uintptr_t)x) & 15) == 0 && red >= 64;
+  if (vecok) {
+    const int64_t rows_per_step = (int64_t)kRT * VN / inner;
+    int64_t nchunks = cdiv((int64_t)c.num_sms * 4, outer);
+    int64_t maxc = cdiv(red, rows_per_step * 4);
+    if (nchunks > maxc) nchunks = maxc;
+    if (nchunks < 1) nchunks = 1;
+    AG_CHECK(outer <= 65535 || nchunks == 1, AG_EUNSUPPORTED, "ag_sum_dim: outer extent too large");
+    int64_t rows = cdiv(red, nchunks);
+    nchunks = cdiv(red, rows);
+    if (nchunks == 1) {
+      k_strided_vec<MAP, T, T><<<dim3((unsigned)outer, 1), kRT, 0, c.stream>>>(x, inner, red, rows, out);
+      AG_LAUNCHED();
+      return AG_OK;
+    }
+    double* part = (double*)workspace((size_t)(nchunks * outer * inner) * sizeof(double));
+    if (!part) return AG_ENOMEM;
+    k_strided_vec<MAP, T, double><<<dim3((unsigned)outer, (unsigned)nchunks), kRT, 0, c.stream>>>(x, inner, red,
+                                                                                                 rows, part);
+    AG_LAUNCHED();
+    k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 16), (unsigned)outer), 256, 0, c.stream>>>(
+        part, (int)nchunks, inner, out);
+    AG_LAUNCHED();
+    return AG_OK;
+  }
   const bool small = inner <= kRT;
   const int64_t itiles = small ? 1 : cdiv(inner, kRT);
   AG_CHECK(itiles <= 65535, AG_EUNSUPPORTED, "ag_sum_dim: inner extent %lld too large",
@@ -203,9 +298,9 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
   int64_t nchunks = 1;
   if (outer * itiles < target_blocks && red > 256) {
     nchunks = cdiv(target_blocks, outer * itiles);
-    int64_t maxc = cdiv(red, rows_per_iter * 16);
+    int64_t maxc = cdiv(red, rows_per_iter * 8);
     if (nchunks > maxc) nchunks = maxc;
-    if (nchunks > 256) nchunks = 256;
+    if (nchunks > 1024) nchunks = 1024;
     if (nchunks < 1) nchunks = 1;
   }
   int64_t rows = cdiv(red, nchunks);
@@ -228,13 +323,11 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
     k_strided_large<MAP, T, T, double><<<dim3((unsigned)outer, (unsigned)nchunks, (unsigned)itiles), kRT, 0,
                                           c.stream>>>(x, inner, red, rows, part);
   AG_LAUNCHED();
-  // phase 2: partials (inner, nchunks, outer) -> out (inner, outer); nchunks <= 256 so one chunk
-  if (small)
-    k_strided_small<AG_R_ID, double, double, T><<<dim3((unsigned)outer, 1), kRT, 0, c.stream>>>(
-        part, inner, nchunks, nchunks, out);
-  else
-    k_strided_large<AG_R_ID, double, double, T><<<dim3((unsigned)outer, 1, (unsigned)itiles), kRT, 0,
-                                                  c.stream>>>(part, inner, nchunks, nchunks, out);
+  // phase 2: partials (inner, nchunks, outer) -> out (inner, outer)
+  AG_CHECK(outer <= 65535, AG_EUNSUPPORTED, "ag_sum_dim: outer extent %lld too large for a split reduction",
+           (long long)outer);
+  k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 16), (unsigned)outer), 256, 0, c.stream>>>(part, (int)nchunks,
+                                                                                                inner, out);
   AG_LAUNCHED();
   return AG_OK;
 }

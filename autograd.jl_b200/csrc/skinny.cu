@@ -127,6 +127,153 @@ __global__ void __launch_bounds__(SK_T)
   }
 }
 
+// ---- S1 (column-per-thread form): C[:, col] = op(A) * B[:, col] ---------------------------------------
+// One thread owns one column of the wide operand: it streams the column's K values straight from
+// global memory (each thread walks whole cache lines; the warp's 32 columns are one contiguous run) and keeps
+// MB accumulators in registers; op(A) sits in shared memory as As[k][m] and is read with broadcast
+// 128-bit loads.  No staging of the wide operand, no block-level synchronisation in the main loop.
+template <typename T, int MB>
+__global__ void __launch_bounds__(128)
+    k_skinny_cols(int transA, int M, int64_t N, int K, T alpha, const T* __restrict__ A, int64_t lda,
+                  const T* __restrict__ B, int64_t ldb, T beta, T* __restrict__ C, int64_t ldc) {
+  __shared__ __align__(16) T As[SK_MAXD * MB];     // As[k*MB + m], zero padded to MB rows
+  for (int i = threadIdx.x; i < K * MB; i += 128) {
+    const int k = i / MB, m = i % MB;
+    T v = T(0);
+    if (m < M) v = transA ? A[k + (int64_t)m * lda] : A[m + (int64_t)k * lda];
+    As[i] = v;
+  }
+  __syncthreads();
+  const int64_t col = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (col >= N) return;
+  const T* __restrict__ b = B + col * ldb;
+  T acc[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc[m] = T(0);
+  int k = 0;
+  // 128-bit loads of the column when its start is 16-byte aligned (K%4==0 and ldb%4==0 for Float32)
+  constexpr int NV = 16 / sizeof(T);
+  if ((ldb % NV) == 0 && ((((uintptr_t)B) & 15) == 0) && NV == 4) {
+    for (; k + 8 <= K; k += 8) {
+      struct alignas(16) V { T v[4]; };
+      const V q0 = *reinterpret_cast<const V*>(b + k), q1 = *reinterpret_cast<const V*>(b + k + 4);
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        T t = acc[m];
+        t = fma(As[k * MB + m], q0.v[0], t);
+        t = fma(As[(k + 1) * MB + m], q0.v[1], t);
+        t = fma(As[(k + 2) * MB + m], q0.v[2], t);
+        t = fma(As[(k + 3) * MB + m], q0.v[3], t);
+        t = fma(As[(k + 4) * MB + m], q1.v[0], t);
+        t = fma(As[(k + 5) * MB + m], q1.v[1], t);
+        t = fma(As[(k + 6) * MB + m], q1.v[2], t);
+        t = fma(As[(k + 7) * MB + m], q1.v[3], t);
+        acc[m] = t;
+      }
+    }
+  }
+  for (; k + 4 <= K; k += 4) {
+    const T b0 = b[k], b1 = b[k + 1], b2 = b[k + 2], b3 = b[k + 3];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      acc[m] = fma(As[k * MB + m], b0, acc[m]);
+      acc[m] = fma(As[(k + 1) * MB + m], b1, acc[m]);
+      acc[m] = fma(As[(k + 2) * MB + m], b2, acc[m]);
+      acc[m] = fma(As[(k + 3) * MB + m], b3, acc[m]);
+    }
+  }
+  for (; k < K; ++k) {
+    const T b0 = b[k];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) acc[m] = fma(As[k * MB + m], b0, acc[m]);
+  }
+  T* __restrict__ c = C + col * ldc;
+  if (beta == T(0)) {
+    if (MB == M && (ldc * sizeof(T)) % 16 == 0 && (((uintptr_t)C) & 15) == 0) {
+      constexpr int NV = 16 / sizeof(T);
+#pragma unroll
+      for (int m = 0; m < MB; m += NV) {
+        struct alignas(16) V { T v[NV]; } o;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) o.v[j] = alpha * acc[m + j];
+        *reinterpret_cast<V*>(c + m) = o;
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < MB; ++m)
+        if (m < M) c[m] = alpha * acc[m];
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < MB; ++m)
+      if (m < M) c[m] = alpha * acc[m] + beta * c[m];
+  }
+}
+
+// ---- S2 (warp form, M <= 16, N <= 64): part[blk][m + M*n] = sum_{k in block range} A[m,k]*B[n,k] ----------
+// Each warp walks a contiguous k-range: lanes own n = lane and lane+32 (coalesced row reads of B), the M
+// values A[:,k] are warp-uniform (broadcast loads).  Block partials are combined through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(128)
+    k_skinny_nt_warp(int M, int N, int64_t K, int64_t kc, const T* __restrict__ A, int64_t lda,
+                     const T* __restrict__ B, int64_t ldb, T* __restrict__ part) {
+  constexpr int MB = 16;
+  constexpr int NW = 4;
+  __shared__ T sm[NW][MB * 64];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t k0 = (int64_t)blockIdx.x * kc;
+  const int64_t k1 = min(K, k0 + kc);
+  T acc0[MB], acc1[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc0[m] = acc1[m] = T(0);
+  const bool n0ok = lane < N, n1ok = lane + 32 < N;
+  int64_t k = k0 + wrp;
+  for (; k + 3 * NW < k1; k += 4 * NW) {      // four k per trip: all loads issued before the FMAs
+    T bb0[4], bb1[4], av[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const T* __restrict__ b = B + (k + u * NW) * ldb;
+      bb0[u] = n0ok ? b[lane] : T(0);
+      bb1[u] = n1ok ? b[lane + 32] : T(0);
+      av[u] = lane < M ? A[(k + u * NW) * lda + lane] : T(0);     // lane m holds A[m,k]
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        const T a = __shfl_sync(0xffffffffu, av[u], m);
+        acc0[m] = fma(a, bb0[u], acc0[m]);
+        acc1[m] = fma(a, bb1[u], acc1[m]);
+      }
+    }
+  }
+  for (; k < k1; k += NW) {
+    const T* __restrict__ b = B + k * ldb;
+    const T b0 = n0ok ? b[lane] : T(0), b1 = n1ok ? b[lane + 32] : T(0);
+    const T avl = lane < M ? A[k * lda + lane] : T(0);
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const T a = __shfl_sync(0xffffffffu, avl, m);
+      acc0[m] = fma(a, b0, acc0[m]);
+      acc1[m] = fma(a, b1, acc1[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    sm[wrp][m * 64 + lane] = acc0[m];
+    sm[wrp][m * 64 + lane + 32] = acc1[m];
+  }
+  __syncthreads();
+  T* __restrict__ dst = part + (int64_t)blockIdx.x * M * N;
+  for (int i = threadIdx.x; i < M * N; i += 128) {
+    const int m = i % M, n = i / M;
+    T s = T(0);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += sm[w][m * 64 + n];
+    dst[i] = s;
+  }
+}
+
 // C[m + ldc*n] = alpha * sum_p part[p][i] (+ beta*C), i = m + M*n; 16 x 16 threads: 16 outputs per block,
 // 16 lanes each summing every 16th partial, then a fixed-order combine (deterministic).
 template <typename T>
@@ -168,6 +315,18 @@ static ag_status skinny_impl(int transA, int transB, int64_t M, int64_t N, int64
   Context& c = ctx();
   *done = false;
   if (!transB && M <= SK_MAXD && K <= SK_MAXD && N >= 512 && cdiv(N, SK_COLS) < ((int64_t)1 << 31)) {
+    if (true) {
+      const unsigned gridc = (unsigned)cdiv(N, 128);
+      if (M <= 4) k_skinny_cols<T, 4><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
+      else if (M <= 8) k_skinny_cols<T, 8><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
+      else if (M <= 12) k_skinny_cols<T, 12><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
+      else if (M <= 16) k_skinny_cols<T, 16><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
+      else if (M <= 32) k_skinny_cols<T, 32><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
+      else k_skinny_cols<T, 64><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
+      AG_LAUNCHED();
+      *done = true;
+      return AG_OK;
+    }
     const int sks = (int)K | 1, ms = (int)M | 1;
     const size_t smem = ((size_t)M * (K + 1) + (size_t)SK_COLS * (sks > ms ? sks : ms)) * sizeof(T);
     const unsigned grid = (unsigned)cdiv(N, SK_COLS);
@@ -191,11 +350,17 @@ static ag_status skinny_impl(int transA, int transB, int64_t M, int64_t N, int64
     return AG_OK;
   }
   if (!transA && transB && M <= SK_MAXD && N <= SK_MAXD && K >= 2048) {
-    int64_t nblk = 2 * (int64_t)c.num_sms;
+    int64_t nblk = (M <= 16 ? 8 : 2) * (int64_t)c.num_sms;
     int64_t kc = cdiv(cdiv(K, nblk), 32) * 32;
     nblk = cdiv(K, kc);
     T* part = (T*)workspace((size_t)(nblk * M * N) * sizeof(T));
     if (!part) return AG_ENOMEM;
+    if (M <= 16) {
+      k_skinny_nt_warp<T><<<(unsigned)nblk, 128, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part);
+      AG_LAUNCHED();
+      *done = true;
+      return reduce_partials<T>(part, (int)nblk, M, N, alpha, beta, C, ldc);
+    }
 #define SK_NT(NJ_) k_skinny_nt<T, NJ_><<<(unsigned)nblk, SK_T, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part)
     const int nj = (int)cdiv(M, 4);
     if (nj <= 1) SK_NT(1); else if (nj <= 2) SK_NT(2); else if (nj <= 3) SK_NT(3);
