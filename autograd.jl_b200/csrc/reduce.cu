@@ -197,24 +197,31 @@ __global__ void __launch_bounds__(kRT)
   out[(o * gridDim.y + c) * inner + i] = (TO)s;
 }
 
-// phase 2 of the strided reductions: out[i,o] = sum_c part[o][c][i]; 16 outputs x 16 lanes per block, each lane
-// sums every 16th partial, fixed-order combine (deterministic).  grid (ceil(inner/16), outer)
+// phase 2 of the strided reductions: out[i,o] = sum_c part[o][c][i]; 8 outputs x 32 lanes per block: a lane sums
+// every 32nd partial (8 consecutive outputs = one 64-byte run per load), fixed-order combine (deterministic).
+// grid (ceil(inner/8), outer)
 template <typename TO>
 __global__ void __launch_bounds__(256)
     k_partials_reduce(const double* __restrict__ part, int nchunks, int64_t inner, TO* __restrict__ out) {
-  __shared__ double sm[16][17];
-  const int li = threadIdx.x % 16, g = threadIdx.x / 16;
-  const int64_t i = (int64_t)blockIdx.x * 16 + li, o = blockIdx.y;
+  __shared__ double sm[32][9];
+  const int li = threadIdx.x % 8, g = threadIdx.x / 8;
+  const int64_t i = (int64_t)blockIdx.x * 8 + li, o = blockIdx.y;
   const double* __restrict__ p = part + o * nchunks * inner;
-  double s = 0;
-  if (i < inner)
-    for (int c = g; c < nchunks; c += 16) s += p[(int64_t)c * inner + i];
-  sm[g][li] = s;
+  double s0 = 0, s1 = 0;
+  if (i < inner) {
+    int c = g;
+    for (; c + 32 < nchunks; c += 64) {
+      s0 += p[(int64_t)c * inner + i];
+      s1 += p[(int64_t)(c + 32) * inner + i];
+    }
+    if (c < nchunks) s0 += p[(int64_t)c * inner + i];
+  }
+  sm[g][li] = s0 + s1;
   __syncthreads();
   if (g == 0 && i < inner) {
     double r = 0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) r += sm[q][li];
+    for (int q = 0; q < 32; ++q) r += sm[q][li];
     out[o * inner + i] = (TO)r;
   }
 }
@@ -285,7 +292,7 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
     k_strided_vec<MAP, T, double><<<dim3((unsigned)outer, (unsigned)nchunks), kRT, 0, c.stream>>>(x, inner, red,
                                                                                                  rows, part);
     AG_LAUNCHED();
-    k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 16), (unsigned)outer), 256, 0, c.stream>>>(
+    k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 8), (unsigned)outer), 256, 0, c.stream>>>(
         part, (int)nchunks, inner, out);
     AG_LAUNCHED();
     return AG_OK;
@@ -326,7 +333,7 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
   // phase 2: partials (inner, nchunks, outer) -> out (inner, outer)
   AG_CHECK(outer <= 65535, AG_EUNSUPPORTED, "ag_sum_dim: outer extent %lld too large for a split reduction",
            (long long)outer);
-  k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 16), (unsigned)outer), 256, 0, c.stream>>>(part, (int)nchunks,
+  k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 8), (unsigned)outer), 256, 0, c.stream>>>(part, (int)nchunks,
                                                                                                 inner, out);
   AG_LAUNCHED();
   return AG_OK;

@@ -274,24 +274,30 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// C[m + ldc*n] = alpha * sum_p part[p][i] (+ beta*C), i = m + M*n; 16 x 16 threads: 16 outputs per block,
-// 16 lanes each summing every 16th partial, then a fixed-order combine (deterministic).
+// C[m + ldc*n] = alpha * sum_p part[p][i] (+ beta*C), i = m + M*n; 8 outputs x 32 lanes per block: a lane sums
+// every 32nd partial, then a fixed-order combine (deterministic).
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_reduce_partials(const T* __restrict__ part, int nparts, int64_t len, T alpha, T beta, T* __restrict__ C,
                       int64_t M, int64_t ldc) {
-  __shared__ double sm[16][17];
-  const int li = threadIdx.x % 16, g = threadIdx.x / 16;
-  const int64_t i = (int64_t)blockIdx.x * 16 + li;
-  double s = 0;
-  if (i < len)
-    for (int p = g; p < nparts; p += 16) s += (double)part[(int64_t)p * len + i];
-  sm[g][li] = s;
+  __shared__ double sm[32][9];
+  const int li = threadIdx.x % 8, g = threadIdx.x / 8;
+  const int64_t i = (int64_t)blockIdx.x * 8 + li;
+  double s0 = 0, s1 = 0;
+  if (i < len) {
+    int p = g;
+    for (; p + 32 < nparts; p += 64) {
+      s0 += (double)part[(int64_t)p * len + i];
+      s1 += (double)part[(int64_t)(p + 32) * len + i];
+    }
+    if (p < nparts) s0 += (double)part[(int64_t)p * len + i];
+  }
+  sm[g][li] = s0 + s1;
   __syncthreads();
   if (g == 0 && i < len) {
     double r = 0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) r += sm[q][li];
+    for (int q = 0; q < 32; ++q) r += sm[q][li];
     T* dst = C + (i % M) + (i / M) * ldc;
     *dst = beta == T(0) ? (T)(alpha * r) : (T)(alpha * r + (double)beta * (double)(*dst));
   }
@@ -301,7 +307,7 @@ template <typename T>
 ag_status reduce_partials(const T* part, int nparts, int64_t M, int64_t N, double alpha, double beta, T* C,
                           int64_t ldc) {
   Context& c = ctx();
-  k_reduce_partials<T><<<(unsigned)cdiv(M * N, 16), 256, 0, c.stream>>>(part, nparts, M * N, (T)alpha, (T)beta, C,
+  k_reduce_partials<T><<<(unsigned)cdiv(M * N, 8), 256, 0, c.stream>>>(part, nparts, M * N, (T)alpha, (T)beta, C,
                                                                        M, ldc);
   AG_LAUNCHED();
   return AG_OK;
