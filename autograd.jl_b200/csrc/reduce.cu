@@ -210,11 +210,14 @@ __global__ void __launch_bounds__(256)
   double s0 = 0, s1 = 0;
   if (i < inner) {
     int c = g;
-    for (; c + 32 < nchunks; c += 64) {
-      s0 += p[(int64_t)c * inner + i];
-      s1 += p[(int64_t)(c + 32) * inner + i];
+    for (; c + 7 * 32 < nchunks; c += 8 * 32) {      // 8 independent loads in flight
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(c + 32 * u) * inner + i];
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) { s0 += v[u]; s1 += v[u + 1]; }
     }
-    if (c < nchunks) s0 += p[(int64_t)c * inner + i];
+    for (; c < nchunks; c += 32) s0 += p[(int64_t)c * inner + i];
   }
   sm[g][li] = s0 + s1;
   __syncthreads();

@@ -136,6 +136,8 @@ template <typename T, int MB>
 __global__ void __launch_bounds__(128)
     k_skinny_cols(int transA, int M, int64_t N, int K, T alpha, const T* __restrict__ A, int64_t lda,
                   const T* __restrict__ B, int64_t ldb, T beta, T* __restrict__ C, int64_t ldc) {
+  constexpr int NV = 16 / sizeof(T);               // elements per 128-bit access
+  struct alignas(16) V { T v[NV]; };
   __shared__ __align__(16) T As[SK_MAXD * MB];     // As[k*MB + m], zero padded to MB rows
   for (int i = threadIdx.x; i < K * MB; i += 128) {
     const int k = i / MB, m = i % MB;
@@ -150,50 +152,45 @@ __global__ void __launch_bounds__(128)
   T acc[MB];
 #pragma unroll
   for (int m = 0; m < MB; ++m) acc[m] = T(0);
-  int k = 0;
-  // 128-bit loads of the column when its start is 16-byte aligned (K%4==0 and ldb%4==0 for Float32)
-  constexpr int NV = 16 / sizeof(T);
-  if ((ldb % NV) == 0 && ((((uintptr_t)B) & 15) == 0) && NV == 4) {
-    for (; k + 8 <= K; k += 8) {
-      struct alignas(16) V { T v[4]; };
-      const V q0 = *reinterpret_cast<const V*>(b + k), q1 = *reinterpret_cast<const V*>(b + k + 4);
+  // rank-1 update with a 128-bit broadcast read of NV rows of op(A) per instruction
+  auto fma_k = [&](int k, T bv) {
 #pragma unroll
-      for (int m = 0; m < MB; ++m) {
-        T t = acc[m];
-        t = fma(As[k * MB + m], q0.v[0], t);
-        t = fma(As[(k + 1) * MB + m], q0.v[1], t);
-        t = fma(As[(k + 2) * MB + m], q0.v[2], t);
-        t = fma(As[(k + 3) * MB + m], q0.v[3], t);
-        t = fma(As[(k + 4) * MB + m], q1.v[0], t);
-        t = fma(As[(k + 5) * MB + m], q1.v[1], t);
-        t = fma(As[(k + 6) * MB + m], q1.v[2], t);
-        t = fma(As[(k + 7) * MB + m], q1.v[3], t);
-        acc[m] = t;
-      }
+    for (int m = 0; m < MB; m += NV) {
+      const V a4 = *reinterpret_cast<const V*>(&As[k * MB + m]);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc[m + j] = fma(a4.v[j], bv, acc[m + j]);
+    }
+  };
+  int k = 0;
+  const bool vecB = (ldb % NV) == 0 && ((((uintptr_t)B) & 15) == 0);
+  if (vecB) {
+    // the column is 16-byte aligned: stream it with 128-bit loads, 4 in flight
+    for (; k + 4 * NV <= K; k += 4 * NV) {
+      V q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const V*>(b + k + u * NV);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) fma_k(k + u * NV + j, q[u].v[j]);
+    }
+    for (; k + NV <= K; k += NV) {
+      const V q = *reinterpret_cast<const V*>(b + k);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) fma_k(k + j, q.v[j]);
     }
   }
   for (; k + 4 <= K; k += 4) {
     const T b0 = b[k], b1 = b[k + 1], b2 = b[k + 2], b3 = b[k + 3];
-#pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      acc[m] = fma(As[k * MB + m], b0, acc[m]);
-      acc[m] = fma(As[(k + 1) * MB + m], b1, acc[m]);
-      acc[m] = fma(As[(k + 2) * MB + m], b2, acc[m]);
-      acc[m] = fma(As[(k + 3) * MB + m], b3, acc[m]);
-    }
+    fma_k(k, b0); fma_k(k + 1, b1); fma_k(k + 2, b2); fma_k(k + 3, b3);
   }
-  for (; k < K; ++k) {
-    const T b0 = b[k];
-#pragma unroll
-    for (int m = 0; m < MB; ++m) acc[m] = fma(As[k * MB + m], b0, acc[m]);
-  }
+  for (; k < K; ++k) fma_k(k, b[k]);
   T* __restrict__ c = C + col * ldc;
   if (beta == T(0)) {
-    if (MB == M && (ldc * sizeof(T)) % 16 == 0 && (((uintptr_t)C) & 15) == 0) {
-      constexpr int NV = 16 / sizeof(T);
+    if (MB == M && (ldc % NV) == 0 && (((uintptr_t)C) & 15) == 0) {
 #pragma unroll
       for (int m = 0; m < MB; m += NV) {
-        struct alignas(16) V { T v[NV]; } o;
+        V o;
 #pragma unroll
         for (int j = 0; j < NV; ++j) o.v[j] = alpha * acc[m + j];
         *reinterpret_cast<V*>(c + m) = o;
@@ -286,11 +283,14 @@ __global__ void __launch_bounds__(256)
   double s0 = 0, s1 = 0;
   if (i < len) {
     int p = g;
-    for (; p + 32 < nparts; p += 64) {
-      s0 += (double)part[(int64_t)p * len + i];
-      s1 += (double)part[(int64_t)(p + 32) * len + i];
+    for (; p + 7 * 32 < nparts; p += 8 * 32) {       // 8 independent loads in flight
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[(int64_t)(p + 32 * u) * len + i];
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) { s0 += (double)v[u]; s1 += (double)v[u + 1]; }
     }
-    if (p < nparts) s0 += (double)part[(int64_t)p * len + i];
+    for (; p < nparts; p += 32) s0 += (double)part[(int64_t)p * len + i];
   }
   sm[g][li] = s0 + s1;
   __syncthreads();

@@ -207,21 +207,27 @@ def main():
     for _ in range(2):
         eager_step()
     ag.sync()
-    if world == 1:
+    graphs, replay = [], None
+    try:
+        # the whole step (tape forward + backward sweep + NCCL allreduce + axpy!) as ONE CUDA graph
         with ag.StepGraph() as g_all:
             eager_step()
-        graphs = [g_all]
+        graphs, replay = [g_all], "CUDA graph (single, collective captured)" if world > 1 else "CUDA graph"
 
         def step():
             g_all.launch()
-    else:
+    except Exception as exc:          # NCCL refused capture: graph | eager allreduce | graph
+        if world == 1:
+            raise
+        sys.stderr.write("rank %d: single-graph capture failed (%s); falling back to split graphs\n" % (rank, exc))
+        ag.sync()
         with ag.StepGraph() as g_a:
             fwd_bwd()
         pre = state["grads"]
         exchange()                       # eager once: fixes the bucket views
         with ag.StepGraph() as g_b:
             update()
-        graphs = [g_a, g_b]
+        graphs, replay = [g_a, g_b], "CUDA graphs around an eager NCCL allreduce"
 
         def step():
             g_a.launch()
@@ -339,7 +345,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "examples/mnist.jl MLP 784-64-10 softmax (configs[1]), batch %d per GPU, Float32, "
                                    "@diff + grad + allreduce + axpy!; value counts one per-rank step per rank" % B,
-                       "global_batch": gB, "parallelism": "dp%d" % world, "replay": "CUDA graph",
+                       "global_batch": gB, "parallelism": "dp%d" % world, "replay": replay,
                        "l2": "inputs (x = %.0f MB per rank) larger than the 126 MB L2; no flush" % (x_np.nbytes / 1e6)},
             "forward_ms": fwd_ms, "backward_update_ms": bwd_ms,
             "backward_hbm_gbs": bb / (bwd_ms * 1e-3) / 1e9,
