@@ -316,9 +316,16 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None          # dram__bytes_read+write of this kernel, one `ncu --set full` launch (profiles/)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = tj["kernels"]["dw1" if "dw1" in top else "fwd"]["traffic"]
+    except Exception:
+        pass
     roofline = {"kernel": top, "engine": eng_b if "dw1" in top else eng_f, "bound": "hbm",
                 "achieved": bytes_ / (t_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": bytes_ / (t_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                "frac": bytes_ / (t_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
+                "algorithmic_bytes": bytes_,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "ms_per_launch": t_ms, "tflops": flops / (t_ms * 1e-3) / 1e12,
                 "all": {k: {"ms": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9} for k, v in cand.items()}}
