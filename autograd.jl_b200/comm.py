@@ -16,9 +16,12 @@ from .sparse import Sparse
 
 
 class DataParallel:
-    def __init__(self, rank=0, world=1, broadcast_bytes=None):
-        """broadcast_bytes(b: bytes|None) -> bytes: returns rank 0's payload on every rank."""
+    def __init__(self, rank=0, world=1, broadcast_bytes=None, allgather_bytes=None, p2p_bytes=8 << 20):
+        """broadcast_bytes(b: bytes|None) -> bytes: returns rank 0's payload on every rank.
+        allgather_bytes(b: bytes) -> list[bytes] (optional): enables the one-shot peer-memory allreduce
+        (ag_p2p_*) for buckets up to p2p_bytes; larger buckets and missing peer access use NCCL."""
         self.rank, self.world = rank, world
+        self.p2p_cap = 0
         if world > 1:
             idbuf = (C.c_uint8 * 128)()
             if rank == 0:
@@ -26,6 +29,13 @@ class DataParallel:
             payload = broadcast_bytes(bytes(idbuf) if rank == 0 else None)
             idbuf = (C.c_uint8 * 128).from_buffer_copy(payload)
             check(lib.ag_comm_init(world, rank, idbuf))
+            if allgather_bytes is not None and p2p_bytes > 0:
+                h = (C.c_uint8 * 64)()
+                check(lib.ag_p2p_export(int(p2p_bytes), h))
+                handles = b"".join(allgather_bytes(bytes(h)))
+                hb = (C.c_uint8 * (64 * world)).from_buffer_copy(handles)
+                check(lib.ag_p2p_connect(world, rank, hb))
+                self.p2p_cap = int(p2p_bytes)
         self._bucket = None
 
     @staticmethod
@@ -55,8 +65,59 @@ class DataParallel:
             D.slab_copy(g, n, 0, b, tot, off, 1, n, 1)
             views.append(DArray(b.buf, b.ptr + off * b.dtype.itemsize, g.shape, b.dtype))
             off += n
-        check(lib.ag_allreduce_sum(b.dt, D.vptr(b), tot))
+        if self.p2p_cap and tot * b.dtype.itemsize <= self.p2p_cap:
+            check(lib.ag_p2p_allreduce_sum(b.dt, D.vptr(b), tot))
+        else:
+            check(lib.ag_allreduce_sum(b.dt, D.vptr(b), tot))
         return views
+
+    def update(self, alpha, grads, params):
+        """The data-parallel SGD step: params[k] += alpha * (sum over ranks of grads[k]), i.e. allreduce followed
+        by `axpy!(alpha, g, w)` for every Param.  One launch when the peer-memory collective is available (the
+        update is fused behind it); one multi-tensor axpy launch on a single rank.  Returns the reduced grads."""
+        from .core import value
+        dense = [g.full() if isinstance(g, Sparse) else g for g in grads]
+        live = [(D.materialize(g), value(p)) for g, p in zip(dense, params) if g is not None]
+        if not live:
+            return dense
+        dt = live[0][0].dtype
+        nbytes = sum(-(-g.size // 4) * 4 for g, _ in live) * dt.itemsize
+        fits = len(live) <= 16 and all(g.dtype == dt and w.dtype == dt for g, w in live)
+        if fits and (self.world == 1 or (self.p2p_cap and nbytes <= self.p2p_cap)):
+            n = len(live)
+            src = (C.c_void_p * n)(*[g.ptr for g, _ in live])
+            dst = (C.c_void_p * n)(*[w.ptr for _, w in live])
+            sizes = (C.c_int64 * n)(*[g.size for g, _ in live])
+            if self.world == 1:
+                check(lib.ag_multi_axpy(live[0][0].dt, n, float(alpha), src, dst, sizes))
+            else:
+                check(lib.ag_p2p_allreduce_multi(live[0][0].dt, n, src, dst, sizes, float(alpha)))
+            return dense
+        if fits:
+            # NCCL path with multi-tensor pack / update: 3 launches (pack, allreduce, axpy!) instead of 2k+1
+            n = len(live)
+            sizes_l = [g.size for g, _ in live]
+            tot = sum(sizes_l)
+            if self._bucket is None or self._bucket.size != tot or self._bucket.dtype != dt:
+                self._bucket = DArray.empty((tot,), dt)
+            b, off, views = self._bucket, 0, []
+            for g, _ in live:
+                views.append(DArray(b.buf, b.ptr + off * dt.itemsize, g.shape, dt))
+                off += g.size
+            src = (C.c_void_p * n)(*[g.ptr for g, _ in live])
+            bkt = (C.c_void_p * n)(*[v.ptr for v in views])
+            dst = (C.c_void_p * n)(*[w.ptr for _, w in live])
+            sizes = (C.c_int64 * n)(*sizes_l)
+            check(lib.ag_multi_copy(b.dt, n, src, bkt, sizes))
+            check(lib.ag_allreduce_sum(b.dt, D.vptr(b), tot))
+            check(lib.ag_multi_axpy(b.dt, n, float(alpha), bkt, dst, sizes))
+            it = iter(views)
+            return [None if g is None else next(it) for g in dense]
+        reduced = self.allreduce_grads(dense)
+        for g, p in zip(reduced, params):
+            if g is not None:
+                D.axpy_(alpha, g, value(p))
+        return reduced
 
     def close(self):
         check(lib.ag_comm_destroy())

@@ -161,7 +161,13 @@ def main():
             obj = [payload]
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
-        dp = ag.DataParallel(rank, world, bcast)
+        def allgather(payload):
+            out = [None] * world
+            dist.all_gather_object(out, payload)
+            return out
+        use_p2p = os.environ.get("AGB_ALLREDUCE", "nccl") == "p2p"     # measured: NCCL wins at 200 KB
+        dp = ag.DataParallel(rank, world, bcast, allgather if use_p2p else None)
+        dist.barrier()
     else:
         dp = ag.DataParallel(0, 1)
 
@@ -192,11 +198,10 @@ def main():
         return t
 
     def exchange():
-        state["grads"] = dp.allreduce_grads(state["grads"])
+        pass        # folded into dp.update: allreduce (+ fused axpy!) is one launch
 
     def update():
-        for p, g in zip(params, state["grads"]):
-            ag.axpy(-LR, g, p)
+        state["grads"] = dp.update(-LR, state["grads"], params)
 
     def eager_step():
         fwd_bwd()
@@ -353,6 +358,8 @@ def main():
             "config": {"workload": "examples/mnist.jl MLP 784-64-10 softmax (configs[1]), batch %d per GPU, Float32, "
                                    "@diff + grad + allreduce + axpy!; value counts one per-rank step per rank" % B,
                        "global_batch": gB, "parallelism": "dp%d" % world, "replay": replay,
+                       "allreduce": ("one-shot peer-memory kernel over NVLink (ag_p2p_allreduce_sum)" if dp.p2p_cap else
+                                     "NCCL") if world > 1 else None,
                        "l2": "inputs (x = %.0f MB per rank) larger than the 126 MB L2; no flush" % (x_np.nbytes / 1e6)},
             "forward_ms": fwd_ms, "backward_update_ms": bwd_ms,
             "backward_hbm_gbs": bb / (bwd_ms * 1e-3) / 1e9,

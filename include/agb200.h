@@ -192,6 +192,13 @@ ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, i
 ag_status ag_add(int32_t dtype, const void* a, const void* b, void* out, int64_t n);
 /* y += alpha*x.  LinearAlgebra.axpy! in the SGD loop (README.md:70-77; src/core.jl:55). */
 ag_status ag_axpy(int32_t dtype, double alpha, const void* x, void* y, int64_t n);
+/* y[k] += alpha*x[k] for up to 16 tensors in one launch: the loop `for w in params(f); axpy!(-lr, grad(J,w), w); end`
+ * (README.md:73-76). */
+ag_status ag_multi_axpy(int32_t dtype, int32_t nseg, double alpha, void* const* x, void* const* y,
+                        const int64_t* sizes);
+/* dst[k] = src[k] for up to 16 tensors in one launch: packs the Param gradients into the flat allreduce bucket
+ * (cat1d order, src/cat.jl:150-182). */
+ag_status ag_multi_copy(int32_t dtype, int32_t nseg, void* const* src, void* const* dst, const int64_t* sizes);
 /* x *= alpha (lmul!, gradient clipping examples/charlm.jl:148-149). */
 ag_status ag_scale(int32_t dtype, double alpha, void* x, int64_t n);
 
@@ -243,6 +250,20 @@ ag_status ag_comm_init(int32_t nranks, int32_t rank, const uint8_t* id128);
 ag_status ag_comm_destroy(void);
 /* In-place sum-allreduce of a flat gradient bucket on the library stream. */
 ag_status ag_allreduce_sum(int32_t dtype, void* buf, int64_t n);
+/* One-shot peer-memory allreduce for latency-bound buckets (single node, NVLink/NVSwitch): each rank
+ * exports a symmetric buffer (CUDA IPC handle, 64 bytes), the launcher gathers the handles of all ranks and
+ * hands them to ag_p2p_connect; ag_p2p_allreduce_sum then sums `buf` over all ranks in place with ONE kernel
+ * (publish, flag every peer, sum all peers' buckets in rank order: bit-identical on every rank).
+ * n*sizeof(dtype) must not exceed cap_bytes.  Graph-capturable. */
+ag_status ag_p2p_export(int64_t cap_bytes, uint8_t* handle64);
+ag_status ag_p2p_connect(int32_t nranks, int32_t rank, const uint8_t* handles /* nranks x 64 bytes */);
+ag_status ag_p2p_allreduce_sum(int32_t dtype, void* buf, int64_t n);
+/* Multi-tensor form (<= 16 segments, no bucket copies): src[k] (n = sizes[k]) is replaced by its sum over all
+ * ranks; when dst is non-NULL, dst[k] += alpha * sum is applied in the same kernel -- the SGD update
+ * `axpy!(-lr, grad(J,w), w)` (README.md:70-77) fused behind the collective. */
+ag_status ag_p2p_allreduce_multi(int32_t dtype, int32_t nseg, void* const* src, void* const* dst,
+                                 const int64_t* sizes, double alpha);
+ag_status ag_p2p_destroy(void);
 
 #ifdef __cplusplus
 }

@@ -298,6 +298,47 @@ class FakeLib:
 
     def ag_comm_destroy(self): return 0
 
+    def ag_p2p_export(self, cap, h):
+        return 0
+
+    def ag_p2p_connect(self, nranks, rank, handles):
+        self.nranks = nranks
+        return 0
+
+    def ag_p2p_allreduce_sum(self, dtype, buf, n):
+        return self.ag_allreduce_sum(dtype, buf, n)
+
+    def ag_p2p_destroy(self): return 0
+
+    def ag_p2p_allreduce_multi(self, dtype, nseg, src, dst, sizes, alpha):
+        T = _DT[dtype]
+        for k in range(nseg):
+            n = int(sizes[k])
+            g = _arr(src[k], n, T)
+            if self.nranks > 1:
+                g[:] = self.allreduce(g)
+            if dst and dst[k]:
+                w = _arr(dst[k], n, T)
+                w[:] = w + T(alpha) * g
+        return 0
+
+    def ag_multi_copy(self, dtype, nseg, src, dst, sizes):
+        self.launches += 1
+        T = _DT[dtype]
+        for k in range(nseg):
+            n = int(sizes[k])
+            _arr(dst[k], n, T)[:] = _arr(src[k], n, T)
+        return 0
+
+    def ag_multi_axpy(self, dtype, nseg, alpha, x, y, sizes):
+        self.launches += 1
+        T = _DT[dtype]
+        for k in range(nseg):
+            n = int(sizes[k])
+            w = _arr(y[k], n, T)
+            w[:] = w + T(alpha) * _arr(x[k], n, T)
+        return 0
+
     def ag_allreduce_sum(self, dtype, buf, n):
         if self.nranks > 1:
             v = _arr(buf, n, _DT[dtype])

@@ -41,7 +41,11 @@ def _worker(rank, world, port, out_dir):
         obj = [payload]
         dist.broadcast_object_list(obj, src=0)
         return obj[0]
-    dp = ag.DataParallel(rank, world, bcast)
+    def allgather(payload):
+        out = [None] * world
+        dist.all_gather_object(out, payload)
+        return out
+    dp = ag.DataParallel(rank, world, bcast, allgather if os.environ.get('AGB_TEST_P2P') else None)
     W = ag.workloads
     B = 96
     w, x, y = W.mnist_init(np.random.default_rng(11), B, np.float64)
@@ -49,9 +53,7 @@ def _worker(rank, world, port, out_dir):
     params = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
     xd, yd = ag.DArray.from_numpy(x[:, lo:hi]), ag.DArray.from_numpy(y[:, lo:hi])
     t = ag.diff(lambda: W.mnist_loss(ag, params, xd, yd, global_batch=B))
-    grads = dp.allreduce_grads([ag.grad(t, p) for p in params])
-    for p, g in zip(params, grads):
-        ag.axpy(-0.1, g, p)
+    grads = dp.update(-0.1, [ag.grad(t, p) for p in params], params)      # allreduce + fused axpy!
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *[p.value.to_numpy() for p in params],
              *[g.to_numpy() for g in grads])
     dist.barrier()

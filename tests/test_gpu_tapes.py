@@ -187,6 +187,22 @@ def test_graph_replay_matches_eager(ag):
     g.destroy()
 
 
+def test_multi_tensor_update_matches_axpy_loop(ag):
+    """DataParallel.update on one rank (one multi-tensor launch) == the reference loop of axpy! calls."""
+    W = ag.workloads
+    w, x, y = W.mnist_init(np.random.default_rng(12), 300)
+    xd, yd = ag.DArray.from_numpy(x), ag.DArray.from_numpy(y)
+    pa = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    pb = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    ta = ag.diff(lambda: W.mnist_loss(ag, pa, xd, yd))
+    for p in pa:
+        ag.axpy(-0.1, ag.grad(ta, p), p)
+    tb = ag.diff(lambda: W.mnist_loss(ag, pb, xd, yd))
+    ag.DataParallel(0, 1).update(-0.1, [ag.grad(tb, p) for p in pb], pb)
+    for a, b in zip(pa, pb):
+        assert np.array_equal(a.value.to_numpy(), b.value.to_numpy())
+
+
 def test_full_size_properties(ag):
     """BASELINE config 2 at the bench size (B = 65536): properties that need no oracle.
     (a) softmax cross-entropy: column sums of d loss / d logits are 0, so grad(b2) sums to ~0;
