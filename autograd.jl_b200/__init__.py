@@ -7,7 +7,7 @@ importing this package without the built library raises ImportError -- there is 
 """
 from . import _lib
 from ._lib import DeviceError, DimensionMismatch, UnsupportedOnDevice
-from .darray import (DArray, device_info, gemm_engine, init, launch_count, set_gemm_engine, sync,
+from .darray import (DArray, IArray, device_info, gemm_engine, init, launch_count, set_gemm_engine, sync,
                      zeros)
 from .core import (Node, Param, Result, Tape, Tracked, Value, differentiate, diff, gcnode, grad,
                    gradloss, params, recording, release_node, set_gc_function, value)

@@ -25,6 +25,7 @@ Context& ctx();
 void set_error(const char* fmt, ...);
 ag_status cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void* workspace(size_t bytes);  // grows the shared workspace (not during graph capture)
+int32_t* oob_flag();            // sticky device flag raised by index checks; read and cleared by ag_sync
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

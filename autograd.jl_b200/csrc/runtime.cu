@@ -156,6 +156,21 @@ void* workspace(size_t bytes) {
   return c.ws;
 }
 
+static int32_t* g_oob = nullptr;
+static bool g_oob_armed = false;
+int32_t* oob_flag() {
+  if (!g_oob) {
+    if (cudaMalloc((void**)&g_oob, 4) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("out of device memory allocating the index-check flag");
+      return nullptr;
+    }
+    cudaMemset(g_oob, 0, 4);
+  }
+  g_oob_armed = true;
+  return g_oob;
+}
+
 // ---- kernels --------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) k_fill(T* __restrict__ dst, int64_t n, T v) {
@@ -191,6 +206,8 @@ ag_status ag_init(int32_t device) {
   c.ws_bytes = (size_t)64 << 20;
   AG_CUDA(cudaMalloc(&c.ws, c.ws_bytes));
   AG_CUDA(cudaMemsetAsync(c.ws, 0, c.ws_bytes, c.stream));
+  if (!oob_flag()) return AG_ENOMEM;   // allocate the sticky index-check flag outside of any capture
+  g_oob_armed = false;
   c.launches = 0;
   c.capturing = false;
   c.ready = true;
@@ -228,6 +245,16 @@ ag_status ag_shutdown(void) {
 ag_status ag_sync(void) {
   AG_REQUIRE_INIT();
   AG_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (g_oob_armed && g_oob && !ctx().capturing) {
+    int32_t h = 0;
+    AG_CUDA(cudaMemcpy(&h, g_oob, 4, cudaMemcpyDeviceToHost));
+    g_oob_armed = false;
+    if (h) {
+      cudaMemset(g_oob, 0, 4);
+      set_error("index out of range in an earlier gather/scatter (BoundsError)");
+      return AG_EINVAL;
+    }
+  }
   return AG_OK;
 }
 

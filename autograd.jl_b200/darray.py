@@ -499,6 +499,44 @@ def adjoint(x):
 
 # ---- indexing ---------------------------------------------------------------------------------------
 
+class IArray:
+    """Device-resident Int64 index vector (0-based).  Keeping the indices of a batch on the device (and
+    refreshing them in place with `update`) lets `W[:, ids]` and its Sparse gradient run without any host
+    synchronisation, so a whole recurrent step can be captured and replayed as one CUDA graph.  The host copy is
+    kept for the bookkeeping the tape does on the host (lengths, bounds)."""
+    __slots__ = ("host", "buf", "lo", "hi")
+
+    def __init__(self, host):
+        self.host = np.ascontiguousarray(host, dtype=np.int64).reshape(-1)
+        self.buf = _Buffer(max(self.host.nbytes, 8))
+        self._upload()
+
+    def _upload(self):
+        self.lo = int(self.host.min()) if self.host.size else 0
+        self.hi = int(self.host.max()) if self.host.size else -1
+        if self.host.size:
+            check(lib.ag_copy_h2d(C.c_void_p(self.buf.ptr), self.host.ctypes.data_as(C.c_void_p), self.host.nbytes))
+            sync()
+
+    def update(self, host):
+        host = np.ascontiguousarray(host, dtype=np.int64).reshape(-1)
+        if host.size != self.host.size:
+            raise L.DimensionMismatch("IArray.update: length %d != %d" % (host.size, self.host.size))
+        self.host = host
+        self._upload()
+
+    @property
+    def size(self):
+        return self.host.size
+
+    @property
+    def ptr(self):
+        return self.buf.ptr
+
+    def __len__(self):
+        return self.host.size
+
+
 def index_to_device(idx):
     """int64 numpy index vector -> device buffer (returned as a raw _Buffer)."""
     idx = np.ascontiguousarray(idx, dtype=np.int64)
@@ -520,12 +558,38 @@ def gather(x, flat_idx, out_shape):
 
 def gather_cols(x, cols):
     x = materialize(x)
-    cols = np.ascontiguousarray(cols, dtype=np.int64)
+    if not isinstance(cols, IArray):
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
     out = DArray.empty((x.shape[0], cols.size), x.dtype)
     if out.size:
-        ib = index_to_device(cols)
+        ib = cols if isinstance(cols, IArray) else index_to_device(cols)
         check(lib.ag_gather_cols(x.dt, vptr(x), x.shape[0], C.c_void_p(ib.ptr), vptr(out), cols.size))
     return out
+
+
+def concat_index(blocks):
+    """Concatenate IArray blocks on the device (raw 8-byte copies); returns (buffer, n, lo, hi)."""
+    n = sum(b.size for b in blocks)
+    buf = _Buffer(max(n * 8, 8))
+    off = 0
+    for b in blocks:
+        if b.size:
+            check(lib.ag_slab_copy(L.F64, C.c_void_p(b.ptr), b.size, 0, C.c_void_p(buf.ptr), n, off, 1, b.size, 1))
+        off += b.size
+    return buf, n, min(b.lo for b in blocks), max(b.hi for b in blocks)
+
+
+def scatter_add_dev_(dest, idx_buf, n, lo, hi, vals, block=1):
+    """scatter_add_ with destinations already on the device (bounds known from the host bookkeeping)."""
+    if n == 0:
+        return dest
+    vals = materialize(vals)
+    if vals.size != n * block:
+        raise L.DimensionMismatch("scatter-add: %d values for %d destinations" % (vals.size, n * block))
+    if lo < 0 or (hi + 1) * block > dest.size:
+        raise IndexError("BoundsError")
+    check(lib.ag_scatter_add(dest.dt, vptr(dest), dest.size, C.c_void_p(idx_buf.ptr), vptr(vals), n, block))
+    return dest
 
 
 def scatter_add_(dest, flat_idx, vals, block=1):

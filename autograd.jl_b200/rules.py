@@ -23,7 +23,7 @@ import numpy as np
 from . import darray as D
 from ._lib import DimensionMismatch, UnsupportedOnDevice
 from .core import Result, Tracked, Value, forw, recording, value
-from .darray import DArray, isnum
+from .darray import DArray, IArray, isnum
 from .sparse import Sparse, flat_dest
 
 # ---------------------------------------------------------------------------------------------------
@@ -524,6 +524,8 @@ def _col_index(x, idx):
     """(Colon, Vector{Int}) on a matrix -> the column ids, else None (embedding lookup fast path)."""
     if x.ndim == 2 and len(idx) == 2 and isinstance(idx[0], slice) and idx[0] == slice(None):
         j = idx[1]
+        if isinstance(j, IArray):
+            return j
         if isinstance(j, (list, np.ndarray)) and np.asarray(j).dtype != np.bool_ and np.asarray(j).ndim == 1:
             return np.asarray(j, dtype=np.int64)
     return None
@@ -534,9 +536,11 @@ def _getindex_fwd(x, *idx):
         return x
     cols = _col_index(x, idx)
     if cols is not None:
-        if cols.size and (cols.min() < 0 or cols.max() >= x.shape[1]):
+        lo, hi = (cols.lo, cols.hi) if isinstance(cols, IArray) else ((cols.min(), cols.max()) if cols.size else (0, -1))
+        if cols.size and (lo < 0 or hi >= x.shape[1]):
             raise IndexError("BoundsError")
         return D.gather_cols(x, cols)
+    idx = tuple(i.host if isinstance(i, IArray) else i for i in idx)
     dest, outshape = flat_dest(x.shape, idx)
     return D.gather(x, dest, outshape)
 

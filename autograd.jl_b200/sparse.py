@@ -15,7 +15,7 @@ import numpy as np
 
 from . import darray as D
 from ._lib import DimensionMismatch
-from .darray import DArray, isnum
+from .darray import DArray, IArray, isnum
 
 
 def _prod(s):
@@ -137,6 +137,9 @@ class Sparse:
                     and idx[0] == slice(None)):
                 return None
             j = idx[1]
+            if isinstance(j, IArray):
+                cols.append(j)
+                continue
             if isinstance(j, (int, np.integer)) and not isinstance(j, (bool, np.bool_)):
                 j = [int(j)]
             j = np.asarray(j)
@@ -158,13 +161,23 @@ class Sparse:
         rows = self.shape[0] if len(self.shape) == 2 else 0
         if cols is not None and all(isinstance(v, DArray) and v.size == rows * c.size
                                     for v, c in zip(self.values, cols)):
+            vals = _concat_flat(self.values, self.dtype)
+            if all(isinstance(c, IArray) for c in cols):          # indices live on the device: no host round trip
+                if len(cols) == 1:
+                    ib, n, lo, hi = cols[0], cols[0].size, cols[0].lo, cols[0].hi
+                else:
+                    ib, n, lo, hi = D.concat_index(cols)
+                if n and (lo < 0 or hi >= self.shape[1]):
+                    raise IndexError("BoundsError")
+                return D.scatter_add_dev_(a, ib, n, lo, hi, vals, block=rows)
+            cols = [c.host if isinstance(c, IArray) else c for c in cols]
             dest = np.concatenate(cols) if len(cols) > 1 else cols[0]
             if dest.size and (dest.min() < 0 or dest.max() >= self.shape[1]):
                 raise IndexError("BoundsError")
-            vals = _concat_flat(self.values, self.dtype)
             return D.scatter_add_(a, dest, vals, block=rows)
         dests, vals = [], []
         for idx, v in zip(self.indices, self.values):
+            idx = tuple(i.host if isinstance(i, IArray) else i for i in (idx if isinstance(idx, tuple) else (idx,)))
             d, _ = flat_dest(self.shape, idx)
             if isnum(v) or (isinstance(v, DArray) and v.size == 1 and d.size != 1):
                 v = D.full_like_shape((d.size,), self.dtype, float(v))

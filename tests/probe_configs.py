@@ -51,6 +51,24 @@ def lstm_step():
     return t
 ms, nl = timeit(lstm_step, 2)
 print("charlm LSTM H=%d T=%d B=%d: %.1f ms/step (eager host-driven tape), %d launches/step" % (H, T, B, ms, nl))
+ids_host = ids
+ids = [ag.IArray(i) for i in ids_host]          # device-resident ids: the step captures into one CUDA graph
+lstm_step(); ag.sync()
+t0 = time.perf_counter()
+with ag.StepGraph() as g:
+    lstm_step()
+print("  graph capture + instantiate: %.1f ms" % ((time.perf_counter() - t0) * 1e3))
+for _ in range(2):
+    g.launch()
+ag.sync()
+e0, e1 = ag.Event(), ag.Event()
+e0.record()
+for _ in range(5):
+    g.launch()
+e1.record()
+print("  CUDA-graph replay: %.2f ms/step" % (e1.elapsed_ms_since(e0) / 5))
+g.destroy()
+ids = ids_host
 t = lstm_step()
 print("  loss %.4f  grad(W_embedding) type %s" % (float(ag.value(t)), type(ag.grad(t, params["W_embedding"])).__name__))
 

@@ -187,6 +187,62 @@ def test_graph_replay_matches_eager(ag):
     g.destroy()
 
 
+def test_lstm_graph_replay_with_device_indices(ag, oracle):
+    """Config 4 with device-resident ids (IArray): the whole step (W[:, ids] gathers, Sparse gradient
+    accumulation, one batched scatter-add, axpy! with a Sparse gradient) captures into one CUDA graph; replay
+    with refreshed ids matches the eager host-driven tape bit for bit and the oracle within tolerance."""
+    W = ag.workloads
+    rng = np.random.default_rng(21)
+    H, E, V, B, T = 32, 16, 20, 24, 3
+    wd = W.lstm_init(rng, H, E, V, np.float32)
+    keys = list(wd)
+    ids_a = [rng.integers(0, V, B) for _ in range(T)]
+    ids_b = [rng.integers(0, V, B) for _ in range(T)]
+    tg = []
+    for t in range(T):
+        oh = np.zeros((V, B), np.float32)
+        oh[rng.integers(0, V, B), np.arange(B)] = 1
+        tg.append(np.asfortranarray(oh))
+    tgd = [ag.DArray.from_numpy(a) for a in tg]
+    h0 = ag.zeros((H, B), np.float32)
+
+    def make():
+        return {k: ag.Param(ag.DArray.from_numpy(wd[k])) for k in keys}
+
+    def step(params, ids):
+        t = ag.diff(lambda: W.lstm_loss(ag, params, ids, tgd, h0, h0))
+        for k in keys:
+            ag.axpy(-0.05, ag.grad(t, params[k]), params[k])
+        return t
+    # eager reference: two steps with host (numpy) indices
+    pe = make()
+    step(pe, ids_a)
+    step(pe, ids_b)
+    # graph: capture with device indices, replay twice with refreshed ids
+    pg = make()
+    dev_ids = [ag.IArray(i) for i in ids_a]
+    warm = make()
+    step(warm, dev_ids)                      # eager warm-up (pool, workspace)
+    with ag.StepGraph() as g:
+        step(pg, dev_ids)
+    g.launch()
+    for d, i in zip(dev_ids, ids_b):
+        d.update(i)
+    g.launch()
+    ag.sync()
+    for k in keys:
+        assert np.array_equal(pe[k].value.to_numpy(), pg[k].value.to_numpy()), k
+    g.destroy()
+    # and against the oracle (one step from the initial weights)
+    po = {k: oracle.Param(np.asfortranarray(wd[k].astype(np.float64))) for k in keys}
+    to = oracle.diff(lambda: W.lstm_loss(oracle, po, ids_a, [a.astype(np.float64) for a in tg],
+                                         np.zeros((H, B)), np.zeros((H, B))))
+    p1 = make()
+    t1 = ag.diff(lambda: W.lstm_loss(ag, p1, [ag.IArray(i) for i in ids_a], tgd, h0, h0))
+    for k in keys:
+        assert relerr(ag.full(ag.grad(t1, p1[k])).to_numpy(), oracle.full(oracle.grad(to, po[k]))) <= 2e-5, k
+
+
 def test_multi_tensor_update_matches_axpy_loop(ag):
     """DataParallel.update on one rank (one multi-tensor launch) == the reference loop of axpy! calls."""
     W = ag.workloads
