@@ -55,6 +55,8 @@ _SIGS = {
     "ag_binary_bwd": [i32, i32, i32, vp, pi64, vp, dbl, pi64, vp, dbl, pi64, vp, pi64, vp, i32, pi64],
     "ag_sum_all": [i32, i32, vp, i64, vp],
     "ag_sum_dim": [i32, i32, vp, i64, i64, i64, vp],
+    "ag_reduce_dim": [i32, i32, vp, i64, i64, i64, vp],
+    "ag_permute": [i32, vp, i32, pi64, C.POINTER(i32), vp],
     "ag_add": [i32, vp, vp, vp, i64],
     "ag_axpy": [i32, dbl, vp, vp, i64],
     "ag_scale": [i32, dbl, vp, i64],

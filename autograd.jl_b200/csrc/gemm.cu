@@ -113,20 +113,6 @@ __global__ void __launch_bounds__(GT)
   }
 }
 
-// C = alpha * sum_s ws[s] + beta*C, fixed summation order (deterministic split-K)
-template <typename T>
-__global__ void __launch_bounds__(256)
-    k_splitk_reduce(const T* __restrict__ ws, int splits, int64_t M, int64_t N, T alpha, T beta,
-                    T* __restrict__ C, int64_t ldc) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
-  int64_t m = i % M, n = i / M;
-  double s = 0;
-  for (int k = 0; k < splits; ++k) s += (double)ws[(int64_t)k * M * N + i];
-  T* c = C + m + n * ldc;
-  *c = beta == T(0) ? (T)(alpha * s) : (T)(alpha * s + (double)beta * (double)(*c));
-}
-
 template <typename T>
 static ag_status gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
                            const void* A, int64_t lda, const void* B, int64_t ldb, double beta,

@@ -99,6 +99,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// out = permutedims(x, perm) for <= 4 dims: thread per output element (out is written coalesced)
+struct PermArgs {
+  int64_t oshape[4];   // shape of out
+  int64_t xstride[4];  // stride in x of each out dimension
+  int64_t n;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_permute(const T* __restrict__ x, T* __restrict__ out, const PermArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  int64_t r = i, off = 0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const int64_t q = r / a.oshape[d];
+    off += (r - q * a.oshape[d]) * a.xstride[d];
+    r = q;
+  }
+  out[i] = x[off];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_axpy(T alpha, const T* __restrict__ x, T* __restrict__ y, int64_t n) {
@@ -245,6 +265,41 @@ ag_status ag_transpose(int32_t dtype, const void* x, int64_t rows, int64_t cols,
   if (dtype == AG_F32) k_transpose<float><<<grid, 256, 0, c.stream>>>((const float*)x, rows, cols, (float*)out);
   else if (dtype == AG_F64) k_transpose<double><<<grid, 256, 0, c.stream>>>((const double*)x, rows, cols, (double*)out);
   else { set_error("ag_transpose: dtype %d", dtype); return AG_EUNSUPPORTED; }
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+ag_status ag_permute(int32_t dtype, const void* x, int32_t ndims, const int64_t* shape, const int32_t* perm,
+                     void* out) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(ndims >= 1 && ndims <= 4 && shape && perm, AG_EUNSUPPORTED, "ag_permute: ndims=%d (max 4)", ndims);
+  PermArgs a;
+  int64_t xs[4] = {1, 1, 1, 1}, n = 1;
+  bool seen[4] = {false, false, false, false};
+  for (int d = 0; d < ndims; ++d) {
+    AG_CHECK(shape[d] >= 0, AG_EINVAL, "ag_permute: negative extent");
+    xs[d] = n;
+    n *= shape[d];
+  }
+  for (int d = 0; d < 4; ++d) {
+    if (d < ndims) {
+      AG_CHECK(perm[d] >= 0 && perm[d] < ndims && !seen[perm[d]], AG_EINVAL, "ag_permute: not a permutation");
+      seen[perm[d]] = true;
+      a.oshape[d] = shape[perm[d]];
+      a.xstride[d] = xs[perm[d]];
+    } else {
+      a.oshape[d] = 1;
+      a.xstride[d] = 0;
+    }
+  }
+  a.n = n;
+  if (n == 0) return AG_OK;
+  AG_CHECK(x && out, AG_EINVAL, "ag_permute: null pointer");
+  Context& c = ctx();
+  unsigned nb = (unsigned)cdiv(n, 256);
+  if (dtype == AG_F32) k_permute<float><<<nb, 256, 0, c.stream>>>((const float*)x, (float*)out, a);
+  else if (dtype == AG_F64) k_permute<double><<<nb, 256, 0, c.stream>>>((const double*)x, (double*)out, a);
+  else { set_error("ag_permute: dtype %d", dtype); return AG_EUNSUPPORTED; }
   AG_LAUNCHED();
   return AG_OK;
 }

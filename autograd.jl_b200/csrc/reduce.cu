@@ -342,6 +342,40 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
   return AG_OK;
 }
 
+// ---- maximum / minimum / prod over one (merged) dimension --------------------------------------------
+// out[i,o] = op_r x[i,r,o].  Rules: src/base.jl:202-206,221 (`dy.*(y.==x)`, `dy.*(y./x)`).  Not on the bench
+// path: one warp per output when inner == 1 (contiguous segment), one thread per output otherwise.
+template <int OP, typename T>
+__device__ __forceinline__ T red_combine(T a, T b) {
+  if (OP == 0) return (a != a || b != b) ? (a + b) : (a > b ? a : b);   // max, NaN-propagating like Julia
+  if (OP == 1) return (a != a || b != b) ? (a + b) : (a < b ? a : b);   // min
+  return a * b;                                                         // prod
+}
+
+template <int OP, typename T>
+__global__ void __launch_bounds__(256)
+    k_reduce_op(const T* __restrict__ x, int64_t inner, int64_t red, int64_t outer, T* __restrict__ out) {
+  if (inner == 1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t o = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (o >= outer) return;
+    const T* __restrict__ p = x + o * red;
+    T acc = OP == 2 ? T(1) : p[0];                     // identity: 1 for prod; a real element for max/min
+    for (int64_t r = lane; r < red; r += 32) acc = red_combine<OP>(acc, p[r]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc = red_combine<OP>(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    if (lane == 0) out[o] = acc;
+  } else {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= inner * outer) return;
+    const int64_t i = idx % inner, o = idx / inner;
+    const T* __restrict__ p = x + i + inner * red * o;
+    T acc = p[0];
+    for (int64_t r = 1; r < red; ++r) acc = red_combine<OP>(acc, p[r * inner]);
+    out[idx] = acc;
+  }
+}
+
 template <typename T>
 static ag_status sum_dim_map(int32_t map, const void* x, int64_t inner, int64_t red, int64_t outer,
                              void* out) {
@@ -371,6 +405,29 @@ ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, i
   AG_CHECK(x, AG_EINVAL, "ag_sum_dim: null input");
   return dtype == AG_F32 ? sum_dim_map<float>(map, x, inner, red, outer, out)
                          : sum_dim_map<double>(map, x, inner, red, outer, out);
+}
+
+ag_status ag_reduce_dim(int32_t op, int32_t dtype, const void* x, int64_t inner, int64_t red, int64_t outer,
+                        void* out) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_reduce_dim: dtype %d", dtype);
+  AG_CHECK(op >= 0 && op <= 2, AG_EUNSUPPORTED, "ag_reduce_dim: op %d", op);
+  AG_CHECK(inner >= 0 && red >= 0 && outer >= 0, AG_EINVAL, "ag_reduce_dim: negative extent");
+  if (inner * outer == 0) return AG_OK;
+  AG_CHECK(red > 0, AG_EINVAL, "ag_reduce_dim: reducing over an empty collection is not allowed (ArgumentError)");
+  AG_CHECK(x && out, AG_EINVAL, "ag_reduce_dim: null pointer");
+  Context& c = ctx();
+  const int64_t threads = inner == 1 ? outer * 32 : inner * outer;
+  const unsigned nb = (unsigned)cdiv(threads, 256);
+#define RED_LAUNCH(OP_)                                                                                        \
+  do {                                                                                                         \
+    if (dtype == AG_F32) k_reduce_op<OP_, float><<<nb, 256, 0, c.stream>>>((const float*)x, inner, red, outer, (float*)out); \
+    else k_reduce_op<OP_, double><<<nb, 256, 0, c.stream>>>((const double*)x, inner, red, outer, (double*)out);  \
+  } while (0)
+  if (op == 0) RED_LAUNCH(0); else if (op == 1) RED_LAUNCH(1); else RED_LAUNCH(2);
+#undef RED_LAUNCH
+  AG_LAUNCHED();
+  return AG_OK;
 }
 
 ag_status ag_sum_all(int32_t map, int32_t dtype, const void* x, int64_t n, void* out_scalar) {

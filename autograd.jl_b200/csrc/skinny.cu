@@ -3,7 +3,7 @@
 //                                                              gradient w2'*dy (64x10 * 10xB), src/base.jl:26
 //   S2  C[MxN] = A[MxK] * B[NxK]',     M,N <= 64, K huge      gradient dy*a3' (10xB * Bx64)
 // These are HBM/L2-bound streaming passes over the wide operand (algorithmic bytes (MK+KN+MN)*s); the
-// tiny operand lives in shared memory.  A 128-row tensor-core tile would waste >= 84 % of its rows on
+// tiny operand lives in shared memory (S1: one thread per column of the wide operand; S2: one warp per k-range).  A 128-row tensor-core tile would waste >= 84 % of its rows on
 // M = 10 and TMA cannot address a 40-byte leading dimension, so they stay on the FFMA/DFMA pipe.
 // Reductions over K are deterministic (per-block partials, fixed-order second phase).
 #include "common.cuh"
@@ -13,66 +13,6 @@ namespace agb {
 constexpr int SK_T = 256;     // threads
 constexpr int SK_COLS = 64;   // columns of the wide operand per block (S1)
 constexpr int SK_MAXD = 64;   // max extent of the small dims
-
-// ---- S1 ---------------------------------------------------------------------------------------------
-template <typename T, int NJ>
-__global__ void __launch_bounds__(SK_T)
-    k_skinny_left(int transA, int M, int64_t N, int K, T alpha, const T* __restrict__ A, int64_t lda,
-                  const T* __restrict__ B, int64_t ldb, T beta, T* __restrict__ C, int64_t ldc) {
-  extern __shared__ __align__(16) unsigned char sk_smem[];
-  T* As = reinterpret_cast<T*>(sk_smem);        // As[m*(K+1) + k]
-  T* Bs = As + M * (K + 1);                     // Bs[col*SKs + k]; reused for the output tile [col][M]
-  const int t = threadIdx.x;
-  const int SKs = K | 1;                        // odd stride: conflict-free column access
-  const int64_t n0 = (int64_t)blockIdx.x * SK_COLS;
-  const int ncols = (int)min((int64_t)SK_COLS, N - n0);
-  for (int i = t; i < M * K; i += SK_T) {
-    int m, k;
-    if (transA) { k = i % K; m = i / K; As[m * (K + 1) + k] = A[k + (int64_t)m * lda]; }
-    else { m = i % M; k = i / M; As[m * (K + 1) + k] = A[m + (int64_t)k * lda]; }
-  }
-  if (ldb == K) {   // the tile is one contiguous run
-    const T* __restrict__ src = B + n0 * ldb;
-    for (int i = t; i < ncols * K; i += SK_T) Bs[(i / K) * SKs + (i % K)] = src[i];
-  } else {
-    for (int i = t; i < ncols * K; i += SK_T) {
-      int col = i / K, k = i % K;
-      Bs[col * SKs + k] = B[k + (n0 + col) * ldb];
-    }
-  }
-  __syncthreads();
-  const int col = t % SK_COLS, mg = t / SK_COLS;   // 4 row groups
-  T acc[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) acc[j] = T(0);
-  if (col < ncols) {
-    for (int k = 0; k < K; ++k) {
-      const T b = Bs[col * SKs + k];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int m = mg + 4 * j;
-        if (m < M) acc[j] = fma(As[m * (K + 1) + k], b, acc[j]);
-      }
-    }
-  }
-  __syncthreads();
-  T* Cs = Bs;   // output tile [col][M], odd row stride against bank conflicts
-  const int MS = M | 1;
-  if (col < ncols) {
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int m = mg + 4 * j;
-      if (m < M) Cs[col * MS + m] = alpha * acc[j];
-    }
-  }
-  __syncthreads();
-  for (int i = t; i < ncols * M; i += SK_T) {
-    const int c = i / M, m = i % M;
-    T* dst = C + m + (n0 + c) * ldc;
-    const T v = Cs[c * MS + m];
-    *dst = beta == T(0) ? v : v + beta * (*dst);
-  }
-}
 
 // ---- S2 ---------------------------------------------------------------------------------------------
 // block b handles k in [b*kc, min(K,(b+1)*kc)); part[b][m + M*n] = sum_k A[m,k]*B[n,k]
@@ -320,8 +260,8 @@ static ag_status skinny_impl(int transA, int transB, int64_t M, int64_t N, int64
                              int64_t lda, const T* B, int64_t ldb, double beta, T* C, int64_t ldc, bool* done) {
   Context& c = ctx();
   *done = false;
-  if (!transB && M <= SK_MAXD && K <= SK_MAXD && N >= 512 && cdiv(N, SK_COLS) < ((int64_t)1 << 31)) {
-    if (true) {
+  if (!transB && M <= SK_MAXD && K <= SK_MAXD && N >= 512 && cdiv(N, 128) < ((int64_t)1 << 31)) {
+    {
       const unsigned gridc = (unsigned)cdiv(N, 128);
       if (M <= 4) k_skinny_cols<T, 4><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
       else if (M <= 8) k_skinny_cols<T, 8><<<gridc, 128, 0, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B, ldb, (T)beta, C, ldc);
@@ -333,27 +273,6 @@ static ag_status skinny_impl(int transA, int transB, int64_t M, int64_t N, int64
       *done = true;
       return AG_OK;
     }
-    const int sks = (int)K | 1, ms = (int)M | 1;
-    const size_t smem = ((size_t)M * (K + 1) + (size_t)SK_COLS * (sks > ms ? sks : ms)) * sizeof(T);
-    const unsigned grid = (unsigned)cdiv(N, SK_COLS);
-#define SK_LEFT(NJ_)                                                                                        \
-  do {                                                                                                      \
-    static bool attr_set = false;                                                                           \
-    if (!attr_set) {                                                                                        \
-      AG_CUDA(cudaFuncSetAttribute(k_skinny_left<T, NJ_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                   80 * 1024));                                                             \
-      attr_set = true;                                                                                      \
-    }                                                                                                       \
-    k_skinny_left<T, NJ_><<<grid, SK_T, smem, c.stream>>>(transA, (int)M, N, (int)K, (T)alpha, A, lda, B,   \
-                                                         ldb, (T)beta, C, ldc);                             \
-  } while (0)
-    const int nj = (int)cdiv(M, 4);
-    if (nj <= 1) SK_LEFT(1); else if (nj <= 2) SK_LEFT(2); else if (nj <= 3) SK_LEFT(3);
-    else if (nj <= 4) SK_LEFT(4); else if (nj <= 8) SK_LEFT(8); else if (nj <= 12) SK_LEFT(12); else SK_LEFT(16);
-#undef SK_LEFT
-    AG_LAUNCHED();
-    *done = true;
-    return AG_OK;
   }
   if (!transA && transB && M <= SK_MAXD && N <= SK_MAXD && K >= 2048) {
     int64_t nblk = (M <= 16 ? 8 : 2) * (int64_t)c.num_sms;

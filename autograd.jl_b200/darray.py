@@ -416,6 +416,42 @@ def sum_dims(x, dims, mapname="id"):
     return cur
 
 
+def reduce_dims(x, dims, op):
+    """maximum / minimum / prod over dims (keep-dims, Julia): op in {'max','min','prod'}."""
+    x = materialize(x)
+    code = {"max": 0, "min": 1, "prod": 2}[op]
+    dims = sorted({int(d) for d in dims if int(d) < x.ndim}) if dims is not None else list(range(x.ndim))
+    cur, cur_shape = x, list(x.shape)
+    if not dims:
+        return x
+    runs, i = [], 0
+    while i < len(dims):
+        j = i
+        while j + 1 < len(dims) and dims[j + 1] == dims[j] + 1:
+            j += 1
+        runs.append((dims[i], dims[j]))
+        i = j + 1
+    for lo, hi in runs:
+        inner, red, outer = _prod(cur_shape[:lo]), _prod(cur_shape[lo:hi + 1]), _prod(cur_shape[hi + 1:])
+        new_shape = [1 if lo <= d <= hi else e for d, e in enumerate(cur_shape)]
+        out = DArray.empty(new_shape, x.dtype)
+        if out.size:
+            check(lib.ag_reduce_dim(code, x.dt, vptr(cur), inner, red, outer, vptr(out)))
+        cur, cur_shape = out, new_shape
+    return cur
+
+
+def permutedims(x, perm):
+    x = materialize(x)
+    perm = [int(p) for p in perm]
+    if sorted(perm) != list(range(x.ndim)):
+        raise L.DimensionMismatch("permutedims: %s is not a permutation of %d dims" % (perm, x.ndim))
+    out = DArray.empty([x.shape[p] for p in perm], x.dtype)
+    if out.size:
+        check(lib.ag_permute(x.dt, vptr(x), x.ndim, _i64arr(x.shape), (C.c_int32 * x.ndim)(*perm), vptr(out)))
+    return out
+
+
 def add(a, b):
     if a.shape != b.shape:
         raise L.DimensionMismatch("addto!: %s vs %s" % (a.shape, b.shape))

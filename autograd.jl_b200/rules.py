@@ -446,6 +446,43 @@ sumabs2 = primitive("sum(abs2,·)", _sum_fwd_map("abs2"), _sumabs2_back)
 sumabs = primitive("sum(abs,·)", _sum_fwd_map("abs"), _sumabs_back)
 
 
+def _extremum(op, hostf):
+    def fwd(x, dims=None):
+        if isnum(x):
+            return x
+        r = D.reduce_dims(x, _dims(dims), op)
+        return r.reshape(()) if dims is None else r
+    return fwd
+
+
+def _extremum_back(dy, y, x, dims=None):
+    """maximum/minimum: dy.*(y.==x)  (src/base.jl:202,205); y, dy broadcast against x."""
+    if _fusable() and isinstance(value(x), DArray):
+        xv, yv, dyv = value(x), value(y), value(dy)
+        if isinstance(yv, DArray) and yv.ndim < xv.ndim:
+            yv = yv.reshape((1,) * xv.ndim)
+        if isinstance(dyv, DArray) and dyv.ndim < xv.ndim:
+            dyv = dyv.reshape((1,) * xv.ndim)
+        return D.binary_bwd("max", 2, dyv, None, xv, yv)
+    return mul(dy, _mask(y, x))
+
+
+maximum = primitive("maximum", _extremum("max", max), _extremum_back)
+minimum = primitive("minimum", _extremum("min", min), _extremum_back)
+prod = primitive("prod", _extremum("prod", None), lambda dy, y, x, dims=None: mul(dy, div(y, x)))
+
+
+def _invperm(d):
+    r = [0] * len(d)
+    for i, p_ in enumerate(d):
+        r[p_] = i
+    return tuple(r)
+
+
+permutedims = primitive("permutedims", lambda x, d: D.permutedims(x, d),
+                        lambda dy, y, x, d: permutedims(dy, _invperm(d)))
+
+
 def _mean_fwd(x, dims=None):
     s = _sum_fwd_map("id")(x, dims)
     return div.fwd(s, length(x) // max(length(s), 1))
@@ -453,6 +490,27 @@ def _mean_fwd(x, dims=None):
 
 mean = primitive("mean", _mean_fwd,
                  lambda dy, y, x, dims=None: div(_sum_back(dy, y, x, dims), length(x) // length(dy)))
+
+def var(x, dims=None, corrected=True, mean_=None):
+    """var as a composite over primitives (src/statistics.jl:24-35): sum(abs2, x .- m) / (n - corrected)."""
+    m = mean(x, dims=dims) if mean_ is None else mean_
+    n = length(x) if dims is None else length(x) // length(m)
+    return div(sumabs2(sub(x, m), dims=dims), n - (1 if corrected else 0))
+
+
+def std(x, dims=None, corrected=True, mean_=None):
+    return sqrt(var(x, dims=dims, corrected=corrected, mean_=mean_))
+
+
+def norm(x):
+    """2-norm (src/linearalgebra.jl:64-65, p = 2 branch of normback :222-238) as sqrt(sum(abs2, x))."""
+    return sqrt(sumabs2(x))
+
+
+def dot(a, b):
+    """dot(x1,x2) = sum(x1 .* x2)  (src/linearalgebra.jl:23)."""
+    return sum_(mul(a, b))
+
 
 # ---------------------------------------------------------------------------------------------------
 # linear algebra (src/base.jl:26; src/linearalgebra.jl:16,87)

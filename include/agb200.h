@@ -187,6 +187,11 @@ ag_status ag_sum_all(int32_t map, int32_t dtype, const void* x, int64_t n, void*
 ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, int64_t red,
                      int64_t outer, void* out);
 
+/* out[i,o] = op over r of x[i,r,o], op: 0 = maximum, 1 = minimum, 2 = prod (forward of the rules at
+ * src/base.jl:202-206,221; their gradients `dy.*(y.==x)` / `dy.*(y./x)` go through ag_binary_bwd / ag_binary_fwd). */
+ag_status ag_reduce_dim(int32_t op, int32_t dtype, const void* x, int64_t inner, int64_t red, int64_t outer,
+                        void* out);
+
 /* ---- accumulation / update ---------------------------------------------------------------------- */
 /* out = a + b (out may alias a or b).  addto!(a::AbstractArray,b) = a+b, src/addto.jl:23. */
 ag_status ag_add(int32_t dtype, const void* a, const void* b, void* out, int64_t n);
@@ -239,6 +244,9 @@ ag_status ag_scatter_add(int32_t dtype, void* dest, int64_t dest_len, const int6
  * src/cat.jl:27-31,46-67; also getindex/ungetindex with range indices. */
 ag_status ag_slab_copy(int32_t dtype, const void* src, int64_t src_red, int64_t src_off, void* dst,
                        int64_t dst_red, int64_t dst_off, int64_t inner, int64_t len, int64_t outer);
+/* permutedims(x, perm) for ndims <= 4 (src/base.jl:217-218); perm is 0-based: out dim d = x dim perm[d]. */
+ag_status ag_permute(int32_t dtype, const void* x, int32_t ndims, const int64_t* shape, const int32_t* perm,
+                     void* out);
 /* permutedims(x, (2,1)) materialised: out (cols x rows) = transpose of x (rows x cols). */
 ag_status ag_transpose(int32_t dtype, const void* x, int64_t rows, int64_t cols, void* out);
 

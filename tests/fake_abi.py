@@ -204,6 +204,23 @@ class FakeLib:
         _arr(out, inner * outer, T)[:] = r.astype(T).reshape(-1, order="F")
         return 0
 
+    def ag_reduce_dim(self, op, dtype, x, inner, red, outer, out):
+        self.launches += 1
+        T = _DT[dtype]
+        v = _arr(x, inner * red * outer, T).reshape((inner, red, outer), order="F")
+        r = [np.max, np.min, np.prod][op](v, axis=1)
+        _arr(out, inner * outer, T)[:] = r.astype(T).reshape(-1, order="F")
+        return 0
+
+    def ag_permute(self, dtype, x, nd, shape, perm, out):
+        self.launches += 1
+        T = _DT[dtype]
+        shp = [int(shape[i]) for i in range(nd)]
+        pm = [int(perm[i]) for i in range(nd)]
+        v = _arr(x, int(np.prod(shp)), T).reshape(shp, order="F")
+        _arr(out, v.size, T)[:] = np.transpose(v, pm).reshape(-1, order="F")
+        return 0
+
     def ag_add(self, dtype, a, b, out, n):
         self.launches += 1
         T = _DT[dtype]

@@ -246,3 +246,28 @@ def test_axpy_and_fill(ag):
     ag.axpy(-0.5, ag.DArray.from_numpy(x), yd)
     assert np.array_equal(yd.to_numpy(), y - np.float32(0.5) * x)
     assert np.array_equal(ag.zeros((3, 5), np.float64).to_numpy(), np.zeros((3, 5)))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_extrema_prod_permute_stats(ag, oracle, dtype):
+    """maximum / minimum / prod / permutedims / mean / var / std / norm on device against the oracle."""
+    rng = np.random.default_rng(13)
+    x = rng.uniform(0.5, 1.5, (6, 7, 33)).astype(dtype)
+    tol = TOL[dtype]
+    for name, kw in [("maximum", {}), ("maximum", {"dims": 0}), ("maximum", {"dims": 1}), ("minimum", {"dims": (0, 2)}),
+                     ("minimum", {"dims": 2}), ("prod", {"dims": 0}), ("prod", {"dims": 1}), ("mean", {"dims": 2})]:
+        po = oracle.Param(np.asfortranarray(x.astype(np.float64)))
+        to = oracle.diff(lambda: oracle.sumabs2(getattr(oracle, name)(po, **kw)))
+        pd = ag.Param(ag.DArray.from_numpy(x))
+        td = ag.diff(lambda: ag.sumabs2(getattr(ag, name)(pd, **kw)))
+        lo, ld = float(oracle.value(to)), float(ag.value(td))
+        assert abs(lo - ld) <= 8 * tol * abs(lo), (name, kw)
+        assert relerr(ag.grad(td, pd).to_numpy(), oracle.grad(to, po)) <= 8 * tol, (name, kw)
+    xd = ag.DArray.from_numpy(x)
+    for perm in [(1, 0, 2), (2, 0, 1), (2, 1, 0)]:
+        assert np.array_equal(ag.permutedims(xd, perm).to_numpy(), np.transpose(x, perm))
+    x64 = x.astype(np.float64)
+    assert abs(float(ag.var(xd)) - x64.var(ddof=1)) <= 20 * tol * x64.var(ddof=1)
+    assert relerr(ag.std(xd, dims=1).to_numpy(), x64.std(axis=1, ddof=1, keepdims=True)) <= 20 * tol
+    assert abs(float(ag.norm(xd)) - np.linalg.norm(x64)) <= tol * np.linalg.norm(x64)
+    assert ag.gradcheck(lambda z: ag.permutedims(z, (1, 0)), ag.DArray.from_numpy(x64[:, :, 0]))

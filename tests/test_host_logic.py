@@ -215,3 +215,27 @@ def test_cat(hostlib, oracle):
     assert abs(lo - ld) <= 1e-12 * abs(lo)
     for u, v in zip(gd, go):
         assert relerr(u, v) <= 1e-13
+
+
+def test_reductions_and_permute(hostlib, oracle):
+    """maximum / minimum / prod / permutedims / mean / var (src/base.jl:202-221, src/statistics.jl:20-35)."""
+    rng = np.random.default_rng(10)
+    x = rng.uniform(0.5, 1.5, (3, 4, 5))
+    for name, kw in [("maximum", {}), ("maximum", {"dims": 1}), ("minimum", {"dims": (0, 2)}), ("prod", {"dims": 2}),
+                     ("mean", {"dims": 0}), ("sumabs", {"dims": 1})]:
+        def loss(m, p):
+            return m.sumabs2(getattr(m, name)(p[0], **kw))
+        lo, go, ld, gd = run_both(hostlib, oracle, loss, [x], [], np.float64)
+        assert abs(lo - ld) <= 1e-12 * abs(lo), (name, kw)
+        assert relerr(gd[0], go[0]) <= 1e-12, (name, kw)
+
+    def loss(m, p):
+        return m.sumabs2(m.mul(m.permutedims(p[0], (2, 0, 1)), 2.0))
+    lo, go, ld, gd = run_both(hostlib, oracle, loss, [x], [], np.float64)
+    assert abs(lo - ld) <= 1e-12 * abs(lo) and relerr(gd[0], go[0]) <= 1e-12
+    ag = hostlib
+    xd = ag.DArray.from_numpy(x)
+    assert abs(float(ag.var(xd)) - x.var(ddof=1)) < 1e-12
+    assert relerr(ag.var(xd, dims=1).to_numpy(), x.var(axis=1, ddof=1, keepdims=True)) < 1e-12
+    assert abs(float(ag.norm(xd)) - np.linalg.norm(x)) < 1e-12
+    assert ag.gradcheck(lambda z: ag.std(z, dims=0), xd)
