@@ -72,7 +72,7 @@ _SIGS = {
     "ag_comm_init": [i32, i32, C.POINTER(C.c_uint8)],
     "ag_comm_destroy": [],
     "ag_allreduce_sum": [i32, vp, i64],
-    "ag_p2p_export": [i64, C.POINTER(C.c_uint8)],
+    "ag_p2p_export": [i64, i32, C.POINTER(C.c_uint8)],
     "ag_p2p_connect": [i32, i32, C.POINTER(C.c_uint8)],
     "ag_p2p_allreduce_sum": [i32, vp, i64],
     "ag_p2p_allreduce_multi": [i32, i32, C.POINTER(vp), C.POINTER(vp), pi64, dbl],

@@ -31,7 +31,7 @@ class DataParallel:
             check(lib.ag_comm_init(world, rank, idbuf))
             if allgather_bytes is not None and p2p_bytes > 0:
                 h = (C.c_uint8 * 64)()
-                check(lib.ag_p2p_export(int(p2p_bytes), h))
+                check(lib.ag_p2p_export(int(p2p_bytes), world, h))
                 handles = b"".join(allgather_bytes(bytes(h)))
                 hb = (C.c_uint8 * (64 * world)).from_buffer_copy(handles)
                 check(lib.ag_p2p_connect(world, rank, hb))
@@ -65,7 +65,7 @@ class DataParallel:
             D.slab_copy(g, n, 0, b, tot, off, 1, n, 1)
             views.append(DArray(b.buf, b.ptr + off * b.dtype.itemsize, g.shape, b.dtype))
             off += n
-        if self.p2p_cap and tot * b.dtype.itemsize <= self.p2p_cap:
+        if self.p2p_cap and b.dtype == np.float32 and tot * 4 <= min(self.p2p_cap, 1 << 20):
             check(lib.ag_p2p_allreduce_sum(b.dt, D.vptr(b), tot))
         else:
             check(lib.ag_allreduce_sum(b.dt, D.vptr(b), tot))
@@ -83,7 +83,9 @@ class DataParallel:
         dt = live[0][0].dtype
         nbytes = sum(-(-g.size // 4) * 4 for g, _ in live) * dt.itemsize
         fits = len(live) <= 16 and all(g.dtype == dt and w.dtype == dt for g, w in live)
-        if fits and (self.world == 1 or (self.p2p_cap and nbytes <= self.p2p_cap)):
+        # the peer-memory kernel wins only in its flag-in-data form (Float32, <= 1 MB); beyond that NCCL is faster
+        p2p_ok = self.p2p_cap and dt == np.float32 and nbytes <= min(self.p2p_cap, 1 << 20)
+        if fits and (self.world == 1 or p2p_ok):
             n = len(live)
             src = (C.c_void_p * n)(*[g.ptr for g, _ in live])
             dst = (C.c_void_p * n)(*[w.ptr for _, w in live])

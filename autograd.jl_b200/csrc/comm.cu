@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 
 namespace agb {
 
@@ -60,16 +61,19 @@ static ag_status nccl_load() {
 // (measured ~45 us at 8 ranks).  Here every rank publishes its bucket in a symmetric buffer that all peers
 // have mapped through CUDA IPC, raises a flag in every peer's memory, and then sums all peers' buckets itself
 // with plain loads over NVLink/NVSwitch, in rank order (bit-identical result on every rank, deterministic).
-//   symmetric region per rank: [flags: 64 x u32][ctrl: epoch, arrive1, arrive2][pad][buf0: cap][buf1: cap]
+//   symmetric region per rank: [ctrl: epoch, done][flags: 16 x 64 x u32][buf0: cap][buf1: cap]
 struct P2P {
   int nranks = 0, rank = 0;
   size_t cap = 0;
   void* sym = nullptr;                 // my region
   void* peer[16] = {nullptr};          // all regions (peer[rank] == sym)
   void** peer_dev = nullptr;           // device copy of peer[]
+  size_t ll_cap = 0;                   // payload bytes the LL (flag-in-data) receive slots can take
+  size_t ll_off = 0;                   // byte offset of the LL receive area inside the region
+  int ll_ranks = 0;                    // slots allocated per parity
 };
 static P2P g_p2p;
-constexpr size_t P2P_HDR = 1024;
+constexpr size_t P2P_HDR = 8192;    // ctrl words (1 KB) + flags[16 ranks][64 blocks]
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
@@ -93,96 +97,176 @@ struct P2PArgs {
   double alpha;
 };
 
-// One kernel = gather the segments into my symmetric buffer, publish (flag every peer), wait for every peer,
-// sum all peers' buffers in rank order, write the sums back to the segments (+ optional fused axpy!).
+// One kernel = gather the segments into my symmetric buffer, publish, wait for the peers, sum all peers' buffers
+// in rank order, write the sums back to the segments (+ optional fused axpy!).
+// Latency design: the flat index space is cut into one contiguous slice per CTA, identically on every rank, and
+// CTA b only ever touches slice b.  So there is NO grid-wide synchronisation: CTA b copies its slice, fences,
+// raises flag[rank][b] in every peer's memory, spins (one thread per peer) on its own flag[r][b] words, and then
+// reads slice b of every peer.  Flags live in the reader's memory (local polling); they carry the epoch, buffers are
+// double-buffered by epoch parity, so one barrier per call suffices.
+constexpr int P2P_MAXBLK = 64;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-    k_p2p_allreduce(void* const* __restrict__ peers, int nranks, int rank, size_t cap, const P2PArgs a) {
+    k_p2p_allreduce(void* const* __restrict__ peers, int nranks, int rank, size_t cap, const P2PArgs a,
+                    int64_t total_vec) {
   constexpr int NV = 16 / sizeof(T);
   struct alignas(16) V { T v[NV]; };
   uint8_t* my = (uint8_t*)peers[rank];
-  uint32_t* flags = (uint32_t*)my;                       // flags[r]: last epoch published by rank r (+1)
-  uint32_t* ctrl = (uint32_t*)(my + 256);                // [0] epoch, [1] arrive1, [2] arrive2
+  uint32_t* flags = (uint32_t*)(my + 1024);              // flags[r * P2P_MAXBLK + b]
+  uint32_t* ctrl = (uint32_t*)my;                        // [0] epoch, [1] blocks done
   __shared__ uint32_t s_epoch;
   if (threadIdx.x == 0) s_epoch = *(volatile uint32_t*)&ctrl[0];
   __syncthreads();
   const uint32_t e = s_epoch;
   const size_t boff = P2P_HDR + (size_t)(e & 1) * cap;
-  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-  // phase 1: publish my segments in my symmetric buffer
-  T* mine = (T*)(my + boff);
-  for (int k = 0; k < a.nseg; ++k) {
+  // this CTA's slice of the flat (16-byte vector) index space
+  const int64_t per = (total_vec + gridDim.x - 1) / gridDim.x;
+  const int64_t v0 = (int64_t)blockIdx.x * per, v1 = min(total_vec, v0 + per);
+  V* mine = (V*)(my + boff);
+  // phase 1: publish my slice (segments are padded to whole vectors inside the symmetric buffer)
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+    // locate the segment of vector v
+    int k = 0;
+    while (k + 1 < a.nseg && (a.seg[k + 1].off / NV) <= v) ++k;
+    const int64_t i = v * NV - a.seg[k].off;             // element offset inside the segment
     const T* __restrict__ src = (const T*)a.seg[k].src;
-    T* __restrict__ d = mine + a.seg[k].off;
-    const int64_t n = a.seg[k].n;
-    const int64_t nvec = ((((uintptr_t)src) & 15) == 0) ? n / NV : 0;
-    for (int64_t v = t0; v < nvec; v += stride) ((V*)d)[v] = ((const V*)src)[v];
-    for (int64_t i = nvec * NV + t0; i < n; i += stride) d[i] = src[i];
+    V t;
+    if (i + NV <= a.seg[k].n && ((((uintptr_t)src) & 15) == 0)) {
+      t = *reinterpret_cast<const V*>(src + i);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) t.v[j] = (i + j < a.seg[k].n) ? src[i + j] : T(0);
+    }
+    mine[v] = t;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();                              // cumulative: orders the whole block's stores (bar.sync above)
-    const uint32_t t = atomicAdd(&ctrl[1], 1u);
-    if (t == gridDim.x - 1) {                            // whole bucket is visible: raise my flag everywhere
-      ctrl[1] = 0;
-      __threadfence_system();
-      for (int r = 0; r < nranks; ++r) st_release_sys((uint32_t*)peers[r] + rank, e + 1);
-    }
-    // phase 2: wait until every rank has published epoch e (flags are written into MY memory: local polling)
-    for (int r = 0; r < nranks; ++r) {
-      uint32_t spin = 0;
-      while ((int32_t)(ld_acquire_sys(&flags[r]) - (e + 1)) < 0) {
-        if (++spin > (1u << 26)) {
-          printf("libagb200 p2p allreduce: rank %d timed out waiting for rank %d (epoch %u)\n", rank, r, e);
-          __trap();
-        }
+  if ((int)threadIdx.x < nranks) {
+    __threadfence_system();                              // cumulative over the CTA's stores (bar.sync above)
+    st_release_sys((uint32_t*)((uint8_t*)peers[threadIdx.x] + 1024) + rank * P2P_MAXBLK + blockIdx.x, e + 1);
+    // phase 2: wait for slice b of peer `threadIdx.x`
+    const uint32_t* f = flags + threadIdx.x * P2P_MAXBLK + blockIdx.x;
+    uint32_t spin = 0;
+    while ((int32_t)(ld_acquire_sys(f) - (e + 1)) < 0) {
+      if (++spin > (1u << 26)) {
+        printf("libagb200 p2p allreduce: rank %d block %d timed out waiting for rank %d (epoch %u)\n", rank,
+               blockIdx.x, threadIdx.x, e);
+        __trap();
       }
     }
   }
   __syncthreads();
-  // phase 3: sum all published buffers in rank order; 128-bit loads, all peers' loads in flight together
+  // phase 3: sum slice b of every peer in rank order; all peers' loads in flight together
   const T alpha = (T)a.alpha;
-  for (int k = 0; k < a.nseg; ++k) {
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+    V acc, t[8];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc.v[j] = T(0);
+    for (int r0 = 0; r0 < nranks; r0 += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (r0 + u < nranks) t[u] = ((const V*)((const uint8_t*)peers[r0 + u] + boff))[v];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (r0 + u < nranks) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) acc.v[j] += t[u].v[j];
+        }
+    }
+    int k = 0;
+    while (k + 1 < a.nseg && (a.seg[k + 1].off / NV) <= v) ++k;
+    const int64_t i = v * NV - a.seg[k].off;
     T* __restrict__ src = (T*)a.seg[k].src;
     T* __restrict__ dst = (T*)a.seg[k].dst;
-    const int64_t n = a.seg[k].n, off = a.seg[k].off;
-    const bool vec = ((((uintptr_t)src) & 15) == 0) && (!dst || (((uintptr_t)dst) & 15) == 0);
-    const int64_t nvec = vec ? n / NV : 0;
-    for (int64_t v = t0; v < nvec; v += stride) {
-      V acc, t[8];
-#pragma unroll
-      for (int j = 0; j < NV; ++j) acc.v[j] = T(0);
-      for (int r0 = 0; r0 < nranks; r0 += 8) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (r0 + u < nranks) t[u] = ((const V*)((const T*)((const uint8_t*)peers[r0 + u] + boff) + off))[v];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (r0 + u < nranks) {
-#pragma unroll
-            for (int j = 0; j < NV; ++j) acc.v[j] += t[u].v[j];
-          }
-      }
-      ((V*)src)[v] = acc;
+    if (i + NV <= a.seg[k].n && ((((uintptr_t)src) & 15) == 0) && (!dst || (((uintptr_t)dst) & 15) == 0)) {
+      *reinterpret_cast<V*>(src + i) = acc;
       if (dst) {
-        V w = ((V*)dst)[v];
+        V w = *reinterpret_cast<V*>(dst + i);
 #pragma unroll
         for (int j = 0; j < NV; ++j) w.v[j] = fma(alpha, acc.v[j], w.v[j]);
-        ((V*)dst)[v] = w;
+        *reinterpret_cast<V*>(dst + i) = w;
       }
-    }
-    for (int64_t i = nvec * NV + t0; i < n; i += stride) {
-      T sum = T(0);
-      for (int r = 0; r < nranks; ++r) sum += ((const T*)((const uint8_t*)peers[r] + boff))[off + i];
-      src[i] = sum;
-      if (dst) dst[i] = fma(alpha, sum, dst[i]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (i + j < a.seg[k].n) {
+          src[i + j] = acc.v[j];
+          if (dst) dst[i + j] = fma(alpha, acc.v[j], dst[i + j]);
+        }
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const uint32_t t = atomicAdd(&ctrl[2], 1u);
-    if (t == gridDim.x - 1) {                            // every block has read the epoch: advance it
-      ctrl[2] = 0;
+    const uint32_t t = atomicAdd(&ctrl[1], 1u);
+    if (t == gridDim.x - 1) {                            // every CTA has read the epoch: advance it
+      ctrl[1] = 0;
+      __threadfence();
+      *(volatile uint32_t*)&ctrl[0] = e + 1;
+    }
+  }
+}
+
+// ---- LL variant (Float32, small buckets): flag-in-data, push model -------------------------------------
+// Every element travels as one 8-byte word {float bits, epoch+1}.  A rank PUSHES its words into slot `rank` of
+// every peer's receive area (remote 8-byte stores are single-copy atomic), then sums the nranks slots of its OWN
+// receive area in rank order, spinning on each word until its flag shows the current epoch.  No fence, no flag
+// round trip, no grid-wide synchronisation: the critical path is one NVLink store latency plus local loads.
+// Receive areas are double-buffered by epoch parity (a sender can be at most one epoch ahead of a receiver).
+__global__ void __launch_bounds__(256)
+    k_p2p_allreduce_ll(void* const* __restrict__ peers, int nranks, int rank, size_t ll_off, size_t slot_words,
+                       int ll_ranks, const P2PArgs a, int64_t total) {
+  uint8_t* my = (uint8_t*)peers[rank];
+  uint32_t* ctrl = (uint32_t*)my;                        // [0] epoch, [1] blocks done
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = *(volatile uint32_t*)&ctrl[0];
+  __syncthreads();
+  const uint32_t e = s_epoch, flag = e + 1;
+  const size_t par_words = (size_t)(e & 1) * ll_ranks * slot_words;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  // push my elements into slot `rank` of every rank (my own included: uniform summation order)
+  for (int64_t i = i0; i < total; i += stride) {
+    int k = 0;
+    while (k + 1 < a.nseg && a.seg[k + 1].off <= i) ++k;
+    const int64_t j = i - a.seg[k].off;
+    const float v = j < a.seg[k].n ? ((const float*)a.seg[k].src)[j] : 0.f;
+    const uint2 w = make_uint2(__float_as_uint(v), flag);
+    for (int r = 0; r < nranks; ++r) {
+      uint2* dst = (uint2*)((uint8_t*)peers[r] + ll_off) + par_words + (size_t)rank * slot_words + i;
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(w.x), "r"(w.y) : "memory");
+    }
+  }
+  // sum the slots of my receive area in rank order
+  const uint2* recv = (const uint2*)(my + ll_off) + par_words;
+  const float alpha = (float)a.alpha;
+  for (int64_t i = i0; i < total; i += stride) {
+    float sum = 0.f;
+    for (int r = 0; r < nranks; ++r) {
+      const uint2* src = recv + (size_t)r * slot_words + i;
+      uint2 w;
+      uint32_t spin = 0;
+      do {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(src) : "memory");
+        if (++spin > (1u << 26)) {
+          printf("libagb200 p2p LL allreduce: rank %d timed out on slot %d (epoch %u)\n", rank, r, e);
+          __trap();
+        }
+      } while (w.y != flag);
+      sum += __uint_as_float(w.x);
+    }
+    int k = 0;
+    while (k + 1 < a.nseg && a.seg[k + 1].off <= i) ++k;
+    const int64_t j = i - a.seg[k].off;
+    if (j < a.seg[k].n) {
+      ((float*)a.seg[k].src)[j] = sum;
+      float* dst = (float*)a.seg[k].dst;
+      if (dst) dst[j] = fmaf(alpha, sum, dst[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(&ctrl[1], 1u);
+    if (t == gridDim.x - 1) {
+      ctrl[1] = 0;
       __threadfence();
       *(volatile uint32_t*)&ctrl[0] = e + 1;
     }
@@ -227,13 +311,17 @@ using namespace agb;
 
 extern "C" {
 
-ag_status ag_p2p_export(int64_t cap_bytes, uint8_t* handle64) {
+ag_status ag_p2p_export(int64_t cap_bytes, int32_t nranks, uint8_t* handle64) {
   AG_REQUIRE_INIT();
-  AG_CHECK(cap_bytes > 0 && handle64, AG_EINVAL, "ag_p2p_export: bad arguments");
+  AG_CHECK(cap_bytes > 0 && handle64 && nranks >= 1 && nranks <= 16, AG_EINVAL, "ag_p2p_export: bad arguments");
   AG_CHECK(!g_p2p.sym, AG_ESTATE, "ag_p2p_export: already exported");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   g_p2p.cap = ((size_t)cap_bytes + 255) & ~size_t(255);
-  const size_t total = P2P_HDR + 2 * g_p2p.cap;
+  // LL receive area: 2 parities x nranks slots x (8-byte word per Float32 element), payload <= 1 MB
+  g_p2p.ll_cap = g_p2p.cap < ((size_t)1 << 20) ? g_p2p.cap : ((size_t)1 << 20);
+  g_p2p.ll_ranks = nranks;
+  g_p2p.ll_off = P2P_HDR + 2 * g_p2p.cap;
+  const size_t total = g_p2p.ll_off + (size_t)2 * nranks * (g_p2p.ll_cap * 2);
   AG_CUDA(cudaMalloc(&g_p2p.sym, total));
   AG_CUDA(cudaMemset(g_p2p.sym, 0, total));
   AG_CUDA(cudaDeviceSynchronize());
@@ -248,6 +336,8 @@ ag_status ag_p2p_connect(int32_t nranks, int32_t rank, const uint8_t* handles) {
   AG_CHECK(g_p2p.sym, AG_ESTATE, "ag_p2p_connect: call ag_p2p_export first");
   AG_CHECK(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks && handles, AG_EINVAL,
            "ag_p2p_connect: rank %d of %d", rank, nranks);
+  AG_CHECK(nranks == g_p2p.ll_ranks, AG_EINVAL, "ag_p2p_connect: exported for %d ranks, connecting %d",
+           g_p2p.ll_ranks, nranks);
   g_p2p.nranks = nranks;
   g_p2p.rank = rank;
   for (int r = 0; r < nranks; ++r) {
@@ -278,14 +368,25 @@ ag_status ag_p2p_allreduce_multi(int32_t dtype, int32_t nseg, void* const* src, 
   AG_CHECK(bytes <= g_p2p.cap, AG_EINVAL, "ag_p2p_allreduce_multi: %zu bytes exceed the symmetric buffer (%zu)",
            bytes, g_p2p.cap);
   Context& c = ctx();
-  int64_t blocks = cdiv(total, 256 * 16);          // latency-bound: few blocks, 4 x 128-bit items per thread
-  if (blocks > c.num_sms) blocks = c.num_sms;      // every block polls the flags: co-resident by construction
+  if (dtype == AG_F32 && bytes <= g_p2p.ll_cap && !getenv("AGB_P2P_NO_LL")) {
+    int64_t blocks = cdiv(total, 256);
+    if (blocks > 2 * c.num_sms) blocks = 2 * c.num_sms;
+    k_p2p_allreduce_ll<<<(unsigned)blocks, 256, 0, c.stream>>>(g_p2p.peer_dev, g_p2p.nranks, g_p2p.rank,
+                                                               g_p2p.ll_off, g_p2p.ll_cap / 4, g_p2p.ll_ranks, a, total);
+    AG_LAUNCHED();
+    return AG_OK;
+  }
+  const int64_t nv = dtype == AG_F32 ? 4 : 2;
+  const int64_t total_vec = total / nv;              // segments are padded to whole 16-byte vectors
+  int64_t blocks = cdiv(total_vec, 256);             // latency-bound: one vector per thread where possible
+  if (blocks > P2P_MAXBLK) blocks = P2P_MAXBLK;
+  if (blocks < 1) blocks = 1;
   if (dtype == AG_F32)
     k_p2p_allreduce<float><<<(unsigned)blocks, 256, 0, c.stream>>>(g_p2p.peer_dev, g_p2p.nranks, g_p2p.rank,
-                                                                   g_p2p.cap, a);
+                                                                   g_p2p.cap, a, total_vec);
   else
     k_p2p_allreduce<double><<<(unsigned)blocks, 256, 0, c.stream>>>(g_p2p.peer_dev, g_p2p.nranks, g_p2p.rank,
-                                                                    g_p2p.cap, a);
+                                                                    g_p2p.cap, a, total_vec);
   AG_LAUNCHED();
   return AG_OK;
 }

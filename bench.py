@@ -165,7 +165,7 @@ def main():
             out = [None] * world
             dist.all_gather_object(out, payload)
             return out
-        use_p2p = os.environ.get("AGB_ALLREDUCE", "nccl") == "p2p"     # measured: NCCL wins at 200 KB
+        use_p2p = os.environ.get("AGB_ALLREDUCE", "p2p") == "p2p"      # AGB_ALLREDUCE=nccl forces the NCCL path
         dp = ag.DataParallel(rank, world, bcast, allgather if use_p2p else None)
         dist.barrier()
     else:
@@ -358,7 +358,7 @@ def main():
             "config": {"workload": "examples/mnist.jl MLP 784-64-10 softmax (configs[1]), batch %d per GPU, Float32, "
                                    "@diff + grad + allreduce + axpy!; value counts one per-rank step per rank" % B,
                        "global_batch": gB, "parallelism": "dp%d" % world, "replay": replay,
-                       "allreduce": ("one-shot peer-memory kernel over NVLink (ag_p2p_allreduce_sum)" if dp.p2p_cap else
+                       "allreduce": ("one-shot peer-memory kernel over NVLink, flag-in-data, fused axpy! (ag_p2p_allreduce_multi)" if dp.p2p_cap else
                                      "NCCL") if world > 1 else None,
                        "l2": "inputs (x = %.0f MB per rank) larger than the 126 MB L2; no flush" % (x_np.nbytes / 1e6)},
             "forward_ms": fwd_ms, "backward_update_ms": bwd_ms,

@@ -262,8 +262,9 @@ ag_status ag_allreduce_sum(int32_t dtype, void* buf, int64_t n);
  * exports a symmetric buffer (CUDA IPC handle, 64 bytes), the launcher gathers the handles of all ranks and
  * hands them to ag_p2p_connect; ag_p2p_allreduce_sum then sums `buf` over all ranks in place with ONE kernel
  * (publish, flag every peer, sum all peers' buckets in rank order: bit-identical on every rank).
- * n*sizeof(dtype) must not exceed cap_bytes.  Graph-capturable. */
-ag_status ag_p2p_export(int64_t cap_bytes, uint8_t* handle64);
+ * n*sizeof(dtype) must not exceed cap_bytes.  Float32 buckets up to 1 MB use a flag-in-data (LL) push protocol:
+ * no fence and no flag round trip on the critical path.  Graph-capturable. */
+ag_status ag_p2p_export(int64_t cap_bytes, int32_t nranks, uint8_t* handle64);
 ag_status ag_p2p_connect(int32_t nranks, int32_t rank, const uint8_t* handles /* nranks x 64 bytes */);
 ag_status ag_p2p_allreduce_sum(int32_t dtype, void* buf, int64_t n);
 /* Multi-tensor form (<= 16 segments, no bucket copies): src[k] (n = sizes[k]) is replaced by its sum over all

@@ -315,7 +315,7 @@ class FakeLib:
 
     def ag_comm_destroy(self): return 0
 
-    def ag_p2p_export(self, cap, h):
+    def ag_p2p_export(self, cap, nranks, h):
         return 0
 
     def ag_p2p_connect(self, nranks, rank, handles):
