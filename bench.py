@@ -47,7 +47,7 @@ class Clocks:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -62,9 +62,11 @@ class Clocks:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for ts, r in self.rows if (t0 is None or ts >= t0 - 0.05) and (t1 is None or ts <= t1 + 0.15)]
-        if not rows:
+        rows = [r for ts, r in self.rows if (t0 is None or ts >= t0 - 0.02) and (t1 is None or ts <= t1 + 0.02)]
+        window = "timed region"
+        if len(rows) < 3:       # the timed region is only a few ms: fall back to every sample taken under load
             rows = [r for _, r in self.rows]
+            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -77,7 +79,7 @@ class Clocks:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_reference_run(steps, warmup, budget_s=20.0):
@@ -129,8 +131,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="agb200")
     ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -240,13 +242,15 @@ def main():
             exchange()
             g_b.launch()
 
+    clocks = Clocks(local)
     for _ in range(W_):
         step()
     barrier()
 
     # ---- timed region: device-resident inputs (x = 205 MB > 126 MB L2, so no L2 flush needed)
-    clocks = Clocks(local)
-    time.sleep(0.3)
+    for _ in range(200):          # keep the GPU under load while nvidia-smi takes its first samples
+        step()
+    barrier()
     l0 = ag.launch_count()
     e0, e1 = ag.Event(), ag.Event()
     barrier()
