@@ -30,12 +30,18 @@ class DataParallel:
             idbuf = (C.c_uint8 * 128).from_buffer_copy(payload)
             check(lib.ag_comm_init(world, rank, idbuf))
             if allgather_bytes is not None and p2p_bytes > 0:
+                # every rank must agree on the collective: gather a success flag after each stage and fall back
+                # to NCCL everywhere if CUDA IPC / peer access is unavailable on any rank
                 h = (C.c_uint8 * 64)()
-                check(lib.ag_p2p_export(int(p2p_bytes), world, h))
-                handles = b"".join(allgather_bytes(bytes(h)))
-                hb = (C.c_uint8 * (64 * world)).from_buffer_copy(handles)
-                check(lib.ag_p2p_connect(world, rank, hb))
-                self.p2p_cap = int(p2p_bytes)
+                ok = lib.ag_p2p_export(int(p2p_bytes), world, h) == 0
+                got = allgather_bytes((b"\x01" if ok else b"\x00") + bytes(h))
+                if all(g[:1] == b"\x01" for g in got):
+                    hb = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(g[1:] for g in got))
+                    ok = lib.ag_p2p_connect(world, rank, hb) == 0
+                    if all(g == b"\x01" for g in allgather_bytes(b"\x01" if ok else b"\x00")):
+                        self.p2p_cap = int(p2p_bytes)
+                if not self.p2p_cap:
+                    lib.ag_p2p_destroy()
         self._bucket = None
 
     @staticmethod

@@ -101,30 +101,29 @@ __global__ void __launch_bounds__(128)
       for (int j = 0; j < NV; ++j) acc[m + j] = fma(a4.v[j], bv, acc[m + j]);
     }
   };
-  int k = 0;
-  const bool vecB = (ldb % NV) == 0 && ((((uintptr_t)B) & 15) == 0);
+  // the whole column (K <= 64) is fetched before any arithmetic: one round of memory latency per thread
+  const bool vecB = (ldb % NV) == 0 && ((((uintptr_t)B) & 15) == 0) && (K % NV) == 0;
   if (vecB) {
-    // the column is 16-byte aligned: stream it with 128-bit loads, 4 in flight
-    for (; k + 4 * NV <= K; k += 4 * NV) {
-      V q[4];
+    V q[SK_MAXD / NV];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const V*>(b + k + u * NV);
+    for (int u = 0; u < SK_MAXD / NV; ++u)
+      if (u * NV < K) q[u] = *reinterpret_cast<const V*>(b + u * NV);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < SK_MAXD / NV; ++u)
+      if (u * NV < K) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) fma_k(k + u * NV + j, q[u].v[j]);
-    }
-    for (; k + NV <= K; k += NV) {
-      const V q = *reinterpret_cast<const V*>(b + k);
+        for (int j = 0; j < NV; ++j) fma_k(u * NV + j, q[u].v[j]);
+      }
+  } else {
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      T bv[16];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) fma_k(k + j, q.v[j]);
+      for (int u = 0; u < 16; ++u) bv[u] = (k0 + u < K) ? b[k0 + u] : T(0);
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (k0 + u < K) fma_k(k0 + u, bv[u]);
     }
   }
-  for (; k + 4 <= K; k += 4) {
-    const T b0 = b[k], b1 = b[k + 1], b2 = b[k + 2], b3 = b[k + 3];
-    fma_k(k, b0); fma_k(k + 1, b1); fma_k(k + 2, b2); fma_k(k + 3, b3);
-  }
-  for (; k < K; ++k) fma_k(k, b[k]);
   T* __restrict__ c = C + col * ldc;
   if (beta == T(0)) {
     if (MB == M && (ldc % NV) == 0 && (((uintptr_t)C) & 15) == 0) {
@@ -150,11 +149,10 @@ __global__ void __launch_bounds__(128)
 // ---- S2 (warp form, M <= 16, N <= 64): part[blk][m + M*n] = sum_{k in block range} A[m,k]*B[n,k] ----------
 // Each warp walks a contiguous k-range: lanes own n = lane and lane+32 (coalesced row reads of B), the M
 // values A[:,k] are warp-uniform (broadcast loads).  Block partials are combined through shared memory.
-template <typename T>
+template <typename T, int MB>
 __global__ void __launch_bounds__(128)
     k_skinny_nt_warp(int M, int N, int64_t K, int64_t kc, const T* __restrict__ A, int64_t lda,
                      const T* __restrict__ B, int64_t ldb, T* __restrict__ part) {
-  constexpr int MB = 16;
   constexpr int NW = 4;
   __shared__ T sm[NW][MB * 64];
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -165,17 +163,17 @@ __global__ void __launch_bounds__(128)
   for (int m = 0; m < MB; ++m) acc0[m] = acc1[m] = T(0);
   const bool n0ok = lane < N, n1ok = lane + 32 < N;
   int64_t k = k0 + wrp;
-  for (; k + 3 * NW < k1; k += 4 * NW) {      // four k per trip: all loads issued before the FMAs
-    T bb0[4], bb1[4], av[4];
+  for (; k + 7 * NW < k1; k += 8 * NW) {      // eight k per trip: all loads issued before the FMAs
+    T bb0[8], bb1[8], av[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const T* __restrict__ b = B + (k + u * NW) * ldb;
       bb0[u] = n0ok ? b[lane] : T(0);
       bb1[u] = n1ok ? b[lane + 32] : T(0);
       av[u] = lane < M ? A[(k + u * NW) * lda + lane] : T(0);     // lane m holds A[m,k]
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
 #pragma unroll
       for (int m = 0; m < MB; ++m) {
         const T a = __shfl_sync(0xffffffffu, av[u], m);
@@ -281,7 +279,10 @@ static ag_status skinny_impl(int transA, int transB, int64_t M, int64_t N, int64
     T* part = (T*)workspace((size_t)(nblk * M * N) * sizeof(T));
     if (!part) return AG_ENOMEM;
     if (M <= 16) {
-      k_skinny_nt_warp<T><<<(unsigned)nblk, 128, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part);
+      if (M <= 4) k_skinny_nt_warp<T, 4><<<(unsigned)nblk, 128, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part);
+      else if (M <= 8) k_skinny_nt_warp<T, 8><<<(unsigned)nblk, 128, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part);
+      else if (M <= 12) k_skinny_nt_warp<T, 12><<<(unsigned)nblk, 128, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part);
+      else k_skinny_nt_warp<T, 16><<<(unsigned)nblk, 128, 0, c.stream>>>((int)M, (int)N, K, kc, A, lda, B, ldb, part);
       AG_LAUNCHED();
       *done = true;
       return reduce_partials<T>(part, (int)nblk, M, N, alpha, beta, C, ldc);

@@ -291,3 +291,54 @@ def test_full_size_properties(ag):
     da2 = (w64[2].T @ dp) * (a2_dev >= 0)
     assert relerr(g1[1], da2.sum(1)) <= 1e-5
     assert relerr(g1[0], da2 @ x.astype(np.float64).T) <= 1e-5
+
+
+def test_sweep_full_size_properties(ag):
+    """BASELINE config 3 at 2^26 elements (256 MB arrays): size-independent properties.
+    (a) scaling x by 2 scales sum(abs2, .) by exactly 4 and its gradient by exactly 2 (powers of two are exact);
+    (b) the broadcast gradients equal the row / column sums of the full gradient (unbroadcast, src/unbroadcast.jl:17-24);
+    (c) deterministic: two runs are bit-identical."""
+    rng = np.random.default_rng(31)
+    rows, cols = 1024, 65536
+    x = rng.standard_normal((rows, cols), dtype=np.float32)
+    xd = ag.DArray.from_numpy(x)
+    x2 = ag.mul(2.0, xd)
+    g1 = ag.grad(lambda v: ag.sumabs2(v))(xd)
+    g2 = ag.grad(lambda v: ag.sumabs2(v))(x2)
+    assert float(ag.sumabs2(x2)) == 4.0 * float(ag.sumabs2(xd))
+    assert np.array_equal(g2.to_numpy(), 2 * g1.to_numpy())
+    ref = float(np.sum(x.astype(np.float64) ** 2))
+    assert abs(float(ag.sumabs2(xd)) - ref) <= 1e-6 * ref
+    brow = ag.Param(ag.DArray.from_numpy((0.1 * rng.standard_normal((1, cols))).astype(np.float32)))
+    bcol = ag.Param(ag.DArray.from_numpy((0.1 * rng.standard_normal((rows, 1))).astype(np.float32)))
+    px = ag.Param(xd)
+    W = ag.workloads
+    t = ag.diff(lambda: W.sweep_loss(ag, px, brow, bcol))
+    gx = ag.grad(t, px).to_numpy().astype(np.float64)
+    gcol = ag.grad(t, bcol).to_numpy()
+    grow = ag.grad(t, brow).to_numpy()
+    # d/dbrow = column sums of d/d(0.1x + brow) = 10 * column sums of gx
+    assert relerr(grow, 10.0 * gx.sum(axis=0, keepdims=True)) <= 1e-5
+    t2 = ag.diff(lambda: W.sweep_loss(ag, px, brow, bcol))
+    assert np.array_equal(ag.grad(t2, bcol).to_numpy(), gcol)
+    assert float(ag.value(t)) == float(ag.value(t2))
+
+
+def test_sparse_scatter_full_size(ag):
+    """Config 4's embedding gradient at full size: 100 blocks of (128 x 256) values, 25 600 column indices into a
+    (128 x 128) container.  Touched-column set bit-exact, values within tolerance of a float64 host scatter,
+    result bit-reproducible."""
+    rng = np.random.default_rng(32)
+    E, V, B, T = 128, 128, 256, 100
+    Wd = ag.zeros((E, V), np.float32)
+    ids = [rng.integers(0, V - 5, B) for _ in range(T)]          # the last 5 columns stay untouched
+    vals = [rng.standard_normal((E, B)).astype(np.float32) for _ in range(T)]
+    sp = ag.Sparse(Wd, [ag.DArray.from_numpy(v) for v in vals], [(slice(None), ag.IArray(i)) for i in ids])
+    got = sp.full().to_numpy()
+    ref = np.zeros((E, V))
+    for i, v in zip(ids, vals):
+        np.add.at(ref, (slice(None), i), v.astype(np.float64))
+    assert np.array_equal(got[:, V - 5:], np.zeros((E, 5), np.float32))
+    assert np.array_equal(np.any(got != 0, axis=0), np.any(ref != 0, axis=0))
+    assert relerr(got, ref) <= 1e-5
+    assert np.array_equal(got, sp.full().to_numpy())
