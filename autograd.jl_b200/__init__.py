@@ -18,5 +18,6 @@ from . import rules, workloads
 from .graph import StepGraph, Event, pinned_empty
 from .comm import DataParallel
 from .gradcheck import gradcheck
+from .vm import E, Expr, primitive_expr
 
 __all__ = [n for n in dir() if not n.startswith("_")]

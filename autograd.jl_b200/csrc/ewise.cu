@@ -388,6 +388,137 @@ static ag_status launch_map(MapArgs<NIN>& a) {
   return AG_OK;
 }
 
+// ---- bytecode evaluator: fused elementwise kernels for user-defined primitives ------------------------
+// `@primitive f(x),dy,y (expr)` accepts arbitrary broadcast expressions (src/macros.jl:88-105; e.g. sigm at
+// examples/charlm.jl:46-47).  The host compiles such an expression to postfix bytecode once; this kernel
+// evaluates it per element in ONE pass over memory (no temporaries).  Elementwise kernels have ~100 spare FP32
+// instructions per element at HBM speed, so interpretation (decoded once per 128-bit vector) stays near the
+// memory roofline for short programs.
+constexpr int VM_MAXCODE = 64, VM_MAXCONST = 16, VM_MAXIN = 4, VM_STACK = 8;
+enum { VM_IN = 0, VM_CONST = 1, VM_ADD = 2, VM_SUB = 3, VM_MUL = 4, VM_DIV = 5, VM_NEG = 6, VM_MAX = 7, VM_MIN = 8,
+       VM_POW = 9, VM_EQ = 10, VM_LT = 11, VM_LE = 12, VM_GT = 13, VM_GE = 14, VM_UNARY = 15 };
+struct VmArgs {
+  int32_t code[VM_MAXCODE];
+  double consts[VM_MAXCONST];
+  const void* in[VM_MAXIN];
+  double imm[VM_MAXIN];
+  int32_t mode[VM_MAXIN];   // 0 array, 1 device scalar, 2 immediate
+  int32_t ncode, nin;
+  void* out;
+  int64_t n;
+};
+
+template <typename T>
+__device__ __forceinline__ T vm_unary(int u, T x) {
+  switch (u) {
+    case AG_U_IDENTITY: return x;
+    case AG_U_NEG: return -x;
+    case AG_U_ABS: return fabs(x);
+    case AG_U_ABS2: return x * x;
+    case AG_U_EXP: return exp(x);
+    case AG_U_LOG: return log(x);
+    case AG_U_TANH: return tanh(x);
+    case AG_U_SIGM: return T(1) / (T(1) + exp(-x));
+    case AG_U_SQRT: return sqrt(x);
+    case AG_U_SIN: return sin(x);
+    case AG_U_COS: return cos(x);
+    case AG_U_TAN: return tan(x);
+    case AG_U_SINH: return sinh(x);
+    case AG_U_COSH: return cosh(x);
+    case AG_U_ASIN: return asin(x);
+    case AG_U_ACOS: return acos(x);
+    case AG_U_ATAN: return atan(x);
+    case AG_U_ASINH: return asinh(x);
+    case AG_U_ACOSH: return acosh(x);
+    case AG_U_ATANH: return atanh(x);
+    case AG_U_EXP2: return exp2(x);
+    case AG_U_EXP10: return exp10(x);
+    case AG_U_EXPM1: return expm1(x);
+    case AG_U_LOG2: return log2(x);
+    case AG_U_LOG10: return log10(x);
+    case AG_U_LOG1P: return log1p(x);
+    case AG_U_CBRT: return cbrt(x);
+    case AG_U_SIGN: return sgn(x);
+    case AG_U_RELU: return relu(x);
+    case AG_U_ONE: return T(1);
+  }
+  return x;
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_vm(const VmArgs a) {
+  constexpr int N = VEC ? Pack<T>::N : 1;
+  const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * N;
+  if (i >= a.n) return;
+  T inv[VM_MAXIN][N];
+#pragma unroll
+  for (int k = 0; k < VM_MAXIN; ++k) {
+    if (k < a.nin) {
+      if (a.mode[k] == 0) {
+        if (VEC) {
+          const Pack<T> t = *reinterpret_cast<const Pack<T>*>((const T*)a.in[k] + i);
+#pragma unroll
+          for (int j = 0; j < N; ++j) inv[k][j] = t.v[j];
+        } else {
+          inv[k][0] = ((const T*)a.in[k])[i];
+        }
+      } else {
+        const T sc = a.mode[k] == 1 ? ((const T*)a.in[k])[0] : (T)a.imm[k];
+#pragma unroll
+        for (int j = 0; j < N; ++j) inv[k][j] = sc;
+      }
+    }
+  }
+  T st[VM_STACK][N];
+  int sp = 0;
+  for (int pc = 0; pc < a.ncode; ++pc) {
+    const int op = a.code[pc] & 0xff, arg = a.code[pc] >> 8;
+    if (op == VM_IN) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) st[sp][j] = arg == 0 ? inv[0][j] : (arg == 1 ? inv[1][j] : (arg == 2 ? inv[2][j] : inv[3][j]));
+      ++sp;
+    } else if (op == VM_CONST) {
+      const T cv = (T)a.consts[arg];
+#pragma unroll
+      for (int j = 0; j < N; ++j) st[sp][j] = cv;
+      ++sp;
+    } else if (op >= VM_UNARY || op == VM_NEG) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) st[sp - 1][j] = op == VM_NEG ? -st[sp - 1][j] : vm_unary<T>(op - VM_UNARY, st[sp - 1][j]);
+    } else {
+      --sp;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const T x = st[sp - 1][j], y = st[sp][j];
+        T r;
+        switch (op) {
+          case VM_ADD: r = x + y; break;
+          case VM_SUB: r = x - y; break;
+          case VM_MUL: r = x * y; break;
+          case VM_DIV: r = x / y; break;
+          case VM_MAX: r = jmax(x, y); break;
+          case VM_MIN: r = jmin(x, y); break;
+          case VM_POW: r = pow(x, y); break;
+          case VM_EQ: r = x == y ? T(1) : T(0); break;
+          case VM_LT: r = x < y ? T(1) : T(0); break;
+          case VM_LE: r = x <= y ? T(1) : T(0); break;
+          case VM_GT: r = x > y ? T(1) : T(0); break;
+          default: r = x >= y ? T(1) : T(0); break;
+        }
+        st[sp - 1][j] = r;
+      }
+    }
+  }
+  if (VEC) {
+    Pack<T> o;
+#pragma unroll
+    for (int j = 0; j < N; ++j) o.v[j] = st[0][j];
+    *reinterpret_cast<Pack<T>*>((T*)a.out + i) = o;
+  } else {
+    ((T*)a.out)[i] = st[0][0];
+  }
+}
+
 static ag_status fill_shape(int32_t ndims, const int64_t* shape, int64_t* out_shape, int64_t* n) {
   AG_CHECK(ndims >= 1 && ndims <= 4 && shape, AG_EUNSUPPORTED,
            "broadcast map: ndims=%d (collapse to <=4 dims on the host)", ndims);
@@ -598,6 +729,60 @@ ag_status ag_binary_bwd(int32_t op, int32_t argno, int32_t dtype, const void* dy
       return AG_EUNSUPPORTED;
   }
   return dtype == AG_F32 ? ternary_dispatch<float>(which, m) : ternary_dispatch<double>(which, m);
+}
+
+ag_status ag_ewise_vm(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts, int32_t nconsts,
+                      int32_t nin, const void* const* in, const int32_t* in_mode, const double* in_imm, void* out,
+                      int64_t n) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_ewise_vm: dtype %d", dtype);
+  AG_CHECK(code && ncode >= 1 && ncode <= VM_MAXCODE, AG_EUNSUPPORTED, "ag_ewise_vm: program length %d (max %d)", ncode,
+           VM_MAXCODE);
+  AG_CHECK(nconsts >= 0 && nconsts <= VM_MAXCONST && nin >= 0 && nin <= VM_MAXIN, AG_EUNSUPPORTED,
+           "ag_ewise_vm: %d constants / %d inputs (max %d / %d)", nconsts, nin, VM_MAXCONST, VM_MAXIN);
+  if (n == 0) return AG_OK;
+  AG_CHECK(out && n > 0, AG_EINVAL, "ag_ewise_vm: bad output");
+  VmArgs a;
+  // validate the program: operand indices and stack discipline
+  int depth = 0;
+  for (int pc = 0; pc < ncode; ++pc) {
+    const int op = code[pc] & 0xff, arg = code[pc] >> 8;
+    if (op == VM_IN) { AG_CHECK(arg >= 0 && arg < nin, AG_EINVAL, "ag_ewise_vm: input %d of %d", arg, nin); ++depth; }
+    else if (op == VM_CONST) { AG_CHECK(arg >= 0 && arg < nconsts, AG_EINVAL, "ag_ewise_vm: constant %d of %d", arg, nconsts); ++depth; }
+    else if (op == VM_NEG || op >= VM_UNARY) {
+      AG_CHECK(depth >= 1 && (op == VM_NEG || op - VM_UNARY < AG_U_COUNT), AG_EINVAL, "ag_ewise_vm: bad unary op %d", op);
+    } else { AG_CHECK(depth >= 2, AG_EINVAL, "ag_ewise_vm: stack underflow at %d", pc); --depth; }
+    AG_CHECK(depth <= VM_STACK, AG_EUNSUPPORTED, "ag_ewise_vm: expression too deep (stack %d)", VM_STACK);
+    a.code[pc] = code[pc];
+  }
+  AG_CHECK(depth == 1, AG_EINVAL, "ag_ewise_vm: program leaves %d values on the stack", depth);
+  for (int k = 0; k < nconsts; ++k) a.consts[k] = consts[k];
+  bool vec = aligned16(out);
+  for (int k = 0; k < nin; ++k) {
+    a.mode[k] = in_mode ? in_mode[k] : 0;
+    a.in[k] = in ? in[k] : nullptr;
+    a.imm[k] = in_imm ? in_imm[k] : 0.0;
+    AG_CHECK(a.mode[k] >= 0 && a.mode[k] <= 2 && (a.mode[k] == 2 || a.in[k]), AG_EINVAL, "ag_ewise_vm: bad input %d", k);
+    if (a.mode[k] == 0) vec = vec && aligned16(a.in[k]);
+  }
+  a.ncode = ncode;
+  a.nin = nin;
+  a.out = out;
+  a.n = n;
+  Context& c = ctx();
+  const int N = dtype == AG_F32 ? 4 : 2;
+  vec = vec && (n % N == 0);
+  if (vec) {
+    unsigned nb = (unsigned)cdiv(n / N, kThreads);
+    if (dtype == AG_F32) k_vm<float, true><<<nb, kThreads, 0, c.stream>>>(a);
+    else k_vm<double, true><<<nb, kThreads, 0, c.stream>>>(a);
+  } else {
+    unsigned nb = (unsigned)cdiv(n, kThreads);
+    if (dtype == AG_F32) k_vm<float, false><<<nb, kThreads, 0, c.stream>>>(a);
+    else k_vm<double, false><<<nb, kThreads, 0, c.stream>>>(a);
+  }
+  AG_LAUNCHED();
+  return AG_OK;
 }
 
 ag_status ag_add(int32_t dtype, const void* a, const void* b, void* out, int64_t n) {

@@ -176,6 +176,16 @@ ag_status ag_binary_bwd(int32_t op, int32_t argno, int32_t dtype, const void* dy
                         const int64_t* x2_strides, const void* y, const int64_t* y_strides,
                         void* dx, int32_t ndims, const int64_t* shape);
 
+/* Fused evaluator for user-defined primitives (`@primitive f(x),dy,y (expr)`, src/macros.jl:88-105; e.g. sigm,
+ * examples/charlm.jl:46-47): out[i] = program(in0[i], ..., in3[i]) in one pass.  `code` is postfix bytecode, one
+ * int32 per instruction = op | (arg << 8): 0 push input[arg], 1 push consts[arg], 2 + 3 - 4 * 5 / 6 neg 7 max 8 min
+ * 9 pow 10 == 11 < 12 <= 13 > 14 >= (comparisons give 1.0/0.0), 15+u = unary f of AG_U_* id u.  <= 64
+ * instructions, <= 16 constants, <= 4 inputs (in_mode: 0 array of n, 1 device scalar, 2 immediate in_imm),
+ * stack depth <= 8.  Inputs must already have the output's shape (the caller unbroadcasts afterwards). */
+ag_status ag_ewise_vm(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts, int32_t nconsts,
+                      int32_t nin, const void* const* in, const int32_t* in_mode, const double* in_imm, void* out,
+                      int64_t n);
+
 /* ---- reductions -------------------------------------------------------------------------------- */
 /* out[0] = sum(map.(x)) over n elements; deterministic two-phase tree.  sum(x), sum(abs2,x),
  * sum(abs,x) forward (rules at src/base.jl:245-247); unbroadcast's Number branch

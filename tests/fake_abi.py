@@ -188,6 +188,30 @@ class FakeLib:
         _arr(dx, int(np.prod(shape)), T)[:] = r.reshape(-1, order="F")
         return 0
 
+    def ag_ewise_vm(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, out, n):
+        self.launches += 1
+        T = _DT[dtype]
+        vals = []
+        for k in range(nin):
+            m = int(modes[k])
+            vals.append(_arr(ins[k], n, T) if m == 0 else (_arr(ins[k], 1, T)[0] if m == 1 else T(imms[k])))
+        st = []
+        with np.errstate(all="ignore"):
+            for pc in range(ncode):
+                op, arg = int(code[pc]) & 0xff, int(code[pc]) >> 8
+                if op == 0: st.append(vals[arg])
+                elif op == 1: st.append(T(consts[arg]))
+                elif op == 6: st.append(-st.pop())
+                elif op >= 15: st.append(_U[op - 15][0](np.asarray(st.pop(), dtype=T)))
+                else:
+                    b, a = st.pop(), st.pop()
+                    f = {2: np.add, 3: np.subtract, 4: np.multiply, 5: np.divide, 7: np.maximum, 8: np.minimum, 9: np.power,
+                         10: lambda p, q: (p == q), 11: lambda p, q: (p < q), 12: lambda p, q: (p <= q),
+                         13: lambda p, q: (p > q), 14: lambda p, q: (p >= q)}[op]
+                    st.append(np.asarray(f(a, b)).astype(T))
+        _arr(out, n, T)[:] = np.broadcast_to(st[0], (n,))
+        return 0
+
     # ---- reductions
     @staticmethod
     def _map(m, v):
@@ -368,7 +392,7 @@ def install(ag, fake=None):
     import sys
     fake = fake or FakeLib()
     saved = {}
-    for name in ("agb200._lib", "agb200.darray", "agb200.graph", "agb200.comm"):
+    for name in ("agb200._lib", "agb200.darray", "agb200.graph", "agb200.comm", "agb200.vm"):
         mod = sys.modules[name]
         saved[name] = mod.lib
         mod.lib = fake

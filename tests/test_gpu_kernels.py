@@ -271,3 +271,49 @@ def test_extrema_prod_permute_stats(ag, oracle, dtype):
     assert relerr(ag.std(xd, dims=1).to_numpy(), x64.std(axis=1, ddof=1, keepdims=True)) <= 20 * tol
     assert abs(float(ag.norm(xd)) - np.linalg.norm(x64)) <= tol * np.linalg.norm(x64)
     assert ag.gradcheck(lambda z: ag.permutedims(z, (1, 0)), ag.DArray.from_numpy(x64[:, :, 0]))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 5, 4099, 1 << 20])
+def test_fused_expression_evaluator(ag, dtype, n):
+    """ag_ewise_vm: user-defined `@primitive f(x),dy,y (expr)` (src/macros.jl:88-105; sigm of
+    examples/charlm.jl:46-47) as ONE fused pass; value, gradient and second derivative against closed forms."""
+    E = ag.E
+    sigm2 = ag.primitive_expr("sigm2", lambda x: 1 / (1 + E.exp(-x)), lambda dy, y, x: dy * y * (1 - y))
+    mix = ag.primitive_expr("mix", lambda a, b: E.max(a, 0.25) * E.tanh(b) - a ** 2 / (1 + E.abs2(b)),
+                            lambda dy, y, a, b: dy * (E.gt(a, 0.25) * E.tanh(b) - 2 * a / (1 + E.abs2(b))),
+                            lambda dy, y, a, b: dy * (E.max(a, 0.25) * (1 - E.tanh(b) ** 2)
+                                                      + 2 * b * a ** 2 / (1 + E.abs2(b)) ** 2))
+    rng = np.random.default_rng(n)
+    x, b = rng.standard_normal(n).astype(dtype), rng.standard_normal(n).astype(dtype)
+    x64, b64 = x.astype(np.float64), b.astype(np.float64)
+    xd, bd = ag.DArray.from_numpy(x), ag.DArray.from_numpy(b)
+    s = 1 / (1 + np.exp(-x64))
+    k0 = ag.launch_count()
+    y = sigm2(xd)
+    assert ag.launch_count() - k0 == 1
+    assert relerr(y.to_numpy(), s) < TOL[dtype]
+    assert relerr(ag.grad(lambda v: ag.sum_(sigm2(v)))(xd).to_numpy(), s * (1 - s)) < TOL[dtype]
+    g1 = ag.grad(lambda v: ag.sum_(sigm2(v)))
+    assert relerr(ag.grad(lambda v: ag.sum_(g1(v)))(xd).to_numpy(), s * (1 - s) * (1 - 2 * s)) < 4 * TOL[dtype]
+    ref = np.maximum(x64, 0.25) * np.tanh(b64) - x64 ** 2 / (1 + b64 * b64)
+    assert relerr(mix(xd, bd).to_numpy(), ref) < TOL[dtype]
+    ga, gb = ag.grad(lambda u: ag.sum_(mix(u, bd)))(xd), ag.grad(lambda v: ag.sum_(mix(xd, v)))(bd)
+    assert relerr(ga.to_numpy(), (x64 > 0.25) * np.tanh(b64) - 2 * x64 / (1 + b64 * b64)) < TOL[dtype]
+    assert relerr(gb.to_numpy(), np.maximum(x64, 0.25) * (1 - np.tanh(b64) ** 2)
+                  + 2 * b64 * x64 ** 2 / (1 + b64 * b64) ** 2) < TOL[dtype]
+    # scalar operand as an immediate and a broadcasting operand (composite path) agree with the fused path
+    assert relerr(mix(xd, 0.5).to_numpy(), np.maximum(x64, 0.25) * np.tanh(0.5) - x64 ** 2 / 1.25) < TOL[dtype]
+
+
+def test_fused_expression_evaluator_rejects_bad_programs(ag):
+    import ctypes as C
+    lib = ag._lib.lib
+    x = ag.DArray.from_numpy(np.ones(8, np.float32))
+    out = ag.DArray.empty((8,), np.float32)
+    ptrs, modes, imms = (C.c_void_p * 1)(x.ptr), (C.c_int32 * 1)(0), (C.c_double * 1)(0.0)
+    consts = (C.c_double * 1)(0.0)
+    for prog in ([2], [0, 0], [0 | (3 << 8)], [1 | (5 << 8)], [0, 15 + 200]):   # underflow, 2 results, bad input/const/op
+        code = (C.c_int32 * len(prog))(*prog)
+        st = lib.ag_ewise_vm(out.dt, code, len(prog), consts, 1, 1, ptrs, modes, imms, out.ptr, 8)
+        assert st != 0, prog

@@ -239,3 +239,33 @@ def test_reductions_and_permute(hostlib, oracle):
     assert relerr(ag.var(xd, dims=1).to_numpy(), x.var(axis=1, ddof=1, keepdims=True)) < 1e-12
     assert abs(float(ag.norm(xd)) - np.linalg.norm(x)) < 1e-12
     assert ag.gradcheck(lambda z: ag.std(z, dims=0), xd)
+
+
+def test_primitive_expr(hostlib, oracle):
+    """User-defined primitives (src/macros.jl:88-105; sigm of examples/charlm.jl:46-47) compiled to the fused
+    evaluator: value, first and second derivative against the built-in primitive / closed forms."""
+    ag = hostlib
+    E = ag.E
+    sigm2 = ag.primitive_expr("sigm2", lambda x: 1 / (1 + E.exp(-x)), lambda dy, y, x: dy * y * (1 - y))
+    swish = ag.primitive_expr("swish", lambda x: x * E.sigm(x),
+                              lambda dy, y, x: dy * (E.sigm(x) + x * E.sigm(x) * (1 - E.sigm(x))))
+    scaled = ag.primitive_expr("scaled", lambda a, b: a * E.tanh(b), lambda dy, y, a, b: dy * E.tanh(b),
+                               lambda dy, y, a, b: dy * a * (1 - E.tanh(b) ** 2))
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((5, 7))
+    xd = ag.DArray.from_numpy(x)
+    assert relerr(sigm2(xd).to_numpy(), 1 / (1 + np.exp(-x))) < 1e-15
+    assert relerr(ag.grad(lambda v: ag.sum_(sigm2(v)))(xd).to_numpy(), ag.grad(lambda v: ag.sum_(ag.sigm(v)))(xd).to_numpy()) < 1e-14
+    assert ag.gradcheck(swish, xd)
+    assert ag.gradcheck(scaled, xd, ag.DArray.from_numpy(rng.standard_normal((5, 7))))
+    assert ag.gradcheck(scaled, xd, ag.DArray.from_numpy(rng.standard_normal((5, 1))))      # broadcasting operand
+    # second order: the gradient expression records itself under the outer tape
+    g1 = ag.grad(lambda v: ag.sum_(sigm2(v)))
+    g2 = ag.grad(lambda v: ag.sum_(g1(v)))(xd).to_numpy()
+    s = 1 / (1 + np.exp(-x))
+    assert relerr(g2, s * (1 - s) * (1 - 2 * s)) < 1e-13
+    # host scalars never touch the device
+    assert abs(sigm2(0.0) - 0.5) < 1e-15
+    kernels = ag.launch_count()
+    sigm2(xd)
+    assert ag.launch_count() - kernels == 1                # one fused pass
