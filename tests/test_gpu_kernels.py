@@ -159,7 +159,10 @@ GEMM = [(64, 784, 1000, 0, 0), (64, 1000, 784, 0, 1), (64, 10, 1000, 1, 0), (10,
         (1, 13, 506, 0, 0), (1, 506, 13, 0, 1), (130, 70, 33, 0, 0), (130, 70, 33, 1, 1), (5, 1, 7, 0, 0),
         (512, 640, 256, 0, 0), (512, 256, 640, 0, 1), (640, 512, 256, 1, 0), (128, 128, 4096, 0, 1),
         (10, 5000, 64, 0, 1), (64, 4100, 64, 0, 1), (10, 64, 4096, 0, 0), (64, 10, 5000, 1, 0), (33, 17, 777, 0, 0),
-        (64, 784, 4096, 0, 0), (64, 8192, 784, 0, 1), (132, 72, 2000, 1, 1)]
+        (64, 784, 4096, 0, 0), (64, 8192, 784, 0, 1), (132, 72, 2000, 1, 1),
+        # streaming skinny forms: S1a (few rows, K % 4 == 0), S1b (K <= 16, many rows), S2 (huge contraction)
+        (7, 20, 1000, 0, 0), (16, 64, 515, 1, 0), (12, 16, 65536, 0, 0), (40, 3, 777, 0, 0), (33, 16, 600, 0, 0),
+        (64, 10, 65536, 1, 0), (3, 2051, 12, 0, 1), (16, 70001, 64, 0, 1), (10, 65536, 64, 0, 1)]
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
