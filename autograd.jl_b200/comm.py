@@ -57,6 +57,8 @@ class DataParallel:
         dense = [g.full() if isinstance(g, Sparse) else g for g in grads]
         if self.world == 1:
             return dense
+        from . import lazy
+        lazy.flush()        # the bucket is reused in place from step to step
         ref = next(g for g in dense if g is not None)
         sizes = [0 if g is None else g.size for g in dense]
         tot = sum(sizes)
@@ -82,7 +84,9 @@ class DataParallel:
         by `axpy!(alpha, g, w)` for every Param.  One launch when the peer-memory collective is available (the
         update is fused behind it); one multi-tensor axpy launch on a single rank.  Returns the reduced grads."""
         from .core import value
+        from . import lazy
         dense = [g.full() if isinstance(g, Sparse) else g for g in grads]
+        lazy.flush()        # the collective and the update work in place
         live = [(D.materialize(g), value(p)) for g, p in zip(dense, params) if g is not None]
         if not live:
             return dense

@@ -1,0 +1,131 @@
+// ewise_ops.cuh -- the elementwise op tables shared by the single-rule kernels (ewise.cu) and the fused
+// evaluator (fuse.cu): unary f / g = df/dx table (src/math.jl:9-74, src/base.jl:73-74), binary maps and the
+// ternary gradient maps of the broadcasting binary rules (src/base.jl:21-49, src/math.jl:24,48,54-55).
+// One definition of every expression, so a fused program is bit-identical to the chain of single kernels.
+#pragma once
+#include "common.cuh"
+
+namespace agb {
+
+template <typename T>
+struct alignas(16) Pack {
+  static constexpr int N = 16 / sizeof(T);
+  T v[N];
+};
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+// ---- unary op table -----------------------------------------------------------------------------
+template <int OP, typename T>
+struct U;
+
+#define AG_DEF_U(OP, NX, NY, FEXPR, GEXPR)                         \
+  template <typename T>                                            \
+  struct U<OP, T> {                                                \
+    static constexpr bool needs_x = NX, needs_y = NY;              \
+    static __device__ __forceinline__ T f(T x) { return FEXPR; }   \
+    static __device__ __forceinline__ T g(T x, T y) { return GEXPR; } \
+  };
+
+template <typename T>
+__device__ __forceinline__ T sgn(T x) {
+  return x > T(0) ? T(1) : (x < T(0) ? T(-1) : x);  // sign(0)=0, sign(NaN)=NaN like Julia
+}
+template <typename T>
+__device__ __forceinline__ T relu(T x) {
+  return x > T(0) ? x : (x != x ? x : T(0));
+}
+
+//        op            x?     y?     f(x)                          g(x,y)
+AG_DEF_U(AG_U_IDENTITY, false, false, x, T(1))
+AG_DEF_U(AG_U_NEG, false, false, -x, T(-1))
+AG_DEF_U(AG_U_ABS, true, false, fabs(x), sgn(x))
+AG_DEF_U(AG_U_ABS2, true, false, x* x, T(2) * x)
+AG_DEF_U(AG_U_EXP, false, true, exp(x), y)
+AG_DEF_U(AG_U_LOG, true, false, log(x), T(1) / x)
+AG_DEF_U(AG_U_TANH, false, true, tanh(x), T(1) - y * y)
+AG_DEF_U(AG_U_SIGM, false, true, T(1) / (T(1) + exp(-x)), y*(T(1) - y))
+AG_DEF_U(AG_U_SQRT, false, true, sqrt(x), T(1) / (T(2) * y))
+AG_DEF_U(AG_U_SIN, true, false, sin(x), cos(x))
+AG_DEF_U(AG_U_COS, true, false, cos(x), -sin(x))
+AG_DEF_U(AG_U_TAN, false, true, tan(x), T(1) + y * y)
+AG_DEF_U(AG_U_SINH, true, false, sinh(x), cosh(x))
+AG_DEF_U(AG_U_COSH, true, false, cosh(x), sinh(x))
+AG_DEF_U(AG_U_ASIN, true, false, asin(x), T(1) / sqrt(T(1) - x * x))
+AG_DEF_U(AG_U_ACOS, true, false, acos(x), T(-1) / sqrt(T(1) - x * x))
+AG_DEF_U(AG_U_ATAN, true, false, atan(x), T(1) / (T(1) + x * x))
+AG_DEF_U(AG_U_ASINH, true, false, asinh(x), T(1) / sqrt(T(1) + x * x))
+AG_DEF_U(AG_U_ACOSH, true, false, acosh(x), T(1) / sqrt(x * x - T(1)))
+AG_DEF_U(AG_U_ATANH, true, false, atanh(x), T(1) / (T(1) - x * x))
+AG_DEF_U(AG_U_EXP2, false, true, exp2(x), y* T(0.69314718055994530942))
+AG_DEF_U(AG_U_EXP10, false, true, exp10(x), y* T(2.30258509299404568402))
+AG_DEF_U(AG_U_EXPM1, false, true, expm1(x), T(1) + y)
+AG_DEF_U(AG_U_LOG2, true, false, log2(x), T(1) / (T(0.69314718055994530942) * x))
+AG_DEF_U(AG_U_LOG10, true, false, log10(x), T(1) / (T(2.30258509299404568402) * x))
+AG_DEF_U(AG_U_LOG1P, true, false, log1p(x), T(1) / (T(1) + x))
+AG_DEF_U(AG_U_CBRT, false, true, cbrt(x), T(1) / (T(3) * y * y))
+AG_DEF_U(AG_U_SIGN, false, false, sgn(x), T(0))
+AG_DEF_U(AG_U_RELU, true, false, relu(x), (x >= T(0) ? T(1) : T(0)))
+AG_DEF_U(AG_U_ONE, false, false, T(1), T(0))
+
+#define AG_FOR_UNARY(X)                                                                          \
+  X(AG_U_IDENTITY) X(AG_U_NEG) X(AG_U_ABS) X(AG_U_ABS2) X(AG_U_EXP) X(AG_U_LOG) X(AG_U_TANH)     \
+  X(AG_U_SIGM) X(AG_U_SQRT) X(AG_U_SIN) X(AG_U_COS) X(AG_U_TAN) X(AG_U_SINH) X(AG_U_COSH)        \
+  X(AG_U_ASIN) X(AG_U_ACOS) X(AG_U_ATAN) X(AG_U_ASINH) X(AG_U_ACOSH) X(AG_U_ATANH) X(AG_U_EXP2)  \
+  X(AG_U_EXP10) X(AG_U_EXPM1) X(AG_U_LOG2) X(AG_U_LOG10) X(AG_U_LOG1P) X(AG_U_CBRT) X(AG_U_SIGN) \
+  X(AG_U_RELU) X(AG_U_ONE)
+
+template <typename T>
+__device__ __forceinline__ T jmax(T a, T b) {  // Julia max: NaN-propagating
+  return (a != a || b != b) ? (a + b) : (a > b ? a : (b > a ? b : (signbit(a) ? b : a)));
+}
+template <typename T>
+__device__ __forceinline__ T jmin(T a, T b) {
+  return (a != a || b != b) ? (a + b) : (a < b ? a : (b < a ? b : (signbit(a) ? a : b)));
+}
+
+#define AG_DEF_F(NAME, EXPR)                                          \
+  template <typename T>                                               \
+  struct NAME {                                                       \
+    static __device__ __forceinline__ T apply(const T* in) {          \
+      const T a = in[0], b = in[1];                                   \
+      (void)a; (void)b;                                               \
+      return EXPR;                                                    \
+    }                                                                 \
+  };
+AG_DEF_F(FAdd, a + b)
+AG_DEF_F(FSub, a - b)
+AG_DEF_F(FMul, a* b)
+AG_DEF_F(FDiv, a / b)
+AG_DEF_F(FMax, jmax(a, b))
+AG_DEF_F(FMin, jmin(a, b))
+AG_DEF_F(FPow, pow(a, b))
+AG_DEF_F(FEq, (a == b ? T(1) : T(0)))
+AG_DEF_F(FLt, (a < b ? T(1) : T(0)))
+AG_DEF_F(FLe, (a <= b ? T(1) : T(0)))
+AG_DEF_F(FGt, (a > b ? T(1) : T(0)))
+AG_DEF_F(FGe, (a >= b ? T(1) : T(0)))
+AG_DEF_F(FAtan2, atan2(a, b))
+AG_DEF_F(FHypot, hypot(a, b))
+
+// ternary gradient maps: in[0] = dy, in[1] = p, in[2] = q
+#define AG_DEF_F3(NAME, EXPR)                                         \
+  template <typename T>                                               \
+  struct NAME {                                                       \
+    static __device__ __forceinline__ T apply(const T* in) {          \
+      const T dy = in[0], p = in[1], q = in[2];                       \
+      return EXPR;                                                    \
+    }                                                                 \
+  };
+AG_DEF_F3(GDiv2, -dy* p / (q * q))               // ./ arg2: -dy.*x1./abs2.(x2)   base.jl:33  (p=x1,q=x2)
+AG_DEF_F3(GEqMask, dy*(p == q ? T(1) : T(0)))    // max/min: dy.*(y.==xi)         math.jl:54-55 (p=y,q=xi)
+AG_DEF_F3(GPow1, dy* q* pow(p, q - T(1)))        // .^ arg1: dy.*x2.*x1.^(x2-1)   base.jl:49  (p=x1,q=x2)
+AG_DEF_F3(GPow2, dy* p* log(q))                  // .^ arg2: dy.*y.*log.(x1)      base.jl:45  (p=y,q=x1)
+AG_DEF_F3(GAtan1, dy* q / (p * p + q * q))       // atan arg1                     math.jl:24  (p=x1,q=x2)
+AG_DEF_F3(GAtan2, dy*(-p) / (p * p + q * q))     // atan arg2
+AG_DEF_F3(GHypot, dy* p / q)                     // hypot: dy.*(xi./y)            math.jl:48  (p=xi,q=y)
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace agb

@@ -38,6 +38,13 @@ def _require_init():
 
 
 def sync():
+    _lazy.flush()
+    check(lib.ag_sync())
+
+
+def _sync_stream():
+    """Wait for the stream only (a pageable host source is about to be released); pending deferred operations
+    cannot depend on a buffer that is being created, so they stay pending."""
     check(lib.ag_sync())
 
 
@@ -114,11 +121,12 @@ class DArray:
         if a.size:
             flat = np.ascontiguousarray(a.reshape(-1, order="F"))
             check(lib.ag_copy_h2d(C.c_void_p(out.ptr), flat.ctypes.data_as(C.c_void_p), flat.nbytes))
-            sync()   # `flat` is pageable and about to be released
+            _sync_stream()   # `flat` is pageable and about to be released
         return out
 
     def copy_from_host(self, host_ptr, nbytes):
         """Async h2d from a pinned staging buffer (ag_host_alloc)."""
+        _lazy.flush()               # pending operations must read the old contents first
         check(lib.ag_copy_h2d(C.c_void_p(self.ptr), C.c_void_p(host_ptr), int(nbytes)))
 
     def to_numpy(self):
@@ -201,6 +209,13 @@ def zeros(shape, dtype):
 
 
 def full_like_shape(shape, dtype, v):
+    """fill(v, shape): read-only by convention (results that are updated in place start from `zeros`)."""
+    if _lazy.enabled[0] and np.dtype(dtype) in _DT:
+        return _lazy.fill(shape, dtype, v)
+    return _full_like_shape_eager(shape, dtype, v)
+
+
+def _full_like_shape_eager(shape, dtype, v):
     out = DArray.empty(shape, dtype)
     if out.size:
         check(lib.ag_fill(vptr(out), out.size, out.dt, float(v)))
@@ -228,6 +243,12 @@ def copy(x):
 # ---- elementwise ---------------------------------------------------------------------------------
 
 def unary_fwd(op, x):
+    if _lazy.enabled[0]:
+        return _lazy.unary_fwd(op, x)
+    return _unary_fwd_eager(op, x)
+
+
+def _unary_fwd_eager(op, x):
     x = materialize(x)
     y = DArray.empty(x.shape, x.dtype)
     check(lib.ag_unary_fwd(U[op], x.dt, vptr(x), vptr(y), x.size))
@@ -236,6 +257,27 @@ def unary_fwd(op, x):
 
 def unary_bwd(op, dy, x, y, shape=None, dtype=None):
     """dx = dy .* g(x, y).  dy: DArray of the full shape, 0-dim DArray, or host Number."""
+    if not _lazy.enabled[0]:
+        return _unary_bwd_eager(op, dy, x, y, shape, dtype)
+    ref = x if x is not None else y
+    if ref is None:
+        ref = dy
+    shape = tuple(ref.shape if shape is None else shape)
+    dtype = ref.dtype if dtype is None else dtype
+    n = _prod(shape)
+
+    def fit(v, what):
+        if v is None or isnum(v) or v.shape == shape:
+            return v
+        if v.size != n:
+            raise L.DimensionMismatch("unary_bwd: %s %s vs %s" % (what, v.shape, shape))
+        return materialize(v).reshape(shape)
+    if not isnum(dy) and not (dy.size == 1 and n != 1):
+        dy = fit(dy, "dy")
+    return _lazy.unary_bwd(op, dy, fit(x, "x"), fit(y, "y"), shape, dtype)
+
+
+def _unary_bwd_eager(op, dy, x, y, shape=None, dtype=None):
     ref = x if x is not None else y
     if ref is None:
         ref = dy
@@ -319,6 +361,15 @@ def _common_dtype(*xs):
 
 def binary_fwd(op, a, b):
     """op.(a, b) with Julia broadcasting; a, b: DArray or host Number (at least one DArray)."""
+    if _lazy.enabled[0]:
+        dtype = _common_dtype(a, b)
+        out_shape = bcast_shape(shape_of(a), shape_of(b))
+        if len(out_shape) <= 4 and _prod(out_shape):
+            return _lazy.binary_fwd(op, a, b, out_shape, dtype)
+    return _binary_fwd_eager(op, a, b)
+
+
+def _binary_fwd_eager(op, a, b):
     a = materialize(a) if isinstance(a, DArray) else a
     b = materialize(b) if isinstance(b, DArray) else b
     dtype = _common_dtype(a, b)
@@ -342,6 +393,20 @@ def binary_fwd(op, a, b):
 
 def binary_bwd(op, argno, dy, x1, x2, y):
     """dy .* d(op)/d(x_argno), full broadcast shape (before unbroadcast)."""
+    if _lazy.enabled[0]:
+        vs = [v for v in (dy, x1, x2, y) if v is not None]
+        dtype = _common_dtype(*vs)
+        out_shape = bcast_shape(*[shape_of(v) for v in vs])
+        if len(out_shape) <= 4 and _prod(out_shape):
+            form = _lazy._bb_form(op, argno)
+            named = {"dy": dy, "x1": x1, "x2": x2, "y": y}
+            if form[0] != "binc" and any(named[k] is None for k in form[2:]):
+                raise L.DimensionMismatch("binary_bwd: %s needs %s" % (op, "/".join(form[2:])))
+            return _lazy.binary_bwd(op, argno, dy, x1, x2, y, out_shape, dtype)
+    return _binary_bwd_eager(op, argno, dy, x1, x2, y)
+
+
+def _binary_bwd_eager(op, argno, dy, x1, x2, y):
     arrs = [materialize(v) if isinstance(v, DArray) else v for v in (dy, x1, x2, y)]
     dy, x1, x2, y = arrs
     dtype = _common_dtype(*[v for v in arrs if v is not None])
@@ -452,12 +517,39 @@ def permutedims(x, perm):
     return out
 
 
+def bcast_to(a, shape):
+    """Broadcast-copy `a` to `shape` (dy .* one.(x) with a keep-dims dy, src/base.jl:245)."""
+    shape = tuple(int(e) for e in shape)
+    if bcast_shape(a.shape, shape) != shape:
+        raise L.DimensionMismatch("cannot broadcast %s to %s" % (a.shape, shape))
+    if _lazy.enabled[0] and len(shape) <= 4 and _prod(shape):
+        return _lazy.bcast_to(a, shape)
+    return _bcast_to_eager(a, shape)
+
+
+def _bcast_to_eager(a, shape):
+    # through the binary map: a .* 1 evaluated on the target shape
+    a = materialize(a)
+    out = DArray.empty(shape, a.dtype)
+    if out.size == 0:
+        return out
+    st_a = _strides_for(a.shape, shape)
+    shp, sts = collapse(list(shape), [st_a, _strides_for(shape, shape)])
+    if len(shp) > 4:
+        raise L.UnsupportedOnDevice("broadcast needs %d collapsed dims (max 4)" % len(shp))
+    check(lib.ag_binary_fwd(B["mul"], a.dt, vptr(a), 0.0, _i64arr(sts[0]), None, 1.0, _i64arr([0] * len(shp)),
+                            vptr(out), len(shp), _i64arr(shp)))
+    return out
+
+
 def add(a, b):
     if a.shape != b.shape:
         raise L.DimensionMismatch("addto!: %s vs %s" % (a.shape, b.shape))
-    a, b = materialize(a), materialize(b)
     if a.dtype != b.dtype:
         raise L.UnsupportedOnDevice("addto!: eltypes %s, %s" % (a.dtype, b.dtype))
+    if _lazy.enabled[0] and a.size:
+        return _lazy.binary_fwd("add", a, b, a.shape, a.dtype)
+    a, b = materialize(a), materialize(b)
     out = DArray.empty(a.shape, a.dtype)
     check(lib.ag_add(a.dt, vptr(a), vptr(b), vptr(out), a.size))
     return out
@@ -470,11 +562,13 @@ def axpy_(alpha, x, y):
         raise L.DimensionMismatch("axpy!: %s vs %s" % (x.shape, y.shape))
     if y.tr:
         raise L.UnsupportedOnDevice("axpy! into a lazy adjoint")
+    _lazy.flush()
     check(lib.ag_axpy(y.dt, float(alpha), vptr(x), vptr(y), y.size))
     return y
 
 
 def scale_(alpha, x):
+    _lazy.flush()
     check(lib.ag_scale(x.dt, float(alpha), vptr(x), x.size))
     return x
 
@@ -579,7 +673,7 @@ def index_to_device(idx):
     buf = _Buffer(max(idx.nbytes, 8))
     if idx.size:
         check(lib.ag_copy_h2d(C.c_void_p(buf.ptr), idx.ctypes.data_as(C.c_void_p), idx.nbytes))
-        sync()
+        _sync_stream()
     return buf
 
 
@@ -624,6 +718,7 @@ def scatter_add_dev_(dest, idx_buf, n, lo, hi, vals, block=1):
         raise L.DimensionMismatch("scatter-add: %d values for %d destinations" % (vals.size, n * block))
     if lo < 0 or (hi + 1) * block > dest.size:
         raise IndexError("BoundsError")
+    _lazy.flush()
     check(lib.ag_scatter_add(dest.dt, vptr(dest), dest.size, C.c_void_p(idx_buf.ptr), vptr(vals), n, block))
     return dest
 
@@ -640,6 +735,7 @@ def scatter_add_(dest, flat_idx, vals, block=1):
     if flat_idx.min() < 0 or (flat_idx.max() + 1) * block > dest.size:
         raise IndexError("BoundsError")
     ib = index_to_device(flat_idx)
+    _lazy.flush()
     check(lib.ag_scatter_add(dest.dt, vptr(dest), dest.size, C.c_void_p(ib.ptr), vptr(vals), n, block))
     return dest
 
@@ -663,3 +759,6 @@ HOST_BINARY = dict(
     max=max, min=min, pow=lambda a, b: a ** b, eq=lambda a, b: float(a == b), lt=lambda a, b: float(a < b),
     le=lambda a, b: float(a <= b), gt=lambda a, b: float(a > b), ge=lambda a, b: float(a >= b),
     atan2=math.atan2, hypot=math.hypot)
+
+
+from . import lazy as _lazy  # noqa: E402  (deferred elementwise evaluation; needs the definitions above)

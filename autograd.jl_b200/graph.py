@@ -9,6 +9,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import lib, check
+from . import lazy as _lazy
 
 
 class StepGraph:
@@ -19,11 +20,14 @@ class StepGraph:
         self.keep = []      # objects whose device buffers the graph reads/writes
 
     def __enter__(self):
+        _lazy.flush()       # nothing enqueued before the capture may run inside it
         check(lib.ag_graph_begin())
         return self
 
     def __exit__(self, et, ev, tb):
         h = C.c_uint64()
+        if et is None:
+            _lazy.flush()   # everything the step defined belongs to the captured step
         st = lib.ag_graph_end(C.byref(h))
         if et is None:
             check(st)
@@ -31,6 +35,7 @@ class StepGraph:
         return False
 
     def launch(self):
+        _lazy.flush()
         check(lib.ag_graph_launch(C.c_uint64(self.handle)))
 
     def destroy(self):
@@ -47,6 +52,7 @@ class Event:
         self.h = h.value
 
     def record(self):
+        _lazy.flush()       # the event marks program order
         check(lib.ag_event_record(C.c_uint64(self.h)))
         return self
 

@@ -1,0 +1,456 @@
+"""Deferred elementwise evaluation: horizontal fusion of the tape's elementwise chains.
+
+The reference evaluates every dotted call on a tracked value as its own Base broadcast pass
+(src/core.jl:68-70 materialises each `Broadcasted`), every gradient rule of src/math.jl:9-74 and
+src/base.jl:20-49,73-74 as another pass, and the dense `addto!` (src/addto.jl:23) as one more.  The tape
+semantics do not need that: a value only has to exist when a non-elementwise consumer (matmul, a reduction,
+a gather, a host read) or an in-place update asks for it.
+
+Here the raw elementwise operations of darray.py return a `LazyArray`: a DArray whose storage does not exist
+yet and which remembers the operation that defines it.  Touching `.ptr` / `.buf` (which every kernel wrapper
+does) forces it: the whole pending expression DAG below it is compiled to the bytecode of ag_ewise_fused and
+evaluated by ONE kernel.  Leaves are read once; the root and every intermediate that something else still
+refers to (a Result on the tape, a Node's outgrad, a user variable -- found by reference count) is written
+once; temporaries of the gradient expressions are never stored.  Every instruction of the fused kernel
+evaluates the same expression as the single-rule kernel, so results are bit-identical to unfused execution
+(AGB_FUSION=0 or `set_fusion(False)` runs the unfused path).
+
+Safety rules: (1) shapes and eltypes are checked when the node is created, so DimensionMismatch surfaces at
+the call like in the reference; (2) anything that mutates device memory in place (axpy!, lmul!, scatter-add,
+host copies into an existing array, collectives, graph capture/launch, sync) first evaluates everything
+pending (`flush`), because a pending node reads its leaves later than the program order says; (3) a DAG whose
+operand layouts the fused kernel cannot express is evaluated node by node with the ordinary kernels.
+"""
+import ctypes as C
+import itertools
+import os
+import sys
+import weakref
+
+import numpy as np
+
+from . import darray as D
+from ._lib import check, DimensionMismatch, UnsupportedOnDevice
+
+_RAW_PTR = D.DArray.__dict__["ptr"]
+_RAW_BUF = D.DArray.__dict__["buf"]
+
+MAX_NODES = 24          # pending nodes per DAG before the largest argument is evaluated early
+MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 8, 4, 8
+LD_IN, LD_CONST, LD_TMP, ST_TMP, UNARY, BIN, BIN_IN, BIN_CONST, UGRAD, TERN, STORE = range(11)
+M_FULL, M_DEVSCALAR, M_IMM, M_COLVEC, M_ROWVEC = range(5)
+
+enabled = [os.environ.get("AGB_FUSION", "1") != "0"]
+stats = {"fused_launches": 0, "fused_nodes": 0, "fallback_nodes": 0, "splits": 0}
+_counter = itertools.count()
+_pending = weakref.WeakValueDictionary()
+
+
+def set_fusion(on):
+    """Enable / disable deferred evaluation; returns the previous setting.  Disabling evaluates what is pending."""
+    prev = enabled[0]
+    if not on:
+        flush()
+    enabled[0] = bool(on)
+    return prev
+
+
+class LazyArray(D.DArray):
+    """A DArray defined by a pending elementwise operation.  kind is None once the storage exists."""
+    __slots__ = ("kind", "op", "args", "nnodes", "seq")
+
+    def __init__(self, shape, dtype, kind, op, args, nnodes):
+        _RAW_BUF.__set__(self, None)
+        _RAW_PTR.__set__(self, 0)
+        self.shape, self.dtype, self.tr = tuple(int(s) for s in shape), np.dtype(dtype), False
+        self.kind, self.op, self.args, self.nnodes = kind, op, args, nnodes
+        self.seq = next(_counter)
+        _pending[self.seq] = self
+
+    @property
+    def ptr(self):
+        if self.kind is not None:
+            force(self)
+        return _RAW_PTR.__get__(self, D.DArray)
+
+    @property
+    def buf(self):
+        if self.kind is not None:
+            force(self)
+        return _RAW_BUF.__get__(self, D.DArray)
+
+    def _set_storage(self, arr):
+        _RAW_BUF.__set__(self, _RAW_BUF.__get__(arr, D.DArray))
+        _RAW_PTR.__set__(self, _RAW_PTR.__get__(arr, D.DArray))
+        self.kind = self.op = self.args = None
+        self.nnodes = 0
+        _pending.pop(self.seq, None)
+
+    def __repr__(self):
+        if self.kind is not None:
+            return "LazyArray{%s}%s<%s %s>" % (self.dtype.name, self.shape, self.kind, self.op)
+        return D.DArray.__repr__(self)
+
+
+def is_pending(x):
+    return isinstance(x, LazyArray) and x.kind is not None
+
+
+def pending_count():
+    return sum(1 for v in list(_pending.values()) if v.kind is not None)
+
+
+# ---- node construction ----------------------------------------------------------------------------------
+
+def _norm(v):
+    """Operand of a node: host Number -> float, lazy adjoint -> dense, everything else as is."""
+    if v is None:
+        return None
+    if D.isnum(v):
+        return float(v)
+    if isinstance(v, D.DArray):
+        if v.tr:
+            return D.materialize(v)
+        return v
+    raise UnsupportedOnDevice("elementwise operand of type %s" % type(v).__name__)
+
+
+def _make(kind, op, args, shape, dtype):
+    shape = tuple(int(s) for s in shape)
+    args = tuple(_norm(a) for a in args)
+    dts = {a.dtype for a in args if isinstance(a, D.DArray)}
+    dts.add(np.dtype(dtype))
+    if len(dts) != 1:
+        raise UnsupportedOnDevice("mixed or missing device eltypes %s" % (dts,))
+    nn = 1
+    for a in args:
+        if is_pending(a):
+            if a.shape != shape:
+                force(a)                      # a broadcast operand must be concrete (it becomes a leaf)
+            else:
+                nn += a.nnodes
+    while nn > MAX_NODES:
+        big = max((a for a in args if is_pending(a)), key=lambda a: a.nnodes)
+        nn -= big.nnodes
+        force(big)
+    return LazyArray(shape, dtype, kind, op, args, nn)
+
+
+def unary_fwd(op, x):
+    return _make("u", op, (x,), x.shape, x.dtype)
+
+
+def unary_bwd(op, dy, x, y, shape, dtype):
+    """dx = dy .* g(x, y); dy a Number, a size-1 device array or an array of `shape`."""
+    return _make("ug", op, (dy, x, y), shape, dtype)
+
+
+def binary_fwd(op, a, b, out_shape, dtype):
+    return _make("b", op, (a, b), out_shape, dtype)
+
+
+def binary_bwd(op, argno, dy, x1, x2, y, out_shape, dtype):
+    return _make("bb", (op, argno), (dy, x1, x2, y), out_shape, dtype)
+
+
+def fill(shape, dtype, v):
+    return _make("fill", None, (float(v),), shape, dtype)
+
+
+def bcast_to(a, shape):
+    return _make("id", None, (a,), shape, a.dtype)
+
+
+# ---- evaluation -------------------------------------------------------------------------------------------
+
+class _TooBig(Exception):
+    """The DAG needs more inputs / outputs / instructions / slots than one launch has: evaluate arguments first."""
+
+
+class _NotFusable(Exception):
+    """Some operand layout is not a full array, row vector, column vector or scalar of the iteration space."""
+
+
+def _topo(root):
+    order, seen = [], set()
+
+    def visit(n):
+        seen.add(id(n))
+        for a in n.args:
+            if is_pending(a) and id(a) not in seen:
+                visit(a)
+        order.append(n)
+    visit(root)
+    return order
+
+
+def flush():
+    """Evaluate everything pending (latest first, so that whole chains go out as one kernel)."""
+    if not _pending:
+        return
+    for k in sorted(_pending.keys(), reverse=True):
+        n = _pending.get(k)
+        if n is not None and n.kind is not None:
+            force(n)
+        n = None
+
+
+def force(root):
+    if root.kind is None:
+        return
+    order = _topo(root)
+    try:
+        _run_fused(order, root)
+        return
+    except _TooBig:
+        stats["splits"] += 1
+        sub = [a for a in root.args if is_pending(a)]
+        order = None
+        if sub:
+            for a in sub:
+                force(a)
+            force(root)
+            return
+        order = [root]
+    except _NotFusable:
+        pass
+    _run_eager(order)
+
+
+def _run_eager(order):
+    """Node-by-node evaluation with the ordinary kernels (general <= 4-d strided broadcasting)."""
+    for n in order:
+        if n.kind is None:
+            continue
+        k, a = n.kind, n.args
+        if k == "u":
+            r = D._unary_fwd_eager(n.op, a[0])
+        elif k == "ug":
+            r = D._unary_bwd_eager(n.op, a[0], a[1], a[2], shape=n.shape, dtype=n.dtype)
+        elif k == "b":
+            r = D._binary_fwd_eager(n.op, a[0], a[1])
+        elif k == "bb":
+            r = D._binary_bwd_eager(n.op[0], n.op[1], a[0], a[1], a[2], a[3])
+        elif k == "fill":
+            r = D._full_like_shape_eager(n.shape, n.dtype, a[0])
+        else:
+            r = D._bcast_to_eager(a[0], n.shape)
+        stats["fallback_nodes"] += 1
+        n._set_storage(r)
+
+
+# (op, argno) of a broadcasting binary rule -> ("bin", binary op, other operand) or ("tern", map id, p, q)
+# with operands named dy/x1/x2/y: exactly the table of ag_binary_bwd (csrc/ewise.cu).
+def _bb_form(op, argno):
+    xi = "x1" if argno == 1 else "x2"
+    if op == "add":
+        return ("binc", "mul", 1.0)
+    if op == "sub":
+        return ("binc", "mul", 1.0 if argno == 1 else -1.0)
+    if op == "mul":
+        return ("bin", "mul", "x2" if argno == 1 else "x1")
+    if op == "div":
+        return ("bin", "div", "x2") if argno == 1 else ("tern", 0, "x1", "x2")
+    if op in ("max", "min"):
+        return ("tern", 1, "y", xi)
+    if op == "pow":
+        return ("tern", 2, "x1", "x2") if argno == 1 else ("tern", 3, "y", "x1")
+    if op == "atan2":
+        return ("tern", 4 if argno == 1 else 5, "x1", "x2")
+    if op == "hypot":
+        return ("tern", 6, xi, "y")
+    raise UnsupportedOnDevice("binary op %s has no gradient (zerograd)" % op)
+
+
+def _run_fused(order, root):
+    S = root.shape
+    n_elem = D._prod(S)
+    dtype = root.dtype
+    # ---- which nodes must exist afterwards / are used more than once
+    uses = {}
+    for n in order:
+        for a in n.args:
+            if is_pending(a):
+                uses[id(a)] = uses.get(id(a), 0) + 1
+    anchors, outputs = [], []
+    for idx in range(len(order)):
+        n = order[idx]
+        u = uses.get(id(n), 0)
+        # references: `order`, the local `n`, getrefcount's argument, one per use inside the DAG; more = external
+        ext = n is root or (sys.getrefcount(n) - 3 - u) > 0
+        if ext or u > 1:
+            anchors.append(n)
+            if ext:
+                outputs.append(n)
+    n = None
+    if len(outputs) > MAXOUT:
+        raise _TooBig()
+    if n_elem == 0:
+        for o in outputs:
+            o._set_storage(D.DArray.empty(S, dtype))
+        return
+
+    code, consts, leaves, leaf_idx = [], [], [], {}
+    state = {"depth": 0, "maxdepth": 0}
+    tmp_slot, remaining, free_slots, used_slots = {}, {}, list(range(SLOTS - 1, -1, -1)), set()
+
+    def emit(op, a=0, b=0):
+        code.append(op | (a << 8) | (b << 16))
+
+    def const_idx(v):
+        for i, c in enumerate(consts):
+            if c == v and np.signbit(c) == np.signbit(v):
+                return i
+        if len(consts) >= MAXCONST:
+            raise _TooBig()
+        consts.append(v)
+        return len(consts) - 1
+
+    def leaf(x):
+        i = leaf_idx.get(id(x))
+        if i is None:
+            if len(leaves) >= MAXIN:
+                raise _TooBig()
+            i = leaf_idx[id(x)] = len(leaves)
+            leaves.append(x)
+        return i
+
+    def pushed(push):
+        if push:
+            state["depth"] += 1
+            state["maxdepth"] = max(state["maxdepth"], state["depth"])
+
+    def simple(x):
+        return isinstance(x, float) or (isinstance(x, D.DArray) and not is_pending(x))
+
+    def gen(x, push):
+        if x is None:
+            x = 0.0
+        if isinstance(x, float):
+            emit(LD_CONST, const_idx(x), 1 if push else 0)
+            pushed(push)
+        elif is_pending(x):
+            if id(x) in tmp_slot:
+                emit(LD_TMP, tmp_slot[id(x)], 1 if push else 0)
+                pushed(push)
+                remaining[id(x)] -= 1
+                if remaining[id(x)] == 0:
+                    free_slots.append(tmp_slot[id(x)])
+            else:
+                gen_node(x, push)
+        else:
+            emit(LD_IN, leaf(x), 1 if push else 0)
+            pushed(push)
+
+    def gen_bin(bop, a, b, push):
+        bid = D.B[bop]
+        if simple(b):
+            gen(a, push)
+            if isinstance(b, float):
+                emit(BIN_CONST, bid, const_idx(b))
+            else:
+                emit(BIN_IN, bid, leaf(b))
+        elif simple(a):
+            gen(b, push)
+            if isinstance(a, float):
+                emit(BIN_CONST, bid, const_idx(a) | 0x80)
+            else:
+                emit(BIN_IN, bid, leaf(a) | 0x80)
+        else:
+            gen(a, push)
+            gen(b, True)
+            emit(BIN, bid)
+            state["depth"] -= 1
+
+    def gen_node(n, push):
+        k, a = n.kind, n.args
+        if k == "u":
+            gen(a[0], push)
+            emit(UNARY, D.U[n.op])
+        elif k == "b":
+            gen_bin(n.op, a[0], a[1], push)
+        elif k == "ug":
+            gen(a[0], push)
+            gen(a[1], True)
+            gen(a[2], True)
+            emit(UGRAD, D.U[n.op])
+            state["depth"] -= 2
+        elif k == "bb":
+            named = {"dy": a[0], "x1": a[1], "x2": a[2], "y": a[3]}
+            form = _bb_form(*n.op)
+            if form[0] == "binc":
+                gen_bin(form[1], named["dy"], form[2], push)
+            elif form[0] == "bin":
+                gen_bin(form[1], named["dy"], named[form[2]], push)
+            else:
+                gen(named["dy"], push)
+                gen(named[form[2]], True)
+                gen(named[form[3]], True)
+                emit(TERN, form[1])
+                state["depth"] -= 2
+        elif k == "fill":
+            gen(a[0], push)
+        else:                                   # "id": broadcast of the operand to the iteration space
+            gen(a[0], push)
+
+    for n in anchors:
+        state["depth"] = 0
+        gen_node(n, False)
+        if n in outputs:
+            emit(STORE, outputs.index(n))
+        u = uses.get(id(n), 0)
+        if u > 0:
+            if not free_slots:
+                raise _TooBig()
+            s = max(free_slots)
+            free_slots.remove(s)
+            tmp_slot[id(n)], remaining[id(n)] = s, u
+            used_slots.add(s)
+            emit(ST_TMP, s)
+    n = None
+    lowest_tmp = min(used_slots) if used_slots else SLOTS
+    if len(code) > MAXCODE or state["maxdepth"] > lowest_tmp:
+        raise _TooBig()
+
+    # ---- operand layouts: full / scalar / row vector / column vector of a collapsed rows x cols space
+    modes, imms, bc = [], [], []
+    for x in leaves:
+        if x.shape == S:
+            modes.append(M_FULL)
+        elif x.size == 1:
+            modes.append(M_DEVSCALAR)
+        else:
+            modes.append(None)
+            bc.append(x)
+    rows, cols = n_elem, 1
+    if bc:
+        sl = [D._strides_for(x.shape, S) for x in bc] + [D._strides_for(S, S)]
+        shp, sts = D.collapse(list(S), sl)
+        if len(shp) != 2:
+            raise _NotFusable()
+        rows, cols = shp
+        it = iter(sts)
+        for i, m in enumerate(modes):
+            if m is None:
+                st = next(it)
+                if st == [1, 0]:
+                    modes[i] = M_COLVEC
+                elif st == [0, 1]:
+                    modes[i] = M_ROWVEC
+                else:
+                    raise _NotFusable()
+
+    outs = [D.DArray.empty(S, dtype) for _ in outputs]
+    nin, nout = len(leaves), len(outs)
+    c_code = (C.c_int32 * len(code))(*code)
+    c_consts = (C.c_double * max(len(consts), 1))(*(consts or [0.0]))
+    c_in = (C.c_void_p * max(nin, 1))(*[x.ptr for x in leaves])
+    c_mode = (C.c_int32 * max(nin, 1))(*modes)
+    c_imm = (C.c_double * max(nin, 1))()
+    c_out = (C.c_void_p * nout)(*[o.ptr for o in outs])
+    check(D.lib.ag_ewise_fused(D._DT[dtype], c_code, len(code), c_consts, len(consts), nin, c_in, c_mode, c_imm,
+                               nout, c_out, rows, cols))
+    stats["fused_launches"] += 1
+    stats["fused_nodes"] += len(order)
+    for o, arr in zip(outputs, outs):
+        o._set_storage(arr)

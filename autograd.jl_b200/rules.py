@@ -405,17 +405,7 @@ def _expand_to(dy, x):
 
 
 def _bcast_to(a, shape):
-    # broadcast-copy through the binary map: a .* 1 evaluated on the target shape
-    out = D.DArray.empty(shape, a.dtype)
-    if out.size == 0:
-        return out
-    st_a = D._strides_for(a.shape, shape)
-    shp, sts = D.collapse(list(shape), [st_a, D._strides_for(shape, shape)])
-    if len(shp) > 4:
-        raise UnsupportedOnDevice("broadcast needs %d collapsed dims (max 4)" % len(shp))
-    D.check(D.lib.ag_binary_fwd(D.B["mul"], a.dt, D.vptr(a), 0.0, D._i64arr(sts[0]), None, 1.0,
-                                D._i64arr([0] * len(shp)), D.vptr(out), len(shp), D._i64arr(shp)))
-    return out
+    return D.bcast_to(a, shape)
 
 
 def _sum_back(dy, y, x, dims=None):

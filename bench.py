@@ -266,8 +266,14 @@ def main():
     clk = clocks.stop(t_wall0, t_wall1)
 
     # ---- forward / backward split (two graphs, events between them), N-independent
+    #      (recorded on a tape, so the forward writes every value the backward sweep will read)
+    from agb200 import core as _core
     with ag.StepGraph() as g_f:
-        loss_t = Wl.mnist_loss(ag, [p.value for p in params], xd, yd, global_batch=gB)
+        _core._tapes.append(_core.Tape())
+        try:
+            loss_t = Wl.mnist_loss(ag, params, xd, yd, global_batch=gB)
+        finally:
+            _core._tapes.pop()
     ef0, ef1 = ag.Event(), ag.Event()
     ef0.record()
     for _ in range(K):
@@ -364,6 +370,9 @@ def main():
                        "global_batch": gB, "parallelism": "dp%d" % world, "replay": replay,
                        "allreduce": ("one-shot peer-memory kernel over NVLink, flag-in-data, fused axpy! (ag_p2p_allreduce_multi)" if dp.p2p_cap else
                                      "NCCL") if world > 1 else None,
+                       "fusion": ("elementwise chains of the tape deferred and evaluated by one ag_ewise_fused launch each"
+                                  if sys.modules["agb200.lazy"].enabled[0] else "off (AGB_FUSION=0)"),
+                       "launches_per_step": launches / max(K, 1),
                        "l2": "inputs (x = %.0f MB per rank) larger than the 126 MB L2; no flush" % (x_np.nbytes / 1e6)},
             "forward_ms": fwd_ms, "backward_update_ms": bwd_ms,
             "backward_hbm_gbs": bb / (bwd_ms * 1e-3) / 1e9,
