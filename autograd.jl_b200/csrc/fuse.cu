@@ -19,6 +19,9 @@
 #include "common.cuh"
 #include "ewise_ops.cuh"
 
+#include <stdlib.h>
+#include <utility>
+
 namespace agb {
 
 constexpr int FZ_MAXCODE = 96, FZ_MAXCONST = 16, FZ_MAXIN = 8, FZ_MAXOUT = 4, FZ_SLOTS = 8;
@@ -53,71 +56,92 @@ struct FzArgs {
 
 #define FZ_CASE8(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ FzArgs a) {
+template <typename T, int N>
+__device__ __forceinline__ void fz_coords(const FzArgs& a, int64_t i, int64_t* c0, int64_t* c1) {
+  int64_t q, r;
+  if (a.n < ((int64_t)1 << 31)) {
+    const uint32_t qq = (uint32_t)i / (uint32_t)a.rows;
+    q = qq;
+    r = (uint32_t)i - qq * (uint32_t)a.rows;
+  } else {
+    q = i / a.rows;
+    r = i - q * a.rows;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    c0[j] = r;
+    c1[j] = q;
+    if (++r == a.rows) { r = 0; ++q; }
+  }
+}
+
+template <typename T, int N, bool VEC>
+__device__ __forceinline__ void fz_load(const FzArgs& a, int k, int64_t i, const int64_t* c0, const int64_t* c1,
+                                        T* dst) {
+  const T* __restrict__ p = (const T*)a.in[k];
+  const int m = a.mode[k];
+  if (m == FZ_M_FULL) {
+    if (VEC) {
+      const Pack<T> t = *reinterpret_cast<const Pack<T>*>(p + i);
+#pragma unroll
+      for (int j = 0; j < N; ++j) dst[j] = t.v[j];
+    } else {
+      dst[0] = p[i];
+    }
+  } else if (m == FZ_M_COLVEC) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = p[c0[j]];
+  } else if (m == FZ_M_ROWVEC) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = p[c1[j]];
+  } else {
+    const T sc = m == FZ_M_DEVSCALAR ? p[0] : (T)a.imm[k];
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = sc;
+  }
+}
+
+template <typename T, int N, bool VEC>
+__device__ __forceinline__ void fz_store(const FzArgs& a, int o, int64_t i, const T* v) {
+  T* __restrict__ p = (T*)a.out[o];
+  if (VEC) {
+    Pack<T> t;
+#pragma unroll
+    for (int j = 0; j < N; ++j) t.v[j] = v[j];
+    *reinterpret_cast<Pack<T>*>(p + i) = t;
+  } else {
+    p[i] = v[0];
+  }
+}
+
+// ---- general evaluator: bytecode interpreted at run time -------------------------------------------------
+// NI input register sets and NS slots are template parameters (2/2, 4/4, 8/8): the register budget decides how
+// many threads -- and so how many bytes in flight -- an SM holds, which is what bounds an elementwise kernel.
+template <typename T, bool VEC, int NI, int NS, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_fused(const __grid_constant__ FzArgs a) {
   constexpr int N = VEC ? Pack<T>::N : 1;
   const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * N;
   if (i >= a.n) return;
 
-  // (i0, i1) of each lane, only when some operand is a row / column vector
   int64_t c0[N], c1[N];
-  if (a.has_bcast) {
-    int64_t q, r;
-    if (a.n < ((int64_t)1 << 31)) {
-      const uint32_t qq = (uint32_t)i / (uint32_t)a.rows;
-      q = qq;
-      r = (uint32_t)i - qq * (uint32_t)a.rows;
-    } else {
-      q = i / a.rows;
-      r = i - q * a.rows;
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      c0[j] = r;
-      c1[j] = q;
-      if (++r == a.rows) { r = 0; ++q; }
-    }
-  }
+  if (a.has_bcast) fz_coords<T, N>(a, i, c0, c1);
 
   // all leaf loads are issued before any arithmetic
-  T inv[FZ_MAXIN][N];
+  T inv[NI][N];
 #pragma unroll
-  for (int k = 0; k < FZ_MAXIN; ++k) {
-    if (k < a.nin) {
-      const T* __restrict__ p = (const T*)a.in[k];
-      const int m = a.mode[k];
-      if (m == FZ_M_FULL) {
-        if (VEC) {
-          const Pack<T> t = *reinterpret_cast<const Pack<T>*>(p + i);
-#pragma unroll
-          for (int j = 0; j < N; ++j) inv[k][j] = t.v[j];
-        } else {
-          inv[k][0] = p[i];
-        }
-      } else if (m == FZ_M_COLVEC) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) inv[k][j] = p[c0[j]];
-      } else if (m == FZ_M_ROWVEC) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) inv[k][j] = p[c1[j]];
-      } else {
-        const T sc = m == FZ_M_DEVSCALAR ? p[0] : (T)a.imm[k];
-#pragma unroll
-        for (int j = 0; j < N; ++j) inv[k][j] = sc;
-      }
-    }
-  }
+  for (int k = 0; k < NI; ++k)
+    if (k < a.nin) fz_load<T, N, VEC>(a, k, i, c0, c1, inv[k]);
 
-  T tos[N], S[FZ_SLOTS][N];
+  T tos[N], S[NS][N];
 #pragma unroll
   for (int j = 0; j < N; ++j) tos[j] = T(0);
   int sp = 0;
 
-#define FZ_SLOT_ST_CASE(s) case s: _Pragma("unroll") for (int j = 0; j < N; ++j) S[s][j] = tos[j]; break;
+#define FZ_SLOT_ST_CASE(s) case s: if constexpr (s < NS) { _Pragma("unroll") for (int j = 0; j < N; ++j) S[s][j] = tos[j]; } break;
 #define FZ_SLOT_ST(idx) switch (idx) { FZ_CASE8(FZ_SLOT_ST_CASE) }
-#define FZ_SLOT_LD_CASE(s) case s: _Pragma("unroll") for (int j = 0; j < N; ++j) dst_[j] = S[s][j]; break;
+#define FZ_SLOT_LD_CASE(s) case s: if constexpr (s < NS) { _Pragma("unroll") for (int j = 0; j < N; ++j) dst_[j] = S[s][j]; } break;
 #define FZ_SLOT_LD(dst, idx) { T* dst_ = dst; switch (idx) { FZ_CASE8(FZ_SLOT_LD_CASE) } }
-#define FZ_IN_LD_CASE(s) case s: _Pragma("unroll") for (int j = 0; j < N; ++j) dst_[j] = inv[s][j]; break;
+#define FZ_IN_LD_CASE(s) case s: if constexpr (s < NI) { _Pragma("unroll") for (int j = 0; j < N; ++j) dst_[j] = inv[s][j]; } break;
 #define FZ_IN_LD(dst, idx) { T* dst_ = dst; switch (idx) { FZ_CASE8(FZ_IN_LD_CASE) } }
 #define FZ_BIN_CASE(ID, F) case ID: _Pragma("unroll") for (int j = 0; j < N; ++j) { const T ab[2] = {l_[j], r_[j]}; tos[j] = F<T>::apply(ab); } break;
 #define FZ_APPLY_BIN(b, l, r)                                                                        \
@@ -212,31 +236,193 @@ __global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ FzAr
         }
         break;
       }
-      case FZ_STORE: {
-        T* __restrict__ o = nullptr;
+      case FZ_STORE:
         switch (x) {
-          case 0: o = (T*)a.out[0]; break;
-          case 1: o = (T*)a.out[1]; break;
-          case 2: o = (T*)a.out[2]; break;
-          default: o = (T*)a.out[3]; break;
-        }
-        if (VEC) {
-          Pack<T> t;
-#pragma unroll
-          for (int j = 0; j < N; ++j) t.v[j] = tos[j];
-          *reinterpret_cast<Pack<T>*>(o + i) = t;
-        } else {
-          o[i] = tos[0];
+          case 0: fz_store<T, N, VEC>(a, 0, i, tos); break;
+          case 1: fz_store<T, N, VEC>(a, 1, i, tos); break;
+          case 2: fz_store<T, N, VEC>(a, 2, i, tos); break;
+          default: fz_store<T, N, VEC>(a, 3, i, tos); break;
         }
         break;
-      }
     }
   }
 }
 
+// ---- specialised evaluators: the same machine with the program as a compile-time constant ------------------
+// The programs the BASELINE configs produce (generated list, fuse_static.inc) are instantiated ahead of time:
+// every switch above folds away, stack slots become plain registers, two vectors per thread are in flight.
+struct StaticProg {
+  int n, nin;
+  uint32_t code[FZ_MAXCODE];
+};
+
+#include "fuse_static.inc"
+
+constexpr int fz_sp_before(const StaticProg& p, int pc) {
+  int sp = 0;
+  for (int i = 0; i < pc; ++i) {
+    const int op = p.code[i] & 0xff, y = (p.code[i] >> 16) & 0xff;
+    if (op <= FZ_LD_TMP && y) ++sp;
+    if (op == FZ_BIN) --sp;
+    if (op == FZ_UGRAD || op == FZ_TERN) sp -= 2;
+  }
+  return sp;
+}
+constexpr int fz_slots_needed(const StaticProg& p) {
+  int need = 1;
+  for (int i = 0; i < p.n; ++i) {
+    const int op = p.code[i] & 0xff, x = (p.code[i] >> 8) & 0xff;
+    const int sp = fz_sp_before(p, i + 1);
+    if (sp > need) need = sp;
+    if ((op == FZ_LD_TMP || op == FZ_ST_TMP) && x + 1 > need) need = x + 1;
+  }
+  return need;
+}
+
+template <int B, typename T> struct BinSel;
+#define FZ_BINSEL(ID, F) template <typename T> struct BinSel<ID, T> { using type = F<T>; };
+FZ_BINSEL(AG_B_ADD, FAdd) FZ_BINSEL(AG_B_SUB, FSub) FZ_BINSEL(AG_B_MUL, FMul) FZ_BINSEL(AG_B_DIV, FDiv)
+FZ_BINSEL(AG_B_MAX, FMax) FZ_BINSEL(AG_B_MIN, FMin) FZ_BINSEL(AG_B_POW, FPow) FZ_BINSEL(AG_B_EQ, FEq)
+FZ_BINSEL(AG_B_LT, FLt) FZ_BINSEL(AG_B_LE, FLe) FZ_BINSEL(AG_B_GT, FGt) FZ_BINSEL(AG_B_GE, FGe)
+FZ_BINSEL(AG_B_ATAN2, FAtan2) FZ_BINSEL(AG_B_HYPOT, FHypot)
+template <int G, typename T> struct TernSel;
+#define FZ_TERNSEL(ID, F) template <typename T> struct TernSel<ID, T> { using type = F<T>; };
+FZ_TERNSEL(0, GDiv2) FZ_TERNSEL(1, GEqMask) FZ_TERNSEL(2, GPow1) FZ_TERNSEL(3, GPow2) FZ_TERNSEL(4, GAtan1)
+FZ_TERNSEL(5, GAtan2) FZ_TERNSEL(6, GHypot)
+
+template <int PROG, int PC, typename T, int N, int NIN, int NSL>
+__device__ __forceinline__ void fz_step(const FzArgs& a, int64_t i, const T (&inv)[NIN][N], T (&S)[NSL][N], T (&tos)[N]) {
+  constexpr uint32_t w = kProgs[PROG].code[PC];
+  constexpr int op = w & 0xff, x = (w >> 8) & 0xff, y = (w >> 16) & 0xff;
+  constexpr int sp = fz_sp_before(kProgs[PROG], PC);
+  if constexpr (op <= FZ_LD_TMP) {
+    if constexpr (y != 0) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) S[sp][j] = tos[j];
+    }
+    if constexpr (op == FZ_LD_IN) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) tos[j] = inv[x][j];
+    } else if constexpr (op == FZ_LD_CONST) {
+      const T cv = (T)a.consts[x];
+#pragma unroll
+      for (int j = 0; j < N; ++j) tos[j] = cv;
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) tos[j] = S[x][j];
+    }
+  } else if constexpr (op == FZ_ST_TMP) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) S[x][j] = tos[j];
+  } else if constexpr (op == FZ_UNARY) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) tos[j] = U<x, T>::f(tos[j]);
+  } else if constexpr (op == FZ_BIN) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const T ab[2] = {S[sp - 1][j], tos[j]};
+      tos[j] = BinSel<x, T>::type::apply(ab);
+    }
+  } else if constexpr (op == FZ_BIN_IN || op == FZ_BIN_CONST) {
+    constexpr int k = y & 0x7f;
+    constexpr bool rev = (y & 0x80) != 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      T o;
+      if constexpr (op == FZ_BIN_IN) o = inv[k][j];
+      else o = (T)a.consts[k];
+      const T ab[2] = {rev ? o : tos[j], rev ? tos[j] : o};
+      tos[j] = BinSel<x, T>::type::apply(ab);
+    }
+  } else if constexpr (op == FZ_UGRAD) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      tos[j] = S[sp - 2][j] * U<x, T>::g(U<x, T>::needs_x ? S[sp - 1][j] : T(0), U<x, T>::needs_y ? tos[j] : T(0));
+  } else if constexpr (op == FZ_TERN) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const T t3[3] = {S[sp - 2][j], S[sp - 1][j], tos[j]};
+      tos[j] = TernSel<x, T>::type::apply(t3);
+    }
+  } else if constexpr (op == FZ_STORE) {
+    fz_store<T, N, true>(a, x, i, tos);
+  }
+}
+
+template <int PROG, typename T, int N, int NIN, int NSL, int... PC>
+__device__ __forceinline__ void fz_run(const FzArgs& a, int64_t i, const T (&inv)[NIN][N], T (&S)[NSL][N], T (&tos)[N],
+                                       std::integer_sequence<int, PC...>) {
+  (fz_step<PROG, PC, T, N, NIN, NSL>(a, i, inv, S, tos), ...);
+}
+
+constexpr int FZ_UN = 2;   // vectors per thread of a specialised kernel
+
+template <typename T, int PROG>
+__global__ void __launch_bounds__(kThreads) k_fused_static(const __grid_constant__ FzArgs a) {
+  constexpr int N = Pack<T>::N;
+  constexpr int NIN = kProgs[PROG].nin > 0 ? kProgs[PROG].nin : 1;
+  constexpr int NSL = fz_slots_needed(kProgs[PROG]);
+  const int64_t base = ((int64_t)blockIdx.x * (kThreads * FZ_UN) + threadIdx.x) * N;
+  T inv[FZ_UN][NIN][N];
+#pragma unroll
+  for (int u = 0; u < FZ_UN; ++u) {
+    const int64_t i = base + (int64_t)u * kThreads * N;
+    if (i < a.n) {
+      int64_t c0[N], c1[N];
+      if (a.has_bcast) fz_coords<T, N>(a, i, c0, c1);
+#pragma unroll
+      for (int k = 0; k < kProgs[PROG].nin; ++k) fz_load<T, N, true>(a, k, i, c0, c1, inv[u][k]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < FZ_UN; ++u) {
+    const int64_t i = base + (int64_t)u * kThreads * N;
+    if (i < a.n) {
+      T tos[N], S[NSL][N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) tos[j] = T(0);
+      fz_run<PROG, T, N, NIN, NSL>(a, i, inv[u], S, tos, std::make_integer_sequence<int, kProgs[PROG].n>{});
+    }
+  }
+}
+
+template <typename T>
+static bool launch_static(int prog, const FzArgs& a, unsigned nb, cudaStream_t st) {
+  switch (prog) {
+#define X(P) case P: k_fused_static<T, P><<<nb, kThreads, 0, st>>>(a); return true;
+    FZ_STATIC_LIST(X)
+#undef X
+  }
+  return false;
+}
+
+static int find_static(const int32_t* code, int ncode) {
+  for (int p = 0; p < FZ_NSTATIC; ++p) {
+    if (kProgs[p].n != ncode) continue;
+    bool same = true;
+    for (int k = 0; k < ncode && same; ++k) same = kProgs[p].code[k] == (uint32_t)code[k];
+    if (same) return p;
+  }
+  return -1;
+}
+
+template <typename T, bool VEC>
+static void launch_dynamic(int ni, int ns, const FzArgs& a, unsigned nb, cudaStream_t st) {
+  if (ni <= 2 && ns <= 2) k_fused<T, VEC, 2, 2, 4><<<nb, kThreads, 0, st>>>(a);
+  else if (ni <= 4 && ns <= 4) k_fused<T, VEC, 4, 4, 3><<<nb, kThreads, 0, st>>>(a);
+  else k_fused<T, VEC, 8, 8, 2><<<nb, kThreads, 0, st>>>(a);
+}
+
+static int g_fused_static_enabled = -1;
+
 }  // namespace agb
 
 using namespace agb;
+
+extern "C" ag_status ag_ewise_fused_set_static(int32_t on) {
+  g_fused_static_enabled = on ? 1 : 0;
+  return AG_OK;
+}
 
 extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts,
                                     int32_t nconsts, int32_t nin, const void* const* in, const int32_t* in_mode,
@@ -256,7 +442,7 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
   if (n == 0) return AG_OK;
   FzArgs a;
   // validate the program: operand indices, slot bounds, stack discipline, every output written
-  int sp = 0, tmp_lo = FZ_SLOTS;
+  int sp = 0, tmp_lo = FZ_SLOTS, ns_need = 1;
   uint32_t stored = 0;
   for (int pc = 0; pc < ncode; ++pc) {
     const uint32_t w = (uint32_t)code[pc];
@@ -281,6 +467,8 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
     if (op == FZ_UGRAD || op == FZ_TERN) sp -= 2;
     AG_CHECK(sp >= 0, AG_EINVAL, "ag_ewise_fused: stack underflow at %d", pc);
     if (op == FZ_ST_TMP && x < tmp_lo) tmp_lo = x;
+    if (sp > ns_need) ns_need = sp;
+    if ((op == FZ_ST_TMP || op == FZ_LD_TMP) && x + 1 > ns_need) ns_need = x + 1;
     AG_CHECK(sp <= tmp_lo, AG_EUNSUPPORTED, "ag_ewise_fused: expression too deep (%d slots)", FZ_SLOTS);
     a.code[pc] = code[pc];
   }
@@ -310,14 +498,28 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
   Context& c = ctx();
   const int N = dtype == AG_F32 ? 4 : 2;
   vec = vec && (n % N == 0);
-  const int64_t items = vec ? n / N : n;
-  const unsigned nb = (unsigned)cdiv(items, kThreads);
-  if (vec) {
-    if (dtype == AG_F32) k_fused<float, true><<<nb, kThreads, 0, c.stream>>>(a);
-    else k_fused<double, true><<<nb, kThreads, 0, c.stream>>>(a);
-  } else {
-    if (dtype == AG_F32) k_fused<float, false><<<nb, kThreads, 0, c.stream>>>(a);
-    else k_fused<double, false><<<nb, kThreads, 0, c.stream>>>(a);
+  if (g_fused_static_enabled < 0) {
+    const char* e = getenv("AGB_FUSED_STATIC");
+    g_fused_static_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  bool done = false;
+  if (vec && g_fused_static_enabled) {
+    const int prog = find_static(code, ncode);
+    if (prog >= 0) {
+      const unsigned nbs = (unsigned)cdiv(n / N, (int64_t)kThreads * FZ_UN);
+      done = dtype == AG_F32 ? launch_static<float>(prog, a, nbs, c.stream) : launch_static<double>(prog, a, nbs, c.stream);
+    }
+  }
+  if (!done) {
+    const int64_t items = vec ? n / N : n;
+    const unsigned nb = (unsigned)cdiv(items, kThreads);
+    if (vec) {
+      if (dtype == AG_F32) launch_dynamic<float, true>(nin, ns_need, a, nb, c.stream);
+      else launch_dynamic<double, true>(nin, ns_need, a, nb, c.stream);
+    } else {
+      if (dtype == AG_F32) launch_dynamic<float, false>(nin, ns_need, a, nb, c.stream);
+      else launch_dynamic<double, false>(nin, ns_need, a, nb, c.stream);
+    }
   }
   AG_LAUNCHED();
   return AG_OK;

@@ -408,6 +408,24 @@ def _run_fused(order, root):
             used_slots.add(s)
             emit(ST_TMP, s)
     n = None
+    # peephole: "ST_TMP s; LD_TMP s (overwrite)" with no later load of s -- the value is already on top
+    k = 0
+    while k + 1 < len(code):
+        a_, b_ = code[k], code[k + 1]
+        if (a_ & 0xff) == ST_TMP and b_ == (LD_TMP | (a_ & 0xff00)):
+            slot = (a_ >> 8) & 0xff
+            later = False
+            for c in code[k + 2:]:
+                if (c & 0xff) == ST_TMP and ((c >> 8) & 0xff) == slot:
+                    break
+                if (c & 0xff) == LD_TMP and ((c >> 8) & 0xff) == slot:
+                    later = True
+                    break
+            if not later:
+                del code[k:k + 2]
+                continue
+        k += 1
+    used_slots = {(c >> 8) & 0xff for c in code if (c & 0xff) in (ST_TMP, LD_TMP)}
     lowest_tmp = min(used_slots) if used_slots else SLOTS
     if len(code) > MAXCODE or state["maxdepth"] > lowest_tmp:
         raise _TooBig()

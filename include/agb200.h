@@ -207,6 +207,11 @@ ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t ncode, cons
                          int32_t nin, const void* const* in, const int32_t* in_mode, const double* in_imm,
                          int32_t nout, void* const* out, int64_t rows, int64_t cols);
 
+/* Programs that the BASELINE configs produce are also instantiated ahead of time (csrc/fuse_static.inc, generated
+ * by tools/gen_fused_programs.py) and picked by an exact match of `code`; on = 0 forces the general interpreter
+ * kernel for every program (default 1, or environment AGB_FUSED_STATIC=0).  Results are identical either way. */
+ag_status ag_ewise_fused_set_static(int32_t on);
+
 /* ---- reductions -------------------------------------------------------------------------------- */
 /* out[0] = sum(map.(x)) over n elements; deterministic two-phase tree.  sum(x), sum(abs2,x),
  * sum(abs,x) forward (rules at src/base.jl:245-247); unbroadcast's Number branch

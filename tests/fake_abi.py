@@ -212,6 +212,9 @@ class FakeLib:
         _arr(out, n, T)[:] = np.broadcast_to(st[0], (n,))
         return 0
 
+    def ag_ewise_fused_set_static(self, on):
+        return 0
+
     def ag_ewise_fused(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols):
         """Stack machine of include/agb200.h `ag_ewise_fused` over a rows x cols column-major iteration space."""
         self.launches += 1

@@ -199,6 +199,21 @@ def test_whole_steps_identical_with_and_without_fusion(ag, L, cfg):
     print("%s: %d launches fused, %d unfused" % (cfg, nf, nu))
 
 
+@pytest.mark.parametrize("cfg", ["mnist", "sweep", "rnn", "lstm"])
+def test_specialised_and_interpreted_kernels_agree(ag, L, cfg):
+    """The ahead-of-time instantiated programs (fuse_static.inc) and the general interpreter give the same bits."""
+    W = ag.workloads
+    lib = ag._lib.lib
+    try:
+        ag._lib.check(lib.ag_ewise_fused_set_static(0))
+        ri, _ = _step_all(ag, W, cfg, True, L)
+    finally:
+        ag._lib.check(lib.ag_ewise_fused_set_static(1))
+    rs, _ = _step_all(ag, W, cfg, True, L)
+    for a, b in zip(ri, rs):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
 def test_graph_capture_of_a_fused_step(ag, L):
     W = ag.workloads
     w, x, y = W.mnist_init(np.random.default_rng(9), 2048)

@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Generate autograd.jl_b200/csrc/fuse_static.inc: the fused elementwise programs that the BASELINE.json
+configs produce, to be instantiated ahead of time as specialised kernels (csrc/fuse.cu, k_fused_static).
+
+The host runtime (autograd.jl_b200/lazy.py) compiles each pending elementwise chain of a tape to bytecode.
+Which programs occur depends only on the STRUCTURE of the model code (not on sizes or data), so the list is
+collected here on the CPU: the five config workloads (autograd.jl_b200/workloads.py) are run at tiny sizes on
+the numpy stand-in for the C ABI (tests/fake_abi.py, a build-time use of the test double: nothing is computed
+for the product) and every distinct program handed to ag_ewise_fused is recorded.  Programs outside the list
+still run -- on the general interpreter kernel.
+
+Usage: python tools/gen_fused_programs.py   (then rebuild: python __graft_entry__.py)
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import __graft_entry__ as ge  # noqa: E402
+import fake_abi  # noqa: E402
+
+OUT = os.path.join(ROOT, "autograd.jl_b200", "csrc", "fuse_static.inc")
+MAX_STATIC = 96
+
+
+def main():
+    ag = ge.load_package()
+    progs = {}
+
+    class Recorder(fake_abi.FakeLib):
+        def ag_ewise_fused(self, dtype, code, ncode, consts, nconsts, nin, *rest):
+            key = tuple(int(code[k]) & 0xffffffff for k in range(ncode))
+            ent = progs.setdefault(key, {"nin": nin, "count": 0, "where": set()})
+            ent["count"] += 1
+            ent["where"].add(CUR[0])
+            return super().ag_ewise_fused(dtype, code, ncode, consts, nconsts, nin, *rest)
+
+    CUR = ["?"]
+    fake, restore = fake_abi.install(ag, Recorder())
+    L = sys.modules["agb200.lazy"]
+    prev = L.set_fusion(True)
+    W = ag.workloads
+    dev = ag.DArray.from_numpy
+    rng = np.random.default_rng(0)
+
+    def sgd(loss, params, steps=2, lr=-0.05, clip=None):
+        for _ in range(steps):
+            t = ag.diff(lambda: loss(params))
+            float(ag.value(t))
+            gs = [ag.grad(t, p) for p in params]
+            if clip is not None:                                   # examples/charlm.jl:116-118,148-149
+                gn = ag.sqrt(sum((ag.sumabs2(ag.full(g)) for g in gs[1:]), ag.sumabs2(ag.full(gs[0]))))
+                float(gn)
+            for p, g in zip(params, gs):
+                ag.axpy(lr, g, p)
+        ag.sync()
+
+    try:
+        for gc in (None, ag.release_node):
+            ag.set_gc_function(gc if gc is not None else (lambda n, t: None))
+            for dtype in (np.float64, np.float32):
+                CUR[0] = "housing"
+                w, x, y = W.housing_init(rng, 24, 5, dtype)
+                xd, yd = dev(x), dev(y)
+                sgd(lambda p: W.housing_loss(ag, p, xd, yd), [ag.Param(dev(a)) for a in w])
+                w2 = [w[0], 0.0]                                   # scalar bias Param (README.md:72)
+                CUR[0] = "mnist"
+                w, x, y = W.mnist_init(rng, 32, dtype)
+                xd, yd = dev(x), dev(y)
+                sgd(lambda p: W.mnist_loss(ag, p, xd, yd), [ag.Param(dev(a)) for a in w])
+                sgd(lambda p: W.mnist_loss(ag, p, xd, yd, global_batch=64), [ag.Param(dev(a)) for a in w])
+                CUR[0] = "sweep"
+                x, brow, bcol = W.sweep_init(rng, 16, 24, dtype)
+                sgd(lambda p: W.sweep_loss(ag, p[0], p[1], p[2]), [ag.Param(dev(a)) for a in (x, brow, bcol)])
+                xd = dev(x)
+                sgd(lambda p: W.sweep_loss(ag, xd, p[0], p[1]), [ag.Param(dev(a)) for a in (brow, bcol)])
+                CUR[0] = "charlm"
+                H, E, V, B, T = 16, 8, 12, 8, 3
+                wd = W.lstm_init(rng, H, E, V, dtype)
+                keys = list(wd)
+                for dev_ids in (False, True):
+                    ids = [rng.integers(0, V, B) for _ in range(T)]
+                    if dev_ids:
+                        ids = [ag.IArray(i) for i in ids]
+                    tg = []
+                    for _ in range(T):
+                        oh = np.zeros((V, B), dtype)
+                        oh[rng.integers(0, V, B), np.arange(B)] = 1
+                        tg.append(dev(np.asfortranarray(oh)))
+                    h0, c0 = dev(np.zeros((H, B), dtype)), dev(np.zeros((H, B), dtype))
+                    sgd(lambda p: W.lstm_loss(ag, dict(zip(keys, p)), ids, tg, h0, c0),
+                        [ag.Param(dev(wd[k])) for k in keys], clip=5.0)
+                CUR[0] = "rnn"
+                H, V, B, T = 8, 6, 8, 3
+                w = W.rnn_init(rng, H, V, dtype)
+                xs = []
+                for _ in range(T):
+                    oh = np.zeros((V, B), dtype)
+                    oh[rng.integers(0, V, B), np.arange(B)] = 1
+                    xs.append(dev(np.asfortranarray(oh)))
+                y = np.zeros((V, B), dtype)
+                y[rng.integers(0, V, B), np.arange(B)] = 1
+                yd, hd = dev(np.asfortranarray(y)), dev(np.zeros((H, B), dtype))
+                sgd(lambda p: W.rnn_loss(ag, p, xs, yd, hd), [ag.Param(dev(a)) for a in w])
+                wdv = [dev(a) for a in w]
+
+                def loss(whh):
+                    return W.rnn_loss(ag, [wdv[0], whh, wdv[2], wdv[3], wdv[4]], xs, yd, hd)
+                inner = ag.grad(loss)
+                ag.grad(lambda whh: ag.sumabs2(inner(whh)))(wdv[1]).to_numpy()
+    finally:
+        ag.set_gc_function(lambda n, t: None)
+        L.flush()
+        L.set_fusion(prev)
+        restore()
+
+    items = sorted(progs.items(), key=lambda kv: (-kv[1]["count"], kv[0]))[:MAX_STATIC]
+    lines = ["// fuse_static.inc -- GENERATED by tools/gen_fused_programs.py; do not edit.",
+             "// The fused elementwise programs of the BASELINE.json configs (housing, mnist, sweep, charlm, rnn incl.",
+             "// grad-of-grad), instantiated ahead of time by csrc/fuse.cu.  Instruction word: op | a << 8 | b << 16.",
+             "#define FZ_NSTATIC %d" % len(items),
+             "#define FZ_STATIC_LIST(X) " + " ".join("X(%d)" % i for i in range(len(items))),
+             "constexpr StaticProg kProgs[%d] = {" % max(len(items), 1)]
+    for i, (code, ent) in enumerate(items):
+        lines.append("  /* %2d: %s */ {%d, %d, {%s}}," % (i, ",".join(sorted(ent["where"])), len(code), ent["nin"],
+                                                         ", ".join("0x%xu" % c for c in code)))
+    if not items:
+        lines.append("  {0, 0, {0}},")
+    lines.append("};")
+    with open(OUT, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("wrote %d programs (of %d distinct) to %s" % (len(items), len(progs), OUT))
+
+
+if __name__ == "__main__":
+    main()
