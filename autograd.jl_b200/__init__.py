@@ -19,5 +19,7 @@ from .graph import StepGraph, Event, pinned_empty
 from .comm import DataParallel
 from .gradcheck import gradcheck
 from .vm import E, Expr, primitive_expr
+from .lazy import set_fusion
+from .loader import UByteBatch, read_idx_ubyte
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -66,6 +66,8 @@ _SIGS = {
     "ag_gemm": [i32, i32, i32, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64],
     "ag_gemm_set_engine": [i32],
     "ag_gemm_last_engine": [C.c_char_p, i64],
+    "ag_ubyte_to_float": [i32, vp, vp, i64, dbl],
+    "ag_onehot_labels": [i32, vp, i64, i32, i32, vp],
     "ag_gather": [i32, vp, vp, vp, i64],
     "ag_gather_cols": [i32, vp, i64, vp, vp, i64],
     "ag_scatter_add": [i32, vp, i64, vp, vp, i64, i64],
@@ -115,6 +117,8 @@ def check(status):
         return
     msg = last_error()
     if status == EINVAL:
+        if "BoundsError" in msg:
+            raise IndexError(msg)          # the sticky device-side index check (Julia: BoundsError)
         raise DimensionMismatch(msg)
     if status == ENOMEM:
         raise MemoryError(msg)

@@ -1,0 +1,72 @@
+"""Minibatches in the dataset's own byte format (examples/mnist.jl:77-96).
+
+The reference loads the idx-ubyte files on the host and keeps `xtrn = reshape(a ./ 255f0, 784, :)` (Float32,
+4 bytes per pixel) and a dense one-hot `ytrn` (10 x N Float32); `minibatch` slices columns out of those.  Fed
+to a device that way, a step moves 4 bytes per pixel over PCIe -- 208 MB for a 65536-column batch, which costs
+20x the step itself.  `UByteBatch` keeps the dataset's bytes: a batch crosses PCIe as 1 byte per pixel and 1 byte
+per label and `ag_ubyte_to_float` / `ag_onehot_labels` rebuild exactly the arrays the reference builds (IEEE
+division by 255; exact 0/1), in place, so a captured step graph keeps reading the same device arrays.
+"""
+import ctypes as C
+import gzip
+import struct
+
+import numpy as np
+
+from . import darray as D
+from . import lazy as _lazy
+from ._lib import check, DimensionMismatch
+
+
+def read_idx_ubyte(path):
+    """Parse an idx-ubyte file (optionally .gz) into a uint8 array; examples/mnist.jl:83-86 skips the same
+    16-byte (images) / 8-byte (labels) header by offset.  Images come back as (rows*cols, n) column-major."""
+    op = gzip.open if str(path).endswith(".gz") else open
+    with op(path, "rb") as f:
+        raw = f.read()
+    zero, dtype, nd = struct.unpack(">HBB", raw[:4])
+    if zero != 0 or dtype != 0x08:
+        raise ValueError("%s: not an idx-ubyte file" % path)
+    dims = struct.unpack(">" + "I" * nd, raw[4:4 + 4 * nd])
+    data = np.frombuffer(raw, dtype=np.uint8, offset=4 + 4 * nd)
+    if data.size != int(np.prod(dims)):
+        raise ValueError("%s: truncated idx file" % path)
+    if nd == 1:
+        return data.copy()
+    return np.asfortranarray(data.reshape(dims[0], -1).T)          # (pixels, n): one image per column
+
+
+class UByteBatch:
+    """Device-side minibatch rebuilt from bytes: `x` (nfeat, ncols) = pixels ./ divisor, `y` (nclass, ncols) one-hot.
+
+    load(pixels, labels) takes host uint8 arrays (ideally pinned, see `pinned_empty`), copies them to the device
+    asynchronously and converts in place; the DArrays `x` and `y` keep their addresses from batch to batch."""
+
+    def __init__(self, nfeat, ncols, nclass=10, dtype=np.float32, divisor=255.0, zero_to=10):
+        self.nfeat, self.ncols, self.nclass = int(nfeat), int(ncols), int(nclass)
+        self.divisor, self.zero_to = float(divisor), int(zero_to)
+        self.x = D.DArray.empty((self.nfeat, self.ncols), dtype)
+        self.y = D.DArray.empty((self.nclass, self.ncols), dtype)
+        self._px = D._Buffer(max(self.nfeat * self.ncols, 16))
+        self._lb = D._Buffer(max(self.ncols, 16))
+
+    @property
+    def h2d_bytes(self):
+        return self.nfeat * self.ncols + self.ncols
+
+    def load(self, pixels, labels):
+        pixels, labels = np.asarray(pixels), np.asarray(labels)
+        if pixels.dtype != np.uint8 or labels.dtype != np.uint8:
+            raise TypeError("UByteBatch.load takes uint8 arrays")
+        if pixels.size != self.nfeat * self.ncols or labels.size != self.ncols:
+            raise DimensionMismatch("UByteBatch.load: %s pixels / %s labels for a (%d, %d) batch"
+                                    % (pixels.shape, labels.shape, self.nfeat, self.ncols))
+        if not (pixels.flags.f_contiguous or pixels.flags.c_contiguous and pixels.ndim == 1):
+            pixels = np.asfortranarray(pixels)
+        _lazy.flush()                                   # pending operations must read the previous batch first
+        check(D.lib.ag_copy_h2d(C.c_void_p(self._px.ptr), C.c_void_p(pixels.ctypes.data), pixels.size))
+        check(D.lib.ag_copy_h2d(C.c_void_p(self._lb.ptr), C.c_void_p(labels.ctypes.data), labels.size))
+        check(D.lib.ag_ubyte_to_float(self.x.dt, C.c_void_p(self._px.ptr), D.vptr(self.x), self.x.size, self.divisor))
+        check(D.lib.ag_onehot_labels(self.y.dt, C.c_void_p(self._lb.ptr), self.ncols, self.nclass, self.zero_to,
+                                     D.vptr(self.y)))
+        return self.x, self.y

@@ -37,6 +37,24 @@ def mnist_init(rng, batch, dtype=np.float32, hidden=64, nin=784, nout=10):
     return w, np.asfortranarray(x), np.asfortranarray(y)
 
 
+def mnist_ubyte_batch(rng, batch, nin=784):
+    """A synthetic minibatch in the dataset's byte format (idx-ubyte, examples/mnist.jl:83-86): pixels 0..255 as
+    (nin, batch) uint8 and digit labels 0..9."""
+    return (np.asfortranarray(rng.integers(0, 256, (nin, batch), dtype=np.uint8)),
+            rng.integers(0, 10, batch, dtype=np.uint8))
+
+
+def mnist_from_ubyte(pixels, labels, dtype=np.float32, nout=10):
+    """The host arrays the reference builds from the bytes (examples/mnist.jl:80-81): x = pixels ./ 255f0 and the
+    one-hot y with digit 0 in row 10."""
+    x = np.asfortranarray(pixels.astype(dtype) / dtype(255))
+    cls = labels.astype(np.int64)
+    cls[cls == 0] = 10
+    y = np.zeros((nout, labels.size), dtype, order="F")
+    y[cls - 1, np.arange(labels.size)] = 1
+    return x, y
+
+
 def mnist_predict(m, w, x):
     a = m.relu(m.add(m.matmul(w[0], x), w[1]))
     return m.add(m.matmul(w[2], a), w[3])

@@ -89,7 +89,7 @@ def cpu_reference_run(steps, warmup, budget_s=20.0):
     W = ge.load_package().workloads        # workload definitions only (pure Python, no device call)
     rng = np.random.default_rng(1)
     w, _, _ = W.mnist_init(rng, 1)
-    _, x, y = W.mnist_init(np.random.default_rng(1000), BATCH)
+    x, y = W.mnist_from_ubyte(*W.mnist_ubyte_batch(np.random.default_rng(1000), BATCH))   # the arrays of mnist.jl:80-81
     params = [agref.Param(np.asfortranarray(a)) for a in w]
 
     def step():
@@ -180,16 +180,23 @@ def main():
 
     # identical Params on every rank, per-rank batch shard
     w_np, _, _ = Wl.mnist_init(np.random.default_rng(1), 1)
-    _, x_np, y_np = Wl.mnist_init(np.random.default_rng(1000 + rank), B)
+    # the batch in the dataset's byte format and the Float32 arrays the reference builds from it (mnist.jl:80-81)
+    px_np, lb_np = Wl.mnist_ubyte_batch(np.random.default_rng(1000 + rank), B)
+    x_np, y_np = Wl.mnist_from_ubyte(px_np, lb_np)
     params = [ag.Param(ag.DArray.from_numpy(a)) for a in w_np]
-    xd, yd = ag.DArray.empty(x_np.shape, np.float32), ag.DArray.empty(y_np.shape, np.float32)
+    batch = ag.UByteBatch(x_np.shape[0], B)
+    xd, yd = batch.x, batch.y
     xh, yh = ag.pinned_empty(x_np.shape, np.float32), ag.pinned_empty(y_np.shape, np.float32)
     xh[...] = x_np
     yh[...] = y_np
+    pxh, lbh = ag.pinned_empty(px_np.shape, np.uint8), ag.pinned_empty(lb_np.shape, np.uint8)
+    pxh[...] = px_np
+    lbh[...] = lb_np
     loss_h = ag.pinned_empty((1,), np.float32)
-    xd.copy_from_host(xh.host_ptr, xh.nbytes)
-    yd.copy_from_host(yh.host_ptr, yh.nbytes)
+    batch.load(pxh, lbh)
     ag.sync()
+    if rank == 0:       # the device conversions rebuild the reference's arrays bit for bit
+        assert np.array_equal(xd.to_numpy(), x_np) and np.array_equal(yd.to_numpy(), y_np), "ubyte batch mismatch"
     gB = B * world
     state = {}
 
@@ -290,16 +297,26 @@ def main():
         yd.copy_from_host(yh.host_ptr, yh.nbytes)
         step()
         ag._lib.check(ag._lib.lib.ag_copy_d2h(C_.c_void_p(loss_h.host_ptr), C_.c_void_p(state["loss"].ptr), 4))
-    for _ in range(2):
-        e2e_step()
-    barrier()
+
+    def e2e_ubyte_step():       # same arrays rebuilt on the device from the dataset's bytes
+        batch.load(pxh, lbh)
+        step()
+        ag._lib.check(ag._lib.lib.ag_copy_d2h(C_.c_void_p(loss_h.host_ptr), C_.c_void_p(state["loss"].ptr), 4))
+
+    def time_e2e(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            fn()
+        ag.sync()
+        dt = (time.perf_counter() - t0) / Ke
+        barrier()
+        return dt
     Ke = max(3, min(K, 20))
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
-    ag.sync()
-    e2e_s = (time.perf_counter() - t0) / Ke
-    barrier()
+    e2e_s = time_e2e(e2e_step)
+    e2e_ub_s = time_e2e(e2e_ubyte_step)
 
     # ---- dominant kernel, timed alone on the library stream (inputs > L2)
     cand = {}
@@ -349,9 +366,9 @@ def main():
     ms_all, e2e_all = ms, e2e_s
     if dist is not None:
         import torch
-        tt = torch.tensor([ms, e2e_s, fwd_ms], dtype=torch.float64)
+        tt = torch.tensor([ms, e2e_s, fwd_ms, e2e_ub_s], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_all, e2e_all, fwd_ms = tt.tolist()
+        ms_all, e2e_all, fwd_ms, e2e_ub_s = tt.tolist()
     ms_per_step = ms_all / K
     fb, bb = algo_bytes(B)
     bwd_ms = max(ms_per_step - fwd_ms, 1e-9)
@@ -380,7 +397,12 @@ def main():
             "algorithmic_bytes": {"forward": fb, "backward": bb},
             "clocks": clk,
             "e2e": {"value": world / e2e_all, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes + yh.nbytes),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_all * 1e3},
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_all * 1e3,
+                    "input": "the reference's host arrays: x (784,B) and one-hot y (10,B) Float32, pinned"},
+            "e2e_ubyte": {"value": world / e2e_ub_s, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes),
+                          "d2h_bytes_per_step": 4, "ms_per_step": e2e_ub_s * 1e3,
+                          "input": "the same batch as idx-ubyte bytes (1 B per pixel / label); x ./ 255f0 and the one-hot "
+                                   "y of examples/mnist.jl:80-81 rebuilt on the device, bit-identical (asserted)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_base,

@@ -259,6 +259,17 @@ ag_status ag_gemm_set_engine(int32_t engine);
 ag_status ag_gemm_last_engine(char* buf, int64_t buflen);
 
 /* ---- indexing: getindex / Sparse / addtoindex! ------------------------------------------------- */
+/* Minibatches in the dataset's byte format (examples/mnist.jl:77-88): the host builds `a ./ 255f0` (xshape, :80)
+ * and the one-hot label matrix (yshape, :81) and every step would move 4 bytes per pixel; here the bytes cross
+ * PCIe and the conversions run on the device with identical results (IEEE division; exact 0/1).
+ * ag_ubyte_to_float: dst[i] = T(src[i]) / divisor for n bytes on the device.
+ * ag_onehot_labels: dst is (nclass, ncols) column-major; column j has a 1 in row (labels[j] == 0 ? zero_to :
+ * labels[j]) - 1 (1-based classes, `a[a.==0] = 10`), 0 elsewhere; a label outside 1..nclass raises the sticky
+ * bounds flag (reported by the next ag_sync, like an index out of range). */
+ag_status ag_ubyte_to_float(int32_t dtype, const void* src, void* dst, int64_t n, double divisor);
+ag_status ag_onehot_labels(int32_t dtype, const void* labels, int64_t ncols, int32_t nclass, int32_t zero_to,
+                           void* dst);
+
 /* out[j] = x[idx[j]], j < n; idx are 0-based flat offsets on device.  getindex forward,
  * src/getindex.jl:32. */
 ag_status ag_gather(int32_t dtype, const void* x, const int64_t* idx, void* out, int64_t n);

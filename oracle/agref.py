@@ -996,3 +996,19 @@ def gradcheck(f, *x, kw=None, args=None, nsample=10, rtol=0.05, atol=0.01, delta
                     print("gradcheck fail", i, j, nd, ad)
                 ok &= good
     return ok
+
+
+# ---- input formats (examples/mnist.jl:77-88) ------------------------------------------------------------------
+def xshape(a, nfeat=784, dtype=np.float32):
+    """examples/mnist.jl:80  xshape(a) = reshape(a ./ 255f0, 784, div(length(a),784))  (column-major)."""
+    a = np.asarray(a, dtype=np.uint8).reshape(-1, order="F")
+    return np.asfortranarray((a.astype(dtype) / dtype(255)).reshape((nfeat, a.size // nfeat), order="F"))
+
+
+def yshape(a, nclass=10, dtype=np.float32):
+    """examples/mnist.jl:81  yshape(a) = (a[a.==0] = 10; full(sparse(Vector{Int}(a), 1:length(a), 1f0)))."""
+    a = np.asarray(a, dtype=np.int64).reshape(-1).copy()
+    a[a == 0] = 10
+    y = np.zeros((nclass, a.size), dtype=dtype, order="F")
+    y[a - 1, np.arange(a.size)] = 1
+    return y

@@ -266,6 +266,24 @@ class FakeLib:
                     return self._fail(1, "ag_ewise_fused: bad opcode")
         return 0
 
+    # ---- input formats
+    def ag_ubyte_to_float(self, dtype, src, dst, n, divisor):
+        self.launches += 1
+        T = _DT[dtype]
+        _arr(dst, n, T)[:] = _arr(src, n, np.uint8).astype(T) / T(divisor)
+        return 0
+
+    def ag_onehot_labels(self, dtype, labels, ncols, nclass, zero_to, dst):
+        self.launches += 1
+        T = _DT[dtype]
+        lb = _arr(labels, ncols, np.uint8).astype(np.int64)
+        lb[lb == 0] = zero_to
+        out = _arr(dst, nclass * ncols, T).reshape((nclass, ncols), order="F")
+        out[:] = 0
+        ok = (lb >= 1) & (lb <= nclass)
+        out[lb[ok] - 1, np.arange(ncols)[ok]] = 1
+        return 0
+
     # ---- reductions
     @staticmethod
     def _map(m, v):

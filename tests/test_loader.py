@@ -1,0 +1,109 @@
+"""Input formats either side of the path: the oracle's restatement of examples/mnist.jl:80-81
+(xshape / yshape), the host logic of UByteBatch on the numpy stand-in, and -- on the GPU -- bit-exact parity of the
+device conversions with the oracle, plus a whole MNIST step fed from bytes against the same step fed from the
+reference's Float32 arrays."""
+import gzip
+import struct
+
+import numpy as np
+import pytest
+
+
+def test_oracle_xshape_yshape_known_answers(oracle):
+    # examples/mnist.jl:80-81 by hand: pixels/255 in Float32; label 0 -> class 10, label d -> class d (1-based rows)
+    x = oracle.xshape(np.array([0, 255, 51, 128], np.uint8), nfeat=2)
+    assert x.dtype == np.float32 and x.shape == (2, 2)
+    assert np.array_equal(x, np.array([[0.0, np.float32(51) / np.float32(255)], [1.0, np.float32(128) / np.float32(255)]], np.float32))
+    y = oracle.yshape(np.array([0, 1, 9, 3], np.uint8))
+    assert y.shape == (10, 4) and y.sum() == 4
+    assert [int(np.argmax(y[:, j])) for j in range(4)] == [9, 0, 8, 2]
+
+
+def test_idx_reader_roundtrip(agpkg, tmp_path):
+    rng = np.random.default_rng(0)
+    imgs = rng.integers(0, 256, (5, 4, 3), dtype=np.uint8)           # 5 images of 4x3
+    labels = rng.integers(0, 10, 5, dtype=np.uint8)
+    pi, pl = tmp_path / "img-idx3-ubyte.gz", tmp_path / "lab-idx1-ubyte"
+    with gzip.open(pi, "wb") as f:
+        f.write(struct.pack(">HBBIII", 0, 8, 3, 5, 4, 3) + imgs.tobytes())
+    with open(pl, "wb") as f:
+        f.write(struct.pack(">HBBI", 0, 8, 1, 5) + labels.tobytes())
+    a = agpkg.read_idx_ubyte(pi)
+    assert a.shape == (12, 5) and np.array_equal(a[:, 2], imgs[2].reshape(-1))
+    assert np.array_equal(agpkg.read_idx_ubyte(pl), labels)
+    with open(pl, "wb") as f:
+        f.write(b"\x00\x00\x0d\x01" + b"\x00" * 8)
+    with pytest.raises(ValueError):
+        agpkg.read_idx_ubyte(pl)
+
+
+def _batch(rng, nfeat, ncols):
+    px = np.asfortranarray(rng.integers(0, 256, (nfeat, ncols), dtype=np.uint8))
+    lb = rng.integers(0, 10, ncols, dtype=np.uint8)
+    return px, lb
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_ubyte_batch_host_logic(hostlib, oracle, dtype):
+    ag = hostlib
+    px, lb = _batch(np.random.default_rng(1), 12, 7)
+    b = ag.UByteBatch(12, 7, dtype=dtype)
+    x, y = b.load(px, lb)
+    assert np.array_equal(x.to_numpy(), oracle.xshape(px, 12, dtype))
+    assert np.array_equal(y.to_numpy(), oracle.yshape(lb, 10, dtype))
+    assert b.h2d_bytes == 12 * 7 + 7
+    with pytest.raises(ag.DimensionMismatch):
+        b.load(px[:, :3], lb)
+    with pytest.raises(TypeError):
+        b.load(px.astype(np.float32), lb)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nfeat,ncols", [(784, 100), (784, 4099), (13, 1), (33, 515)])
+def test_device_conversions_match_the_oracle_bit_for_bit(ag, oracle, dtype, nfeat, ncols):
+    px, lb = _batch(np.random.default_rng(2), nfeat, ncols)
+    b = ag.UByteBatch(nfeat, ncols, dtype=dtype)
+    x, y = b.load(px, lb)
+    assert np.array_equal(x.to_numpy(), oracle.xshape(px, nfeat, dtype))
+    assert np.array_equal(y.to_numpy(), oracle.yshape(lb, 10, dtype))
+    px2, lb2 = _batch(np.random.default_rng(3), nfeat, ncols)          # in place: same device arrays
+    p0 = x.ptr
+    x2, y2 = b.load(px2, lb2)
+    assert x2.ptr == p0 and np.array_equal(x2.to_numpy(), oracle.xshape(px2, nfeat, dtype))
+    assert np.array_equal(y2.to_numpy(), oracle.yshape(lb2, 10, dtype))
+
+
+@pytest.mark.gpu
+def test_bad_label_raises_the_sticky_flag(ag):
+    b = ag.UByteBatch(4, 3)
+    b.load(np.zeros((4, 3), np.uint8), np.array([1, 200, 3], np.uint8))
+    with pytest.raises(IndexError):
+        ag.sync()
+    ag.sync()
+
+
+@pytest.mark.gpu
+def test_mnist_step_from_bytes_equals_step_from_float_arrays(ag, oracle):
+    W = ag.workloads
+    rng = np.random.default_rng(4)
+    B = 2048
+    w, _, _ = W.mnist_init(rng, 1)
+    px, lb = _batch(rng, 784, B)
+    xf, yf = oracle.xshape(px), oracle.yshape(lb)
+
+    def run(xd, yd):
+        p = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+        t = ag.diff(lambda: W.mnist_loss(ag, p, xd, yd))
+        return [float(ag.value(t))] + [ag.grad(t, q).to_numpy() for q in p]
+    bt = ag.UByteBatch(784, B)
+    r1 = run(*bt.load(px, lb))
+    r2 = run(ag.DArray.from_numpy(xf), ag.DArray.from_numpy(yf))
+    for a, c in zip(r1, r2):
+        assert np.array_equal(np.asarray(a), np.asarray(c))
+    # and against the float64 oracle tape on the reference's own arrays
+    po = [oracle.Param(np.asfortranarray(a.astype(np.float64))) for a in w]
+    to = oracle.diff(lambda: W.mnist_loss(oracle, po, xf.astype(np.float64), yf.astype(np.float64)))
+    for q, g in zip(po, r1[1:]):
+        ref = oracle.full(oracle.grad(to, q))
+        assert np.max(np.abs(g - ref)) <= 1e-5 * np.max(np.abs(ref))
