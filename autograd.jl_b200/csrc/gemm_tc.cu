@@ -483,13 +483,22 @@ __global__ void __launch_bounds__(256)
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
   int64_t m = i % M, n = i / M;
+  // all partials of a block of 8 are in flight before the (fixed-order) additions
   float s0 = 0.f, s1 = 0.f;
+  const int64_t MN = M * N;
   int k = 0;
-  for (; k + 1 < splits; k += 2) {
-    s0 += ws[(int64_t)k * M * N + i];
-    s1 += ws[(int64_t)(k + 1) * M * N + i];
+  for (; k + 8 <= splits; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = ws[(int64_t)(k + u) * MN + i];
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) { s0 += v[u]; s1 += v[u + 1]; }
   }
-  if (k < splits) s0 += ws[(int64_t)k * M * N + i];
+  for (; k + 1 < splits; k += 2) {
+    s0 += ws[(int64_t)k * MN + i];
+    s1 += ws[(int64_t)(k + 1) * MN + i];
+  }
+  if (k < splits) s0 += ws[(int64_t)k * MN + i];
   float* c = C + m + n * ldc;
   float r = alpha * (s0 + s1);
   *c = beta == 0.f ? r : r + beta * (*c);

@@ -175,6 +175,32 @@ function addto!(a::DArray{T,2}, b::Sparse) where T
     a
 end
 
+# ---- horizontal fusion (SURVEY.md 8f-1): deferred elementwise chains -> ONE launch ------------------------
+# The executable host logic lives in autograd.jl_b200/lazy.py; in Julia the same thing is a `LazyDArray <: DArray`
+# whose `getproperty(:ptr)` forces the pending expression DAG.  The ccall it ends in:
+function ewise_fused!(outs::Vector{<:DArray{T}}, code::Vector{Int32}, consts::Vector{Float64},
+                      ins::Vector{Ptr{Cvoid}}, modes::Vector{Int32}, imms::Vector{Float64}, rows::Integer, cols::Integer) where T
+    op = Ptr{Cvoid}[o.ptr for o in outs]
+    check(ccall((:ag_ewise_fused, LIB), Int32,
+                (Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Ptr{Float64}, Int32,
+                 Ptr{Ptr{Cvoid}}, Int64, Int64),
+                dtcode(T), code, length(code), consts, length(consts), length(ins), ins, modes, imms, length(outs), op,
+                rows, cols))
+    outs
+end
+
+# ---- minibatches in the dataset's byte format (examples/mnist.jl:80-81 rebuilt on the device) -------------
+function ubyte_batch!(x::DArray{T,2}, y::DArray{T,2}, px_dev::Ptr{Cvoid}, lb_dev::Ptr{Cvoid},
+                      pixels::Array{UInt8}, labels::Vector{UInt8}) where T
+    check(ccall((:ag_copy_h2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), px_dev, pixels, length(pixels)))
+    check(ccall((:ag_copy_h2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), lb_dev, labels, length(labels)))
+    check(ccall((:ag_ubyte_to_float, LIB), Int32, (Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Float64),
+                dtcode(T), px_dev, x.ptr, length(x), 255.0))                       # xshape: a ./ 255f0
+    check(ccall((:ag_onehot_labels, LIB), Int32, (Int32, Ptr{Cvoid}, Int64, Int32, Int32, Ptr{Cvoid}),
+                dtcode(T), lb_dev, size(y, 2), size(y, 1), 10, y.ptr))             # yshape: a[a.==0] = 10; one-hot
+    x, y
+end
+
 # gcnode hook (src/core.jl:168,235-237): release a consumed node's buffers to the pool early
 AutoGrad.set_gc_function((n, tape) -> (n.outgrad = nothing; n.Value isa AutoGrad.Result && (n.Value.value = nothing)))
 
