@@ -196,25 +196,50 @@ def flush():
 
 
 def force(root):
-    if root.kind is None:
-        return
-    order = _topo(root)
-    try:
-        _run_fused(order, root)
-        return
-    except _TooBig:
-        stats["splits"] += 1
-        sub = [a for a in root.args if is_pending(a)]
-        order = None
-        if sub:
-            for a in sub:
-                force(a)
-            force(root)
+    """Evaluate `root` (and every pending node below it that something else refers to)."""
+    while root.kind is not None:
+        order = _topo(root)
+        try:
+            _run_fused(order, root)
             return
-        order = [root]
-    except _NotFusable:
-        pass
-    _run_eager(order)
+        except _TooBig as why:
+            stats["splits"] += 1
+            key = "split_" + (why.args[0] if why.args else "?")
+            stats[key] = stats.get(key, 0) + 1
+            sub = _pick_split(order, root, why.args[1] if len(why.args) > 1 else set())
+            order = None
+            if sub is None:                     # a single operation always fits; defensive
+                _run_eager([root])
+                return
+            force(sub)
+            sub = None
+        except _NotFusable:
+            _run_eager(order)
+            return
+
+
+def _pick_split(order, root, ext):
+    """The largest sub-DAG (by pending nodes) that fits one launch: its root is evaluated first, then `root` is
+    retried with that node as a leaf.  Sizes are tree estimates (a shared node counts once per use)."""
+    leaves, nout, nn, best = {}, {}, {}, None
+    for n in order:
+        lv, no, k = set(), 0, 1
+        for a in n.args:
+            if is_pending(a):
+                lv |= leaves[id(a)]
+                no += nout[id(a)]
+                k += nn[id(a)]
+            elif isinstance(a, D.DArray):
+                lv.add(id(a))
+        leaves[id(n)], nn[id(n)] = lv, k
+        nout[id(n)] = no + (1 if id(n) in ext else 0)
+        if n is root:
+            continue
+        outs_if_root = no + 1                   # the sub-root is written whether or not something refers to it
+        if len(lv) <= MAXIN and outs_if_root <= MAXOUT and 4 * k <= MAXCODE and k <= SLOTS * 2:
+            if best is None or k > nn[id(best)]:
+                best = n
+    return best
 
 
 def _run_eager(order):
@@ -283,8 +308,9 @@ def _run_fused(order, root):
             if ext:
                 outputs.append(n)
     n = None
+    ext_ids = {id(o) for o in outputs}
     if len(outputs) > MAXOUT:
-        raise _TooBig()
+        raise _TooBig("outputs", ext_ids)
     if n_elem == 0:
         for o in outputs:
             o._set_storage(D.DArray.empty(S, dtype))
@@ -302,7 +328,7 @@ def _run_fused(order, root):
             if c == v and np.signbit(c) == np.signbit(v):
                 return i
         if len(consts) >= MAXCONST:
-            raise _TooBig()
+            raise _TooBig("constants", ext_ids)
         consts.append(v)
         return len(consts) - 1
 
@@ -310,7 +336,7 @@ def _run_fused(order, root):
         i = leaf_idx.get(id(x))
         if i is None:
             if len(leaves) >= MAXIN:
-                raise _TooBig()
+                raise _TooBig("inputs", ext_ids)
             i = leaf_idx[id(x)] = len(leaves)
             leaves.append(x)
         return i
@@ -401,7 +427,7 @@ def _run_fused(order, root):
         u = uses.get(id(n), 0)
         if u > 0:
             if not free_slots:
-                raise _TooBig()
+                raise _TooBig("slots", ext_ids)
             s = max(free_slots)
             free_slots.remove(s)
             tmp_slot[id(n)], remaining[id(n)] = s, u
@@ -428,7 +454,7 @@ def _run_fused(order, root):
     used_slots = {(c >> 8) & 0xff for c in code if (c & 0xff) in (ST_TMP, LD_TMP)}
     lowest_tmp = min(used_slots) if used_slots else SLOTS
     if len(code) > MAXCODE or state["maxdepth"] > lowest_tmp:
-        raise _TooBig()
+        raise _TooBig("code" if len(code) > MAXCODE else "slots", ext_ids)
 
     # ---- operand layouts: full / scalar / row vector / column vector of a collapsed rows x cols space
     modes, imms, bc = [], [], []

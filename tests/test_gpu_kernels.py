@@ -136,7 +136,9 @@ def test_sum_all(ag, dtype, n):
 
 RED = [((10, 1000), 0), ((10, 1000), 1), ((64, 5000), 1), ((64, 5000), 0), ((1, 777), 1), ((300, 50), 1),
        ((1000, 33), 1), ((1000, 33), 0), ((100, 7, 13), 1), ((2, 3, 5), (0, 2)), ((2, 3, 5), (0, 1)),
-       ((6, 4, 5, 3), (1, 2)), ((5000, 3), 0), ((3, 100000), 1), ((100000, 3), 0), ((17, 1), 1)]
+       ((6, 4, 5, 3), (1, 2)), ((5000, 3), 0), ((3, 100000), 1), ((100000, 3), 0), ((17, 1), 1),
+       # tiled strided form (inner > 256, short reduced extent): the LSTM bias gradients
+       ((512, 256), 1), ((640, 256), 1), ((513, 17), 1), ((257, 64, 3), 1), ((300, 16), 1), ((4099, 1000), 1)]
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
