@@ -13,6 +13,8 @@ The host language is Python here because no Julia toolchain exists in this image
 julia/AutoGradB200.jl holds the equivalent Julia binding.  The arrays inside Param/Result are
 DArray; every array operation the sweep triggers is a kernel in libagb200.so.
 """
+import weakref
+
 from .darray import DArray, isnum
 
 
@@ -64,10 +66,18 @@ class Result(Tracked):
 
 
 class Node:
-    __slots__ = ("Value", "parents", "children", "outgrad")
+    """src/core.jl:29-34.  `children` holds WEAK references (see `node_children`): parents <-> children would be a
+    reference cycle, and a dropped Tape must release its device arrays at once (reference counting), not whenever
+    the cyclic collector runs -- pending deferred operations of a dead tape would otherwise still be evaluated."""
+    __slots__ = ("Value", "parents", "children", "outgrad", "__weakref__")
 
     def __init__(self, v):
         self.Value, self.parents, self.children, self.outgrad = v, [], [], None
+
+
+def node_children(n):
+    """The live children of a node (src/core.jl:32)."""
+    return [c for c in (r() for r in n.children) if c is not None]
 
 
 class Tape:
@@ -122,7 +132,7 @@ def _record(v, f, args, kwargs):
             if isinstance(a, Tracked):
                 p = _node_of(tape, a)
                 node.parents[i] = p
-                p.children.append(node)
+                p.children.append(weakref.ref(node))
         tape.dict[id(result)] = node
         tape.list.append(node)
     return result

@@ -52,6 +52,7 @@ struct FzArgs {
   void* out[FZ_MAXOUT];
   int32_t ncode, nin, nout, has_bcast;
   int64_t n, rows;
+  int32_t zero;   // always 0, but only known at run time: see fz_opaque
 };
 
 #define FZ_CASE8(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
@@ -279,6 +280,15 @@ constexpr int fz_slots_needed(const StaticProg& p) {
   return need;
 }
 
+// A value that crosses an instruction boundary must be the ROUNDED result of that instruction.  Left alone, ptxas
+// contracts the `mul.f32` that ends one instruction with the `add.f32` that starts the next into an FFMA (an empty
+// asm barrier stops NVVM but not ptxas), and the fused chain would differ in the last bit from the sequence of
+// single kernels.  XOR with a zero that is only known at run time is a bit-exact identity no optimiser can remove.
+__device__ __forceinline__ void fz_opaque(float& v, int zero) { v = __int_as_float(__float_as_int(v) ^ zero); }
+__device__ __forceinline__ void fz_opaque(double& v, int zero) {
+  v = __longlong_as_double(__double_as_longlong(v) ^ (long long)zero);
+}
+
 template <int B, typename T> struct BinSel;
 #define FZ_BINSEL(ID, F) template <typename T> struct BinSel<ID, T> { using type = F<T>; };
 FZ_BINSEL(AG_B_ADD, FAdd) FZ_BINSEL(AG_B_SUB, FSub) FZ_BINSEL(AG_B_MUL, FMul) FZ_BINSEL(AG_B_DIV, FDiv)
@@ -347,6 +357,11 @@ __device__ __forceinline__ void fz_step(const FzArgs& a, int64_t i, const T (&in
   } else if constexpr (op == FZ_STORE) {
     fz_store<T, N, true>(a, x, i, tos);
   }
+  if constexpr (op == FZ_UNARY || op == FZ_BIN || op == FZ_BIN_IN || op == FZ_BIN_CONST || op == FZ_UGRAD ||
+                op == FZ_TERN) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) fz_opaque(tos[j], a.zero);
+  }
 }
 
 template <int PROG, typename T, int N, int NIN, int NSL, int... PC>
@@ -414,10 +429,18 @@ static void launch_dynamic(int ni, int ns, const FzArgs& a, unsigned nb, cudaStr
 }
 
 static int g_fused_static_enabled = -1;
+static int64_t g_fused_hits = 0, g_fused_misses = 0;   // launches of specialised / interpreted programs
 
 }  // namespace agb
 
 using namespace agb;
+
+extern "C" ag_status ag_ewise_fused_stats(int64_t* out2) {
+  if (!out2) return AG_EINVAL;
+  out2[0] = g_fused_hits;
+  out2[1] = g_fused_misses;
+  return AG_OK;
+}
 
 extern "C" ag_status ag_ewise_fused_set_static(int32_t on) {
   g_fused_static_enabled = on ? 1 : 0;
@@ -495,6 +518,7 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
   a.nout = nout;
   a.n = n;
   a.rows = rows > 0 ? rows : 1;
+  a.zero = 0;
   Context& c = ctx();
   const int N = dtype == AG_F32 ? 4 : 2;
   vec = vec && (n % N == 0);
@@ -510,6 +534,7 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
       done = dtype == AG_F32 ? launch_static<float>(prog, a, nbs, c.stream) : launch_static<double>(prog, a, nbs, c.stream);
     }
   }
+  if (done) ++g_fused_hits; else ++g_fused_misses;
   if (!done) {
     const int64_t items = vec ? n / N : n;
     const unsigned nb = (unsigned)cdiv(items, kThreads);

@@ -92,6 +92,13 @@ class LazyArray(D.DArray):
         return D.DArray.__repr__(self)
 
 
+def kernel_stats():
+    """(launches that ran an ahead-of-time specialised program, launches on the general interpreter)."""
+    a = (C.c_int64 * 2)()
+    check(D.lib.ag_ewise_fused_stats(a))
+    return int(a[0]), int(a[1])
+
+
 def is_pending(x):
     return isinstance(x, LazyArray) and x.kind is not None
 

@@ -67,6 +67,17 @@ def mnist_loss(m, w, x, y, global_batch=None):
     return m.div(m.neg(m.sum_(m.mul(y, m.sub(p, logz)))), nb)
 
 
+def mnist_train_step(m, dp, params, x, y, lr, state, global_batch=None):
+    """One data-parallel SGD step of the MLP (examples/mnist.jl:52-62 with the update of README.md:73-76):
+    @diff + grad for every Param, then allreduce + axpy! through `dp.update`.  `state` keeps the loss and the
+    gradients alive exactly as bench.py does (what stays referenced decides which values a fused chain stores)."""
+    t = m.diff(lambda: mnist_loss(m, params, x, y, global_batch=global_batch))
+    state["loss"] = m.value(t)
+    state["grads"] = [m.grad(t, p) for p in params]
+    del t
+    state["grads"] = dp.update(-lr, state["grads"], params)
+
+
 # ---- broadcast / unbroadcast sweep ---------------------------------------------------------------
 def sweep_init(rng, rows, cols, dtype=np.float32):
     x = np.asfortranarray(rng.standard_normal((rows, cols), dtype=np.float32).astype(dtype))

@@ -212,20 +212,21 @@ def main():
     def update():
         state["grads"] = dp.update(-LR, state["grads"], params)
 
-    def eager_step():
-        fwd_bwd()
-        exchange()
-        update()
+    def eager_step():       # = fwd_bwd + update; shared with tools/gen_fused_programs.py
+        Wl.mnist_train_step(ag, dp, params, xd, yd, LR, state, global_batch=gB)
 
     # eager warm-up populates the pool / workspace, then capture the step
     for _ in range(2):
         eager_step()
     ag.sync()
-    graphs, replay = [], None
+    graphs, replay, fused_in_step = [], None, None
     try:
         # the whole step (tape forward + backward sweep + NCCL allreduce + axpy!) as ONE CUDA graph
+        fz0 = sys.modules["agb200.lazy"].kernel_stats()
         with ag.StepGraph() as g_all:
             eager_step()
+        fz1 = sys.modules["agb200.lazy"].kernel_stats()
+        fused_in_step = {"specialised": fz1[0] - fz0[0], "interpreted": fz1[1] - fz0[1]}
         graphs, replay = [g_all], "CUDA graph (single, collective captured)" if world > 1 else "CUDA graph"
 
         def step():
@@ -389,7 +390,7 @@ def main():
                                      "NCCL") if world > 1 else None,
                        "fusion": ("elementwise chains of the tape deferred and evaluated by one ag_ewise_fused launch each"
                                   if sys.modules["agb200.lazy"].enabled[0] else "off (AGB_FUSION=0)"),
-                       "launches_per_step": launches / max(K, 1),
+                       "launches_per_step": launches / max(K, 1), "fused_launches_per_step": fused_in_step,
                        "l2": "inputs (x = %.0f MB per rank) larger than the 126 MB L2; no flush" % (x_np.nbytes / 1e6)},
             "forward_ms": fwd_ms, "backward_update_ms": bwd_ms,
             "backward_hbm_gbs": bb / (bwd_ms * 1e-3) / 1e9,

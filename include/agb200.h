@@ -211,6 +211,8 @@ ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t ncode, cons
  * by tools/gen_fused_programs.py) and picked by an exact match of `code`; on = 0 forces the general interpreter
  * kernel for every program (default 1, or environment AGB_FUSED_STATIC=0).  Results are identical either way. */
 ag_status ag_ewise_fused_set_static(int32_t on);
+/* out2[0] = launches that ran a specialised program, out2[1] = launches on the general interpreter. */
+ag_status ag_ewise_fused_stats(int64_t* out2);
 
 /* ---- reductions -------------------------------------------------------------------------------- */
 /* out[0] = sum(map.(x)) over n elements; deterministic two-phase tree.  sum(x), sum(abs2,x),

@@ -215,6 +215,10 @@ class FakeLib:
     def ag_ewise_fused_set_static(self, on):
         return 0
 
+    def ag_ewise_fused_stats(self, out2):
+        out2[0], out2[1] = 0, 0
+        return 0
+
     def ag_ewise_fused(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols):
         """Stack machine of include/agb200.h `ag_ewise_fused` over a rows x cols column-major iteration space."""
         self.launches += 1

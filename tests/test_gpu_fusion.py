@@ -214,6 +214,48 @@ def test_specialised_and_interpreted_kernels_agree(ag, L, cfg):
         assert np.array_equal(np.asarray(a), np.asarray(b))
 
 
+@pytest.mark.parametrize("cfg", ["mnist", "sweep", "rnn", "lstm"])
+def test_every_fused_launch_specialised_equals_interpreted(ag, L, cfg):
+    """Each ag_ewise_fused call of a whole step is executed on BOTH evaluators and the outputs compared bit for
+    bit (this is what catches e.g. a mul of one instruction contracted with the add of the next into an FMA)."""
+    import ctypes as C
+    D = sys.modules["agb200.darray"]
+    lib, real = D.lib, D.lib.ag_ewise_fused
+    bad, seen = {}, [0]
+
+    def d2h(ptr, n, dt):
+        out = np.empty(n, dt)
+        ag._lib.check(lib.ag_copy_d2h(out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), out.nbytes))
+        return out
+
+    class Shim:
+        def __getattr__(self, k):
+            return getattr(lib, k)
+
+        def ag_ewise_fused(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols):
+            dt, n, res = (np.float32 if dtype == 0 else np.float64), rows * cols, []
+            for static in (1, 0):
+                lib.ag_ewise_fused_set_static(static)
+                st = real(dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols)
+                if st:
+                    lib.ag_ewise_fused_set_static(1)
+                    return st
+                res.append([d2h(outs[k], n, dt) for k in range(nout)])
+            lib.ag_ewise_fused_set_static(1)
+            seen[0] += 1
+            for k in range(nout):
+                if not np.array_equal(res[0][k], res[1][k], equal_nan=True):
+                    bad.setdefault(tuple(hex(int(code[j])) for j in range(ncode)), []).append(k)
+            return real(dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols)
+    D.lib = Shim()
+    try:
+        _step_all(ag, ag.workloads, cfg, True, L)
+    finally:
+        D.lib = lib
+        lib.ag_ewise_fused_set_static(1)
+    assert seen[0] > 0 and not bad, bad
+
+
 def test_graph_capture_of_a_fused_step(ag, L):
     W = ag.workloads
     w, x, y = W.mnist_init(np.random.default_rng(9), 2048)

@@ -221,3 +221,15 @@ def test_higher_order_through_deferred_rules(lz, oracle):
     g2 = ag.grad(lambda v: ag.sum_(ag.grad(lambda u: f(ag, u))(v)))(dev(ag, x))
     r2 = oracle.grad(lambda v: oracle.sum_(oracle.grad(lambda u: f(oracle, u))(v)))(x)
     assert np.allclose(g2.to_numpy(), r2, rtol=1e-12)
+
+
+def test_specialised_program_list_is_up_to_date(agpkg):
+    """csrc/fuse_static.inc must be what tools/gen_fused_programs.py generates from the current host logic
+    (a stale list would silently send the configs' chains to the slower general interpreter)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_fused_programs.py"), "--check"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, "run `python tools/gen_fused_programs.py` and rebuild\n" + r.stderr[-2000:]

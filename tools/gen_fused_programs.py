@@ -27,7 +27,7 @@ OUT = os.path.join(ROOT, "autograd.jl_b200", "csrc", "fuse_static.inc")
 MAX_STATIC = 96
 
 
-def main():
+def main(out=OUT):
     ag = ge.load_package()
     progs = {}
 
@@ -38,6 +38,12 @@ def main():
             ent["count"] += 1
             ent["where"].add(CUR[0])
             return super().ag_ewise_fused(dtype, code, ncode, consts, nconsts, nin, *rest)
+
+        # stream capture on the stand-in: the step simply runs (only the sequence of programs matters here)
+        def ag_graph_begin(self): return 0
+        def ag_graph_end(self, ref): ref._obj.value = 1; return 0
+        def ag_graph_launch(self, h): return 0
+        def ag_graph_destroy(self, h): return 0
 
     CUR = ["?"]
     fake, restore = fake_abi.install(ag, Recorder())
@@ -73,6 +79,14 @@ def main():
                 xd, yd = dev(x), dev(y)
                 sgd(lambda p: W.mnist_loss(ag, p, xd, yd), [ag.Param(dev(a)) for a in w])
                 sgd(lambda p: W.mnist_loss(ag, p, xd, yd, global_batch=64), [ag.Param(dev(a)) for a in w])
+                dp, state = ag.DataParallel(0, 1), {}                # bench.py's step (state keeps loss and grads)
+                pb = [ag.Param(dev(a)) for a in w]
+                for gb in (None, 64):
+                    for _ in range(3):
+                        W.mnist_train_step(ag, dp, pb, xd, yd, 0.1, state, global_batch=gb)
+                    with ag.StepGraph():
+                        W.mnist_train_step(ag, dp, pb, xd, yd, 0.1, state, global_batch=gb)
+                    ag.sync()
                 CUR[0] = "sweep"
                 x, brow, bcol = W.sweep_init(rng, 16, 24, dtype)
                 sgd(lambda p: W.sweep_loss(ag, p[0], p[1], p[2]), [ag.Param(dev(a)) for a in (x, brow, bcol)])
@@ -131,10 +145,16 @@ def main():
     if not items:
         lines.append("  {0, 0, {0}},")
     lines.append("};")
-    with open(OUT, "w") as f:
-        f.write("\n".join(lines) + "\n")
-    print("wrote %d programs (of %d distinct) to %s" % (len(items), len(progs), OUT))
+    text = "\n".join(lines) + "\n"
+    if out is not None:
+        with open(out, "w") as f:
+            f.write(text)
+        print("wrote %d programs (of %d distinct) to %s" % (len(items), len(progs), out))
+    return text
 
 
 if __name__ == "__main__":
+    if "--check" in sys.argv[1:]:           # exit 1 when the committed list is stale
+        with open(OUT) as f:
+            sys.exit(0 if f.read() == main(out=None) else 1)
     main()
