@@ -24,7 +24,7 @@
 
 namespace agb {
 
-constexpr int FZ_MAXCODE = 96, FZ_MAXCONST = 16, FZ_MAXIN = 8, FZ_MAXOUT = 4, FZ_SLOTS = 8;
+constexpr int FZ_MAXCODE = 96, FZ_MAXCONST = 16, FZ_MAXIN = 8, FZ_MAXOUT = 6, FZ_SLOTS = 8;
 
 // instruction word: op | a << 8 | b << 16
 enum {
@@ -242,7 +242,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_fused(const __grid_constant_
           case 0: fz_store<T, N, VEC>(a, 0, i, tos); break;
           case 1: fz_store<T, N, VEC>(a, 1, i, tos); break;
           case 2: fz_store<T, N, VEC>(a, 2, i, tos); break;
-          default: fz_store<T, N, VEC>(a, 3, i, tos); break;
+          case 3: fz_store<T, N, VEC>(a, 3, i, tos); break;
+          case 4: fz_store<T, N, VEC>(a, 4, i, tos); break;
+          default: fz_store<T, N, VEC>(a, 5, i, tos); break;
         }
         break;
     }

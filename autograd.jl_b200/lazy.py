@@ -36,12 +36,13 @@ _RAW_PTR = D.DArray.__dict__["ptr"]
 _RAW_BUF = D.DArray.__dict__["buf"]
 
 MAX_NODES = 24          # pending nodes per DAG before the largest argument is evaluated early
-MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 8, 4, 8
+MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 8, 6, 8
 LD_IN, LD_CONST, LD_TMP, ST_TMP, UNARY, BIN, BIN_IN, BIN_CONST, UGRAD, TERN, STORE = range(11)
 M_FULL, M_DEVSCALAR, M_IMM, M_COLVEC, M_ROWVEC = range(5)
 
 enabled = [os.environ.get("AGB_FUSION", "1") != "0"]
 stats = {"fused_launches": 0, "fused_nodes": 0, "fallback_nodes": 0, "splits": 0}
+trace = None            # set to a list to record (n elements, full-array inputs, outputs, program) of every fused launch
 _counter = itertools.count()
 _pending = weakref.WeakValueDictionary()
 
@@ -178,16 +179,19 @@ class _NotFusable(Exception):
     """Some operand layout is not a full array, row vector, column vector or scalar of the iteration space."""
 
 
-def _topo(root):
-    order, seen = [], set()
+def _visit(n, order, seen):
+    seen.add(id(n))
+    for a in n.args:
+        if is_pending(a) and id(a) not in seen:
+            _visit(a, order, seen)
+    order.append(n)
 
-    def visit(n):
-        seen.add(id(n))
-        for a in n.args:
-            if is_pending(a) and id(a) not in seen:
-                visit(a)
-        order.append(n)
-    visit(root)
+
+def _topo(root):
+    """Pending nodes below `root`, arguments first.  (Module-level recursion: a self-referencing closure would be a
+    reference cycle keeping `order` -- and so every node of the DAG -- alive until the cyclic collector runs.)"""
+    order = []
+    _visit(root, order, set())
     return order
 
 
@@ -294,6 +298,153 @@ def _bb_form(op, argno):
     raise UnsupportedOnDevice("binary op %s has no gradient (zerograd)" % op)
 
 
+class _Codegen:
+    """Expression DAG -> bytecode of ag_ewise_fused.  (A class rather than nested functions: mutually recursive
+    closures are reference cycles, and everything they capture -- pending nodes included -- would only die when
+    the cyclic collector runs.)"""
+
+    def __init__(self, uses, outputs, ext_ids):
+        self.uses, self.outputs, self.ext_ids = uses, outputs, ext_ids
+        self.code, self.consts, self.leaves, self.leaf_idx = [], [], [], {}
+        self.depth = self.maxdepth = 0
+        self.tmp_slot, self.remaining, self.free_slots = {}, {}, list(range(SLOTS - 1, -1, -1))
+
+    def emit(self, op, a=0, b=0):
+        self.code.append(op | (a << 8) | (b << 16))
+
+    def const_idx(self, v):
+        for i, c in enumerate(self.consts):
+            if c == v and np.signbit(c) == np.signbit(v):
+                return i
+        if len(self.consts) >= MAXCONST:
+            raise _TooBig("constants", self.ext_ids)
+        self.consts.append(v)
+        return len(self.consts) - 1
+
+    def leaf(self, x):
+        i = self.leaf_idx.get(id(x))
+        if i is None:
+            if len(self.leaves) >= MAXIN:
+                raise _TooBig("inputs", self.ext_ids)
+            i = self.leaf_idx[id(x)] = len(self.leaves)
+            self.leaves.append(x)
+        return i
+
+    def pushed(self, push):
+        if push:
+            self.depth += 1
+            self.maxdepth = max(self.maxdepth, self.depth)
+
+    @staticmethod
+    def simple(x):
+        return isinstance(x, float) or (isinstance(x, D.DArray) and not is_pending(x))
+
+    def gen(self, x, push):
+        if x is None:
+            x = 0.0
+        if isinstance(x, float):
+            self.emit(LD_CONST, self.const_idx(x), 1 if push else 0)
+            self.pushed(push)
+        elif is_pending(x):
+            if id(x) in self.tmp_slot:
+                self.emit(LD_TMP, self.tmp_slot[id(x)], 1 if push else 0)
+                self.pushed(push)
+                self.remaining[id(x)] -= 1
+                if self.remaining[id(x)] == 0:
+                    self.free_slots.append(self.tmp_slot[id(x)])
+            else:
+                self.gen_node(x, push)
+        else:
+            self.emit(LD_IN, self.leaf(x), 1 if push else 0)
+            self.pushed(push)
+
+    def gen_bin(self, bop, a, b, push):
+        bid = D.B[bop]
+        if self.simple(b):
+            self.gen(a, push)
+            if isinstance(b, float):
+                self.emit(BIN_CONST, bid, self.const_idx(b))
+            else:
+                self.emit(BIN_IN, bid, self.leaf(b))
+        elif self.simple(a):
+            self.gen(b, push)
+            if isinstance(a, float):
+                self.emit(BIN_CONST, bid, self.const_idx(a) | 0x80)
+            else:
+                self.emit(BIN_IN, bid, self.leaf(a) | 0x80)
+        else:
+            self.gen(a, push)
+            self.gen(b, True)
+            self.emit(BIN, bid)
+            self.depth -= 1
+
+    def gen_node(self, n, push):
+        k, a = n.kind, n.args
+        if k == "u":
+            self.gen(a[0], push)
+            self.emit(UNARY, D.U[n.op])
+        elif k == "b":
+            self.gen_bin(n.op, a[0], a[1], push)
+        elif k == "ug":
+            self.gen(a[0], push)
+            self.gen(a[1], True)
+            self.gen(a[2], True)
+            self.emit(UGRAD, D.U[n.op])
+            self.depth -= 2
+        elif k == "bb":
+            named = {"dy": a[0], "x1": a[1], "x2": a[2], "y": a[3]}
+            form = _bb_form(*n.op)
+            if form[0] == "binc":
+                self.gen_bin(form[1], named["dy"], form[2], push)
+            elif form[0] == "bin":
+                self.gen_bin(form[1], named["dy"], named[form[2]], push)
+            else:
+                self.gen(named["dy"], push)
+                self.gen(named[form[2]], True)
+                self.gen(named[form[3]], True)
+                self.emit(TERN, form[1])
+                self.depth -= 2
+        else:                                   # "fill" / "id": a constant or a broadcast operand as is
+            self.gen(a[0], push)
+
+    def run(self, anchors):
+        code = self.code
+        for n in anchors:
+            self.depth = 0
+            self.gen_node(n, False)
+            if n in self.outputs:
+                self.emit(STORE, self.outputs.index(n))
+            u = self.uses.get(id(n), 0)
+            if u > 0:
+                if not self.free_slots:
+                    raise _TooBig("slots", self.ext_ids)
+                s = max(self.free_slots)
+                self.free_slots.remove(s)
+                self.tmp_slot[id(n)], self.remaining[id(n)] = s, u
+                self.emit(ST_TMP, s)
+        # peephole: "ST_TMP s; LD_TMP s (overwrite)" with no later load of s -- the value is already on top
+        k = 0
+        while k + 1 < len(code):
+            a_, b_ = code[k], code[k + 1]
+            if (a_ & 0xff) == ST_TMP and b_ == (LD_TMP | (a_ & 0xff00)):
+                slot = (a_ >> 8) & 0xff
+                later = False
+                for c in code[k + 2:]:
+                    if (c & 0xff) == ST_TMP and ((c >> 8) & 0xff) == slot:
+                        break
+                    if (c & 0xff) == LD_TMP and ((c >> 8) & 0xff) == slot:
+                        later = True
+                        break
+                if not later:
+                    del code[k:k + 2]
+                    continue
+            k += 1
+        used_slots = {(c >> 8) & 0xff for c in code if (c & 0xff) in (ST_TMP, LD_TMP)}
+        lowest_tmp = min(used_slots) if used_slots else SLOTS
+        if len(code) > MAXCODE or self.maxdepth > lowest_tmp:
+            raise _TooBig("code" if len(code) > MAXCODE else "slots", self.ext_ids)
+
+
 def _run_fused(order, root):
     S = root.shape
     n_elem = D._prod(S)
@@ -323,145 +474,10 @@ def _run_fused(order, root):
             o._set_storage(D.DArray.empty(S, dtype))
         return
 
-    code, consts, leaves, leaf_idx = [], [], [], {}
-    state = {"depth": 0, "maxdepth": 0}
-    tmp_slot, remaining, free_slots, used_slots = {}, {}, list(range(SLOTS - 1, -1, -1)), set()
-
-    def emit(op, a=0, b=0):
-        code.append(op | (a << 8) | (b << 16))
-
-    def const_idx(v):
-        for i, c in enumerate(consts):
-            if c == v and np.signbit(c) == np.signbit(v):
-                return i
-        if len(consts) >= MAXCONST:
-            raise _TooBig("constants", ext_ids)
-        consts.append(v)
-        return len(consts) - 1
-
-    def leaf(x):
-        i = leaf_idx.get(id(x))
-        if i is None:
-            if len(leaves) >= MAXIN:
-                raise _TooBig("inputs", ext_ids)
-            i = leaf_idx[id(x)] = len(leaves)
-            leaves.append(x)
-        return i
-
-    def pushed(push):
-        if push:
-            state["depth"] += 1
-            state["maxdepth"] = max(state["maxdepth"], state["depth"])
-
-    def simple(x):
-        return isinstance(x, float) or (isinstance(x, D.DArray) and not is_pending(x))
-
-    def gen(x, push):
-        if x is None:
-            x = 0.0
-        if isinstance(x, float):
-            emit(LD_CONST, const_idx(x), 1 if push else 0)
-            pushed(push)
-        elif is_pending(x):
-            if id(x) in tmp_slot:
-                emit(LD_TMP, tmp_slot[id(x)], 1 if push else 0)
-                pushed(push)
-                remaining[id(x)] -= 1
-                if remaining[id(x)] == 0:
-                    free_slots.append(tmp_slot[id(x)])
-            else:
-                gen_node(x, push)
-        else:
-            emit(LD_IN, leaf(x), 1 if push else 0)
-            pushed(push)
-
-    def gen_bin(bop, a, b, push):
-        bid = D.B[bop]
-        if simple(b):
-            gen(a, push)
-            if isinstance(b, float):
-                emit(BIN_CONST, bid, const_idx(b))
-            else:
-                emit(BIN_IN, bid, leaf(b))
-        elif simple(a):
-            gen(b, push)
-            if isinstance(a, float):
-                emit(BIN_CONST, bid, const_idx(a) | 0x80)
-            else:
-                emit(BIN_IN, bid, leaf(a) | 0x80)
-        else:
-            gen(a, push)
-            gen(b, True)
-            emit(BIN, bid)
-            state["depth"] -= 1
-
-    def gen_node(n, push):
-        k, a = n.kind, n.args
-        if k == "u":
-            gen(a[0], push)
-            emit(UNARY, D.U[n.op])
-        elif k == "b":
-            gen_bin(n.op, a[0], a[1], push)
-        elif k == "ug":
-            gen(a[0], push)
-            gen(a[1], True)
-            gen(a[2], True)
-            emit(UGRAD, D.U[n.op])
-            state["depth"] -= 2
-        elif k == "bb":
-            named = {"dy": a[0], "x1": a[1], "x2": a[2], "y": a[3]}
-            form = _bb_form(*n.op)
-            if form[0] == "binc":
-                gen_bin(form[1], named["dy"], form[2], push)
-            elif form[0] == "bin":
-                gen_bin(form[1], named["dy"], named[form[2]], push)
-            else:
-                gen(named["dy"], push)
-                gen(named[form[2]], True)
-                gen(named[form[3]], True)
-                emit(TERN, form[1])
-                state["depth"] -= 2
-        elif k == "fill":
-            gen(a[0], push)
-        else:                                   # "id": broadcast of the operand to the iteration space
-            gen(a[0], push)
-
-    for n in anchors:
-        state["depth"] = 0
-        gen_node(n, False)
-        if n in outputs:
-            emit(STORE, outputs.index(n))
-        u = uses.get(id(n), 0)
-        if u > 0:
-            if not free_slots:
-                raise _TooBig("slots", ext_ids)
-            s = max(free_slots)
-            free_slots.remove(s)
-            tmp_slot[id(n)], remaining[id(n)] = s, u
-            used_slots.add(s)
-            emit(ST_TMP, s)
-    n = None
-    # peephole: "ST_TMP s; LD_TMP s (overwrite)" with no later load of s -- the value is already on top
-    k = 0
-    while k + 1 < len(code):
-        a_, b_ = code[k], code[k + 1]
-        if (a_ & 0xff) == ST_TMP and b_ == (LD_TMP | (a_ & 0xff00)):
-            slot = (a_ >> 8) & 0xff
-            later = False
-            for c in code[k + 2:]:
-                if (c & 0xff) == ST_TMP and ((c >> 8) & 0xff) == slot:
-                    break
-                if (c & 0xff) == LD_TMP and ((c >> 8) & 0xff) == slot:
-                    later = True
-                    break
-            if not later:
-                del code[k:k + 2]
-                continue
-        k += 1
-    used_slots = {(c >> 8) & 0xff for c in code if (c & 0xff) in (ST_TMP, LD_TMP)}
-    lowest_tmp = min(used_slots) if used_slots else SLOTS
-    if len(code) > MAXCODE or state["maxdepth"] > lowest_tmp:
-        raise _TooBig("code" if len(code) > MAXCODE else "slots", ext_ids)
+    cg = _Codegen(uses, outputs, ext_ids)
+    cg.run(anchors)
+    code, consts, leaves = cg.code, cg.consts, cg.leaves
+    cg = None
 
     # ---- operand layouts: full / scalar / row vector / column vector of a collapsed rows x cols space
     modes, imms, bc = [], [], []
@@ -503,5 +519,7 @@ def _run_fused(order, root):
                                nout, c_out, rows, cols))
     stats["fused_launches"] += 1
     stats["fused_nodes"] += len(order)
+    if trace is not None:
+        trace.append((n_elem, sum(1 for m in modes if m == M_FULL), nout, tuple(code)))
     for o, arr in zip(outputs, outs):
         o._set_storage(arr)

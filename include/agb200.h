@@ -189,7 +189,7 @@ ag_status ag_ewise_vm(int32_t dtype, const int32_t* code, int32_t ncode, const d
 /* Horizontal fusion of a chain of elementwise tape operations: the host runtime defers dotted
  * calls (src/core.jl:68-70 evaluates each one as its own Base broadcast pass), gradient rules (src/math.jl:9-74,
  * src/base.jl:20-49,73-74) and the dense `addto!` (src/addto.jl:23), and evaluates the whole expression DAG with ONE
- * launch: each leaf read once, each value the tape still holds written once (up to 4 outputs), temporaries never
+ * launch: each leaf read once, each value the tape still holds written once (up to 6 outputs), temporaries never
  * stored.  Iteration space rows x cols (column-major, n = rows*cols).  in_mode: 0 full array of n, 1 device scalar,
  * 2 immediate in_imm, 3 column vector (rows; broadcast along dim 2, e.g. a bias), 4 row vector (cols; broadcast along
  * dim 1, e.g. the softmax normaliser).  `code`: one int32 per instruction = op | a << 8 | b << 16, a stack machine
@@ -201,7 +201,7 @@ ag_status ag_ewise_vm(int32_t dtype, const int32_t* code, int32_t ncode, const d
  *   9 TERN a: q = top, p = pop(), dy = pop(); top = G_a(dy, p, q)      (0 ./ arg2, 1 max/min mask, 2 .^ arg1,
  *     3 .^ arg2, 4 atan arg1, 5 atan arg2, 6 hypot: the ternary maps of ag_binary_bwd)
  *   10 STORE: out[a] = top.
- * <= 96 instructions, 16 constants, 8 inputs, 4 outputs.  Every instruction evaluates the same expression as the
+ * <= 96 instructions, 16 constants, 8 inputs, 6 outputs.  Every instruction evaluates the same expression as the
  * corresponding single kernel, so results are bit-identical to the unfused sequence. */
 ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts, int32_t nconsts,
                          int32_t nin, const void* const* in, const int32_t* in_mode, const double* in_imm,
