@@ -57,7 +57,7 @@ class Clocks:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0=None, t1=None):
+    def stop(self, t0=None, t1=None, t_load=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -65,8 +65,8 @@ class Clocks:
         rows = [r for ts, r in self.rows if (t0 is None or ts >= t0 - 0.02) and (t1 is None or ts <= t1 + 0.02)]
         window = "timed region"
         if len(rows) < 3:       # the timed region is only a few ms: fall back to every sample taken under load
-            rows = [r for _, r in self.rows]
-            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
+            rows = [r for ts, r in self.rows if t_load is None or ts >= t_load]
+            window = "pre-load + timed region, all under load (timed region shorter than 3 sampling periods)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -153,6 +153,7 @@ def main():
     ag = ge.load_package()
     ag.init(local)
     Wl = ag.workloads
+    clocks = Clocks(local) if rank == 0 else None        # started early: nvidia-smi needs about a second before its first sample
 
     dist = None
     if world > 1:
@@ -250,13 +251,13 @@ def main():
             exchange()
             g_b.launch()
 
-    clocks = Clocks(local)
     for _ in range(W_):
         step()
     barrier()
 
     # ---- timed region: device-resident inputs (x = 205 MB > 126 MB L2, so no L2 flush needed)
-    for _ in range(200):          # keep the GPU under load while nvidia-smi takes its first samples
+    t_load0 = time.time()
+    for _ in range(2000):         # ~0.4 s under load before the timed region: nvidia-smi samples every 20 ms
         step()
     barrier()
     l0 = ag.launch_count()
@@ -271,7 +272,7 @@ def main():
     barrier()
     t_wall1 = time.time()
     launches = ag.launch_count() - l0
-    clk = clocks.stop(t_wall0, t_wall1)
+    clk = clocks.stop(t_wall0, t_wall1, t_load0) if clocks is not None else None
 
     # ---- forward / backward split (two graphs, events between them), N-independent
     #      (recorded on a tape, so the forward writes every value the backward sweep will read)
