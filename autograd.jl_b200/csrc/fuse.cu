@@ -39,7 +39,8 @@ enum {
   FZ_UGRAD = 8,      // y = top, x = pop(), dy = pop(): top = dy * g_a(x, y)
   FZ_TERN = 9,       // q = top, p = pop(), dy = pop(): top = G_a(dy, p, q)
   FZ_STORE = 10,     // out[a] = top
-  FZ_NOPS = 11
+  FZ_REDUCE = 11,    // the top is the operand of the fused sum (ag_ewise_fused_reduce); it stays on top
+  FZ_NOPS = 12
 };
 enum { FZ_M_FULL = 0, FZ_M_DEVSCALAR = 1, FZ_M_IMM = 2, FZ_M_COLVEC = 3, FZ_M_ROWVEC = 4 };
 
@@ -53,6 +54,13 @@ struct FzArgs {
   int32_t ncode, nin, nout, has_bcast;
   int64_t n, rows;
   int32_t zero;   // always 0, but only known at run time: see fz_opaque
+  // fused sum of the FZ_REDUCE operand (specialised kernels only)
+  int32_t rmode;  // 0 none, 1 whole array -> double partial per block, 2 contiguous runs of rlen -> final values,
+                  // 3 row sums of an rlen x (n/rlen) matrix -> rlen double partials per block
+  int32_t chunk;  // elements per block (a multiple of rlen for modes 2 and 3)
+  int32_t tps;    // mode 2: threads that share one run (power of two)
+  int64_t rlen;
+  void* rout;
 };
 
 #define FZ_CASE8(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
@@ -118,20 +126,34 @@ __device__ __forceinline__ void fz_store(const FzArgs& a, int o, int64_t i, cons
 // ---- general evaluator: bytecode interpreted at run time -------------------------------------------------
 // NI input register sets and NS slots are template parameters (2/2, 4/4, 8/8): the register budget decides how
 // many threads -- and so how many bytes in flight -- an SM holds, which is what bounds an elementwise kernel.
-template <typename T, bool VEC, int NI, int NS, int MINB>
+// UN vectors per thread share one decode of every instruction (the interpreter is issue-bound, not memory-bound).
+template <typename T, bool VEC, int NI, int NS, int UN, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_fused(const __grid_constant__ FzArgs a) {
-  constexpr int N = VEC ? Pack<T>::N : 1;
-  const int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * N;
-  if (i >= a.n) return;
-
-  int64_t c0[N], c1[N];
-  if (a.has_bcast) fz_coords<T, N>(a, i, c0, c1);
+  constexpr int NV = VEC ? Pack<T>::N : 1;        // elements per vector
+  constexpr int N = NV * UN;                      // lanes of this thread
+  const int64_t base = ((int64_t)blockIdx.x * (kThreads * UN) + threadIdx.x) * NV;
+  if (base >= a.n) return;
+  bool on[UN];
 
   // all leaf loads are issued before any arithmetic
   T inv[NI][N];
 #pragma unroll
-  for (int k = 0; k < NI; ++k)
-    if (k < a.nin) fz_load<T, N, VEC>(a, k, i, c0, c1, inv[k]);
+  for (int u = 0; u < UN; ++u) {
+    const int64_t i = base + (int64_t)u * kThreads * NV;
+    on[u] = i < a.n;
+    if (on[u]) {
+      int64_t c0[NV], c1[NV];
+      if (a.has_bcast) fz_coords<T, NV>(a, i, c0, c1);
+#pragma unroll
+      for (int k = 0; k < NI; ++k)
+        if (k < a.nin) fz_load<T, NV, VEC>(a, k, i, c0, c1, &inv[k][u * NV]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < NI; ++k)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) inv[k][u * NV + j] = T(0);
+    }
+  }
 
   T tos[N], S[NS][N];
 #pragma unroll
@@ -237,16 +259,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_fused(const __grid_constant_
         }
         break;
       }
-      case FZ_STORE:
-        switch (x) {
-          case 0: fz_store<T, N, VEC>(a, 0, i, tos); break;
-          case 1: fz_store<T, N, VEC>(a, 1, i, tos); break;
-          case 2: fz_store<T, N, VEC>(a, 2, i, tos); break;
-          case 3: fz_store<T, N, VEC>(a, 3, i, tos); break;
-          case 4: fz_store<T, N, VEC>(a, 4, i, tos); break;
-          default: fz_store<T, N, VEC>(a, 5, i, tos); break;
-        }
+      case FZ_STORE: {
+        const int o = x < FZ_MAXOUT ? x : FZ_MAXOUT - 1;
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          if (on[u]) fz_store<T, NV, VEC>(a, o, base + (int64_t)u * kThreads * NV, &tos[u * NV]);
         break;
+      }
     }
   }
 }
@@ -303,7 +322,8 @@ FZ_TERNSEL(0, GDiv2) FZ_TERNSEL(1, GEqMask) FZ_TERNSEL(2, GPow1) FZ_TERNSEL(3, G
 FZ_TERNSEL(5, GAtan2) FZ_TERNSEL(6, GHypot)
 
 template <int PROG, int PC, typename T, int N, int NIN, int NSL>
-__device__ __forceinline__ void fz_step(const FzArgs& a, int64_t i, const T (&inv)[NIN][N], T (&S)[NSL][N], T (&tos)[N]) {
+__device__ __forceinline__ void fz_step(const FzArgs& a, int64_t i, const T (&inv)[NIN][N], T (&S)[NSL][N], T (&tos)[N],
+                                        T* red_at, double& acc) {
   constexpr uint32_t w = kProgs[PROG].code[PC];
   constexpr int op = w & 0xff, x = (w >> 8) & 0xff, y = (w >> 16) & 0xff;
   constexpr int sp = fz_sp_before(kProgs[PROG], PC);
@@ -358,6 +378,12 @@ __device__ __forceinline__ void fz_step(const FzArgs& a, int64_t i, const T (&in
     }
   } else if constexpr (op == FZ_STORE) {
     fz_store<T, N, true>(a, x, i, tos);
+  } else if constexpr (op == FZ_REDUCE) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      red_at[j] = tos[j];
+      acc += (double)tos[j];
+    }
   }
   if constexpr (op == FZ_UNARY || op == FZ_BIN || op == FZ_BIN_IN || op == FZ_BIN_CONST || op == FZ_UGRAD ||
                 op == FZ_TERN) {
@@ -368,8 +394,55 @@ __device__ __forceinline__ void fz_step(const FzArgs& a, int64_t i, const T (&in
 
 template <int PROG, typename T, int N, int NIN, int NSL, int... PC>
 __device__ __forceinline__ void fz_run(const FzArgs& a, int64_t i, const T (&inv)[NIN][N], T (&S)[NSL][N], T (&tos)[N],
-                                       std::integer_sequence<int, PC...>) {
-  (fz_step<PROG, PC, T, N, NIN, NSL>(a, i, inv, S, tos), ...);
+                                       T* red_at, double& acc, std::integer_sequence<int, PC...>) {
+  (fz_step<PROG, PC, T, N, NIN, NSL>(a, i, inv, S, tos, red_at, acc), ...);
+}
+
+constexpr bool fz_has_reduce(const StaticProg& p) {
+  for (int i = 0; i < p.n; ++i)
+    if ((p.code[i] & 0xff) == FZ_REDUCE) return true;
+  return false;
+}
+
+// Sum epilogue of a specialised kernel: `red` holds the block's chunk of the FZ_REDUCE operand (zeros beyond the
+// data), `acc` this thread's own sum.  Fixed summation order throughout (deterministic), accumulation in double.
+template <typename T, int E>
+__device__ __forceinline__ void fz_reduce_epilogue(const FzArgs& a, const T* red, double acc) {
+  __shared__ double part[kThreads];
+  const int tid = threadIdx.x;
+  if (a.rmode == 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double r = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) r += part[w];
+      ((double*)a.rout)[blockIdx.x] = r;
+    }
+  } else if (a.rmode == 2) {
+    const int rlen = (int)a.rlen, nrun = a.chunk / rlen, tps = a.tps;
+    const int g = tid / tps, q = tid - g * tps;
+    double s = 0;
+    if (g < nrun)
+      for (int k = q; k < rlen; k += tps) s += (double)red[g * rlen + k];
+    part[tid] = s;
+    __syncthreads();
+    const int64_t run = (int64_t)blockIdx.x * nrun + g;
+    if (q == 0 && g < nrun && run * a.rlen < a.n) {
+      double r = 0;
+      for (int k = 0; k < tps; ++k) r += part[g * tps + k];
+      ((T*)a.rout)[run] = (T)r;
+    }
+  } else {
+    const int R = (int)a.rlen, ncol = a.chunk / R;
+    for (int r = tid; r < R; r += kThreads) {
+      double s = 0;
+      for (int c = 0; c < ncol; ++c) s += (double)red[r + R * c];
+      ((double*)a.rout)[(int64_t)blockIdx.x * R + r] = s;
+    }
+  }
 }
 
 constexpr int FZ_UN = 2;   // vectors per thread of a specialised kernel
@@ -379,27 +452,43 @@ __global__ void __launch_bounds__(kThreads) k_fused_static(const __grid_constant
   constexpr int N = Pack<T>::N;
   constexpr int NIN = kProgs[PROG].nin > 0 ? kProgs[PROG].nin : 1;
   constexpr int NSL = fz_slots_needed(kProgs[PROG]);
-  const int64_t base = ((int64_t)blockIdx.x * (kThreads * FZ_UN) + threadIdx.x) * N;
+  constexpr bool RED = fz_has_reduce(kProgs[PROG]);
+  constexpr int E = kThreads * FZ_UN * N;                       // elements a block can hold
+  __shared__ __align__(16) T red[RED ? E : 1];
+  const int chunk = RED ? a.chunk : E;                          // a reducing launch may use a shorter chunk
+  const int64_t blk0 = (int64_t)blockIdx.x * chunk;
   T inv[FZ_UN][NIN][N];
+  bool on[FZ_UN];
 #pragma unroll
   for (int u = 0; u < FZ_UN; ++u) {
-    const int64_t i = base + (int64_t)u * kThreads * N;
-    if (i < a.n) {
+    const int l = (u * kThreads + (int)threadIdx.x) * N;
+    const int64_t i = blk0 + l;
+    on[u] = l < chunk && i < a.n;
+    if (on[u]) {
       int64_t c0[N], c1[N];
       if (a.has_bcast) fz_coords<T, N>(a, i, c0, c1);
 #pragma unroll
       for (int k = 0; k < kProgs[PROG].nin; ++k) fz_load<T, N, true>(a, k, i, c0, c1, inv[u][k]);
     }
   }
+  double acc = 0;
 #pragma unroll
   for (int u = 0; u < FZ_UN; ++u) {
-    const int64_t i = base + (int64_t)u * kThreads * N;
-    if (i < a.n) {
+    const int l = (u * kThreads + (int)threadIdx.x) * N;
+    if (on[u]) {
       T tos[N], S[NSL][N];
 #pragma unroll
       for (int j = 0; j < N; ++j) tos[j] = T(0);
-      fz_run<PROG, T, N, NIN, NSL>(a, i, inv[u], S, tos, std::make_integer_sequence<int, kProgs[PROG].n>{});
+      fz_run<PROG, T, N, NIN, NSL>(a, blk0 + l, inv[u], S, tos, RED ? red + l : red, acc,
+                                   std::make_integer_sequence<int, kProgs[PROG].n>{});
+    } else if (RED) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) red[l + j] = T(0);
     }
+  }
+  if constexpr (RED) {
+    __syncthreads();
+    fz_reduce_epilogue<T, E>(a, red, acc);
   }
 }
 
@@ -425,9 +514,10 @@ static int find_static(const int32_t* code, int ncode) {
 
 template <typename T, bool VEC>
 static void launch_dynamic(int ni, int ns, const FzArgs& a, unsigned nb, cudaStream_t st) {
-  if (ni <= 2 && ns <= 2) k_fused<T, VEC, 2, 2, 4><<<nb, kThreads, 0, st>>>(a);
-  else if (ni <= 4 && ns <= 4) k_fused<T, VEC, 4, 4, 3><<<nb, kThreads, 0, st>>>(a);
-  else k_fused<T, VEC, 8, 8, 2><<<nb, kThreads, 0, st>>>(a);
+  // nb is given for one vector per thread
+  if (ni <= 2 && ns <= 2) k_fused<T, VEC, 2, 2, 2, 2><<<(nb + 1) / 2, kThreads, 0, st>>>(a);
+  else if (ni <= 4 && ns <= 4) k_fused<T, VEC, 4, 4, 1, 3><<<nb, kThreads, 0, st>>>(a);
+  else k_fused<T, VEC, 8, 8, 1, 2><<<nb, kThreads, 0, st>>>(a);
 }
 
 static int g_fused_static_enabled = -1;
@@ -449,25 +539,27 @@ extern "C" ag_status ag_ewise_fused_set_static(int32_t on) {
   return AG_OK;
 }
 
-extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts,
-                                    int32_t nconsts, int32_t nin, const void* const* in, const int32_t* in_mode,
-                                    const double* in_imm, int32_t nout, void* const* out, int64_t rows,
-                                    int64_t cols) {
+// r_out == nullptr: plain fused launch.  Otherwise the FZ_REDUCE operand (viewed as inner x red x outer, column-major)
+// is summed over `red` into r_out (inner*outer values), in the same launch plus one small combine kernel.
+static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts, int32_t nconsts,
+                            int32_t nin, const void* const* in, const int32_t* in_mode, const double* in_imm,
+                            int32_t nout, void* const* out, int64_t rows, int64_t cols, int64_t r_inner, int64_t r_red,
+                            int64_t r_outer, void* r_out) {
   AG_REQUIRE_INIT();
   AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_ewise_fused: dtype %d", dtype);
   AG_CHECK(code && ncode >= 1 && ncode <= FZ_MAXCODE, AG_EUNSUPPORTED, "ag_ewise_fused: program length %d (max %d)",
            ncode, FZ_MAXCODE);
-  AG_CHECK(nconsts >= 0 && nconsts <= FZ_MAXCONST && nin >= 0 && nin <= FZ_MAXIN && nout >= 1 && nout <= FZ_MAXOUT,
+  AG_CHECK(nconsts >= 0 && nconsts <= FZ_MAXCONST && nin >= 0 && nin <= FZ_MAXIN && nout >= (r_out ? 0 : 1) && nout <= FZ_MAXOUT,
            AG_EUNSUPPORTED, "ag_ewise_fused: %d constants / %d inputs / %d outputs (max %d / %d / %d)", nconsts, nin,
            nout, FZ_MAXCONST, FZ_MAXIN, FZ_MAXOUT);
   AG_CHECK(rows >= 0 && cols >= 0, AG_EINVAL, "ag_ewise_fused: negative extent");
-  AG_CHECK((nin == 0 || (in && in_mode && in_imm)) && out && (nconsts == 0 || consts), AG_EINVAL,
+  AG_CHECK((nin == 0 || (in && in_mode && in_imm)) && (out || nout == 0) && (nconsts == 0 || consts), AG_EINVAL,
            "ag_ewise_fused: null argument table");
   const int64_t n = rows * cols;
   if (n == 0) return AG_OK;
   FzArgs a;
   // validate the program: operand indices, slot bounds, stack discipline, every output written
-  int sp = 0, tmp_lo = FZ_SLOTS, ns_need = 1;
+  int sp = 0, tmp_lo = FZ_SLOTS, ns_need = 1, nreduce = 0;
   uint32_t stored = 0;
   for (int pc = 0; pc < ncode; ++pc) {
     const uint32_t w = (uint32_t)code[pc];
@@ -486,6 +578,7 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
       case FZ_BIN_CONST: AG_CHECK(x < AG_B_COUNT && (y & 0x7f) < nconsts, AG_EINVAL, "ag_ewise_fused: bad BIN_CONST at %d", pc); break;
       case FZ_TERN: AG_CHECK(x < 7, AG_EINVAL, "ag_ewise_fused: ternary map %d", x); break;
       case FZ_STORE: AG_CHECK(x < nout, AG_EINVAL, "ag_ewise_fused: output %d of %d", x, nout); stored |= 1u << x; break;
+      case FZ_REDUCE: ++nreduce; break;
     }
     if (op <= FZ_LD_TMP && y) ++sp;
     if (op == FZ_BIN) sp -= 1;
@@ -498,6 +591,7 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
     a.code[pc] = code[pc];
   }
   AG_CHECK(stored == (1u << nout) - 1u, AG_EINVAL, "ag_ewise_fused: an output is never stored");
+  AG_CHECK(nreduce == (r_out ? 1 : 0), AG_EINVAL, "ag_ewise_fused: %d REDUCE instructions", nreduce);
   for (int k = 0; k < nconsts; ++k) a.consts[k] = consts[k];
   bool vec = true;
   a.has_bcast = 0;
@@ -528,16 +622,61 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
     const char* e = getenv("AGB_FUSED_STATIC");
     g_fused_static_enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  bool done = false;
-  if (vec && g_fused_static_enabled) {
-    const int prog = find_static(code, ncode);
-    if (prog >= 0) {
-      const unsigned nbs = (unsigned)cdiv(n / N, (int64_t)kThreads * FZ_UN);
-      done = dtype == AG_F32 ? launch_static<float>(prog, a, nbs, c.stream) : launch_static<double>(prog, a, nbs, c.stream);
+  const int prog = (vec && g_fused_static_enabled) ? find_static(code, ncode) : -1;
+  a.rmode = 0;
+  a.chunk = kThreads * FZ_UN * N;
+  a.tps = 1;
+  a.rlen = 1;
+  a.rout = nullptr;
+  if (r_out) {
+    // the sum is fused only into specialised kernels, and only for layouts a block's chunk can cover
+    AG_CHECK(r_inner >= 1 && r_red >= 1 && r_outer >= 1 && r_inner * r_red * r_outer == n, AG_EINVAL,
+             "ag_ewise_fused_reduce: %lld x %lld x %lld is not %lld elements", (long long)r_inner, (long long)r_red,
+             (long long)r_outer, (long long)n);
+    AG_CHECK(prog >= 0, AG_EUNSUPPORTED, "ag_ewise_fused_reduce: no specialised kernel for this program");
+    const int E = a.chunk;
+    if (r_inner == 1 && r_outer == 1) {
+      a.rmode = 1;
+    } else if (r_inner == 1) {                       // contiguous runs of r_red
+      AG_CHECK(r_red <= E, AG_EUNSUPPORTED, "ag_ewise_fused_reduce: runs of %lld exceed a block", (long long)r_red);
+      int runs = (int)(E / r_red);
+      while (runs > 1 && (runs * r_red) % N) --runs;
+      AG_CHECK((runs * r_red) % N == 0 && runs <= kThreads, AG_EUNSUPPORTED, "ag_ewise_fused_reduce: run length %lld",
+               (long long)r_red);
+      a.rmode = 2;
+      a.chunk = (int)(runs * r_red);
+      a.rlen = r_red;
+      int tps = 1;
+      while (tps * 2 * runs <= kThreads && tps * 2 <= r_red) tps *= 2;
+      a.tps = tps;
+    } else {                                         // row sums: value is r_inner x r_red, r_outer == 1
+      AG_CHECK(r_outer == 1 && r_inner * 16 <= E, AG_EUNSUPPORTED,
+               "ag_ewise_fused_reduce: unsupported layout %lld x %lld x %lld", (long long)r_inner, (long long)r_red,
+               (long long)r_outer);
+      int colsb = (int)(E / r_inner);
+      while (colsb > 1 && (colsb * r_inner) % N) --colsb;
+      AG_CHECK((colsb * r_inner) % N == 0, AG_EUNSUPPORTED, "ag_ewise_fused_reduce: %lld rows", (long long)r_inner);
+      a.rmode = 3;
+      a.chunk = (int)(colsb * r_inner);
+      a.rlen = r_inner;
     }
   }
+  const int64_t nblk = cdiv(n, (int64_t)a.chunk);
+  double* part = nullptr;
+  if (a.rmode == 1 || a.rmode == 3) {
+    part = (double*)workspace(((size_t)nblk * (size_t)a.rlen + 64) * sizeof(double));
+    if (!part) return AG_ENOMEM;
+    a.rout = part;
+  } else if (a.rmode == 2) {
+    a.rout = r_out;
+  }
+  bool done = false;
+  if (prog >= 0)
+    done = dtype == AG_F32 ? launch_static<float>(prog, a, (unsigned)nblk, c.stream)
+                           : launch_static<double>(prog, a, (unsigned)nblk, c.stream);
   if (done) ++g_fused_hits; else ++g_fused_misses;
   if (!done) {
+    AG_CHECK(!r_out, AG_EUNSUPPORTED, "ag_ewise_fused_reduce: no specialised kernel for this program");
     const int64_t items = vec ? n / N : n;
     const unsigned nb = (unsigned)cdiv(items, kThreads);
     if (vec) {
@@ -549,5 +688,24 @@ extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t 
     }
   }
   AG_LAUNCHED();
+  if (part) return reduce_double_partials(dtype, part, nblk, a.rmode == 1 ? 1 : a.rlen, r_out);
   return AG_OK;
+}
+
+extern "C" ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts,
+                                    int32_t nconsts, int32_t nin, const void* const* in, const int32_t* in_mode,
+                                    const double* in_imm, int32_t nout, void* const* out, int64_t rows,
+                                    int64_t cols) {
+  return fused_impl(dtype, code, ncode, consts, nconsts, nin, in, in_mode, in_imm, nout, out, rows, cols, 0, 0, 0,
+                    nullptr);
+}
+
+extern "C" ag_status ag_ewise_fused_reduce(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts,
+                                           int32_t nconsts, int32_t nin, const void* const* in, const int32_t* in_mode,
+                                           const double* in_imm, int32_t nout, void* const* out, int64_t rows,
+                                           int64_t cols, int64_t r_inner, int64_t r_red, int64_t r_outer,
+                                           void* r_out) {
+  AG_CHECK(r_out, AG_EINVAL, "ag_ewise_fused_reduce: null result");
+  return fused_impl(dtype, code, ncode, consts, nconsts, nin, in, in_mode, in_imm, nout, out, rows, cols, r_inner,
+                    r_red, r_outer, r_out);
 }

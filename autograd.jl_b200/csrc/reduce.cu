@@ -429,6 +429,29 @@ static ag_status sum_dim_map(int32_t map, const void* x, int64_t inner, int64_t 
   return AG_EUNSUPPORTED;
 }
 
+// second phase of a sum fused into an elementwise kernel (fuse.cu): out[i] = sum_c part[c*inner + i].
+// `part` has room for 64 more doubles behind its nchunks*inner entries (second level of a long whole-array sum).
+ag_status reduce_double_partials(int dtype, const double* part, int64_t nchunks, int64_t inner, void* out) {
+  Context& c = ctx();
+  if (inner == 1) {
+    if (nchunks > 8192) {           // one block per 1/64th of the partials, then one block over the 64
+      double* lvl2 = const_cast<double*>(part) + nchunks;
+      k_seg_block<AG_R_ID, double, double><<<dim3(1, 64), kRT, 0, c.stream>>>(part, nchunks, cdiv(nchunks, 64), lvl2);
+      AG_LAUNCHED();
+      part = lvl2;
+      nchunks = 64;
+    }
+    if (dtype == AG_F32) k_seg_block<AG_R_ID, double, float><<<dim3(1, 1), kRT, 0, c.stream>>>(part, nchunks, nchunks, (float*)out);
+    else k_seg_block<AG_R_ID, double, double><<<dim3(1, 1), kRT, 0, c.stream>>>(part, nchunks, nchunks, (double*)out);
+  } else {
+    const dim3 grid((unsigned)cdiv(inner, 8), 1);
+    if (dtype == AG_F32) k_partials_reduce<float><<<grid, 256, 0, c.stream>>>(part, (int)nchunks, inner, (float*)out);
+    else k_partials_reduce<double><<<grid, 256, 0, c.stream>>>(part, (int)nchunks, inner, (double*)out);
+  }
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
 }  // namespace agb
 
 using namespace agb;

@@ -441,6 +441,10 @@ def _binary_bwd_eager(op, argno, dy, x1, x2, y):
 # ---- reductions -------------------------------------------------------------------------------------
 
 def sum_all(x, mapname="id"):
+    if x.size and _lazy.is_pending(x):
+        r = _lazy.reduce(x, 1, x.size, 1, mapname)
+        if r is not None:
+            return r.reshape(())
     x = materialize(x)
     out = DArray.empty((), x.dtype)
     if x.size == 0:
@@ -468,6 +472,11 @@ def sum_dims(x, dims, mapname="id"):
             j += 1
         runs.append((dims[i], dims[j]))
         i = j + 1
+    if len(runs) == 1 and _lazy.is_pending(x):
+        lo, hi = runs[0]
+        r = _lazy.reduce(x, _prod(shape[:lo]), _prod(shape[lo:hi + 1]), _prod(shape[hi + 1:]), mapname)
+        if r is not None:
+            return r.reshape(out_shape)
     cur, cur_shape, m = x, shape, mapname
     for lo, hi in runs:
         inner = _prod(cur_shape[:lo])

@@ -37,10 +37,11 @@ _RAW_BUF = D.DArray.__dict__["buf"]
 
 MAX_NODES = 24          # pending nodes per DAG before the largest argument is evaluated early
 MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 8, 6, 8
-LD_IN, LD_CONST, LD_TMP, ST_TMP, UNARY, BIN, BIN_IN, BIN_CONST, UGRAD, TERN, STORE = range(11)
+LD_IN, LD_CONST, LD_TMP, ST_TMP, UNARY, BIN, BIN_IN, BIN_CONST, UGRAD, TERN, STORE, REDUCE = range(12)
 M_FULL, M_DEVSCALAR, M_IMM, M_COLVEC, M_ROWVEC = range(5)
 
 enabled = [os.environ.get("AGB_FUSION", "1") != "0"]
+reduce_fusion = [os.environ.get("AGB_FUSE_REDUCE", "1") != "0"]   # sums of a pending chain in the chain's own launch
 stats = {"fused_launches": 0, "fused_nodes": 0, "fallback_nodes": 0, "splits": 0}
 trace = None            # set to a list to record (n elements, full-array inputs, outputs, program) of every fused launch
 _counter = itertools.count()
@@ -170,6 +171,28 @@ def bcast_to(a, shape):
 
 
 # ---- evaluation -------------------------------------------------------------------------------------------
+
+def reduce(x, inner, red, outer, mapname):
+    """sum(map, x) over the middle extent of x viewed as inner x red x outer, evaluated in the launch that evaluates
+    the pending chain x (src/unbroadcast.jl:17-24 and src/base.jl:245-247 without a second pass over x).  Returns a
+    flat DArray of inner*outer values, or None when the sum is not fused (the caller reduces the stored array)."""
+    if not (enabled[0] and reduce_fusion[0] and is_pending(x)) or red < 2:
+        return None
+    f32 = x.dtype == np.float32
+    E, N = (2048, 4) if f32 else (1024, 2)
+    if x.size % N or x.size != inner * red * outer:
+        return None
+    if not ((inner == 1 and (outer == 1 or red <= E)) or (outer == 1 and inner * 16 <= E)):
+        return None
+    order = _topo(x)
+    out = D.DArray.empty((inner * outer,), x.dtype)
+    try:
+        _run_fused(order, x, (inner, red, outer, mapname, out))
+    except (_TooBig, _NotFusable, UnsupportedOnDevice):
+        stats["unfused_reductions"] = stats.get("unfused_reductions", 0) + 1
+        return None
+    return out
+
 
 class _TooBig(Exception):
     """The DAG needs more inputs / outputs / instructions / slots than one launch has: evaluate arguments first."""
@@ -407,7 +430,7 @@ class _Codegen:
         else:                                   # "fill" / "id": a constant or a broadcast operand as is
             self.gen(a[0], push)
 
-    def run(self, anchors):
+    def run(self, anchors, reduce_map=None):
         code = self.code
         for n in anchors:
             self.depth = 0
@@ -422,6 +445,10 @@ class _Codegen:
                 self.free_slots.remove(s)
                 self.tmp_slot[id(n)], self.remaining[id(n)] = s, u
                 self.emit(ST_TMP, s)
+        if reduce_map is not None:              # the root (last anchor) is on top: sum it, or abs2 / abs of it
+            if reduce_map != "id":
+                self.emit(UNARY, D.U[reduce_map])
+            self.emit(REDUCE)
         # peephole: "ST_TMP s; LD_TMP s (overwrite)" with no later load of s -- the value is already on top
         k = 0
         while k + 1 < len(code):
@@ -445,7 +472,7 @@ class _Codegen:
             raise _TooBig("code" if len(code) > MAXCODE else "slots", self.ext_ids)
 
 
-def _run_fused(order, root):
+def _run_fused(order, root, reduce=None):
     S = root.shape
     n_elem = D._prod(S)
     dtype = root.dtype
@@ -475,7 +502,7 @@ def _run_fused(order, root):
         return
 
     cg = _Codegen(uses, outputs, ext_ids)
-    cg.run(anchors)
+    cg.run(anchors, None if reduce is None else reduce[3])
     code, consts, leaves = cg.code, cg.consts, cg.leaves
     cg = None
 
@@ -514,9 +541,15 @@ def _run_fused(order, root):
     c_in = (C.c_void_p * max(nin, 1))(*[x.ptr for x in leaves])
     c_mode = (C.c_int32 * max(nin, 1))(*modes)
     c_imm = (C.c_double * max(nin, 1))()
-    c_out = (C.c_void_p * nout)(*[o.ptr for o in outs])
-    check(D.lib.ag_ewise_fused(D._DT[dtype], c_code, len(code), c_consts, len(consts), nin, c_in, c_mode, c_imm,
-                               nout, c_out, rows, cols))
+    c_out = (C.c_void_p * max(nout, 1))(*[o.ptr for o in outs])
+    if reduce is None:
+        check(D.lib.ag_ewise_fused(D._DT[dtype], c_code, len(code), c_consts, len(consts), nin, c_in, c_mode, c_imm,
+                                   nout, c_out, rows, cols))
+    else:
+        check(D.lib.ag_ewise_fused_reduce(D._DT[dtype], c_code, len(code), c_consts, len(consts), nin, c_in, c_mode,
+                                          c_imm, nout, c_out, rows, cols, reduce[0], reduce[1], reduce[2],
+                                          C.c_void_p(reduce[4].ptr)))
+        stats["fused_reductions"] = stats.get("fused_reductions", 0) + 1
     stats["fused_launches"] += 1
     stats["fused_nodes"] += len(order)
     if trace is not None:

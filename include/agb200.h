@@ -207,6 +207,18 @@ ag_status ag_ewise_fused(int32_t dtype, const int32_t* code, int32_t ncode, cons
                          int32_t nin, const void* const* in, const int32_t* in_mode, const double* in_imm,
                          int32_t nout, void* const* out, int64_t rows, int64_t cols);
 
+/* The same launch followed by a sum of one of its values: unbroadcast(x, expr) = sum(expr; dims) (src/unbroadcast.jl:17-24),
+ * sum / sum(abs2,.) of a chain (src/base.jl:245-247) without a second pass over the data.  The program contains exactly
+ * one instruction 11 REDUCE (the top of stack at that point is the operand; nout may be 0).  The operand, viewed as
+ * r_inner x r_red x r_outer (column-major, = rows*cols elements), is summed over r_red into r_out (r_inner*r_outer
+ * values): whole array (1, n, 1), contiguous runs (1, red, outer) with red <= 2048, row sums (inner, red, 1) with
+ * inner <= 128.  Deterministic (fixed order, double accumulation).  AG_EUNSUPPORTED when the layout or the program has no
+ * specialised kernel -- the caller then evaluates the chain and reduces with ag_sum_dim. */
+ag_status ag_ewise_fused_reduce(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts,
+                                int32_t nconsts, int32_t nin, const void* const* in, const int32_t* in_mode,
+                                const double* in_imm, int32_t nout, void* const* out, int64_t rows, int64_t cols,
+                                int64_t r_inner, int64_t r_red, int64_t r_outer, void* r_out);
+
 /* Programs that the BASELINE configs produce are also instantiated ahead of time (csrc/fuse_static.inc, generated
  * by tools/gen_fused_programs.py) and picked by an exact match of `code`; on = 0 forces the general interpreter
  * kernel for every program (default 1, or environment AGB_FUSED_STATIC=0).  Results are identical either way. */

@@ -221,6 +221,26 @@ class FakeLib:
 
     def ag_ewise_fused(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols):
         """Stack machine of include/agb200.h `ag_ewise_fused` over a rows x cols column-major iteration space."""
+        st = self._fused(dtype, code, ncode, consts, nin, ins, modes, imms, outs, rows, cols)
+        return 0 if not isinstance(st, int) or st == 0 else st
+
+    def ag_ewise_fused_reduce(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols,
+                              r_inner, r_red, r_outer, r_out):
+        """... followed by the sum of the REDUCE operand over r_red of its (r_inner, r_red, r_outer) view."""
+        T = _DT[dtype]
+        E = 2048 if dtype == 0 else 1024
+        ok = (r_inner == 1 and (r_outer == 1 or r_red <= E)) or (r_outer == 1 and r_inner * 16 <= E)
+        if not ok or (rows * cols) % (4 if dtype == 0 else 2):
+            return self._fail(5, "ag_ewise_fused_reduce: unsupported layout")
+        v = self._fused(dtype, code, ncode, consts, nin, ins, modes, imms, outs, rows, cols)
+        if isinstance(v, int):
+            return v
+        self.launches += 0 if r_inner == 1 and r_outer > 1 else 1           # the combine kernel
+        v = np.broadcast_to(v, (rows, cols)).reshape(-1, order="F").reshape((r_inner, r_red, r_outer), order="F")
+        _arr(r_out, r_inner * r_outer, T)[:] = v.astype(np.float64).sum(axis=1).astype(T).reshape(-1, order="F")
+        return 0
+
+    def _fused(self, dtype, code, ncode, consts, nin, ins, modes, imms, outs, rows, cols):
         self.launches += 1
         T = _DT[dtype]
         n = rows * cols
@@ -238,7 +258,7 @@ class FakeLib:
                 2: lambda dy, p, q: dy * q * np.power(p, q - 1), 3: lambda dy, p, q: dy * p * np.log(q),
                 4: lambda dy, p, q: dy * q / (p * p + q * q), 5: lambda dy, p, q: dy * (-p) / (p * p + q * q),
                 6: lambda dy, p, q: dy * p / q}
-        S, tos, sp = [None] * 8, None, 0
+        S, tos, sp, reduced = [None] * 8, None, 0, None
         as_t = lambda v: np.asarray(v).astype(T)
         with np.errstate(all="ignore"):
             for pc in range(ncode):
@@ -266,9 +286,11 @@ class FakeLib:
                     tos = as_t(tern[x](S[sp], S[sp + 1], tos))
                 elif op == 10:
                     _arr(outs[x], n, T)[:] = np.broadcast_to(as_t(tos), (rows, cols)).reshape(-1, order="F")
+                elif op == 11:
+                    reduced = as_t(tos)
                 else:
                     return self._fail(1, "ag_ewise_fused: bad opcode")
-        return 0
+        return reduced if reduced is not None else 0
 
     # ---- input formats
     def ag_ubyte_to_float(self, dtype, src, dst, n, divisor):

@@ -13,10 +13,25 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture()
 def L(ag):
+    """Deferred evaluation on, sums NOT fused into their producers: a fused sum adds in another order than the
+    stand-alone reduction kernels, so only the elementwise part can be compared bit for bit."""
     lz = sys.modules["agb200.lazy"]
-    prev = lz.set_fusion(True)
+    prev, prev_r = lz.set_fusion(True), lz.reduce_fusion[0]
+    lz.reduce_fusion[0] = False
     yield lz
     lz.flush()
+    lz.reduce_fusion[0] = prev_r
+    lz.set_fusion(prev)
+
+
+@pytest.fixture()
+def LR(ag):
+    lz = sys.modules["agb200.lazy"]
+    prev, prev_r = lz.set_fusion(True), lz.reduce_fusion[0]
+    lz.reduce_fusion[0] = True
+    yield lz
+    lz.flush()
+    lz.reduce_fusion[0] = prev_r
     lz.set_fusion(prev)
 
 
@@ -284,3 +299,61 @@ def test_graph_capture_of_a_fused_step(ag, L):
         assert np.array_equal(a.value.to_numpy(), b.value.to_numpy())
     assert float(le) == float(lg)
     g.destroy()
+
+
+# ---- sums fused into the launch of the chain they reduce (ag_ewise_fused_reduce) ---------------------------------
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-6), (np.float64, 1e-14)])
+@pytest.mark.parametrize("shape", [(10, 4099), (64, 5000), (128, 300), (1024, 96), (7, 33), (2048, 5), (100, 64), (12,)])
+def test_fused_sums_against_float64(ag, LR, dtype, tol, shape):
+    """Whole-array sums, column sums (dims=1) and row sums (dims=2) of a pending chain, for the run lengths /
+    row counts of the configs (10, 64, 128, 1024) and awkward ones; reference = numpy in float64."""
+    D = sys.modules["agb200.darray"]
+    rng = np.random.default_rng(31)
+    x = np.asfortranarray(rng.standard_normal(shape).astype(dtype))
+    b = rng.standard_normal((shape[0],) + (1,) * (len(shape) - 1)).astype(dtype)
+    xd, bd = ag.DArray.from_numpy(x), ag.DArray.from_numpy(b)
+    chain = lambda: D.unary_fwd("tanh", D.binary_fwd("add", D.binary_fwd("mul", xd, 0.5), bd))
+    ref = np.tanh((x * dtype(0.5) + b).astype(dtype)).astype(np.float64)     # per-op rounding of the chain
+    f0 = LR.stats.get("fused_reductions", 0)
+    cases = [(None, "id", ref.sum()), (None, "abs2", (ref * ref).sum())]
+    if len(shape) == 2:
+        cases += [(0, "id", ref.sum(axis=0, keepdims=True)), (1, "id", ref.sum(axis=1, keepdims=True)),
+                  (1, "abs2", (ref * ref).sum(axis=1, keepdims=True))]
+    for dims, mp, want in cases:
+        y = chain()
+        f = {"id": ag.sum_, "abs2": ag.sumabs2}[mp]
+        got = f(y) if dims is None else f(y, dims=dims)
+        got = got.to_numpy().astype(np.float64)
+        scale = np.abs(ref).sum() if dims is None else np.abs(ref).sum(axis=dims, keepdims=True)
+        assert got.shape == np.asarray(want).shape
+        assert np.all(np.abs(got - want) <= tol * np.maximum(scale, 1e-30)), (dims, mp, shape)
+        # the chain's own value is still the chain's value (stored by the same launch)
+        assert np.allclose(y.to_numpy(), ref, rtol=2e-6 if dtype == np.float32 else 1e-13, atol=0)
+    if len(shape) == 2 and shape[0] * shape[1] % 4 == 0:
+        assert LR.stats.get("fused_reductions", 0) > f0, "no sum was fused for %s" % (shape,)
+
+
+@pytest.mark.parametrize("cfg", ["mnist", "sweep", "rnn", "lstm"])
+def test_whole_steps_with_fused_sums_within_tolerance(ag, LR, cfg):
+    W = ag.workloads
+    f0 = LR.stats.get("fused_reductions", 0)
+    rf, nf = _step_all(ag, W, cfg, True, LR)
+    assert LR.stats.get("fused_reductions", 0) > f0
+    ru, nu = _step_all(ag, W, cfg, False, LR)
+    for a, b in zip(rf, ru):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        assert np.max(np.abs(a - b)) <= 1e-5 * max(np.max(np.abs(b)), 1e-30)
+    assert nf < nu
+    print("%s: %d launches with fused sums, %d unfused" % (cfg, nf, nu))
+
+
+def test_fused_sum_is_deterministic(ag, LR):
+    D = sys.modules["agb200.darray"]
+    x = ag.DArray.from_numpy(np.asfortranarray(np.random.default_rng(5).standard_normal((64, 8192)).astype(np.float32)))
+    outs = []
+    for _ in range(3):
+        y = D.unary_fwd("exp", D.binary_fwd("mul", x, 0.1))
+        outs.append((float(ag.sum_(y)), ag.sum_(D.unary_fwd("exp", D.binary_fwd("mul", x, 0.1)), dims=1).to_numpy()))
+    assert outs[0][0] == outs[1][0] == outs[2][0]
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], outs[2][1])

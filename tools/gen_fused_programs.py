@@ -39,6 +39,24 @@ def main(out=OUT):
             ent["where"].add(CUR[0])
             return super().ag_ewise_fused(dtype, code, ncode, consts, nconsts, nin, *rest)
 
+        def ag_ewise_fused_reduce(self, dtype, code, ncode, consts, nconsts, nin, *rest):
+            st = super().ag_ewise_fused_reduce(dtype, code, ncode, consts, nconsts, nin, *rest)
+            if st == 0:                      # chains whose sum is fused into their own launch (instruction 11)
+                key = tuple(int(code[k]) & 0xffffffff for k in range(ncode))
+                ent = progs.setdefault(key, {"nin": nin, "count": 0, "where": set()})
+                ent["count"] += 1
+                ent["where"].add(CUR[0])
+                # the same chain without the fused sum: what runs when the layout of the sum is not fusable
+                # (e.g. row sums of a matrix with more than 128 rows), which depends on sizes, not on structure
+                plain = list(key[:-1])
+                if len(plain) >= 2 and (plain[-1] & 0xff) == 4 and (plain[-2] & 0xff) == 10:
+                    plain.pop()
+                if plain and (plain[-1] & 0xff) == 10:
+                    ent = progs.setdefault(tuple(plain), {"nin": nin, "count": 0, "where": set()})
+                    ent["count"] += 1
+                    ent["where"].add(CUR[0])
+            return st
+
         # stream capture on the stand-in: the step simply runs (only the sequence of programs matters here)
         def ag_graph_begin(self): return 0
         def ag_graph_end(self, ref): ref._obj.value = 1; return 0
@@ -54,6 +72,17 @@ def main(out=OUT):
     rng = np.random.default_rng(0)
 
     def sgd(loss, params, steps=2, lr=-0.05, clip=None):
+        for _ in range(steps):                  # the same step without reading the loss (tests/probe_*.py, user loops)
+            t = ag.diff(lambda: loss(params))
+            gs = [ag.grad(t, p) for p in params]
+            del t
+            for p, g in zip(params, gs):
+                ag.axpy(lr, g, p)
+            ag.sync()
+            t = ag.diff(lambda: loss(params))
+            gs = [ag.grad(t, p) for p in params]
+            ag.sync()
+            del t, gs
         for _ in range(steps):
             t = ag.diff(lambda: loss(params))
             float(ag.value(t))
@@ -108,6 +137,14 @@ def main(out=OUT):
                     h0, c0 = dev(np.zeros((H, B), dtype)), dev(np.zeros((H, B), dtype))
                     sgd(lambda p: W.lstm_loss(ag, dict(zip(keys, p)), ids, tg, h0, c0),
                         [ag.Param(dev(wd[k])) for k in keys], clip=5.0)
+                CUR[0] = "selftest"                                # the generic chain of tests/test_gpu_fusion.py
+                D = sys.modules["agb200.darray"]
+                xs_, bs_ = dev(rng.standard_normal((8, 12)).astype(dtype)), dev(rng.standard_normal((8, 1)).astype(dtype))
+                for f in (ag.sum_, ag.sumabs2):
+                    for dims in (None, 0, 1):
+                        y_ = D.unary_fwd("tanh", D.binary_fwd("add", D.binary_fwd("mul", xs_, 0.5), bs_))
+                        (f(y_) if dims is None else f(y_, dims=dims)).to_numpy()
+                        del y_
                 CUR[0] = "rnn"
                 H, V, B, T = 8, 6, 8, 3
                 w = W.rnn_init(rng, H, V, dtype)
