@@ -189,6 +189,20 @@ function ewise_fused!(outs::Vector{<:DArray{T}}, code::Vector{Int32}, consts::Ve
     outs
 end
 
+# ... and the variant that also sums the chain (sum(x; dims) / sum(abs2, x) of a pending x, src/unbroadcast.jl:17-24):
+# same arguments plus the (inner, red, outer) view of the operand and the result array; a MethodError-class status
+# (5) means "not fusable here" and the caller falls back to forcing x and calling ag_sum_dim.
+function ewise_fused_reduce!(r::DArray{T}, outs::Vector{<:DArray{T}}, code::Vector{Int32}, consts::Vector{Float64},
+                             ins::Vector{Ptr{Cvoid}}, modes::Vector{Int32}, imms::Vector{Float64}, rows::Integer,
+                             cols::Integer, inner::Integer, red::Integer, outer::Integer) where T
+    op = Ptr{Cvoid}[o.ptr for o in outs]
+    ccall((:ag_ewise_fused_reduce, LIB), Int32,
+          (Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Ptr{Float64}, Int32,
+           Ptr{Ptr{Cvoid}}, Int64, Int64, Int64, Int64, Int64, Ptr{Cvoid}),
+          dtcode(T), code, length(code), consts, length(consts), length(ins), ins, modes, imms, length(outs), op,
+          rows, cols, inner, red, outer, r.ptr)
+end
+
 # ---- minibatches in the dataset's byte format (examples/mnist.jl:80-81 rebuilt on the device) -------------
 function ubyte_batch!(x::DArray{T,2}, y::DArray{T,2}, px_dev::Ptr{Cvoid}, lb_dev::Ptr{Cvoid},
                       pixels::Array{UInt8}, labels::Vector{UInt8}) where T
