@@ -27,6 +27,7 @@ ag_status cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 void* workspace(size_t bytes);  // grows the shared workspace (not during graph capture)
 int32_t* oob_flag();            // sticky device flag raised by index checks; read and cleared by ag_sync
 
+bool reduce_scratch_init();     // reduce.cu: counters / second-level partials of the split combine (at ag_init)
 ag_status reduce_double_partials(int dtype, const double* part, int64_t nchunks, int64_t inner, void* out);  // reduce.cu
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -267,6 +267,87 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same combine when there are MANY chunks but only a few outputs (bias gradients: 64 outputs, 2048 chunks): the
+// grid above would be 8 blocks.  Here the chunk range is split over gridDim.z blocks; each writes its partial sums to
+// a second-level buffer and the LAST block to finish for an output tile (atomic ticket) adds those in a fixed order,
+// so the result does not depend on the schedule.  grid (ceil(inner/8), outer, Z).
+constexpr int kPRTiles = 1024, kPRZ = 16;
+static int32_t* g_pr_tickets = nullptr;     // kPRTiles tickets, zero between launches (the last block resets its own)
+static double* g_pr_lvl2 = nullptr;         // kPRTiles * kPRZ * 8 second-level partials
+
+bool reduce_scratch_init() {
+  if (g_pr_tickets) return true;
+  if (cudaMalloc((void**)&g_pr_tickets, kPRTiles * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc((void**)&g_pr_lvl2, (size_t)kPRTiles * kPRZ * 8 * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("out of device memory allocating the reduction scratch");
+    return false;
+  }
+  cudaMemset(g_pr_tickets, 0, kPRTiles * sizeof(int32_t));
+  return true;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+    k_partials_reduce_split(const double* __restrict__ part, int nchunks, int64_t inner, double* __restrict__ lvl2,
+                            int32_t* __restrict__ tickets, TO* __restrict__ out) {
+  __shared__ double sm[32][9];
+  __shared__ int last;
+  const int li = threadIdx.x % 8, g = threadIdx.x / 8, Z = gridDim.z, z = blockIdx.z;
+  const int64_t i = (int64_t)blockIdx.x * 8 + li, o = blockIdx.y;
+  const int tile = (int)(o * gridDim.x + blockIdx.x);
+  const int per = (nchunks + Z - 1) / Z, c0 = z * per, c1 = min(nchunks, c0 + per);
+  const double* __restrict__ p = part + o * nchunks * inner;
+  double s0 = 0, s1 = 0;
+  if (i < inner) {
+    int c = c0 + g;
+    for (; c + 7 * 32 < c1; c += 8 * 32) {           // 8 independent loads in flight
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(c + 32 * u) * inner + i];
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) { s0 += v[u]; s1 += v[u + 1]; }
+    }
+    for (; c < c1; c += 32) s0 += p[(int64_t)c * inner + i];
+  }
+  sm[g][li] = s0 + s1;
+  __syncthreads();
+  if (g == 0) {
+    double r = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) r += sm[q][li];
+    lvl2[((int64_t)tile * Z + z) * 8 + li] = r;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&tickets[tile], 1) == Z - 1;
+  __syncthreads();
+  if (last) {
+    if (g == 0 && i < inner) {
+      double r = 0;
+      for (int q = 0; q < Z; ++q) r += __ldcg(&lvl2[((int64_t)tile * Z + q) * 8 + li]);
+      out[o * inner + i] = (TO)r;
+    }
+    if (threadIdx.x == 0) tickets[tile] = 0;
+  }
+}
+
+// out[i,o] = sum_c part[o][c][i]: picks the split form when the plain grid would leave the GPU idle
+template <typename TO>
+static void launch_partials_reduce(const double* part, int64_t nchunks, int64_t inner, int64_t outer, TO* out) {
+  Context& c = ctx();
+  const int64_t tiles = cdiv(inner, 8) * outer;
+  if (tiles < 64 && tiles <= kPRTiles && nchunks >= 512 && g_pr_tickets) {
+    int Z = (int)(nchunks / 128);
+    if (Z > kPRZ) Z = kPRZ;
+    k_partials_reduce_split<TO><<<dim3((unsigned)cdiv(inner, 8), (unsigned)outer, (unsigned)Z), 256, 0, c.stream>>>(
+        part, (int)nchunks, inner, g_pr_lvl2, g_pr_tickets, out);
+  } else {
+    k_partials_reduce<TO><<<dim3((unsigned)cdiv(inner, 8), (unsigned)outer), 256, 0, c.stream>>>(part, (int)nchunks,
+                                                                                                  inner, out);
+  }
+}
+
 // Partials are kept in double in the workspace so the second phase loses nothing.
 template <int MAP, typename T>
 static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t outer, T* out) {
@@ -333,8 +414,7 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
     k_strided_vec<MAP, T, double><<<dim3((unsigned)outer, (unsigned)nchunks), kRT, 0, c.stream>>>(x, inner, red,
                                                                                                  rows, part);
     AG_LAUNCHED();
-    k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 8), (unsigned)outer), 256, 0, c.stream>>>(
-        part, (int)nchunks, inner, out);
+    launch_partials_reduce<T>(part, nchunks, inner, outer, out);
     AG_LAUNCHED();
     return AG_OK;
   }
@@ -377,8 +457,7 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
   // phase 2: partials (inner, nchunks, outer) -> out (inner, outer)
   AG_CHECK(outer <= 65535, AG_EUNSUPPORTED, "ag_sum_dim: outer extent %lld too large for a split reduction",
            (long long)outer);
-  k_partials_reduce<T><<<dim3((unsigned)cdiv(inner, 8), (unsigned)outer), 256, 0, c.stream>>>(part, (int)nchunks,
-                                                                                                inner, out);
+  launch_partials_reduce<T>(part, nchunks, inner, outer, out);
   AG_LAUNCHED();
   return AG_OK;
 }
@@ -444,9 +523,8 @@ ag_status reduce_double_partials(int dtype, const double* part, int64_t nchunks,
     if (dtype == AG_F32) k_seg_block<AG_R_ID, double, float><<<dim3(1, 1), kRT, 0, c.stream>>>(part, nchunks, nchunks, (float*)out);
     else k_seg_block<AG_R_ID, double, double><<<dim3(1, 1), kRT, 0, c.stream>>>(part, nchunks, nchunks, (double*)out);
   } else {
-    const dim3 grid((unsigned)cdiv(inner, 8), 1);
-    if (dtype == AG_F32) k_partials_reduce<float><<<grid, 256, 0, c.stream>>>(part, (int)nchunks, inner, (float*)out);
-    else k_partials_reduce<double><<<grid, 256, 0, c.stream>>>(part, (int)nchunks, inner, (double*)out);
+    if (dtype == AG_F32) launch_partials_reduce<float>(part, nchunks, inner, 1, (float*)out);
+    else launch_partials_reduce<double>(part, nchunks, inner, 1, (double*)out);
   }
   AG_LAUNCHED();
   return AG_OK;

@@ -208,6 +208,7 @@ ag_status ag_init(int32_t device) {
   AG_CUDA(cudaMemsetAsync(c.ws, 0, c.ws_bytes, c.stream));
   if (!oob_flag()) return AG_ENOMEM;   // allocate the sticky index-check flag outside of any capture
   g_oob_armed = false;
+  if (!reduce_scratch_init()) return AG_ENOMEM;
   c.launches = 0;
   c.capturing = false;
   c.ready = true;
