@@ -57,6 +57,7 @@ _SIGS = {
     "ag_ewise_fused": [i32, C.POINTER(i32), i32, C.POINTER(dbl), i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl), i32, C.POINTER(vp), i64, i64],
     "ag_ewise_fused_reduce": [i32, C.POINTER(i32), i32, C.POINTER(dbl), i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl), i32, C.POINTER(vp), i64, i64, i64, i64, i64, vp],
     "ag_ewise_fused_set_static": [i32],
+    "ag_ewise_fused_query": [C.POINTER(i32), i32, C.POINTER(i32)],
     "ag_ewise_fused_stats": [pi64],
     "ag_sum_all": [i32, i32, vp, i64, vp],
     "ag_sum_dim": [i32, i32, vp, i64, i64, i64, vp],

@@ -534,6 +534,16 @@ extern "C" ag_status ag_ewise_fused_stats(int64_t* out2) {
   return AG_OK;
 }
 
+extern "C" ag_status ag_ewise_fused_query(const int32_t* code, int32_t ncode, int32_t* is_static) {
+  if (!code || !is_static || ncode < 1) return AG_EINVAL;
+  if (g_fused_static_enabled < 0) {
+    const char* e = getenv("AGB_FUSED_STATIC");
+    g_fused_static_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  *is_static = (g_fused_static_enabled && find_static(code, ncode) >= 0) ? 1 : 0;
+  return AG_OK;
+}
+
 extern "C" ag_status ag_ewise_fused_set_static(int32_t on) {
   g_fused_static_enabled = on ? 1 : 0;
   return AG_OK;

@@ -36,12 +36,14 @@ _RAW_PTR = D.DArray.__dict__["ptr"]
 _RAW_BUF = D.DArray.__dict__["buf"]
 
 MAX_NODES = 24          # pending nodes per DAG before the largest argument is evaluated early
+BIG = 1 << 20           # elements from which a chain WITHOUT a specialised kernel is not handed to the interpreter
 MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 8, 6, 8
 LD_IN, LD_CONST, LD_TMP, ST_TMP, UNARY, BIN, BIN_IN, BIN_CONST, UGRAD, TERN, STORE, REDUCE = range(12)
 M_FULL, M_DEVSCALAR, M_IMM, M_COLVEC, M_ROWVEC = range(5)
 
 enabled = [os.environ.get("AGB_FUSION", "1") != "0"]
-reduce_fusion = [os.environ.get("AGB_FUSE_REDUCE", "1") != "0"]   # sums of a pending chain in the chain's own launch
+reduce_fusion = [os.environ.get("AGB_FUSE_REDUCE", "1") != "0"]
+static_only = [os.environ.get("AGB_FUSE_BIG_INTERPRETED", "0") == "0"]   # see BIG   # sums of a pending chain in the chain's own launch
 stats = {"fused_launches": 0, "fused_nodes": 0, "fallback_nodes": 0, "splits": 0}
 trace = None            # set to a list to record (n elements, full-array inputs, outputs, program) of every fused launch
 _counter = itertools.count()
@@ -198,6 +200,27 @@ class _TooBig(Exception):
     """The DAG needs more inputs / outputs / instructions / slots than one launch has: evaluate arguments first."""
 
 
+class _NotStatic(Exception):
+    """A large chain has no specialised kernel: evaluate its arguments as chains of their own, single operations
+    with the single kernels (the interpreter is issue-bound; it pays off only where launches dominate)."""
+
+
+_static_cache = {}
+
+
+def _is_static(code):
+    key = tuple(code)
+    r = _static_cache.get(key)
+    if r is None:
+        flag = C.c_int32(0)
+        c_code = (C.c_int32 * len(code))(*code)
+        check(D.lib.ag_ewise_fused_query(c_code, len(code), C.byref(flag)))
+        r = _static_cache[key] = bool(flag.value)
+        if len(_static_cache) > 4096:
+            _static_cache.clear()
+    return r
+
+
 class _NotFusable(Exception):
     """Some operand layout is not a full array, row vector, column vector or scalar of the iteration space."""
 
@@ -246,6 +269,16 @@ def force(root):
                 _run_eager([root])
                 return
             force(sub)
+            sub = None
+        except _NotStatic:
+            stats["big_unspecialised"] = stats.get("big_unspecialised", 0) + 1
+            sub = [a for a in root.args if is_pending(a)]
+            order = None
+            if not sub:
+                _run_eager([root])
+                return
+            for a in sub:
+                force(a)
             sub = None
         except _NotFusable:
             _run_eager(order)
@@ -505,6 +538,9 @@ def _run_fused(order, root, reduce=None):
     cg.run(anchors, None if reduce is None else reduce[3])
     code, consts, leaves = cg.code, cg.consts, cg.leaves
     cg = None
+    if reduce is None and n_elem >= BIG and static_only[0] and len(order) >= 1:
+        if n_elem % (4 if dtype == np.float32 else 2) or not _is_static(code):
+            raise _NotStatic()
 
     # ---- operand layouts: full / scalar / row vector / column vector of a collapsed rows x cols space
     modes, imms, bc = [], [], []

@@ -223,6 +223,10 @@ ag_status ag_ewise_fused_reduce(int32_t dtype, const int32_t* code, int32_t ncod
  * by tools/gen_fused_programs.py) and picked by an exact match of `code`; on = 0 forces the general interpreter
  * kernel for every program (default 1, or environment AGB_FUSED_STATIC=0).  Results are identical either way. */
 ag_status ag_ewise_fused_set_static(int32_t on);
+/* is_static = 1 when `code` has a specialised kernel.  The host uses it for GB-size arrays: a chain without one is
+ * evaluated as smaller chains / single kernels there, because the general interpreter is issue-bound (about 40 % of the
+ * memory roofline) and only pays off where launches, not bytes, dominate. */
+ag_status ag_ewise_fused_query(const int32_t* code, int32_t ncode, int32_t* is_static);
 /* out2[0] = launches that ran a specialised program, out2[1] = launches on the general interpreter. */
 ag_status ag_ewise_fused_stats(int64_t* out2);
 

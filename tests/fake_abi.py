@@ -215,6 +215,10 @@ class FakeLib:
     def ag_ewise_fused_set_static(self, on):
         return 0
 
+    def ag_ewise_fused_query(self, code, ncode, ref):
+        ref._obj.value = 1 if getattr(self, "all_static", True) else 0
+        return 0
+
     def ag_ewise_fused_stats(self, out2):
         out2[0], out2[1] = 0, 0
         return 0

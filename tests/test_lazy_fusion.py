@@ -223,6 +223,32 @@ def test_higher_order_through_deferred_rules(lz, oracle):
     assert np.allclose(g2.to_numpy(), r2, rtol=1e-12)
 
 
+def test_large_chain_without_specialised_kernel_uses_single_kernels(lz):
+    """From lazy.BIG elements on, a chain the library has no ahead-of-time kernel for is evaluated by the single
+    kernels (each at the memory roofline) instead of the issue-bound interpreter; small chains still fuse."""
+    ag, L, D = lz
+    lib = ag._lib.lib
+    lib.all_static = False
+    L._static_cache.clear()
+    try:
+        n = L.BIG
+        x = dev(ag, np.linspace(-1, 1, n).astype(np.float32).reshape(1024, n // 1024))
+        f0, e0, b0 = L.stats["fused_launches"], L.stats["fallback_nodes"], L.stats.get("big_unspecialised", 0)
+        y = D.unary_fwd("tanh", D.binary_fwd("mul", D.unary_fwd("exp", x), 0.5))
+        got = y.to_numpy()
+        assert L.stats["fused_launches"] == f0 and L.stats["fallback_nodes"] == e0 + 3
+        assert L.stats.get("big_unspecialised", 0) > b0
+        ref = np.tanh((np.exp(x.to_numpy()) * np.float32(0.5)).astype(np.float32)).astype(np.float32)
+        assert np.allclose(got, ref, rtol=1e-6)
+        small = dev(ag, np.ones((8, 8), np.float32))
+        z = D.unary_fwd("tanh", D.binary_fwd("mul", D.unary_fwd("exp", small), 0.5))
+        z.to_numpy()
+        assert L.stats["fused_launches"] == f0 + 1
+    finally:
+        lib.all_static = True
+        L._static_cache.clear()
+
+
 def test_specialised_program_list_is_up_to_date(agpkg):
     """csrc/fuse_static.inc must be what tools/gen_fused_programs.py generates from the current host logic
     (a stale list would silently send the configs' chains to the slower general interpreter)."""
