@@ -37,6 +37,9 @@ _SIGS = {
     "ag_host_alloc": [i64, C.POINTER(vp)],
     "ag_host_free": [vp],
     "ag_copy_h2d": [vp, vp, i64],
+    "ag_copy_h2d_prefetch": [vp, vp, i64],
+    "ag_prefetch_wait": [],
+    "ag_prefetch_release": [],
     "ag_copy_d2h": [vp, vp, i64],
     "ag_copy_d2h_async": [vp, vp, i64],
     "ag_copy_d2d": [vp, vp, i64],

@@ -42,7 +42,10 @@ enum {
   FZ_REDUCE = 11,    // the top is the operand of the fused sum (ag_ewise_fused_reduce); it stays on top
   FZ_NOPS = 12
 };
-enum { FZ_M_FULL = 0, FZ_M_DEVSCALAR = 1, FZ_M_IMM = 2, FZ_M_COLVEC = 3, FZ_M_ROWVEC = 4 };
+enum { FZ_M_FULL = 0, FZ_M_DEVSCALAR = 1, FZ_M_IMM = 2, FZ_M_COLVEC = 3, FZ_M_ROWVEC = 4,
+       // internal (set by the host side below when rows % lanes == 0: a vector never straddles two columns)
+       FZ_M_COLVEC_V = 5,   // the lanes are consecutive rows: one aligned vector load
+       FZ_M_ROWVEC_1 = 6 }; // the lanes share their column: one scalar load
 
 struct FzArgs {
   int32_t code[FZ_MAXCODE];
@@ -97,6 +100,14 @@ __device__ __forceinline__ void fz_load(const FzArgs& a, int k, int64_t i, const
     } else {
       dst[0] = p[i];
     }
+  } else if (VEC && m == FZ_M_COLVEC_V) {
+    const Pack<T> t = *reinterpret_cast<const Pack<T>*>(p + c0[0]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = t.v[j];
+  } else if (m == FZ_M_ROWVEC_1) {
+    const T t = p[c1[0]];
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = t;
   } else if (m == FZ_M_COLVEC) {
 #pragma unroll
     for (int j = 0; j < N; ++j) dst[j] = p[c0[j]];
@@ -631,6 +642,12 @@ static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, c
   if (g_fused_static_enabled < 0) {
     const char* e = getenv("AGB_FUSED_STATIC");
     g_fused_static_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (vec && a.has_bcast && a.rows % N == 0) {
+    for (int k = 0; k < nin; ++k) {
+      if (a.mode[k] == FZ_M_COLVEC && aligned16(a.in[k])) a.mode[k] = FZ_M_COLVEC_V;
+      else if (a.mode[k] == FZ_M_ROWVEC) a.mode[k] = FZ_M_ROWVEC_1;
+    }
   }
   const int prog = (vec && g_fused_static_enabled) ? find_static(code, ncode) : -1;
   a.rmode = 0;

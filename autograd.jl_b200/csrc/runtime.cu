@@ -337,6 +337,47 @@ ag_status ag_copy_h2d(void* dst, const void* src, int64_t bytes) {
   return AG_OK;
 }
 
+// ---- input prefetch on a second stream: the h2d copy of the NEXT batch overlaps the step on the current one ----
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_ev_ready = nullptr, g_ev_consumed = nullptr;
+
+static ag_status prefetch_init() {
+  if (g_copy_stream) return AG_OK;
+  AG_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+  AG_CUDA(cudaEventCreateWithFlags(&g_ev_ready, cudaEventDisableTiming));
+  AG_CUDA(cudaEventCreateWithFlags(&g_ev_consumed, cudaEventDisableTiming));
+  AG_CUDA(cudaEventRecord(g_ev_consumed, ctx().stream));
+  return AG_OK;
+}
+
+ag_status ag_copy_h2d_prefetch(void* dst, const void* src, int64_t bytes) {
+  AG_REQUIRE_INIT();
+  if (bytes == 0) return AG_OK;
+  AG_CHECK(dst && src && bytes > 0, AG_EINVAL, "ag_copy_h2d_prefetch: bad arguments");
+  ag_status st = prefetch_init();
+  if (st != AG_OK) return st;
+  AG_CUDA(cudaStreamWaitEvent(g_copy_stream, g_ev_consumed, 0));     // the staging buffer's last reader is done
+  AG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, g_copy_stream));
+  AG_CUDA(cudaEventRecord(g_ev_ready, g_copy_stream));
+  return AG_OK;
+}
+
+ag_status ag_prefetch_wait(void) {
+  AG_REQUIRE_INIT();
+  ag_status st = prefetch_init();
+  if (st != AG_OK) return st;
+  AG_CUDA(cudaStreamWaitEvent(ctx().stream, g_ev_ready, 0));
+  return AG_OK;
+}
+
+ag_status ag_prefetch_release(void) {
+  AG_REQUIRE_INIT();
+  ag_status st = prefetch_init();
+  if (st != AG_OK) return st;
+  AG_CUDA(cudaEventRecord(g_ev_consumed, ctx().stream));
+  return AG_OK;
+}
+
 ag_status ag_copy_d2h_async(void* dst, const void* src, int64_t bytes) {
   AG_REQUIRE_INIT();
   if (bytes == 0) return AG_OK;

@@ -54,7 +54,21 @@ class UByteBatch:
     def h2d_bytes(self):
         return self.nfeat * self.ncols + self.ncols
 
-    def load(self, pixels, labels):
+    def prefetch(self, pixels, labels):
+        """Start copying the NEXT batch's bytes on the copy stream (they land in the staging buffers while the step
+        on the current batch runs); `convert()` then rebuilds `x` and `y` from them on the main stream."""
+        pixels, labels = self._check(pixels, labels)
+        check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(self._px.ptr), C.c_void_p(pixels.ctypes.data), pixels.size))
+        check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(self._lb.ptr), C.c_void_p(labels.ctypes.data), labels.size))
+
+    def convert(self):
+        _lazy.flush()                                   # pending operations must read the previous batch first
+        check(D.lib.ag_prefetch_wait())
+        self._convert()
+        check(D.lib.ag_prefetch_release())
+        return self.x, self.y
+
+    def _check(self, pixels, labels):
         pixels, labels = np.asarray(pixels), np.asarray(labels)
         if pixels.dtype != np.uint8 or labels.dtype != np.uint8:
             raise TypeError("UByteBatch.load takes uint8 arrays")
@@ -63,10 +77,38 @@ class UByteBatch:
                                     % (pixels.shape, labels.shape, self.nfeat, self.ncols))
         if not (pixels.flags.f_contiguous or pixels.flags.c_contiguous and pixels.ndim == 1):
             pixels = np.asfortranarray(pixels)
+        return pixels, labels
+
+    def load(self, pixels, labels):
+        pixels, labels = self._check(pixels, labels)
         _lazy.flush()                                   # pending operations must read the previous batch first
         check(D.lib.ag_copy_h2d(C.c_void_p(self._px.ptr), C.c_void_p(pixels.ctypes.data), pixels.size))
         check(D.lib.ag_copy_h2d(C.c_void_p(self._lb.ptr), C.c_void_p(labels.ctypes.data), labels.size))
+        self._convert()
+        return self.x, self.y
+
+    def _convert(self):
         check(D.lib.ag_ubyte_to_float(self.x.dt, C.c_void_p(self._px.ptr), D.vptr(self.x), self.x.size, self.divisor))
         check(D.lib.ag_onehot_labels(self.y.dt, C.c_void_p(self._lb.ptr), self.ncols, self.nclass, self.zero_to,
                                      D.vptr(self.y)))
-        return self.x, self.y
+
+
+class StagedInput:
+    """Double-buffered host -> device feed for arrays a captured step graph reads at fixed addresses: `prefetch`
+    copies the NEXT batch from pinned host memory into staging buffers on the copy stream while the current step
+    runs; `commit` moves it into the live arrays (device-to-device, on the main stream)."""
+
+    def __init__(self, *arrays):
+        self.arrays = arrays
+        self.stage = [D._Buffer(max(a.nbytes, 16)) for a in arrays]
+
+    def prefetch(self, *host_ptrs):
+        for a, st, hp in zip(self.arrays, self.stage, host_ptrs):
+            check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(st.ptr), C.c_void_p(int(hp)), a.nbytes))
+
+    def commit(self):
+        _lazy.flush()
+        check(D.lib.ag_prefetch_wait())
+        for a, st in zip(self.arrays, self.stage):
+            check(D.lib.ag_copy_d2d(D.vptr(a), C.c_void_p(st.ptr), a.nbytes))
+        check(D.lib.ag_prefetch_release())

@@ -131,6 +131,14 @@ ag_status ag_pool_trim(void);
 ag_status ag_host_alloc(int64_t bytes, void** ptr_out);
 ag_status ag_host_free(void* ptr);
 ag_status ag_copy_h2d(void* dst_dev, const void* src_host, int64_t bytes); /* async on the stream */
+/* Input prefetch (the `minibatch` loop of examples/mnist.jl:96-106 feeds one batch per step): the copy runs on a second
+ * stream so that the NEXT batch crosses PCIe while the step on the current one executes.  ag_copy_h2d_prefetch waits
+ * (on the device) until the previous contents of the staging buffer were released, then copies; ag_prefetch_wait makes
+ * the main stream wait for the prefetched data; ag_prefetch_release (after the consumer of the staging buffer has been
+ * enqueued) lets the next prefetch overwrite it.  src must be pinned (ag_host_alloc) for the copy to be asynchronous. */
+ag_status ag_copy_h2d_prefetch(void* dst_dev, const void* src_host, int64_t bytes);
+ag_status ag_prefetch_wait(void);
+ag_status ag_prefetch_release(void);
 ag_status ag_copy_d2h(void* dst_host, const void* src_dev, int64_t bytes); /* blocks until done */
 ag_status ag_copy_d2h_async(void* dst_host, const void* src_dev, int64_t bytes);
 ag_status ag_copy_d2d(void* dst_dev, const void* src_dev, int64_t bytes);  /* copy(x), src/base.jl:338 */

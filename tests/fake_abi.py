@@ -114,7 +114,11 @@ class FakeLib:
         C.memmove(_p(dst), _p(src), int(nbytes))
         return 0
 
-    ag_copy_h2d = ag_copy_d2h = ag_copy_d2h_async = ag_copy_d2d = _copy
+    ag_copy_h2d = ag_copy_d2h = ag_copy_d2h_async = ag_copy_d2d = ag_copy_h2d_prefetch = _copy
+
+    def ag_prefetch_wait(self): return 0
+
+    def ag_prefetch_release(self): return 0
 
     def ag_fill(self, dst, n, dtype, v):
         _arr(dst, n, _DT[dtype])[:] = v

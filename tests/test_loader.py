@@ -75,6 +75,46 @@ def test_device_conversions_match_the_oracle_bit_for_bit(ag, oracle, dtype, nfea
 
 
 @pytest.mark.gpu
+def test_prefetched_batches_arrive_in_order(ag, oracle):
+    """prefetch (copy stream) / convert (main stream): batch i+1 crosses PCIe while batch i is in use, and every
+    batch still reaches the device arrays intact and in order; same for Float32 arrays through StagedInput."""
+    rng = np.random.default_rng(8)
+    nfeat, ncols, nb = 784, 2048, 6
+    hosts = []
+    for _ in range(nb):
+        px, lb = ag.pinned_empty((nfeat, ncols), np.uint8), ag.pinned_empty((ncols,), np.uint8)
+        p, l = _batch(rng, nfeat, ncols)
+        px[...] = p
+        lb[...] = l
+        hosts.append((px, lb))
+    b = ag.UByteBatch(nfeat, ncols)
+    b.prefetch(*hosts[0])
+    sums = []
+    for i in range(nb):
+        x, y = b.convert()
+        if i + 1 < nb:
+            b.prefetch(*hosts[i + 1])                  # overlaps the "step" below
+        sums.append((ag.sumabs2(ag.matmul(y, ag.adjoint(x))), x.to_numpy() if i in (0, nb - 1) else None))
+    for i, (s_, xs) in enumerate(sums):
+        xr, yr = oracle.xshape(hosts[i][0]), oracle.yshape(hosts[i][1])
+        ref = float(np.sum((yr.astype(np.float64) @ xr.astype(np.float64).T) ** 2))
+        assert abs(float(s_) - ref) <= 1e-5 * ref
+        if xs is not None:
+            assert np.array_equal(xs, xr)
+    xf = [ag.pinned_empty((64, 512), np.float32) for _ in range(3)]
+    for k, h in enumerate(xf):
+        h[...] = rng.standard_normal((64, 512)).astype(np.float32) + k
+    xd = ag.DArray.empty((64, 512), np.float32)
+    st = ag.StagedInput(xd)
+    st.prefetch(xf[0].host_ptr)
+    for k in range(3):
+        st.commit()
+        if k + 1 < 3:
+            st.prefetch(xf[k + 1].host_ptr)
+        assert np.array_equal(xd.to_numpy(), np.asarray(xf[k]))
+
+
+@pytest.mark.gpu
 def test_bad_label_raises_the_sticky_flag(ag):
     b = ag.UByteBatch(4, 3)
     b.load(np.zeros((4, 3), np.uint8), np.array([1, 200, 3], np.uint8))
