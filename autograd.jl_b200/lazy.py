@@ -256,33 +256,43 @@ def force(root):
     """Evaluate `root` (and every pending node below it that something else refers to)."""
     while root.kind is not None:
         order = _topo(root)
+        action, ext = None, None
         try:
             _run_fused(order, root)
             return
         except _TooBig as why:
-            stats["splits"] += 1
-            key = "split_" + (why.args[0] if why.args else "?")
-            stats[key] = stats.get(key, 0) + 1
-            sub = _pick_split(order, root, why.args[1] if len(why.args) > 1 else set())
-            order = None
-            if sub is None:                     # a single operation always fits; defensive
-                _run_eager([root])
-                return
-            force(sub)
-            sub = None
+            action, ext = "split:" + (why.args[0] if why.args else "?"), (why.args[1] if len(why.args) > 1 else set())
         except _NotStatic:
+            action = "unspecialised"
+        except _NotFusable:
+            action = "eager"
+        # The handlers only take notes: while an exception is being handled its traceback keeps the frames of
+        # _run_fused alive, and with them lists that refer to every node of the DAG -- every node would look
+        # externally referenced to the nested force() calls below and be written out.
+        if action == "eager":
+            _run_eager(order)
+            return
+        if action == "unspecialised":
             stats["big_unspecialised"] = stats.get("big_unspecialised", 0) + 1
-            sub = [a for a in root.args if is_pending(a)]
             order = None
+            sub = [a for a in root.args if is_pending(a)]
             if not sub:
                 _run_eager([root])
                 return
             for a in sub:
                 force(a)
-            sub = None
-        except _NotFusable:
-            _run_eager(order)
+            a = sub = None
+            continue
+        stats["splits"] += 1
+        key = "split_" + action[6:]
+        stats[key] = stats.get(key, 0) + 1
+        sub = _pick_split(order, root, ext)
+        order = ext = None
+        if sub is None:                     # a single operation always fits; defensive
+            _run_eager([root])
             return
+        force(sub)
+        sub = None
 
 
 def _pick_split(order, root, ext):

@@ -24,7 +24,7 @@ import __graft_entry__ as ge  # noqa: E402
 import fake_abi  # noqa: E402
 
 OUT = os.path.join(ROOT, "autograd.jl_b200", "csrc", "fuse_static.inc")
-MAX_STATIC = 96
+MAX_STATIC = 160
 
 
 def main(out=OUT):
@@ -122,10 +122,10 @@ def main(out=OUT):
                 xd = dev(x)
                 sgd(lambda p: W.sweep_loss(ag, xd, p[0], p[1]), [ag.Param(dev(a)) for a in (brow, bcol)])
                 CUR[0] = "charlm"
-                H, E, V, B, T = 16, 8, 12, 8, 3
+                H, E, V, B = 16, 8, 12, 8
                 wd = W.lstm_init(rng, H, E, V, dtype)
                 keys = list(wd)
-                for dev_ids in (False, True):
+                for dev_ids, T in ((False, 3), (True, 3), (True, 10)):   # long sequences: gradient-accumulation chains
                     ids = [rng.integers(0, V, B) for _ in range(T)]
                     if dev_ids:
                         ids = [ag.IArray(i) for i in ids]
