@@ -201,12 +201,13 @@ __global__ void __launch_bounds__(kRT)
 // kernel above would run two blocks that each walk all rows.  Here a block owns 32 consecutive i (one 128-byte
 // run per row) and its 8 warps take rows w, w+8, ... with 8 loads in flight; fixed-order combine (deterministic).
 // grid (outer, 1, ceil(inner/32)), ONE launch.
-template <int MAP, typename T, typename TI, typename TO>
+template <int MAP, int LW, typename T, typename TI, typename TO>
 __global__ void __launch_bounds__(256)
     k_strided_tile(const TI* __restrict__ x, int64_t inner, int64_t red, TO* __restrict__ out) {
-  __shared__ double sm[8][33];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t i = (int64_t)blockIdx.z * 32 + lane, o = blockIdx.x;
+  constexpr int G = 256 / LW;                    // row groups of the block: group w takes rows w, w+G, ...
+  __shared__ double sm[G][LW + 1];
+  const int lane = threadIdx.x % LW, w = threadIdx.x / LW;
+  const int64_t i = (int64_t)blockIdx.z * LW + lane, o = blockIdx.x;
   double s = 0;
   if (i < inner) {
     const TI* __restrict__ p = x + o * inner * red + i;
@@ -214,14 +215,14 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int u = 0; u < 8; ++u) a[u] = T(0);
     int64_t r = w;
-    for (; r + 56 < red; r += 64) {
+    for (; r + 7 * G < red; r += 8 * G) {
       T v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = (T)p[(r + 8 * u) * inner];
+      for (int u = 0; u < 8; ++u) v[u] = (T)p[(r + G * u) * inner];
 #pragma unroll
       for (int u = 0; u < 8; ++u) a[u] += premap<MAP>(v[u]);
     }
-    for (; r < red; r += 8) a[0] += premap<MAP>((T)p[r * inner]);
+    for (; r < red; r += G) a[0] += premap<MAP>((T)p[r * inner]);
     s = (((double)a[0] + (double)a[1]) + ((double)a[2] + (double)a[3])) +
         (((double)a[4] + (double)a[5]) + ((double)a[6] + (double)a[7]));
   }
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(256)
   if (w == 0 && i < inner) {
     double r = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) r += sm[q][lane];
+    for (int q = 0; q < G; ++q) r += sm[q][lane];
     out[o * inner + i] = (TO)r;
   }
 }
@@ -436,9 +437,15 @@ static ag_status sum_dim_impl(const T* x, int64_t inner, int64_t red, int64_t ou
   if (nchunks == 1) {
     if (small)
       k_strided_small<MAP, T, T, T><<<dim3((unsigned)outer, 1), kRT, 0, c.stream>>>(x, inner, red, rows, out);
-    else if (red >= 16 && cdiv(inner, 32) <= 65535)
-      k_strided_tile<MAP, T, T, T><<<dim3((unsigned)outer, 1, (unsigned)cdiv(inner, 32)), 256, 0, c.stream>>>(
-          x, inner, red, out);
+    else if (red >= 16 && cdiv(inner, 16) <= 65535) {
+      // 16-lane tiles (64-byte runs, twice the blocks) while the grid is small, 32-lane tiles otherwise
+      if (outer * cdiv(inner, 32) < 2 * c.num_sms && red >= 32)
+        k_strided_tile<MAP, 16, T, T, T><<<dim3((unsigned)outer, 1, (unsigned)cdiv(inner, 16)), 256, 0, c.stream>>>(
+            x, inner, red, out);
+      else
+        k_strided_tile<MAP, 32, T, T, T><<<dim3((unsigned)outer, 1, (unsigned)cdiv(inner, 32)), 256, 0, c.stream>>>(
+            x, inner, red, out);
+    }
     else
       k_strided_large<MAP, T, T, T><<<dim3((unsigned)outer, 1, (unsigned)itiles), kRT, 0, c.stream>>>(
           x, inner, red, rows, out);
