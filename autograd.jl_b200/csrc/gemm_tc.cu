@@ -540,6 +540,17 @@ static bool make_map(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, i
   return r == CUDA_SUCCESS;
 }
 
+// k-blocks from which a product with fewer tiles than SMs is split along K (experiment knob AGB_TC_SPLIT_KB)
+static int tc_min_split_kblocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_TC_SPLIT_KB");
+    v = e ? atoi(e) : 16;
+    if (v < 4) v = 4;
+  }
+  return v;
+}
+
 bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                        const void* B, int64_t ldb, const void* C, int64_t ldc) {
   (void)transA; (void)transB;
@@ -582,10 +593,12 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
   p.kblocks_total = (int)cdiv(K, TC_BK);
   const int64_t tiles = (int64_t)p.mm_tiles * p.nn_tiles;
   int splits = 1;
-  if (tiles < c.num_sms && p.kblocks_total >= 16) {
+  if (tiles < c.num_sms && p.kblocks_total >= tc_min_split_kblocks()) {
     splits = (int)(c.num_sms / tiles);  // one work item per CTA: tiles*splits <= SMs (a second partial wave
                                         // would leave most SMs idle for a whole item)
-    int maxs = p.kblocks_total / 8;     // >= 8 k-blocks (256 k) per split
+    static int min_kb = -1;             // k-blocks per split at least (experiment knob AGB_TC_SPLIT_MINKB)
+    if (min_kb < 0) { const char* e = getenv("AGB_TC_SPLIT_MINKB"); min_kb = e ? atoi(e) : 4; if (min_kb < 2) min_kb = 2; }
+    int maxs = p.kblocks_total / min_kb;
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
   }
