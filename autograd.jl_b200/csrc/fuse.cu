@@ -24,7 +24,9 @@
 
 namespace agb {
 
-constexpr int FZ_MAXCODE = 96, FZ_MAXCONST = 16, FZ_MAXIN = 8, FZ_MAXOUT = 6, FZ_SLOTS = 8;
+constexpr int FZ_MAXCODE = 96, FZ_MAXCONST = 16, FZ_MAXIN = 12, FZ_MAXOUT = 12, FZ_SLOTS = 8;
+// what the general interpreter handles; larger programs run only as specialised kernels
+constexpr int FZ_DYN_MAXIN = 8, FZ_DYN_MAXOUT = 6;
 
 // instruction word: op | a << 8 | b << 16
 enum {
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_fused(const __grid_constant_
         break;
       }
       case FZ_STORE: {
-        const int o = x < FZ_MAXOUT ? x : FZ_MAXOUT - 1;
+        const int o = x < FZ_DYN_MAXOUT ? x : FZ_DYN_MAXOUT - 1;
 #pragma unroll
         for (int u = 0; u < UN; ++u)
           if (on[u]) fz_store<T, NV, VEC>(a, o, base + (int64_t)u * kThreads * NV, &tos[u * NV]);
@@ -456,7 +458,13 @@ __device__ __forceinline__ void fz_reduce_epilogue(const FzArgs& a, const T* red
   }
 }
 
-constexpr int FZ_UN = 2;   // vectors per thread of a specialised kernel
+// vectors per thread of a specialised kernel: two, or one for programs with many operands (register budget)
+constexpr int fz_un(const StaticProg& p) {
+  int stores = 0;
+  for (int i = 0; i < p.n; ++i)
+    if ((p.code[i] & 0xff) == FZ_STORE) ++stores;
+  return (p.nin > 6 || stores > 6) ? 1 : 2;
+}
 
 template <typename T, int PROG>
 __global__ void __launch_bounds__(kThreads) k_fused_static(const __grid_constant__ FzArgs a) {
@@ -464,6 +472,7 @@ __global__ void __launch_bounds__(kThreads) k_fused_static(const __grid_constant
   constexpr int NIN = kProgs[PROG].nin > 0 ? kProgs[PROG].nin : 1;
   constexpr int NSL = fz_slots_needed(kProgs[PROG]);
   constexpr bool RED = fz_has_reduce(kProgs[PROG]);
+  constexpr int FZ_UN = fz_un(kProgs[PROG]);
   constexpr int E = kThreads * FZ_UN * N;                       // elements a block can hold
   __shared__ __align__(16) T red[RED ? E : 1];
   const int chunk = RED ? a.chunk : E;                          // a reducing launch may use a shorter chunk
@@ -511,6 +520,15 @@ static bool launch_static(int prog, const FzArgs& a, unsigned nb, cudaStream_t s
 #undef X
   }
   return false;
+}
+
+static int static_un(int prog) {
+  switch (prog) {
+#define X(P) case P: return fz_un(kProgs[P]);
+    FZ_STATIC_LIST(X)
+#undef X
+  }
+  return 2;
 }
 
 static int find_static(const int32_t* code, int ncode) {
@@ -650,8 +668,11 @@ static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, c
     }
   }
   const int prog = (vec && g_fused_static_enabled) ? find_static(code, ncode) : -1;
+  AG_CHECK(prog >= 0 || (nin <= FZ_DYN_MAXIN && nout <= FZ_DYN_MAXOUT), AG_EUNSUPPORTED,
+           "ag_ewise_fused: %d inputs / %d outputs need a specialised kernel (the interpreter takes %d / %d)", nin, nout,
+           FZ_DYN_MAXIN, FZ_DYN_MAXOUT);
   a.rmode = 0;
-  a.chunk = kThreads * FZ_UN * N;
+  a.chunk = kThreads * (prog >= 0 ? static_un(prog) : 2) * N;
   a.tps = 1;
   a.rlen = 1;
   a.rout = nullptr;

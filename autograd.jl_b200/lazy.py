@@ -37,7 +37,8 @@ _RAW_BUF = D.DArray.__dict__["buf"]
 
 MAX_NODES = 24          # pending nodes per DAG before the largest argument is evaluated early
 BIG = 1 << 20           # elements from which a chain WITHOUT a specialised kernel is not handed to the interpreter
-MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 8, 6, 8
+MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 12, 12, 8
+DYN_MAXIN, DYN_MAXOUT = 8, 6     # what the general interpreter takes; larger programs need a specialised kernel
 LD_IN, LD_CONST, LD_TMP, ST_TMP, UNARY, BIN, BIN_IN, BIN_CONST, UGRAD, TERN, STORE, REDUCE = range(12)
 M_FULL, M_DEVSCALAR, M_IMM, M_COLVEC, M_ROWVEC = range(5)
 
@@ -101,6 +102,12 @@ def kernel_stats():
     a = (C.c_int64 * 2)()
     check(D.lib.ag_ewise_fused_stats(a))
     return int(a[0]), int(a[1])
+
+
+def set_static(on):
+    """Use (default) / ignore the ahead-of-time specialised kernels; what the host remembers about them is dropped."""
+    check(D.lib.ag_ewise_fused_set_static(1 if on else 0))
+    _static_cache.clear()
 
 
 def is_pending(x):
@@ -313,7 +320,7 @@ def _pick_split(order, root, ext):
         if n is root:
             continue
         outs_if_root = no + 1                   # the sub-root is written whether or not something refers to it
-        if len(lv) <= MAXIN and outs_if_root <= MAXOUT and 4 * k <= MAXCODE and k <= SLOTS * 2:
+        if len(lv) <= DYN_MAXIN and outs_if_root <= DYN_MAXOUT and 4 * k <= MAXCODE and k <= SLOTS * 2:
             if best is None or k > nn[id(best)]:
                 best = n
     return best
@@ -548,6 +555,9 @@ def _run_fused(order, root, reduce=None):
     cg.run(anchors, None if reduce is None else reduce[3])
     code, consts, leaves = cg.code, cg.consts, cg.leaves
     cg = None
+    if (len(leaves) > DYN_MAXIN or len(outputs) > DYN_MAXOUT) and \
+            (n_elem % (4 if dtype == np.float32 else 2) or not _is_static(code)):
+        raise _TooBig("inputs" if len(leaves) > DYN_MAXIN else "outputs", ext_ids)
     if reduce is None and n_elem >= BIG and static_only[0] and len(order) >= 1:
         if n_elem % (4 if dtype == np.float32 else 2) or not _is_static(code):
             raise _NotStatic()

@@ -197,7 +197,7 @@ ag_status ag_ewise_vm(int32_t dtype, const int32_t* code, int32_t ncode, const d
 /* Horizontal fusion of a chain of elementwise tape operations: the host runtime defers dotted
  * calls (src/core.jl:68-70 evaluates each one as its own Base broadcast pass), gradient rules (src/math.jl:9-74,
  * src/base.jl:20-49,73-74) and the dense `addto!` (src/addto.jl:23), and evaluates the whole expression DAG with ONE
- * launch: each leaf read once, each value the tape still holds written once (up to 6 outputs), temporaries never
+ * launch: each leaf read once, each value the tape still holds written once (up to 6 outputs; 12 inputs / 12 outputs for programs that have a specialised kernel), temporaries never
  * stored.  Iteration space rows x cols (column-major, n = rows*cols).  in_mode: 0 full array of n, 1 device scalar,
  * 2 immediate in_imm, 3 column vector (rows; broadcast along dim 2, e.g. a bias), 4 row vector (cols; broadcast along
  * dim 1, e.g. the softmax normaliser).  `code`: one int32 per instruction = op | a << 8 | b << 16, a stack machine

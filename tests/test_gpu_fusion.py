@@ -218,12 +218,11 @@ def test_whole_steps_identical_with_and_without_fusion(ag, L, cfg):
 def test_specialised_and_interpreted_kernels_agree(ag, L, cfg):
     """The ahead-of-time instantiated programs (fuse_static.inc) and the general interpreter give the same bits."""
     W = ag.workloads
-    lib = ag._lib.lib
     try:
-        ag._lib.check(lib.ag_ewise_fused_set_static(0))
+        L.set_static(False)
         ri, _ = _step_all(ag, W, cfg, True, L)
     finally:
-        ag._lib.check(lib.ag_ewise_fused_set_static(1))
+        L.set_static(True)
     rs, _ = _step_all(ag, W, cfg, True, L)
     for a, b in zip(ri, rs):
         assert np.array_equal(np.asarray(a), np.asarray(b))
@@ -249,6 +248,8 @@ def test_every_fused_launch_specialised_equals_interpreted(ag, L, cfg):
 
         def ag_ewise_fused(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols):
             dt, n, res = (np.float32 if dtype == 0 else np.float64), rows * cols, []
+            if nin > 8 or nout > 6:          # only a specialised kernel takes these; nothing to compare with
+                return real(dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols)
             for static in (1, 0):
                 lib.ag_ewise_fused_set_static(static)
                 st = real(dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, rows, cols)
