@@ -145,6 +145,24 @@ def main(out=OUT):
                         y_ = D.unary_fwd("tanh", D.binary_fwd("add", D.binary_fwd("mul", xs_, 0.5), bs_))
                         (f(y_) if dims is None else f(y_, dims=dims)).to_numpy()
                         del y_
+                CUR[0] = "zoo"        # close relatives of the configs (test/neuralnet.jl-style nets), same step loops
+                xz, yz = dev(rng.standard_normal((12, 16)).astype(dtype)), dev(rng.standard_normal((4, 16)).astype(dtype))
+                oh = np.zeros((4, 16), dtype)
+                oh[rng.integers(0, 4, 16), np.arange(16)] = 1
+                ohz = dev(np.asfortranarray(oh))
+                wz = lambda: [ag.Param(dev((0.1 * rng.standard_normal(sh)).astype(dtype)))
+                              for sh in ((8, 12), (8, 1), (4, 8), (4, 1))]
+                for act in (ag.tanh, ag.sigm, ag.relu):
+                    def net(p, act=act):
+                        return ag.add(ag.matmul(p[2], act(ag.add(ag.matmul(p[0], xz), p[1]))), p[3])
+                    sgd(lambda p: ag.div(ag.sumabs2(ag.sub(net(p), yz)), 16), wz())                 # squared error
+                    sgd(lambda p: ag.div(ag.neg(ag.sum_(ag.mul(ohz, ag.sub(net(p), ag.log(ag.sum_(ag.exp(net(p)), dims=0)))))), 16), wz())
+                wl = [ag.Param(dev((0.1 * rng.standard_normal((1, 12))).astype(dtype))), ag.Param(dev(np.zeros((1, 1), dtype)))]
+                tz = dev((rng.random((1, 16)) > 0.5).astype(dtype))
+                def logistic(p):                                   # -mean(t*log(s) + (1-t)*log(1-s))
+                    s_ = ag.sigm(ag.add(ag.matmul(p[0], xz), p[1]))
+                    return ag.div(ag.neg(ag.sum_(ag.add(ag.mul(tz, ag.log(s_)), ag.mul(ag.sub(1, tz), ag.log(ag.sub(1, s_)))))), 16)
+                sgd(logistic, wl)
                 CUR[0] = "rnn"
                 H, V, B, T = 8, 6, 8, 3
                 w = W.rnn_init(rng, H, V, dtype)
