@@ -152,6 +152,36 @@ static ag_status gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t
   return reduce_partials<T>(ws, (int)splits, M, N, alpha, beta, (T*)C, ldc);
 }
 
+// ---- tiny outputs with a long contraction (housing.jl: dw = dy*x', 1 x 506 times 506 x 13) -------------------
+// The tiled kernel above would spend a whole 64 x 64 tile of (double) FMAs on 13 outputs.  Here one warp owns one
+// output element: lanes stride over k, fixed-order shuffle reduction (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_gemm_warp_per_output(int transA, int transB, int64_t M, int64_t N, int64_t K, T alpha, const T* __restrict__ A,
+                           int64_t lda, const T* __restrict__ B, int64_t ldb, T beta, T* __restrict__ C, int64_t ldc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t o = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= M * N) return;
+  const int64_t m = o % M, n = o / M;
+  const int64_t sa = transA ? 1 : lda, sb = transB ? ldb : 1;
+  const T* __restrict__ a = A + (transA ? m * lda : m);
+  const T* __restrict__ b = B + (transB ? n : n * ldb);
+  T s0 = 0, s1 = 0;
+  int64_t k = lane;
+  for (; k + 32 < K; k += 64) {
+    s0 = fma(a[k * sa], b[k * sb], s0);
+    s1 = fma(a[(k + 32) * sa], b[(k + 32) * sb], s1);
+  }
+  if (k < K) s0 = fma(a[k * sa], b[k * sb], s0);
+  T s = s0 + s1;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0) {
+    T* c = C + m + n * ldc;
+    *c = beta == T(0) ? alpha * s : alpha * s + beta * (*c);
+  }
+}
+
 // gemm_tc.cu
 bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A,
                        int64_t lda, const void* B, int64_t ldb, const void* C, int64_t ldc);
@@ -204,6 +234,19 @@ ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int6
       g_last_engine = "skinny";
       return AG_OK;
     }
+  }
+  if (K >= 32 && M * N <= 1024 && K * M * N <= ((int64_t)1 << 22)) {
+    Context& c = ctx();
+    const unsigned nb = (unsigned)cdiv(M * N, 8);
+    if (dtype == AG_F64)
+      k_gemm_warp_per_output<double><<<nb, 256, 0, c.stream>>>(transA, transB, M, N, K, alpha, (const double*)A, lda,
+                                                               (const double*)B, ldb, beta, (double*)C, ldc);
+    else
+      k_gemm_warp_per_output<float><<<nb, 256, 0, c.stream>>>(transA, transB, M, N, K, (float)alpha, (const float*)A,
+                                                              lda, (const float*)B, ldb, (float)beta, (float*)C, ldc);
+    AG_LAUNCHED();
+    g_last_engine = "warp-per-output";
+    return AG_OK;
   }
   if (dtype == AG_F64) {
     g_last_engine = "dfma";

@@ -164,7 +164,9 @@ GEMM = [(64, 784, 1000, 0, 0), (64, 1000, 784, 0, 1), (64, 10, 1000, 1, 0), (10,
         (64, 784, 4096, 0, 0), (64, 8192, 784, 0, 1), (132, 72, 2000, 1, 1),
         # streaming skinny forms: S1a (few rows, K % 4 == 0), S1b (K <= 16, many rows), S2 (huge contraction)
         (7, 20, 1000, 0, 0), (16, 64, 515, 1, 0), (12, 16, 65536, 0, 0), (40, 3, 777, 0, 0), (33, 16, 600, 0, 0),
-        (64, 10, 65536, 1, 0), (3, 2051, 12, 0, 1), (16, 70001, 64, 0, 1), (10, 65536, 64, 0, 1)]
+        (64, 10, 65536, 1, 0), (3, 2051, 12, 0, 1), (16, 70001, 64, 0, 1), (10, 65536, 64, 0, 1),
+        # warp-per-output form (tiny outputs): housing's dw = dy*x', dot products, all four transposes
+        (3, 100, 5, 1, 0), (7, 64, 9, 1, 1), (1, 2000, 1, 0, 0), (16, 40, 64, 0, 0), (13, 506, 1, 0, 1), (2, 33, 3, 0, 1)]
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
