@@ -1,0 +1,48 @@
+"""Finite-difference check of EVERY primitive of the catalogue (shared by the GPU parity test and the CPU host-logic
+test; the reference's instrument is test/gradcheck.jl:35-133, its per-primitive lists test/math.jl:21-87, test/base.jl)."""
+import numpy as np
+
+
+def check_catalogue(ag):
+    rng = np.random.default_rng(18)
+    dev = ag.DArray.from_numpy
+    doms = {"acosh": (1.2, 2.0), "log": (0.2, 2.0), "sqrt": (0.2, 2.0), "log2": (0.2, 2.0), "log10": (0.2, 2.0),
+            "log1p": (-0.5, 2.0), "asin": (-0.8, 0.8), "acos": (-0.8, 0.8), "atanh": (-0.8, 0.8), "cbrt": (0.2, 2.0),
+            "tan": (-1.0, 1.0), "abs_": (0.2, 2.0), "relu": (0.2, 2.0)}
+    unary = ["neg", "abs_", "abs2", "exp", "log", "tanh", "sigm", "sqrt", "sin", "cos", "tan", "sinh", "cosh", "asin",
+             "acos", "atan", "asinh", "acosh", "atanh", "exp2", "exp10", "expm1", "log2", "log10", "log1p", "cbrt",
+             "relu", "identity", "copy"]
+    for name in unary:
+        lo, hi = doms.get(name, (-1.0, 1.0))
+        x = dev(rng.uniform(lo, hi, (3, 4)))
+        assert ag.gradcheck(getattr(ag, name), x), name
+    a, b = dev(rng.uniform(0.5, 1.5, (3, 4))), dev(rng.uniform(0.5, 1.5, (3, 4)))
+    row, col = dev(rng.uniform(0.5, 1.5, (1, 4))), dev(rng.uniform(0.5, 1.5, (3, 1)))
+    for name in ["add", "sub", "mul", "div", "pow_", "atan2", "hypot"]:
+        f = getattr(ag, name)
+        for q in (b, row, col):
+            assert ag.gradcheck(f, a, q), (name, q.shape)
+        assert ag.gradcheck(lambda z: f(z, 1.7), a) and ag.gradcheck(lambda z: f(1.7, z), a), name
+    far = dev(np.asarray(a.to_numpy() + np.where(rng.random((3, 4)) > 0.5, 0.4, -0.4)))      # no ties
+    for name in ["max_", "min_"]:
+        assert ag.gradcheck(getattr(ag, name), a, far), name
+    for f in (ag.sum_, ag.sumabs2, ag.sumabs, ag.mean):
+        assert ag.gradcheck(f, a), f
+        for dims in (0, 1):
+            assert ag.gradcheck(lambda z: f(z, dims=dims), a), (f, dims)
+    distinct = dev(rng.permutation(12).reshape(3, 4) / 7.0 + 0.3)
+    for f in (ag.maximum, ag.minimum, ag.prod):
+        assert ag.gradcheck(f, distinct) and ag.gradcheck(lambda z: f(z, dims=0), distinct), f
+    for f in (ag.var, ag.std, ag.norm):
+        assert ag.gradcheck(f, a), f
+    assert ag.gradcheck(ag.dot, a, b)
+    m1, m2 = dev(rng.standard_normal((4, 3))), dev(rng.standard_normal((3, 5)))
+    assert ag.gradcheck(ag.matmul, m1, m2)
+    assert ag.gradcheck(lambda p, q: ag.matmul(ag.adjoint(p), q), dev(rng.standard_normal((3, 4))), m2)
+    assert ag.gradcheck(lambda p, q: ag.matmul(p, ag.adjoint(q)), m1, dev(rng.standard_normal((5, 3))))
+    assert ag.gradcheck(lambda z: ag.reshape(z, (2, 6)), a) and ag.gradcheck(ag.vec, a) and ag.gradcheck(ag.adjoint, a)
+    assert ag.gradcheck(lambda z: ag.permutedims(z, (1, 0)), a)
+    assert ag.gradcheck(lambda p, q: ag.vcat(p, q), a, b) and ag.gradcheck(lambda p, q: ag.hcat(p, q), a, b)
+    assert ag.gradcheck(lambda p, q: ag.cat1d(p, q), a, row)
+    for idx in [(slice(None), [1, 1, 2]), ([0, 2],), (1, 2), (slice(0, 2), slice(1, 3))]:
+        assert ag.gradcheck(lambda z: ag.getindex(z, *idx), a), idx

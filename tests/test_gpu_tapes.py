@@ -160,6 +160,14 @@ def test_gradcheck_primitives(ag):
     assert ag.gradcheck(lambda p, q: ag.vcat(p, q), a, ag.DArray.from_numpy(rng.standard_normal((2, 3))))
 
 
+def test_gradcheck_every_primitive(ag):
+    """north_star: gradients "checked with test/gradcheck.jl on every primitive" -- the whole catalogue of rules.py
+    (src/math.jl:9-74, src/base.jl:20-49,73-74,202-250, src/statistics.jl:20-35, src/linearalgebra.jl:16,23,64-65,
+    src/cat.jl, src/getindex.jl), each on a domain where it is differentiable, Float64, reference tolerances."""
+    from gradcheck_catalogue import check_catalogue
+    check_catalogue(ag)
+
+
 def test_graph_replay_matches_eager(ag):
     """CUDA-graph replay of a whole step gives bit-identical parameters to the eager step."""
     W = ag.workloads

@@ -269,3 +269,9 @@ def test_primitive_expr(hostlib, oracle):
     kernels = ag.launch_count()
     sigm2(xd)
     assert ag.launch_count() - kernels == 1                # one fused pass
+
+
+def test_gradcheck_every_primitive_host_logic(hostlib):
+    """The same catalogue as the GPU test, through the host rules on the numpy stand-in (CPU)."""
+    from gradcheck_catalogue import check_catalogue
+    check_catalogue(hostlib)
