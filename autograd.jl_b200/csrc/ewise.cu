@@ -295,36 +295,9 @@ struct VmArgs {
 template <typename T>
 __device__ __forceinline__ T vm_unary(int u, T x) {
   switch (u) {
-    case AG_U_IDENTITY: return x;
-    case AG_U_NEG: return -x;
-    case AG_U_ABS: return fabs(x);
-    case AG_U_ABS2: return x * x;
-    case AG_U_EXP: return exp(x);
-    case AG_U_LOG: return log(x);
-    case AG_U_TANH: return tanh(x);
-    case AG_U_SIGM: return T(1) / (T(1) + exp(-x));
-    case AG_U_SQRT: return sqrt(x);
-    case AG_U_SIN: return sin(x);
-    case AG_U_COS: return cos(x);
-    case AG_U_TAN: return tan(x);
-    case AG_U_SINH: return sinh(x);
-    case AG_U_COSH: return cosh(x);
-    case AG_U_ASIN: return asin(x);
-    case AG_U_ACOS: return acos(x);
-    case AG_U_ATAN: return atan(x);
-    case AG_U_ASINH: return asinh(x);
-    case AG_U_ACOSH: return acosh(x);
-    case AG_U_ATANH: return atanh(x);
-    case AG_U_EXP2: return exp2(x);
-    case AG_U_EXP10: return exp10(x);
-    case AG_U_EXPM1: return expm1(x);
-    case AG_U_LOG2: return log2(x);
-    case AG_U_LOG10: return log10(x);
-    case AG_U_LOG1P: return log1p(x);
-    case AG_U_CBRT: return cbrt(x);
-    case AG_U_SIGN: return sgn(x);
-    case AG_U_RELU: return relu(x);
-    case AG_U_ONE: return T(1);
+#define X(OP) case OP: return U<OP, T>::f(x);
+    AG_FOR_UNARY(X)
+#undef X
   }
   return x;
 }

@@ -37,6 +37,68 @@ __device__ __forceinline__ T relu(T x) {
   return x > T(0) ? x : (x != x ? x : T(0));
 }
 
+
+// ---- special functions (src/specialfunctions.jl): what CUDA's math library has (erf family, gamma, lgamma, Bessel
+// j0/j1/jn, y0/y1/yn) plus digamma / trigamma / polygamma(2,.) for the gamma-family gradients: upward recurrence to
+// x >= 8 (12 in double), then the asymptotic series; reflection for x < 0.5 (digamma, trigamma).
+template <typename T>
+__device__ __forceinline__ T digamma_(T x) {
+  const T PI = T(3.14159265358979323846);
+  T refl = T(0);
+  bool neg = false;
+  if (x < T(0.5)) {            // psi(x) = psi(1-x) - pi*cot(pi*x)
+    refl = PI / tan(PI * x);
+    x = T(1) - x;
+    neg = true;
+  }
+  T r = T(0);
+  const T big = sizeof(T) == 8 ? T(12) : T(8);
+  while (x < big) { r -= T(1) / x; x += T(1); }
+  const T i = T(1) / x, i2 = i * i;
+  r += log(x) - T(0.5) * i -
+       i2 * (T(1.0 / 12) - i2 * (T(1.0 / 120) - i2 * (T(1.0 / 252) - i2 * (T(1.0 / 240) - i2 * (T(1.0 / 132) - i2 * T(691.0 / 32760))))));
+  return neg ? r - refl : r;
+}
+template <typename T>
+__device__ __forceinline__ T trigamma_(T x) {
+  const T PI = T(3.14159265358979323846);
+  T refl = T(0);
+  bool neg = false;
+  if (x < T(0.5)) {            // psi1(x) = -psi1(1-x) + pi^2 / sin^2(pi*x)
+    const T sp = sin(PI * x);
+    refl = PI * PI / (sp * sp);
+    x = T(1) - x;
+    neg = true;
+  }
+  T r = T(0);
+  const T big = sizeof(T) == 8 ? T(12) : T(8);
+  while (x < big) { r += T(1) / (x * x); x += T(1); }
+  const T i = T(1) / x, i2 = i * i;
+  r += i + T(0.5) * i2 +
+       i * i2 * (T(1.0 / 6) - i2 * (T(1.0 / 30) - i2 * (T(1.0 / 42) - i2 * (T(1.0 / 30) - i2 * (T(5.0 / 66) - i2 * T(691.0 / 2730))))));
+  return neg ? refl - r : r;
+}
+template <typename T>
+__device__ __forceinline__ T polygamma2_(T x) {   // psi''(x)
+  const T PI = T(3.14159265358979323846);
+  T refl = T(0);
+  if (x < T(0.5)) {            // psi2(x) = psi2(1-x) - 2 pi^3 cos(pi x) / sin^3(pi x)
+    const T sp = sin(PI * x);
+    refl = T(2) * PI * PI * PI * cos(PI * x) / (sp * sp * sp);
+    x = T(1) - x;
+  }
+  T r = T(0);
+  const T big = sizeof(T) == 8 ? T(12) : T(8);
+  while (x < big) { r -= T(2) / (x * x * x); x += T(1); }
+  const T i = T(1) / x, i2 = i * i;
+  r -= i2 * (T(1) + i + i2 * (T(0.5) - i2 * (T(1.0 / 6) - i2 * (T(1.0 / 6) - i2 * (T(3.0 / 10) - i2 * T(5.0 / 6))))));
+  return r - refl;
+}
+__device__ __forceinline__ float bessel_jn2(float x) { return jnf(2, x); }
+__device__ __forceinline__ double bessel_jn2(double x) { return jn(2, x); }
+__device__ __forceinline__ float bessel_yn2(float x) { return ynf(2, x); }
+__device__ __forceinline__ double bessel_yn2(double x) { return yn(2, x); }
+
 //        op            x?     y?     f(x)                          g(x,y)
 AG_DEF_U(AG_U_IDENTITY, false, false, x, T(1))
 AG_DEF_U(AG_U_NEG, false, false, -x, T(-1))
@@ -68,13 +130,30 @@ AG_DEF_U(AG_U_CBRT, false, true, cbrt(x), T(1) / (T(3) * y * y))
 AG_DEF_U(AG_U_SIGN, false, false, sgn(x), T(0))
 AG_DEF_U(AG_U_RELU, true, false, relu(x), (x >= T(0) ? T(1) : T(0)))
 AG_DEF_U(AG_U_ONE, false, false, T(1), T(0))
+// src/specialfunctions.jl:35-41,44,63-64 (erf family), :42 (gamma), :63-64 (lgamma / loggamma), :34 (digamma),
+// :67 (trigamma), :20-21,29-30 (Bessel functions of order 0 and 1)
+AG_DEF_U(AG_U_ERF, true, false, erf(x), T(1.12837916709551257390) * exp(-(x * x)))
+AG_DEF_U(AG_U_ERFC, true, false, erfc(x), -T(1.12837916709551257390) * exp(-(x * x)))
+AG_DEF_U(AG_U_ERFCX, true, true, erfcx(x), (T(2) * y) * x - T(1.12837916709551257390))
+AG_DEF_U(AG_U_ERFINV, false, true, erfinv(x), exp(y * y) * T(0.88622692545275801365))
+AG_DEF_U(AG_U_ERFCINV, false, true, erfcinv(x), -(exp(y * y)) * T(0.88622692545275801365))
+AG_DEF_U(AG_U_GAMMA, true, true, tgamma(x), y * digamma_(x))
+AG_DEF_U(AG_U_LGAMMA, true, false, lgamma(x), digamma_(x))
+AG_DEF_U(AG_U_DIGAMMA, true, false, digamma_(x), trigamma_(x))
+AG_DEF_U(AG_U_TRIGAMMA, true, false, trigamma_(x), polygamma2_(x))
+AG_DEF_U(AG_U_BESSELJ0, true, false, j0(x), -j1(x))
+AG_DEF_U(AG_U_BESSELJ1, true, false, j1(x), (j0(x) - bessel_jn2(x)) / T(2))
+AG_DEF_U(AG_U_BESSELY0, true, false, y0(x), -y1(x))
+AG_DEF_U(AG_U_BESSELY1, true, false, y1(x), (y0(x) - bessel_yn2(x)) / T(2))
 
 #define AG_FOR_UNARY(X)                                                                          \
   X(AG_U_IDENTITY) X(AG_U_NEG) X(AG_U_ABS) X(AG_U_ABS2) X(AG_U_EXP) X(AG_U_LOG) X(AG_U_TANH)     \
   X(AG_U_SIGM) X(AG_U_SQRT) X(AG_U_SIN) X(AG_U_COS) X(AG_U_TAN) X(AG_U_SINH) X(AG_U_COSH)        \
   X(AG_U_ASIN) X(AG_U_ACOS) X(AG_U_ATAN) X(AG_U_ASINH) X(AG_U_ACOSH) X(AG_U_ATANH) X(AG_U_EXP2)  \
   X(AG_U_EXP10) X(AG_U_EXPM1) X(AG_U_LOG2) X(AG_U_LOG10) X(AG_U_LOG1P) X(AG_U_CBRT) X(AG_U_SIGN) \
-  X(AG_U_RELU) X(AG_U_ONE)
+  X(AG_U_RELU) X(AG_U_ONE) X(AG_U_ERF) X(AG_U_ERFC) X(AG_U_ERFCX) X(AG_U_ERFINV) X(AG_U_ERFCINV) X(AG_U_GAMMA)      \
+  X(AG_U_LGAMMA) X(AG_U_DIGAMMA) X(AG_U_TRIGAMMA) X(AG_U_BESSELJ0) X(AG_U_BESSELJ1) X(AG_U_BESSELY0)              \
+  X(AG_U_BESSELY1)
 
 template <typename T>
 __device__ __forceinline__ T jmax(T a, T b) {  // Julia max: NaN-propagating

@@ -20,7 +20,9 @@ _DT = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64}
 # op ids (include/agb200.h)
 U = dict(identity=0, neg=1, abs=2, abs2=3, exp=4, log=5, tanh=6, sigm=7, sqrt=8, sin=9, cos=10, tan=11,
          sinh=12, cosh=13, asin=14, acos=15, atan=16, asinh=17, acosh=18, atanh=19, exp2=20, exp10=21,
-         expm1=22, log2=23, log10=24, log1p=25, cbrt=26, sign=27, relu=28, one=29)
+         expm1=22, log2=23, log10=24, log1p=25, cbrt=26, sign=27, relu=28, one=29,
+         erf=30, erfc=31, erfcx=32, erfinv=33, erfcinv=34, gamma=35, lgamma=36, digamma=37, trigamma=38,
+         besselj0=39, besselj1=40, bessely0=41, bessely1=42)
 B = dict(add=0, sub=1, mul=2, div=3, max=4, min=5, pow=6, eq=7, lt=8, le=9, gt=10, ge=11, atan2=12, hypot=13)
 R = dict(id=0, abs2=1, abs=2)
 
@@ -763,6 +765,22 @@ HOST_UNARY = dict(
     expm1=math.expm1, log2=math.log2, log10=math.log10, log1p=math.log1p,
     cbrt=lambda x: math.copysign(abs(x) ** (1.0 / 3.0), x), sign=lambda x: (x > 0) - (x < 0),
     relu=lambda x: x if x > 0 else 0 * x, one=lambda x: type(x)(1))
+
+
+def _special(name):
+    """Host Numbers through scipy.special (the SpecialFunctions.jl counterpart); only when actually called."""
+    def f(x):
+        import scipy.special as sp
+        table = dict(erf=sp.erf, erfc=sp.erfc, erfcx=sp.erfcx, erfinv=sp.erfinv, erfcinv=sp.erfcinv, gamma=sp.gamma,
+                     lgamma=sp.gammaln, digamma=sp.digamma, trigamma=lambda v: sp.polygamma(1, v), besselj0=sp.j0,
+                     besselj1=sp.j1, bessely0=sp.y0, bessely1=sp.y1)
+        return float(table[name](x))
+    return f
+
+
+for _n in ("erf", "erfc", "erfcx", "erfinv", "erfcinv", "gamma", "lgamma", "digamma", "trigamma", "besselj0", "besselj1",
+           "bessely0", "bessely1"):
+    HOST_UNARY[_n] = _special(_n)
 HOST_BINARY = dict(
     add=lambda a, b: a + b, sub=lambda a, b: a - b, mul=lambda a, b: a * b, div=lambda a, b: a / b,
     max=max, min=min, pow=lambda a, b: a ** b, eq=lambda a, b: float(a == b), lt=lambda a, b: float(a < b),

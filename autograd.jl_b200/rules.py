@@ -363,6 +363,33 @@ log1p = _unary("log1p", "log1p", lambda dy, y, x: mul(dy, div(1, add(1, x))), Tr
 cbrt = _unary("cbrt", "cbrt", lambda dy, y, x: mul(dy, div(1, mul(3, abs2(y)))), False, True)
 
 
+# special functions (src/specialfunctions.jl:20-21,29-30,34-42,63-67): the ones CUDA's math library provides, plus
+# digamma / trigamma; composites are the reference's own gradient expressions (used under an outer tape)
+_2SPI, _SPI2 = 2.0 / math.sqrt(math.pi), math.sqrt(math.pi) / 2.0
+polygamma2 = zerograd("polygamma(2,·)", lambda x: D.unary_bwd("trigamma", 1.0, x, None))     # psi''(x), forward only
+erf = _unary("erf", "erf", lambda dy, y, x: mul(dy, mul(exp(neg(abs2(x))), _2SPI)), True, False)
+erfc = _unary("erfc", "erfc", lambda dy, y, x: mul(dy, mul(neg(exp(neg(abs2(x)))), _2SPI)), True, False)
+erfcx = _unary("erfcx", "erfcx", lambda dy, y, x: mul(dy, sub(mul(mul(2, y), x), _2SPI)), True, True)
+erfinv = _unary("erfinv", "erfinv", lambda dy, y, x: mul(dy, mul(exp(abs2(y)), _SPI2)), False, True)
+erfcinv = _unary("erfcinv", "erfcinv", lambda dy, y, x: mul(dy, mul(neg(exp(abs2(y))), _SPI2)), False, True)
+gamma = _unary("gamma", "gamma", lambda dy, y, x: mul(dy, mul(y, digamma(x))), True, True)
+lgamma = _unary("lgamma", "lgamma", lambda dy, y, x: mul(dy, digamma(x)), True, False)
+loggamma = lgamma
+digamma = _unary("digamma", "digamma", lambda dy, y, x: mul(dy, trigamma(x)), True, False)
+trigamma = _unary("trigamma", "trigamma", lambda dy, y, x: mul(dy, polygamma2(x)), True, False)
+besselj0 = _unary("besselj0", "besselj0", lambda dy, y, x: mul(dy, neg(besselj1(x))), True, False)
+bessely0 = _unary("bessely0", "bessely0", lambda dy, y, x: mul(dy, neg(bessely1(x))), True, False)
+# order-1 Bessel gradients need order 2 (no forward primitive for it): the fused kernel only, no higher order
+def _no_order2(name):
+    def composite(dy, y, x):
+        raise UnsupportedOnDevice("%s: only the first derivative is available on device (its rule needs order 2)" % name)
+    return composite
+
+
+besselj1 = _unary("besselj1", "besselj1", _no_order2("besselj1"), True, False)
+bessely1 = _unary("bessely1", "bessely1", _no_order2("bessely1"), True, False)
+
+
 def _copy_fwd(x):
     return D.copy(x) if isinstance(x, DArray) else x
 

@@ -79,7 +79,21 @@ enum {
   AG_U_SIGN = 27,    /* @zerograd sign                src/base.jl (zero gradient; fwd only) */
   AG_U_RELU = 28,    /* max.(0,x): dy.*(y.==x)        src/math.jl:54 with x1 = 0 (examples/mnist.jl:32) */
   AG_U_ONE = 29,     /* one.(x) (fwd only; used by dy.*one.(x), src/base.jl:245) */
-  AG_U_COUNT = 30
+  /* src/specialfunctions.jl (the functions CUDA's math library provides, plus digamma / trigamma) */
+  AG_U_ERF = 30,      /* dy.*exp(-x^2)*2/sqrt(pi)      src/specialfunctions.jl:35 */
+  AG_U_ERFC = 31,     /* -dy.*exp(-x^2)*2/sqrt(pi)     :36 */
+  AG_U_ERFCX = 32,    /* dy.*(2y.*x - 2/sqrt(pi))      :38 */
+  AG_U_ERFINV = 33,   /* dy.*exp(y^2)*sqrt(pi)/2       :40 */
+  AG_U_ERFCINV = 34,  /* -dy.*exp(y^2)*sqrt(pi)/2      :37 */
+  AG_U_GAMMA = 35,    /* dy.*y.*digamma(x)             :42 */
+  AG_U_LGAMMA = 36,   /* dy.*digamma(x)                :63-64 (lgamma / loggamma) */
+  AG_U_DIGAMMA = 37,  /* dy.*trigamma(x)               :34 */
+  AG_U_TRIGAMMA = 38, /* dy.*polygamma(2,x)            :67 */
+  AG_U_BESSELJ0 = 39, /* -dy.*besselj1(x)              :20 */
+  AG_U_BESSELJ1 = 40, /* dy.*(besselj0 - besselj(2,x))/2  :21 */
+  AG_U_BESSELY0 = 41, /* -dy.*bessely1(x)              :29 */
+  AG_U_BESSELY1 = 42, /* dy.*(bessely0 - bessely(2,x))/2  :30 */
+  AG_U_COUNT = 43
 };
 
 /* Binary broadcasting primitives (src/base.jl:21-49, src/math.jl:24,48,54-55). */

@@ -661,6 +661,35 @@ copy = primitive("copy", lambda x: np.array(x, order="F", copy=True) if isinstan
                  lambda dy, y, x: dy)
 
 
+# special functions (src/specialfunctions.jl:20-21,29-30,34-42,63-67) through scipy.special, the counterpart of
+# SpecialFunctions.jl; gradient expressions exactly as the reference writes them
+def _sp(name, *pre):
+    def f(a):
+        import scipy.special as sp
+        return getattr(sp, name)(*pre, a)
+    return f
+
+
+_2SPI, _SPI2 = 2.0 / np.sqrt(np.pi), np.sqrt(np.pi) / 2.0
+erf = primitive("erf", _np(_sp("erf")), lambda dy, y, x: mul(dy, mul(exp(neg(abs2(x))), _2SPI)))
+erfc = primitive("erfc", _np(_sp("erfc")), lambda dy, y, x: mul(dy, mul(neg(exp(neg(abs2(x)))), _2SPI)))
+erfcx = primitive("erfcx", _np(_sp("erfcx")), lambda dy, y, x: mul(dy, sub(mul(mul(2, y), x), _2SPI)))
+erfinv = primitive("erfinv", _np(_sp("erfinv")), lambda dy, y, x: mul(dy, mul(exp(abs2(y)), _SPI2)))
+erfcinv = primitive("erfcinv", _np(_sp("erfcinv")), lambda dy, y, x: mul(dy, mul(neg(exp(abs2(y))), _SPI2)))
+polygamma2 = lambda x: _np(_sp("polygamma", 2))(value(x))                     # forward only
+trigamma = primitive("trigamma", _np(_sp("polygamma", 1)), lambda dy, y, x: mul(dy, polygamma2(x)))
+digamma = primitive("digamma", _np(_sp("digamma")), lambda dy, y, x: mul(dy, trigamma(x)))
+gamma = primitive("gamma", _np(_sp("gamma")), lambda dy, y, x: mul(dy, mul(y, digamma(x))))
+lgamma = primitive("lgamma", _np(_sp("gammaln")), lambda dy, y, x: mul(dy, digamma(x)))
+loggamma = lgamma
+besselj1 = primitive("besselj1", _np(_sp("j1")),
+                     lambda dy, y, x: mul(dy, div(sub(besselj0(x), _np(_sp("jn", 2))(value(x))), 2)))
+besselj0 = primitive("besselj0", _np(_sp("j0")), lambda dy, y, x: mul(dy, neg(besselj1(x))))
+bessely1 = primitive("bessely1", _np(_sp("y1")),
+                     lambda dy, y, x: mul(dy, div(sub(bessely0(x), _np(_sp("yn", 2))(value(x))), 2)))
+bessely0 = primitive("bessely0", _np(_sp("y0")), lambda dy, y, x: mul(dy, neg(bessely1(x))))
+
+
 def relu(x):
     """`max.(0, x)` (examples/mnist.jl:32)."""
     return max_(0, x)

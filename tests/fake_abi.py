@@ -53,6 +53,27 @@ _U = {
     27: (np.sign, lambda x, y: 0.0), 28: (lambda x: np.maximum(x, 0), lambda x, y: (x >= 0).astype(x.dtype)),
     29: (np.ones_like, lambda x, y: 0.0),
 }
+def _sp():
+    import scipy.special as sp
+    return sp
+
+
+_SQPI = 1.1283791670955126
+_U.update({
+    30: (lambda x: _sp().erf(x), lambda x, y: _SQPI * np.exp(-x * x)),
+    31: (lambda x: _sp().erfc(x), lambda x, y: -_SQPI * np.exp(-x * x)),
+    32: (lambda x: _sp().erfcx(x), lambda x, y: 2 * y * x - _SQPI),
+    33: (lambda x: _sp().erfinv(x), lambda x, y: np.exp(y * y) / _SQPI),
+    34: (lambda x: _sp().erfcinv(x), lambda x, y: -np.exp(y * y) / _SQPI),
+    35: (lambda x: _sp().gamma(x), lambda x, y: y * _sp().digamma(x)),
+    36: (lambda x: _sp().gammaln(x), lambda x, y: _sp().digamma(x)),
+    37: (lambda x: _sp().digamma(x), lambda x, y: _sp().polygamma(1, x)),
+    38: (lambda x: _sp().polygamma(1, x), lambda x, y: _sp().polygamma(2, x)),
+    39: (lambda x: _sp().j0(x), lambda x, y: -_sp().j1(x)),
+    40: (lambda x: _sp().j1(x), lambda x, y: (_sp().j0(x) - _sp().jn(2, x)) / 2),
+    41: (lambda x: _sp().y0(x), lambda x, y: -_sp().y1(x)),
+    42: (lambda x: _sp().y1(x), lambda x, y: (_sp().y0(x) - _sp().yn(2, x)) / 2),
+})
 _B = {
     0: np.add, 1: np.subtract, 2: np.multiply, 3: np.divide, 4: np.maximum, 5: np.minimum, 6: np.power,
     7: lambda a, b: (a == b), 8: lambda a, b: (a < b), 9: lambda a, b: (a <= b), 10: lambda a, b: (a > b),

@@ -16,6 +16,12 @@ def check_catalogue(ag):
         lo, hi = doms.get(name, (-1.0, 1.0))
         x = dev(rng.uniform(lo, hi, (3, 4)))
         assert ag.gradcheck(getattr(ag, name), x), name
+    # src/specialfunctions.jl (erf family, gamma family, Bessel functions of order 0 and 1)
+    for name, (lo, hi) in {"erf": (-1, 1), "erfc": (-1, 1), "erfcx": (0.1, 1.5), "erfinv": (-0.7, 0.7),
+                           "erfcinv": (0.3, 1.5), "gamma": (1.2, 3.0), "lgamma": (1.2, 3.0), "digamma": (1.2, 3.0),
+                           "trigamma": (1.2, 3.0), "besselj0": (0.5, 3.0), "besselj1": (0.5, 3.0),
+                           "bessely0": (0.5, 3.0), "bessely1": (0.5, 3.0)}.items():
+        assert ag.gradcheck(getattr(ag, name), dev(rng.uniform(lo, hi, (3, 4)))), name
     a, b = dev(rng.uniform(0.5, 1.5, (3, 4))), dev(rng.uniform(0.5, 1.5, (3, 4)))
     row, col = dev(rng.uniform(0.5, 1.5, (1, 4))), dev(rng.uniform(0.5, 1.5, (3, 1)))
     for name in ["add", "sub", "mul", "div", "pow_", "atan2", "hypot"]:

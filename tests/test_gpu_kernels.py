@@ -37,6 +37,37 @@ NP_G = dict(neg=lambda x, y: -1 + 0 * x, abs_=lambda x, y: np.sign(x), abs2=lamb
             log1p=lambda x, y: 1 / (1 + x), cbrt=lambda x, y: 1 / (3 * y * y))
 
 
+SPECIAL = {"erf": (-1.5, 1.5), "erfc": (-1.5, 1.5), "erfcx": (-0.5, 3.0), "erfinv": (-0.9, 0.9), "erfcinv": (0.1, 1.9),
+           "gamma": (0.3, 4.0), "lgamma": (0.3, 6.0), "digamma": (0.3, 20.0), "trigamma": (0.3, 20.0),
+           "besselj0": (0.2, 9.0), "besselj1": (0.2, 9.0), "bessely0": (0.3, 9.0), "bessely1": (0.3, 9.0)}
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-5), (np.float64, 1e-11)])
+def test_special_functions_against_the_oracle(ag, oracle, dtype, tol):
+    """src/specialfunctions.jl on device (CUDA math library + digamma / trigamma / polygamma(2,.) series) against the
+    oracle's scipy.special restatement: values and the gradients of the reference's rules, also for negative
+    non-integer arguments of the gamma family (reflection)."""
+    rng = np.random.default_rng(77)
+    for name, (lo, hi) in SPECIAL.items():
+        xs = [rng.uniform(lo, hi, 4099)]
+        if name in ("gamma", "lgamma", "digamma", "trigamma"):
+            xs.append(-rng.uniform(0.05, 0.95, 4099) - rng.integers(0, 3, 4099))       # negative, not an integer
+        for x in xs:
+            x = x.astype(dtype)
+            x64 = x.astype(np.float64)
+            fo = getattr(oracle, name)
+            yref = fo(x64)
+            gref = oracle.grad(lambda v: oracle.sum_(fo(v)))(x64)
+            xd = ag.DArray.from_numpy(x)
+            y = getattr(ag, name)(xd).to_numpy().astype(np.float64)
+            g = ag.grad(lambda v: ag.sum_(getattr(ag, name)(v)))(xd).to_numpy().astype(np.float64)
+            # element-wise, relative to the size of the value and of the terms that cancel near zeros
+            yscale = np.maximum(np.abs(yref), 1.0) if name != "lgamma" else np.maximum(np.abs(yref), np.abs(np.log(np.abs(x64))) + 1)
+            assert np.max(np.abs(y - yref) / yscale) <= tol * (30 if x[0] < 0 else 4), (name, "value", x[0] < 0)
+            gscale = np.maximum(np.abs(gref), 1.0 + np.abs(yref))
+            assert np.max(np.abs(g - gref) / gscale) <= tol * (60 if x[0] < 0 else 8), (name, "gradient", x[0] < 0)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [1, 3, 1023, 4096, 100003])
 def test_unary_fwd_bwd(ag, dtype, n):

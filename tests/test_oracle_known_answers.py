@@ -223,3 +223,26 @@ def test_softmax_xent_identity():
     g = grad(loss)(p)
     sm = np.exp(p) / np.exp(p).sum(0, keepdims=True)
     assert np.allclose(g, (sm - y) / 6, rtol=1e-13, atol=1e-15)
+
+
+def test_special_function_known_answers(oracle):
+    """src/specialfunctions.jl rules on closed-form points: erf'(0) = 2/sqrt(pi), gamma(5) = 24 with
+    gamma'(1) = -euler_gamma = digamma(1), trigamma(1) = pi^2/6 = digamma'(1), lgamma'(x) = digamma(x),
+    besselj0'(x) = -besselj1(x), erfinv(erf(x)) = x."""
+    import math
+    g = oracle.grad
+    eg = 0.5772156649015329
+    assert abs(g(lambda x: oracle.sum_(oracle.erf(x)))(np.array([0.0]))[0] - 2 / math.sqrt(math.pi)) < 1e-15
+    assert abs(g(lambda x: oracle.sum_(oracle.erfc(x)))(np.array([0.0]))[0] + 2 / math.sqrt(math.pi)) < 1e-15
+    assert abs(oracle.gamma(np.array([5.0]))[0] - 24.0) < 1e-12
+    assert abs(g(lambda x: oracle.sum_(oracle.gamma(x)))(np.array([1.0]))[0] + eg) < 1e-12
+    assert abs(oracle.digamma(np.array([1.0]))[0] + eg) < 1e-14
+    assert abs(g(lambda x: oracle.sum_(oracle.digamma(x)))(np.array([1.0]))[0] - math.pi ** 2 / 6) < 1e-12
+    assert abs(g(lambda x: oracle.sum_(oracle.lgamma(x)))(np.array([2.5]))[0] - oracle.digamma(np.array([2.5]))[0]) < 1e-14
+    x = np.array([0.3, 1.7, 4.0])
+    assert np.allclose(g(lambda v: oracle.sum_(oracle.besselj0(v)))(x), -oracle.besselj1(x), rtol=1e-14)
+    assert np.allclose(oracle.erfinv(oracle.erf(np.array([0.4]))), [0.4], rtol=1e-13)
+    for name, pt in [("erf", 0.3), ("erfc", 0.3), ("erfcx", 0.7), ("erfinv", 0.4), ("erfcinv", 0.6), ("gamma", 2.3),
+                     ("lgamma", 2.3), ("digamma", 1.9), ("trigamma", 1.9), ("besselj0", 1.1), ("besselj1", 1.1),
+                     ("bessely0", 1.1), ("bessely1", 1.1)]:
+        assert oracle.gradcheck(getattr(oracle, name), np.asfortranarray([[pt, pt + 0.2], [pt + 0.35, pt + 0.1]])), name
