@@ -519,9 +519,23 @@ def std(x, dims=None, corrected=True, mean_=None):
     return sqrt(var(x, dims=dims, corrected=corrected, mean_=mean_))
 
 
-def norm(x):
-    """2-norm (src/linearalgebra.jl:64-65, p = 2 branch of normback :222-238) as sqrt(sum(abs2, x))."""
-    return sqrt(sumabs2(x))
+def norm(x, p=2):
+    """norm(x), norm(x, p) of the vectorised array (src/linearalgebra.jl:64-65) as composites whose derivatives are the
+    branches of `normback` (:222-238): p = 2 sqrt(sum(abs2, x)); 1 sum(abs, x); Inf / -Inf maximum / minimum of abs.(x)
+    (ties share the gradient, like `dy*sign.(x).*(abs.(x).==y)`); 0 the number of nonzeros (zero gradient); otherwise
+    sum(abs.(x).^p)^(1/p)."""
+    if p == 2:
+        return sqrt(sumabs2(x))
+    if p == 1:
+        return sumabs(x)
+    if p == math.inf:
+        return maximum(abs_(x))
+    if p == -math.inf:
+        return minimum(abs_(x))
+    if p == 0:
+        xv = value(x)
+        return D.binary_fwd("sub", float(length(xv)), D.sum_all(D.binary_fwd("eq", xv, 0.0)))
+    return pow_(sum_(pow_(abs_(x), p)), 1.0 / p)
 
 
 def dot(a, b):

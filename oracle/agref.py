@@ -690,6 +690,39 @@ bessely1 = primitive("bessely1", _np(_sp("y1")),
 bessely0 = primitive("bessely0", _np(_sp("y0")), lambda dy, y, x: mul(dy, neg(bessely1(x))))
 
 
+def _normback(x, p, dy, y):
+    """src/linearalgebra.jl:222-238, branch for branch (raw arrays)."""
+    if x.size == 0:
+        return np.empty_like(x)
+    if p == 2:
+        return (dy / y) * x
+    if p == 1:
+        return dy * np.sign(x)
+    if p == np.inf or p == -np.inf:
+        return dy * np.sign(x) * (np.abs(x) == y)
+    if p == 0:
+        return np.zeros_like(x)
+    return dy * y ** (1 - p) * np.abs(x) ** (p - 1) * np.sign(x)
+
+
+def _norm_fwd(x, p=2):
+    v = np.abs(np.asarray(x, dtype=np.float64)).reshape(-1)
+    if p == np.inf:
+        r = v.max()
+    elif p == -np.inf:
+        r = v.min()
+    elif p == 0:
+        r = float(np.count_nonzero(v))
+    elif p == 1:
+        r = v.sum()
+    else:
+        r = (v ** p).sum() ** (1.0 / p)
+    return np.asarray(x).dtype.type(r)
+
+
+norm = primitive("norm", _norm_fwd, lambda dy, y, x, p=2: _normback(value(x), p, value(dy), value(y)))
+
+
 def relu(x):
     """`max.(0, x)` (examples/mnist.jl:32)."""
     return max_(0, x)

@@ -168,6 +168,25 @@ def test_gradcheck_every_primitive(ag):
     check_catalogue(ag)
 
 
+def test_norm_p_against_normback(ag, oracle):
+    """norm(x, p) for the branches of normback (src/linearalgebra.jl:222-238): device composites against the
+    oracle's branch-for-branch restatement, values and gradients."""
+    rng = np.random.default_rng(23)
+    x = np.asfortranarray(rng.standard_normal((7, 9)))
+    x[2, 3] = 0.0
+    xd = ag.DArray.from_numpy(x)
+    for p in (2, 1, np.inf, -np.inf, 0, 3, 2.5, 0.5):
+        xx, xxd = (x, xd) if p != -np.inf else (x + np.sign(x) + (x == 0), ag.DArray.from_numpy(x + np.sign(x) + (x == 0)))
+        vo, vd = float(oracle.norm(xx, p)), float(ag.norm(xxd, p))
+        assert abs(vo - vd) <= 1e-12 * max(abs(vo), 1), p
+        if p == 0.5:
+            xx, xxd = np.abs(x) + 0.1, ag.DArray.from_numpy(np.abs(x) + 0.1)       # |x|^(p-1) at 0
+        go = oracle.grad(lambda v: oracle.norm(v, p))(xx)
+        gd = ag.grad(lambda v: ag.norm(v, p))(xxd)
+        gd = np.zeros_like(xx) if gd is None else gd.to_numpy()
+        assert relerr(gd, go) <= 1e-11 if np.any(go) else not np.any(gd), p
+
+
 def test_graph_replay_matches_eager(ag):
     """CUDA-graph replay of a whole step gives bit-identical parameters to the eager step."""
     W = ag.workloads

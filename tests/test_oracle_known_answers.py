@@ -246,3 +246,15 @@ def test_special_function_known_answers(oracle):
                      ("lgamma", 2.3), ("digamma", 1.9), ("trigamma", 1.9), ("besselj0", 1.1), ("besselj1", 1.1),
                      ("bessely0", 1.1), ("bessely1", 1.1)]:
         assert oracle.gradcheck(getattr(oracle, name), np.asfortranarray([[pt, pt + 0.2], [pt + 0.35, pt + 0.1]])), name
+
+
+def test_norm_known_answers(oracle):
+    """src/linearalgebra.jl:64-65,222-238 on a 3-4-5 triangle: norm = 5, gradient x/5; p = 1: 7, sign(x); p = Inf: 4,
+    the gradient goes to the largest entry; p = 0 counts nonzeros and has a zero gradient."""
+    x = np.array([3.0, -4.0, 0.0])
+    g = lambda p: oracle.grad(lambda v: oracle.norm(v, p))(x)
+    assert oracle.norm(x) == 5.0 and np.allclose(g(2), [0.6, -0.8, 0.0])
+    assert oracle.norm(x, 1) == 7.0 and np.array_equal(g(1), [1.0, -1.0, 0.0])
+    assert oracle.norm(x, np.inf) == 4.0 and np.array_equal(g(np.inf), [0.0, -1.0, 0.0])
+    assert oracle.norm(x, 0) == 2.0 and not np.any(g(0))
+    assert abs(oracle.norm(x, 3) - (27 + 64) ** (1 / 3)) < 1e-14
