@@ -88,6 +88,8 @@ _SIGS = {
     "ag_p2p_allreduce_sum": [i32, vp, i64],
     "ag_p2p_allreduce_multi": [i32, i32, C.POINTER(vp), C.POINTER(vp), pi64, dbl],
     "ag_multi_axpy": [i32, i32, dbl, C.POINTER(vp), C.POINTER(vp), pi64],
+    "ag_multi_sumabs2": [i32, i32, C.POINTER(vp), pi64, vp],
+    "ag_multi_axpy_scaled": [i32, i32, dbl, vp, C.POINTER(vp), C.POINTER(vp), pi64],
     "ag_multi_copy": [i32, i32, C.POINTER(vp), C.POINTER(vp), pi64],
     "ag_p2p_destroy": [],
 }

@@ -79,12 +79,20 @@ class DataParallel:
             check(lib.ag_allreduce_sum(b.dt, D.vptr(b), tot))
         return views
 
-    def update(self, alpha, grads, params):
+    def update(self, alpha, grads, params, gclip=None):
         """The data-parallel SGD step: params[k] += alpha * (sum over ranks of grads[k]), i.e. allreduce followed
         by `axpy!(alpha, g, w)` for every Param.  One launch when the peer-memory collective is available (the
-        update is fused behind it); one multi-tensor axpy launch on a single rank.  Returns the reduced grads."""
+        update is fused behind it); one multi-tensor axpy launch on a single rank.  Returns the reduced grads.
+
+        gclip (examples/charlm.jl:116-118,148-152): the step is scaled by min(1, gclip / gnorm) with
+        gnorm = sqrt(sum over params of sum(abs2, g)) of the reduced gradients -- computed and applied on the device
+        (ag_multi_sumabs2, ag_multi_axpy_scaled), so a clipped step has no host round trip and replays as a graph."""
         from .core import value
         from . import lazy
+        if gclip is not None and gclip > 0:
+            reduced = self.update(0.0, grads, params) if self.world > 1 else \
+                [g.full() if isinstance(g, Sparse) else g for g in grads]
+            return self._clipped_update(alpha, reduced, params, float(gclip))
         dense = [g.full() if isinstance(g, Sparse) else g for g in grads]
         lazy.flush()        # the collective and the update work in place
         live = [(D.materialize(g), value(p)) for g, p in zip(dense, params) if g is not None]
@@ -130,6 +138,28 @@ class DataParallel:
             if g is not None:
                 D.axpy_(alpha, g, value(p))
         return reduced
+
+    def _clipped_update(self, alpha, dense, params, gclip):
+        from .core import value
+        from . import lazy
+        lazy.flush()
+        live = [(D.materialize(g), value(p)) for g, p in zip(dense, params) if g is not None]
+        if not live:
+            return dense
+        dt = live[0][0].dtype
+        if len(live) > 16 or any(g.dtype != dt or w.dtype != dt for g, w in live):
+            raise D.L.UnsupportedOnDevice("clipped update: at most 16 tensors of one eltype")
+        n = len(live)
+        src = (C.c_void_p * n)(*[g.ptr for g, _ in live])
+        dst = (C.c_void_p * n)(*[w.ptr for _, w in live])
+        sizes = (C.c_int64 * n)(*[g.size for g, _ in live])
+        nrm2 = DArray.empty((), dt)
+        check(lib.ag_multi_sumabs2(nrm2.dt, n, src, sizes, D.vptr(nrm2)))
+        # scale = min(1, gclip / sqrt(nrm2)) as a (deferred, fused) scalar chain; gnorm = 0 gives min(1, Inf) = 1
+        scale = D.binary_fwd("min", D.binary_fwd("div", gclip, D.unary_fwd("sqrt", nrm2)), 1.0)
+        self.last_gnorm2 = nrm2
+        check(lib.ag_multi_axpy_scaled(nrm2.dt, n, float(alpha), D.vptr(scale), src, dst, sizes))
+        return dense
 
     def close(self):
         check(lib.ag_comm_destroy())

@@ -95,6 +95,7 @@ struct P2PArgs {
   P2PSeg seg[P2P_MAXSEG];
   int nseg;
   double alpha;
+  const void* scale;   // optional device scalar multiplied into alpha (gradient clipping); nullptr: none
 };
 
 // One kernel = gather the segments into my symmetric buffer, publish, wait for the peers, sum all peers' buffers
@@ -277,11 +278,43 @@ __global__ void __launch_bounds__(256)
 template <typename T, bool COPY>
 __global__ void __launch_bounds__(256) k_multi_axpy(const P2PArgs a) {
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-  const T alpha = (T)a.alpha;
+  T alpha = (T)a.alpha;
+  if (!COPY && a.scale) alpha *= *(const T*)a.scale;
   for (int k = 0; k < a.nseg; ++k) {
     const T* __restrict__ x = (const T*)a.seg[k].src;
     T* __restrict__ y = (T*)a.seg[k].dst;
     for (int64_t i = t0; i < a.seg[k].n; i += stride) y[i] = COPY ? x[i] : fma(alpha, x[i], y[i]);
+  }
+}
+
+// sum over all tensors of sum(abs2, x_k): the gradient norm of examples/charlm.jl:116-118 in one launch.
+// Fixed grid, fixed per-thread order, double accumulation: deterministic.  part[blockIdx.x] = the block's sum.
+template <typename T>
+__global__ void __launch_bounds__(256) k_multi_sumabs2(const P2PArgs a, double* __restrict__ part) {
+  __shared__ double sm[8];
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  double acc = 0;
+  for (int k = 0; k < a.nseg; ++k) {
+    const T* __restrict__ x = (const T*)a.seg[k].src;
+    T s0 = 0, s1 = 0;
+    int64_t i = t0;
+    for (; i + stride < a.seg[k].n; i += 2 * stride) {
+      const T u = x[i], v = x[i + stride];
+      s0 = fma(u, u, s0);
+      s1 = fma(v, v, s1);
+    }
+    if (i < a.seg[k].n) s0 = fma(x[i], x[i], s0);
+    acc += (double)s0 + (double)s1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += sm[w];
+    part[blockIdx.x] = r;
   }
 }
 
@@ -301,6 +334,7 @@ static ag_status fill_args(P2PArgs& a, int32_t dtype, int32_t nseg, void* const*
   }
   a.nseg = nseg;
   a.alpha = alpha;
+  a.scale = nullptr;
   *total_out = off;
   return AG_OK;
 }
@@ -416,6 +450,46 @@ ag_status ag_multi_axpy(int32_t dtype, int32_t nseg, double alpha, void* const* 
   else k_multi_axpy<double, false><<<(unsigned)blocks, 256, 0, c.stream>>>(a);
   AG_LAUNCHED();
   return AG_OK;
+}
+
+ag_status ag_multi_axpy_scaled(int32_t dtype, int32_t nseg, double alpha, const void* scale_dev, void* const* x,
+                               void* const* y, const int64_t* sizes) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_multi_axpy_scaled: dtype %d", dtype);
+  AG_CHECK(y && scale_dev, AG_EINVAL, "ag_multi_axpy_scaled: null y / scale");
+  P2PArgs a;
+  int64_t total = 0;
+  ag_status st = fill_args(a, dtype, nseg, x, y, sizes, alpha, &total);
+  if (st != AG_OK) return st;
+  if (total == 0) return AG_OK;
+  for (int k = 0; k < nseg; ++k) AG_CHECK(sizes[k] == 0 || y[k], AG_EINVAL, "ag_multi_axpy_scaled: null y[%d]", k);
+  a.scale = scale_dev;
+  Context& c = ctx();
+  int64_t blocks = cdiv(total, 256 * 2);
+  if (blocks > 4 * c.num_sms) blocks = 4 * c.num_sms;
+  if (dtype == AG_F32) k_multi_axpy<float, false><<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+  else k_multi_axpy<double, false><<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+ag_status ag_multi_sumabs2(int32_t dtype, int32_t nseg, void* const* x, const int64_t* sizes, void* out_scalar) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_multi_sumabs2: dtype %d", dtype);
+  AG_CHECK(out_scalar, AG_EINVAL, "ag_multi_sumabs2: null result");
+  P2PArgs a;
+  int64_t total = 0;
+  ag_status st = fill_args(a, dtype, nseg, x, nullptr, sizes, 0.0, &total);
+  if (st != AG_OK) return st;
+  Context& c = ctx();
+  int64_t blocks = cdiv(total > 0 ? total : 1, 256 * 4);
+  if (blocks > 2 * c.num_sms) blocks = 2 * c.num_sms;
+  double* part = (double*)workspace(((size_t)blocks + 64) * sizeof(double));
+  if (!part) return AG_ENOMEM;
+  if (dtype == AG_F32) k_multi_sumabs2<float><<<(unsigned)blocks, 256, 0, c.stream>>>(a, part);
+  else k_multi_sumabs2<double><<<(unsigned)blocks, 256, 0, c.stream>>>(a, part);
+  AG_LAUNCHED();
+  return reduce_double_partials(dtype, part, blocks, 1, out_scalar);
 }
 
 ag_status ag_multi_copy(int32_t dtype, int32_t nseg, void* const* src, void* const* dst, const int64_t* sizes) {

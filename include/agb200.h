@@ -268,6 +268,15 @@ ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, i
 ag_status ag_reduce_dim(int32_t op, int32_t dtype, const void* x, int64_t inner, int64_t red, int64_t outer,
                         void* out);
 
+/* Gradient clipping on the device (examples/charlm.jl:116-118,148-152: gnorm = sqrt(sum over params of sum(abs2, g));
+ * if gnorm > gclip the step is scaled by gclip/gnorm) without a host round trip, so a clipped step still replays as
+ * one CUDA graph.  ag_multi_sumabs2: out_scalar = sum_k sum(abs2, x_k) for up to 16 tensors, one launch + one combine
+ * (deterministic, double accumulation).  ag_multi_axpy_scaled: y_k += alpha * (*scale_dev) * x_k, the update with the
+ * clipping factor min(1, gclip/gnorm) read from device memory. */
+ag_status ag_multi_sumabs2(int32_t dtype, int32_t nseg, void* const* x, const int64_t* sizes, void* out_scalar);
+ag_status ag_multi_axpy_scaled(int32_t dtype, int32_t nseg, double alpha, const void* scale_dev, void* const* x,
+                               void* const* y, const int64_t* sizes);
+
 /* ---- accumulation / update ---------------------------------------------------------------------- */
 /* out = a + b (out may alias a or b).  addto!(a::AbstractArray,b) = a+b, src/addto.jl:23. */
 ag_status ag_add(int32_t dtype, const void* a, const void* b, void* out, int64_t n);

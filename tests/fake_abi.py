@@ -507,6 +507,20 @@ class FakeLib:
             w[:] = w + T(alpha) * _arr(x[k], n, T)
         return 0
 
+    def ag_multi_axpy_scaled(self, dtype, nseg, alpha, scale, x, y, sizes):
+        T = _DT[dtype]
+        return self.ag_multi_axpy(dtype, nseg, float(T(alpha) * _arr(scale, 1, T)[0]), x, y, sizes)
+
+    def ag_multi_sumabs2(self, dtype, nseg, x, sizes, out):
+        self.launches += 2
+        T = _DT[dtype]
+        tot = 0.0
+        for k in range(nseg):
+            v = _arr(x[k], int(sizes[k]), T).astype(np.float64)
+            tot += float((v * v).sum())
+        _arr(out, 1, T)[0] = T(tot)
+        return 0
+
     def ag_allreduce_sum(self, dtype, buf, n):
         if self.nranks > 1:
             v = _arr(buf, n, _DT[dtype])

@@ -21,10 +21,18 @@ if os.environ.get("GC", "1") == "1":
     ag.set_gc_function(ag.release_node)
 
 
+GCLIP = float(os.environ.get("GCLIP", 5.0))      # examples/charlm.jl:148-152 (0: plain axpy! loop)
+dp = ag.DataParallel(0, 1)
+plist = list(params.values())
+
+
 def lstm_step():
     t = ag.diff(lambda: W.lstm_loss(ag, params, ids, tg, h0, h0))
-    for k, p in params.items():
-        ag.axpy(-0.01, ag.grad(t, p), p)
+    if GCLIP > 0:
+        dp.update(-0.01, [ag.grad(t, p) for p in plist], plist, gclip=GCLIP)
+    else:
+        for k, p in params.items():
+            ag.axpy(-0.01, ag.grad(t, p), p)
     return t
 
 

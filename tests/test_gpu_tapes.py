@@ -369,3 +369,32 @@ def test_sparse_scatter_full_size(ag):
     assert np.array_equal(np.any(got != 0, axis=0), np.any(ref != 0, axis=0))
     assert relerr(got, ref) <= 1e-5
     assert np.array_equal(got, sp.full().to_numpy())
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-6), (np.float64, 1e-13)])
+def test_clipped_update_on_device_and_in_a_graph(ag, dtype, tol):
+    """Gradient clipping without a host round trip (ag_multi_sumabs2 + ag_multi_axpy_scaled): against numpy, and
+    captured in a CUDA graph whose replay clips with the norm of the CURRENT gradients."""
+    from test_host_logic import _clip_case
+    for gclip in (5.0, 1e6, None):
+        got, want, gn = _clip_case(ag, dtype, gclip)
+        for a, b in zip(got, want):
+            assert np.max(np.abs(a - b)) <= tol * max(np.max(np.abs(b)), 1), gclip
+    rng = np.random.default_rng(42)
+    w0 = rng.standard_normal((64, 33)).astype(dtype)
+    g1, g2 = (rng.standard_normal((64, 33)) * 2).astype(dtype), (rng.standard_normal((64, 33)) * 0.01).astype(dtype)
+    p = ag.Param(ag.DArray.from_numpy(w0.copy()))
+    gd = ag.DArray.from_numpy(g1)
+    dp = ag.DataParallel(0, 1)
+    dp.update(-0.5, [gd], [p], gclip=3.0)                      # eager warm-up: w0 - 0.5*s1*g1
+    with ag.StepGraph() as g:
+        dp.update(-0.5, [gd], [p], gclip=3.0)
+    g2_flat = np.ascontiguousarray(g2.reshape(-1, order="F"))       # must outlive the (asynchronous) copy
+    gd.copy_from_host(g2_flat.ctypes.data, g2_flat.nbytes)
+    ag.sync()
+    g.launch()                                                 # clips with the norm of g2 (no clipping: small)
+    ag.sync()
+    s1 = min(1.0, 3.0 / np.sqrt(float((g1.astype(np.float64) ** 2).sum())))
+    want = w0.astype(np.float64) - 0.5 * s1 * g1 - 0.5 * 1.0 * g2
+    assert s1 < 1.0 and np.max(np.abs(p.value.to_numpy() - want)) <= 4 * tol * np.max(np.abs(want))
+    g.destroy()

@@ -275,3 +275,25 @@ def test_gradcheck_every_primitive_host_logic(hostlib):
     """The same catalogue as the GPU test, through the host rules on the numpy stand-in (CPU)."""
     from gradcheck_catalogue import check_catalogue
     check_catalogue(hostlib)
+
+def _clip_case(ag, dtype, gclip):
+    rng = np.random.default_rng(41)
+    shapes = [(6, 5), (6, 1), (3, 6), (3,)]
+    w = [rng.standard_normal(s).astype(dtype) for s in shapes]
+    g = [(rng.standard_normal(s) * 3).astype(dtype) for s in shapes]
+    params = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    grads = [ag.DArray.from_numpy(a) for a in g]
+    dp = ag.DataParallel(0, 1)
+    dp.update(-0.1, grads, params, gclip=gclip)
+    gn = np.sqrt(sum(float((a.astype(np.float64) ** 2).sum()) for a in g))
+    scale = min(1.0, gclip / gn) if gclip else 1.0
+    return [p.value.to_numpy() for p in params], [a.astype(np.float64) - 0.1 * scale * b.astype(np.float64) for a, b in zip(w, g)], gn
+
+
+def test_clipped_update_host_logic(hostlib):
+    """examples/charlm.jl:116-118,148-152: the step is scaled by min(1, gclip/gnorm); gnorm over ALL parameters."""
+    for gclip in (5.0, 1e6, None):
+        got, want, gn = _clip_case(hostlib, np.float64, gclip)
+        assert gn > 5.0
+        for a, b in zip(got, want):
+            assert np.allclose(a, b, rtol=1e-12), gclip
