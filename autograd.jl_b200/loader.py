@@ -112,3 +112,59 @@ class StagedInput:
         for a, st in zip(self.arrays, self.stage):
             check(D.lib.ag_copy_d2d(D.vptr(a), C.c_void_p(st.ptr), a.nbytes))
         check(D.lib.ag_prefetch_release())
+
+
+# ---- character data of examples/charlm.jl:166-203 -------------------------------------------------------------------
+
+def read_chars(source, char_limit=0):
+    """`loaddata` (examples/charlm.jl:166-190): the characters of a text (a path, or the text itself) as ids in order
+    of first appearance.  Returns (ids, char_to_index, index_to_char); ids are 0-based here (the reference's Int32
+    indices minus one), so `index_to_char[ids[k]]` is the k-th character."""
+    import os
+    text = source
+    if isinstance(source, (str, bytes)) and len(source) < 4096 and os.path.exists(source):
+        with open(source, "r", encoding="utf-8", errors="replace") as f:
+            text = f.read()
+    if isinstance(text, bytes):
+        text = text.decode("utf-8", errors="replace")
+    char_to_index, ids = {}, []
+    for c in text:
+        ids.append(char_to_index.setdefault(c, len(char_to_index)))
+        if char_limit > 0 and len(ids) >= char_limit:
+            break
+    index_to_char = [None] * len(char_to_index)
+    for c, i in char_to_index.items():
+        index_to_char[i] = c
+    return np.asarray(ids, dtype=np.int64), char_to_index, index_to_char
+
+
+def charlm_minibatch_ids(ids, batch_size):
+    """`minibatch` (examples/charlm.jl:192-203) without the one-hot matrices: batch i holds, for each of the
+    batch_size parallel streams j, the character at position i + nbatch*j (0-based), i.e. exactly the column in which
+    the reference sets d[char, j] = 1.  Returns an (nbatch, batch_size) int64 array."""
+    ids = np.asarray(ids, dtype=np.int64)
+    nbatch = ids.size // batch_size
+    return np.ascontiguousarray(ids[:nbatch * batch_size].reshape(batch_size, nbatch).T)
+
+
+class CharBatches:
+    """Device form of the charlm data: `ids[t]` (IArray, for the embedding lookup W[:, ids]) and `onehot(t)` (the
+    (V, B) matrix the reference builds on the host, rebuilt on the device from one byte per entry) for a window of
+    consecutive batches."""
+
+    def __init__(self, batch_ids, vocab, dtype=np.float32):
+        if vocab > 255:
+            raise DimensionMismatch("CharBatches: vocabulary of %d does not fit one byte per label" % vocab)
+        self.batch_ids = np.asarray(batch_ids, dtype=np.int64)
+        self.vocab, self.dtype = int(vocab), np.dtype(dtype)
+        self.ids = [D.IArray(row) for row in self.batch_ids]
+        self._lb = D._Buffer(max(self.batch_ids.size, 16))
+        flat = np.ascontiguousarray((self.batch_ids + 1).astype(np.uint8))     # 1-based classes
+        check(D.lib.ag_copy_h2d(C.c_void_p(self._lb.ptr), C.c_void_p(flat.ctypes.data), flat.size))
+        D._sync_stream()
+
+    def onehot(self, t):
+        B = self.batch_ids.shape[1]
+        out = D.DArray.empty((self.vocab, B), self.dtype)
+        check(D.lib.ag_onehot_labels(out.dt, C.c_void_p(self._lb.ptr + t * B), B, self.vocab, 0, D.vptr(out)))
+        return out

@@ -1074,3 +1074,25 @@ def yshape(a, nclass=10, dtype=np.float32):
     y = np.zeros((nclass, a.size), dtype=dtype, order="F")
     y[a - 1, np.arange(a.size)] = 1
     return y
+
+
+def charlm_loaddata(text, batch_size, char_limit=0):
+    """examples/charlm.jl:166-203 restated: (data, chars, char_to_index (1-based), index_to_char); data[i] is the
+    (vocab, batch_size) Float32 one-hot matrix with d[char_to_index[chars[i + nbatch*(j-1)]], j] = 1 (1-based i, j)."""
+    chars, char_to_index = [], {}
+    for c in text:
+        char_to_index.setdefault(c, 1 + len(char_to_index))
+        chars.append(c)
+        if char_limit > 0 and len(chars) >= char_limit:
+            break
+    nbatch = len(chars) // batch_size
+    data = []
+    for i in range(1, nbatch + 1):
+        d = np.zeros((len(char_to_index), batch_size), np.float32, order="F")
+        for j in range(1, batch_size + 1):
+            d[char_to_index[chars[(i + nbatch * (j - 1)) - 1]] - 1, j - 1] = 1
+        data.append(d)
+    index_to_char = [None] * len(char_to_index)
+    for c, i in char_to_index.items():
+        index_to_char[i - 1] = c
+    return data, chars, char_to_index, index_to_char

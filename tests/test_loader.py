@@ -147,3 +147,35 @@ def test_mnist_step_from_bytes_equals_step_from_float_arrays(ag, oracle):
     for q, g in zip(po, r1[1:]):
         ref = oracle.full(oracle.grad(to, q))
         assert np.max(np.abs(g - ref)) <= 1e-5 * np.max(np.abs(ref))
+
+
+TEXT = "the quick brown fox jumps over the lazy dog; THE QUICK BROWN FOX!\n" * 7
+
+
+def test_charlm_data_matches_the_reference_pipeline(agpkg, oracle):
+    """read_chars / charlm_minibatch_ids against the restated loaddata + minibatch of examples/charlm.jl:166-203:
+    same vocabulary order, and the id of stream j in batch i is the row of the 1 in column j of the reference's
+    one-hot matrix."""
+    ag = agpkg
+    data, chars, c2i, i2c = oracle.charlm_loaddata(TEXT, 16)
+    ids, c2i0, i2c0 = ag.read_chars(TEXT)
+    assert i2c0 == i2c and all(c2i0[c] == c2i[c] - 1 for c in c2i)
+    assert "".join(i2c0[k] for k in ids) == TEXT
+    b = ag.charlm_minibatch_ids(ids, 16)
+    assert b.shape == (len(data), 16)
+    for i, d in enumerate(data):
+        assert np.array_equal(np.argmax(d, axis=0), b[i]) and d.sum() == 16
+    ids2, _, _ = ag.read_chars(TEXT, char_limit=50)
+    assert ids2.size == 50 and np.array_equal(ids2, ids[:50])
+
+
+@pytest.mark.gpu
+def test_charlm_batches_on_device(ag, oracle):
+    data, chars, c2i, i2c = oracle.charlm_loaddata(TEXT, 16)
+    ids, _, i2c0 = ag.read_chars(TEXT)
+    cb = ag.CharBatches(ag.charlm_minibatch_ids(ids, 16)[:8], len(i2c0))
+    W = ag.DArray.from_numpy(np.asfortranarray(np.random.default_rng(0).standard_normal((5, len(i2c0))).astype(np.float32)))
+    for t in range(8):
+        assert np.array_equal(cb.onehot(t).to_numpy(), data[t])                      # the reference's matrix, bit for bit
+        emb = ag.getindex(W, slice(None), cb.ids[t]).to_numpy()                      # W[:, ids] == W * onehot
+        assert np.array_equal(emb, W.to_numpy() @ data[t])
