@@ -54,8 +54,13 @@ def _worker(rank, world, port, out_dir):
     xd, yd = ag.DArray.from_numpy(x[:, lo:hi]), ag.DArray.from_numpy(y[:, lo:hi])
     t = ag.diff(lambda: W.mnist_loss(ag, params, xd, yd, global_batch=B))
     grads = dp.update(-0.1, [ag.grad(t, p) for p in params], params)      # allreduce + fused axpy!
+    # a second, clipped step on fresh Params (examples/charlm.jl:148-152): allreduce first, then the norm of the SUMMED
+    # gradients decides the scale, identically on every rank
+    params2 = [ag.Param(ag.DArray.from_numpy(a)) for a in w]
+    t2 = ag.diff(lambda: W.mnist_loss(ag, params2, xd, yd, global_batch=B))
+    dp.update(-0.1, [ag.grad(t2, p) for p in params2], params2, gclip=0.05)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *[p.value.to_numpy() for p in params],
-             *[g.to_numpy() for g in grads])
+             *[g.to_numpy() for g in grads], *[p.value.to_numpy() for p in params2])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -81,6 +86,12 @@ def test_two_rank_gradients_match_full_batch(tmp_path, oracle):
         want = w[i] - 0.1 * g                                   # identical axpy! on every rank
         assert np.max(np.abs(r0["arr_%d" % i] - want)) <= 1e-12
         assert np.array_equal(r0["arr_%d" % i], r1["arr_%d" % i])
+    gn = np.sqrt(sum(float((g ** 2).sum()) for g in gref))
+    assert gn > 0.05                                            # so the clipped step really is scaled
+    for i, g in enumerate(gref):
+        want = w[i] - 0.1 * (0.05 / gn) * g
+        assert np.max(np.abs(r0["arr_%d" % (8 + i)] - want)) <= 1e-12
+        assert np.array_equal(r0["arr_%d" % (8 + i)], r1["arr_%d" % (8 + i)])
 
 
 def test_shard_columns_cover_the_batch(agpkg):
