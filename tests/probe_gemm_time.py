@@ -1,4 +1,5 @@
-"""Timing probe of the two big MNIST products (run on the GPU box)."""
+"""[historic probe: the AGB_TC_MMAS / AGB_TC_NOSPLIT experiment knobs it mentions were removed from gemm_tc.cu after the
+TS-mode rewrite; it still runs and times the current kernel]  Timing probe of the two big MNIST products (run on the GPU box)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

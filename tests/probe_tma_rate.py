@@ -1,4 +1,5 @@
-"""TMA feed-rate probe: the forward product with different K (row pitch of x) -- run with
+"""[historic probe: the AGB_TC_MMAS / AGB_TC_NOSPLIT experiment knobs it mentions were removed from gemm_tc.cu after the
+TS-mode rewrite; it still runs and times the current kernel]  TMA feed-rate probe: the forward product with different K (row pitch of x) -- run with
 AGB_TC_MMAS=1 AGB_TC_NOSPLIT=1 so the kernel is essentially a TMA streaming loop."""
 import os, sys
 import numpy as np
