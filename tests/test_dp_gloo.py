@@ -61,6 +61,27 @@ def _worker(rank, world, port, out_dir):
     dp.update(-0.1, [ag.grad(t2, p) for p in params2], params2, gclip=0.05)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *[p.value.to_numpy() for p in params],
              *[g.to_numpy() for g in grads], *[p.value.to_numpy() for p in params2])
+    # config 4 (charlm LSTM): the batch dimension of ids[t], targets and the recurrent state is split the same way;
+    # the embedding gradient is a Sparse on every rank and is densified before the reduction
+    H, E, V, Bl, T = 12, 6, 9, 10, 3
+    rl = np.random.default_rng(5)
+    wd = W.lstm_init(rl, H, E, V, np.float64)
+    keys = list(wd)
+    ids = [rl.integers(0, V, Bl) for _ in range(T)]
+    tg = []
+    for _ in range(T):
+        oh = np.zeros((V, Bl))
+        oh[rl.integers(0, V, Bl), np.arange(Bl)] = 1
+        tg.append(oh)
+    lo, hi = dp.shard_columns(Bl, rank, world)
+    pl = [ag.Param(ag.DArray.from_numpy(wd[k])) for k in keys]
+    ids_r = [ag.IArray(i[lo:hi]) for i in ids]
+    tg_r = [ag.DArray.from_numpy(np.asfortranarray(t_[:, lo:hi])) for t_ in tg]
+    h0 = ag.zeros((H, hi - lo), np.float64)
+    tl = ag.diff(lambda: W.lstm_loss(ag, dict(zip(keys, pl)), ids_r, tg_r, h0, h0, global_batch=Bl))
+    gl = dp.update(-0.05, [ag.grad(tl, p) for p in pl], pl)
+    np.savez(os.path.join(out_dir, "lstm_rank%d.npz" % rank), *[p.value.to_numpy() for p in pl],
+             *[ag.full(g).to_numpy() for g in gl])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -92,6 +113,40 @@ def test_two_rank_gradients_match_full_batch(tmp_path, oracle):
         want = w[i] - 0.1 * (0.05 / gn) * g
         assert np.max(np.abs(r0["arr_%d" % (8 + i)] - want)) <= 1e-12
         assert np.array_equal(r0["arr_%d" % (8 + i)], r1["arr_%d" % (8 + i)])
+
+
+def test_two_rank_lstm_matches_full_batch(tmp_path, oracle):
+    """Runs after the worker test above in the same spawn (files are written there); the LSTM part: reduced
+    gradients (dense and the Sparse embedding gradient) and updated Params equal the oracle's full-batch step."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    W = ge.load_package().workloads
+    H, E, V, Bl, T = 12, 6, 9, 10, 3
+    rl = np.random.default_rng(5)
+    wd = W.lstm_init(rl, H, E, V, np.float64)
+    keys = list(wd)
+    ids = [rl.integers(0, V, Bl) for _ in range(T)]
+    tg = []
+    for _ in range(T):
+        oh = np.zeros((V, Bl))
+        oh[rl.integers(0, V, Bl), np.arange(Bl)] = 1
+        tg.append(np.asfortranarray(oh))
+    po = [oracle.Param(np.asfortranarray(wd[k])) for k in keys]
+    h0 = np.zeros((H, Bl))
+    to = oracle.diff(lambda: W.lstm_loss(oracle, dict(zip(keys, po)), ids, tg, h0, h0))
+    gref = [oracle.full(oracle.grad(to, p)) for p in po]
+    r0 = np.load(os.path.join(str(tmp_path), "lstm_rank0.npz"))
+    r1 = np.load(os.path.join(str(tmp_path), "lstm_rank1.npz"))
+    n = len(keys)
+    for i, (k, g) in enumerate(zip(keys, gref)):
+        got0, got1 = r0["arr_%d" % (n + i)], r1["arr_%d" % (n + i)]
+        assert np.array_equal(got0, got1), k
+        assert np.max(np.abs(got0 - g)) <= 1e-11 * max(np.max(np.abs(g)), 1e-30), k
+        assert np.max(np.abs(r0["arr_%d" % i] - (wd[k] - 0.05 * g))) <= 1e-11, k
+        assert np.array_equal(r0["arr_%d" % i], r1["arr_%d" % i]), k
 
 
 def test_shard_columns_cover_the_batch(agpkg):
