@@ -53,6 +53,37 @@ for p, a, w0 in zip(params, po, w):
     gerr = np.max(np.abs(ag.grad(t, p).to_numpy() - agref.grad(to, a))) / np.max(np.abs(agref.grad(to, a)))
     print("rank %d update check shape %s: rel err %.3e  (reduced grad err %.3e) ok_so_far=%s" % (rank, want.shape, err, gerr, ok), flush=True)
     ok &= bool(err <= 1e-5)
+# config 4: the LSTM sharded over the batch dimension (Sparse embedding gradient -> dense -> reduction), with the
+# clipped update of examples/charlm.jl:148-152, against the oracle's full-batch step
+H, E, V, T = 64, 32, 40, 4
+Bl = 24 * world
+rl = np.random.default_rng(17)
+wdl = W.lstm_init(rl, H, E, V, np.float32)
+keys = list(wdl)
+ids = [rl.integers(0, V, Bl) for _ in range(T)]
+tgs = []
+for _ in range(T):
+    oh = np.zeros((V, Bl), np.float32); oh[rl.integers(0, V, Bl), np.arange(Bl)] = 1
+    tgs.append(np.asfortranarray(oh))
+lo2, hi2 = dp.shard_columns(Bl, rank, world)
+pl = [ag.Param(ag.DArray.from_numpy(wdl[k])) for k in keys]
+ids_r = [ag.IArray(i[lo2:hi2]) for i in ids]
+tg_r = [ag.DArray.from_numpy(np.asfortranarray(t_[:, lo2:hi2])) for t_ in tgs]
+h0 = ag.zeros((H, hi2 - lo2), np.float32)
+tl = ag.diff(lambda: W.lstm_loss(ag, dict(zip(keys, pl)), ids_r, tg_r, h0, h0, global_batch=Bl))
+dp.update(-0.05, [ag.grad(tl, p) for p in pl], pl, gclip=0.2)
+pol = [agref.Param(np.asfortranarray(wdl[k].astype(np.float64))) for k in keys]
+h064 = np.zeros((H, Bl))
+tol_ = agref.diff(lambda: W.lstm_loss(agref, dict(zip(keys, pol)), ids, [t_.astype(np.float64) for t_ in tgs], h064, h064))
+gl = [agref.full(agref.grad(tol_, p)) for p in pol]
+gn = np.sqrt(sum(float((g ** 2).sum()) for g in gl))
+sc = min(1.0, 0.2 / gn)
+worst = 0.0
+for k, p, g in zip(keys, pl, gl):
+    want = wdl[k].astype(np.float64) - 0.05 * sc * g
+    worst = max(worst, float(np.max(np.abs(p.value.to_numpy() - want)) / max(np.max(np.abs(want)), 1e-30)))
+print("rank %d LSTM clipped data-parallel update: gnorm %.4f scale %.4f worst rel err %.3e" % (rank, gn, sc, worst), flush=True)
+ok &= bool(worst <= 2e-5)
 # every rank must hold bit-identical reduced gradients
 digest = [float(np.sum(a.astype(np.float64))) for a in g_p2p]
 alld = allgather(digest)
