@@ -68,6 +68,27 @@ def main():
              "vec": ([0, 1],), "repeated": ([1, 1],), "empty": ([],), "mask": (mask,), "colon_int": (slice(None), 1),
              "int_colon": (1, slice(None)), "outer": ([0, 2], [1, 1, 3]), "matrix_index": (np.array([[0, 1], [2, 2]]),)}
     save("flat_dest_3x4", **{k: agref.flat_dest(shape, idx)[0] for k, idx in kinds.items()})
+    # src/specialfunctions.jl and norm(x, p): values and gradients on a fixed grid (Float64)
+    grid = np.linspace(0.35, 3.6, 27)
+    doms = {"erfinv": grid / 4.0, "erfcinv": grid / 2.0, "erf": grid - 1.5, "erfc": grid - 1.5}
+    out = {"grid": grid}
+    for name in ("erf", "erfc", "erfcx", "erfinv", "erfcinv", "gamma", "lgamma", "digamma", "trigamma", "besselj0",
+                 "besselj1", "bessely0", "bessely1"):
+        xs = doms.get(name, grid)
+        f = getattr(agref, name)
+        out["x_" + name], out["y_" + name] = xs, f(xs)
+        out["g_" + name] = agref.grad(lambda v: agref.sum_(f(v)))(xs)
+    xn = np.asfortranarray(np.random.default_rng(6).standard_normal((5, 6)))
+    out["norm_x"] = xn
+    for p in (1, 2, 3, 2.5, np.inf):
+        tag = str(p).replace(".", "_")
+        out["norm_" + tag] = agref.norm(xn, p)
+        out["gnorm_" + tag] = agref.grad(lambda v: agref.norm(v, p))(xn)
+    save("special_and_norm", **out)
+    # the MNIST loader's conversions (examples/mnist.jl:80-81) on a fixed byte batch
+    rb = np.random.default_rng(7)
+    px, lb = np.asfortranarray(rb.integers(0, 256, (784, 12), dtype=np.uint8)), rb.integers(0, 10, 12, dtype=np.uint8)
+    save("mnist_bytes", pixels=px, labels=lb, x=agref.xshape(px), y=agref.yshape(lb))
 
 
 if __name__ == "__main__":
