@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libagb200.so")
+LIB_PATH = os.environ.get("AGB200_LIB") or os.path.join(_HERE, "libagb200.so")   # AGB200_LIB: an instrumented build (experiments)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -70,6 +70,7 @@ _SIGS = {
     "ag_axpy": [i32, dbl, vp, vp, i64],
     "ag_scale": [i32, dbl, vp, i64],
     "ag_gemm": [i32, i32, i32, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64],
+    "ag_gemm_epilogue": [i32, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, vp, i64],
     "ag_gemm_set_engine": [i32],
     "ag_gemm_last_engine": [C.c_char_p, i64],
     "ag_ubyte_to_float": [i32, vp, vp, i64, dbl],

@@ -59,10 +59,11 @@ class Param(Tracked):
 
 
 class Result(Tracked):
-    __slots__ = ("value", "func", "args", "kwargs")
+    __slots__ = ("value", "func", "args", "kwargs", "_soft")
 
     def __init__(self, value, func, args, kwargs):
         self.value, self.func, self.args, self.kwargs = value, func, args, kwargs
+        self._soft = False
 
 
 class Node:
@@ -125,6 +126,7 @@ def _record(v, f, args, kwargs):
     if isinstance(v, Tracked):       # reference issue #106
         return v
     result = Result(v, f, args, kwargs)
+    _mark_soft(result, v, f, args)
     for tape in _tapes:
         node = Node(result)
         node.parents = [None] * len(args)
@@ -136,6 +138,26 @@ def _record(v, f, args, kwargs):
         tape.dict[id(result)] = node
         tape.list.append(node)
     return result
+
+
+def _mark_soft(result, v, f, args):
+    """Deferred evaluation (lazy.py) stores every pending value that something still refers to.  A Result refers to
+    its value, but many values on a tape are never read again: the gradient rules of `*` read its arguments, not its
+    output (src/base.jl:26); those of `+` / `-` read neither (src/base.jl:21,23: only sizes, for unbroadcast).  A Result
+    of such a primitive holds a pending value SOFTLY (it is not stored just because the tape points at it; if somebody
+    reads it after all, it is computed then), and a consumer whose rule does read an argument turns that argument's
+    hold into a hard one.  This is what lets `w*x .+ b` run as one launch without writing `w*x`."""
+    if getattr(v, "kind", None) is not None and getattr(f, "y_unused", False):
+        v.soft += 1
+        result._soft = True
+    unused = getattr(f, "args_unused", False)
+    if unused is True:
+        return
+    for i, a in enumerate(args):
+        if isinstance(a, Result) and a._soft and not (unused and i < len(unused) and unused[i]):
+            a._soft = False
+            if getattr(a.value, "kind", None) is not None:
+                a.value.soft -= 1
 
 
 gcnode = [lambda node, tape: None]
@@ -192,6 +214,14 @@ def differentiate(f, *x, **o):
             p.outgrad = addto(p.outgrad, g)
         if not _tapes and isinstance(r, Result) and n is not resultnode:
             gcnode[0](n, tape)
+    if not _tapes:
+        # latest first: a softly held sum that refers to a softly held product releases it
+        soft = [n.Value.value for n in reversed(lst) if isinstance(n.Value, Result) and n.Value._soft
+                and getattr(n.Value.value, "kind", None) is not None]
+        n = r = p = None
+        if soft:
+            from . import lazy
+            lazy.discard_soft(soft)
     return tape
 
 

@@ -9,6 +9,7 @@
 // shared-memory tiled CUDA-core kernel with deterministic split-K for everything else (Float64
 // has no tcgen05 kind).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace agb {
 
@@ -182,12 +183,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// gemm_tc.cu
-bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A,
-                       int64_t lda, const void* B, int64_t ldb, const void* C, int64_t ldc);
-ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
-                  const void* A, int64_t lda, const void* B, int64_t ldb, double beta, void* C,
-                  int64_t ldc);
+bool gemm_skinny_takes(int dtype, int transA, int transB, int64_t M, int64_t N, int64_t K);   // skinny.cu
 
 static int g_engine = 0;
 static const char* g_last_engine = "none";
@@ -258,10 +254,66 @@ ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int6
   }
   if (tc_ok && g_engine != 1) {
     g_last_engine = "tcgen05";
-    return gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr);
   }
   g_last_engine = "ffma";
   return gemm_simt<float>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+/* C = op(A)*op(B) .+ bias (bias: M values, broadcast along dim 2), then optionally an activation: one launch when the
+ * tcgen05 engine takes the shape (bias and activation in its epilogue), otherwise the same three kernels the unfused
+ * tape would run (product, broadcast add, elementwise map) -- results are identical either way. */
+ag_status ag_gemm_epilogue(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                           const void* A, int64_t lda, const void* B, int64_t ldb, const void* bias, int32_t act,
+                           void* C, void* C2, int64_t ldc) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_gemm_epilogue: dtype %d", dtype);
+  AG_CHECK(act == AG_U_IDENTITY || act == AG_U_RELU || act == AG_U_TANH || act == AG_U_SIGM, AG_EUNSUPPORTED,
+           "ag_gemm_epilogue: activation %d (identity, relu, tanh, sigm)", act);
+  AG_CHECK(M >= 0 && N >= 0 && K >= 0, AG_EINVAL, "ag_gemm_epilogue: negative dimension");
+  AG_CHECK((transA == 0 || transA == 1) && (transB == 0 || transB == 1), AG_EINVAL,
+           "ag_gemm_epilogue: trans flags must be 0 or 1");
+  AG_CHECK(!(C2 && act == AG_U_IDENTITY), AG_EINVAL, "ag_gemm_epilogue: second output without an activation");
+  if (M == 0 || N == 0) return AG_OK;
+  AG_CHECK(C && ldc >= M, AG_EINVAL, "ag_gemm_epilogue: bad C/ldc (DimensionMismatch)");
+  if (K > 0) {
+    AG_CHECK(A && B, AG_EINVAL, "ag_gemm_epilogue: null operand");
+    AG_CHECK(lda >= (transA ? K : M) && ldb >= (transB ? N : K), AG_EINVAL,
+             "ag_gemm_epilogue: leading dimension too small (DimensionMismatch)");
+  }
+  const bool tc_ok = dtype == AG_F32 && g_engine != 1 && K > 0 && ldc == M && (!C2 || ((uintptr_t)C2 & 15) == 0) &&
+                     !(K >= 32 && M * N <= 1024 && K * M * N <= ((int64_t)1 << 22)) &&
+                     gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
+  if (tc_ok) {
+    bool skinny_first = false;
+    if (g_engine != 2) skinny_first = gemm_skinny_takes(dtype, transA, transB, M, N, K);   // those stay unfused (below)
+    if (!skinny_first) {
+      TcEpilogue e;
+      e.bias = bias;
+      e.act = act == AG_U_RELU ? TC_ACT_RELU : act == AG_U_TANH ? TC_ACT_TANH : act == AG_U_SIGM ? TC_ACT_SIGM : TC_ACT_NONE;
+      e.out2 = C2;
+      g_last_engine = "tcgen05+epilogue";
+      return gemm_tc(transA, transB, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, &e);
+    }
+  }
+  // unfused: product, then z = C .+ bias in place, then the activation (into C2, or in place)
+  AG_CHECK(ldc == M, AG_EUNSUPPORTED, "ag_gemm_epilogue: ldc != M");
+  ag_status st = ag_gemm(dtype, transA, transB, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc);
+  if (st != AG_OK) return st;
+  if (bias) {
+    const int64_t shape[2] = {M, N}, sc[2] = {1, M}, sb[2] = {1, 0};
+    st = ag_binary_fwd(AG_B_ADD, dtype, C, 0.0, sc, bias, 0.0, sb, C, 2, shape);
+    if (st != AG_OK) return st;
+  }
+  if (act != AG_U_IDENTITY) {
+    if (act == AG_U_RELU) {   // max.(0, z): the binary map, as the tape would run it
+      const int64_t shape[1] = {M * N}, s1[1] = {1}, s0[1] = {0};
+      st = ag_binary_fwd(AG_B_MAX, dtype, nullptr, 0.0, s0, C, 0.0, s1, C2 ? C2 : C, 1, shape);
+    } else {
+      st = ag_unary_fwd(act, dtype, C, C2 ? C2 : C, M * N);
+    }
+  }
+  return st;
 }
 
 }  // extern "C"

@@ -1,25 +1,46 @@
 // gemm_tc.cu -- the Float32 matrix product on the 5th-generation tensor cores.
 //
-// Reference: forward `*` and its gradient products `dy*x2'` (NT) and `x1'*dy` (TN), src/base.jl:26,
-// which the reference hands to OpenBLAS sgemm.
+// Reference: forward `*` and its gradient products `dy*x2'` (NT) and `x1'*dy` (TN), src/base.jl:26, which the
+// reference hands to OpenBLAS sgemm; with an optional fused epilogue for the `.+ b` / activation nodes that follow
+// a product in every model of the reference (examples/mnist.jl:32, examples/charlm.jl:74-77).
 //
 // Design (sm_100a):
 //   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread),
-//     warps 2-9 = operand splitters, warps 10-13 = epilogue.  One CTA per SM; 6-stage TMA ring + 3-stage lo ring.
-//   * operands are fed by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) straight from the caller's
-//     column-major arrays; either operand may be K-major or MN-major, so NN / NT / TN / TT all map onto
+//     warps 2-9 = operand splitters, warps 10-13 = epilogue.  One CTA per SM; one 6-stage ring (TMA tile in smem,
+//     B_lo in smem, A hi/lo in tensor memory).
+//   * operands are fed by TMA (cp.async.bulk.tensor.2d) straight from the caller's column-major arrays; either
+//     operand may be K-major (SWIZZLE_128B) or MN-major (SWIZZLE_128B_ATOM_32B), so NN / NT / TN / TT all map onto
 //     the same kernel without a transpose pass (the instruction descriptor carries the majors).
-//   * Float32 accuracy on a TF32 pipe (3xTF32): the tensor core reads the fp32 tile as loaded and truncates
-//     it to tf32 (hi); the splitter warps write lo = rna_tf32(x - hi) to a second ring;
-//     D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi with fp32 accumulation in TMEM, promoted to registers every
-//     8 k-blocks.  Dropped term lo*lo ~ 2^-22 relative.  Measured error ~2e-6 of max|C| (tests/probe_gemm_accuracy.py).
-//   * D tile = 128 (mm) x 64 (nn) fp32 in TMEM, double buffered (2 x 64 columns) so the epilogue of
-//     one tile overlaps the main loop of the next.  The large extent of C is mapped to mm.
-//   * split-K for small outputs with a huge contraction (dW = dy*x', K = batch): partials go to the
-//     workspace and are summed in a fixed order (deterministic).
-// Roofline: for the MNIST-MLP shapes (M = 64) the products are HBM-bound:
-// algorithmic bytes (MK + KN + MN)*4.
+//   * Float32 accuracy on a TF32 pipe (3xTF32): D += A_hi*B_lo + A_lo*B_hi + A_hi*B_hi with fp32 accumulation in
+//     TMEM.  Two accuracy findings of round 2 (tests/test_gpu_baseline_sizes.py, tests/probe_lstm_accuracy.py):
+//     (1) A_hi must be ROUNDED to tf32, not truncated: with truncation the residual A_lo has the sign of A, the
+//     dropped A_lo*B_lo term has the sign of the product, and every product shrinks systematically;
+//     (2) the tensor core accumulates with truncation, a shrink of ~1.7e-7 per accumulated k-block; it is
+//     harmless for one product but compounds through a recurrent chain (config 4, T = 100: 2e-5 of the gradient when
+//     the TMEM partial is promoted to fp32 registers every 8 k-blocks, 2.7e-6 when promoted every k-block; FFMA
+//     6e-7).  The promotion interval is a template parameter: 1 for general shapes, 8 for the HBM-bound skinny
+//     shapes (min(M,N) <= 64: the MNIST products, where the epilogue warps would otherwise bound the kernel).
+//   * D tile = 128 (mm) x 64 (nn) fp32 in TMEM, double buffered (2 x 64 columns) so the promotion of one chunk
+//     overlaps the MMAs of the next.  The large extent of C is mapped to mm.
+//   * A goes through tensor memory (TS-mode MMA): with N = 64 an SS-mode MMA re-reads a 4 KB A slice from smem for
+//     32 cycles of math and is smem-port bound; the splitters stage exact tf32 hi / lo values with tcgen05.st.
+//   * split-K for small outputs with a huge contraction (dW = dy*x', K = batch): partials go to the workspace and
+//     are summed in a fixed order (deterministic) by k_tc_splitk_reduce, which also applies the epilogue.
+//   * Round-2 experiments that did NOT pay (each measured on the GPU and reverted, gpurun_out/r2_*.txt):
+//     (1) separate rings for A (8 stages, released by the splitters), B (6) and the TMEM staging (4) with four
+//     accumulators: 63 us against 50 us for the balanced 3-wave case -- and releasing a TMA stage right after
+//     generic-proxy loads needs fence.proxy.async before the mbarrier arrive (without it later tiles of a CTA read
+//     rows the refill had already overwritten);  (2) work distribution in units of k-blocks ("stream-K": 512 tiles
+//     on 148 SMs in 3.46 instead of 4 tile times) with the shared tiles combined in-kernel through the workspace
+//     (last arrival adds the partials in k order): the store / fence / atomic / read-back of the combination costs
+//     what the balance gains (63.7 us against 60.6 us), also when the shared tiles are processed first;  (3) the
+//     split-K reduction in-kernel (every CTA of a tile reduces a slice after a counter barrier): 64.6 us against
+//     60.8 us with the separate combine launch.
+// Roofline: for the MNIST-MLP shapes (M = 64) the products are HBM-bound: algorithmic bytes
+// (MK + KN + MN)*4.
 #include "common.cuh"
+#include "ewise_ops.cuh"
+#include "gemm_tc.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -30,28 +51,33 @@ constexpr int TC_BM = 128;      // mm tile (TMEM lanes)
 constexpr int TC_BN = 64;       // nn tile (TMEM columns per accumulator)
 constexpr int TC_BK = 32;       // k block: 32 floats = one 128-byte swizzle row
 constexpr int TC_STAGES = 6;    // one ring: TMA tiles (smem), B_lo (smem), A hi/lo (TMEM)
-constexpr int TC_FLUSH_KB = 8;  // k-blocks accumulated in TMEM before the partial is promoted to registers
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   //  8 KB
 constexpr int TC_RAW_BYTES = TC_A_BYTES + TC_B_BYTES;          // TMA stage: A and B as loaded (fp32)
-constexpr int TC_SPLIT_THREADS = 256;                          // 8 operand-splitter warps
-constexpr int TC_THREADS = 64 + TC_SPLIT_THREADS + 128;
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_THREADS = 14 * 32;
+constexpr int TC_EPI_WARP0 = 10;                // warps 10..13
 constexpr int TC_NBARS = 3 * TC_STAGES + 4;
-constexpr int TC_SMEM = TC_STAGES * (TC_RAW_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SMEM_DATA = TC_STAGES * (TC_RAW_BYTES + TC_B_BYTES);
+constexpr int TC_SMEM = TC_SMEM_DATA + 1024 /*align*/ + 8 * TC_NBARS + 64;
 constexpr int TC_TMEM_ACC = 2 * TC_BN;          // columns [0,128): two accumulators
 constexpr int TC_TMEM_ASTAGE = 2 * TC_BK;       // per stage: 32 columns A_hi + 32 columns A_lo
 constexpr int TC_TMEM_COLS = 512;               // 128 + 6*64 = 512: the whole tensor memory of the SM
+static_assert(TC_TMEM_ACC + TC_STAGES * TC_TMEM_ASTAGE <= TC_TMEM_COLS, "tensor memory budget");
+static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 struct TcParams {
   int mm_tiles, nn_tiles, splits;
   int kblocks_total, kblocks_per_split;
   int64_t MM, NN;          // extents along mm / nn
   float* out;              // C, or the split-K workspace
+  float* out2;             // optional second output (activation), same layout as C (direct path only)
+  const float* bias;       // optional, indexed by C's row (direct path only)
+  int act;                 // TC_ACT_*
   int64_t ld_out;          // leading dimension of out (elements)
   int64_t split_stride;    // elements between consecutive split partials
   int transposed;          // 1: mm runs along C's columns (out[nn + ld*mm]); 0: out[mm + ld*nn]
-  float alpha;
-  long long* dbg_t;        // AGB_TC_TIMING: per-role wait-cycle counters of block 0 (nullptr in production)
+  float alpha, beta;       // beta != 0 goes through the workspace path
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -81,7 +107,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug must trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin) {
-    if (spin > (1u << 24)) {
+    if (spin > (1u << 26)) {
       printf("libagb200 gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
       __trap();
@@ -97,7 +123,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // One lane of a fully converged warp.  Keeping the TMA / MMA roles warp-uniform (every lane runs the loop, only
 // the instruction itself is predicated on the elected lane) lets ptxas keep descriptors and barrier addresses
 // in uniform registers; wrapping the whole role in `if (lane == 0)` instead costs a serialising ELECT/R2UR loop
-// around every UTCHMMA/UTMALDG (measured: ~1000 cycles of issue time per k-block).
+// around every UTCHMMA/UTMALDG (measured in round 1: ~1000 cycles of issue time per k-block).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
@@ -106,46 +132,17 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // lo = x - trunc_tf32(x) (exact in fp32), then +half-ulp(tf32) on the bit pattern: the tensor core's own
 // truncation of the operand then yields round-to-nearest (ties away) -- integer ops instead of cvt.rna.tf32.
+// (B's hi part is the TMA tile itself, truncated by the tensor core; A's hi part is rounded, see split_tf32.)
 __device__ __forceinline__ float lo_tf32(float x) {
   const float d = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   return __uint_as_float(__float_as_uint(d) + 0x1000u);
 }
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// shared-memory matrix descriptor, Blackwell version field = 1.
-// K-major operands use SWIZZLE_128B (layout type 2, 16-byte atoms, 8-row groups of 1024 B).
-// MN-major tf32 operands must use SWIZZLE_128B_BASE32B (layout type 1: 32-byte atoms, the pattern
-// repeats every 4 k-rows = 512 B); TMA counterpart: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // version
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-// TS-mode MMA: A (128 x 8 tf32) from tensor memory, B from shared memory
+// TS-mode MMA: A (128 x 8 tf32) from tensor memory, B from shared memory through a UMMA descriptor
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -163,33 +160,92 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-// exact tf32 split of an fp32 value: hi = trunc_tf32(x), lo = rna_tf32(x - hi) (integer rounding)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// tf32 split of an fp32 value: hi = rna_tf32(x), lo = rna_tf32(x - hi) (integer rounding on the magnitude bits).
+// hi must be ROUNDED, not truncated: with hi = trunc(x) the residual lo always has the sign of x, so the dropped
+// term a_lo*b_lo always has the sign of a*b and every product shrinks systematically.  With a rounded hi the
+// residual has either sign and the dropped term is zero-mean.
 __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
-  hi = x & 0xFFFFE000u;
-  const float d = __uint_as_float(x) - __uint_as_float(hi);
+  hi = (x + 0x1000u) & 0xFFFFE000u;
+  const float d = __uint_as_float(x) - __uint_as_float(hi);      // exact in fp32
   lo = (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
 }
-
-// Per-role wait-cycle instrumentation (block 0), compiled in only with -DAGB_TC_TIMING: the clock reads
-// themselves cost ~150 cycles per k-block in the MMA warp.
-#ifdef AGB_TC_TIMING
-#define TWAIT(slot, bar, par)                                         \
-  do {                                                               \
-    long long _t0 = clock64();                                       \
-    mbar_wait(bar, par);                                             \
-    tacc[slot] += clock64() - _t0;                                   \
+template <int ACT>
+__device__ __forceinline__ float tc_activation(float z) {
+  if (ACT == TC_ACT_RELU) return jmax(0.0f, z);                  // max.(0, z): the FMax map of ewise_ops.cuh
+  if (ACT == TC_ACT_TANH) return U<AG_U_TANH, float>::f(z);
+  if (ACT == TC_ACT_SIGM) return U<AG_U_SIGM, float>::f(z);
+  return z;
+}
+// One finished element of C: alpha, beta, bias, activation -- each operation rounded on its own, so the values are
+// those of the unfused sequence `*` -> `.+` -> activation.
+template <int ACT>
+__device__ __forceinline__ void tc_store_elem(const TcParams& p, int64_t mm, int64_t nn, float v) {
+  const int64_t row = p.transposed ? nn : mm;
+  const int64_t idx = p.transposed ? nn + p.ld_out * mm : mm + p.ld_out * nn;
+  float z = p.alpha == 1.0f ? v : __fmul_rn(p.alpha, v);
+  if (p.bias) z = __fadd_rn(z, __ldg(p.bias + row));
+  if (p.out2) {
+    p.out[idx] = z;
+    p.out2[idx] = tc_activation<ACT>(z);
+  } else {
+    p.out[idx] = tc_activation<ACT>(z);
+  }
+}
+// The 64 values of one tile row (mm) held by an epilogue thread.
+template <int ACT>
+__device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int64_t nn0, const float* v) {
+  if (mm >= p.MM) return;
+  if (p.transposed && nn0 + TC_BN <= p.NN && (p.ld_out & 3) == 0) {
+    // this thread owns 64 consecutive elements of one column of C: vector stores; bias is indexed by nn (C's row)
+    float* dst = p.out + nn0 + p.ld_out * mm;
+    float* dst2 = p.out2 ? p.out2 + nn0 + p.ld_out * mm : nullptr;
+#pragma unroll
+    for (int j = 0; j < TC_BN; j += 4) {
+      float z[4], a[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        z[e] = p.alpha == 1.0f ? v[j + e] : __fmul_rn(p.alpha, v[j + e]);
+        if (p.bias) z[e] = __fadd_rn(z[e], __ldg(p.bias + nn0 + j + e));
+        a[e] = tc_activation<ACT>(z[e]);
+      }
+      if (dst2) {
+        *reinterpret_cast<float4*>(dst + j) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4*>(dst2 + j) = make_float4(a[0], a[1], a[2], a[3]);
+      } else {
+        *reinterpret_cast<float4*>(dst + j) = make_float4(a[0], a[1], a[2], a[3]);
+      }
+    }
+  } else {
+    // lanes hold consecutive mm: coalesced per nn when mm runs along C's rows
+#pragma unroll
+    for (int j = 0; j < TC_BN; ++j)
+      if (nn0 + j < p.NN) tc_store_elem<ACT>(p, mm, nn0 + j, v[j]);
+  }
+}
+#define TC_DISPATCH_ACT(act, CALL)                 \
+  do {                                             \
+    switch (act) {                                 \
+      case TC_ACT_RELU: CALL(TC_ACT_RELU); break;  \
+      case TC_ACT_TANH: CALL(TC_ACT_TANH); break;  \
+      case TC_ACT_SIGM: CALL(TC_ACT_SIGM); break;  \
+      default: CALL(TC_ACT_NONE); break;           \
+    }                                              \
   } while (0)
-#define TCLOCK() clock64()
-#else
-#define TWAIT(slot, bar, par) mbar_wait(bar, par)
-#define TCLOCK() 0ll
-#endif
 
 // A_KMAJOR / B_KMAJOR: memory major of the two operands (K contiguous or mm/nn contiguous).
-// B is consumed from shared memory through a UMMA descriptor in either major; A is consumed from TENSOR
-// MEMORY (TS mode): with N = 64 an SS-mode MMA re-reads a 4 KB A slice from smem for 32 cycles of math
-// (measured 42-50 cycles per UTCHMMA, smem-port bound), so the splitter warps stage A_hi / A_lo into TMEM.
-template <bool A_KMAJOR, bool B_KMAJOR>
+// FLUSH: k-blocks accumulated in TMEM before the partial is promoted to fp32 registers.
+template <bool A_KMAJOR, bool B_KMAJOR, int FLUSH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const TcParams p) {
@@ -201,29 +257,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   auto full_bar = [&](int s) { return bars + 8u * s; };                     // TMA bytes landed
   auto ready_bar = [&](int s) { return bars + 8u * (TC_STAGES + s); };      // A in TMEM, B_lo in smem
   auto empty_bar = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };  // MMAs of the stage retired
-  auto tfull_bar = [&](int a) { return bars + 8u * (3 * TC_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (3 * TC_STAGES + 2 + a); };
+  auto tfull = [&](int a) { return bars + 8u * (3 * TC_STAGES + a); };
+  auto tempty = [&](int a) { return bars + 8u * (3 * TC_STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * TC_NBARS;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(
-      smem_gen + TC_STAGES * (TC_RAW_BYTES + TC_B_BYTES) + 8 * TC_NBARS);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TC_SMEM_DATA + 8 * TC_NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_work = p.mm_tiles * p.nn_tiles * p.splits;
-  long long tacc[6] = {0, 0, 0, 0, 0, 0};
-  const long long t_begin = TCLOCK();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(ready_bar(s), TC_SPLIT_THREADS / 32);   // one elected arrival per splitter warp
+      mbar_init(ready_bar(s), TC_SPLIT_WARPS);   // one elected arrival per splitter warp
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
-    }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -236,6 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
+  const int total_work = p.mm_tiles * p.nn_tiles * p.splits;
   // work item -> (mm tile, nn tile, split)
   auto decode = [&](int w, int& mt, int& nt, int& kb0, int& kb1) {
     mt = w % p.mm_tiles;
@@ -255,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       int mt, nt, kb0, kb1;
       decode(w, mt, nt, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb) {
-        TWAIT(0, empty_bar(s), ph ^ 1);
+        mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t st = smem_base + s * TC_RAW_BYTES;
         if (elect_one()) {
           mbar_expect_tx(full_bar(s), TC_RAW_BYTES);
@@ -279,7 +329,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       }
     }
-    if (p.dbg_t && blockIdx.x == 0 && lane == 0) { p.dbg_t[0] = tacc[0]; p.dbg_t[1] = TCLOCK() - t_begin; }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform; one elected lane issues) =====
     // instruction descriptor: D=f32, A=B=tf32, A K-major (TMEM), B major, N, M
@@ -288,8 +337,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t b_lbo = B_KMAJOR ? 16u : 4096u;
     const uint32_t b_kstep = B_KMAJOR ? 32u : 1024u;   // bytes per UMMA_K = 8
     const uint32_t b_sbo = B_KMAJOR ? 1024u : 512u;
-    const uint32_t b_lt = B_KMAJOR ? 2u : 1u;
-    // descriptor words (see make_desc): hi = SBO | version<<14 | layout<<29 ; lo = addr>>4 | (LBO>>4)<<16
+    const uint32_t b_lt = B_KMAJOR ? 2u : 1u;          // SWIZZLE_128B / SWIZZLE_128B_BASE32B
+    // descriptor words: hi = SBO | version<<14 | layout<<29 ; lo = addr>>4 | (LBO>>4)<<16
     const uint32_t desc_hi_b = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (b_lt << 29);
     const uint32_t desc_lo_bhi = (((smem_base + TC_A_BYTES) >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
     const uint32_t desc_lo_blo = ((blo_base >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
@@ -298,14 +347,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int mt, nt, kb0, kb1;
       decode(w, mt, nt, kb0, kb1);
-      for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
-        const int kc1 = min(kc0 + TC_FLUSH_KB, kb1);
+      for (int kc0 = kb0; kc0 < kb1; kc0 += FLUSH, ++ci) {
+        const int kc1 = min(kc0 + FLUSH, kb1);
         const int acc = ci & 1;
-        TWAIT(0, tempty_bar(acc), ((ci >> 1) & 1) ^ 1);
+        mbar_wait(tempty(acc), ((ci >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_BN;
         for (int kb = kc0; kb < kc1; ++kb) {
-          TWAIT(1, ready_bar(s), ph);
+          mbar_wait(ready_bar(s), ph);
           tc_fence_after();
           // operands: A_hi / A_lo in TMEM (columns), B_hi in the TMA stage, B_lo in the B_lo ring
           const uint32_t a_t = tmem_base + TC_TMEM_ACC + (uint32_t)s * TC_TMEM_ASTAGE;
@@ -319,7 +368,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           const uint32_t first = kb > kc0 ? 1u : 0u;
           const uint32_t bar_e = empty_bar(s);
-          const long long t_i0 = TCLOCK();
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 8; ++k) {
@@ -330,19 +378,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
             umma_commit(bar_e);               // stage (smem + TMEM) reusable when these MMAs retire
           }
-          tacc[3] += TCLOCK() - t_i0;
           __syncwarp();
           if (++s == TC_STAGES) { s = 0; ph ^= 1; }
         }
-        if (elect_one()) umma_commit(tfull_bar(acc));        // chunk partial complete
+        if (elect_one()) umma_commit(tfull(acc));        // chunk partial complete
         __syncwarp();
       }
     }
-    if (p.dbg_t && blockIdx.x == 0 && lane == 0) {
-      p.dbg_t[2] = tacc[0]; p.dbg_t[3] = tacc[1]; p.dbg_t[4] = 0; p.dbg_t[5] = TCLOCK() - t_begin;
-      p.dbg_t[11] = tacc[3]; p.dbg_t[12] = 0;
-    }
-  } else if (warp < 2 + TC_SPLIT_THREADS / 32) {
+  } else if (warp < 2 + TC_SPLIT_WARPS) {
     // ===== operand splitters =====
     // A: each thread owns one tile row (= its TMEM lane) and half of the k-block: reads 16 fp32 from the TMA
     //    tile, writes hi and lo (exact tf32 values) to tensor memory with tcgen05.st.
@@ -357,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       int mt, nt, kb0, kb1;
       decode(w, mt, nt, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb) {
-        TWAIT(0, full_bar(s), ph);
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();                   // order the TMEM stores below after the stage hand-over
         const uint8_t* rawA = smem_gen + s * TC_RAW_BYTES;
         uint32_t v[16];
@@ -390,11 +433,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const float4* rawB = reinterpret_cast<const float4*>(smem_gen + s * TC_RAW_BYTES + TC_A_BYTES);
         float4* blo = reinterpret_cast<float4*>(smem_gen + TC_STAGES * TC_RAW_BYTES + s * TC_B_BYTES);
 #pragma unroll
-        for (int i = 0; i < TC_B_BYTES / 16 / TC_SPLIT_THREADS; ++i) {
-          const float4 x4 = rawB[tid + i * TC_SPLIT_THREADS];
+        for (int i = 0; i < TC_B_BYTES / 16 / 256; ++i) {
+          const float4 x4 = rawB[tid + i * 256];
           float4 r;
           r.x = lo_tf32(x4.x); r.y = lo_tf32(x4.y); r.z = lo_tf32(x4.z); r.w = lo_tf32(x4.w);
-          blo[tid + i * TC_SPLIT_THREADS] = r;
+          blo[tid + i * 256] = r;
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         fence_async_smem();                 // generic-proxy smem writes -> visible to the tensor core
@@ -404,10 +447,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       }
     }
-    if (p.dbg_t && blockIdx.x == 0 && tid == 0) { p.dbg_t[6] = tacc[0]; p.dbg_t[7] = 0; p.dbg_t[8] = TCLOCK() - t_begin; }
-  } else {
-    // ===== epilogue: promote each chunk partial TMEM -> registers (fp32 RN adds), write the tile =====
+  } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + 4) {
+    // ===== epilogue: promote each chunk partial TMEM -> registers (fp32 RN adds), finish the tile =====
     const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int etid = threadIdx.x - TC_EPI_WARP0 * 32;     // 0..127
+    const int r_loc = q * 32 + lane;     // tile row of this thread
     int ci = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int mt, nt, kb0, kb1;
@@ -415,57 +459,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       float accv[TC_BN];
 #pragma unroll
       for (int j = 0; j < TC_BN; ++j) accv[j] = 0.f;
-      for (int kc0 = kb0; kc0 < kb1; kc0 += TC_FLUSH_KB, ++ci) {
+      for (int kc0 = kb0; kc0 < kb1; kc0 += FLUSH, ++ci) {
         const int acc = ci & 1;
-        TWAIT(0, tfull_bar(acc), (ci >> 1) & 1);
+        mbar_wait(tfull(acc), (ci >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
           uint32_t r[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr));
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c0), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) accv[c0 + j] += __uint_as_float(r[j]);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) mbar_arrive(tempty(acc));
       }
-      const int64_t mm = (int64_t)mt * TC_BM + q * 32 + lane;
+      const int64_t mm = (int64_t)mt * TC_BM + r_loc;
       const int64_t nn0 = (int64_t)nt * TC_BN;
-      float* __restrict__ out = p.out + (int64_t)sp * p.split_stride;
-      if (mm < p.MM) {
+      if (p.split_stride == 0) {
+        // direct path: alpha, bias, activation and the stores
+#define TC_CALL(ACT) tc_store_row<ACT>(p, mm, nn0, accv)
+        TC_DISPATCH_ACT(p.act, TC_CALL);
+#undef TC_CALL
+      } else if (mm < p.MM) {
+        // workspace path (split-K or beta != 0): raw partial in C's own layout, combined by k_tc_splitk_reduce
+        float* __restrict__ out = p.out + (int64_t)sp * p.split_stride;
         if (p.transposed) {
-          // this thread owns 64 consecutive elements of one column of C
           float* dst = out + nn0 + p.ld_out * mm;
           if (nn0 + TC_BN <= p.NN && (p.ld_out & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < TC_BN; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(p.alpha * accv[j], p.alpha * accv[j + 1],
-                                                                p.alpha * accv[j + 2], p.alpha * accv[j + 3]);
+              *reinterpret_cast<float4*>(dst + j) = make_float4(accv[j], accv[j + 1], accv[j + 2], accv[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < TC_BN; ++j)
-              if (nn0 + j < p.NN) dst[j] = p.alpha * accv[j];
+              if (nn0 + j < p.NN) dst[j] = accv[j];
           }
         } else {
-          // lanes hold consecutive rows of C: coalesced per column
 #pragma unroll
           for (int j = 0; j < TC_BN; ++j)
-            if (nn0 + j < p.NN) out[mm + p.ld_out * (nn0 + j)] = p.alpha * accv[j];
+            if (nn0 + j < p.NN) out[mm + p.ld_out * (nn0 + j)] = accv[j];
         }
       }
     }
-    if (p.dbg_t && blockIdx.x == 0 && threadIdx.x == TC_THREADS - 128) { p.dbg_t[9] = tacc[0]; p.dbg_t[10] = TCLOCK() - t_begin; }
   }
 
   tc_fence_before();
@@ -476,10 +513,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// C = alpha * sum_s ws[s] + beta*C in a fixed order (deterministic split-K)
+// C = act(alpha * sum_s ws[s] + beta*C + bias) in a fixed order (deterministic split-K); ws partials are M x N
+// column-major with leading dimension M.  With C2: C receives the pre-activation value, C2 the activation.
+template <int ACT>
 __global__ void __launch_bounds__(256)
     k_tc_splitk_reduce(const float* __restrict__ ws, int splits, int64_t M, int64_t N, float alpha, float beta,
-                       float* __restrict__ C, int64_t ldc) {
+                       const float* __restrict__ bias, float* __restrict__ C, float* __restrict__ C2, int64_t ldc) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
   int64_t m = i % M, n = i / M;
@@ -499,9 +538,16 @@ __global__ void __launch_bounds__(256)
     s1 += ws[(int64_t)(k + 1) * MN + i];
   }
   if (k < splits) s0 += ws[(int64_t)k * MN + i];
-  float* c = C + m + n * ldc;
-  float r = alpha * (s0 + s1);
-  *c = beta == 0.f ? r : r + beta * (*c);
+  const int64_t idx = m + n * ldc;
+  float z = __fmul_rn(alpha, s0 + s1);
+  if (beta != 0.f) z = __fadd_rn(z, __fmul_rn(beta, C[idx]));
+  if (bias) z = __fadd_rn(z, bias[m]);
+  if (C2) {
+    C[idx] = z;
+    C2[idx] = tc_activation<ACT>(z);
+  } else {
+    C[idx] = tc_activation<ACT>(z);
+  }
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -540,15 +586,31 @@ static bool make_map(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, i
   return r == CUDA_SUCCESS;
 }
 
-// k-blocks from which a product with fewer tiles than SMs is split along K (experiment knob AGB_TC_SPLIT_KB)
-static int tc_min_split_kblocks() {
-  static int v = -1;
-  if (v < 0) {
+// Experiment knobs, read once (not on every product): AGB_TC_SPLIT_KB = k-blocks from which a product with fewer
+// tiles than SMs is split along K, AGB_TC_SPLIT_MINKB = k-blocks per split at least,
+// AGB_TC_FLUSH_SKINNY = 1 promotes every k-block for the skinny shapes as well.
+struct TcKnobs {
+  int split_kb, min_kb, flush_skinny;
+  TcKnobs() {
+    const char* f = getenv("AGB_TC_FLUSH_SKINNY");     // 1: promote every k-block for the skinny shapes too
+    flush_skinny = f ? atoi(f) : 8;
     const char* e = getenv("AGB_TC_SPLIT_KB");
-    v = e ? atoi(e) : 16;
-    if (v < 4) v = 4;
+    split_kb = e ? atoi(e) : 16;
+    if (split_kb < 4) split_kb = 4;
+    e = getenv("AGB_TC_SPLIT_MINKB");
+    min_kb = e ? atoi(e) : 4;
+    if (min_kb < 2) min_kb = 2;
   }
-  return v;
+};
+static const TcKnobs& tc_knobs() {
+  static TcKnobs k;
+  return k;
+}
+
+bool gemm_tc_init() {        // reads the environment knobs once, at ag_init (not on every product)
+  (void)tc_knobs();
+  (void)encode_fn();
+  return true;
 }
 
 bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
@@ -564,7 +626,8 @@ bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, 
 }
 
 ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const void* A,
-                  int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc) {
+                  int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc,
+                  const TcEpilogue* epi) {
   Context& c = ctx();
   // Map the larger extent of C onto the 128-row mm tile.
   //   normal     : mm = row index m of C,    Aop = op(A) (M x K),  Bop = op(B)^T (N x K)
@@ -593,12 +656,10 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
   p.kblocks_total = (int)cdiv(K, TC_BK);
   const int64_t tiles = (int64_t)p.mm_tiles * p.nn_tiles;
   int splits = 1;
-  if (tiles < c.num_sms && p.kblocks_total >= tc_min_split_kblocks()) {
+  if (tiles < c.num_sms && p.kblocks_total >= tc_knobs().split_kb) {
     splits = (int)(c.num_sms / tiles);  // one work item per CTA: tiles*splits <= SMs (a second partial wave
                                         // would leave most SMs idle for a whole item)
-    static int min_kb = -1;             // k-blocks per split at least (experiment knob AGB_TC_SPLIT_MINKB)
-    if (min_kb < 0) { const char* e = getenv("AGB_TC_SPLIT_MINKB"); min_kb = e ? atoi(e) : 4; if (min_kb < 2) min_kb = 2; }
-    int maxs = p.kblocks_total / min_kb;
+    const int maxs = p.kblocks_total / tc_knobs().min_kb;
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
   }
@@ -609,56 +670,57 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
   p.MM = MM;
   p.NN = NN;
   p.transposed = transposed ? 1 : 0;
+  p.alpha = (float)alpha;
+  p.beta = (float)beta;
+  p.out2 = epi ? (float*)epi->out2 : nullptr;
+  p.bias = epi ? (const float*)epi->bias : nullptr;
+  p.act = epi ? epi->act : TC_ACT_NONE;
+  float* ws = nullptr;
   if (via_ws) {
-    float* ws = (float*)workspace((size_t)splits * (size_t)(M * N) * sizeof(float));
+    ws = (float*)workspace((size_t)splits * (size_t)(M * N) * sizeof(float));
     if (!ws) return AG_ENOMEM;
     p.out = ws;
     p.ld_out = M;
     p.split_stride = M * N;
-    p.alpha = 1.0f;
   } else {
     p.out = (float*)C;
     p.ld_out = ldc;
     p.split_stride = 0;
-    p.alpha = (float)alpha;
-  }
-  static long long* dbg_t_dev = nullptr;
-  p.dbg_t = nullptr;
-  if (getenv("AGB_TC_TIMING")) {
-    if (!dbg_t_dev) cudaMalloc(&dbg_t_dev, 16 * 8);
-    p.dbg_t = dbg_t_dev;
   }
   const int64_t work = tiles * splits;
-  const unsigned grid = (unsigned)(work < c.num_sms ? work : c.num_sms);
+  const int64_t grid = work < c.num_sms ? work : c.num_sms;
 
-#define LAUNCH(AK, BK_)                                                                              \
-  do {                                                                                               \
-    static bool attr_set = false;                                                                    \
-    if (!attr_set) {                                                                                 \
-      AG_CUDA(cudaFuncSetAttribute(k_gemm_tc<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                   TC_SMEM));                                                        \
-      attr_set = true;                                                                               \
-    }                                                                                                \
-    k_gemm_tc<AK, BK_><<<grid, TC_THREADS, TC_SMEM, c.stream>>>(tmA, tmB, p);                        \
+  // promotion interval: every k-block, except for the HBM-bound skinny shapes (see the header comment)
+  const bool skinny = (M <= 64 || N <= 64) && tc_knobs().flush_skinny != 1;
+#define LAUNCH(AK, BK_, FL)                                                                              \
+  do {                                                                                                   \
+    static bool attr_set = false;                                                                        \
+    if (!attr_set) {                                                                                     \
+      AG_CUDA(cudaFuncSetAttribute(k_gemm_tc<AK, BK_, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                   TC_SMEM));                                                            \
+      attr_set = true;                                                                                   \
+    }                                                                                                    \
+    k_gemm_tc<AK, BK_, FL><<<(unsigned)grid, TC_THREADS, TC_SMEM, c.stream>>>(tmA, tmB, p);              \
   } while (0)
-  if (ak && bk) LAUNCH(true, true);
-  else if (ak && !bk) LAUNCH(true, false);
-  else if (!ak && bk) LAUNCH(false, true);
-  else LAUNCH(false, false);
+#define LAUNCH2(AK, BK_)              \
+  do {                                \
+    if (skinny) LAUNCH(AK, BK_, 8);   \
+    else LAUNCH(AK, BK_, 1);          \
+  } while (0)
+  if (ak && bk) LAUNCH2(true, true);
+  else if (ak && !bk) LAUNCH2(true, false);
+  else if (!ak && bk) LAUNCH2(false, true);
+  else LAUNCH2(false, false);
+#undef LAUNCH2
 #undef LAUNCH
   AG_LAUNCHED();
-#ifdef AGB_TC_TIMING
-  if (p.dbg_t) {
-    long long h[16];
-    cudaStreamSynchronize(c.stream);
-    cudaMemcpy(h, p.dbg_t, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "tc timing (block 0, cycles): work=%lld kb/tile=%d | producer wait_empty=%lld total=%lld | mma wait_tempty=%lld wait_full=%lld wait_lo=%lld total=%lld | split wait_full=%lld (unused)=%lld total=%lld | epi wait_tfull=%lld total=%lld | mma issue=%lld commit=%lld\n",
-            (long long)((work + grid - 1) / grid), p.kblocks_per_split, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
-  }
-#endif
   if (via_ws) {
-    k_tc_splitk_reduce<<<(unsigned)cdiv(M * N, 256), 256, 0, c.stream>>>(p.out, splits, M, N, (float)alpha,
-                                                                        (float)beta, (float*)C, ldc);
+    const unsigned nb = (unsigned)cdiv(M * N, 256);
+#define TC_CALL(ACT)                                                                                       \
+    k_tc_splitk_reduce<ACT><<<nb, 256, 0, c.stream>>>(ws, splits, M, N, (float)alpha, (float)beta, p.bias, \
+                                                      (float*)C, p.out2, ldc)
+    TC_DISPATCH_ACT(p.act, TC_CALL);
+#undef TC_CALL
     AG_LAUNCHED();
   }
   return AG_OK;

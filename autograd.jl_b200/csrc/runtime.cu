@@ -2,6 +2,7 @@
 // No reference counterpart (the reference is CPU-only Julia); the hooks it serves are
 // `@gs` (src/AutoGrad.jl:11) -> ag_sync and gcnode (src/core.jl:168,235-237) -> ag_free.
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 #include <map>
 #include <mutex>
@@ -209,6 +210,7 @@ ag_status ag_init(int32_t device) {
   if (!oob_flag()) return AG_ENOMEM;   // allocate the sticky index-check flag outside of any capture
   g_oob_armed = false;
   if (!reduce_scratch_init()) return AG_ENOMEM;
+  if (!gemm_tc_init()) return AG_ENOMEM;
   c.launches = 0;
   c.capturing = false;
   c.ready = true;

@@ -546,7 +546,8 @@ static ag_status skinny_f32(int transA, int transB, int64_t M, int64_t N, int64_
                             int64_t lda, const float* B, int64_t ldb, double beta, float* C, int64_t ldc,
                             bool* done) {
   Context& c = ctx();
-  if (getenv("AGB_SKINNY_OLD")) return AG_OK;
+  static const bool old_only = getenv("AGB_SKINNY_OLD") != nullptr;   // experiment knob, read once
+  if (old_only) return AG_OK;
   const bool b16 = (((uintptr_t)B) & 15) == 0 && (ldb & 3) == 0;
   if (!transB && beta == 0.0 && N >= 512 && N < ((int64_t)1 << 35)) {
     if (M <= 16 && K >= 16 && K <= SK_MAXD && (K & 3) == 0 && b16 &&
@@ -643,6 +644,14 @@ static ag_status skinny_impl(int transA, int transB, int64_t M, int64_t N, int64
     return reduce_partials<T>(part, (int)nblk, M, N, alpha, beta, C, ldc);
   }
   return AG_OK;
+}
+
+// The shapes skinny_impl takes (kept in step with its two branches): a product with two extents <= 64.
+bool gemm_skinny_takes(int dtype, int transA, int transB, int64_t M, int64_t N, int64_t K) {
+  (void)dtype;
+  if (!transB && M <= SK_MAXD && K <= SK_MAXD && N >= 512) return true;
+  if (!transA && transB && M <= SK_MAXD && N <= SK_MAXD && K >= 2048) return true;
+  return false;
 }
 
 ag_status gemm_skinny(int dtype, int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,

@@ -607,14 +607,35 @@ def matmul(a, b):
     out_shape = (m,) if (b.ndim == 1) else (m, n)
     if a.ndim == 1 and b.ndim == 2:
         out_shape = (m, n)
+    if _lazy.enabled[0] and len(out_shape) == 2 and m and n and ka:
+        A.ptr, Bm.ptr                       # operands must exist (a pending operand is evaluated now)
+        return _lazy.matmul(A, ta, Bm, tb, m, n, ka, lda, ldb, out_shape, dtype)
+    return _matmul_eager(A, Bm, (ta, tb, m, n, ka, lda, ldb), out_shape, dtype)
+
+
+def _matmul_eager(A, Bm, op, out_shape, dtype):
+    ta, tb, m, n, ka, lda, ldb = op
     c = DArray.empty(out_shape, dtype)
     if c.size == 0:
         return c
     if ka == 0:
         check(lib.ag_fill(vptr(c), c.size, c.dt, 0.0))
         return c
-    check(lib.ag_gemm(_DT[dtype], ta, tb, m, n, ka, 1.0, vptr(A), lda, vptr(Bm), ldb, 0.0, vptr(c), max(m, 1)))
+    check(lib.ag_gemm(_DT[np.dtype(dtype)], ta, tb, m, n, ka, 1.0, vptr(A), lda, vptr(Bm), ldb, 0.0, vptr(c), max(m, 1)))
     return c
+
+
+def _gemm_epilogue(A, Bm, op, out_shape, dtype, bias, act, want_z):
+    """(z, a) = (op(A)*op(B) .+ bias, act.(z)) by one ag_gemm_epilogue call; z is None unless want_z (then the
+    activation, if any, goes to a second array)."""
+    ta, tb, m, n, ka, lda, ldb = op
+    c = DArray.empty(out_shape, dtype)
+    c2 = DArray.empty(out_shape, dtype) if (want_z and act != "identity") else None
+    check(lib.ag_gemm_epilogue(_DT[np.dtype(dtype)], ta, tb, m, n, ka, vptr(A), lda, vptr(Bm), ldb, vptr(bias), U[act],
+                               vptr(c), vptr(c2), max(m, 1)))
+    if act == "identity":
+        return c, None
+    return (c, c2) if want_z else (None, c)
 
 
 def gemm_engine():

@@ -62,13 +62,15 @@ def set_fusion(on):
 
 class LazyArray(D.DArray):
     """A DArray defined by a pending elementwise operation.  kind is None once the storage exists."""
-    __slots__ = ("kind", "op", "args", "nnodes", "seq")
+    __slots__ = ("kind", "op", "args", "nnodes", "seq", "soft")
 
     def __init__(self, shape, dtype, kind, op, args, nnodes):
         _RAW_BUF.__set__(self, None)
         _RAW_PTR.__set__(self, 0)
         self.shape, self.dtype, self.tr = tuple(int(s) for s in shape), np.dtype(dtype), False
         self.kind, self.op, self.args, self.nnodes = kind, op, args, nnodes
+        self.soft = 0           # holders that do not need the value stored (see core._record): a tape Result whose
+                                # value no gradient rule reads, e.g. the product under `w*x .+ b`
         self.seq = next(_counter)
         _pending[self.seq] = self
 
@@ -179,6 +181,14 @@ def bcast_to(a, shape):
     return _make("id", None, (a,), shape, a.dtype)
 
 
+def matmul(A, ta, B, tb, m, n, k, lda, ldb, out_shape, dtype):
+    """A pending product op(A)*op(B) (src/base.jl:26 forward).  Deferred so that the `.+ b` and the activation
+    that follow it in every model of the reference (examples/mnist.jl:32, examples/charlm.jl:74-77) can run in the
+    product's epilogue (ag_gemm_epilogue) instead of as separate passes over the output; a product nobody builds
+    on is evaluated by ag_gemm when it is touched.  A and B are concrete storage (the caller forced them)."""
+    return LazyArray(out_shape, dtype, "mm", (int(ta), int(tb), int(m), int(n), int(k), int(lda), int(ldb)), (A, B), 1)
+
+
 # ---- evaluation -------------------------------------------------------------------------------------------
 
 def reduce(x, inner, red, outer, mapname):
@@ -193,7 +203,13 @@ def reduce(x, inner, red, outer, mapname):
         return None
     if not ((inner == 1 and (outer == 1 or red <= E)) or (outer == 1 and inner * 16 <= E)):
         return None
+    if x.kind == "mm":
+        return None
     order = _topo(x)
+    while _resolve_products(order, x):
+        if x.kind is None:
+            return None
+        order = _topo(x)
     out = D.DArray.empty((inner * outer,), x.dtype)
     try:
         _run_fused(order, x, (inner, red, outer, mapname, out))
@@ -259,10 +275,35 @@ def flush():
         n = None
 
 
+def discard_soft(nodes):
+    """End of a backward sweep (core.differentiate): pending values that only the finished tape's Results hold, and
+    that no gradient rule reads (soft holds), will never be needed by the sweep.  They are dropped instead of being
+    computed by the next flush (an in-place `axpy!` on a Param flushes, and would otherwise run the product under
+    `w*x .+ b` once more just to store a value nobody reads).  Reading such a value afterwards raises: its inputs may
+    have been updated in place since, so recomputing it could silently give a different array than the reference's
+    stored one.  Keep a reference to `value(x)` during the forward pass to have it stored."""
+    for i in range(len(nodes)):
+        if nodes[i].kind is not None and nodes[i].kind != "lost" and nodes[i].soft > 0 and _external(nodes[i], 0) <= 0:
+            v = nodes[i]
+            v.kind, v.op, v.args, v.nnodes = "lost", None, (), 0
+            _pending.pop(v.seq, None)
+            v = None
+            stats["discarded"] = stats.get("discarded", 0) + 1
+
+
 def force(root):
     """Evaluate `root` (and every pending node below it that something else refers to)."""
+    if root.kind == "lost":
+        raise RuntimeError("this intermediate value was not stored: no gradient rule reads it and nothing else held it "
+                           "when the backward sweep finished (lazy.discard_soft); hold value(x) to keep it")
     while root.kind is not None:
+        if root.kind == "mm":
+            root._set_storage(D._matmul_eager(root.args[0], root.args[1], root.op, root.shape, root.dtype))
+            return
         order = _topo(root)
+        if _resolve_products(order, root):
+            order = None
+            continue                        # some nodes got their storage from a fused product: walk the rest again
         action, ext = None, None
         try:
             _run_fused(order, root)
@@ -342,6 +383,8 @@ def _run_eager(order):
             r = D._binary_bwd_eager(n.op[0], n.op[1], a[0], a[1], a[2], a[3])
         elif k == "fill":
             r = D._full_like_shape_eager(n.shape, n.dtype, a[0])
+        elif k == "mm":
+            r = D._matmul_eager(a[0], a[1], n.op, n.shape, n.dtype)
         else:
             r = D._bcast_to_eager(a[0], n.shape)
         stats["fallback_nodes"] += 1
@@ -369,6 +412,102 @@ def _bb_form(op, argno):
     if op == "hypot":
         return ("tern", 6, xi, "y")
     raise UnsupportedOnDevice("binary op %s has no gradient (zerograd)" % op)
+
+
+_REF_BASE = 0
+
+
+def _external(n, uses):
+    """Number of references to the pending node n from outside its DAG that need the value stored: everything that
+    holds n except the DAG's own bookkeeping (the `order` list, the call's own references), the uses inside the DAG
+    and the soft holders.  Always called as `_external(order[i], uses)`."""
+    return sys.getrefcount(n) - _REF_BASE - uses - n.soft
+
+
+def _calibrate_refs():
+    """The bookkeeping references seen by `_external(lst[i], 0)` for an object held by nothing but the list: measured
+    on a throwaway object instead of hard-coding CPython's calling convention (the count differs between interpreter
+    versions and builds; 3.14 borrowed references, tracers).  Returns None if the measurement is not stable."""
+    class _Probe:
+        __slots__ = ("soft",)
+
+        def __init__(self):
+            self.soft = 0
+    seen = set()
+    for _ in range(3):
+        lst = [_Probe(), _Probe()]
+        for i in range(len(lst)):
+            seen.add(_external(lst[i], 0))
+    return seen.pop() if len(seen) == 1 else None
+
+
+_REF_BASE = _calibrate_refs()
+_REFS_OK = _REF_BASE is not None
+if not _REFS_OK:          # cannot tell internal from external references: store every anchor (correct, just more writes)
+    _REF_BASE = -(1 << 30)
+
+_ACTS = {("b", "max"): "relu", ("u", "tanh"): "tanh", ("u", "sigm"): "sigm"}
+
+
+def _resolve_products(order, root):
+    """Evaluate the pending products (kind "mm") below `root`.  A product whose only use is `M .+ bias` with a column
+    vector bias -- optionally followed by max.(0, .), tanh.(.) or sigm.(.) as the only use of the sum -- runs as ONE
+    launch with the sum and the activation in its epilogue (ag_gemm_epilogue); only the values something outside
+    still needs are written (the product itself and, when no gradient rule reads it, the pre-activation sum are
+    never stored).  Any other product is evaluated by ag_gemm.  Returns True if anything was evaluated."""
+    if not any(n.kind == "mm" for n in order):
+        return False
+    uses = {}
+    for n in order:
+        for a in n.args:
+            if is_pending(a):
+                uses[id(a)] = uses.get(id(a), 0) + 1
+    n = a = None
+    # outside references first, while nothing but `order` and the nodes' own argument tuples holds the nodes
+    ext = [order[i] is root or _external(order[i], uses.get(id(order[i]), 0)) > 0 for i in range(len(order))]
+    index = {id(order[i]): i for i in range(len(order))}
+    users = {}
+    for n in order:
+        for a in n.args:
+            if is_pending(a):
+                users.setdefault(id(a), []).append(n)
+    n = a = None
+    for i in range(len(order)):
+        m = order[i]
+        if m.kind != "mm":
+            continue
+        us = users.get(id(m), [])
+        z = us[0] if len(us) == 1 and uses.get(id(m), 0) == 1 else None
+        bias = None
+        if z is not None and z.kind == "b" and z.op == "add" and z.shape == m.shape and not ext[i]:
+            other = z.args[1] if z.args[0] is m else z.args[0]
+            if isinstance(other, D.DArray) and not is_pending(other) and not other.tr and other.dtype == m.dtype \
+                    and other.shape in ((m.shape[0],), (m.shape[0], 1)):
+                bias = other
+        if bias is None:
+            m._set_storage(D._matmul_eager(m.args[0], m.args[1], m.op, m.shape, m.dtype))
+            stats["products_plain"] = stats.get("products_plain", 0) + 1
+            continue
+        z_needed = ext[index[id(z)]]
+        zu = users.get(id(z), [])
+        act, anode = "identity", None
+        if len(zu) == 1 and uses.get(id(z), 0) == 1 and zu[0].shape == z.shape:
+            c = zu[0]
+            if c.kind == "u" and ("u", c.op) in _ACTS:
+                act, anode = _ACTS[("u", c.op)], c
+            elif c.kind == "b" and c.op == "max" and ((c.args[0] == 0.0 and c.args[1] is z) if isinstance(c.args[0], float)
+                                                      else (isinstance(c.args[1], float) and c.args[1] == 0.0 and c.args[0] is z)):
+                act, anode = "relu", c
+        zs, as_ = D._gemm_epilogue(m.args[0], m.args[1], m.op, m.shape, m.dtype, bias, act, z_needed or anode is None)
+        stats["products_fused"] = stats.get("products_fused", 0) + 1
+        if anode is not None:
+            anode._set_storage(as_)
+            if z_needed:
+                z._set_storage(zs)
+        else:
+            z._set_storage(zs)
+        # m (and z when nothing needs it) stay pending: they are only held softly and would be recomputed if read
+    return True
 
 
 class _Codegen:
@@ -532,12 +671,15 @@ def _run_fused(order, root, reduce=None):
         for a in n.args:
             if is_pending(a):
                 uses[id(a)] = uses.get(id(a), 0) + 1
+    n = a = None
     anchors, outputs = [], []
     for idx in range(len(order)):
         n = order[idx]
         u = uses.get(id(n), 0)
-        # references: `order`, the local `n`, getrefcount's argument, one per use inside the DAG; more = external
-        ext = n is root or (sys.getrefcount(n) - 3 - u) > 0
+        # references from outside the DAG that need the value (tape Results that read it, outgrads, user variables)
+        n = None
+        ext = order[idx] is root or _external(order[idx], u) > 0
+        n = order[idx]
         if ext or u > 1:
             anchors.append(n)
             if ext:

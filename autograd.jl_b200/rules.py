@@ -35,8 +35,11 @@ class Primitive:
     """`@primitive f(args...),dy,y  rule1 rule2 ...`: a callable that records itself on the active
     tapes when any argument is boxed."""
 
-    def __init__(self, name, fwd, backs=(), only_first=False):
+    def __init__(self, name, fwd, backs=(), only_first=False, y_unused=False, args_unused=False):
         self.name, self.fwd, self.backs, self.only_first = name, fwd, tuple(backs), only_first
+        # which values the gradient rules read (core._mark_soft): y_unused = no rule reads the output;
+        # args_unused = True (no rule reads any argument's value) or a tuple of per-argument flags
+        self.y_unused, self.args_unused = y_unused, args_unused
 
     def __call__(self, *args, **kwargs):
         for a in args:
@@ -247,8 +250,8 @@ def _passthru(argno, negate=False):
     return rule
 
 
-add = primitive("+", _bin_fwd("add"), _passthru(1), _passthru(2))
-sub = primitive("-", _bin_fwd("sub"), _passthru(1), _passthru(2, negate=True))
+add = primitive("+", _bin_fwd("add"), _passthru(1), _passthru(2), y_unused=True, args_unused=True)
+sub = primitive("-", _bin_fwd("sub"), _passthru(1), _passthru(2, negate=True), y_unused=True, args_unused=True)
 mul = primitive(".*", _bin_fwd("mul"),
                 _bin_back("mul", 1, lambda dy, y, x1, x2: mul(dy, x2)),
                 _bin_back("mul", 2, lambda dy, y, x1, x2: mul(x1, dy)))
@@ -327,7 +330,8 @@ def _un_back(op, composite, needs_x, needs_y):
 
 
 def _unary(name, op, composite, needs_x, needs_y):
-    return primitive(name, _un_fwd(op), _un_back(op, composite, needs_x, needs_y))
+    return primitive(name, _un_fwd(op), _un_back(op, composite, needs_x, needs_y),
+                     y_unused=not needs_y, args_unused=(not needs_x,))
 
 
 _LN2, _LN10 = math.log(2.0), math.log(10.0)
@@ -571,7 +575,7 @@ def _matmul_back2(dy, y, x1, x2):
     return matmul(adjoint(x1), dy)
 
 
-matmul = primitive("*", _matmul_fwd, _matmul_back1, _matmul_back2)
+matmul = primitive("*", _matmul_fwd, _matmul_back1, _matmul_back2, y_unused=True)
 
 
 def _adjoint_fwd(x):

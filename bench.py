@@ -19,6 +19,14 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # The CPU arm uses every host core it is allowed to: torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    # workers, which silently made the N > 1 reference single-threaded in round 1.  Must happen before numpy
+    # (OpenBLAS) is imported.
+    _ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_ncores)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -28,6 +36,45 @@ BATCH = 65536
 LR = 0.1
 METRIC = "@diff+grad steps/sec (MNIST-shape MLP 784-64-10, Float32, batch 65536 per GPU)"
 UNIT = "steps/s"
+
+
+def workload_name(B):
+    """config.workload: the same string in both arms (the driver compares them)."""
+    return ("examples/mnist.jl MLP 784-64-10 softmax (configs[1]), batch %d per GPU, Float32, "
+            "@diff + grad + allreduce + axpy!; value counts one per-rank step per rank" % B)
+
+
+def load_workloads():
+    """autograd.jl_b200/workloads.py by file path: pure numpy model definitions.  The reference arm must not import
+    the product package (that would map libagb200.so into the CPU arm's process)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("agb200_workloads",
+                                                  os.path.join(ROOT, "autograd.jl_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", "0") or 0) or None
+
+
+def reference_runtime():
+    """prefer the real reference when it can run.  It is a Julia package: needs `julia` on PATH or
+    under baseline/_ref/.  Neither exists in this image, so the numpy restatement (oracle/agref.py) is timed."""
+    import shutil
+    j = shutil.which("julia")
+    if j is None:
+        for cand in (os.path.join(ROOT, "baseline", "_ref", "bin", "julia"), os.path.join(ROOT, "baseline", "_ref", "julia")):
+            if os.path.exists(cand):
+                j = cand
+    return {"julia": j, "baseline_ref": os.path.isdir(os.path.join(ROOT, "baseline", "_ref")),
+            "used": "oracle/agref.py (numpy restatement; julia not found)" if j is None else
+                    "oracle/agref.py (julia found at %s but AutoGrad.jl's dependencies cannot be resolved offline)" % j}
 
 
 def algo_bytes(B, s=4):
@@ -85,8 +132,7 @@ class Clocks:
 def cpu_reference_run(steps, warmup, budget_s=20.0):
     """The CPU restatement of the reference on the host cores: same tape, same temporaries."""
     from oracle import agref
-    import __graft_entry__ as ge
-    W = ge.load_package().workloads        # workload definitions only (pure Python, no device call)
+    W = load_workloads()                   # workload definitions only (pure numpy; the product package is not imported)
     rng = np.random.default_rng(1)
     w, _, _ = W.mnist_init(rng, 1)
     x, y = W.mnist_from_ubyte(*W.mnist_ubyte_batch(np.random.default_rng(1000), BATCH))   # the arrays of mnist.jl:80-81
@@ -107,21 +153,25 @@ def cpu_reference_run(steps, warmup, budget_s=20.0):
         if time.perf_counter() - t_start > budget_s and len(times) >= 3:
             break
     mean = sum(times) / len(times)
-    return {"value": 1.0 / mean, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": "%d full steps (forward+backward+axpy!) at batch %d Float32, numpy/OpenBLAS, all host threads"
-                      % (len(times), BATCH), "ms_per_step": mean * 1e3}, len(times)
+    nthr = blas_threads()
+    return {"value": 1.0 / mean, "unit": UNIT, "cores": nthr or os.cpu_count(), "kind": "port",
+            "host_cpus": os.cpu_count(), "blas_threads": nthr,
+            "sample": "%d full steps (forward+backward+axpy!) at batch %d Float32, numpy/OpenBLAS, %s BLAS threads"
+                      % (len(times), BATCH, nthr if nthr else "?"), "ms_per_step": mean * 1e3}, len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cb, done = cpu_reference_run(args.steps, min(args.warmup, 2), budget_s=120.0)
+    W_ = max(args.warmup, 3)               # the same warm-up rule as the device arm
+    cb, done = cpu_reference_run(args.steps, W_, budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": cb["ms_per_step"],
+            "steps": done, "warmup": W_, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "examples/mnist.jl MLP 784-64-10 softmax, batch 65536, Float32, "
-                                   "@diff + grad + axpy! (CPU restatement of the reference; Julia absent)"},
+            "config": {"workload": workload_name(BATCH), "global_batch": BATCH, "parallelism": "cpu",
+                       "arm": "CPU restatement of the reference (oracle/agref.py, numpy/OpenBLAS) on rank 0's host cores",
+                       "reference_runtime": reference_runtime()},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -331,6 +381,7 @@ def main():
     # ---- dominant kernel, timed alone on the library stream (inputs > L2)
     cand = {}
     a1 = ag.matmul(params[0].value, xd)
+    a1.ptr                                   # products are deferred (lazy.py): touching the pointer evaluates them
     dy1 = ag.DArray.empty(a1.shape, np.float32)
     ag._lib.check(ag._lib.lib.ag_fill(C_.c_void_p(dy1.ptr), dy1.size, 0, 0.001))
 
@@ -344,12 +395,18 @@ def main():
         b.record()
         return b.elapsed_ms_since(a) / reps
     s = 4
-    cand["gemm_fwd w1*x (64x784 * 784xB, NN)"] = (time_op(lambda: ag.matmul(params[0].value, xd)),
+    cand["gemm_fwd w1*x (64x784 * 784xB, NN)"] = (time_op(lambda: ag.matmul(params[0].value, xd).ptr),
                                                    s * (64 * 784 + 784 * B + 64 * B), 2.0 * 64 * 784 * B)
     eng_f = ag.gemm_engine()
-    cand["gemm_dw1 dy*x' (64xB * Bx784, NT)"] = (time_op(lambda: ag.matmul(dy1, ag.adjoint(xd))),
+    cand["gemm_dw1 dy*x' (64xB * Bx784, NT)"] = (time_op(lambda: ag.matmul(dy1, ag.adjoint(xd)).ptr),
                                                   s * (64 * B + 784 * B + 64 * 784), 2.0 * 64 * 784 * B)
     eng_b = ag.gemm_engine()
+    # the form the step actually runs: max.(0, w1*x .+ b1) as ONE launch (bias and relu in the product's epilogue,
+    # writes a2 and a3, never writes w1*x); algorithmic bytes of the three tape nodes it replaces
+    t_fused = time_op(lambda: ag.relu(ag.add(ag.matmul(params[0].value, xd), params[1].value)).ptr)
+    fused_fwd = {"ms": t_fused, "engine": ag.gemm_engine(),
+                 "algorithmic_bytes": s * (64 * 784 + 784 * B + 64 * B) + s * (3 * 64 * B) + s * (3 * 64 * B)}
+    fused_fwd["GBps"] = fused_fwd["algorithmic_bytes"] / (t_fused * 1e-3) / 1e9
     top = max(cand, key=lambda k: cand[k][0])
     t_ms, bytes_, flops = cand[top]
     # the two elementwise launches of the step that move > 32 MB, timed alone the same way:
@@ -401,7 +458,8 @@ def main():
             g.destroy()
         return max(out[0] - out[1], 1e-6)
     elementwise = {
-        "fused bias+relu fwd (64xB): a1 -> a2, a3": (time_op_flushed(ew_fwd), s * 3 * N1),
+        "bias+relu fwd as its own launch (64xB): a1 -> a2, a3 [no longer in the step: runs in the w1*x epilogue]":
+            (time_op_flushed(ew_fwd), s * 3 * N1),
         "fused relu gradient + bias-gradient row sums (64xB)": (time_op_flushed(ew_bwd), s * (4 * N1 + 64)),
     }
     del flush_buf
@@ -425,6 +483,8 @@ def main():
                 "ms_per_launch": t_ms, "tflops": flops / (t_ms * 1e-3) / 1e12,
                 "all": {k: {"ms": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9,
                             "frac": v[1] / (v[0] * 1e-3) / 1e9 / hbm_peak} for k, v in cand.items()},
+                "fused_forward_layer1": dict(fused_fwd, frac=fused_fwd["GBps"] / hbm_peak,
+                                             note="w1*x, .+ b1 and max.(0,.) in one launch; bytes of the three unfused nodes"),
                 "elementwise": {k: {"ms": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9,
                                     "frac": v[1] / (v[0] * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": v[1],
                                     "l2": "flushed (256 MB written) before every launch; graph replay, flush-only replay subtracted"}
@@ -450,8 +510,7 @@ def main():
             "metric": METRIC, "value": world * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W_, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "examples/mnist.jl MLP 784-64-10 softmax (configs[1]), batch %d per GPU, Float32, "
-                                   "@diff + grad + allreduce + axpy!; value counts one per-rank step per rank" % B,
+            "config": {"workload": workload_name(B),
                        "global_batch": gB, "parallelism": "dp%d" % world, "replay": replay,
                        "allreduce": ("one-shot peer-memory kernel over NVLink, flag-in-data, fused axpy! (ag_p2p_allreduce_multi)" if dp.p2p_cap else
                                      "NCCL") if world > 1 else None,

@@ -301,10 +301,21 @@ ag_status ag_scale(int32_t dtype, double alpha, void* x, int64_t n);
 ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
                   double alpha, const void* A, int64_t lda, const void* B, int64_t ldb, double beta,
                   void* C, int64_t ldc);
+/* The product followed by the `.+ b` and the activation that every model of the reference applies to it
+ * (examples/mnist.jl:32 `max.(0, w*x .+ b)`, examples/charlm.jl:74-77 `sigm.(W*x .+ b)`, `tanh.(W*x .+ b)`), i.e. the tape
+ * nodes `*` (src/base.jl:26), broadcast `+` (src/base.jl:21) and the elementwise map (src/math.jl:54,74) evaluated by
+ * ONE launch: z = op(A)*op(B) .+ bias (bias: M values or NULL), a = act.(z), act an AG_U_* id out of
+ * {AG_U_IDENTITY, AG_U_RELU (max.(0,z)), AG_U_TANH, AG_U_SIGM}.  C2 == NULL: C receives a.  C2 != NULL: C receives z and
+ * C2 receives a (the tape keeps both when a gradient rule reads both, e.g. relu's mask y .== x).  Each step is rounded
+ * on its own, so the values are bit-identical to ag_gemm + ag_binary_fwd + ag_unary_fwd.  Float32 shapes the tcgen05
+ * engine takes run fused (bias and activation in its epilogue); anything else runs exactly those three kernels. */
+ag_status ag_gemm_epilogue(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                           const void* A, int64_t lda, const void* B, int64_t ldb, const void* bias, int32_t act,
+                           void* C, void* C2, int64_t ldc);
 /* Select the Float32 GEMM engine: 0 = auto, 1 = force FFMA, 2 = force tcgen05 (error if the
  * shape does not qualify).  Test hook. */
 ag_status ag_gemm_set_engine(int32_t engine);
-/* Name of the engine the last ag_gemm call used ("ffma", "dfma", "tcgen05"). */
+/* Name of the engine the last ag_gemm call used ("ffma", "dfma", "tcgen05", "tcgen05+epilogue", "skinny", ...). */
 ag_status ag_gemm_last_engine(char* buf, int64_t buflen);
 
 /* ---- indexing: getindex / Sparse / addtoindex! ------------------------------------------------- */

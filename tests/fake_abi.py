@@ -407,6 +407,19 @@ class FakeLib:
         c[:] = (r + (beta * c if beta != 0 else 0)).astype(T)
         return 0
 
+    def ag_gemm_epilogue(self, dtype, ta, tb, M, N, K, A, lda, B, ldb, bias, act, Cp, C2p, ldc):
+        T = _DT[dtype]
+        self.ag_gemm(dtype, ta, tb, M, N, K, 1.0, A, lda, B, ldb, 0.0, Cp, ldc)
+        c = _arr(Cp, ldc * N, T).reshape((ldc, N), order="F")[:M]
+        if _p(bias):
+            c[:] = (c + _arr(bias, M, T)[:, None]).astype(T)
+        a = np.asarray(_U[act][0](c.copy()), dtype=T)          # the same expression as the single kernels, in T
+        if _p(C2p):
+            _arr(C2p, ldc * N, T).reshape((ldc, N), order="F")[:M] = a
+        else:
+            c[:] = a
+        return 0
+
     def ag_gemm_set_engine(self, e): return 0
 
     def ag_gemm_last_engine(self, buf, n):
