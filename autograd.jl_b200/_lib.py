@@ -71,6 +71,7 @@ _SIGS = {
     "ag_scale": [i32, dbl, vp, i64],
     "ag_gemm": [i32, i32, i32, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64],
     "ag_gemm_epilogue": [i32, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, vp, i64],
+    "ag_gemm_epilogue_query": [i32, i32, i32, i64, i64, i64, vp, i64, vp, i64, C.POINTER(i32)],
     "ag_gemm_set_engine": [i32],
     "ag_gemm_last_engine": [C.c_char_p, i64],
     "ag_ubyte_to_float": [i32, vp, vp, i64, dbl],

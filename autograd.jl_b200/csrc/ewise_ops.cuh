@@ -155,13 +155,17 @@ AG_DEF_U(AG_U_BESSELY1, true, false, y1(x), (y0(x) - bessel_yn2(x)) / T(2))
   X(AG_U_LGAMMA) X(AG_U_DIGAMMA) X(AG_U_TRIGAMMA) X(AG_U_BESSELJ0) X(AG_U_BESSELJ1) X(AG_U_BESSELY0)              \
   X(AG_U_BESSELY1)
 
+// sign bit as a bit test (signbit() compiles to an out-of-line call on some paths: 11 us on the 64 x 65536 relu
+// epilogue of the product, tests/probe_epilogue.py)
+__device__ __forceinline__ bool sbit(float a) { return (__float_as_uint(a) >> 31) != 0u; }
+__device__ __forceinline__ bool sbit(double a) { return (__double2hiint(a) >> 31) != 0; }
 template <typename T>
-__device__ __forceinline__ T jmax(T a, T b) {  // Julia max: NaN-propagating
-  return (a != a || b != b) ? (a + b) : (a > b ? a : (b > a ? b : (signbit(a) ? b : a)));
+__device__ __forceinline__ T jmax(T a, T b) {  // Julia max: NaN-propagating, max(-0.0, 0.0) = 0.0
+  return (a != a || b != b) ? (a + b) : (a > b ? a : (b > a ? b : (sbit(a) ? b : a)));
 }
 template <typename T>
 __device__ __forceinline__ T jmin(T a, T b) {
-  return (a != a || b != b) ? (a + b) : (a < b ? a : (b < a ? b : (signbit(a) ? a : b)));
+  return (a != a || b != b) ? (a + b) : (a < b ? a : (b < a ? b : (sbit(a) ? a : b)));
 }
 
 #define AG_DEF_F(NAME, EXPR)                                          \

@@ -260,6 +260,28 @@ ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int6
   return gemm_simt<float>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
+// would ag_gemm_epilogue run this product on the tcgen05 engine (bias and activation in its epilogue)?
+static bool epilogue_runs_fused(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                                const void* A, int64_t lda, const void* B, int64_t ldb, const void* C, const void* C2,
+                                int64_t ldc) {
+  if (!(dtype == AG_F32 && g_engine != 1 && K > 0 && ldc == M && (!C2 || ((uintptr_t)C2 & 15) == 0))) return false;
+  if (K >= 32 && M * N <= 1024 && K * M * N <= ((int64_t)1 << 22)) return false;     // warp-per-output shapes
+  if (!gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb, C, ldc)) return false;
+  if (g_engine != 2 && gemm_skinny_takes(dtype, transA, transB, M, N, K)) return false;   // those stay unfused
+  return true;
+}
+
+/* *fused_out = 1 if ag_gemm_epilogue would run this product as one launch.  The host defers `w*x .+ b` only then;
+ * otherwise the sum stays part of the elementwise chain that follows it. */
+ag_status ag_gemm_epilogue_query(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                                 const void* A, int64_t lda, const void* B, int64_t ldb, int32_t* fused_out) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(fused_out, AG_EINVAL, "ag_gemm_epilogue_query: null");
+  // C / C2 come from the pool (512-byte aligned): a 16-byte aligned stand-in
+  *fused_out = epilogue_runs_fused(dtype, transA, transB, M, N, K, A, lda, B, ldb, (const void*)16, nullptr, M) ? 1 : 0;
+  return AG_OK;
+}
+
 /* C = op(A)*op(B) .+ bias (bias: M values, broadcast along dim 2), then optionally an activation: one launch when the
  * tcgen05 engine takes the shape (bias and activation in its epilogue), otherwise the same three kernels the unfused
  * tape would run (product, broadcast add, elementwise map) -- results are identical either way. */
@@ -281,20 +303,13 @@ ag_status ag_gemm_epilogue(int32_t dtype, int32_t transA, int32_t transB, int64_
     AG_CHECK(lda >= (transA ? K : M) && ldb >= (transB ? N : K), AG_EINVAL,
              "ag_gemm_epilogue: leading dimension too small (DimensionMismatch)");
   }
-  const bool tc_ok = dtype == AG_F32 && g_engine != 1 && K > 0 && ldc == M && (!C2 || ((uintptr_t)C2 & 15) == 0) &&
-                     !(K >= 32 && M * N <= 1024 && K * M * N <= ((int64_t)1 << 22)) &&
-                     gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
-  if (tc_ok) {
-    bool skinny_first = false;
-    if (g_engine != 2) skinny_first = gemm_skinny_takes(dtype, transA, transB, M, N, K);   // those stay unfused (below)
-    if (!skinny_first) {
-      TcEpilogue e;
-      e.bias = bias;
-      e.act = act == AG_U_RELU ? TC_ACT_RELU : act == AG_U_TANH ? TC_ACT_TANH : act == AG_U_SIGM ? TC_ACT_SIGM : TC_ACT_NONE;
-      e.out2 = C2;
-      g_last_engine = "tcgen05+epilogue";
-      return gemm_tc(transA, transB, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, &e);
-    }
+  if (epilogue_runs_fused(dtype, transA, transB, M, N, K, A, lda, B, ldb, C, C2, ldc)) {
+    TcEpilogue e;
+    e.bias = bias;
+    e.act = act == AG_U_RELU ? TC_ACT_RELU : act == AG_U_TANH ? TC_ACT_TANH : act == AG_U_SIGM ? TC_ACT_SIGM : TC_ACT_NONE;
+    e.out2 = C2;
+    g_last_engine = "tcgen05+epilogue";
+    return gemm_tc(transA, transB, M, N, K, 1.0, A, lda, B, ldb, 0.0, C, ldc, &e);
   }
   // unfused: product, then z = C .+ bias in place, then the activation (into C2, or in place)
   AG_CHECK(ldc == M, AG_EUNSUPPORTED, "ag_gemm_epilogue: ldc != M");

@@ -182,7 +182,7 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 }
 template <int ACT>
 __device__ __forceinline__ float tc_activation(float z) {
-  if (ACT == TC_ACT_RELU) return jmax(0.0f, z);                  // max.(0, z): the FMax map of ewise_ops.cuh
+  if (ACT == TC_ACT_RELU) return relu(z);     // max.(0, z): same values as the FMax map jmax(0, z) of ewise_ops.cuh
   if (ACT == TC_ACT_TANH) return U<AG_U_TANH, float>::f(z);
   if (ACT == TC_ACT_SIGM) return U<AG_U_SIGM, float>::f(z);
   return z;

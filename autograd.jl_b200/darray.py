@@ -625,6 +625,14 @@ def _matmul_eager(A, Bm, op, out_shape, dtype):
     return c
 
 
+def _gemm_epilogue_fused(A, Bm, op, dtype):
+    """Would ag_gemm_epilogue run this product as one launch?"""
+    ta, tb, m, n, ka, lda, ldb = op
+    flag = C.c_int32(0)
+    check(lib.ag_gemm_epilogue_query(_DT[np.dtype(dtype)], ta, tb, m, n, ka, vptr(A), lda, vptr(Bm), ldb, C.byref(flag)))
+    return bool(flag.value)
+
+
 def _gemm_epilogue(A, Bm, op, out_shape, dtype, bias, act, want_z):
     """(z, a) = (op(A)*op(B) .+ bias, act.(z)) by one ag_gemm_epilogue call; z is None unless want_z (then the
     activation, if any, goes to a second array)."""

@@ -482,7 +482,8 @@ def _resolve_products(order, root):
         if z is not None and z.kind == "b" and z.op == "add" and z.shape == m.shape and not ext[i]:
             other = z.args[1] if z.args[0] is m else z.args[0]
             if isinstance(other, D.DArray) and not is_pending(other) and not other.tr and other.dtype == m.dtype \
-                    and other.shape in ((m.shape[0],), (m.shape[0], 1)):
+                    and other.shape in ((m.shape[0],), (m.shape[0], 1)) \
+                    and D._gemm_epilogue_fused(m.args[0], m.args[1], m.op, m.dtype):
                 bias = other
         if bias is None:
             m._set_storage(D._matmul_eager(m.args[0], m.args[1], m.op, m.shape, m.dtype))

@@ -129,6 +129,40 @@ class Clocks:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(local_rank, world):
+    """Bind this rank's host threads to the CPUs local to its GPU (NVML's affinity mask = the GPU's NUMA node),
+    split evenly among the ranks that share that mask, before any pinned staging buffer is allocated: the pages
+    are then first-touched on the GPU's own node and the ranks' host loops do not migrate.  (Round 1: 8 ranks
+    pulling 208 MB/step each through unpinned processes collapsed the end-to-end rate to 44 %.)"""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            peers = []          # local ranks sharing this mask
+            for r in range(world):
+                try:
+                    hw = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r), (ncpu + 63) // 64)
+                    if list(hw) == list(words):
+                        peers.append(r)
+                except Exception:
+                    pass
+            k = peers.index(local_rank) if local_rank in peers else 0
+            share = max(1, len(allowed) // max(len(peers), 1))
+            mine = allowed[k * share:(k + 1) * share] or allowed
+            os.sched_setaffinity(0, mine)
+            info = {"bound": True, "gpu_local_cpus": len(allowed), "ranks_on_node": len(peers), "cpus": len(mine)}
+        pynvml.nvmlShutdown()
+    except Exception as exc:        # noqa: BLE001
+        info["error"] = str(exc)[:120]
+    return info
+
+
 def cpu_reference_run(steps, warmup, budget_s=20.0):
     """The CPU restatement of the reference on the host cores: same tape, same temporaries."""
     from oracle import agref
@@ -186,6 +220,7 @@ def main():
     ap.add_argument("--impl", default="agb200")
     ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (housing, sweep, charlm, rnn)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -199,6 +234,7 @@ def main():
     K = args.steps
     B = args.batch
 
+    affinity = bind_to_gpu_numa(local, world)     # before any pinned allocation (first touch = this rank's node)
     import __graft_entry__ as ge
     ag = ge.load_package()
     ag.init(local)
@@ -490,6 +526,34 @@ def main():
                                     "l2": "flushed (256 MB written) before every launch; graph replay, flush-only replay subtracted"}
                                 for k, v in elementwise.items()}}
 
+    # ---- numeric check of the N-rank step, and the other BASELINE configs (bench_configs.py)
+    import bench_configs as BC
+
+    def allmax(v):
+        if dist is None:
+            return v
+        import torch
+        tt_ = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        return float(tt_[0])
+
+    def allgather_obj(o):
+        out = [None] * world
+        dist.all_gather_object(out, o)
+        return out
+    dpc = BC.dp_check(ag, Wl, dp, rank, world, allgather_obj if dist is not None else None)
+    secondary = {}
+    if not args.no_secondary:
+        for name, fn in (("housing", lambda: BC.housing(ag, Wl, barrier, allmax, world)),
+                         ("sweep", lambda: BC.sweep(ag, Wl, barrier, allmax, world, hbm_peak)),
+                         ("charlm", lambda: BC.lstm(ag, Wl, dp, barrier, allmax, world, peaks)),
+                         ("rnn_grad_of_grad", lambda: BC.rnn_grad_of_grad(ag, Wl, barrier, allmax, world, peaks))):
+            try:
+                secondary[name] = fn()
+            except Exception as exc:        # noqa: BLE001  (a failing secondary config must not hide the headline)
+                secondary[name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+            ag.sync()
+
     # ---- max over ranks
     ms_all, e2e_all = ms, e2e_s
     if dist is not None:
@@ -523,15 +587,22 @@ def main():
             "step_hbm_gbs": (fb + bb) / (ms_per_step * 1e-3) / 1e9,
             "algorithmic_bytes": {"forward": fb, "backward": bb},
             "clocks": clk,
-            "e2e": {"value": world / e2e_all, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes + yh.nbytes),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_all * 1e3,
-                    "input": "the reference's host arrays: x (784,B) and one-hot y (10,B) Float32, pinned; "
-                             "the copy of batch i+1 overlaps step i (second stream), one h2d + one d2h per step"},
-            "e2e_ubyte": {"value": world / e2e_ub_s, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes),
-                          "d2h_bytes_per_step": 4, "ms_per_step": e2e_ub_s * 1e3,
-                          "input": "the same batch as idx-ubyte bytes (1 B per pixel / label); x ./ 255f0 and the one-hot "
-                                   "y of examples/mnist.jl:80-81 rebuilt on the device, bit-identical (asserted)"},
+            "e2e": {"value": world / e2e_ub_s, "unit": UNIT, "h2d_bytes_per_step": int(batch.h2d_bytes),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ub_s * 1e3,
+                    "h2d_GBps_per_rank": batch.h2d_bytes / e2e_ub_s / 1e9,
+                    "input": "the batch in the reference loader's own format (examples/mnist.jl:77-96: idx-ubyte, 1 B per "
+                             "pixel / label) in pinned host memory; x ./ 255f0 and the one-hot y of :80-81 are rebuilt on "
+                             "the device, bit-identical to the host arrays (asserted); the copy of batch i+1 overlaps "
+                             "step i (second stream); one h2d + one d2h (loss) per step",
+                    "host_binding": affinity},
+            "e2e_f32": {"value": world / e2e_all, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes + yh.nbytes),
+                        "d2h_bytes_per_step": 4, "ms_per_step": e2e_all * 1e3,
+                        "h2d_GBps_per_rank": (xh.nbytes + yh.nbytes) / e2e_all / 1e9,
+                        "input": "the host arrays the reference builds from those bytes: x (784,B) and one-hot y (10,B) "
+                                 "Float32, pinned (4x the bytes; PCIe-bound)"},
             "gpu_launches": int(launches),
+            "dp_check": dpc,
+            "secondary": secondary,
             "roofline": roofline,
             "cpu_baseline": cpu_base,
         }

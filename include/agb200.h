@@ -312,6 +312,11 @@ ag_status ag_gemm(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int6
 ag_status ag_gemm_epilogue(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
                            const void* A, int64_t lda, const void* B, int64_t ldb, const void* bias, int32_t act,
                            void* C, void* C2, int64_t ldc);
+/* *fused_out = 1 when ag_gemm_epilogue would run this product as ONE launch (tcgen05 engine), 0 when it would run the
+ * separate kernels.  The host defers `w*x .+ b` into the product only in the first case; otherwise the sum stays part of
+ * the fused elementwise chain that follows it (ag_ewise_fused). */
+ag_status ag_gemm_epilogue_query(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                                 const void* A, int64_t lda, const void* B, int64_t ldb, int32_t* fused_out);
 /* Select the Float32 GEMM engine: 0 = auto, 1 = force FFMA, 2 = force tcgen05 (error if the
  * shape does not qualify).  Test hook. */
 ag_status ag_gemm_set_engine(int32_t engine);
