@@ -22,6 +22,8 @@ class DataParallel:
         (ag_p2p_*) for buckets up to p2p_bytes; larger buckets and missing peer access use NCCL."""
         self.rank, self.world = rank, world
         self.p2p_cap = 0
+        self._allgather = allgather_bytes
+        self._layouts_ok = set()
         if world > 1:
             idbuf = (C.c_uint8 * 128)()
             if rank == 0:
@@ -70,7 +72,7 @@ class DataParallel:
                 views.append(None)
                 continue
             g = D.materialize(g)
-            D.slab_copy(g, n, 0, b, tot, off, 1, n, 1)
+            D.slab_copy(g, n, 0, b, tot, off, 1, n, 1, fresh=True)
             views.append(DArray(b.buf, b.ptr + off * b.dtype.itemsize, g.shape, b.dtype))
             off += n
         if self.p2p_cap and b.dtype == np.float32 and tot * 4 <= min(self.p2p_cap, 1 << 20):
@@ -94,10 +96,15 @@ class DataParallel:
                 [g.full() if isinstance(g, Sparse) else g for g in grads]
             return self._clipped_update(alpha, reduced, params, float(gclip))
         dense = [g.full() if isinstance(g, Sparse) else g for g in grads]
+        if self.world > 1:
+            # a Param without a gradient on THIS rank (`nothing`, src/core.jl:215-216) still takes part in the sum: the
+            # segment layout of the collective must not depend on the data of one rank
+            dense = [D.zeros(value(p).shape, value(p).dtype) if g is None else g for g, p in zip(dense, params)]
         lazy.flush()        # the collective and the update work in place
         live = [(D.materialize(g), value(p)) for g, p in zip(dense, params) if g is not None]
         if not live:
             return dense
+        self._check_layout([(g.size, str(g.dtype)) for g, _ in live])
         dt = live[0][0].dtype
         nbytes = sum(-(-g.size // 4) * 4 for g, _ in live) * dt.itemsize
         fits = len(live) <= 16 and all(g.dtype == dt and w.dtype == dt for g, w in live)
@@ -138,6 +145,22 @@ class DataParallel:
             if g is not None:
                 D.axpy_(alpha, g, value(p))
         return reduced
+
+    def _check_layout(self, layout):
+        """Every rank must hand the collective the same segments (count, sizes, eltype) and so make the same choice
+        between the peer-memory kernel and NCCL: a mismatch would otherwise end in a hang inside the kernel.  The
+        layouts are compared once per distinct layout (one small host-side allgather), not per step."""
+        if self.world == 1 or self._allgather is None:
+            return
+        import hashlib
+        h = hashlib.sha1(repr(layout).encode()).digest()
+        if h in self._layouts_ok:
+            return
+        got = self._allgather(h)
+        if any(x != h for x in got):
+            raise D.L.DeviceError("DataParallel.update: ranks disagree on the gradient layout (this rank: %d segments %s); "
+                                  "every rank must pass the same Params in the same order" % (len(layout), layout[:4]))
+        self._layouts_ok.add(h)
 
     def _clipped_update(self, alpha, dense, params, gclip):
         from .core import value

@@ -84,6 +84,31 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Waits on peers are bounded by a wall-clock deadline (AGB_P2P_TIMEOUT_MS, default 10 minutes: a rank that is merely
+// late -- data loading, a checkpoint write, first-call compilation -- must not kill the job; NCCL would simply wait).
+// A wait that does expire raises a sticky device flag that the next ag_sync reports as AG_ENCCL; the kernel does
+// not __trap (a trap poisons the CUDA context of the whole process).
+__device__ int32_t g_p2p_timeout_flag = 0;
+__device__ __forceinline__ uint64_t gtimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct Deadline {
+  uint64_t t0, limit_ns;
+  uint32_t spin;
+  __device__ __forceinline__ Deadline(uint64_t limit) : t0(0), limit_ns(limit), spin(0) {}
+  // true when the wait has expired (checked every 4096 polls, so the clock read costs nothing on the fast path)
+  __device__ __forceinline__ bool expired(int who) {
+    if ((++spin & 4095u) != 0) return false;
+    const uint64_t now = gtimer_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    if (now - t0 < limit_ns) return false;
+    atomicExch(&g_p2p_timeout_flag, 1 + who);
+    return true;
+  }
+};
+
 constexpr int P2P_MAXSEG = 16;
 struct P2PSeg {
   void* src;        // this rank's gradient (overwritten with the global sum)
@@ -95,6 +120,7 @@ struct P2PArgs {
   P2PSeg seg[P2P_MAXSEG];
   int nseg;
   double alpha;
+  uint64_t timeout_ns; // wall-clock bound of every wait on a peer
   const void* scale;   // optional device scalar multiplied into alpha (gradient clipping); nullptr: none
 };
 
@@ -147,13 +173,9 @@ __global__ void __launch_bounds__(256)
     st_release_sys((uint32_t*)((uint8_t*)peers[threadIdx.x] + 1024) + rank * P2P_MAXBLK + blockIdx.x, e + 1);
     // phase 2: wait for slice b of peer `threadIdx.x`
     const uint32_t* f = flags + threadIdx.x * P2P_MAXBLK + blockIdx.x;
-    uint32_t spin = 0;
+    Deadline dl(a.timeout_ns);
     while ((int32_t)(ld_acquire_sys(f) - (e + 1)) < 0) {
-      if (++spin > (1u << 26)) {
-        printf("libagb200 p2p allreduce: rank %d block %d timed out waiting for rank %d (epoch %u)\n", rank,
-               blockIdx.x, threadIdx.x, e);
-        __trap();
-      }
+      if (dl.expired((int)threadIdx.x)) break;           // reported by the next ag_sync (AG_ENCCL)
     }
   }
   __syncthreads();
@@ -244,13 +266,10 @@ __global__ void __launch_bounds__(256)
     for (int r = 0; r < nranks; ++r) {
       const uint2* src = recv + (size_t)r * slot_words + i;
       uint2 w;
-      uint32_t spin = 0;
+      Deadline dl(a.timeout_ns);
       do {
         asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(src) : "memory");
-        if (++spin > (1u << 26)) {
-          printf("libagb200 p2p LL allreduce: rank %d timed out on slot %d (epoch %u)\n", rank, r, e);
-          __trap();
-        }
+        if (w.y != flag && dl.expired(r)) break;         // reported by the next ag_sync (AG_ENCCL)
       } while (w.y != flag);
       sum += __uint_as_float(w.x);
     }
@@ -335,8 +354,26 @@ static ag_status fill_args(P2PArgs& a, int32_t dtype, int32_t nseg, void* const*
   a.nseg = nseg;
   a.alpha = alpha;
   a.scale = nullptr;
+  static const uint64_t timeout_ns = []() {
+    const char* e = getenv("AGB_P2P_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 600000.0;
+    return (uint64_t)((ms > 1.0 ? ms : 1.0) * 1.0e6);
+  }();
+  a.timeout_ns = timeout_ns;
   *total_out = off;
   return AG_OK;
+}
+
+// Called by ag_sync: a peer wait that expired since the last check (0 = none, else 1 + the rank waited for).
+int comm_take_timeout() {
+  if (!g_p2p.peer_dev) return 0;
+  int32_t h = 0;
+  if (cudaMemcpyFromSymbol(&h, g_p2p_timeout_flag, sizeof(h)) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (h) {
+    const int32_t z = 0;
+    cudaMemcpyToSymbol(g_p2p_timeout_flag, &z, sizeof(z));
+  }
+  return h;
 }
 
 }  // namespace agb
@@ -402,7 +439,8 @@ ag_status ag_p2p_allreduce_multi(int32_t dtype, int32_t nseg, void* const* src, 
   AG_CHECK(bytes <= g_p2p.cap, AG_EINVAL, "ag_p2p_allreduce_multi: %zu bytes exceed the symmetric buffer (%zu)",
            bytes, g_p2p.cap);
   Context& c = ctx();
-  if (dtype == AG_F32 && bytes <= g_p2p.ll_cap && !getenv("AGB_P2P_NO_LL")) {
+  static const bool no_ll = getenv("AGB_P2P_NO_LL") != nullptr;      // experiment knob, read once
+  if (dtype == AG_F32 && bytes <= g_p2p.ll_cap && !no_ll) {
     int64_t blocks = cdiv(total, 256);
     if (blocks > 2 * c.num_sms) blocks = 2 * c.num_sms;
     k_p2p_allreduce_ll<<<(unsigned)blocks, 256, 0, c.stream>>>(g_p2p.peer_dev, g_p2p.nranks, g_p2p.rank,

@@ -51,6 +51,7 @@ static std::unordered_map<uint64_t, GraphRec*> g_graphs;
 static uint64_t g_next_graph = 1;
 static uint64_t g_capturing_graph = 0;
 static int64_t g_capture_launch0 = 0;
+static std::vector<void*> g_parked_ws;     // workspaces outgrown while graphs that point into them exist
 
 static size_t round_size(size_t b) {
   if (b == 0) b = 1;
@@ -93,7 +94,9 @@ static ag_status pool_alloc(size_t bytes, void** out) {
     cudaError_t e = cudaMalloc(&p, sz);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      trim_locked();
+      // free cached blocks and retry -- but not while graphs exist: a block the host has freed may still be read by
+      // a captured kernel that did not own it (an input of the captured step)
+      if (g_graphs.empty()) trim_locked();
       e = cudaMalloc(&p, sz);
       if (e != cudaSuccess) {
         cudaGetLastError();
@@ -144,7 +147,14 @@ void* workspace(size_t bytes) {
     return nullptr;
   }
   cudaStreamSynchronize(c.stream);
-  if (c.ws) cudaFree(c.ws);
+  // Instantiated graphs have the workspace pointer baked into their kernel arguments (split-K partials, reduction
+  // partials, sort scratch): while any graph exists the old block is parked, not freed, until the last graph is
+  // destroyed -- replaying a graph after an eager call grew the workspace must not touch freed memory.
+  if (c.ws) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_graphs.empty()) cudaFree(c.ws);
+    else g_parked_ws.push_back(c.ws);
+  }
   size_t nb = bytes * 2;
   if (cudaMalloc(&c.ws, nb) != cudaSuccess) {
     cudaGetLastError();
@@ -248,6 +258,14 @@ ag_status ag_shutdown(void) {
 ag_status ag_sync(void) {
   AG_REQUIRE_INIT();
   AG_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (!ctx().capturing) {
+    const int who = comm_take_timeout();
+    if (who) {
+      set_error("peer-memory allreduce: the wait for rank %d expired (AGB_P2P_TIMEOUT_MS); the ranks' parameters "
+                "are no longer in step", who - 1);
+      return AG_ENCCL;
+    }
+  }
   if (g_oob_armed && g_oob && !ctx().capturing) {
     int32_t h = 0;
     AG_CUDA(cudaMemcpy(&h, g_oob, 4, cudaMemcpyDeviceToHost));
@@ -314,6 +332,8 @@ ag_status ag_pool_trim(void) {
   AG_REQUIRE_INIT();
   AG_CUDA(cudaStreamSynchronize(ctx().stream));
   std::lock_guard<std::mutex> lk(g_mu);
+  AG_CHECK(g_graphs.empty(), AG_ESTATE, "ag_pool_trim: %zu captured graphs may read cached blocks; destroy them first",
+           g_graphs.size());
   trim_locked();
   return AG_OK;
 }
@@ -539,6 +559,10 @@ ag_status ag_graph_destroy(uint64_t id) {
   }
   delete gr;
   g_graphs.erase(it);
+  if (g_graphs.empty()) {                   // nothing can replay into the outgrown workspaces any more
+    for (void* p : g_parked_ws) cudaFree(p);
+    g_parked_ws.clear();
+  }
   return AG_OK;
 }
 

@@ -780,7 +780,12 @@ def scatter_add_(dest, flat_idx, vals, block=1):
     return dest
 
 
-def slab_copy(src, src_red, src_off, dst, dst_red, dst_off, inner, length, outer):
+def slab_copy(src, src_red, src_off, dst, dst_red, dst_off, inner, length, outer, fresh=False):
+    """Raw strided copy into `dst`.  fresh=True: dst was allocated by the caller for this purpose and nothing pending
+    can read it; otherwise dst is an existing array and everything pending is evaluated first (a pending operation
+    reads its leaves later than program order says -- lazy.py safety rule 2)."""
+    if not fresh:
+        _lazy.flush()
     check(lib.ag_slab_copy(src.dt, vptr(src), src_red, src_off, vptr(dst), dst_red, dst_off, inner, length, outer))
     return dst
 

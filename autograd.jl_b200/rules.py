@@ -695,7 +695,7 @@ def _cat_fwd(*xs, dims):
             x = D.full_like_shape((1,), dtype, x)
         x = D.materialize(x)
         if s[dims]:
-            D.slab_copy(x, s[dims], 0, out, tot, off, inner, s[dims], outer)
+            D.slab_copy(x, s[dims], 0, out, tot, off, inner, s[dims], outer, fresh=True)
         off += s[dims]
     return out
 
@@ -715,7 +715,7 @@ def _uncat_fwd(y1, argn, dims, *xs):
     target = size(xs[argn]) if not _isnumv(xs[argn]) else (1,)
     out = D.DArray.empty(target, y1.dtype)
     if out.size:
-        D.slab_copy(D.materialize(y1), tot, lo, out, ln, 0, inner, ln, outer)
+        D.slab_copy(D.materialize(y1), tot, lo, out, ln, 0, inner, ln, outer, fresh=True)
     return out
 
 
@@ -725,7 +725,7 @@ def _uncat1_fwd(x2, y1, argn, dims, *xs):
     inner, tot, outer = D._prod(shp[:dims]), shp[dims], D._prod(shp[dims + 1:])
     out = D.zeros(y1.shape, y1.dtype)
     if isinstance(x2, DArray) and x2.size:
-        D.slab_copy(D.materialize(x2), ln, 0, out, tot, lo, inner, ln, outer)
+        D.slab_copy(D.materialize(x2), ln, 0, out, tot, lo, inner, ln, outer, fresh=True)
     return out
 
 
@@ -768,7 +768,7 @@ def _cat1d_fwd(*xs):
         if isnum(a):
             a = D.full_like_shape((1,), dtype, a)
         if a.size:
-            D.slab_copy(a, a.size, 0, out, tot, off, 1, a.size, 1)
+            D.slab_copy(a, a.size, 0, out, tot, off, 1, a.size, 1, fresh=True)
         off += a.size
     return out
 

@@ -210,6 +210,6 @@ def _concat_flat(blocks, dtype):
     off = 0
     for b in blocks:
         if b.size:
-            D.slab_copy(b, b.size, 0, out, tot, off, 1, b.size, 1)
+            D.slab_copy(b, b.size, 0, out, tot, off, 1, b.size, 1, fresh=True)
         off += b.size
     return out

@@ -259,3 +259,102 @@ def test_specialised_program_list_is_up_to_date(agpkg):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_fused_programs.py"), "--check"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, "run `python tools/gen_fused_programs.py` and rebuild\n" + r.stderr[-2000:]
+
+
+# ---- round 2: deferred products, soft tape holds, raw writers ---------------------------------------------------
+
+def test_product_bias_activation_is_one_launch_and_only_needed_values_are_stored(lz):
+    """`max.(0, w*x .+ b)` (examples/mnist.jl:32): product, sum and relu go out as ONE ag_gemm_epilogue call that writes
+    the sum (relu's rule reads it, src/math.jl:54) and the relu, never the product; `sigm.(w*x .+ b)`
+    (examples/charlm.jl:74) writes only the activation.  Values are identical to the unfused sequence."""
+    ag, L, D = lz
+    rng = np.random.default_rng(3)
+    w, b, x = (rng.standard_normal(s).astype(np.float32) for s in ((40, 30), (40,), (30, 50)))
+    wd, bd, xd = ag.Param(dev(ag, w)), ag.Param(dev(ag, b)), dev(ag, x)
+    fake = ag._lib.lib
+    calls = []
+    orig = fake.ag_gemm_epilogue
+
+    def spy(dtype, ta, tb, M, N, K, A, lda, B, ldb, bias, act, Cp, C2p, ldc):
+        calls.append((act, bool(getattr(C2p, "value", C2p))))
+        return orig(dtype, ta, tb, M, N, K, A, lda, B, ldb, bias, act, Cp, C2p, ldc)
+    fake.ag_gemm_epilogue = spy
+    try:
+        for fn, act_id, two in ((ag.relu, 28, True), (ag.sigm, 7, False), (ag.tanh, 6, False)):
+            calls.clear()
+            t = ag.diff(lambda: ag.sum_(fn(ag.add(ag.matmul(wd, xd), bd))))
+            gw = ag.grad(t, wd).to_numpy()
+            assert calls == [(act_id, two)], (fn, calls)
+            prev = L.set_fusion(False)
+            t0 = ag.diff(lambda: ag.sum_(fn(ag.add(ag.matmul(wd, xd), bd))))
+            L.set_fusion(prev)
+            assert float(ag.value(t)) == float(ag.value(t0))
+            assert np.array_equal(gw, ag.grad(t0, wd).to_numpy())
+    finally:
+        fake.ag_gemm_epilogue = orig
+
+
+def test_soft_held_product_is_recomputed_on_demand_and_dropped_after_the_sweep(lz):
+    ag, L, D = lz
+    rng = np.random.default_rng(4)
+    w, b, x = (rng.standard_normal(s).astype(np.float32) for s in ((40, 30), (40,), (30, 50)))
+    wd, bd, xd = ag.Param(dev(ag, w)), ag.Param(dev(ag, b)), dev(ag, x)
+    seen = {}
+
+    def f():
+        m = ag.matmul(wd, xd)
+        seen["m"] = m                               # the tracked product (a Result)
+        return ag.sum_(ag.tanh(ag.add(m, bd)))
+    t = ag.diff(f)
+    assert L.stats.get("discarded", 0) >= 1
+    with pytest.raises(RuntimeError):               # dropped at the end of the sweep: nobody held its value
+        ag.value(seen["m"]).to_numpy()
+    # held by the user during the forward pass -> stored (hard reference), equal to the plain product
+    held = {}
+
+    def g():
+        m = ag.matmul(wd, xd)
+        held["v"] = ag.value(m)
+        return ag.sum_(ag.tanh(ag.add(m, bd)))
+    ag.diff(g)
+    assert np.allclose(held["v"].to_numpy(), w.astype(np.float64) @ x, rtol=1e-5, atol=1e-5)
+
+
+def test_externally_held_intermediate_is_stored_exactly_once(lz):
+    """The reference-count test that decides which values of a chain are written (calibrated at import, lazy._REF_BASE):
+    a held intermediate is an output of the one fused launch, an unheld one is not."""
+    ag, L, D = lz
+    assert L._REFS_OK
+    x = dev(ag, np.linspace(0.1, 1.0, 64).astype(np.float32))
+    fake = ag._lib.lib
+    nouts = []
+    orig = fake.ag_ewise_fused
+
+    def spy(dtype, code, ncode, consts, nconsts, nin, inp, in_mode, in_imm, nout, out, rows, cols):
+        nouts.append(nout)
+        return orig(dtype, code, ncode, consts, nconsts, nin, inp, in_mode, in_imm, nout, out, rows, cols)
+    fake.ag_ewise_fused = spy
+    try:
+        held = D.unary_fwd("exp", x)
+        y = D.unary_fwd("tanh", D.binary_fwd("mul", held, 2.0))
+        y.ptr
+        assert nouts == [2]                          # y and the held exp, not the unheld product
+        held.ptr
+        assert nouts == [2]                          # already stored: no second launch
+        nouts.clear()
+        z = D.unary_fwd("tanh", D.binary_fwd("mul", D.unary_fwd("exp", x), 2.0))
+        z.ptr
+        assert nouts == [1]
+    finally:
+        fake.ag_ewise_fused = orig
+
+
+def test_slab_copy_into_an_existing_array_flushes_pending_reads(lz):
+    """y = W .+ 1 pending, then a raw copy into W, then reading y must still see the OLD W."""
+    ag, L, D = lz
+    W = dev(ag, np.ones((4, 2), np.float32))
+    src = dev(ag, np.full((4, 2), 7.0, np.float32))
+    y = D.binary_fwd("add", W, 1.0)
+    D.slab_copy(src, 8, 0, W, 8, 0, 1, 8, 1)
+    assert np.array_equal(y.to_numpy(), np.full((4, 2), 2.0, np.float32))
+    assert np.array_equal(W.to_numpy(), np.full((4, 2), 7.0, np.float32))
