@@ -146,3 +146,19 @@ def test_tcgen05_product_has_no_systematic_shrink(ag):
     d = c - ref
     assert abs((d * ref).sum() / (ref * ref).sum()) <= 3e-7         # 1.7e-7 measured; 1.3e-6 with 8 k-blocks per promotion
     assert np.abs(d).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_cabi_smoke_runs(tmp_path):
+    """The C ABI without Python: tests/cabi_smoke.c (gcc, include/agb200.h only) in its own process."""
+    import os
+    import subprocess
+    import __graft_entry__ as ge
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(ge.LIB)
+    exe = str(tmp_path / "cabi_smoke")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cabi_smoke.c"),
+                        "-o", exe, "-L", libdir, "-lagb200", "-Wl,-rpath," + libdir, "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "tcgen05" in r.stdout
