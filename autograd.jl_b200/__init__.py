@@ -20,6 +20,7 @@ from .comm import DataParallel
 from .gradcheck import gradcheck
 from .vm import E, Expr, primitive_expr
 from .lazy import set_fusion
+from .ctape import CTape
 from .loader import CharBatches, StagedInput, UByteBatch, charlm_minibatch_ids, read_chars, read_idx_ubyte
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -94,6 +94,13 @@ _SIGS = {
     "ag_multi_axpy_scaled": [i32, i32, dbl, vp, C.POINTER(vp), C.POINTER(vp), pi64],
     "ag_multi_copy": [i32, i32, C.POINTER(vp), C.POINTER(vp), pi64],
     "ag_p2p_destroy": [],
+    "ag_tape_new": [C.POINTER(u64)],
+    "ag_tape_free": [u64],
+    "ag_tape_leaf": [u64, i32, vp, i32, pi64, i32, C.POINTER(i32)],
+    "ag_tape_record": [u64, i32, i32, i32, C.POINTER(i32), dbl, C.POINTER(i32)],
+    "ag_tape_backward": [u64, i32],
+    "ag_tape_grad": [u64, i32, C.POINTER(vp)],
+    "ag_tape_value": [u64, i32, C.POINTER(vp), C.POINTER(i32), pi64],
 }
 
 EXPORTS = sorted(_SIGS)

@@ -362,6 +362,41 @@ ag_status ag_permute(int32_t dtype, const void* x, int32_t ndims, const int64_t*
 /* permutedims(x, (2,1)) materialised: out (cols x rows) = transpose of x (rows x cols). */
 ag_status ag_transpose(int32_t dtype, const void* x, int64_t rows, int64_t cols, void* out);
 
+/* ---- C-side tape ------------------------------------------------------------------ */
+/* The reference records a Node per Result on a host tape (src/core.jl:110-129) and sweeps it in reverse, one `back` and
+ * one `addto!` per tracked parent (src/core.jl:153-170).  For tapes made only of device primitives the same bookkeeping
+ * lives behind the ABI: one call per recorded operation (which also runs its forward kernel) and ONE call for the whole
+ * backward sweep.  Values are small integer ids local to the tape.  Node order, the order of the `back` calls and
+ * the out-of-place accumulation are the reference's, so gradients are bit-identical to the host-recorded tape running
+ * the same (unfused) kernels.  First order only.  Arrays have <= 4 dims. */
+enum {
+  AG_T_MATMUL = 0,     /* x1*x2: dy*x2', x1'*dy                            src/base.jl:26 */
+  AG_T_ADD = 1,        /* x1 .+ x2 (Julia broadcasting): unbroadcast(xi, dy)        :21 */
+  AG_T_SUB = 2,        /* x1 .- x2                                                  :23 */
+  AG_T_MUL = 3,        /* x1 .* x2: unbroadcast(x1, dy.*x2), unbroadcast(x2, x1.*dy) :27 */
+  AG_T_DIV_SCALAR = 4, /* x ./ scalar: dy ./ scalar                                 :33 */
+  AG_T_MUL_SCALAR = 5, /* scalar .* x                                               :27 */
+  AG_T_UNARY = 6,      /* f.(x), f = AG_U_* id in `arg`: dy .* g(x,y)     src/math.jl:9-74 */
+  AG_T_SUM = 7,        /* sum(x): dy .* one.(x)                           src/base.jl:245 */
+  AG_T_SUMABS2 = 8,    /* sum(abs2, x): dy .* 2x                                    :247 */
+  AG_T_SUM_DIM = 9     /* sum(x; dims = arg + 1), keeps the dim with extent 1       :245 */
+};
+ag_status ag_tape_new(uint64_t* tape_out);
+/* Frees the tape, the values it computed and every gradient it produced (leaf arrays belong to the caller). */
+ag_status ag_tape_free(uint64_t tape);
+/* Register an array the caller owns: a Param (tracked = 1, src/core.jl:201) or a constant (tracked = 0). */
+ag_status ag_tape_leaf(uint64_t tape, int32_t dtype, void* ptr, int32_t ndims, const int64_t* shape, int32_t tracked,
+                       int32_t* id_out);
+/* forw + record! (src/core.jl:64-79,110-129): run primitive `op` on the values in_ids[0..nin) and append a node. */
+ag_status ag_tape_record(uint64_t tape, int32_t op, int32_t arg, int32_t nin, const int32_t* in_ids, double scalar,
+                         int32_t* id_out);
+/* The backward sweep of `differentiate` (src/core.jl:153-170) from the scalar value result_id. */
+ag_status ag_tape_backward(uint64_t tape, int32_t result_id);
+/* grad(tape, x) (src/core.jl:215-216): device pointer of the accumulated gradient, NULL when none reached it. */
+ag_status ag_tape_grad(uint64_t tape, int32_t id, void** ptr_out);
+/* value(x): pointer, number of dims and shape (4 entries) of a value of the tape. */
+ag_status ag_tape_value(uint64_t tape, int32_t id, void** ptr_out, int32_t* ndims_out, int64_t* shape4_out);
+
 /* ---- data-parallel exchange (no reference counterpart: BASELINE.json north_star) --------------- */
 /* NCCL communicator over the ranks of one node; id is the 128-byte ncclUniqueId produced on rank
  * 0 by ag_comm_unique_id and distributed by the host launcher. */

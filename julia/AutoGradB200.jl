@@ -690,6 +690,36 @@ end
 release_node(n, tape) = (n.outgrad = nothing; n.Value isa AutoGrad.Result && (n.Value.value = nothing); nothing)
 use_release_node!() = AutoGrad.set_gc_function(release_node)
 
+# C-side tape (csrc/tape.cu): one ccall per recorded operation, ONE for the whole backward sweep (src/core.jl:153-170)
+struct CTape
+    h::UInt64
+end
+CTape() = (r = Ref{UInt64}(0); check(ccall((:ag_tape_new, LIB), Int32, (Ref{UInt64},), r)); CTape(r[]))
+free!(t::CTape) = check(ccall((:ag_tape_free, LIB), Int32, (UInt64,), t.h))
+function leaf!(t::CTape, x::DArray{T,N}, tracked::Bool) where {T,N}
+    id = Ref{Int32}(0)
+    check(ccall((:ag_tape_leaf, LIB), Int32, (UInt64, Int32, Ptr{Cvoid}, Int32, Ptr{Int64}, Int32, Ref{Int32}),
+                t.h, dtcode(T), x.ptr, N, collect(Int64, size(x)), tracked, id))
+    id[]
+end
+function record!(t::CTape, op::Integer, arg::Integer, ins::Vector{Int32}, scalar::Real=0.0)
+    id = Ref{Int32}(0)
+    check(ccall((:ag_tape_record, LIB), Int32, (UInt64, Int32, Int32, Int32, Ptr{Int32}, Float64, Ref{Int32}),
+                t.h, op, arg, length(ins), ins, Float64(scalar), id))
+    id[]
+end
+backward!(t::CTape, result::Integer) = check(ccall((:ag_tape_backward, LIB), Int32, (UInt64, Int32), t.h, result))
+function tape_grad(t::CTape, id::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ag_tape_grad, LIB), Int32, (UInt64, Int32, Ref{Ptr{Cvoid}}), t.h, id, p))
+    p[]                                   # C_NULL = nothing (src/core.jl:215-216)
+end
+function tape_value(t::CTape, id::Integer)
+    p, nd, shp = Ref{Ptr{Cvoid}}(C_NULL), Ref{Int32}(0), zeros(Int64, 4)
+    check(ccall((:ag_tape_value, LIB), Int32, (UInt64, Int32, Ref{Ptr{Cvoid}}, Ref{Int32}, Ptr{Int64}), t.h, id, p, nd, shp))
+    p[], Tuple(shp[1:nd[]])
+end
+
 # ---- §11 data parallel: one process per GPU, gradients summed over the ranks, then the same axpy! everywhere -------------
 # The launcher (MPI.jl, Distributed, torchrun-style env) moves two small byte strings between the ranks: rank 0's
 # 128-byte NCCL id and every rank's 64-byte CUDA-IPC handle.  `exchange_all(bytes)::Vector{Vector{UInt8}}` is that

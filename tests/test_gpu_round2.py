@@ -162,3 +162,44 @@ def test_cabi_smoke_runs(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "tcgen05" in r.stdout
+
+
+@pytest.mark.parametrize("cfg,dtype", [("mnist", np.float32), ("mnist", np.float64), ("housing", np.float64), ("sweep", np.float32)])
+def test_c_side_tape_matches_the_host_tape_bitwise(ag, cfg, dtype):
+    """ag_tape_* (csrc/tape.cu): the same model functions recorded and swept behind the C ABI give the loss and the
+    gradients of the host-recorded tape running the same unfused kernels, bit for bit (node order, order of the `back`
+    calls and out-of-place accumulation follow src/core.jl:153-170)."""
+    W = ag.workloads
+    rng = np.random.default_rng(11)
+    if cfg == "mnist":
+        w, x, y = W.mnist_init(rng, 3000, dtype)
+        loss = lambda m, p, c: W.mnist_loss(m, p, c[0], c[1])
+        consts = [x, y]
+    elif cfg == "housing":
+        w, x, y = W.housing_init(rng, dtype=dtype)
+        loss = lambda m, p, c: W.housing_loss(m, p, c[0], c[1])
+        consts = [x, y]
+    else:
+        x, brow, bcol = W.sweep_init(rng, 96, 200, dtype)
+        w = [x, brow, bcol]
+        loss = lambda m, p, c: W.sweep_loss(m, p[0], p[1], p[2])
+        consts = []
+    wd = [ag.DArray.from_numpy(a) for a in w]
+    cd = [ag.DArray.from_numpy(a) for a in consts]
+    prev = ag.set_fusion(False)
+    try:
+        ph = [ag.Param(a) for a in wd]
+        th = ag.diff(lambda: loss(ag, ph, cd))
+        want = [ag.grad(th, p).to_numpy() for p in ph]
+        lwant = float(ag.value(th))
+    finally:
+        ag.set_fusion(prev)
+    t = ag.CTape()
+    pc = [t.param(a) for a in wd]
+    out = loss(t, pc, [t.const(a) for a in cd])
+    t.backward(out)
+    assert float(t.value(out).to_numpy()) == lwant
+    for p, g in zip(pc, want):
+        got = t.grad(p).to_numpy()
+        assert np.array_equal(got.reshape(g.shape), g)
+    t.close()
