@@ -10,7 +10,7 @@ from ._lib import DeviceError, DimensionMismatch, UnsupportedOnDevice
 from .darray import (DArray, IArray, device_info, gemm_engine, init, launch_count, set_gemm_engine, sync,
                      zeros)
 from .core import (Node, Param, Result, Tape, Tracked, Value, differentiate, diff, gcnode, grad,
-                   gradloss, params, recording, release_node, set_gc_function, value)
+                   gradloss, params, recording, release_node, set_gc_function, set_timer, timer_report, value)
 from .sparse import Sparse, flat_dest, to_indices
 from .rules import *  # noqa: F401,F403  (the primitive catalogue)
 from .rules import (Primitive, abs_, addto, back, full, max_, min_, pow_, primitive, sum_, zerograd)

@@ -48,6 +48,8 @@ _SIGS = {
     "ag_event_record": [u64],
     "ag_event_elapsed_ms": [u64, u64, C.POINTER(C.c_float)],
     "ag_event_destroy": [u64],
+    "ag_range_push": [C.c_char_p],
+    "ag_range_pop": [],
     "ag_graph_begin": [],
     "ag_graph_end": [C.POINTER(u64)],
     "ag_graph_launch": [u64],

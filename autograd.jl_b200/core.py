@@ -13,9 +13,57 @@ The host language is Python here because no Julia toolchain exists in this image
 julia/AutoGradB200.jl holds the equivalent Julia binding.  The arrays inside Param/Result are
 DArray; every array operation the sweep triggers is a kernel in libagb200.so.
 """
+import os
+import time
 import weakref
 
 from .darray import DArray, isnum
+
+# `@timer` (src/AutoGrad.jl:7-12): with AUTOGRAD_TIMER set, every forward call, every `back` call and every
+# accumulation is labelled with its tape position exactly like the reference (ftimer / btimer / stimer,
+# src/core.jl:177-182): "[>ti]f", "[ti]f[i]", "[ti]addto![i]".  Each label opens an NVTX range around the kernels it
+# launches (ag_range_push / ag_range_pop) and accumulates host wall time (after a stream sync, like the
+# reference's `@gs`) and launch counts, reported by timer_report().
+TIMER = [bool(os.environ.get("AUTOGRAD_TIMER"))]
+_timings = {}
+
+
+def set_timer(on):
+    prev = TIMER[0]
+    TIMER[0] = bool(on)
+    return prev
+
+
+class _timed:
+    __slots__ = ("label", "t0", "l0")
+
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        from . import darray as D
+        D.check(D.lib.ag_range_push(self.label.encode()))
+        self.l0 = D.launch_count()
+        self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        from . import darray as D
+        D.sync()                                     # `@gs`
+        dt = time.perf_counter() - self.t0
+        D.check(D.lib.ag_range_pop())
+        e = _timings.setdefault(self.label, [0, 0.0, 0])
+        e[0] += 1
+        e[1] += dt
+        e[2] += D.launch_count() - self.l0
+        return False
+
+
+def timer_report(reset=True, top=40):
+    """[(label, calls, seconds, launches)] sorted by time (AutoGrad.to of the reference)."""
+    rows = sorted(((k, v[0], v[1], v[2]) for k, v in _timings.items()), key=lambda r: -r[2])[:top]
+    if reset:
+        _timings.clear()
+    return rows
 
 
 class Value:
@@ -105,7 +153,11 @@ def value(x):
 def forw(f, *args, **kwargs):
     """src/core.jl:64-79: strip the boxes, run the primitive on raw values, record if needed."""
     raw = tuple(a.value if isinstance(a, Value) else a for a in args)
-    v = f.fwd(*raw, **kwargs)
+    if TIMER[0]:
+        with _timed(("[>%d]%s" % (1 + len(_tapes[-1].list), f.name)) if _tapes else f.name):      # ftimer
+            v = f.fwd(*raw, **kwargs)
+    else:
+        v = f.fwd(*raw, **kwargs)
     if _tapes:
         for a in args:
             if isinstance(a, Tracked):
@@ -210,6 +262,12 @@ def differentiate(f, *x, **o):
                 continue
             if isinstance(n.outgrad, Sparse):
                 n.outgrad = full(n.outgrad)
+            if TIMER[0]:
+                with _timed("[%d]%s[%d]" % (ti + 1, r.func.name, i + 1)):                             # btimer
+                    g = back(r.func, i, n.outgrad, r, *r.args, **r.kwargs)
+                with _timed("[%d]addto![%d]" % (ti + 1, i + 1)):                                      # stimer
+                    p.outgrad = addto(p.outgrad, g)
+                continue
             g = back(r.func, i, n.outgrad, r, *r.args, **r.kwargs)
             p.outgrad = addto(p.outgrad, g)
         if not _tapes and isinstance(r, Result) and n is not resultnode:

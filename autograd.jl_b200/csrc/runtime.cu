@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -441,6 +443,18 @@ ag_status ag_fill(void* dst, int64_t n, int32_t dtype, double value) {
   else
     k_fill<double><<<(unsigned)blocks, 256, 0, c.stream>>>((double*)dst, n, value);
   AG_LAUNCHED();
+  return AG_OK;
+}
+
+// ---- profiling ranges: the `@timer` labels of the reference (src/AutoGrad.jl:7-12, src/core.jl:165-166,177-182) as NVTX
+// ranges, so that an nsys / ncu timeline carries the tape position of every kernel ("[ti]f[i]", "[ti]addto![i]") --------
+ag_status ag_range_push(const char* label) {
+  if (label) nvtxRangePushA(label);
+  return AG_OK;
+}
+
+ag_status ag_range_pop(void) {
+  nvtxRangePop();
   return AG_OK;
 }
 

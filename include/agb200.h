@@ -164,6 +164,12 @@ ag_status ag_event_create(uint64_t* ev_out);
 ag_status ag_event_record(uint64_t ev);
 ag_status ag_event_elapsed_ms(uint64_t ev_start, uint64_t ev_stop, float* ms_out); /* syncs on stop */
 ag_status ag_event_destroy(uint64_t ev);
+/* The reference's `@timer` (AUTOGRAD_TIMER; src/AutoGrad.jl:7-12) labels every forward call "[>ti]f", every `back` call
+ * "[ti]f[i]" and every accumulation "[ti]addto![i]" (src/core.jl:165-166,177-182).  These two entries open / close an
+ * NVTX range with such a label around the kernels a tape position launches, so nsys / ncu timelines carry the tape
+ * position; the host also accumulates per-label wall time and launch counts (core.timer_report). */
+ag_status ag_range_push(const char* label);
+ag_status ag_range_pop(void);
 /* Capture everything enqueued between begin/end (one recorded tape's forward+backward+update)
  * into a CUDA graph and replay it.  Pool blocks handed out during capture stay owned by the graph
  * until ag_graph_destroy.  Replaces the per-op dispatch of src/core.jl:64-79,156-169 on replay. */

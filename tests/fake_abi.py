@@ -426,6 +426,10 @@ class FakeLib:
 
     def ag_gemm_set_engine(self, e): return 0
 
+    def ag_range_push(self, label): return 0
+
+    def ag_range_pop(self): return 0
+
     def ag_gemm_last_engine(self, buf, n):
         buf.value = b"fake"
         return 0

@@ -297,3 +297,23 @@ def test_clipped_update_host_logic(hostlib):
         assert gn > 5.0
         for a, b in zip(got, want):
             assert np.allclose(a, b, rtol=1e-12), gclip
+
+
+def test_timer_labels_follow_the_reference(hostlib):
+    """AUTOGRAD_TIMER labels (src/core.jl:165-166,177-182): "[>ti]f" forward, "[ti]f[i]" back, "[ti]addto![i]"."""
+    ag = hostlib
+    w = ag.Param(ag.DArray.from_numpy(np.ones((2, 3))))
+    x = ag.DArray.from_numpy(np.ones((3, 4)))
+    prev = ag.set_timer(True)
+    try:
+        ag.timer_report()
+        ag.diff(lambda: ag.sumabs2(ag.matmul(w, x)))
+        rows = {r[0]: r for r in ag.timer_report()}
+    finally:
+        ag.set_timer(prev)
+    # tape: 1 P(w), 2 *(w,x), 3 sum(abs2, .)   (README.md:116-125 numbering, 1-based)
+    # ftimer prints 1 + length(tape.list) at call time: the Param's node is only created when `*` is recorded
+    assert "[>1]*" in rows and "[>3]sum(abs2,·)" in rows
+    assert "[3]sum(abs2,·)[1]" in rows and "[3]addto![1]" in rows
+    assert "[2]*[1]" in rows and "[2]addto![1]" in rows
+    assert all(r[1] == 1 for r in rows.values())
