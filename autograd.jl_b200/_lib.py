@@ -23,6 +23,13 @@ OK, EINVAL, ENOMEM, ECUDA, ENCCL, EUNSUPPORTED, ESTATE = range(7)
 i32, i64, u64, dbl, vp = C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_void_p
 pi64 = C.POINTER(C.c_int64)
 
+class GemmDesc(C.Structure):
+    """ag_gemm_desc (include/agb200.h)."""
+    _fields_ = [("transA", C.c_int32), ("transB", C.c_int32), ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("bias", C.c_void_p),
+                ("act", C.c_int32), ("C", C.c_void_p), ("C2", C.c_void_p), ("ldc", C.c_int64)]
+
+
 _SIGS = {
     "ag_init": [i32],
     "ag_shutdown": [],
@@ -74,6 +81,7 @@ _SIGS = {
     "ag_gemm": [i32, i32, i32, i64, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64],
     "ag_gemm_epilogue": [i32, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i32, vp, vp, i64],
     "ag_gemm_epilogue_query": [i32, i32, i32, i64, i64, i64, vp, i64, vp, i64, C.POINTER(i32)],
+    "ag_gemm_group": [i32, i32, C.POINTER(GemmDesc)],
     "ag_gemm_set_engine": [i32],
     "ag_gemm_last_engine": [C.c_char_p, i64],
     "ag_ubyte_to_float": [i32, vp, vp, i64, dbl],

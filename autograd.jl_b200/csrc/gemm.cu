@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
+#include <vector>
+
 namespace agb {
 
 ag_status gemm_skinny(int dtype, int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
@@ -279,6 +281,54 @@ ag_status ag_gemm_epilogue_query(int32_t dtype, int32_t transA, int32_t transB, 
   AG_CHECK(fused_out, AG_EINVAL, "ag_gemm_epilogue_query: null");
   // C / C2 come from the pool (512-byte aligned): a 16-byte aligned stand-in
   *fused_out = epilogue_runs_fused(dtype, transA, transB, M, N, K, A, lda, B, ldb, (const void*)16, nullptr, M) ? 1 : 0;
+  return AG_OK;
+}
+
+static int act_to_tc(int act) {
+  return act == AG_U_RELU ? TC_ACT_RELU : act == AG_U_TANH ? TC_ACT_TANH : act == AG_U_SIGM ? TC_ACT_SIGM : TC_ACT_NONE;
+}
+
+/* n independent products with their epilogues (each one as ag_gemm_epilogue).  Products the tcgen05 engine takes are
+ * issued in groups of one class, up to 8 per launch; the others run one by one.  Same values either way. */
+ag_status ag_gemm_group(int32_t dtype, int32_t n, const ag_gemm_desc* d) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(n >= 0 && (n == 0 || d), AG_EINVAL, "ag_gemm_group: bad arguments");
+  std::vector<char> done((size_t)n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (done[i]) continue;
+    const ag_gemm_desc& a = d[i];
+    const bool ok_args = a.M > 0 && a.N > 0 && a.K > 0 && a.A && a.B && a.C && a.ldc == a.M &&
+                         (a.act == AG_U_IDENTITY || a.act == AG_U_RELU || a.act == AG_U_TANH || a.act == AG_U_SIGM);
+    if (!ok_args || !epilogue_runs_fused(dtype, a.transA, a.transB, a.M, a.N, a.K, a.A, a.lda, a.B, a.ldb, a.C, a.C2, a.ldc)) {
+      ag_status st = ag_gemm_epilogue(dtype, a.transA, a.transB, a.M, a.N, a.K, a.A, a.lda, a.B, a.ldb, a.bias, a.act, a.C,
+                                      a.C2, a.ldc);
+      if (st != AG_OK) return st;
+      done[i] = 1;
+      continue;
+    }
+    TcJob jobs[8];
+    int cnt = 0;
+    for (int k = i; k < n && cnt < 8; ++k) {
+      if (done[k]) continue;
+      const ag_gemm_desc& b = d[k];
+      if (k != i) {
+        const bool okb = b.M > 0 && b.N > 0 && b.K > 0 && b.A && b.B && b.C && b.ldc == b.M &&
+                         (b.act == AG_U_IDENTITY || b.act == AG_U_RELU || b.act == AG_U_TANH || b.act == AG_U_SIGM);
+        if (!okb || !epilogue_runs_fused(dtype, b.transA, b.transB, b.M, b.N, b.K, b.A, b.lda, b.B, b.ldb, b.C, b.C2, b.ldc))
+          continue;
+      }
+      TcJob j;
+      j.transA = b.transA; j.transB = b.transB; j.M = b.M; j.N = b.N; j.K = b.K; j.alpha = 1.0; j.beta = 0.0;
+      j.A = b.A; j.lda = b.lda; j.B = b.B; j.ldb = b.ldb; j.C = b.C; j.ldc = b.ldc;
+      j.epi.bias = b.bias; j.epi.act = act_to_tc(b.act); j.epi.out2 = b.C2;
+      if (cnt > 0 && !gemm_tc_same_class(jobs[0], j)) continue;
+      jobs[cnt++] = j;
+      done[k] = 1;
+    }
+    g_last_engine = cnt > 1 ? "tcgen05+epilogue (group)" : "tcgen05+epilogue";
+    ag_status st = gemm_tc_group(cnt, jobs);
+    if (st != AG_OK) return st;
+  }
   return AG_OK;
 }
 

@@ -80,6 +80,19 @@ struct TcParams {
   float alpha, beta;       // beta != 0 goes through the workspace path
 };
 
+// Up to TC_GROUP_MAX independent products of one class (same operand majors, same orientation, same promotion
+// interval) run as ONE launch: the work items of all problems form one list.  The four gate products of an LSTM step
+// (examples/charlm.jl:69-73: "we can probably combine these four operations into one"), their four dx products and
+// the dW products of several timesteps are issued this way by the host (lazy._resolve_products); a small product
+// pays ~9 us of fixed cost per launch (launch, TMEM allocation, pipeline fill and drain), which dominates at those sizes.
+constexpr int TC_GROUP_MAX = 8;
+struct TcGroup {
+  CUtensorMap tmA[TC_GROUP_MAX], tmB[TC_GROUP_MAX];
+  TcParams p[TC_GROUP_MAX];
+  int work_start[TC_GROUP_MAX + 1];     // prefix sums of the problems' work items (tiles * splits)
+  int nprob;
+};
+
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -247,8 +260,7 @@ __device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int6
 // FLUSH: k-blocks accumulated in TMEM before the partial is promoted to fp32 registers.
 template <bool A_KMAJOR, bool B_KMAJOR, int FLUSH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const TcParams p) {
+    k_gemm_tc(const __grid_constant__ TcGroup g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -265,8 +277,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int q = 0; q < g.nprob; ++q) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA[q]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB[q]) : "memory");
+    }
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(ready_bar(s), TC_SPLIT_WARPS);   // one elected arrival per splitter warp
@@ -285,9 +299,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int total_work = p.mm_tiles * p.nn_tiles * p.splits;
-  // work item -> (mm tile, nn tile, split)
-  auto decode = [&](int w, int& mt, int& nt, int& kb0, int& kb1) {
+  const int total_work = g.work_start[g.nprob];
+  // work item -> (problem, mm tile, nn tile, split)
+  auto decode = [&](int w, int& q, int& mt, int& nt, int& kb0, int& kb1) {
+    q = 0;
+    while (q + 1 < g.nprob && w >= g.work_start[q + 1]) ++q;
+    w -= g.work_start[q];
+    const TcParams& p = g.p[q];
     mt = w % p.mm_tiles;
     int r = w / p.mm_tiles;
     nt = r % p.nn_tiles;
@@ -302,27 +320,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int s = 0;
     uint32_t ph = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      int mt, nt, kb0, kb1;
-      decode(w, mt, nt, kb0, kb1);
+      int q, mt, nt, kb0, kb1;
+      decode(w, q, mt, nt, kb0, kb1);
+      const CUtensorMap* mapA = &g.tmA[q];
+      const CUtensorMap* mapB = &g.tmB[q];
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t st = smem_base + s * TC_RAW_BYTES;
         if (elect_one()) {
           mbar_expect_tx(full_bar(s), TC_RAW_BYTES);
           if (A_KMAJOR) {
-            tma_load_2d(st, &tmA, full_bar(s), kb * TC_BK, mt * TC_BM);
+            tma_load_2d(st, mapA, full_bar(s), kb * TC_BK, mt * TC_BM);
           } else {
 #pragma unroll
             for (int c = 0; c < TC_BM / 32; ++c)
-              tma_load_2d(st + c * 4096, &tmA, full_bar(s), mt * TC_BM + c * 32, kb * TC_BK);
+              tma_load_2d(st + c * 4096, mapA, full_bar(s), mt * TC_BM + c * 32, kb * TC_BK);
           }
           const uint32_t sb = st + TC_A_BYTES;
           if (B_KMAJOR) {
-            tma_load_2d(sb, &tmB, full_bar(s), kb * TC_BK, nt * TC_BN);
+            tma_load_2d(sb, mapB, full_bar(s), kb * TC_BK, nt * TC_BN);
           } else {
 #pragma unroll
             for (int c = 0; c < TC_BN / 32; ++c)
-              tma_load_2d(sb + c * 4096, &tmB, full_bar(s), nt * TC_BN + c * 32, kb * TC_BK);
+              tma_load_2d(sb + c * 4096, mapB, full_bar(s), nt * TC_BN + c * 32, kb * TC_BK);
           }
         }
         __syncwarp();
@@ -345,8 +365,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int s = 0, ci = 0;   // stage, chunk counter (selects the TMEM accumulator)
     uint32_t ph = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      int mt, nt, kb0, kb1;
-      decode(w, mt, nt, kb0, kb1);
+      int q, mt, nt, kb0, kb1;
+      decode(w, q, mt, nt, kb0, kb1);
       for (int kc0 = kb0; kc0 < kb1; kc0 += FLUSH, ++ci) {
         const int kc1 = min(kc0 + FLUSH, kb1);
         const int acc = ci & 1;
@@ -391,14 +411,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     //    tile, writes hi and lo (exact tf32 values) to tensor memory with tcgen05.st.
     // B: lo = rna_tf32(x - trunc_tf32(x)) to the B_lo ring in shared memory (the tensor core truncates B_hi itself).
     const int tid = threadIdx.x - 64;          // 0..255
-    const int q = warp & 3;                    // TMEM lane quarter of this warp
+    const int lq = warp & 3;                   // TMEM lane quarter of this warp
     const int half = (warp - 2) >> 2;          // which 16 k of the 32
-    const int row = q * 32 + lane;             // tile row
+    const int row = lq * 32 + lane;             // tile row
     int s = 0;
     uint32_t ph = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      int mt, nt, kb0, kb1;
-      decode(w, mt, nt, kb0, kb1);
+      int q, mt, nt, kb0, kb1;
+      decode(w, q, mt, nt, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();                   // order the TMEM stores below after the stage hand-over
@@ -414,8 +434,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         } else {
           // 32-row (mm) chunks of 4 KB; inside: k-row at k*128 B, 32-byte atom a stored at a ^ (k & 3)
-          // (SWIZZLE_128B_ATOM_32B); this thread's mm = row -> chunk q, position lane
-          const uint8_t* base = rawA + q * 4096 + (lane & 7) * 4;
+          // (SWIZZLE_128B_ATOM_32B); this thread's mm = row -> chunk lq, position lane
+          const uint8_t* base = rawA + lq * 4096 + (lane & 7) * 4;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = half * 16 + j;
@@ -426,7 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) split_tf32(v[j], hi[j], lo[j]);
-        const uint32_t a_t = tmem_base + ((uint32_t)(q * 32) << 16) + TC_TMEM_ACC + (uint32_t)s * TC_TMEM_ASTAGE;
+        const uint32_t a_t = tmem_base + ((uint32_t)(lq * 32) << 16) + TC_TMEM_ACC + (uint32_t)s * TC_TMEM_ASTAGE;
         tmem_st16(a_t + half * 16, hi);
         tmem_st16(a_t + TC_BK + half * 16, lo);
         // B_lo: 512 float4 per stage, 2 per thread
@@ -449,13 +469,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + 4) {
     // ===== epilogue: promote each chunk partial TMEM -> registers (fp32 RN adds), finish the tile =====
-    const int q = warp & 3;              // TMEM lane quarter this warp may read
-    const int etid = threadIdx.x - TC_EPI_WARP0 * 32;     // 0..127
-    const int r_loc = q * 32 + lane;     // tile row of this thread
+    const int lq = warp & 3;             // TMEM lane quarter this warp may read
+    const int r_loc = lq * 32 + lane;     // tile row of this thread
     int ci = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      int mt, nt, kb0, kb1;
-      const int sp = decode(w, mt, nt, kb0, kb1);
+      int q, mt, nt, kb0, kb1;
+      const int sp = decode(w, q, mt, nt, kb0, kb1);
+      const TcParams& p = g.p[q];
       float accv[TC_BN];
 #pragma unroll
       for (int j = 0; j < TC_BN; ++j) accv[j] = 0.f;
@@ -466,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
           uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c0), r);
+          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * TC_BN + c0), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) accv[c0 + j] += __uint_as_float(r[j]);
@@ -513,14 +533,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// C = act(alpha * sum_s ws[s] + beta*C + bias) in a fixed order (deterministic split-K); ws partials are M x N
-// column-major with leading dimension M.  With C2: C receives the pre-activation value, C2 the activation.
-template <int ACT>
-__global__ void __launch_bounds__(256)
-    k_tc_splitk_reduce(const float* __restrict__ ws, int splits, int64_t M, int64_t N, float alpha, float beta,
-                       const float* __restrict__ bias, float* __restrict__ C, float* __restrict__ C2, int64_t ldc) {
+// C = act(alpha * sum_s ws[s] + beta*C + bias) in a fixed order (deterministic split-K) for every problem of a group
+// (blockIdx.y); ws partials are M x N column-major with leading dimension M.  With C2: C receives the pre-activation
+// value, C2 the activation.
+struct TcReduceGroup {
+  const float* ws[TC_GROUP_MAX];
+  int splits[TC_GROUP_MAX];
+  int64_t M[TC_GROUP_MAX], N[TC_GROUP_MAX], ldc[TC_GROUP_MAX];
+  float alpha[TC_GROUP_MAX], beta[TC_GROUP_MAX];
+  const float* bias[TC_GROUP_MAX];
+  float* C[TC_GROUP_MAX];
+  float* C2[TC_GROUP_MAX];
+  int act[TC_GROUP_MAX];
+  int nprob;
+};
+__global__ void __launch_bounds__(256) k_tc_splitk_reduce(const __grid_constant__ TcReduceGroup r) {
+  const int q = blockIdx.y;
+  const int64_t M = r.M[q], N = r.N[q];
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
+  const float* __restrict__ ws = r.ws[q];
+  const int splits = r.splits[q];
   int64_t m = i % M, n = i / M;
   // all partials of a block of 8 are in flight before the (fixed-order) additions
   float s0 = 0.f, s1 = 0.f;
@@ -538,15 +571,23 @@ __global__ void __launch_bounds__(256)
     s1 += ws[(int64_t)(k + 1) * MN + i];
   }
   if (k < splits) s0 += ws[(int64_t)k * MN + i];
-  const int64_t idx = m + n * ldc;
-  float z = __fmul_rn(alpha, s0 + s1);
-  if (beta != 0.f) z = __fadd_rn(z, __fmul_rn(beta, C[idx]));
-  if (bias) z = __fadd_rn(z, bias[m]);
-  if (C2) {
+  const int64_t idx = m + n * r.ldc[q];
+  float* __restrict__ C = r.C[q];
+  float z = __fmul_rn(r.alpha[q], s0 + s1);
+  if (r.beta[q] != 0.f) z = __fadd_rn(z, __fmul_rn(r.beta[q], C[idx]));
+  if (r.bias[q]) z = __fadd_rn(z, r.bias[q][m]);
+  float a = z;
+  switch (r.act[q]) {
+    case TC_ACT_RELU: a = tc_activation<TC_ACT_RELU>(z); break;
+    case TC_ACT_TANH: a = tc_activation<TC_ACT_TANH>(z); break;
+    case TC_ACT_SIGM: a = tc_activation<TC_ACT_SIGM>(z); break;
+    default: break;
+  }
+  if (r.C2[q]) {
     C[idx] = z;
-    C2[idx] = tc_activation<ACT>(z);
+    r.C2[q][idx] = a;
   } else {
-    C[idx] = tc_activation<ACT>(z);
+    C[idx] = a;
   }
 }
 
@@ -625,73 +666,126 @@ bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, 
   return true;
 }
 
-ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const void* A,
-                  int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc,
-                  const TcEpilogue* epi) {
+// One class of products: operand majors after the orientation swap, orientation, promotion interval.
+struct TcClass {
+  bool ak, bk, transposed, skinny;
+  bool operator==(const TcClass& o) const { return ak == o.ak && bk == o.bk && transposed == o.transposed && skinny == o.skinny; }
+};
+static TcClass tc_class(const TcJob& j) {
+  TcClass c;
+  c.transposed = j.N > j.M;
+  const bool a_kmajor = j.transA != 0, b_kmajor = j.transB == 0;
+  c.ak = c.transposed ? b_kmajor : a_kmajor;
+  c.bk = c.transposed ? a_kmajor : b_kmajor;
+  // promotion interval: every k-block, except for the HBM-bound skinny shapes (see the header comment)
+  c.skinny = (j.M <= 64 || j.N <= 64) && tc_knobs().flush_skinny != 1;
+  return c;
+}
+
+bool gemm_tc_same_class(const TcJob& a, const TcJob& b) { return tc_class(a) == tc_class(b); }
+
+// n <= TC_GROUP_MAX products of ONE class as one launch (+ one combine launch when they are split along K).
+ag_status gemm_tc_group(int n, const TcJob* jobs) {
   Context& c = ctx();
+  AG_CHECK(n >= 1 && n <= TC_GROUP_MAX, AG_EINVAL, "gemm_tc_group: %d problems", n);
+  const TcClass cls = tc_class(jobs[0]);
+  for (int q = 1; q < n; ++q) AG_CHECK(tc_class(jobs[q]) == cls, AG_EINVAL, "gemm_tc_group: mixed classes");
+  static TcGroup g;          // 3 KB: filled per call (one host thread, see the header of include/agb200.h)
+  g.nprob = n;
   // Map the larger extent of C onto the 128-row mm tile.
   //   normal     : mm = row index m of C,    Aop = op(A) (M x K),  Bop = op(B)^T (N x K)
   //   transposed : mm = column index n of C, Aop = op(B)^T (N x K), Bop = op(A) (M x K)
-  const bool transposed = N > M;
   // op(A)[m,k]: transA ? A[k + m*lda] (K-major) : A[m + k*lda] (MN-major)
   // op(B)^T[n,k] = op(B)[k,n]: transB ? B[n + k*ldb] (MN-major) : B[k + n*ldb] (K-major)
-  const bool a_kmajor = transA != 0, b_kmajor = transB == 0;
-  const void *pa, *pb;
-  int64_t MM, NN, lda_, ldb_;
-  bool ak, bk;
-  if (!transposed) { pa = A; ak = a_kmajor; lda_ = lda; MM = M; pb = B; bk = b_kmajor; ldb_ = ldb; NN = N; }
-  else { pa = B; ak = b_kmajor; lda_ = ldb; MM = N; pb = A; bk = a_kmajor; ldb_ = lda; NN = M; }
-
-  CUtensorMap tmA, tmB;
-  bool ok;
-  if (ak) ok = make_map(&tmA, pa, K, MM, lda_, TC_BK, TC_BM, true);
-  else ok = make_map(&tmA, pa, MM, K, lda_, 32, TC_BK, false);
-  if (bk) ok = ok && make_map(&tmB, pb, K, NN, ldb_, TC_BK, TC_BN, true);
-  else ok = ok && make_map(&tmB, pb, NN, K, ldb_, 32, TC_BK, false);
-  AG_CHECK(ok, AG_ECUDA, "ag_gemm: cuTensorMapEncodeTiled failed");
-
-  TcParams p;
-  p.mm_tiles = (int)cdiv(MM, TC_BM);
-  p.nn_tiles = (int)cdiv(NN, TC_BN);
-  p.kblocks_total = (int)cdiv(K, TC_BK);
-  const int64_t tiles = (int64_t)p.mm_tiles * p.nn_tiles;
+  int64_t total_tiles = 0;
+  int min_kblocks = 1 << 30;
+  bool any_beta = false;
+  for (int q = 0; q < n; ++q) {
+    const TcJob& j = jobs[q];
+    const void *pa, *pb;
+    int64_t MM, NN, lda_, ldb_;
+    if (!cls.transposed) { pa = j.A; lda_ = j.lda; MM = j.M; pb = j.B; ldb_ = j.ldb; NN = j.N; }
+    else { pa = j.B; lda_ = j.ldb; MM = j.N; pb = j.A; ldb_ = j.lda; NN = j.M; }
+    bool ok;
+    if (cls.ak) ok = make_map(&g.tmA[q], pa, j.K, MM, lda_, TC_BK, TC_BM, true);
+    else ok = make_map(&g.tmA[q], pa, MM, j.K, lda_, 32, TC_BK, false);
+    if (cls.bk) ok = ok && make_map(&g.tmB[q], pb, j.K, NN, ldb_, TC_BK, TC_BN, true);
+    else ok = ok && make_map(&g.tmB[q], pb, NN, j.K, ldb_, 32, TC_BK, false);
+    AG_CHECK(ok, AG_ECUDA, "ag_gemm: cuTensorMapEncodeTiled failed");
+    TcParams& p = g.p[q];
+    p.mm_tiles = (int)cdiv(MM, TC_BM);
+    p.nn_tiles = (int)cdiv(NN, TC_BN);
+    p.kblocks_total = (int)cdiv(j.K, TC_BK);
+    p.MM = MM;
+    p.NN = NN;
+    p.transposed = cls.transposed ? 1 : 0;
+    p.alpha = (float)j.alpha;
+    p.beta = (float)j.beta;
+    p.out2 = (float*)j.epi.out2;
+    p.bias = (const float*)j.epi.bias;
+    p.act = j.epi.act;
+    total_tiles += (int64_t)p.mm_tiles * p.nn_tiles;
+    if (p.kblocks_total < min_kblocks) min_kblocks = p.kblocks_total;
+    any_beta = any_beta || j.beta != 0.0;
+  }
+  // split along K when the whole group has fewer tiles than SMs: one work item per CTA (a second partial wave would
+  // leave most SMs idle for a whole item); the same number of splits for every problem of the group
   int splits = 1;
-  if (tiles < c.num_sms && p.kblocks_total >= tc_knobs().split_kb) {
-    splits = (int)(c.num_sms / tiles);  // one work item per CTA: tiles*splits <= SMs (a second partial wave
-                                        // would leave most SMs idle for a whole item)
-    const int maxs = p.kblocks_total / tc_knobs().min_kb;
+  if (total_tiles < c.num_sms && min_kblocks >= tc_knobs().split_kb) {
+    splits = (int)(c.num_sms / total_tiles);
+    const int maxs = min_kblocks / tc_knobs().min_kb;
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
   }
-  p.kblocks_per_split = (int)cdiv(p.kblocks_total, splits);
-  splits = (int)cdiv(p.kblocks_total, p.kblocks_per_split);
-  const bool via_ws = splits > 1 || beta != 0.0;
-  p.splits = splits;
-  p.MM = MM;
-  p.NN = NN;
-  p.transposed = transposed ? 1 : 0;
-  p.alpha = (float)alpha;
-  p.beta = (float)beta;
-  p.out2 = epi ? (float*)epi->out2 : nullptr;
-  p.bias = epi ? (const float*)epi->bias : nullptr;
-  p.act = epi ? epi->act : TC_ACT_NONE;
+  const bool via_ws = splits > 1 || any_beta;
+  size_t ws_floats = 0;
+  for (int q = 0; q < n; ++q) {
+    TcParams& p = g.p[q];
+    p.kblocks_per_split = (int)cdiv(p.kblocks_total, splits);
+    p.splits = (int)cdiv(p.kblocks_total, p.kblocks_per_split);
+    if (via_ws) ws_floats += (size_t)p.splits * (size_t)(jobs[q].M * jobs[q].N);
+  }
   float* ws = nullptr;
   if (via_ws) {
-    ws = (float*)workspace((size_t)splits * (size_t)(M * N) * sizeof(float));
+    ws = (float*)workspace(ws_floats * sizeof(float));
     if (!ws) return AG_ENOMEM;
-    p.out = ws;
-    p.ld_out = M;
-    p.split_stride = M * N;
-  } else {
-    p.out = (float*)C;
-    p.ld_out = ldc;
-    p.split_stride = 0;
   }
-  const int64_t work = tiles * splits;
+  static TcReduceGroup rg;
+  size_t off = 0;
+  int64_t work = 0;
+  int64_t max_mn = 0;
+  for (int q = 0; q < n; ++q) {
+    TcParams& p = g.p[q];
+    const TcJob& j = jobs[q];
+    g.work_start[q] = (int)work;
+    work += (int64_t)p.mm_tiles * p.nn_tiles * p.splits;
+    if (via_ws) {
+      p.out = ws + off;
+      p.ld_out = j.M;
+      p.split_stride = j.M * j.N;
+      rg.ws[q] = ws + off;
+      rg.splits[q] = p.splits;
+      rg.M[q] = j.M;
+      rg.N[q] = j.N;
+      rg.alpha[q] = (float)j.alpha;
+      rg.beta[q] = (float)j.beta;
+      rg.bias[q] = p.bias;
+      rg.C[q] = (float*)j.C;
+      rg.C2[q] = p.out2;
+      rg.ldc[q] = j.ldc;
+      rg.act[q] = p.act;
+      off += (size_t)p.splits * (size_t)(j.M * j.N);
+      if (j.M * j.N > max_mn) max_mn = j.M * j.N;
+    } else {
+      p.out = (float*)j.C;
+      p.ld_out = j.ldc;
+      p.split_stride = 0;
+    }
+  }
+  g.work_start[n] = (int)work;
+  AG_CHECK(work < ((int64_t)1 << 31), AG_EUNSUPPORTED, "ag_gemm: too many tiles");
   const int64_t grid = work < c.num_sms ? work : c.num_sms;
 
-  // promotion interval: every k-block, except for the HBM-bound skinny shapes (see the header comment)
-  const bool skinny = (M <= 64 || N <= 64) && tc_knobs().flush_skinny != 1;
 #define LAUNCH(AK, BK_, FL)                                                                              \
   do {                                                                                                   \
     static bool attr_set = false;                                                                        \
@@ -700,30 +794,39 @@ ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, doubl
                                    TC_SMEM));                                                            \
       attr_set = true;                                                                                   \
     }                                                                                                    \
-    k_gemm_tc<AK, BK_, FL><<<(unsigned)grid, TC_THREADS, TC_SMEM, c.stream>>>(tmA, tmB, p);              \
+    k_gemm_tc<AK, BK_, FL><<<(unsigned)grid, TC_THREADS, TC_SMEM, c.stream>>>(g);                        \
   } while (0)
-#define LAUNCH2(AK, BK_)              \
-  do {                                \
-    if (skinny) LAUNCH(AK, BK_, 8);   \
-    else LAUNCH(AK, BK_, 1);          \
+#define LAUNCH2(AK, BK_)                  \
+  do {                                    \
+    if (cls.skinny) LAUNCH(AK, BK_, 8);   \
+    else LAUNCH(AK, BK_, 1);              \
   } while (0)
-  if (ak && bk) LAUNCH2(true, true);
-  else if (ak && !bk) LAUNCH2(true, false);
-  else if (!ak && bk) LAUNCH2(false, true);
+  if (cls.ak && cls.bk) LAUNCH2(true, true);
+  else if (cls.ak && !cls.bk) LAUNCH2(true, false);
+  else if (!cls.ak && cls.bk) LAUNCH2(false, true);
   else LAUNCH2(false, false);
 #undef LAUNCH2
 #undef LAUNCH
   AG_LAUNCHED();
   if (via_ws) {
-    const unsigned nb = (unsigned)cdiv(M * N, 256);
-#define TC_CALL(ACT)                                                                                       \
-    k_tc_splitk_reduce<ACT><<<nb, 256, 0, c.stream>>>(ws, splits, M, N, (float)alpha, (float)beta, p.bias, \
-                                                      (float*)C, p.out2, ldc)
-    TC_DISPATCH_ACT(p.act, TC_CALL);
-#undef TC_CALL
+    rg.nprob = n;
+    dim3 grid_r((unsigned)cdiv(max_mn, 256), (unsigned)n);
+    k_tc_splitk_reduce<<<grid_r, 256, 0, c.stream>>>(rg);
     AG_LAUNCHED();
   }
   return AG_OK;
+}
+
+ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const void* A,
+                  int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc,
+                  const TcEpilogue* epi) {
+  TcJob j;
+  j.transA = transA; j.transB = transB; j.M = M; j.N = N; j.K = K; j.alpha = alpha; j.beta = beta;
+  j.A = A; j.lda = lda; j.B = B; j.ldb = ldb; j.C = C; j.ldc = ldc;
+  j.epi.bias = epi ? epi->bias : nullptr;
+  j.epi.act = epi ? epi->act : TC_ACT_NONE;
+  j.epi.out2 = epi ? epi->out2 : nullptr;
+  return gemm_tc_group(1, &j);
 }
 
 }  // namespace agb

@@ -15,6 +15,22 @@ struct TcEpilogue {
   void* out2;
 };
 
+// One product of a group launch (gemm_tc_group): BLAS-style description + epilogue.
+struct TcJob {
+  int transA, transB;
+  int64_t M, N, K;
+  double alpha, beta;
+  const void* A;
+  int64_t lda;
+  const void* B;
+  int64_t ldb;
+  void* C;
+  int64_t ldc;
+  TcEpilogue epi;
+};
+
+bool gemm_tc_same_class(const TcJob& a, const TcJob& b);     // may the two run in one group launch?
+ag_status gemm_tc_group(int n, const TcJob* jobs);           // n <= 8 products of one class, ONE launch
 bool gemm_tc_init();      // allocates the split counters; called from ag_init (never during a capture)
 bool gemm_tc_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                        const void* B, int64_t ldb, const void* C, int64_t ldc);

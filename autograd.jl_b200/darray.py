@@ -633,6 +633,36 @@ def _gemm_epilogue_fused(A, Bm, op, dtype):
     return bool(flag.value)
 
 
+def _gemm_group(jobs):
+    """Independent products [(A, B, op, out_shape, dtype, bias or None, act, want_z)] handed over together
+    (ag_gemm_group); returns [(z, a)] per job: z = op(A)*op(B) (.+ bias), a = act.(z) or None; z is None when an
+    activation was requested without want_z."""
+    if not jobs:
+        return []
+    dtype = np.dtype(jobs[0][4])
+    if len(jobs) == 1 or any(np.dtype(j[4]) != dtype for j in jobs):
+        out = []
+        for A, Bm, op, shape, dt, bias, act, want_z in jobs:
+            if bias is None and act == "identity":
+                out.append((_matmul_eager(A, Bm, op, shape, dt), None))
+            else:
+                out.append(_gemm_epilogue(A, Bm, op, shape, dt, bias, act, want_z))
+        return out
+    descs = (L.GemmDesc * len(jobs))()
+    res = []
+    for d, (A, Bm, op, shape, dt, bias, act, want_z) in zip(descs, jobs):
+        ta, tb, m, n, ka, lda, ldb = op
+        c = DArray.empty(shape, dt)
+        c2 = DArray.empty(shape, dt) if (want_z and act != "identity") else None
+        d.transA, d.transB, d.M, d.N, d.K = ta, tb, m, n, ka
+        d.A, d.lda, d.B, d.ldb = A.ptr, lda, Bm.ptr, ldb
+        d.bias = bias.ptr if bias is not None else None
+        d.act, d.C, d.C2, d.ldc = U[act], c.ptr, (c2.ptr if c2 is not None else None), max(m, 1)
+        res.append((c, None) if act == "identity" else ((c, c2) if want_z else (None, c)))
+    check(lib.ag_gemm_group(_DT[dtype], len(jobs), descs))
+    return res
+
+
 def _gemm_epilogue(A, Bm, op, out_shape, dtype, bias, act, want_z):
     """(z, a) = (op(A)*op(B) .+ bias, act.(z)) by one ag_gemm_epilogue call; z is None unless want_z (then the
     activation, if any, goes to a second array)."""

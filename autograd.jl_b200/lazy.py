@@ -472,6 +472,7 @@ def _resolve_products(order, root):
             if is_pending(a):
                 users.setdefault(id(a), []).append(n)
     n = a = None
+    jobs = []           # (product node, bias, act, z node or None, activation node or None, z_needed)
     for i in range(len(order)):
         m = order[i]
         if m.kind != "mm":
@@ -486,7 +487,7 @@ def _resolve_products(order, root):
                     and D._gemm_epilogue_fused(m.args[0], m.args[1], m.op, m.dtype):
                 bias = other
         if bias is None:
-            m._set_storage(D._matmul_eager(m.args[0], m.args[1], m.op, m.shape, m.dtype))
+            jobs.append((m, None, "identity", None, None, False))
             stats["products_plain"] = stats.get("products_plain", 0) + 1
             continue
         z_needed = ext[index[id(z)]]
@@ -499,11 +500,21 @@ def _resolve_products(order, root):
             elif c.kind == "b" and c.op == "max" and ((c.args[0] == 0.0 and c.args[1] is z) if isinstance(c.args[0], float)
                                                       else (isinstance(c.args[1], float) and c.args[1] == 0.0 and c.args[0] is z)):
                 act, anode = "relu", c
-        zs, as_ = D._gemm_epilogue(m.args[0], m.args[1], m.op, m.shape, m.dtype, bias, act, z_needed or anode is None)
+        jobs.append((m, bias, act, z, anode, z_needed or anode is None))
         stats["products_fused"] = stats.get("products_fused", 0) + 1
-        if anode is not None:
+    # All products of the DAG are independent of each other (operands exist): hand them over together, so that the
+    # library runs those of one class as ONE launch (ag_gemm_group) -- the four gate products of an LSTM step, their
+    # four dx products, the dW products of several timesteps.
+    results = D._gemm_group([(m.args[0], m.args[1], m.op, m.shape, m.dtype, bias, act, want_z)
+                             for m, bias, act, z, anode, want_z in jobs])
+    if len(jobs) > 1:
+        stats["product_groups"] = stats.get("product_groups", 0) + 1
+    for (m, bias, act, z, anode, want_z), (zs, as_) in zip(jobs, results):
+        if z is None:
+            m._set_storage(zs)
+        elif anode is not None:
             anode._set_storage(as_)
-            if z_needed:
+            if want_z:
                 z._set_storage(zs)
         else:
             z._set_storage(zs)

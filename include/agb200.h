@@ -323,6 +323,27 @@ ag_status ag_gemm_epilogue(int32_t dtype, int32_t transA, int32_t transB, int64_
  * the fused elementwise chain that follows it (ag_ewise_fused). */
 ag_status ag_gemm_epilogue_query(int32_t dtype, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
                                  const void* A, int64_t lda, const void* B, int64_t ldb, int32_t* fused_out);
+/* Several independent products (each with the optional bias / activation epilogue of ag_gemm_epilogue) handed over
+ * together, so that the library can run them as ONE launch: the four gate products of an LSTM step -- the reference's
+ * own comment, examples/charlm.jl:69-73: "we can probably combine these four operations into one" -- their four
+ * gradient products, and the weight-gradient products of several timesteps.  Products the tcgen05 engine takes are
+ * grouped by class (operand majors, orientation), up to 8 per launch; the rest run one by one.  Values are those of n
+ * separate ag_gemm_epilogue calls up to the summation order along K (a group that fills the SMs is not split along K
+ * where a lone product would be); deterministic for a given group. */
+typedef struct {
+  int32_t transA, transB;
+  int64_t M, N, K;
+  const void* A;
+  int64_t lda;
+  const void* B;
+  int64_t ldb;
+  const void* bias; /* M values or NULL */
+  int32_t act;      /* AG_U_IDENTITY, AG_U_RELU, AG_U_TANH or AG_U_SIGM */
+  void* C;
+  void* C2;         /* NULL, or the activation goes here and C receives the pre-activation sum */
+  int64_t ldc;
+} ag_gemm_desc;
+ag_status ag_gemm_group(int32_t dtype, int32_t n, const ag_gemm_desc* descs);
 /* Select the Float32 GEMM engine: 0 = auto, 1 = force FFMA, 2 = force tcgen05 (error if the
  * shape does not qualify).  Test hook. */
 ag_status ag_gemm_set_engine(int32_t engine);

@@ -420,6 +420,15 @@ class FakeLib:
             c[:] = a
         return 0
 
+    def ag_gemm_group(self, dtype, n, descs):
+        for i in range(n):
+            d = descs[i]
+            st = self.ag_gemm_epilogue(dtype, d.transA, d.transB, d.M, d.N, d.K, d.A, d.lda, d.B, d.ldb, d.bias, d.act,
+                                       d.C, d.C2, d.ldc)
+            if st:
+                return st
+        return 0
+
     def ag_gemm_epilogue_query(self, dtype, ta, tb, M, N, K, A, lda, B, ldb, out):
         _out(out).value = 1 if (dtype == 0 and 2.0 * M * N * K >= 3.0e4 and not (M <= 16 or N <= 16)) else 0   # a stand-in rule
         return 0

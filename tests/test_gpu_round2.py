@@ -203,3 +203,55 @@ def test_c_side_tape_matches_the_host_tape_bitwise(ag, cfg, dtype):
         got = t.grad(p).to_numpy()
         assert np.array_equal(got.reshape(g.shape), g)
     t.close()
+
+
+def test_gemm_group_equals_separate_calls_bitwise(ag):
+    """ag_gemm_group: products handed over together (grouped by class into single launches, split along K as a group,
+    ineligible ones run one by one) give the values of separate ag_gemm_epilogue calls: bit for bit when the K split
+    is the same (the ineligible product here), otherwise to the rounding of a different summation order (a group fills
+    the SMs without splitting K where a lone product splits), checked at 4e-6 of the largest value."""
+    import sys
+    L = ag._lib
+    lib, check = L.lib, L.check
+    rng = np.random.default_rng(5)
+    H, EH, B = 512, 640, 256
+    x = ag.DArray.from_numpy(rng.standard_normal((EH, B)).astype(np.float32))
+    dz = [ag.DArray.from_numpy(rng.standard_normal((H, B)).astype(np.float32)) for _ in range(4)]
+    Ws = [ag.DArray.from_numpy((rng.standard_normal((H, EH)) / 25).astype(np.float32)) for _ in range(4)]
+    bs = [ag.DArray.from_numpy(rng.standard_normal((H,)).astype(np.float32)) for _ in range(4)]
+    small_a = ag.DArray.from_numpy(rng.standard_normal((10, 64)).astype(np.float32))        # not a tcgen05 shape
+    small_b = ag.DArray.from_numpy(rng.standard_normal((64, 700)).astype(np.float32))
+    acts = [7, 7, 7, 6]
+    # (ta, tb, M, N, K, A, lda, B, ldb, bias, act, two outputs)
+    probs = [(0, 0, H, B, EH, Ws[g], H, x, EH, bs[g], acts[g], g == 1) for g in range(4)]          # gates: W*x .+ b
+    probs += [(0, 1, H, EH, B, dz[g], H, x, EH, None, 0, False) for g in range(4)]                  # dW = dz*x'
+    probs += [(1, 0, EH, B, H, Ws[g], H, dz[g], H, None, 0, False) for g in range(4)]               # dx = W'*dz
+    probs += [(0, 0, 10, 700, 64, small_a, 10, small_b, 64, None, 0, False)]
+
+    def run(grouped):
+        outs = []
+        descs = (L.GemmDesc * len(probs))()
+        for d, (ta, tb, M, N, K, A, lda, Bm, ldb, bias, act, two) in zip(descs, probs):
+            c = ag.DArray.empty((M, N), np.float32)
+            c2 = ag.DArray.empty((M, N), np.float32) if two else None
+            outs.append((c, c2))
+            d.transA, d.transB, d.M, d.N, d.K, d.A, d.lda, d.B, d.ldb = ta, tb, M, N, K, A.ptr, lda, Bm.ptr, ldb
+            d.bias, d.act, d.C, d.C2, d.ldc = (bias.ptr if bias is not None else None), act, c.ptr, (c2.ptr if two else None), M
+        if grouped:
+            check(lib.ag_gemm_group(0, len(probs), descs))
+        else:
+            for i in range(len(probs)):
+                check(lib.ag_gemm_group(0, 1, C.byref(descs[i])))
+        return [(c.to_numpy(), None if c2 is None else c2.to_numpy()) for c, c2 in outs]
+    l0 = ag.launch_count()
+    a = run(True)
+    l1 = ag.launch_count()
+    b = run(False)
+    l2 = ag.launch_count()
+    assert l1 - l0 < l2 - l1
+    for (ca, c2a), (cb, c2b) in zip(a, b):
+        assert np.max(np.abs(ca - cb)) <= 4e-6 * np.max(np.abs(cb))
+        assert (c2a is None) == (c2b is None) and (c2a is None or np.max(np.abs(c2a - c2b)) <= 4e-6 * np.max(np.abs(c2b)))
+    assert np.array_equal(a[-1][0], b[-1][0])
+    ref = Ws[0].to_numpy().astype(np.float64) @ x.to_numpy().astype(np.float64) + bs[0].to_numpy()[:, None]
+    assert np.max(np.abs(a[0][0] - 1 / (1 + np.exp(-ref)))) < 1e-5
