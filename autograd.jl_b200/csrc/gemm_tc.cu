@@ -68,6 +68,7 @@ static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 struct TcParams {
   int mm_tiles, nn_tiles, splits;
+  int mm_pitch;            // rows between consecutive mm tiles (<= TC_BM: a tile always loads TC_BM rows, stores mm_pitch)
   int kblocks_total, kblocks_per_split;
   int64_t MM, NN;          // extents along mm / nn
   float* out;              // C, or the split-K workspace
@@ -324,17 +325,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       decode(w, q, mt, nt, kb0, kb1);
       const CUtensorMap* mapA = &g.tmA[q];
       const CUtensorMap* mapB = &g.tmB[q];
+      const int mm0 = mt * g.p[q].mm_pitch;
+      // a K-major A tile is loaded with a box of mm_pitch rows (the tile's own rows only); an MN-major one in four
+      // 32-row boxes (its last rows overlap the next tile when mm_pitch < TC_BM)
+      const uint32_t tx_bytes = (A_KMAJOR ? (uint32_t)g.p[q].mm_pitch * (TC_BK * 4) : (uint32_t)TC_A_BYTES) + TC_B_BYTES;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t st = smem_base + s * TC_RAW_BYTES;
         if (elect_one()) {
-          mbar_expect_tx(full_bar(s), TC_RAW_BYTES);
+          mbar_expect_tx(full_bar(s), tx_bytes);
           if (A_KMAJOR) {
-            tma_load_2d(st, mapA, full_bar(s), kb * TC_BK, mt * TC_BM);
+            tma_load_2d(st, mapA, full_bar(s), kb * TC_BK, mm0);
           } else {
 #pragma unroll
             for (int c = 0; c < TC_BM / 32; ++c)
-              tma_load_2d(st + c * 4096, mapA, full_bar(s), mt * TC_BM + c * 32, kb * TC_BK);
+              tma_load_2d(st + c * 4096, mapA, full_bar(s), mm0 + c * 32, kb * TC_BK);
           }
           const uint32_t sb = st + TC_A_BYTES;
           if (B_KMAJOR) {
@@ -495,7 +500,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(acc));
       }
-      const int64_t mm = (int64_t)mt * TC_BM + r_loc;
+      // rows beyond the tile pitch belong to the next tile (which computes them itself)
+      const int64_t mm = r_loc < p.mm_pitch ? (int64_t)mt * p.mm_pitch + r_loc : p.MM;
       const int64_t nn0 = (int64_t)nt * TC_BN;
       if (p.split_stride == 0) {
         // direct path: alpha, bias, activation and the stores
@@ -631,8 +637,10 @@ static bool make_map(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, i
 // tiles than SMs is split along K, AGB_TC_SPLIT_MINKB = k-blocks per split at least,
 // AGB_TC_FLUSH_SKINNY = 1 promotes every k-block for the skinny shapes as well.
 struct TcKnobs {
-  int split_kb, min_kb, flush_skinny;
+  int split_kb, min_kb, flush_skinny, even_tiles;
   TcKnobs() {
+    const char* t = getenv("AGB_TC_EVEN_TILES");       // 0: mm tiles of 128 rows with a ragged last tile
+    even_tiles = t ? atoi(t) : 1;
     const char* f = getenv("AGB_TC_FLUSH_SKINNY");     // 1: promote every k-block for the skinny shapes too
     flush_skinny = f ? atoi(f) : 8;
     const char* e = getenv("AGB_TC_SPLIT_KB");
@@ -706,15 +714,33 @@ ag_status gemm_tc_group(int n, const TcJob* jobs) {
     int64_t MM, NN, lda_, ldb_;
     if (!cls.transposed) { pa = j.A; lda_ = j.lda; MM = j.M; pb = j.B; ldb_ = j.ldb; NN = j.N; }
     else { pa = j.B; lda_ = j.ldb; MM = j.N; pb = j.A; ldb_ = j.lda; NN = j.M; }
+    TcParams& p = g.p[q];
+    p.mm_tiles = (int)cdiv(MM, TC_BM);
+    p.nn_tiles = (int)cdiv(NN, TC_BN);
+    // Equal tiles.  (1) 784 rows are 7 tiles of 112 (each loads 128 rows, the overlap comes from L2) instead of 6
+    // full tiles and one of 16 rows whose CTAs idle while the others stream.  (2) A lone product with more tiles than
+    // SMs and a K-major A (w1*x: 512 tiles = 3.46 waves on 148 SMs, i.e. the time of 4) is cut into a whole number
+    // of waves of narrower tiles (586 tiles of 112 rows = 4 waves of 0.875 tile times): the TMA box has mm_pitch
+    // rows, so a narrower tile moves proportionally fewer bytes.
+    p.mm_pitch = TC_BM;
+    if (tc_knobs().even_tiles) {
+      p.mm_pitch = (int)((cdiv(MM, p.mm_tiles) + 7) / 8 * 8);
+      const int64_t tiles = (int64_t)p.mm_tiles * p.nn_tiles;
+      if (n == 1 && cls.ak && tiles > c.num_sms) {
+        const int64_t waves = cdiv(tiles, c.num_sms);
+        const int64_t want = waves * c.num_sms / p.nn_tiles;          // mm tiles that fill `waves` waves
+        const int pitch = (int)((cdiv(MM, want) + 7) / 8 * 8);
+        if (want > p.mm_tiles && pitch >= 64 && pitch < p.mm_pitch) p.mm_pitch = pitch;
+      }
+      if (p.mm_pitch > TC_BM) p.mm_pitch = TC_BM;
+      p.mm_tiles = (int)cdiv(MM, p.mm_pitch);
+    }
     bool ok;
-    if (cls.ak) ok = make_map(&g.tmA[q], pa, j.K, MM, lda_, TC_BK, TC_BM, true);
+    if (cls.ak) ok = make_map(&g.tmA[q], pa, j.K, MM, lda_, TC_BK, p.mm_pitch, true);
     else ok = make_map(&g.tmA[q], pa, MM, j.K, lda_, 32, TC_BK, false);
     if (cls.bk) ok = ok && make_map(&g.tmB[q], pb, j.K, NN, ldb_, TC_BK, TC_BN, true);
     else ok = ok && make_map(&g.tmB[q], pb, NN, j.K, ldb_, 32, TC_BK, false);
     AG_CHECK(ok, AG_ECUDA, "ag_gemm: cuTensorMapEncodeTiled failed");
-    TcParams& p = g.p[q];
-    p.mm_tiles = (int)cdiv(MM, TC_BM);
-    p.nn_tiles = (int)cdiv(NN, TC_BN);
     p.kblocks_total = (int)cdiv(j.K, TC_BK);
     p.MM = MM;
     p.NN = NN;
