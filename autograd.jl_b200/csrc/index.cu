@@ -5,14 +5,16 @@
 // scalar loop addtoindex! (src/addto.jl:107-129); cat/uncat (src/cat.jl:27-31,46-67);
 // axpy!/lmul! (src/sparse.jl:50-52, README.md:70-77).
 //
-// Scatter-add is deterministic: stable LSD radix sort of (destination, source position) pairs, then
-// a segmented reduce that sums each destination's contributions in source order and performs ONE
-// read-modify-write per touched destination.  Index bookkeeping (which destination each value
-// goes to) is bit-exact with the reference; only the floating-point association order inside a
-// destination can differ from the reference's interleaved sequential order.
+// Scatter-add is deterministic: an in-tree stable LSD radix sort (8 bits per pass; only as many passes as the number
+// of destinations needs: one for the 128-column embedding of config 4) of (destination, source position) pairs,
+// then a segmented reduce that sums each destination's contributions in a fixed order derived from the source order
+// (warps take consecutive runs of the segment, 128-bit loads along the value block) and performs ONE
+// read-modify-write per touched destination.  Index bookkeeping (which destination each value goes to) is bit-exact
+// with the reference; only the floating-point association order inside a destination can differ from the
+// reference's interleaved sequential order.
+// Algorithmic bytes of a scatter-add: n*block*s (values) + 8n (indices) + 2*touched*block*s (destination RMW).
 #include "common.cuh"
-
-#include <cub/device/device_radix_sort.cuh>
+#include "ewise_ops.cuh"
 
 namespace agb {
 
@@ -33,41 +35,233 @@ __global__ void __launch_bounds__(256)
   int64_t j = i / rows, r = i - j * rows;
   out[i] = x[r + col[j] * rows];
 }
-
-__global__ void __launch_bounds__(256) k_iota(int32_t* __restrict__ p, int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = (int32_t)i;
-}
-
-// Validate indices: flag[0] |= 1 if any key is out of [0, nkeys)
-__global__ void __launch_bounds__(256)
-    k_check_idx(const int64_t* __restrict__ idx, int64_t n, int64_t nkeys, int32_t* __restrict__ flag) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && (idx[i] < 0 || idx[i] >= nkeys)) *flag = 1;
-}
-
-// One thread-group per (segment head, row): sums the segment's values in source order.
-// keys sorted ascending, pos = source positions (ascending inside a key: stable sort).
-// thread (j, b): if j is a segment head, dest[key*block + b] += sum_{members} vals[pos*block + b]
+// the same with 128-bit accesses (rows a multiple of the vector width, both arrays 16-byte aligned): a thread moves
+// one 16-byte piece of a column
 template <typename T>
 __global__ void __launch_bounds__(256)
-    k_segreduce(const int64_t* __restrict__ keys, const int32_t* __restrict__ pos,
-                const T* __restrict__ vals, int64_t n, int64_t block, int64_t nkeys, T* __restrict__ dest) {
-  // blockIdx.x walks sorted entries in groups; threads along the value block for coalescing
-  const int lanes = block >= 256 ? 256 : (block >= 128 ? 128 : (block >= 64 ? 64 : (block >= 32 ? 32 : (block >= 16 ? 16 : (block >= 8 ? 8 : (block >= 4 ? 4 : (block >= 2 ? 2 : 1)))))));
-  const int per_blk = 256 / lanes;  // entries handled concurrently by one CUDA block
+    k_gather_cols_v(const T* __restrict__ x, int64_t rows, const int64_t* __restrict__ col,
+                    T* __restrict__ out, int64_t total_vec) {
+  constexpr int N = 16 / sizeof(T);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int64_t rv = rows / N;
+  int64_t j = i / rv, r = (i - j * rv) * N;
+  *reinterpret_cast<uint4*>(out + j * rows + r) = __ldg(reinterpret_cast<const uint4*>(x + r + col[j] * rows));
+}
+
+// ---- stable LSD radix sort of (key, source position), 8 bits per pass ------------------------------------
+// A block owns a contiguous tile of the input (tile = a multiple of 256 entries).  Pass = three launches:
+// k_radix_hist (per-block digit counts, stored digit-major), k_radix_scan (exclusive scan of that table: where each
+// (digit, block) run starts), k_radix_scatter (stable ranks inside the tile -> final positions).  The first pass reads
+// the caller's int64 indices (position = entry number), checks their range and narrows them to uint32; entries out
+// of range get the key `nkeys` (sorted behind every valid key, never written) and raise the sticky flag.
+constexpr int kRadixBits = 8, kRadixBins = 1 << kRadixBits;
+
+template <bool FIRST>
+__device__ __forceinline__ uint32_t radix_key(const void* keys, int64_t i, int64_t nkeys, int32_t* flag) {
+  if (FIRST) {
+    const int64_t k = ((const int64_t*)keys)[i];
+    if (k < 0 || k >= nkeys) {
+      *flag = 1;
+      return (uint32_t)nkeys;
+    }
+    return (uint32_t)k;
+  }
+  return ((const uint32_t*)keys)[i];
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256)
+    k_radix_hist(const void* __restrict__ keys, int64_t n, int64_t tile, int shift, int64_t nkeys,
+                 int32_t* __restrict__ flag, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[kRadixBins];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * tile, hi = min(n, lo + tile);
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256)
+    atomicAdd(&h[(radix_key<FIRST>(keys, i, nkeys, flag) >> shift) & (kRadixBins - 1)], 1u);
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of `m` counters in place (one block; a running carry over chunks of 1024)
+__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t* __restrict__ hist, int64_t m) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t base = 0; base < m; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = i < m ? hist[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t t = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      wsum[lane] = t;                       // inclusive sums of the warps
+    }
+    __syncthreads();
+    const uint32_t before = carry + (w ? wsum[w - 1] : 0u) + x - v;
+    if (i < m) hist[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256)
+    k_radix_scatter(const void* __restrict__ keys_in, const int32_t* __restrict__ pos_in, int64_t n, int64_t tile,
+                    int shift, int64_t nkeys, const uint32_t* __restrict__ offs, uint32_t* __restrict__ keys_out,
+                    int32_t* __restrict__ pos_out) {
+  __shared__ uint32_t run[kRadixBins];          // next free position of every digit for this block
+  __shared__ uint32_t cnt[8][kRadixBins];       // this round's entries per warp and digit
+  int32_t dummy = 0;
+  run[threadIdx.x] = offs[(int64_t)threadIdx.x * gridDim.x + blockIdx.x];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t lo = (int64_t)blockIdx.x * tile, hi = min(n, lo + tile);
+  for (int64_t base = lo; base < hi; base += 256) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cnt[q][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = base + threadIdx.x;
+    const bool on = i < hi;
+    uint32_t key = 0, d = 0;
+    if (on) {
+      key = radix_key<FIRST>(keys_in, i, nkeys, &dummy);
+      d = (key >> shift) & (kRadixBins - 1);
+    }
+    // entries of the warp with the same digit, in lane (= source) order
+    const uint32_t act = __ballot_sync(0xffffffffu, on);
+    uint32_t peers = 0;
+    if (on) peers = __match_any_sync(act, d);
+    const uint32_t below = peers & ((1u << lane) - 1u);
+    if (on && below == 0) cnt[w][d] = __popc(peers);
+    __syncthreads();
+    if (on) {
+      uint32_t at = run[d] + __popc(below);
+      for (int q = 0; q < w; ++q) at += cnt[q][d];
+      keys_out[at] = key;
+      pos_out[at] = FIRST ? (int32_t)i : pos_in[i];
+    }
+    __syncthreads();
+    uint32_t tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tot += cnt[q][threadIdx.x];
+    run[threadIdx.x] += tot;
+    __syncthreads();
+  }
+}
+
+// Narrow value blocks (fewer than 32 vector lanes): a group of `lanes` threads per sorted entry, lanes along the value
+// block; the group of a segment head walks its segment in source order, one read-modify-write per destination.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_segreduce_narrow(const uint32_t* __restrict__ keys, const int32_t* __restrict__ pos, const T* __restrict__ vals,
+                       int64_t n, int64_t block, int64_t nkeys, int lanes, T* __restrict__ dest) {
+  const int per_blk = 256 / lanes;
   const int lane = threadIdx.x % lanes, slot = threadIdx.x / lanes;
   const int64_t j = (int64_t)blockIdx.x * per_blk + slot;
-  if (j >= n) return;
-  const int64_t key = keys[j];
-  if (key < 0 || key >= nkeys) return;      // out of range: flagged by k_check_idx, never written
-  if (j > 0 && keys[j - 1] == key) return;  // not a head
+  if (j >= n || lane >= block) return;
+  const uint32_t key = keys[j];
+  if ((int64_t)key >= nkeys) return;          // out of range: flagged by the first sort pass, never written
+  if (j > 0 && keys[j - 1] == key) return;    // not a head
   int64_t e = j + 1;
   while (e < n && keys[e] == key) ++e;
   for (int64_t b = lane; b < block; b += lanes) {
     T s = T(0);
     for (int64_t m = j; m < e; ++m) s += vals[(int64_t)pos[m] * block + b];
-    dest[key * block + b] += s;
+    dest[(int64_t)key * block + b] += s;
+  }
+}
+
+// ---- segmented reduce over the sorted pairs -----------------------------------------------------------------
+// One CUDA block per (segment, slice of 32*V values of the block): the 8 warps take consecutive eighths of the
+// segment, each sums its run in source order (4 entries in flight), the 8 partial sums are added in warp order and
+// the destination is read-modified-written once.  BYKEY: blockIdx.x is a destination, its segment is found by two
+// binary searches (few destinations, many entries: the embedding gradient); otherwise blockIdx.x is a sorted entry
+// and only segment heads work (many destinations).
+template <typename T, int V, bool BYKEY>
+__global__ void __launch_bounds__(256)
+    k_segreduce(const uint32_t* __restrict__ keys, const int32_t* __restrict__ pos, const T* __restrict__ vals,
+                int64_t n, int64_t block, int64_t nkeys, T* __restrict__ dest) {
+  __shared__ T part[8][32 * V];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t j, e;
+  uint32_t key;
+  if (BYKEY) {
+    key = blockIdx.x;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    j = lo;
+    hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] <= key) lo = mid + 1; else hi = mid; }
+    e = lo;
+    if (j == e) return;
+  } else {
+    j = blockIdx.x;
+    key = keys[j];
+    if ((int64_t)key >= nkeys) return;          // out of range: flagged by the first sort pass, never written
+    if (j > 0 && keys[j - 1] == key) return;    // not a head
+    e = j + 1;
+    while (e < n && keys[e] == key) ++e;
+  }
+  const int64_t b = ((int64_t)blockIdx.y * 32 + lane) * V;
+  const int64_t len = e - j, per = (len + 7) / 8;
+  const int64_t m0 = j + w * per, m1 = min(e, m0 + per);
+  T acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = T(0);
+  if (b < block) {
+    int64_t m = m0;
+    for (; m + 4 <= m1; m += 4) {
+      T x[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const T* src = vals + (int64_t)pos[m + u] * block + b;
+        if (V == 4 && sizeof(T) == 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(src);
+          x[u][0] = (T)t4.x; x[u][1 % V] = (T)t4.y; x[u][2 % V] = (T)t4.z; x[u][3 % V] = (T)t4.w;
+        } else if (V == 2 && sizeof(T) == 8) {
+          const double2 t2 = *reinterpret_cast<const double2*>(src);
+          x[u][0] = (T)t2.x; x[u][1 % V] = (T)t2.y;
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) x[u][v] = src[v];
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = (((acc[v] + x[0][v]) + x[1][v]) + x[2][v]) + x[3][v];
+    }
+    for (; m < m1; ++m) {
+      const T* src = vals + (int64_t)pos[m] * block + b;
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] += src[v];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) part[w][lane * V + v] = acc[v];
+  __syncthreads();
+  if (w == 0 && b < block) {
+    T* d = dest + (int64_t)key * block + b;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      T s = part[0][lane * V + v];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) s += part[q][lane * V + v];
+      d[v] += s;
+    }
   }
 }
 
@@ -80,6 +274,20 @@ __global__ void __launch_bounds__(256)
   int64_t slab = inner * len;
   int64_t o = i / slab, w = i - o * slab;  // w = ii + inner*r
   dst[o * inner * dst_red + dst_off * inner + w] = src[o * inner * src_red + src_off * inner + w];
+}
+
+// 128-bit form: every slab (inner*len elements) and both slab origins are multiples of the vector width
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_slab_copy_v(const T* __restrict__ src, int64_t src_red, int64_t src_off, T* __restrict__ dst,
+                  int64_t dst_red, int64_t dst_off, int64_t inner, int64_t len, int64_t total_vec) {
+  constexpr int N = 16 / sizeof(T);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int64_t slab = inner * len, sv = slab / N;
+  int64_t o = i / sv, w = (i - o * sv) * N;
+  *reinterpret_cast<uint4*>(dst + o * inner * dst_red + dst_off * inner + w) =
+      *reinterpret_cast<const uint4*>(src + o * inner * src_red + src_off * inner + w);
 }
 
 template <typename T>
@@ -137,10 +345,20 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// x .*= alpha; a thread owns one aligned 16-byte piece (the ragged head / tail elements go one by one)
 template <typename T>
 __global__ void __launch_bounds__(256) k_scale(T alpha, T* __restrict__ x, int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) x[i] *= alpha;
+  constexpr int N = 16 / sizeof(T);
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * N;
+  if (i >= n) return;
+  if (i + N <= n && (((uintptr_t)(x + i)) & 15) == 0) {
+    Pack<T> v = *reinterpret_cast<Pack<T>*>(x + i);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v.v[k] *= alpha;
+    *reinterpret_cast<Pack<T>*>(x + i) = v;
+  } else {
+    for (int k = 0; k < N && i + k < n; ++k) x[i + k] *= alpha;
+  }
 }
 
 template <typename T>
@@ -148,44 +366,73 @@ static ag_status scatter_add_impl(T* dest, int64_t dest_len, const int64_t* idx,
                                   int64_t n, int64_t block) {
   Context& c = ctx();
   AG_CHECK(n < ((int64_t)1 << 31), AG_EUNSUPPORTED, "ag_scatter_add: n=%lld too large", (long long)n);
-  int64_t nkeys = dest_len / block;
-  int end_bit = 1;
-  while (end_bit < 63 && ((int64_t)1 << end_bit) < nkeys) ++end_bit;
-  size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int64_t*)nullptr, (int64_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, end_bit,
-                                  c.stream);
-  size_t off_keys = 256;
-  size_t off_pos_in = off_keys + (((size_t)n * 8 + 255) & ~size_t(255));
-  size_t off_pos_out = off_pos_in + (((size_t)n * 4 + 255) & ~size_t(255));
-  size_t off_tmp = off_pos_out + (((size_t)n * 4 + 255) & ~size_t(255));
-  size_t total = off_tmp + tmp_bytes;
-  char* ws = (char*)workspace(total);
+  const int64_t nkeys = dest_len / block;
+  AG_CHECK(nkeys < ((int64_t)1 << 31), AG_EUNSUPPORTED, "ag_scatter_add: %lld destinations", (long long)nkeys);
+  // bits that distinguish the keys 0..nkeys (nkeys itself marks an out-of-range entry)
+  int bits = 1;
+  while (bits < 32 && ((int64_t)1 << bits) <= nkeys) ++bits;
+  const int passes = (bits + kRadixBits - 1) / kRadixBits;
+  // tile: 2048 entries per block, more when that would need more than 4096 blocks (the scan is one block)
+  int64_t tile = 2048;
+  if (cdiv(n, tile) > 4096) tile = cdiv(cdiv(n, (int64_t)4096), (int64_t)256) * 256;
+  const int64_t nblk = cdiv(n, tile);
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t sz_k = al((size_t)n * 4), sz_h = al((size_t)nblk * kRadixBins * 4);
+  char* ws = (char*)workspace(256 + 4 * sz_k + sz_h);
   if (!ws) return AG_ENOMEM;
   int32_t* flag = oob_flag();
   if (!flag) return AG_ENOMEM;
-  int64_t* keys_out = (int64_t*)(ws + off_keys);
-  int32_t* pos_in = (int32_t*)(ws + off_pos_in);
-  int32_t* pos_out = (int32_t*)(ws + off_pos_out);
-  void* tmp = ws + off_tmp;
-  unsigned nb = (unsigned)cdiv(n, 256);
-  k_check_idx<<<nb, 256, 0, c.stream>>>(idx, n, nkeys, flag);
-  AG_LAUNCHED();
-  k_iota<<<nb, 256, 0, c.stream>>>(pos_in, n);
-  AG_LAUNCHED();
-  AG_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, idx, keys_out, (const int32_t*)pos_in,
-                                          pos_out, (int)n, 0, end_bit, c.stream));
-  ctx().launches += 1;
+  uint32_t* kbuf[2] = {(uint32_t*)(ws + 256), (uint32_t*)(ws + 256 + sz_k)};
+  int32_t* pbuf[2] = {(int32_t*)(ws + 256 + 2 * sz_k), (int32_t*)(ws + 256 + 3 * sz_k)};
+  uint32_t* hist = (uint32_t*)(ws + 256 + 4 * sz_k);
   // out-of-range destinations are a BoundsError in the reference.  The host wrapper checks the bounds of the
   // index vectors it normalised; the device check is sticky and surfaces at the next ag_sync (no per-call
   // host synchronisation, so a whole step stays capturable); out-of-range entries are skipped, never written.
-  int lanes = block >= 256 ? 256 : 1;
-  if (block < 256) {
-    lanes = 1;
-    while (lanes * 2 <= block) lanes *= 2;
+  int cur = 0;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = p * kRadixBits;
+    if (p == 0) {
+      k_radix_hist<true><<<(unsigned)nblk, 256, 0, c.stream>>>(idx, n, tile, shift, nkeys, flag, hist);
+      AG_LAUNCHED();
+      k_radix_scan<<<1, 1024, 0, c.stream>>>(hist, nblk * kRadixBins);
+      AG_LAUNCHED();
+      k_radix_scatter<true><<<(unsigned)nblk, 256, 0, c.stream>>>(idx, nullptr, n, tile, shift, nkeys, hist, kbuf[0], pbuf[0]);
+      AG_LAUNCHED();
+      cur = 0;
+    } else {
+      k_radix_hist<false><<<(unsigned)nblk, 256, 0, c.stream>>>(kbuf[cur], n, tile, shift, nkeys, flag, hist);
+      AG_LAUNCHED();
+      k_radix_scan<<<1, 1024, 0, c.stream>>>(hist, nblk * kRadixBins);
+      AG_LAUNCHED();
+      k_radix_scatter<false><<<(unsigned)nblk, 256, 0, c.stream>>>(kbuf[cur], pbuf[cur], n, tile, shift, nkeys, hist,
+                                                                  kbuf[cur ^ 1], pbuf[cur ^ 1]);
+      AG_LAUNCHED();
+      cur ^= 1;
+    }
   }
-  int per_blk = 256 / lanes;
-  k_segreduce<T><<<(unsigned)cdiv(n, per_blk), 256, 0, c.stream>>>(keys_out, pos_out, vals, n, block, nkeys, dest);
+  const uint32_t* keys = kbuf[cur];
+  const int32_t* pos = pbuf[cur];
+  constexpr int VMAX = 16 / sizeof(T);
+  const bool vec = block % VMAX == 0 && ((uintptr_t)vals & 15) == 0 && ((uintptr_t)dest & 15) == 0;
+  const int V = vec ? VMAX : 1;
+  if (cdiv(block, (int64_t)V) < 32) {           // narrow value blocks
+    int lanes = 1;
+    while (lanes < block && lanes < 128) lanes *= 2;
+    k_segreduce_narrow<T><<<(unsigned)cdiv(n, (int64_t)(256 / lanes)), 256, 0, c.stream>>>(keys, pos, vals, n, block, nkeys,
+                                                                                       lanes, dest);
+    AG_LAUNCHED();
+    return AG_OK;
+  }
+  const bool bykey = nkeys * 8 <= n;
+  dim3 grid((unsigned)(bykey ? nkeys : n), (unsigned)cdiv(block, (int64_t)32 * V));
+  AG_CHECK(grid.y <= 65535, AG_EUNSUPPORTED, "ag_scatter_add: block of %lld values", (long long)block);
+  if (vec) {
+    if (bykey) k_segreduce<T, VMAX, true><<<grid, 256, 0, c.stream>>>(keys, pos, vals, n, block, nkeys, dest);
+    else k_segreduce<T, VMAX, false><<<grid, 256, 0, c.stream>>>(keys, pos, vals, n, block, nkeys, dest);
+  } else {
+    if (bykey) k_segreduce<T, 1, true><<<grid, 256, 0, c.stream>>>(keys, pos, vals, n, block, nkeys, dest);
+    else k_segreduce<T, 1, false><<<grid, 256, 0, c.stream>>>(keys, pos, vals, n, block, nkeys, dest);
+  }
   AG_LAUNCHED();
   return AG_OK;
 }
@@ -216,10 +463,19 @@ ag_status ag_gather_cols(int32_t dtype, const void* x, int64_t rows, const int64
   if (total == 0) return AG_OK;
   AG_CHECK(x && col && out && rows > 0 && ncols_out > 0, AG_EINVAL, "ag_gather_cols: bad arguments");
   Context& c = ctx();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_gather_cols: dtype %d", dtype);
+  const int N = dtype == AG_F32 ? 4 : 2;
+  if (rows % N == 0 && aligned16(x) && aligned16(out)) {
+    const int64_t tv = total / N;
+    unsigned nbv = (unsigned)cdiv(tv, 256);
+    if (dtype == AG_F32) k_gather_cols_v<float><<<nbv, 256, 0, c.stream>>>((const float*)x, rows, col, (float*)out, tv);
+    else k_gather_cols_v<double><<<nbv, 256, 0, c.stream>>>((const double*)x, rows, col, (double*)out, tv);
+    AG_LAUNCHED();
+    return AG_OK;
+  }
   unsigned nb = (unsigned)cdiv(total, 256);
   if (dtype == AG_F32) k_gather_cols<float><<<nb, 256, 0, c.stream>>>((const float*)x, rows, col, (float*)out, total);
-  else if (dtype == AG_F64) k_gather_cols<double><<<nb, 256, 0, c.stream>>>((const double*)x, rows, col, (double*)out, total);
-  else { set_error("ag_gather_cols: dtype %d", dtype); return AG_EUNSUPPORTED; }
+  else k_gather_cols<double><<<nb, 256, 0, c.stream>>>((const double*)x, rows, col, (double*)out, total);
   AG_LAUNCHED();
   return AG_OK;
 }
@@ -245,6 +501,22 @@ ag_status ag_slab_copy(int32_t dtype, const void* src, int64_t src_red, int64_t 
                src_off + len <= src_red && dst_off + len <= dst_red,
            AG_EINVAL, "ag_slab_copy: slab out of range (BoundsError)");
   Context& c = ctx();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_slab_copy: dtype %d", dtype);
+  {
+    const int N = dtype == AG_F32 ? 4 : 2;
+    const int64_t slab = inner * len;
+    if (slab % N == 0 && (inner * src_red) % N == 0 && (inner * dst_red) % N == 0 && (inner * src_off) % N == 0 &&
+        (inner * dst_off) % N == 0 && aligned16(src) && aligned16(dst)) {
+      const int64_t tv = total / N;
+      unsigned nbv = (unsigned)cdiv(tv, 256);
+      if (dtype == AG_F32)
+        k_slab_copy_v<float><<<nbv, 256, 0, c.stream>>>((const float*)src, src_red, src_off, (float*)dst, dst_red, dst_off, inner, len, tv);
+      else
+        k_slab_copy_v<double><<<nbv, 256, 0, c.stream>>>((const double*)src, src_red, src_off, (double*)dst, dst_red, dst_off, inner, len, tv);
+      AG_LAUNCHED();
+      return AG_OK;
+    }
+  }
   unsigned nb = (unsigned)cdiv(total, 256);
   if (dtype == AG_F32)
     k_slab_copy<float><<<nb, 256, 0, c.stream>>>((const float*)src, src_red, src_off, (float*)dst, dst_red, dst_off, inner, len, total);
@@ -322,7 +594,7 @@ ag_status ag_scale(int32_t dtype, double alpha, void* x, int64_t n) {
   if (n == 0) return AG_OK;
   AG_CHECK(x && n > 0, AG_EINVAL, "ag_scale: bad arguments");
   Context& c = ctx();
-  unsigned nb = (unsigned)cdiv(n, 256);
+  unsigned nb = (unsigned)cdiv(n, dtype == AG_F32 ? 1024 : 512);
   if (dtype == AG_F32) k_scale<float><<<nb, 256, 0, c.stream>>>((float)alpha, (float*)x, n);
   else if (dtype == AG_F64) k_scale<double><<<nb, 256, 0, c.stream>>>(alpha, (double*)x, n);
   else { set_error("ag_scale: dtype %d", dtype); return AG_EUNSUPPORTED; }

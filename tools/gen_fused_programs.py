@@ -57,6 +57,14 @@ def main(out=OUT):
                     ent["where"].add(CUR[0])
             return st
 
+        # Which products take their `.+ b` / activation into the epilogue depends on sizes (the tcgen05 engine takes
+        # them); both outcomes are recorded: EPI[0] = None -> the stand-in's size rule, 0 / 1 -> never / always.
+        def ag_gemm_epilogue_query(self, dtype, ta, tb, M, N, K, A, lda, B, ldb, out):
+            if EPI[0] is None:
+                return super().ag_gemm_epilogue_query(dtype, ta, tb, M, N, K, A, lda, B, ldb, out)
+            fake_abi._out(out).value = EPI[0]
+            return 0
+
         # stream capture on the stand-in: the step simply runs (only the sequence of programs matters here)
         def ag_graph_begin(self): return 0
         def ag_graph_end(self, ref): ref._obj.value = 1; return 0
@@ -64,6 +72,7 @@ def main(out=OUT):
         def ag_graph_destroy(self, h): return 0
 
     CUR = ["?"]
+    EPI = [None]
     fake, restore = fake_abi.install(ag, Recorder())
     L = sys.modules["agb200.lazy"]
     prev = L.set_fusion(True)
@@ -95,9 +104,10 @@ def main(out=OUT):
         ag.sync()
 
     try:
-        for gc in (None, ag.release_node):
+        for gc, epi in ((None, None), (ag.release_node, None), (ag.release_node, 1), (None, 1)):
             ag.set_gc_function(gc if gc is not None else (lambda n, t: None))
-            for dtype in (np.float64, np.float32):
+            EPI[0] = epi
+            for dtype in ((np.float64, np.float32) if epi is None else (np.float32,)):
                 CUR[0] = "housing"
                 w, x, y = W.housing_init(rng, 24, 5, dtype)
                 xd, yd = dev(x), dev(y)
