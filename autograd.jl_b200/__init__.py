@@ -19,7 +19,7 @@ from .graph import StepGraph, Event, pinned_empty
 from .comm import DataParallel
 from .gradcheck import gradcheck
 from .vm import E, Expr, primitive_expr
-from .lazy import set_fusion
+from .lazy import set_fusion, set_col_fusion
 from .ctape import CTape
 from .loader import CharBatches, StagedInput, UByteBatch, charlm_minibatch_ids, read_chars, read_idx_ubyte
 

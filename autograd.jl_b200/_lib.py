@@ -68,6 +68,7 @@ _SIGS = {
     "ag_ewise_vm": [i32, C.POINTER(i32), i32, C.POINTER(dbl), i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl), vp, i64],
     "ag_ewise_fused": [i32, C.POINTER(i32), i32, C.POINTER(dbl), i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl), i32, C.POINTER(vp), i64, i64],
     "ag_ewise_fused_reduce": [i32, C.POINTER(i32), i32, C.POINTER(dbl), i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl), i32, C.POINTER(vp), i64, i64, i64, i64, i64, vp],
+    "ag_ewise_colprog": [i32, C.POINTER(i32), i32, C.POINTER(dbl), i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl), i32, C.POINTER(vp), i64, i64, vp],
     "ag_ewise_fused_set_static": [i32],
     "ag_ewise_fused_query": [C.POINTER(i32), i32, C.POINTER(i32)],
     "ag_ewise_fused_stats": [pi64],

@@ -28,6 +28,7 @@ void* workspace(size_t bytes);  // grows the shared workspace (not during graph 
 int comm_take_timeout();       // comm.cu: a peer-memory wait expired since the last check (0 = none, else 1 + rank)
 int32_t* oob_flag();            // sticky device flag raised by index checks; read and cleared by ag_sync
 
+bool colprog_init();            // fuse.cu: ticket of the column programs (at ag_init)
 bool reduce_scratch_init();     // reduce.cu: counters / second-level partials of the split combine (at ag_init)
 ag_status reduce_double_partials(int dtype, const double* part, int64_t nchunks, int64_t inner, void* out);  // reduce.cu
 

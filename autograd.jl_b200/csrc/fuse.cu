@@ -549,6 +549,382 @@ static void launch_dynamic(int ni, int ns, const FzArgs& a, unsigned nb, cudaStr
   else k_fused<T, VEC, 8, 8, 1, 2><<<nb, kThreads, 0, st>>>(a);
 }
 
+// ---- column programs (ag_ewise_colprog) ------------------------------------------------------------------
+// A chain that contains sums over the rows of an (m, n) matrix and uses them again: the softmax normaliser
+// `ypred .- log.(sum(exp.(ypred), dims=1))` of every model of the reference (examples/mnist.jl:40,
+// examples/charlm.jl:107-110) and the unbroadcast of its gradient (src/unbroadcast.jl:17-24).  The program is a
+// sequence of segments: an ELEMENT segment runs for every row of a column, a COLUMN segment once per column.  G
+// lanes share a column, rows along the lanes (G = 8, 16 or 32: the smallest that gives a short column one row per
+// lane; consecutive lanes read consecutive rows: coalesced); a column sum is accumulated in double by the element
+// segment (CP_CRED), combined over the G lanes and rounded by the next column segment (CP_CFIN).  Instruction set = the one above plus:
+enum {
+  CP_PHASE = 12,   // a = 0: element segment follows, 1: column segment follows
+  CP_CRED = 13,    // column accumulator a += top
+  CP_LD_COL = 14,  // top = column value a (b = 1: push first)
+  CP_ST_COL = 15,  // column value a = top
+  CP_CFIN = 16,    // column value a = top = (T) sum over the lanes of accumulator a; the accumulator is cleared
+  CP_NOPS = 17
+};
+constexpr int CP_COLS = 8;
+
+struct CpArgs {
+  int32_t code[FZ_MAXCODE];
+  double consts[FZ_MAXCONST];
+  const void* in[FZ_DYN_MAXIN];
+  int32_t mode[FZ_DYN_MAXIN];
+  void* out[FZ_DYN_MAXOUT];
+  int32_t ncode, nin, nout;
+  int64_t m, n;          // rows per column, columns
+  double* part;          // per-block partial of the REDUCE operand (or null)
+  int32_t* ticket;
+  void* rout;            // final sum (one T)
+  int32_t zero;          // always 0, but only known at run time: see fz_opaque
+};
+
+template <typename T>
+__device__ __forceinline__ T cp_load(const CpArgs& a, int k, int64_t r, int64_t col) {
+  const T* __restrict__ p = (const T*)a.in[k];
+  switch (a.mode[k]) {
+    case FZ_M_FULL: return p[r + a.m * col];
+    case FZ_M_COLVEC: return p[r];
+    case FZ_M_ROWVEC: return p[col];
+    default: return p[0];
+  }
+}
+
+// one segment [pc0, pc1) for element (r, col) (ELEM) or for column col (!ELEM)
+template <typename T, bool ELEM>
+__device__ __forceinline__ void cp_run(const CpArgs& a, int pc0, int pc1, int64_t r, int64_t col, bool writer,
+                                       T* colval, double* colacc, double& racc) {
+  T tos = T(0), S[FZ_SLOTS];
+  int sp = 0;
+  for (int pc = pc0; pc < pc1; ++pc) {
+    const uint32_t w = (uint32_t)a.code[pc];
+    const int op = w & 0xff, x = (w >> 8) & 0xff, y = (w >> 16) & 0xff;
+    switch (op) {
+      case FZ_LD_IN:
+        if (y) S[sp++] = tos;
+        tos = cp_load<T>(a, x, r, col);
+        break;
+      case FZ_LD_CONST:
+        if (y) S[sp++] = tos;
+        tos = (T)a.consts[x];
+        break;
+      case CP_LD_COL:
+        if (y) S[sp++] = tos;
+        tos = colval[x];
+        break;
+      case CP_ST_COL: colval[x] = tos; break;
+      case FZ_UNARY:
+        switch (x) {
+#define X(OP) case OP: tos = U<OP, T>::f(tos); break;
+          AG_FOR_UNARY(X)
+#undef X
+        }
+        break;
+      case FZ_BIN:
+      case FZ_BIN_IN:
+      case FZ_BIN_CONST: {
+        T l, rr;
+        if (op == FZ_BIN) { l = S[--sp]; rr = tos; }
+        else {
+          const T o = op == FZ_BIN_IN ? cp_load<T>(a, y & 0x7f, r, col) : (T)a.consts[y & 0x7f];
+          l = (y & 0x80) ? o : tos;
+          rr = (y & 0x80) ? tos : o;
+        }
+        const T ab[2] = {l, rr};
+        switch (x) {
+#define CP_BIN_CASE(ID, F) case ID: tos = F<T>::apply(ab); break;
+          CP_BIN_CASE(AG_B_ADD, FAdd) CP_BIN_CASE(AG_B_SUB, FSub) CP_BIN_CASE(AG_B_MUL, FMul)
+          CP_BIN_CASE(AG_B_DIV, FDiv) CP_BIN_CASE(AG_B_MAX, FMax) CP_BIN_CASE(AG_B_MIN, FMin)
+          CP_BIN_CASE(AG_B_POW, FPow) CP_BIN_CASE(AG_B_EQ, FEq) CP_BIN_CASE(AG_B_LT, FLt)
+          CP_BIN_CASE(AG_B_LE, FLe) CP_BIN_CASE(AG_B_GT, FGt) CP_BIN_CASE(AG_B_GE, FGe)
+          CP_BIN_CASE(AG_B_ATAN2, FAtan2) CP_BIN_CASE(AG_B_HYPOT, FHypot)
+#undef CP_BIN_CASE
+        }
+        break;
+      }
+      case FZ_UGRAD: {
+        const T gx = S[--sp];
+        const T gdy = S[--sp];
+        switch (x) {
+#define X(OP) case OP: tos = gdy * U<OP, T>::g(U<OP, T>::needs_x ? gx : T(0), U<OP, T>::needs_y ? tos : T(0)); break;
+          AG_FOR_UNARY(X)
+#undef X
+        }
+        break;
+      }
+      case FZ_TERN: {
+        const T gp = S[--sp];
+        const T gdy = S[--sp];
+        const T t3[3] = {gdy, gp, tos};
+        switch (x) {
+#define CP_TERN_CASE(ID, G) case ID: tos = G<T>::apply(t3); break;
+          CP_TERN_CASE(0, GDiv2) CP_TERN_CASE(1, GEqMask) CP_TERN_CASE(2, GPow1) CP_TERN_CASE(3, GPow2)
+          CP_TERN_CASE(4, GAtan1) CP_TERN_CASE(5, GAtan2) CP_TERN_CASE(6, GHypot)
+#undef CP_TERN_CASE
+        }
+        break;
+      }
+      case FZ_STORE:
+        if (ELEM) ((T*)a.out[x])[r + a.m * col] = tos;
+        else if (writer) ((T*)a.out[x])[col] = tos;
+        break;
+      case CP_CRED: colacc[x] += (double)tos; break;
+      case CP_CFIN: {
+        double v = colacc[x];
+        colacc[x] = 0.0;
+        // (the accumulators were combined over the G lanes before the segment: identical totals on every lane)
+        tos = (T)v;
+        colval[x] = tos;
+        break;
+      }
+      case FZ_REDUCE:
+        if (ELEM || writer) racc += (double)tos;
+        break;
+    }
+  }
+}
+
+// Whole-space sum of the REDUCE operand: per-block partial in double, the last block to finish adds the partials in
+// block order (the result does not depend on the schedule) -- no second launch.
+template <typename T>
+__device__ __forceinline__ void cp_finish(const CpArgs& a, double racc) {
+  if (a.part) {
+    __shared__ double sm[kThreads / 32];
+    __shared__ int last;
+    double v = racc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) r += sm[w];
+      a.part[blockIdx.x] = r;
+      __threadfence();
+      last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+      // the last block to finish adds the partials in block order (the result does not depend on the schedule)
+      double s = 0;
+      for (int64_t i = threadIdx.x; i < gridDim.x; i += kThreads) s += __ldcg(a.part + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double r = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) r += sm[w];
+        *(T*)a.rout = (T)r;
+        *a.ticket = 0;
+      }
+    }
+  }
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads) k_colprog(const __grid_constant__ CpArgs a) {
+  const int lane = threadIdx.x % G;
+  const int64_t col = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+  const bool on = col < a.n;
+  T colval[CP_COLS];
+  double colacc[CP_COLS];
+#pragma unroll
+  for (int k = 0; k < CP_COLS; ++k) { colval[k] = T(0); colacc[k] = 0.0; }
+  double racc = 0.0;
+  int pc = 0;
+  while (pc < a.ncode) {
+    const int elem = (((uint32_t)a.code[pc] >> 8) & 0xff) == 0;      // a CP_PHASE word
+    int pe = pc + 1;
+    while (pe < a.ncode && (a.code[pe] & 0xff) != CP_PHASE) ++pe;
+    if (elem) {
+      if (on)
+        for (int64_t r = lane; r < a.m; r += G) cp_run<T, true>(a, pc + 1, pe, r, col, true, colval, colacc, racc);
+    } else {
+      // finish the column sums this segment reads: combine the accumulators over the G lanes first
+      if (G > 1) {
+        for (int q = pc + 1; q < pe; ++q)
+          if ((a.code[q] & 0xff) == CP_CFIN) {
+            const int x = (a.code[q] >> 8) & 0xff;
+            double v = colacc[x];
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            colacc[x] = v;
+          }
+      }
+      if (on) cp_run<T, false>(a, pc + 1, pe, 0, col, lane == 0, colval, colacc, racc);
+    }
+    pc = pe;
+  }
+  cp_finish<T>(a, racc);
+}
+
+// ---- specialised column programs: the program as a compile-time constant (fuse_static_col.inc) --------------
+struct StaticColProg {
+  int n;
+  uint32_t code[FZ_MAXCODE];
+};
+
+#include "fuse_static_col.inc"
+
+constexpr int cp_seg_end(const StaticColProg& p, int pc) {
+  while (pc < p.n && (p.code[pc] & 0xff) != CP_PHASE) ++pc;
+  return pc;
+}
+constexpr int cp_sp_before(const StaticColProg& p, int pc) {      // stack depth before instruction pc of its segment
+  int sp = 0;
+  for (int i = 0; i < pc; ++i) {
+    const int op = p.code[i] & 0xff, y = (p.code[i] >> 16) & 0xff;
+    if (op == CP_PHASE) sp = 0;
+    if ((op == FZ_LD_IN || op == FZ_LD_CONST || op == CP_LD_COL) && y) ++sp;
+    if (op == FZ_BIN) --sp;
+    if (op == FZ_UGRAD || op == FZ_TERN) sp -= 2;
+  }
+  return sp;
+}
+
+template <int PROG, int PC, bool ELEM, typename T>
+__device__ __forceinline__ void cps_step(const CpArgs& a, int64_t r, int64_t col, bool writer, T (&S)[FZ_SLOTS], T& tos,
+                                         T (&colval)[CP_COLS], double (&colacc)[CP_COLS], double& racc) {
+  constexpr uint32_t w = kColProgs[PROG].code[PC];
+  constexpr int op = w & 0xff, x = (w >> 8) & 0xff, y = (w >> 16) & 0xff;
+  constexpr int sp = cp_sp_before(kColProgs[PROG], PC);
+  if constexpr (op == FZ_LD_IN || op == FZ_LD_CONST || op == CP_LD_COL) {
+    if constexpr (y != 0) S[sp] = tos;
+    if constexpr (op == FZ_LD_IN) tos = cp_load<T>(a, x, r, col);
+    else if constexpr (op == FZ_LD_CONST) tos = (T)a.consts[x];
+    else tos = colval[x];
+  } else if constexpr (op == CP_ST_COL) {
+    colval[x] = tos;
+  } else if constexpr (op == FZ_UNARY) {
+    tos = U<x, T>::f(tos);
+  } else if constexpr (op == FZ_BIN) {
+    const T ab[2] = {S[sp - 1], tos};
+    tos = BinSel<x, T>::type::apply(ab);
+  } else if constexpr (op == FZ_BIN_IN || op == FZ_BIN_CONST) {
+    constexpr int k = y & 0x7f;
+    constexpr bool rev = (y & 0x80) != 0;
+    T o;
+    if constexpr (op == FZ_BIN_IN) o = cp_load<T>(a, k, r, col);
+    else o = (T)a.consts[k];
+    const T ab[2] = {rev ? o : tos, rev ? tos : o};
+    tos = BinSel<x, T>::type::apply(ab);
+  } else if constexpr (op == FZ_UGRAD) {
+    tos = S[sp - 2] * U<x, T>::g(U<x, T>::needs_x ? S[sp - 1] : T(0), U<x, T>::needs_y ? tos : T(0));
+  } else if constexpr (op == FZ_TERN) {
+    const T t3[3] = {S[sp - 2], S[sp - 1], tos};
+    tos = TernSel<x, T>::type::apply(t3);
+  } else if constexpr (op == FZ_STORE) {
+    if constexpr (ELEM) ((T*)a.out[x])[r + a.m * col] = tos;
+    else { if (writer) ((T*)a.out[x])[col] = tos; }
+  } else if constexpr (op == CP_CRED) {
+    colacc[x] += (double)tos;
+  } else if constexpr (op == CP_CFIN) {
+    tos = (T)colacc[x];
+    colacc[x] = 0.0;
+    colval[x] = tos;
+  } else if constexpr (op == FZ_REDUCE) {
+    if (ELEM || writer) racc += (double)tos;
+  }
+  if constexpr (op == FZ_UNARY || op == FZ_BIN || op == FZ_BIN_IN || op == FZ_BIN_CONST || op == FZ_UGRAD ||
+                op == FZ_TERN)
+    fz_opaque(tos, a.zero);            // every instruction's result is rounded on its own (no FMA contraction)
+}
+
+template <int PROG, int P0, bool ELEM, typename T, int... I>
+__device__ __forceinline__ void cps_seg(const CpArgs& a, int64_t r, int64_t col, bool writer, T (&colval)[CP_COLS],
+                                        double (&colacc)[CP_COLS], double& racc, std::integer_sequence<int, I...>) {
+  T S[FZ_SLOTS], tos = T(0);
+  (cps_step<PROG, P0 + I, ELEM, T>(a, r, col, writer, S, tos, colval, colacc, racc), ...);
+}
+
+// combine over the G lanes the accumulators that the column segment [P0, P0 + len) finishes
+template <int PROG, int P0, int G, int... I>
+__device__ __forceinline__ void cps_combine(double (&colacc)[CP_COLS], std::integer_sequence<int, I...>) {
+  (([&] {
+     constexpr uint32_t w = kColProgs[PROG].code[P0 + I];
+     if constexpr ((w & 0xff) == CP_CFIN) {
+       constexpr int x = (w >> 8) & 0xff;
+       double v = colacc[x];
+#pragma unroll
+       for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+       colacc[x] = v;
+     }
+   }()),
+   ...);
+}
+
+template <int PROG, int PC, typename T, int G>
+__device__ __forceinline__ void cps_all(const CpArgs& a, int lane, int64_t col, bool on, T (&colval)[CP_COLS],
+                                        double (&colacc)[CP_COLS], double& racc) {
+  if constexpr (PC < kColProgs[PROG].n) {
+    constexpr bool elem = ((kColProgs[PROG].code[PC] >> 8) & 0xff) == 0;
+    constexpr int pe = cp_seg_end(kColProgs[PROG], PC + 1);
+    constexpr int len = pe - PC - 1;
+    if constexpr (elem) {
+      if (on)
+        for (int64_t r = lane; r < a.m; r += G)
+          cps_seg<PROG, PC + 1, true, T>(a, r, col, true, colval, colacc, racc, std::make_integer_sequence<int, len>{});
+    } else {
+      if constexpr (G > 1) cps_combine<PROG, PC + 1, G>(colacc, std::make_integer_sequence<int, len>{});
+      if (on)
+        cps_seg<PROG, PC + 1, false, T>(a, 0, col, lane == 0, colval, colacc, racc, std::make_integer_sequence<int, len>{});
+    }
+    cps_all<PROG, pe, T, G>(a, lane, col, on, colval, colacc, racc);
+  }
+}
+
+template <typename T, int G, int PROG>
+__global__ void __launch_bounds__(kThreads) k_colprog_static(const __grid_constant__ CpArgs a) {
+  const int lane = threadIdx.x % G;
+  const int64_t col = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / G;
+  const bool on = col < a.n;
+  T colval[CP_COLS];
+  double colacc[CP_COLS];
+#pragma unroll
+  for (int k = 0; k < CP_COLS; ++k) { colval[k] = T(0); colacc[k] = 0.0; }
+  double racc = 0.0;
+  cps_all<PROG, 0, T, G>(a, lane, col, on, colval, colacc, racc);
+  cp_finish<T>(a, racc);
+}
+
+template <int G>
+static bool launch_col_static(int prog, const CpArgs& a, unsigned nb, cudaStream_t st) {
+  switch (prog) {
+#define X(P) case P: k_colprog_static<float, G, P><<<nb, kThreads, 0, st>>>(a); return true;
+    FZ_COLSTATIC_LIST(X)
+#undef X
+  }
+  return false;
+}
+
+static int find_col_static(const int32_t* code, int ncode) {
+  for (int p = 0; p < FZ_NCOLSTATIC; ++p) {
+    if (kColProgs[p].n != ncode) continue;
+    bool same = true;
+    for (int k = 0; k < ncode && same; ++k) same = kColProgs[p].code[k] == (uint32_t)code[k];
+    if (same) return p;
+  }
+  return -1;
+}
+
+static int32_t* g_cp_ticket = nullptr;
+bool colprog_init() {
+  if (g_cp_ticket) return true;
+  if (cudaMalloc((void**)&g_cp_ticket, sizeof(int32_t)) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("out of device memory allocating the column-program ticket");
+    return false;
+  }
+  cudaMemset(g_cp_ticket, 0, sizeof(int32_t));
+  return true;
+}
+
 static int g_fused_static_enabled = -1;
 static int64_t g_fused_hits = 0, g_fused_misses = 0;   // launches of specialised / interpreted programs
 
@@ -756,4 +1132,120 @@ extern "C" ag_status ag_ewise_fused_reduce(int32_t dtype, const int32_t* code, i
   AG_CHECK(r_out, AG_EINVAL, "ag_ewise_fused_reduce: null result");
   return fused_impl(dtype, code, ncode, consts, nconsts, nin, in, in_mode, in_imm, nout, out, rows, cols, r_inner,
                     r_red, r_outer, r_out);
+}
+
+extern "C" ag_status ag_ewise_colprog(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts,
+                                      int32_t nconsts, int32_t nin, const void* const* in, const int32_t* in_mode,
+                                      const double* in_imm, int32_t nout, void* const* out, int64_t m, int64_t n,
+                                      void* r_out) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_ewise_colprog: dtype %d", dtype);
+  AG_CHECK(code && ncode >= 2 && ncode <= FZ_MAXCODE, AG_EUNSUPPORTED, "ag_ewise_colprog: program length %d (max %d)",
+           ncode, FZ_MAXCODE);
+  AG_CHECK(nconsts >= 0 && nconsts <= FZ_MAXCONST && nin >= 0 && nin <= FZ_DYN_MAXIN && nout >= 0 && nout <= FZ_DYN_MAXOUT,
+           AG_EUNSUPPORTED, "ag_ewise_colprog: %d constants / %d inputs / %d outputs (max %d / %d / %d)", nconsts, nin,
+           nout, FZ_MAXCONST, FZ_DYN_MAXIN, FZ_DYN_MAXOUT);
+  AG_CHECK(m >= 0 && n >= 0, AG_EINVAL, "ag_ewise_colprog: negative extent");
+  AG_CHECK((nin == 0 || (in && in_mode)) && (out || nout == 0) && (nconsts == 0 || consts), AG_EINVAL,
+           "ag_ewise_colprog: null argument table");
+  (void)in_imm;
+  if (m * n == 0) return AG_OK;
+  AG_CHECK(g_cp_ticket, AG_ESTATE, "ag_ewise_colprog: not initialised");
+  CpArgs a;
+  // validate: segment structure, operand indices, stack discipline per segment, every output stored
+  AG_CHECK((code[0] & 0xff) == CP_PHASE, AG_EINVAL, "ag_ewise_colprog: the program must start with a segment marker");
+  int sp = 0, nreduce = 0, elem = 0;
+  uint32_t stored = 0;
+  for (int pc = 0; pc < ncode; ++pc) {
+    const uint32_t w = (uint32_t)code[pc];
+    const int op = w & 0xff, x = (w >> 8) & 0xff, y = (w >> 16) & 0xff;
+    AG_CHECK(op < CP_NOPS && op != FZ_LD_TMP && op != FZ_ST_TMP, AG_EINVAL, "ag_ewise_colprog: bad opcode %d at %d", op, pc);
+    switch (op) {
+      case CP_PHASE: AG_CHECK(x <= 1, AG_EINVAL, "ag_ewise_colprog: bad segment marker"); elem = x == 0; sp = 0; break;
+      case FZ_LD_IN:
+        AG_CHECK(x < nin, AG_EINVAL, "ag_ewise_colprog: input %d of %d", x, nin);
+        AG_CHECK(elem || (in_mode[x] != FZ_M_FULL && in_mode[x] != FZ_M_COLVEC), AG_EINVAL,
+                 "ag_ewise_colprog: a column segment reads an element-space input");
+        break;
+      case FZ_LD_CONST: AG_CHECK(x < nconsts, AG_EINVAL, "ag_ewise_colprog: constant %d of %d", x, nconsts); break;
+      case FZ_UNARY:
+      case FZ_UGRAD: AG_CHECK(x < AG_U_COUNT, AG_EINVAL, "ag_ewise_colprog: unary op %d", x); break;
+      case FZ_BIN: AG_CHECK(x < AG_B_COUNT, AG_EINVAL, "ag_ewise_colprog: binary op %d", x); break;
+      case FZ_BIN_IN:
+        AG_CHECK(x < AG_B_COUNT && (y & 0x7f) < nin, AG_EINVAL, "ag_ewise_colprog: bad BIN_IN at %d", pc);
+        AG_CHECK(elem || (in_mode[y & 0x7f] != FZ_M_FULL && in_mode[y & 0x7f] != FZ_M_COLVEC), AG_EINVAL,
+                 "ag_ewise_colprog: a column segment reads an element-space input");
+        break;
+      case FZ_BIN_CONST: AG_CHECK(x < AG_B_COUNT && (y & 0x7f) < nconsts, AG_EINVAL, "ag_ewise_colprog: bad BIN_CONST at %d", pc); break;
+      case FZ_TERN: AG_CHECK(x < 7, AG_EINVAL, "ag_ewise_colprog: ternary map %d", x); break;
+      case FZ_STORE:
+        AG_CHECK(x < nout && !(stored & (1u << x)), AG_EINVAL, "ag_ewise_colprog: output %d of %d (or stored twice)", x, nout);
+        stored |= 1u << x;
+        break;
+      case FZ_REDUCE: ++nreduce; break;
+      case CP_CRED: AG_CHECK(elem && x < CP_COLS, AG_EINVAL, "ag_ewise_colprog: bad CRED at %d", pc); break;
+      case CP_CFIN:
+      case CP_ST_COL: AG_CHECK(!elem && x < CP_COLS, AG_EINVAL, "ag_ewise_colprog: bad column store at %d", pc); break;
+      case CP_LD_COL: AG_CHECK(x < CP_COLS, AG_EINVAL, "ag_ewise_colprog: column value %d", x); break;
+    }
+    if ((op == FZ_LD_IN || op == FZ_LD_CONST || op == CP_LD_COL) && y) ++sp;
+    if (op == FZ_BIN) sp -= 1;
+    if (op == FZ_UGRAD || op == FZ_TERN) sp -= 2;
+    AG_CHECK(sp >= 0 && sp <= FZ_SLOTS, AG_EINVAL, "ag_ewise_colprog: stack depth %d at %d", sp, pc);
+    a.code[pc] = code[pc];
+  }
+  AG_CHECK(stored == (1u << nout) - 1u, AG_EINVAL, "ag_ewise_colprog: an output is never stored");
+  AG_CHECK(nreduce == (r_out ? 1 : 0), AG_EINVAL, "ag_ewise_colprog: %d REDUCE instructions", nreduce);
+  for (int k = 0; k < nconsts; ++k) a.consts[k] = consts[k];
+  for (int k = 0; k < nout; ++k) {
+    AG_CHECK(out[k], AG_EINVAL, "ag_ewise_colprog: null output %d", k);
+    a.out[k] = out[k];
+  }
+  for (int k = 0; k < nin; ++k) {
+    AG_CHECK(in[k] && (in_mode[k] == FZ_M_FULL || in_mode[k] == FZ_M_DEVSCALAR || in_mode[k] == FZ_M_COLVEC ||
+                       in_mode[k] == FZ_M_ROWVEC), AG_EINVAL, "ag_ewise_colprog: bad input %d", k);
+    a.in[k] = in[k];
+    a.mode[k] = in_mode[k];
+  }
+  a.ncode = ncode;
+  a.nin = nin;
+  a.nout = nout;
+  a.m = m;
+  a.n = n;
+  Context& c = ctx();
+  // G lanes share a column, rows along the lanes: enough lanes for a short column to take one row each (a thread
+  // that walks a whole column serialises one memory latency per row and segment: measured 2x slower at m = 10)
+  const int G = m > 16 ? 32 : (m > 8 ? 16 : 8);
+  const int64_t nblk = cdiv(n * G, (int64_t)kThreads);
+  a.part = nullptr;
+  a.ticket = g_cp_ticket;
+  a.rout = r_out;
+  if (r_out) {
+    a.part = (double*)workspace((size_t)nblk * sizeof(double) + 64);
+    if (!a.part) return AG_ENOMEM;
+  }
+  a.zero = 0;
+  if (g_fused_static_enabled < 0) {
+    const char* e = getenv("AGB_FUSED_STATIC");
+    g_fused_static_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int prog = (dtype == AG_F32 && g_fused_static_enabled) ? find_col_static(code, ncode) : -1;
+  bool done = false;
+  if (prog >= 0)
+    done = G == 8 ? launch_col_static<8>(prog, a, (unsigned)nblk, c.stream)
+                  : (G == 16 ? launch_col_static<16>(prog, a, (unsigned)nblk, c.stream)
+                             : launch_col_static<32>(prog, a, (unsigned)nblk, c.stream));
+  if (done) ++g_fused_hits; else ++g_fused_misses;
+  if (done) {
+  } else if (dtype == AG_F32) {
+    if (G == 8) k_colprog<float, 8><<<(unsigned)nblk, kThreads, 0, c.stream>>>(a);
+    else if (G == 16) k_colprog<float, 16><<<(unsigned)nblk, kThreads, 0, c.stream>>>(a);
+    else k_colprog<float, 32><<<(unsigned)nblk, kThreads, 0, c.stream>>>(a);
+  } else {
+    if (G == 8) k_colprog<double, 8><<<(unsigned)nblk, kThreads, 0, c.stream>>>(a);
+    else if (G == 16) k_colprog<double, 16><<<(unsigned)nblk, kThreads, 0, c.stream>>>(a);
+    else k_colprog<double, 32><<<(unsigned)nblk, kThreads, 0, c.stream>>>(a);
+  }
+  AG_LAUNCHED();
+  return AG_OK;
 }

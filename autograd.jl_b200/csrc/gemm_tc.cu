@@ -194,6 +194,13 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
   const float d = __uint_as_float(x) - __uint_as_float(hi);      // exact in fp32
   lo = (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
 }
+// 32 bytes (one full sector) per lane and instruction: the epilogue threads own rows of 256 contiguous bytes at a
+// 256-byte pitch, so 16-byte stores would write half sectors, two instructions per sector
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 template <int ACT>
 __device__ __forceinline__ float tc_activation(float z) {
   if (ACT == TC_ACT_RELU) return relu(z);     // max.(0, z): same values as the FMax map jmax(0, z) of ewise_ops.cuh
@@ -220,8 +227,29 @@ __device__ __forceinline__ void tc_store_elem(const TcParams& p, int64_t mm, int
 template <int ACT>
 __device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int64_t nn0, const float* v) {
   if (mm >= p.MM) return;
-  if (p.transposed && nn0 + TC_BN <= p.NN && (p.ld_out & 3) == 0) {
-    // this thread owns 64 consecutive elements of one column of C: vector stores; bias is indexed by nn (C's row)
+  if (p.transposed && nn0 + TC_BN <= p.NN && (p.ld_out & 7) == 0 &&
+      ((((uintptr_t)p.out) | ((uintptr_t)p.out2)) & 31) == 0) {
+    // this thread owns 64 consecutive elements of one column of C: 256-bit stores; bias is indexed by nn (C's row)
+    float* dst = p.out + nn0 + p.ld_out * mm;
+    float* dst2 = p.out2 ? p.out2 + nn0 + p.ld_out * mm : nullptr;
+#pragma unroll
+    for (int j = 0; j < TC_BN; j += 8) {
+      float z[8], a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        z[e] = p.alpha == 1.0f ? v[j + e] : __fmul_rn(p.alpha, v[j + e]);
+        if (p.bias) z[e] = __fadd_rn(z[e], __ldg(p.bias + nn0 + j + e));
+        a[e] = tc_activation<ACT>(z[e]);
+      }
+      if (dst2) {
+        st_global_v8(dst + j, z);
+        st_global_v8(dst2 + j, a);
+      } else {
+        st_global_v8(dst + j, a);
+      }
+    }
+  } else if (p.transposed && nn0 + TC_BN <= p.NN && (p.ld_out & 3) == 0) {
+    // the same with 128-bit stores (leading dimension or base not 32-byte aligned)
     float* dst = p.out + nn0 + p.ld_out * mm;
     float* dst2 = p.out2 ? p.out2 + nn0 + p.ld_out * mm : nullptr;
 #pragma unroll
@@ -513,7 +541,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         float* __restrict__ out = p.out + (int64_t)sp * p.split_stride;
         if (p.transposed) {
           float* dst = out + nn0 + p.ld_out * mm;
-          if (nn0 + TC_BN <= p.NN && (p.ld_out & 3) == 0) {
+          if (nn0 + TC_BN <= p.NN && (p.ld_out & 7) == 0 && (((uintptr_t)out) & 31) == 0) {
+#pragma unroll
+            for (int j = 0; j < TC_BN; j += 8) st_global_v8(dst + j, accv + j);
+          } else if (nn0 + TC_BN <= p.NN && (p.ld_out & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < TC_BN; j += 4)
               *reinterpret_cast<float4*>(dst + j) = make_float4(accv[j], accv[j + 1], accv[j + 2], accv[j + 3]);
@@ -616,6 +647,16 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+static int tc_l2promo() {        // experiment knob, read once: AGB_TC_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B (default)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_TC_L2PROMO");
+    v = e ? atoi(e) : 3;
+    if (v < 0 || v > 3) v = 3;
+  }
+  return v;
+}
+
 // 2-d fp32 tensor map: inner (contiguous) extent d0, outer extent d1 with `ld` elements between rows
 static bool make_map(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t ld, int box0, int box1,
                      bool kmajor) {
@@ -628,7 +669,7 @@ static bool make_map(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, i
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  (CUtensorMapL2promotion)tc_l2promo(),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

@@ -84,39 +84,38 @@ __global__ void __launch_bounds__(256)
   hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of `m` counters in place (one block; a running carry over chunks of 1024)
+// exclusive scan of `m` counters in place (one block): every thread sums a contiguous run, one block-wide scan of
+// the 1024 run totals, then every thread rewrites its run
 __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t* __restrict__ hist, int64_t m) {
   __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int64_t base = 0; base < m; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const uint32_t v = i < m ? hist[i] : 0u;
-    uint32_t x = v;
+  const int64_t per = (m + 1023) / 1024;
+  const int64_t lo = min(m, (int64_t)threadIdx.x * per), hi = min(m, lo + per);
+  uint32_t tot = 0;
+  for (int64_t i = lo; i < hi; ++i) tot += hist[i];
+  uint32_t x = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t t = wsum[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+      const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
     }
-    if (lane == 31) wsum[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t t = wsum[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += y;
-      }
-      wsum[lane] = t;                       // inclusive sums of the warps
-    }
-    __syncthreads();
-    const uint32_t before = carry + (w ? wsum[w - 1] : 0u) + x - v;
-    if (i < m) hist[i] = before;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = before + v;
-    __syncthreads();
+    wsum[lane] = t;                       // inclusive sums of the warps
+  }
+  __syncthreads();
+  uint32_t run = (w ? wsum[w - 1] : 0u) + x - tot;
+  for (int64_t i = lo; i < hi; ++i) {
+    const uint32_t v = hist[i];
+    hist[i] = run;
+    run += v;
   }
 }
 
@@ -186,6 +185,37 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// First position of the sorted keys that is not below `key`, found by the whole block: 256 probes per round narrow
+// the range 256-fold (two or three dependent loads instead of the ~17 of a per-thread binary search).  All 256
+// threads of the block call it; all return the same value.
+__device__ __forceinline__ int64_t block_lower_bound(const uint32_t* __restrict__ keys, int64_t n, uint32_t key) {
+  __shared__ int64_t s_lo, s_hi;      // the answer lies in [s_lo, s_hi]
+  if (threadIdx.x == 0) { s_lo = 0; s_hi = n; }
+  __syncthreads();
+  while (s_lo < s_hi) {
+    const int64_t lo = s_lo, hi = s_hi;
+    const int64_t stride = (hi - lo + 255) / 256;
+    const int64_t p = lo + (int64_t)threadIdx.x * stride;
+    const int below = (p < hi && keys[p] < key) ? 1 : 0;
+    const int cnt = __syncthreads_count(below);          // the probes below the key form a prefix (sorted keys)
+    if (threadIdx.x == 0) {
+      if (cnt == 0) {
+        s_hi = lo;                                       // keys[lo] is not below: the answer is lo
+      } else if (stride == 1) {
+        s_lo = s_hi = lo + cnt;                          // every position was probed
+      } else {
+        s_lo = lo + (int64_t)(cnt - 1) * stride + 1;     // behind the last probe below the key ...
+        const int64_t q = lo + (int64_t)cnt * stride;    // ... and not behind the first probe that is not
+        s_hi = q < hi ? q : hi;
+      }
+    }
+    __syncthreads();
+  }
+  const int64_t r = s_lo;
+  __syncthreads();
+  return r;
+}
+
 // ---- segmented reduce over the sorted pairs -----------------------------------------------------------------
 // One CUDA block per (segment, slice of 32*V values of the block): the 8 warps take consecutive eighths of the
 // segment, each sums its run in source order (4 entries in flight), the 8 partial sums are added in warp order and
@@ -202,12 +232,8 @@ __global__ void __launch_bounds__(256)
   uint32_t key;
   if (BYKEY) {
     key = blockIdx.x;
-    int64_t lo = 0, hi = n;
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
-    j = lo;
-    hi = n;
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] <= key) lo = mid + 1; else hi = mid; }
-    e = lo;
+    j = block_lower_bound(keys, n, key);
+    e = block_lower_bound(keys, n, key + 1);
     if (j == e) return;
   } else {
     j = blockIdx.x;
@@ -223,31 +249,37 @@ __global__ void __launch_bounds__(256)
   T acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = T(0);
-  if (b < block) {
-    int64_t m = m0;
-    for (; m + 4 <= m1; m += 4) {
-      T x[4][V];
+  // the positions of the run are fetched 32 at a time (one per lane) and handed round by shuffle, so that the row
+  // loads do not wait on an index load each; 8 rows in flight per lane, added in source order
+  for (int64_t base = m0; base < m1; base += 32) {
+    const int cnt = (int)min((int64_t)32, m1 - base);
+    const int32_t pl = lane < cnt ? pos[base + lane] : 0;
+    for (int u0 = 0; u0 < cnt; u0 += 8) {
+      T x[8][V];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const T* src = vals + (int64_t)pos[m + u] * block + b;
-        if (V == 4 && sizeof(T) == 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(src);
-          x[u][0] = (T)t4.x; x[u][1 % V] = (T)t4.y; x[u][2 % V] = (T)t4.z; x[u][3 % V] = (T)t4.w;
-        } else if (V == 2 && sizeof(T) == 8) {
-          const double2 t2 = *reinterpret_cast<const double2*>(src);
-          x[u][0] = (T)t2.x; x[u][1 % V] = (T)t2.y;
+      for (int u = 0; u < 8; ++u) {
+        const int32_t pu = __shfl_sync(0xffffffffu, pl, (u0 + u) & 31);
+        if (u0 + u < cnt && b < block) {
+          const T* src = vals + (int64_t)pu * block + b;
+          if (V == 4 && sizeof(T) == 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(src));
+            x[u][0] = (T)t4.x; x[u][1 % V] = (T)t4.y; x[u][2 % V] = (T)t4.z; x[u][3 % V] = (T)t4.w;
+          } else if (V == 2 && sizeof(T) == 8) {
+            const double2 t2 = __ldg(reinterpret_cast<const double2*>(src));
+            x[u][0] = (T)t2.x; x[u][1 % V] = (T)t2.y;
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) x[u][v] = __ldg(src + v);
+          }
         } else {
 #pragma unroll
-          for (int v = 0; v < V; ++v) x[u][v] = src[v];
+          for (int v = 0; v < V; ++v) x[u][v] = T(0);
         }
       }
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = (((acc[v] + x[0][v]) + x[1][v]) + x[2][v]) + x[3][v];
-    }
-    for (; m < m1; ++m) {
-      const T* src = vals + (int64_t)pos[m] * block + b;
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] += src[v];
+        for (int v = 0; v < V; ++v) acc[v] += x[u][v];
     }
   }
 #pragma unroll
@@ -372,9 +404,9 @@ static ag_status scatter_add_impl(T* dest, int64_t dest_len, const int64_t* idx,
   int bits = 1;
   while (bits < 32 && ((int64_t)1 << bits) <= nkeys) ++bits;
   const int passes = (bits + kRadixBits - 1) / kRadixBits;
-  // tile: 2048 entries per block, more when that would need more than 4096 blocks (the scan is one block)
+  // tile: 2048 entries per block, more when that would need more than 256 blocks (the scan is one block)
   int64_t tile = 2048;
-  if (cdiv(n, tile) > 4096) tile = cdiv(cdiv(n, (int64_t)4096), (int64_t)256) * 256;
+  if (cdiv(n, tile) > 256) tile = cdiv(cdiv(n, (int64_t)256), (int64_t)256) * 256;
   const int64_t nblk = cdiv(n, tile);
   auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
   const size_t sz_k = al((size_t)n * 4), sz_h = al((size_t)nblk * kRadixBins * 4);

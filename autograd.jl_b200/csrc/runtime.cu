@@ -222,6 +222,7 @@ ag_status ag_init(int32_t device) {
   if (!oob_flag()) return AG_ENOMEM;   // allocate the sticky index-check flag outside of any capture
   g_oob_armed = false;
   if (!reduce_scratch_init()) return AG_ENOMEM;
+  if (!colprog_init()) return AG_ENOMEM;
   if (!gemm_tc_init()) return AG_ENOMEM;
   c.launches = 0;
   c.capturing = false;

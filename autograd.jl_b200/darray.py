@@ -478,6 +478,8 @@ def sum_dims(x, dims, mapname="id"):
         lo, hi = runs[0]
         r = _lazy.reduce(x, _prod(shape[:lo]), _prod(shape[lo:hi + 1]), _prod(shape[hi + 1:]), mapname)
         if r is not None:
+            if _lazy.is_pending(r) and r.shape == tuple(out_shape):
+                return r                  # a column sum that stays inside the chain (lazy.reduce)
             return r.reshape(out_shape)
     cur, cur_shape, m = x, shape, mapname
     for lo, hi in runs:

@@ -40,10 +40,20 @@ BIG = 1 << 20           # elements from which a chain WITHOUT a specialised kern
 MAXCODE, MAXCONST, MAXIN, MAXOUT, SLOTS = 96, 16, 12, 12, 8
 DYN_MAXIN, DYN_MAXOUT = 8, 6     # what the general interpreter takes; larger programs need a specialised kernel
 LD_IN, LD_CONST, LD_TMP, ST_TMP, UNARY, BIN, BIN_IN, BIN_CONST, UGRAD, TERN, STORE, REDUCE = range(12)
+# column programs (ag_ewise_colprog): segments over the elements (rows x cols) and over the columns (1 x cols)
+CP_PHASE, CP_CRED, CP_LD_COL, CP_ST_COL, CP_CFIN = range(12, 17)
+COL_SLOTS = 8           # per-column values a column program can hold
+COL_MAXROWS = 1024      # longest column whose sum stays inside a chain
 M_FULL, M_DEVSCALAR, M_IMM, M_COLVEC, M_ROWVEC = range(5)
 
 enabled = [os.environ.get("AGB_FUSION", "1") != "0"]
 reduce_fusion = [os.environ.get("AGB_FUSE_REDUCE", "1") != "0"]
+# Column sums inside a chain (softmax normaliser and its gradient as ONE ag_ewise_colprog launch).  Off by default:
+# measured on the B200 (round 2) the MNIST step goes from 19 to 16 launches but from 185.6 to 196-201 us, and config 4
+# from 3624 to 3324 launches at the same 14.6 ms -- a column program gives a lane one row of one column (10 of 16
+# lanes busy at m = 10, two dependent memory round trips per warp), where the separate chain kernels stream 128-bit
+# vectors with every load in flight.  AGB_FUSE_COLUMNS=1 (or set_col_fusion(True)) turns it on.
+col_fusion = [os.environ.get("AGB_FUSE_COLUMNS", "0") == "1"]
 static_only = [os.environ.get("AGB_FUSE_BIG_INTERPRETED", "0") == "0"]   # see BIG   # sums of a pending chain in the chain's own launch
 stats = {"fused_launches": 0, "fused_nodes": 0, "fallback_nodes": 0, "splits": 0}
 trace = None            # set to a list to record (n elements, full-array inputs, outputs, program) of every fused launch
@@ -57,6 +67,14 @@ def set_fusion(on):
     if not on:
         flush()
     enabled[0] = bool(on)
+    return prev
+
+
+def set_col_fusion(on):
+    """Enable / disable column programs (see col_fusion); returns the previous setting.  Evaluates what is pending."""
+    prev = col_fusion[0]
+    flush()
+    col_fusion[0] = bool(on)
     return prev
 
 
@@ -145,7 +163,7 @@ def _make(kind, op, args, shape, dtype):
     nn = 1
     for a in args:
         if is_pending(a):
-            if a.shape != shape:
+            if a.shape != shape and not _col_operand(a, shape):
                 force(a)                      # a broadcast operand must be concrete (it becomes a leaf)
             else:
                 nn += a.nnodes
@@ -154,6 +172,13 @@ def _make(kind, op, args, shape, dtype):
         nn -= big.nnodes
         force(big)
     return LazyArray(shape, dtype, kind, op, args, nn)
+
+
+def _col_operand(a, shape):
+    """A pending (1, n) value used by an operation over (m, n): it stays pending, and the whole DAG runs as a column
+    program (ag_ewise_colprog) in which the value is held per column."""
+    return (col_fusion[0] and len(shape) == 2 and a.shape == (1, shape[1]) and 2 <= shape[0] <= COL_MAXROWS
+            and shape[1] >= 2 and shape[0] * shape[1] < BIG and a.kind != "mm")
 
 
 def unary_fwd(op, x):
@@ -197,14 +222,29 @@ def reduce(x, inner, red, outer, mapname):
     flat DArray of inner*outer values, or None when the sum is not fused (the caller reduces the stored array)."""
     if not (enabled[0] and reduce_fusion[0] and is_pending(x)) or red < 2:
         return None
-    f32 = x.dtype == np.float32
-    E, N = (2048, 4) if f32 else (1024, 2)
-    if x.size % N or x.size != inner * red * outer:
+    if col_fusion[0] and inner == 1 and outer >= 2 and red <= COL_MAXROWS and mapname == "id" and x.kind != "mm" \
+            and x.shape == (red, outer) and red * outer < BIG:
+        # sum(x, dims=1) of a pending (m, n) chain, m small: the (1, n) result stays pending so that what follows
+        # (log, the broadcast back over the rows, the gradient of both) runs in the SAME launch as the chain
+        # (examples/mnist.jl:40 `ypred .- log.(sum(exp.(ypred),dims=1))`, src/unbroadcast.jl:17-24)
+        nn = 1 + x.nnodes
+        if nn > MAX_NODES:
+            force(x)
+            if x.kind is None:
+                return None
+        return LazyArray((1, outer), x.dtype, "cr", mapname, (x,), 1 + x.nnodes)
+    if x.kind == "mm" or x.size != inner * red * outer:
         return None
-    if not ((inner == 1 and (outer == 1 or red <= E)) or (outer == 1 and inner * 16 <= E)):
-        return None
-    if x.kind == "mm":
-        return None
+    if col_fusion[0] and _mixed_order(_topo(x)):
+        if not (inner == 1 and outer == 1):
+            return None                     # other layouts: the caller evaluates x (as a column program) and sums it
+    else:
+        f32 = x.dtype == np.float32
+        E, N = (2048, 4) if f32 else (1024, 2)
+        if x.size % N:
+            return None
+        if not ((inner == 1 and (outer == 1 or red <= E)) or (outer == 1 and inner * 16 <= E)):
+            return None
     order = _topo(x)
     while _resolve_products(order, x):
         if x.kind is None:
@@ -212,8 +252,11 @@ def reduce(x, inner, red, outer, mapname):
         order = _topo(x)
     out = D.DArray.empty((inner * outer,), x.dtype)
     try:
-        _run_fused(order, x, (inner, red, outer, mapname, out))
-    except (_TooBig, _NotFusable, UnsupportedOnDevice):
+        if col_fusion[0] and _mixed_order(order):
+            _run_colprog(order, x, (mapname, out))
+        else:
+            _run_fused(order, x, (inner, red, outer, mapname, out))
+    except (_TooBig, _NotFusable, _NotStatic, UnsupportedOnDevice):
         stats["unfused_reductions"] = stats.get("unfused_reductions", 0) + 1
         return None
     return out
@@ -305,6 +348,19 @@ def force(root):
             order = None
             continue                        # some nodes got their storage from a fused product: walk the rest again
         action, ext = None, None
+        if col_fusion[0] and _mixed_order(order):
+            ok = False
+            try:
+                _run_colprog(order, root)
+                ok = True
+            except (_TooBig, _NotFusable, UnsupportedOnDevice):
+                pass
+            if ok:
+                return
+            stats["col_fallbacks"] = stats.get("col_fallbacks", 0) + 1
+            _split_columns(order)           # evaluate a column sum / column operand on its own, then walk again
+            order = None
+            continue
         try:
             _run_fused(order, root)
             return
@@ -341,6 +397,52 @@ def force(root):
             return
         force(sub)
         sub = None
+
+
+def _mixed_order(order):
+    """Does the DAG hold a column sum, or an operation whose pending operand has another shape (column space)?"""
+    for n in order:
+        if n.kind == "cr":
+            return True
+        for a in n.args:
+            if is_pending(a) and a.shape != n.shape:
+                return True
+    return False
+
+
+def _split_columns(order):
+    """Fallback of a DAG that does not fit a column program: its first column sum is evaluated as before (fused into
+    the chain below it when possible, else by ag_sum_dim); without column sums, the pending column-space operands."""
+    for i in range(len(order)):
+        if order[i].kind == "cr":
+            c = order[i]
+            x = c.args[0]
+            red, outer = x.shape
+            out = None
+            if is_pending(x):
+                sub = _topo(x)
+                if not _mixed_order(sub) and not any(n.kind == "mm" for n in sub):
+                    f32 = x.dtype == np.float32
+                    E, N = (2048, 4) if f32 else (1024, 2)
+                    if x.size % N == 0 and red <= E:
+                        out = D.DArray.empty((outer,), x.dtype)
+                        try:
+                            _run_fused(sub, x, (1, red, outer, "id", out))
+                        except (_TooBig, _NotFusable, _NotStatic, UnsupportedOnDevice):
+                            out = None
+                sub = None
+            if out is None:
+                out = D.DArray.empty((outer,), x.dtype)
+                check(D.lib.ag_sum_dim(D.R["id"], D._DT[np.dtype(x.dtype)], C.c_void_p(x.ptr), 1, red, outer,
+                                       C.c_void_p(out.ptr)))
+            c._set_storage(D.DArray(out.buf, out.ptr, c.shape, out.dtype))
+            return
+    for i in range(len(order)):
+        for a in order[i].args:
+            if is_pending(a) and a.shape != order[i].shape:
+                force(a)
+                return
+    raise RuntimeError("lazy: a mixed DAG without column operands")
 
 
 def _pick_split(order, root, ext):
@@ -385,6 +487,10 @@ def _run_eager(order):
             r = D._full_like_shape_eager(n.shape, n.dtype, a[0])
         elif k == "mm":
             r = D._matmul_eager(a[0], a[1], n.op, n.shape, n.dtype)
+        elif k == "cr":
+            r = D.DArray.empty(n.shape, n.dtype)
+            check(D.lib.ag_sum_dim(D.R["id"], D._DT[np.dtype(n.dtype)], C.c_void_p(a[0].ptr), 1, a[0].shape[0], a[0].shape[1],
+                                   C.c_void_p(r.ptr)))
         else:
             r = D._bcast_to_eager(a[0], n.shape)
         stats["fallback_nodes"] += 1
@@ -764,5 +870,179 @@ def _run_fused(order, root, reduce=None):
     stats["fused_nodes"] += len(order)
     if trace is not None:
         trace.append((n_elem, sum(1 for m in modes if m == M_FULL), nout, tuple(code)))
+    for o, arr in zip(outputs, outs):
+        o._set_storage(arr)
+
+
+# ---- column programs ------------------------------------------------------------------------------------------
+
+class _ColCodegen(_Codegen):
+    """Code of one segment of a column program: pending column-space values that have a slot are loaded from it,
+    every other pending node is generated in place (element-space nodes used by several segments are recomputed)."""
+
+    def __init__(self, outputs, ext_ids, cslot):
+        _Codegen.__init__(self, {}, outputs, ext_ids)
+        self.cslot = cslot
+
+    def gen(self, x, push):
+        if is_pending(x):
+            if id(x) in self.cslot:
+                self.emit(CP_LD_COL, self.cslot[id(x)], 1 if push else 0)
+                self.pushed(push)
+            else:
+                self.gen_node(x, push)
+        else:
+            _Codegen.gen(self, x, push)
+
+
+def _run_colprog(order, root, reduce=None):
+    """Evaluate a DAG over an (m, n) element space and its (1, n) column space -- column sums (`cr` nodes, the softmax
+    normaliser and the unbroadcast of its gradient), operations on them, and their broadcast back over the rows -- by
+    ONE launch of ag_ewise_colprog.  The program is a sequence of segments: a column segment runs once per column, an
+    element segment for every row of the column; a column sum is accumulated (CP_CRED) by the element segment that
+    computes its operand and finished (CP_CFIN) by the next column segment.  reduce = (map, out): additionally the sum
+    over everything of map(root) goes to `out`."""
+    dtype = root.dtype
+    SE = None
+    for n in order:
+        if n.kind == "cr":
+            SE = n.args[0].shape
+            break
+        for a in n.args:
+            if is_pending(a) and a.shape != n.shape:
+                SE = n.shape
+                break
+        if SE is not None:
+            break
+    n = a = None
+    if SE is None or len(SE) != 2 or SE[0] < 2 or SE[1] < 2:
+        raise _NotFusable()
+    m, ncols = SE
+    SC = (1, ncols)
+    for n in order:
+        if n.shape != SE and n.shape != SC:
+            raise _NotFusable()
+        if n.kind == "cr" and (n.args[0].shape != SE or n.shape != SC):
+            raise _NotFusable()
+        if n.kind == "mm":
+            raise _NotFusable()
+    n = None
+    uses = {}
+    for n in order:
+        for a in n.args:
+            if is_pending(a):
+                uses[id(a)] = uses.get(id(a), 0) + 1
+    n = a = None
+    ext = []
+    for idx in range(len(order)):
+        u = uses.get(id(order[idx]), 0)
+        ext.append(order[idx] is root or _external(order[idx], u) > 0)
+    outputs = [order[i] for i in range(len(order)) if ext[i]]
+    ext_ids = {id(o) for o in outputs}
+    if len(outputs) > MAXOUT:
+        raise _TooBig("outputs", ext_ids)
+    # levels: a column sum lives one level above its operand
+    lev, used_by_e, feeds = {}, set(), {}
+    for n in order:
+        lv = 0
+        for a in n.args:
+            if is_pending(a):
+                lv = max(lv, lev[id(a)])
+                if a.shape == SC and n.shape == SE:
+                    used_by_e.add(id(a))
+        if n.kind == "cr":
+            lv += 1
+            feeds.setdefault(id(n.args[0]), []).append(n)
+        lev[id(n)] = lv
+    n = a = None
+    cslot = {}
+    for i in range(len(order)):
+        n = order[i]
+        if n.shape == SC and (n.kind == "cr" or ext[i] or id(n) in used_by_e or uses.get(id(n), 0) > 1):
+            if len(cslot) >= COL_SLOTS:
+                raise _TooBig("colslots", ext_ids)
+            cslot[id(n)] = len(cslot)
+    n = None
+    cg = _ColCodegen(outputs, ext_ids, cslot)
+    rmap = None if reduce is None else reduce[0]
+    for lv in range(max(lev.values()) + 1):
+        start = len(cg.code)
+        cg.emit(CP_PHASE, 1)
+        for i in range(len(order)):
+            n = order[i]
+            if n.shape != SC or lev[id(n)] != lv or id(n) not in cslot:
+                continue
+            cg.depth = 0
+            if n.kind == "cr":
+                cg.emit(CP_CFIN, cslot[id(n)])
+            else:
+                cg.gen_node(n, False)
+                cg.emit(CP_ST_COL, cslot[id(n)])
+            if ext[i]:
+                cg.emit(STORE, outputs.index(n))
+            if n is root and reduce is not None:
+                if rmap != "id":
+                    cg.emit(UNARY, D.U[rmap])
+                cg.emit(REDUCE)
+        if len(cg.code) == start + 1:
+            cg.code.pop()
+        start = len(cg.code)
+        cg.emit(CP_PHASE, 0)
+        for i in range(len(order)):
+            n = order[i]
+            if n.shape != SE or lev[id(n)] != lv:
+                continue
+            is_root = n is root and reduce is not None
+            if not (ext[i] or id(n) in feeds or is_root):
+                continue
+            cg.depth = 0
+            cg.gen_node(n, False)
+            if ext[i]:
+                cg.emit(STORE, outputs.index(n))
+            for c in feeds.get(id(n), ()):
+                cg.emit(CP_CRED, cslot[id(c)])
+            if is_root:
+                if rmap != "id":
+                    cg.emit(UNARY, D.U[rmap])
+                cg.emit(REDUCE)
+        if len(cg.code) == start + 1:
+            cg.code.pop()
+    n = c = None
+    code, consts, leaves = cg.code, cg.consts, cg.leaves
+    maxdepth = cg.maxdepth
+    cg = None
+    if len(code) > MAXCODE or maxdepth > SLOTS:
+        raise _TooBig("code" if len(code) > MAXCODE else "slots", ext_ids)
+    if len(leaves) > DYN_MAXIN or len(outputs) > DYN_MAXOUT:
+        raise _TooBig("inputs" if len(leaves) > DYN_MAXIN else "outputs", ext_ids)
+    modes = []
+    for x in leaves:
+        if x.shape == SE:
+            modes.append(M_FULL)
+        elif x.size == 1:
+            modes.append(M_DEVSCALAR)
+        elif x.shape == SC:
+            modes.append(M_ROWVEC)
+        elif x.shape in ((m, 1), (m,)):
+            modes.append(M_COLVEC)
+        else:
+            raise _NotFusable()
+    outs = [D.DArray.empty(o.shape, dtype) for o in outputs]
+    nin, nout = len(leaves), len(outs)
+    c_code = (C.c_int32 * len(code))(*code)
+    c_consts = (C.c_double * max(len(consts), 1))(*(consts or [0.0]))
+    c_in = (C.c_void_p * max(nin, 1))(*[x.ptr for x in leaves])
+    c_mode = (C.c_int32 * max(nin, 1))(*modes)
+    c_imm = (C.c_double * max(nin, 1))()
+    c_out = (C.c_void_p * max(nout, 1))(*[o.ptr for o in outs])
+    check(D.lib.ag_ewise_colprog(D._DT[dtype], c_code, len(code), c_consts, len(consts), nin, c_in, c_mode, c_imm,
+                                 nout, c_out, m, ncols, C.c_void_p(reduce[1].ptr) if reduce is not None else None))
+    stats["col_launches"] = stats.get("col_launches", 0) + 1
+    stats["fused_launches"] += 1
+    stats["fused_nodes"] += len(order)
+    if reduce is not None:
+        stats["fused_reductions"] = stats.get("fused_reductions", 0) + 1
+    if trace is not None:
+        trace.append((m * ncols, sum(1 for md in modes if md == M_FULL), nout, tuple(code)))
     for o, arr in zip(outputs, outs):
         o._set_storage(arr)

@@ -247,6 +247,26 @@ ag_status ag_ewise_fused_reduce(int32_t dtype, const int32_t* code, int32_t ncod
                                 const double* in_imm, int32_t nout, void* const* out, int64_t rows, int64_t cols,
                                 int64_t r_inner, int64_t r_red, int64_t r_outer, void* r_out);
 
+/* A chain that sums over the rows of an m x n (column-major) matrix and USES the sums again, as ONE launch: the
+ * softmax normaliser `ypred .- log.(sum(exp.(ypred),dims=1))` of the reference's models (examples/mnist.jl:40,
+ * examples/charlm.jl:107-110, examples/rnn_lonely_integer.jl:52-55) and the unbroadcast of its gradient
+ * (src/unbroadcast.jl:17-24), which the reference runs as one broadcast / reduction pass per node.
+ * The program uses the instruction words of ag_ewise_fused (without the temporary-slot instructions 2 and 3) in
+ * SEGMENTS introduced by instruction 12 PHASE: a = 0, an element segment, runs for every row of every column;
+ * a = 1, a column segment, runs once per column.  Further instructions: 13 CRED a (element segment: column accumulator
+ * a += top, in double), 16 CFIN a (column segment: column value a = top = the rounded accumulator a, which is cleared),
+ * 15 ST_COL a (column value a = top), 14 LD_COL a (top = column value a; b = 1 pushes first; either kind of segment;
+ * a < 8).  STORE writes an m x n output from an element segment and a 1 x n output from a column segment.  Inputs:
+ * in_mode 0 = m x n array, 3 = m values (one per row), 4 = n values (one per column; the only array kind a column
+ * segment may read), 1 = device scalar.  r_out != NULL: the program holds one instruction 11 REDUCE and the sum of
+ * its operand over the whole segment space goes to r_out (one value; deterministic: per-block partials in double,
+ * added in block order by the last block to finish).  Every instruction evaluates the expression of the single
+ * kernels; a column sum is taken in double: every lane of the column's 8, 16 or 32 lanes adds its rows in order, the lanes
+ * combine pairwise. */
+ag_status ag_ewise_colprog(int32_t dtype, const int32_t* code, int32_t ncode, const double* consts, int32_t nconsts,
+                           int32_t nin, const void* const* in, const int32_t* in_mode, const double* in_imm,
+                           int32_t nout, void* const* out, int64_t m, int64_t n, void* r_out);
+
 /* Programs that the BASELINE configs produce are also instantiated ahead of time (csrc/fuse_static.inc, generated
  * by tools/gen_fused_programs.py) and picked by an exact match of `code`; on = 0 forces the general interpreter
  * kernel for every program (default 1, or environment AGB_FUSED_STATIC=0).  Results are identical either way. */

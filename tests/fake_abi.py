@@ -269,6 +269,82 @@ class FakeLib:
         _arr(r_out, r_inner * r_outer, T)[:] = v.astype(np.float64).sum(axis=1).astype(T).reshape(-1, order="F")
         return 0
 
+    def ag_ewise_colprog(self, dtype, code, ncode, consts, nconsts, nin, ins, modes, imms, nout, outs, m, n, r_out):
+        """Column programs of include/agb200.h `ag_ewise_colprog`: numpy broadcasting evaluates an element segment for
+        the whole m x n space and a column segment for the 1 x n space at once."""
+        self.launches += 1
+        T = _DT[dtype]
+        vals = []
+        for k in range(nin):
+            md = int(modes[k])
+            if md == 0: v = _arr(ins[k], m * n, T).reshape((m, n), order="F")
+            elif md == 1: v = _arr(ins[k], 1, T)[0]
+            elif md == 3: v = _arr(ins[k], m, T).reshape((m, 1))
+            elif md == 4: v = _arr(ins[k], n, T).reshape((1, n))
+            else: return self._fail(1, "ag_ewise_colprog: bad input mode")
+            vals.append(v)
+        binf = dict(_B)
+        tern = {0: lambda dy, p, q: -dy * p / (q * q), 1: lambda dy, p, q: dy * (p == q),
+                2: lambda dy, p, q: dy * q * np.power(p, q - 1), 3: lambda dy, p, q: dy * p * np.log(q),
+                4: lambda dy, p, q: dy * q / (p * p + q * q), 5: lambda dy, p, q: dy * (-p) / (p * p + q * q),
+                6: lambda dy, p, q: dy * p / q}
+        S, tos, sp = [None] * 8, None, 0
+        colval, colacc = [None] * 8, [None] * 8
+        as_t = lambda v: np.asarray(v).astype(T)
+        elem, total = True, None
+        if int(code[0]) & 0xff != 12:
+            return self._fail(1, "ag_ewise_colprog: the program must start with a segment marker")
+        with np.errstate(all="ignore"):
+            for pc in range(ncode):
+                w = int(code[pc])
+                op, x, y = w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff
+                shape = (m, n) if elem else (1, n)
+                if op == 12:
+                    elem, sp, tos = (x == 0), 0, None
+                elif op in (0, 1, 14):
+                    if y:
+                        S[sp] = tos
+                        sp += 1
+                    tos = vals[x] if op == 0 else (T(consts[x]) if op == 1 else colval[x])
+                    if op == 0 and not elem and int(modes[x]) in (0, 3):
+                        return self._fail(1, "ag_ewise_colprog: a column segment reads an element-space input")
+                elif op == 15: colval[x] = as_t(tos)
+                elif op == 4: tos = as_t(_U[x][0](as_t(tos)))
+                elif op == 5:
+                    sp -= 1
+                    tos = as_t(binf[x](S[sp], tos))
+                elif op in (6, 7):
+                    o = vals[y & 0x7f] if op == 6 else T(consts[y & 0x7f])
+                    tos = as_t(binf[x](o, tos)) if y & 0x80 else as_t(binf[x](tos, o))
+                elif op == 8:
+                    sp -= 2
+                    gx, gdy = as_t(S[sp + 1]), S[sp]
+                    tos = as_t(gdy * as_t(_U[x][1](gx, as_t(tos))))
+                elif op == 9:
+                    sp -= 2
+                    tos = as_t(tern[x](S[sp], S[sp + 1], tos))
+                elif op == 10:
+                    _arr(outs[x], shape[0] * shape[1], T)[:] = np.broadcast_to(as_t(tos), shape).reshape(-1, order="F")
+                elif op == 13:
+                    if not elem:
+                        return self._fail(1, "ag_ewise_colprog: CRED in a column segment")
+                    part = np.broadcast_to(as_t(tos), (m, n)).astype(np.float64).sum(axis=0).reshape((1, n))
+                    colacc[x] = part if colacc[x] is None else colacc[x] + part
+                elif op == 16:
+                    if elem:
+                        return self._fail(1, "ag_ewise_colprog: CFIN in an element segment")
+                    tos = colval[x] = (np.zeros((1, n)) if colacc[x] is None else colacc[x]).astype(T)
+                    colacc[x] = None
+                elif op == 11:
+                    total = np.broadcast_to(as_t(tos), shape).astype(np.float64).sum()
+                else:
+                    return self._fail(1, "ag_ewise_colprog: bad opcode %d" % op)
+        if bool(r_out is not None and _p(r_out)) != (total is not None):
+            return self._fail(1, "ag_ewise_colprog: REDUCE and r_out do not agree")
+        if total is not None:
+            _arr(r_out, 1, T)[0] = T(total)
+        return 0
+
     def _fused(self, dtype, code, ncode, consts, nin, ins, modes, imms, outs, rows, cols):
         self.launches += 1
         T = _DT[dtype]

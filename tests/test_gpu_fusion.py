@@ -358,3 +358,30 @@ def test_fused_sum_is_deterministic(ag, LR):
         outs.append((float(ag.sum_(y)), ag.sum_(D.unary_fwd("exp", D.binary_fwd("mul", x, 0.1)), dims=1).to_numpy()))
     assert outs[0][0] == outs[1][0] == outs[2][0]
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], outs[2][1])
+
+
+@pytest.mark.parametrize("cfg", ["mnist", "rnn", "lstm"])
+def test_column_programs_on_the_device(ag, L, cfg):
+    """Column fusion on (ag_ewise_colprog: softmax normaliser, what follows it and the unbroadcast of its gradient in one
+    launch each): the whole step agrees with the default path to rounding of the sums (double accumulation on both
+    sides), needs fewer launches, and the specialised and the interpreted column kernels give the same bits."""
+    W = ag.workloads
+    r0, n0 = _step_all(ag, W, cfg, True, L)
+    prev = L.set_col_fusion(True)
+    try:
+        c0 = L.stats.get("col_launches", 0)
+        r1, n1 = _step_all(ag, W, cfg, True, L)
+        assert L.stats.get("col_launches", 0) > c0
+        try:
+            L.set_static(False)
+            r2, _ = _step_all(ag, W, cfg, True, L)
+        finally:
+            L.set_static(True)
+    finally:
+        L.set_col_fusion(prev)
+    for a, b in zip(r0, r1):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        assert np.max(np.abs(a - b)) <= 1e-5 * max(np.max(np.abs(a)), 1e-30)
+    for a, b in zip(r1, r2):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    assert n1 < n0, (cfg, n1, n0)

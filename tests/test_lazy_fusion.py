@@ -358,3 +358,46 @@ def test_slab_copy_into_an_existing_array_flushes_pending_reads(lz):
     D.slab_copy(src, 8, 0, W, 8, 0, 1, 8, 1)
     assert np.array_equal(y.to_numpy(), np.full((4, 2), 2.0, np.float32))
     assert np.array_equal(W.to_numpy(), np.full((4, 2), 7.0, np.float32))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_column_programs_equal_separate_launches(hostlib, dtype):
+    """With column fusion on (lazy.set_col_fusion) the softmax normaliser, what follows it and the unbroadcast of its
+    gradient run as ag_ewise_colprog launches: same values (sums in double either way), fewer launches."""
+    import sys
+    ag, W = hostlib, hostlib.workloads
+    L = sys.modules["agb200.lazy"]
+    v0, g0, a0, n0 = run_step(ag, W, "mnist", dtype, True)
+    prev = L.set_col_fusion(True)
+    try:
+        c0 = L.stats.get("col_launches", 0)
+        v1, g1, a1, n1 = run_step(ag, W, "mnist", dtype, True)
+        assert L.stats.get("col_launches", 0) > c0
+        assert L.stats.get("col_fallbacks", 0) == 0
+    finally:
+        L.set_col_fusion(prev)
+    tol = 2e-6 if dtype == np.float32 else 1e-14
+    assert abs(v0 - v1) <= tol * abs(v0)
+    for x, y in zip(g0 + a0, g1 + a1):
+        assert np.max(np.abs(x - y)) <= tol * max(np.max(np.abs(x)), 1e-30)
+    assert n1 < n0
+
+
+def test_column_program_fallback_when_it_does_not_fit(lz):
+    """A DAG with more column values than a column program holds is evaluated piecewise (column sums on their own)."""
+    ag, L, _ = lz
+    prev = L.set_col_fusion(True)
+    try:
+        rng = np.random.default_rng(3)
+        x = dev(ag, rng.standard_normal((6, 9)))
+        acc = None
+        for k in range(10):                           # ten column sums feeding one element-space expression
+            s = ag.sum_(ag.mul(ag.exp(ag.mul(x, 0.1 * (k + 1))), 1.0), dims=0)
+            t = ag.sub(x, s)
+            acc = t if acc is None else ag.add(acc, t)
+        got = acc.to_numpy()
+        xn = x.to_numpy()
+        ref = sum(xn - np.exp(xn * (0.1 * (k + 1))).sum(axis=0, keepdims=True) for k in range(10))
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)
+    finally:
+        L.set_col_fusion(prev)

@@ -24,12 +24,14 @@ import __graft_entry__ as ge  # noqa: E402
 import fake_abi  # noqa: E402
 
 OUT = os.path.join(ROOT, "autograd.jl_b200", "csrc", "fuse_static.inc")
+OUT_COL = os.path.join(ROOT, "autograd.jl_b200", "csrc", "fuse_static_col.inc")
 MAX_STATIC = 160
+MAX_COL_STATIC = 48
 
 
 def main(out=OUT):
     ag = ge.load_package()
-    progs = {}
+    progs, colprogs = {}, {}
 
     class Recorder(fake_abi.FakeLib):
         def ag_ewise_fused(self, dtype, code, ncode, consts, nconsts, nin, *rest):
@@ -56,6 +58,14 @@ def main(out=OUT):
                     ent["count"] += 1
                     ent["where"].add(CUR[0])
             return st
+
+        def ag_ewise_colprog(self, dtype, code, ncode, consts, nconsts, nin, *rest):
+            key = tuple(int(code[k]) & 0xffffffff for k in range(ncode))
+            ent = colprogs.setdefault(key, {"nin": nin, "count": 0, "where": set(), "f32": False})
+            ent["count"] += 1
+            ent["where"].add(CUR[0])
+            ent["f32"] = ent["f32"] or dtype == 0
+            return super().ag_ewise_colprog(dtype, code, ncode, consts, nconsts, nin, *rest)
 
         # Which products take their `.+ b` / activation into the epilogue depends on sizes (the tcgen05 engine takes
         # them); both outcomes are recorded: EPI[0] = None -> the stand-in's size rule, 0 / 1 -> never / always.
@@ -104,9 +114,14 @@ def main(out=OUT):
         ag.sync()
 
     try:
-        for gc, epi in ((None, None), (ag.release_node, None), (ag.release_node, 1), (None, 1)):
+        # (gc function, epilogue rule, column programs): column sums stay inside a chain only for small arrays
+        # (lazy.BIG), so the chains of both forms occur
+        for gc, epi, colf in ((None, None, True), (ag.release_node, None, True), (ag.release_node, 1, True), (None, 1, True),
+                              (None, None, False), (ag.release_node, None, False), (ag.release_node, 1, False)):
             ag.set_gc_function(gc if gc is not None else (lambda n, t: None))
             EPI[0] = epi
+            L.flush()
+            L.col_fusion[0] = colf
             for dtype in ((np.float64, np.float32) if epi is None else (np.float32,)):
                 CUR[0] = "housing"
                 w, x, y = W.housing_init(rng, 24, 5, dtype)
@@ -194,6 +209,7 @@ def main(out=OUT):
     finally:
         ag.set_gc_function(lambda n, t: None)
         L.flush()
+        L.col_fusion[0] = False
         L.set_fusion(prev)
         restore()
 
@@ -211,15 +227,31 @@ def main(out=OUT):
         lines.append("  {0, 0, {0}},")
     lines.append("};")
     text = "\n".join(lines) + "\n"
+    citems = sorted(((k, v) for k, v in colprogs.items() if v["f32"]), key=lambda kv: (-kv[1]["count"], kv[0]))[:MAX_COL_STATIC]
+    lines = ["// fuse_static_col.inc -- GENERATED by tools/gen_fused_programs.py; do not edit.",
+             "// The column programs (ag_ewise_colprog) of the BASELINE.json configs, instantiated ahead of time for Float32.",
+             "#define FZ_NCOLSTATIC %d" % len(citems),
+             "#define FZ_COLSTATIC_LIST(X) " + " ".join("X(%d)" % i for i in range(len(citems))),
+             "constexpr StaticColProg kColProgs[%d] = {" % max(len(citems), 1)]
+    for i, (code, ent) in enumerate(citems):
+        lines.append("  /* %2d: %s */ {%d, {%s}}," % (i, ",".join(sorted(ent["where"])), len(code),
+                                                    ", ".join("0x%xu" % c for c in code)))
+    if not citems:
+        lines.append("  {0, {0}},")
+    lines.append("};")
+    ctext = "\n".join(lines) + "\n"
     if out is not None:
         with open(out, "w") as f:
             f.write(text)
-        print("wrote %d programs (of %d distinct) to %s" % (len(items), len(progs), out))
-    return text
+        with open(OUT_COL, "w") as f:
+            f.write(ctext)
+        print("wrote %d programs (of %d distinct) to %s; %d column programs (of %d) to %s"
+              % (len(items), len(progs), out, len(citems), len(colprogs), OUT_COL))
+    return text + ctext
 
 
 if __name__ == "__main__":
     if "--check" in sys.argv[1:]:           # exit 1 when the committed list is stale
-        with open(OUT) as f:
-            sys.exit(0 if f.read() == main(out=None) else 1)
+        with open(OUT) as f, open(OUT_COL) as fc:
+            sys.exit(0 if f.read() + fc.read() == main(out=None) else 1)
     main()
