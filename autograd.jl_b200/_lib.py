@@ -91,6 +91,7 @@ _SIGS = {
     "ag_gather_cols": [i32, vp, i64, vp, vp, i64],
     "ag_scatter_add": [i32, vp, i64, vp, vp, i64, i64],
     "ag_slab_copy": [i32, vp, i64, i64, vp, i64, i64, i64, i64, i64],
+    "ag_cat": [i32, i32, C.POINTER(vp), pi64, vp, i64, i64],
     "ag_transpose": [i32, vp, i64, i64, vp],
     "ag_comm_unique_id": [C.POINTER(C.c_uint8)],
     "ag_comm_init": [i32, i32, C.POINTER(C.c_uint8)],

@@ -66,6 +66,10 @@ struct FzArgs {
   int32_t tps;    // mode 2: threads that share one run (power of two)
   int64_t rlen;
   void* rout;
+  // in-kernel finish of the block partials (modes 1 and 3): groups of FZ_FIN_GROUP blocks, two levels of tickets
+  int32_t* tickets;   // [0] = groups finished, [1 + g] = blocks of group g finished; null: a combine launch follows
+  double* lvl2;       // one set of rlen (mode 3) / 1 (mode 1) sums per group
+  void* rfinal;       // the result (rlen or 1 values of T)
 };
 
 #define FZ_CASE8(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
@@ -417,6 +421,52 @@ constexpr bool fz_has_reduce(const StaticProg& p) {
   return false;
 }
 
+constexpr int FZ_FIN_GROUP = 32, FZ_FIN_MAXGROUPS = 4096;
+
+// The block partials of a fused sum (one double, or R row sums, per block) can be finished inside the kernel: the last
+// block of every group of FZ_FIN_GROUP blocks adds the group's partials in block order, the last group to finish adds
+// the group sums in group order -- fixed order, so the result does not depend on the schedule, and no second launch.
+// OFF by default (AGB_FUSED_FINISH=1 turns it on): measured on the B200 the fence + ticket of every block cost more
+// than the combine launch they save inside a CUDA graph (MNIST step 19 -> 16 launches but 183 -> 193 us; the relu
+// gradient with its row sums 20.3 -> 24.2 us; sweep 2^28 elements 2.13 -> 2.34 ms).
+template <typename T>
+__device__ __forceinline__ void fz_finish_partials(const FzArgs& a, int R) {
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int nblk = gridDim.x, g = blockIdx.x / FZ_FIN_GROUP, ngroups = (nblk + FZ_FIN_GROUP - 1) / FZ_FIN_GROUP;
+  const int b0 = g * FZ_FIN_GROUP, b1 = min(nblk, b0 + FZ_FIN_GROUP);
+  const double* __restrict__ part = (const double*)a.rout;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&a.tickets[1 + g], 1) == (b1 - b0) - 1;
+  __syncthreads();
+  if (!s_last) return;
+  for (int r = tid; r < R; r += kThreads) {
+    double s = 0;
+    for (int b = b0; b < b1; ++b) s += __ldcg(part + (int64_t)b * R + r);
+    a.lvl2[(int64_t)g * R + r] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    a.tickets[1 + g] = 0;
+    s_last = atomicAdd(&a.tickets[0], 1) == ngroups - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  for (int r = tid; r < R; r += kThreads) {
+    double s0 = 0, s1 = 0;
+    int q = 0;
+    for (; q + 1 < ngroups; q += 2) {
+      s0 += __ldcg(a.lvl2 + (int64_t)q * R + r);
+      s1 += __ldcg(a.lvl2 + (int64_t)(q + 1) * R + r);
+    }
+    if (q < ngroups) s0 += __ldcg(a.lvl2 + (int64_t)q * R + r);
+    ((T*)a.rfinal)[r] = (T)(s0 + s1);
+  }
+  if (tid == 0) a.tickets[0] = 0;
+}
+
 // Sum epilogue of a specialised kernel: `red` holds the block's chunk of the FZ_REDUCE operand (zeros beyond the
 // data), `acc` this thread's own sum.  Fixed summation order throughout (deterministic), accumulation in double.
 template <typename T, int E>
@@ -434,6 +484,7 @@ __device__ __forceinline__ void fz_reduce_epilogue(const FzArgs& a, const T* red
       for (int w = 0; w < kThreads / 32; ++w) r += part[w];
       ((double*)a.rout)[blockIdx.x] = r;
     }
+    if (a.tickets) fz_finish_partials<T>(a, 1);
   } else if (a.rmode == 2) {
     const int rlen = (int)a.rlen, nrun = a.chunk / rlen, tps = a.tps;
     const int g = tid / tps, q = tid - g * tps;
@@ -455,6 +506,7 @@ __device__ __forceinline__ void fz_reduce_epilogue(const FzArgs& a, const T* red
       for (int c = 0; c < ncol; ++c) s += (double)red[r + R * c];
       ((double*)a.rout)[(int64_t)blockIdx.x * R + r] = s;
     }
+    if (a.tickets) fz_finish_partials<T>(a, R);
   }
 }
 
@@ -913,8 +965,20 @@ static int find_col_static(const int32_t* code, int ncode) {
   return -1;
 }
 
+static int32_t* g_fz_tickets = nullptr;    // 1 + FZ_FIN_MAXGROUPS tickets, zero between launches (self-resetting)
+static int g_fused_finish = 0;             // AGB_FUSED_FINISH=1: finish the partials in the kernel (measured slower)
 static int32_t* g_cp_ticket = nullptr;
 bool colprog_init() {
+  if (!g_fz_tickets) {
+    if (cudaMalloc((void**)&g_fz_tickets, (1 + FZ_FIN_MAXGROUPS) * sizeof(int32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("out of device memory allocating the fused-sum tickets");
+      return false;
+    }
+    cudaMemset(g_fz_tickets, 0, (1 + FZ_FIN_MAXGROUPS) * sizeof(int32_t));
+    const char* e = getenv("AGB_FUSED_FINISH");
+    g_fused_finish = (e && e[0] == '1') ? 1 : 0;
+  }
   if (g_cp_ticket) return true;
   if (cudaMalloc((void**)&g_cp_ticket, sizeof(int32_t)) != cudaSuccess) {
     cudaGetLastError();
@@ -1087,10 +1151,21 @@ static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, c
   }
   const int64_t nblk = cdiv(n, (int64_t)a.chunk);
   double* part = nullptr;
+  a.tickets = nullptr;
+  a.lvl2 = nullptr;
+  a.rfinal = nullptr;
+  bool finish_in_kernel = false;
   if (a.rmode == 1 || a.rmode == 3) {
-    part = (double*)workspace(((size_t)nblk * (size_t)a.rlen + 64) * sizeof(double));
+    const int64_t ngroups = cdiv(nblk, (int64_t)FZ_FIN_GROUP);
+    finish_in_kernel = g_fz_tickets && ngroups <= FZ_FIN_MAXGROUPS && g_fused_finish != 0;
+    part = (double*)workspace(((size_t)(nblk + ngroups) * (size_t)a.rlen + 64) * sizeof(double));
     if (!part) return AG_ENOMEM;
     a.rout = part;
+    if (finish_in_kernel) {
+      a.tickets = g_fz_tickets;
+      a.lvl2 = part + (size_t)nblk * (size_t)a.rlen;
+      a.rfinal = r_out;
+    }
   } else if (a.rmode == 2) {
     a.rout = r_out;
   }
@@ -1112,7 +1187,7 @@ static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, c
     }
   }
   AG_LAUNCHED();
-  if (part) return reduce_double_partials(dtype, part, nblk, a.rmode == 1 ? 1 : a.rlen, r_out);
+  if (part && !finish_in_kernel) return reduce_double_partials(dtype, part, nblk, a.rmode == 1 ? 1 : a.rlen, r_out);
   return AG_OK;
 }
 

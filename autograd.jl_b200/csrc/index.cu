@@ -322,6 +322,32 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<const uint4*>(src + o * inner * src_red + src_off * inner + w);
 }
 
+// cat(xs...; dims) in ONE launch (src/cat.jl:27-31): dst viewed as inner x tot x outer, source j as inner x len[j] x
+// outer; a thread owns one 16-byte piece (V elements) of the destination and finds its source by the running offsets.
+constexpr int kCatMax = 8;
+struct CatArgs {
+  const void* src[kCatMax];
+  int64_t len[kCatMax];      // extent of source j along the concatenated dimension
+  int64_t off[kCatMax + 1];  // running offsets along that dimension; off[n] = tot
+  int n;
+  int64_t inner, outer;
+};
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_cat(const __grid_constant__ CatArgs a, T* __restrict__ dst, int64_t total_vec) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int64_t e = i * V, slab = a.inner * a.off[a.n];
+  const int64_t o = e / slab, w = e - o * slab;
+  const int64_t r = w / a.inner;
+  int j = 0;
+#pragma unroll
+  for (int q = 1; q < kCatMax; ++q)
+    if (q < a.n && r >= a.off[q]) j = q;
+  const T* __restrict__ s = (const T*)a.src[j] + o * a.inner * a.len[j] + (w - a.off[j] * a.inner);
+  if (V == 1) dst[e] = s[0];
+  else *reinterpret_cast<uint4*>(dst + e) = *reinterpret_cast<const uint4*>(s);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_transpose(const T* __restrict__ x, int64_t rows, int64_t cols, T* __restrict__ out) {
@@ -555,6 +581,45 @@ ag_status ag_slab_copy(int32_t dtype, const void* src, int64_t src_red, int64_t 
   else if (dtype == AG_F64)
     k_slab_copy<double><<<nb, 256, 0, c.stream>>>((const double*)src, src_red, src_off, (double*)dst, dst_red, dst_off, inner, len, total);
   else { set_error("ag_slab_copy: dtype %d", dtype); return AG_EUNSUPPORTED; }
+  AG_LAUNCHED();
+  return AG_OK;
+}
+
+ag_status ag_cat(int32_t dtype, int32_t n, const void* const* src, const int64_t* len, void* dst, int64_t inner,
+                 int64_t outer) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_cat: dtype %d", dtype);
+  AG_CHECK(n >= 1 && n <= kCatMax && src && len && inner >= 0 && outer >= 0, AG_EINVAL, "ag_cat: bad arguments (n = %d, max %d)",
+           n, kCatMax);
+  CatArgs a;
+  a.n = n;
+  a.inner = inner;
+  a.outer = outer;
+  int64_t tot = 0;
+  const int N = dtype == AG_F32 ? 4 : 2;
+  bool vec = aligned16(dst);
+  for (int j = 0; j < n; ++j) {
+    AG_CHECK(len[j] >= 0 && (len[j] == 0 || src[j]), AG_EINVAL, "ag_cat: bad source %d", j);
+    a.src[j] = src[j];
+    a.len[j] = len[j];
+    a.off[j] = tot;
+    tot += len[j];
+    vec = vec && aligned16(src[j]) && (len[j] * inner) % N == 0;
+  }
+  for (int j = n; j <= kCatMax; ++j) a.off[j] = tot;
+  for (int j = n; j < kCatMax; ++j) { a.src[j] = nullptr; a.len[j] = 0; }
+  const int64_t total = inner * tot * outer;
+  if (total == 0) return AG_OK;
+  AG_CHECK(dst, AG_EINVAL, "ag_cat: null destination");
+  Context& c = ctx();
+  if (vec) {
+    const int64_t tv = total / N;
+    if (dtype == AG_F32) k_cat<float, 4><<<(unsigned)cdiv(tv, (int64_t)256), 256, 0, c.stream>>>(a, (float*)dst, tv);
+    else k_cat<double, 2><<<(unsigned)cdiv(tv, (int64_t)256), 256, 0, c.stream>>>(a, (double*)dst, tv);
+  } else {
+    if (dtype == AG_F32) k_cat<float, 1><<<(unsigned)cdiv(total, (int64_t)256), 256, 0, c.stream>>>(a, (float*)dst, total);
+    else k_cat<double, 1><<<(unsigned)cdiv(total, (int64_t)256), 256, 0, c.stream>>>(a, (double*)dst, total);
+  }
   AG_LAUNCHED();
   return AG_OK;
 }

@@ -769,15 +769,42 @@ def gather_cols(x, cols):
     return out
 
 
+def cat_into(out, srcs, inner, outer):
+    """out (freshly allocated) = cat of srcs = [(array, extent along the concatenated dimension)] in one launch."""
+    n = len(srcs)
+    ptrs = (C.c_void_p * n)(*[x.ptr if l else None for x, l in srcs])
+    lens = (C.c_int64 * n)(*[l for _, l in srcs])
+    check(lib.ag_cat(out.dt, n, ptrs, lens, vptr(out), inner, outer))
+    return out
+
+
+def multi_copy_flat(dt, segs):
+    """Contiguous copies [(src pointer, dst pointer, elements)] of one eltype code, 16 per launch (ag_multi_copy): the
+    flat concatenations of cat1d / Sparse blocks / index vectors (src/cat.jl:150-182, src/sparse.jl:57) as a handful
+    of launches instead of one per block (config 4: 100 value blocks + 100 index blocks per step)."""
+    segs = [s for s in segs if s[2]]
+    for i in range(0, len(segs), 16):
+        part = segs[i:i + 16]
+        n = len(part)
+        if n == 1:
+            check(lib.ag_slab_copy(dt, C.c_void_p(part[0][0]), part[0][2], 0, C.c_void_p(part[0][1]), part[0][2], 0, 1,
+                                   part[0][2], 1))
+            continue
+        src = (C.c_void_p * n)(*[p_[0] for p_ in part])
+        dst = (C.c_void_p * n)(*[p_[1] for p_ in part])
+        sizes = (C.c_int64 * n)(*[p_[2] for p_ in part])
+        check(lib.ag_multi_copy(dt, n, src, dst, sizes))
+
+
 def concat_index(blocks):
     """Concatenate IArray blocks on the device (raw 8-byte copies); returns (buffer, n, lo, hi)."""
     n = sum(b.size for b in blocks)
     buf = _Buffer(max(n * 8, 8))
-    off = 0
+    off, segs = 0, []
     for b in blocks:
-        if b.size:
-            check(lib.ag_slab_copy(L.F64, C.c_void_p(b.ptr), b.size, 0, C.c_void_p(buf.ptr), n, off, 1, b.size, 1))
+        segs.append((b.ptr, buf.ptr + off * 8, b.size))
         off += b.size
+    multi_copy_flat(L.F64, segs)
     return buf, n, min(b.lo for b in blocks), max(b.hi for b in blocks)
 
 

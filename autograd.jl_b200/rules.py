@@ -689,14 +689,22 @@ def _cat_fwd(*xs, dims):
     out = D.DArray.empty(out_shape, dtype)
     inner = D._prod(out_shape[:dims])
     outer = D._prod(out_shape[dims + 1:])
-    off = 0
+    srcs = []
     for x, s in zip(xs, shapes):
         if isnum(x):
             x = D.full_like_shape((1,), dtype, x)
-        x = D.materialize(x)
-        if s[dims]:
-            D.slab_copy(x, s[dims], 0, out, tot, off, inner, s[dims], outer, fresh=True)
-        off += s[dims]
+        srcs.append((D.materialize(x), s[dims]))
+    if out.size:
+        for i in range(0, len(srcs), 8):                   # ag_cat: up to 8 sources per launch
+            part = srcs[i:i + 8]
+            if i == 0 and len(srcs) <= 8:
+                D.cat_into(out, part, inner, outer)
+            else:                                          # more than 8 sources: slab by slab
+                off = sum(l for _, l in srcs[:i])
+                for x, l in part:
+                    if l:
+                        D.slab_copy(x, l, 0, out, tot, off, inner, l, outer, fresh=True)
+                    off += l
     return out
 
 
@@ -763,13 +771,13 @@ def _cat1d_fwd(*xs):
     dtype = next(a.dtype for a in arrs if isinstance(a, DArray))
     tot = sum(length(a) for a in arrs)
     out = D.DArray.empty((tot,), dtype)
-    off = 0
+    off, segs, isz = 0, [], np.dtype(dtype).itemsize
     for a in arrs:
         if isnum(a):
             a = D.full_like_shape((1,), dtype, a)
-        if a.size:
-            D.slab_copy(a, a.size, 0, out, tot, off, 1, a.size, 1, fresh=True)
+        segs.append((a.ptr, out.ptr + off * isz, a.size))
         off += a.size
+    D.multi_copy_flat(out.dt, segs)
     return out
 
 

@@ -207,9 +207,9 @@ def _concat_flat(blocks, dtype):
         return blocks[0]
     tot = sum(b.size for b in blocks)
     out = DArray.empty((tot,), dtype)
-    off = 0
+    off, segs, isz = 0, [], np.dtype(dtype).itemsize
     for b in blocks:
-        if b.size:
-            D.slab_copy(b, b.size, 0, out, tot, off, 1, b.size, 1, fresh=True)
+        segs.append((b.ptr, out.ptr + off * isz, b.size))
         off += b.size
+    D.multi_copy_flat(out.dt, segs)
     return out

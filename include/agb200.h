@@ -403,6 +403,11 @@ ag_status ag_scatter_add(int32_t dtype, void* dest, int64_t dest_len, const int6
  * src/cat.jl:27-31,46-67; also getindex/ungetindex with range indices. */
 ag_status ag_slab_copy(int32_t dtype, const void* src, int64_t src_red, int64_t src_off, void* dst,
                        int64_t dst_red, int64_t dst_off, int64_t inner, int64_t len, int64_t outer);
+/* cat(xs...; dims) of up to 8 arrays in ONE launch (src/cat.jl:27-31; `vcat(input, hidden)` of examples/charlm.jl:68):
+ * dst viewed as inner x sum(len) x outer (column-major), source j as inner x len[j] x outer.  128-bit accesses when
+ * every inner*len[j] is a multiple of the vector width and all bases are 16-byte aligned. */
+ag_status ag_cat(int32_t dtype, int32_t n, const void* const* src, const int64_t* len, void* dst, int64_t inner,
+                 int64_t outer);
 /* permutedims(x, perm) for ndims <= 4 (src/base.jl:217-218); perm is 0-based: out dim d = x dim perm[d]. */
 ag_status ag_permute(int32_t dtype, const void* x, int32_t ndims, const int64_t* shape, const int32_t* perm,
                      void* out);

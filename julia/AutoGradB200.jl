@@ -400,6 +400,40 @@ function gemm_runs_fused(w::Mat{T}, x::Mat{T}) where T<:DT
                 dtcode(T), ta, tb, m, n, k, sa.ptr, size(sa, 1), sb.ptr, size(sb, 1), r))
     r[] != 0
 end
+# Several independent products handed over together (the four gate products of an LSTM step, examples/charlm.jl:69-73
+# "we can probably combine these four operations into one", their dx products, the dW products of several steps):
+# the library runs those of one class as ONE launch.  GemmDesc mirrors `ag_gemm_desc` of include/agb200.h field by field.
+struct GemmDesc
+    transA::Int32
+    transB::Int32
+    M::Int64
+    N::Int64
+    K::Int64
+    A::Ptr{Cvoid}
+    lda::Int64
+    B::Ptr{Cvoid}
+    ldb::Int64
+    bias::Ptr{Cvoid}
+    act::Int32
+    C::Ptr{Cvoid}
+    C2::Ptr{Cvoid}
+    ldc::Int64
+end
+# jobs: (w, x, b or nothing, act) tuples; returns the outputs in order
+function gemm_group(jobs::Vector{<:Tuple}, ::Type{T}=Float32) where T<:DT
+    descs, outs = GemmDesc[], DArray{T}[]
+    for (w, x, b, act) in jobs
+        m, k = size(w); k2, n = size(x)
+        k == k2 || throw(DimensionMismatch("A has dimensions ($m,$k) but B has dimensions ($k2,$n)"))
+        (sa, ta), (sb, tb) = storage(w), storage(x)
+        c = DArray{T}(undef, (m, n))
+        push!(outs, c)
+        push!(descs, GemmDesc(ta, tb, m, n, k, sa.ptr, size(sa, 1), sb.ptr, size(sb, 1),
+                              b === nothing ? C_NULL : b.ptr, ACTS[act], c.ptr, C_NULL, m))
+    end
+    check(ccall((:ag_gemm_group, LIB), Int32, (Int32, Int32, Ptr{GemmDesc}), dtcode(T), length(descs), descs))
+    outs
+end
 function gemm_engine()
     buf = Vector{UInt8}(undef, 32)
     check(ccall((:ag_gemm_last_engine, LIB), Int32, (Ptr{UInt8}, Int64), buf, 32))
@@ -456,6 +490,13 @@ function cat(xs::DArray{T}...; dims) where T
     oshape = ntuple(i -> i == d ? tot : size(xs[1], i), nd)
     out = DArray{T}(undef, oshape)
     inner, outer, off = prod(oshape[1:d-1]), prod(oshape[d+1:end]), 0
+    if length(xs) <= 8 && !isempty(out)                     # one launch for all sources (ag_cat)
+        srcs = Ptr{Cvoid}[size(x, d) > 0 ? x.ptr : C_NULL for x in xs]
+        lens = Int64[size(x, d) for x in xs]
+        check(ccall((:ag_cat, LIB), Int32, (Int32, Int32, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Cvoid}, Int64, Int64),
+                    dtcode(T), length(xs), srcs, lens, out.ptr, inner, outer))
+        return out
+    end
     for x in xs
         size(x, d) > 0 && slab_copy!(out, tot, off, x, size(x, d), 0, inner, size(x, d), outer)
         off += size(x, d)
@@ -651,6 +692,21 @@ function ewise_fused_reduce!(r::DArray{T}, outs::Vector{<:DArray{T}}, code::Vect
            Ptr{Ptr{Cvoid}}, Int64, Int64, Int64, Int64, Int64, Ptr{Cvoid}),
           dtcode(T), code, length(code), consts, length(consts), length(ins), ins, modes, imms, length(outs), op,
           rows, cols, inner, red, outer, r.ptr)
+end
+
+# Column programs: a chain that sums over the rows of an m x n matrix and uses the sums again (the softmax normaliser
+# of examples/mnist.jl:40 and the unbroadcast of its gradient) as one launch; see include/agb200.h for the segment
+# instructions.  r === nothing: no whole-space sum.
+function ewise_colprog!(r::Union{DArray{T},Nothing}, outs::Vector{<:DArray{T}}, code::Vector{Int32}, consts::Vector{Float64},
+                        ins::Vector{Ptr{Cvoid}}, modes::Vector{Int32}, m::Integer, n::Integer) where T
+    op = Ptr{Cvoid}[o.ptr for o in outs]
+    imms = zeros(Float64, max(length(ins), 1))
+    check(ccall((:ag_ewise_colprog, LIB), Int32,
+                (Int32, Ptr{Int32}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Ptr{Float64}, Int32,
+                 Ptr{Ptr{Cvoid}}, Int64, Int64, Ptr{Cvoid}),
+                dtcode(T), code, length(code), consts, length(consts), length(ins), ins, modes, imms, length(outs), op,
+                m, n, r === nothing ? C_NULL : r.ptr))
+    outs
 end
 
 # ---- §10 graphs, events, hooks ------------------------------------------------------------------------------------------

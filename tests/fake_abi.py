@@ -596,6 +596,19 @@ class FakeLib:
                 w[:] = w + T(alpha) * g
         return 0
 
+    def ag_cat(self, dtype, n, src, lens, dst, inner, outer):
+        self.launches += 1
+        T = _DT[dtype]
+        tot = sum(int(lens[j]) for j in range(n))
+        out = _arr(dst, inner * tot * outer, T).reshape((inner, tot, outer), order="F")
+        off = 0
+        for j in range(n):
+            l = int(lens[j])
+            if l:
+                out[:, off:off + l, :] = _arr(src[j], inner * l * outer, T).reshape((inner, l, outer), order="F")
+            off += l
+        return 0
+
     def ag_multi_copy(self, dtype, nseg, src, dst, sizes):
         self.launches += 1
         T = _DT[dtype]
