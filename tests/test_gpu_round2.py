@@ -255,3 +255,99 @@ def test_gemm_group_equals_separate_calls_bitwise(ag):
     assert np.array_equal(a[-1][0], b[-1][0])
     ref = Ws[0].to_numpy().astype(np.float64) @ x.to_numpy().astype(np.float64) + bs[0].to_numpy()[:, None]
     assert np.max(np.abs(a[0][0] - 1 / (1 + np.exp(-ref)))) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("nkeys,n,block", [(1, 1, 1), (1, 700, 4), (128, 25600, 128), (300, 5000, 7), (70000, 40000, 1),
+                                           (1 << 20, 100000, 2), (257, 3000, 256), (5, 2049, 33)])
+def test_scatter_add_radix_sort_and_segmented_reduce(ag, dtype, nkeys, n, block):
+    """ag_scatter_add with the in-tree radix sort (1, 2 and 3 passes by key range; tile boundaries at 2048 entries) and
+    both forms of the segmented reduce (block per segment for wide value blocks, the narrow form otherwise; segment
+    found by key or by head): values against a float64 np.add.at, the touched set exactly, bit-identical on repeat."""
+    import sys
+    D = sys.modules["agb200.darray"]
+    lib, check = ag._lib.lib, ag._lib.check
+    rng = np.random.default_rng(nkeys + n + block)
+    idx = rng.integers(0, nkeys, n).astype(np.int64)
+    if n > 10:
+        idx[: n // 4] = idx[0]                                      # one long segment
+    vals = rng.standard_normal((n, block)).astype(dtype)
+    base = rng.standard_normal((nkeys, block)).astype(dtype) if nkeys * block <= 1 << 16 else np.zeros((nkeys, block), dtype)
+    ref = base.astype(np.float64)
+    np.add.at(ref, idx, vals.astype(np.float64))
+    dv, ib = ag.DArray.from_numpy(vals.reshape(-1)), D.index_to_device(idx)
+    outs = []
+    for _ in range(2):
+        dest = ag.DArray.from_numpy(base.reshape(-1).copy())
+        check(lib.ag_scatter_add(dest.dt, _vp(dest), dest.size, C.c_void_p(ib.ptr), _vp(dv), n, block))
+        outs.append(dest.to_numpy().reshape(nkeys, block))
+    tol = 2e-5 if dtype == np.float32 else 1e-12                    # n/4 values of one segment summed in another order
+    assert np.max(np.abs(outs[0] - ref)) <= tol * max(np.max(np.abs(ref)), 1.0)
+    assert np.array_equal(outs[0], outs[1])
+    untouched = np.ones(nkeys, bool)
+    untouched[idx] = False
+    assert np.array_equal(outs[0][untouched], base[untouched])       # bit-exact: never read-modify-written
+
+
+def test_scatter_add_flags_out_of_range_indices_without_writing(ag):
+    """A destination outside [0, nkeys) raises the sticky device flag in the first sort pass (surfacing at the next
+    sync, as the header says) and is never written; the in-range entries of the same call are applied."""
+    import sys
+    D = sys.modules["agb200.darray"]
+    lib, check = ag._lib.lib, ag._lib.check
+    idx = np.array([0, 5, 2, 9, -1, 2], np.int64)
+    vals = np.arange(6, dtype=np.float32) + 1
+    dest = ag.zeros((4,), np.float32)
+    ib = D.index_to_device(idx)
+    dv = ag.DArray.from_numpy(vals)
+    check(lib.ag_scatter_add(dest.dt, _vp(dest), 4, C.c_void_p(ib.ptr), _vp(dv), 6, 1))
+    with pytest.raises(Exception):
+        ag.sync()
+    assert np.array_equal(dest.to_numpy(), np.array([1, 0, 3 + 6, 0], np.float32))
+    ag.sync()                                                       # the flag was cleared by the failing sync
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cat_in_one_launch(ag, dtype):
+    """ag_cat: vcat / hcat / cat along a middle dimension of up to 8 arrays is ONE launch (128-bit and scalar forms);
+    more than 8 sources fall back to slab copies; values are exact copies."""
+    rng = np.random.default_rng(9)
+    mk = lambda *s: rng.standard_normal(s).astype(dtype)
+    for shapes, dims in [([(128, 33), (512, 33)], 0), ([(7, 5), (3, 5), (1, 5)], 0), ([(16, 4), (16, 9), (16, 1)], 1),
+                         ([(4, 3, 5), (4, 6, 5), (4, 1, 5)], 1), ([(3, 2)] * 11, 0), ([(8, 8), (0, 8), (4, 8)], 0)]:
+        arrs = [mk(*s) for s in shapes]
+        devs = [ag.DArray.from_numpy(np.asfortranarray(a)) for a in arrs]
+        l0 = ag.launch_count()
+        got = ag.cat(*devs, dims=dims)
+        nl = ag.launch_count() - l0
+        assert np.array_equal(got.to_numpy(), np.concatenate(arrs, axis=dims)), (shapes, dims)
+        if len(arrs) <= 8:
+            assert nl == 1, (shapes, nl)
+    # the gradient of vcat (uncat) still matches
+    a, b = mk(6, 4), mk(10, 4)
+    ga = ag.grad(lambda u: ag.sumabs2(ag.vcat(u, ag.DArray.from_numpy(b))))(ag.DArray.from_numpy(a))
+    assert np.allclose(ga.to_numpy(), 2 * a)
+
+
+def test_flat_concatenations_use_batched_copies(ag):
+    """cat1d of many arrays and a Sparse of many blocks concatenate with ag_multi_copy (16 segments per launch)."""
+    rng = np.random.default_rng(10)
+    parts = [rng.standard_normal((rng.integers(1, 40),)).astype(np.float32) for _ in range(40)]
+    devs = [ag.DArray.from_numpy(p) for p in parts]
+    l0 = ag.launch_count()
+    got = ag.cat1d(*devs)
+    assert ag.launch_count() - l0 <= 3
+    assert np.array_equal(got.to_numpy(), np.concatenate(parts))
+    E, V, T, Bn = 16, 30, 40, 8
+    Wd = ag.zeros((E, V), np.float32)
+    ids = [rng.integers(0, V, Bn) for _ in range(T)]
+    vals = [rng.standard_normal((E, Bn)).astype(np.float32) for _ in range(T)]
+    sp = ag.Sparse(Wd, [ag.DArray.from_numpy(np.asfortranarray(v)) for v in vals],
+                   [(slice(None), ag.IArray(i)) for i in ids])
+    ref = np.zeros((V, E))
+    for i, v in zip(ids, vals):
+        np.add.at(ref, i, v.T.astype(np.float64))
+    l0 = ag.launch_count()
+    got = sp.full().to_numpy()
+    assert ag.launch_count() - l0 <= 14, ag.launch_count() - l0       # 3 + 3 batched copies, sort, reduce, zero fill
+    assert np.max(np.abs(got - ref.T)) <= 1e-5 * np.max(np.abs(ref))
