@@ -22,6 +22,7 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;   // optional (old libraries lack it)
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
 };
@@ -44,6 +45,7 @@ static ag_status nccl_load() {
   SYM(AllReduce, "ncclAllReduce");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
+  *(void**)(&g_nccl.CommGetAsyncError) = dlsym(g_nccl.h, "ncclCommGetAsyncError");
   return AG_OK;
 }
 
@@ -365,6 +367,19 @@ static ag_status fill_args(P2PArgs& a, int32_t dtype, int32_t nseg, void* const*
 }
 
 // Called by ag_sync: a peer wait that expired since the last check (0 = none, else 1 + the rank waited for).
+// Asynchronous NCCL failures (a peer died, a transport error) do not surface from the enqueue call: poll the
+// communicator (ncclCommGetAsyncError) at every ag_sync and before every NCCL allreduce of the fallback path, so that a
+// broken job raises AG_ENCCL instead of hanging in the next collective.  0 = healthy / no communicator.
+int comm_nccl_async_error(char* msg, int msglen) {
+  if (!g_nccl.comm || !g_nccl.CommGetAsyncError) return 0;
+  ncclResult_t st = 0;
+  if (g_nccl.CommGetAsyncError(g_nccl.comm, &st) != 0) st = -1;
+  if (st == 0 || st == 7 /* ncclInProgress */) return 0;
+  if (msg && msglen > 0)
+    snprintf(msg, msglen, "NCCL asynchronous error %d (%s)", st, st > 0 && g_nccl.GetErrorString ? g_nccl.GetErrorString(st) : "?");
+  return st;
+}
+
 int comm_take_timeout() {
   if (!g_p2p.peer_dev) return 0;
   int32_t h = 0;
@@ -602,6 +617,13 @@ ag_status ag_allreduce_sum(int32_t dtype, void* buf, int64_t n) {
   AG_REQUIRE_INIT();
   if (n == 0 || g_nccl.nranks == 1) return AG_OK;
   AG_CHECK(g_nccl.comm, AG_ESTATE, "ag_allreduce_sum: call ag_comm_init first");
+  {
+    char why[160];
+    if (comm_nccl_async_error(why, sizeof(why))) {
+      set_error("ag_allreduce_sum: %s", why);
+      return AG_ENCCL;
+    }
+  }
   AG_CHECK(buf && n > 0, AG_EINVAL, "ag_allreduce_sum: bad arguments");
   AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_allreduce_sum: dtype %d", dtype);
   AG_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, dtype == AG_F32 ? ncclFloat32 : ncclFloat64, ncclSum,

@@ -25,6 +25,7 @@ Context& ctx();
 void set_error(const char* fmt, ...);
 ag_status cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void* workspace(size_t bytes);  // grows the shared workspace (not during graph capture)
+int comm_nccl_async_error(char* msg, int msglen);   // comm.cu: ncclCommGetAsyncError of the communicator (0 = healthy)
 int comm_take_timeout();       // comm.cu: a peer-memory wait expired since the last check (0 = none, else 1 + rank)
 int32_t* oob_flag();            // sticky device flag raised by index checks; read and cleared by ag_sync
 

@@ -269,6 +269,13 @@ ag_status ag_sync(void) {
       return AG_ENCCL;
     }
   }
+  if (!ctx().capturing) {
+    char why[160];
+    if (comm_nccl_async_error(why, sizeof(why))) {
+      set_error("%s", why);
+      return AG_ENCCL;
+    }
+  }
   if (g_oob_armed && g_oob && !ctx().capturing) {
     int32_t h = 0;
     AG_CUDA(cudaMemcpy(&h, g_oob, 4, cudaMemcpyDeviceToHost));

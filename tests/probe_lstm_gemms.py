@@ -53,13 +53,16 @@ cases = {
     "dh    Wp'*dy     (512x256x128, TN)": (1, 0, H, B, V, Wp, V, dyp, V),
     "dWp   dy*h'      (128x512x256, NT)": (0, 1, V, H, B, dyp, V, h, H),
 }
+ENG = os.environ.get("ENGINE", "auto")
+ag.set_gemm_engine(ENG)
+print("engine:", ENG)
 for name, p in cases.items():
     fn, keep = group([p])
     l0 = ag.launch_count()
     fn()
     nl = ag.launch_count() - l0
     us = timeit(fn)
-    eng = ag.last_gemm_engine() if hasattr(ag, "last_gemm_engine") else "?"
+    eng = ag.gemm_engine()
     print("%-40s alone %6.1f us  (%d launches, %s)" % (name, us, nl, eng))
 for name, ps in {
     "4 gates": [(0, 0, H, B, EH, W[g], H, x, EH) for g in range(4)],
