@@ -45,6 +45,7 @@ _SIGS = {
     "ag_host_free": [vp],
     "ag_copy_h2d": [vp, vp, i64],
     "ag_copy_h2d_prefetch": [vp, vp, i64],
+    "ag_prefetch_slot": [i32],
     "ag_prefetch_wait": [],
     "ag_prefetch_release": [],
     "ag_copy_d2h": [vp, vp, i64],

@@ -371,14 +371,28 @@ ag_status ag_copy_h2d(void* dst, const void* src, int64_t bytes) {
 
 // ---- input prefetch on a second stream: the h2d copy of the NEXT batch overlaps the step on the current one ----
 static cudaStream_t g_copy_stream = nullptr;
-static cudaEvent_t g_ev_ready = nullptr, g_ev_consumed = nullptr;
+// Two slots (ag_prefetch_slot): with two staging buffers the copy of batch i+1 only waits for the consumer of batch i-1,
+// so the copy engine never idles while batch i is being converted.
+constexpr int kPrefetchSlots = 2;
+static cudaEvent_t g_ev_ready[kPrefetchSlots] = {nullptr, nullptr}, g_ev_consumed[kPrefetchSlots] = {nullptr, nullptr};
+static int g_prefetch_slot = 0;
 
 static ag_status prefetch_init() {
   if (g_copy_stream) return AG_OK;
   AG_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
-  AG_CUDA(cudaEventCreateWithFlags(&g_ev_ready, cudaEventDisableTiming));
-  AG_CUDA(cudaEventCreateWithFlags(&g_ev_consumed, cudaEventDisableTiming));
-  AG_CUDA(cudaEventRecord(g_ev_consumed, ctx().stream));
+  for (int k = 0; k < kPrefetchSlots; ++k) {
+    AG_CUDA(cudaEventCreateWithFlags(&g_ev_ready[k], cudaEventDisableTiming));
+    AG_CUDA(cudaEventCreateWithFlags(&g_ev_consumed[k], cudaEventDisableTiming));
+    AG_CUDA(cudaEventRecord(g_ev_consumed[k], ctx().stream));
+    AG_CUDA(cudaEventRecord(g_ev_ready[k], ctx().stream));
+  }
+  return AG_OK;
+}
+
+ag_status ag_prefetch_slot(int32_t slot) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(slot >= 0 && slot < kPrefetchSlots, AG_EINVAL, "ag_prefetch_slot: slot %d of %d", slot, kPrefetchSlots);
+  g_prefetch_slot = slot;
   return AG_OK;
 }
 
@@ -388,9 +402,10 @@ ag_status ag_copy_h2d_prefetch(void* dst, const void* src, int64_t bytes) {
   AG_CHECK(dst && src && bytes > 0, AG_EINVAL, "ag_copy_h2d_prefetch: bad arguments");
   ag_status st = prefetch_init();
   if (st != AG_OK) return st;
-  AG_CUDA(cudaStreamWaitEvent(g_copy_stream, g_ev_consumed, 0));     // the staging buffer's last reader is done
+  // the last reader of this slot's staging buffer is done
+  AG_CUDA(cudaStreamWaitEvent(g_copy_stream, g_ev_consumed[g_prefetch_slot], 0));
   AG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, g_copy_stream));
-  AG_CUDA(cudaEventRecord(g_ev_ready, g_copy_stream));
+  AG_CUDA(cudaEventRecord(g_ev_ready[g_prefetch_slot], g_copy_stream));
   return AG_OK;
 }
 
@@ -398,7 +413,7 @@ ag_status ag_prefetch_wait(void) {
   AG_REQUIRE_INIT();
   ag_status st = prefetch_init();
   if (st != AG_OK) return st;
-  AG_CUDA(cudaStreamWaitEvent(ctx().stream, g_ev_ready, 0));
+  AG_CUDA(cudaStreamWaitEvent(ctx().stream, g_ev_ready[g_prefetch_slot], 0));
   return AG_OK;
 }
 
@@ -406,7 +421,7 @@ ag_status ag_prefetch_release(void) {
   AG_REQUIRE_INIT();
   ag_status st = prefetch_init();
   if (st != AG_OK) return st;
-  AG_CUDA(cudaEventRecord(g_ev_consumed, ctx().stream));
+  AG_CUDA(cudaEventRecord(g_ev_consumed[g_prefetch_slot], ctx().stream));
   return AG_OK;
 }
 

@@ -47,8 +47,11 @@ class UByteBatch:
         self.divisor, self.zero_to = float(divisor), int(zero_to)
         self.x = D.DArray.empty((self.nfeat, self.ncols), dtype)
         self.y = D.DArray.empty((self.nclass, self.ncols), dtype)
-        self._px = D._Buffer(max(self.nfeat * self.ncols, 16))
-        self._lb = D._Buffer(max(self.ncols, 16))
+        # two staging buffer sets (prefetch slots): batch i+1 crosses PCIe into one while batch i is converted from
+        # the other, so the copy engine never waits for a conversion
+        self._px = [D._Buffer(max(self.nfeat * self.ncols, 16)) for _ in range(2)]
+        self._lb = [D._Buffer(max(self.ncols, 16)) for _ in range(2)]
+        self._fill, self._cur = 0, 0           # slot the next prefetch fills / slot the next convert reads
 
     @property
     def h2d_bytes(self):
@@ -58,14 +61,22 @@ class UByteBatch:
         """Start copying the NEXT batch's bytes on the copy stream (they land in the staging buffers while the step
         on the current batch runs); `convert()` then rebuilds `x` and `y` from them on the main stream."""
         pixels, labels = self._check(pixels, labels)
-        check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(self._px.ptr), C.c_void_p(pixels.ctypes.data), pixels.size))
-        check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(self._lb.ptr), C.c_void_p(labels.ctypes.data), labels.size))
+        k = self._fill
+        check(D.lib.ag_prefetch_slot(k))
+        check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(self._px[k].ptr), C.c_void_p(pixels.ctypes.data), pixels.size))
+        check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(self._lb[k].ptr), C.c_void_p(labels.ctypes.data), labels.size))
+        self._fill = k ^ 1
 
     def convert(self):
+        """Rebuild `x`, `y` from the oldest prefetched batch (prefetch and convert alternate: at most two batches are
+        in flight)."""
         _lazy.flush()                                   # pending operations must read the previous batch first
+        k = self._cur
+        check(D.lib.ag_prefetch_slot(k))
         check(D.lib.ag_prefetch_wait())
-        self._convert()
+        self._convert(k)
         check(D.lib.ag_prefetch_release())
+        self._cur = k ^ 1
         return self.x, self.y
 
     def _check(self, pixels, labels):
@@ -82,14 +93,14 @@ class UByteBatch:
     def load(self, pixels, labels):
         pixels, labels = self._check(pixels, labels)
         _lazy.flush()                                   # pending operations must read the previous batch first
-        check(D.lib.ag_copy_h2d(C.c_void_p(self._px.ptr), C.c_void_p(pixels.ctypes.data), pixels.size))
-        check(D.lib.ag_copy_h2d(C.c_void_p(self._lb.ptr), C.c_void_p(labels.ctypes.data), labels.size))
-        self._convert()
+        check(D.lib.ag_copy_h2d(C.c_void_p(self._px[0].ptr), C.c_void_p(pixels.ctypes.data), pixels.size))
+        check(D.lib.ag_copy_h2d(C.c_void_p(self._lb[0].ptr), C.c_void_p(labels.ctypes.data), labels.size))
+        self._convert(0)
         return self.x, self.y
 
-    def _convert(self):
-        check(D.lib.ag_ubyte_to_float(self.x.dt, C.c_void_p(self._px.ptr), D.vptr(self.x), self.x.size, self.divisor))
-        check(D.lib.ag_onehot_labels(self.y.dt, C.c_void_p(self._lb.ptr), self.ncols, self.nclass, self.zero_to,
+    def _convert(self, k):
+        check(D.lib.ag_ubyte_to_float(self.x.dt, C.c_void_p(self._px[k].ptr), D.vptr(self.x), self.x.size, self.divisor))
+        check(D.lib.ag_onehot_labels(self.y.dt, C.c_void_p(self._lb[k].ptr), self.ncols, self.nclass, self.zero_to,
                                      D.vptr(self.y)))
 
 
@@ -100,18 +111,25 @@ class StagedInput:
 
     def __init__(self, *arrays):
         self.arrays = arrays
-        self.stage = [D._Buffer(max(a.nbytes, 16)) for a in arrays]
+        self.stage = [[D._Buffer(max(a.nbytes, 16)) for a in arrays] for _ in range(2)]     # two prefetch slots
+        self._fill, self._cur = 0, 0
 
     def prefetch(self, *host_ptrs):
-        for a, st, hp in zip(self.arrays, self.stage, host_ptrs):
+        k = self._fill
+        check(D.lib.ag_prefetch_slot(k))
+        for a, st, hp in zip(self.arrays, self.stage[k], host_ptrs):
             check(D.lib.ag_copy_h2d_prefetch(C.c_void_p(st.ptr), C.c_void_p(int(hp)), a.nbytes))
+        self._fill = k ^ 1
 
     def commit(self):
         _lazy.flush()
+        k = self._cur
+        check(D.lib.ag_prefetch_slot(k))
         check(D.lib.ag_prefetch_wait())
-        for a, st in zip(self.arrays, self.stage):
+        for a, st in zip(self.arrays, self.stage[k]):
             check(D.lib.ag_copy_d2d(D.vptr(a), C.c_void_p(st.ptr), a.nbytes))
         check(D.lib.ag_prefetch_release())
+        self._cur = k ^ 1
 
 
 # ---- character data of examples/charlm.jl:166-203 -------------------------------------------------------------------

@@ -149,7 +149,11 @@ ag_status ag_copy_h2d(void* dst_dev, const void* src_host, int64_t bytes); /* as
  * stream so that the NEXT batch crosses PCIe while the step on the current one executes.  ag_copy_h2d_prefetch waits
  * (on the device) until the previous contents of the staging buffer were released, then copies; ag_prefetch_wait makes
  * the main stream wait for the prefetched data; ag_prefetch_release (after the consumer of the staging buffer has been
- * enqueued) lets the next prefetch overwrite it.  src must be pinned (ag_host_alloc) for the copy to be asynchronous. */
+ * enqueued) lets the next prefetch overwrite it.  src must be pinned (ag_host_alloc) for the copy to be asynchronous.
+ * ag_prefetch_slot selects which of two (ready, released) event pairs the three calls use (default 0): a loader with
+ * two staging buffers alternates the slot, so that the copy of batch i+1 waits for the consumer of batch i-1 only and
+ * the copy engine does not idle while batch i is converted. */
+ag_status ag_prefetch_slot(int32_t slot);
 ag_status ag_copy_h2d_prefetch(void* dst_dev, const void* src_host, int64_t bytes);
 ag_status ag_prefetch_wait(void);
 ag_status ag_prefetch_release(void);

@@ -137,6 +137,8 @@ class FakeLib:
 
     ag_copy_h2d = ag_copy_d2h = ag_copy_d2h_async = ag_copy_d2d = ag_copy_h2d_prefetch = _copy
 
+    def ag_prefetch_slot(self, slot): return 0 if 0 <= slot < 2 else self._fail(1, "ag_prefetch_slot: bad slot")
+
     def ag_prefetch_wait(self): return 0
 
     def ag_prefetch_release(self): return 0
