@@ -363,12 +363,22 @@ def main():
     # ---- forward / backward split (two graphs, events between them), N-independent
     #      (recorded on a tape, so the forward writes every value the backward sweep will read)
     from agb200 import core as _core
+    _lz = sys.modules["agb200.lazy"]
     with ag.StepGraph() as g_f:
-        _core._tapes.append(_core.Tape())
+        tape_f = _core.Tape()
+        _core._tapes.append(tape_f)
         try:
             loss_t = Wl.mnist_loss(ag, params, xd, yd, global_batch=gB)
         finally:
             _core._tapes.pop()
+        # what the full step does at the end of its sweep (core.differentiate): values that only the tape holds
+        # softly (the product under `w*x .+ b`, which no rule reads) are dropped, not computed by the closing flush --
+        # otherwise the forward graph would run w1*x a second time and the split below would charge it to "forward"
+        soft = [n.Value.value for n in reversed(tape_f.list) if isinstance(n.Value, _core.Result) and n.Value._soft
+                and getattr(n.Value.value, "kind", None) is not None]
+        if soft:
+            _lz.discard_soft(soft)
+        del soft
     ef0, ef1 = ag.Event(), ag.Event()
     ef0.record()
     for _ in range(K):
