@@ -266,6 +266,17 @@ __device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int6
     const int64_t ld = p.ld_out;
     float* dst = p.out + mm + ld * nn0;
     float* dst2 = p.out2 ? p.out2 + mm + ld * nn0 : nullptr;
+    if (ACT == TC_ACT_NONE && nvalid == TC_BN && !scale && !hb && !dst2) {
+      // the plain product (every gradient product of the tapes): three instructions per element -- the executed
+      // footprint of this path is what a small product pays in instruction fetch every time the tape comes back to it
+      // (measured: 13.2 us per launch interleaved with other kernels against 9.9 us back to back)
+#pragma unroll
+      for (int j = 0; j < TC_BN; ++j) {
+        *dst = v[j];
+        dst += ld;
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < TC_BN; ++j) {
       if (j < nvalid) {
@@ -589,10 +600,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int nvalid = (int)min((int64_t)TC_BN, p.NN - nn0);
           const int64_t ld = p.ld_out;
           float* dst = out + mm + ld * nn0;
+          if (nvalid == TC_BN) {
 #pragma unroll
-          for (int j = 0; j < TC_BN; ++j) {
-            if (j < nvalid) *dst = accv[j];
-            dst += ld;
+            for (int j = 0; j < TC_BN; ++j) {
+              *dst = accv[j];
+              dst += ld;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BN; ++j) {
+              if (j < nvalid) *dst = accv[j];
+              dst += ld;
+            }
           }
         }
       }
