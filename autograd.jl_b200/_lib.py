@@ -75,6 +75,7 @@ _SIGS = {
     "ag_ewise_fused_stats": [pi64],
     "ag_sum_all": [i32, i32, vp, i64, vp],
     "ag_sum_dim": [i32, i32, vp, i64, i64, i64, vp],
+    "ag_sum_dim_batch": [i32, i32, i32, C.POINTER(vp), i64, i64, i64, C.POINTER(vp)],
     "ag_reduce_dim": [i32, i32, vp, i64, i64, i64, vp],
     "ag_permute": [i32, vp, i32, pi64, C.POINTER(i32), vp],
     "ag_add": [i32, vp, vp, vp, i64],

@@ -236,6 +236,51 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same tile kernel for up to 32 arrays of ONE layout in one launch (blockIdx.y = array): the bias-gradient row sums
+// of the four LSTM gates over many timesteps (the host defers them, lazy.py kind "rs").  Same arithmetic, same order:
+// bit-identical to separate launches.
+constexpr int kBatchMax = 32;
+struct BatchPtrs {
+  const void* x[kBatchMax];
+  void* out[kBatchMax];
+};
+template <int MAP, int LW, typename T>
+__global__ void __launch_bounds__(256)
+    k_strided_tile_batch(const __grid_constant__ BatchPtrs b, int64_t inner, int64_t red) {
+  constexpr int G = 256 / LW;
+  __shared__ double sm[G][LW + 1];
+  const T* __restrict__ x = (const T*)b.x[blockIdx.y];
+  T* __restrict__ out = (T*)b.out[blockIdx.y];
+  const int lane = threadIdx.x % LW, w = threadIdx.x / LW;
+  const int64_t i = (int64_t)blockIdx.z * LW + lane, o = blockIdx.x;
+  double s = 0;
+  if (i < inner) {
+    const T* __restrict__ p = x + o * inner * red + i;
+    T a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = T(0);
+    int64_t r = w;
+    for (; r + 7 * G < red; r += 8 * G) {
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p[(r + G * u) * inner];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += premap<MAP>(v[u]);
+    }
+    for (; r < red; r += G) a[0] += premap<MAP>(p[r * inner]);
+    s = (((double)a[0] + (double)a[1]) + ((double)a[2] + (double)a[3])) +
+        (((double)a[4] + (double)a[5]) + ((double)a[6] + (double)a[7]));
+  }
+  sm[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && i < inner) {
+    double r = 0;
+#pragma unroll
+    for (int q = 0; q < G; ++q) r += sm[q][lane];
+    out[o * inner + i] = (T)r;
+  }
+}
+
 // phase 2 of the strided reductions: out[i,o] = sum_c part[o][c][i]; 8 outputs x 32 lanes per block: a lane sums
 // every 32nd partial (8 consecutive outputs = one 64-byte run per load), fixed-order combine (deterministic).
 // grid (ceil(inner/8), outer)
@@ -554,6 +599,44 @@ ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, i
   AG_CHECK(x, AG_EINVAL, "ag_sum_dim: null input");
   return dtype == AG_F32 ? sum_dim_map<float>(map, x, inner, red, outer, out)
                          : sum_dim_map<double>(map, x, inner, red, outer, out);
+}
+
+ag_status ag_sum_dim_batch(int32_t map, int32_t dtype, int32_t n, const void* const* xs, int64_t inner, int64_t red,
+                           int64_t outer, void* const* outs) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_sum_dim_batch: dtype %d", dtype);
+  AG_CHECK(n >= 0 && (n == 0 || (xs && outs)) && inner >= 0 && red >= 0 && outer >= 0, AG_EINVAL,
+           "ag_sum_dim_batch: bad arguments");
+  AG_CHECK(map >= 0 && map <= 2, AG_EINVAL, "ag_sum_dim_batch: map %d", map);
+  if (n == 0 || inner * outer == 0) return AG_OK;
+  for (int k = 0; k < n; ++k) AG_CHECK(outs[k] && (red == 0 || xs[k]), AG_EINVAL, "ag_sum_dim_batch: null array %d", k);
+  Context& c = ctx();
+  // the layout of the tile kernel (ag_sum_dim's own choice for it): one launch per 32 arrays; anything else one by one
+  const bool tile = red >= 32 && inner > kRT && outer * cdiv(inner, (int64_t)32) < 2 * c.num_sms &&
+                    cdiv(inner, (int64_t)16) <= 65535 && red <= 256;
+  if (!tile || n == 1) {
+    for (int k = 0; k < n; ++k) {
+      ag_status st = ag_sum_dim(map, dtype, xs[k], inner, red, outer, outs[k]);
+      if (st != AG_OK) return st;
+    }
+    return AG_OK;
+  }
+  for (int k0 = 0; k0 < n; k0 += kBatchMax) {
+    const int m = n - k0 < kBatchMax ? n - k0 : kBatchMax;
+    BatchPtrs b;
+    for (int k = 0; k < m; ++k) { b.x[k] = xs[k0 + k]; b.out[k] = outs[k0 + k]; }
+    for (int k = m; k < kBatchMax; ++k) { b.x[k] = nullptr; b.out[k] = nullptr; }
+    const dim3 grid((unsigned)outer, (unsigned)m, (unsigned)cdiv(inner, (int64_t)16));
+#define SDB(MAP_)                                                                                              \
+  do {                                                                                                         \
+    if (dtype == AG_F32) k_strided_tile_batch<MAP_, 16, float><<<grid, 256, 0, c.stream>>>(b, inner, red);     \
+    else k_strided_tile_batch<MAP_, 16, double><<<grid, 256, 0, c.stream>>>(b, inner, red);                    \
+  } while (0)
+    if (map == AG_R_ID) SDB(AG_R_ID); else if (map == AG_R_ABS2) SDB(AG_R_ABS2); else SDB(AG_R_ABS);
+#undef SDB
+    AG_LAUNCHED();
+  }
+  return AG_OK;
 }
 
 ag_status ag_reduce_dim(int32_t op, int32_t dtype, const void* x, int64_t inner, int64_t red, int64_t outer,

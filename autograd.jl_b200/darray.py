@@ -170,6 +170,8 @@ class DArray:
 
     def reshape(self, shape):
         shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        if shape == self.shape and not self.tr:
+            return self                   # same dims: the same data (a pending value stays pending)
         src = materialize(self)
         if _prod(shape) != src.size:
             raise L.DimensionMismatch("reshape %s -> %s" % (src.shape, shape))
@@ -481,6 +483,13 @@ def sum_dims(x, dims, mapname="id"):
             if _lazy.is_pending(r) and r.shape == tuple(out_shape):
                 return r                  # a column sum that stays inside the chain (lazy.reduce)
             return r.reshape(out_shape)
+    if len(runs) == 1 and x.size:
+        lo, hi = runs[0]
+        if _lazy.is_pending(x):
+            x.ptr                         # the chain below the sum is evaluated now; the sum itself waits
+        r = _lazy.reduce_deferred(x, _prod(shape[:lo]), _prod(shape[lo:hi + 1]), _prod(shape[hi + 1:]), mapname, out_shape)
+        if r is not None:
+            return r                      # evaluated later, batched with the other reductions of its layout
     cur, cur_shape, m = x, shape, mapname
     for lo, hi in runs:
         inner = _prod(cur_shape[:lo])

@@ -54,6 +54,7 @@ reduce_fusion = [os.environ.get("AGB_FUSE_REDUCE", "1") != "0"]
 # lanes busy at m = 10, two dependent memory round trips per warp), where the separate chain kernels stream 128-bit
 # vectors with every load in flight.  AGB_FUSE_COLUMNS=1 (or set_col_fusion(True)) turns it on.
 col_fusion = [os.environ.get("AGB_FUSE_COLUMNS", "0") == "1"]
+batch_reductions = [os.environ.get("AGB_BATCH_REDUCTIONS", "1") != "0"]    # defer stand-alone reductions and batch them
 static_only = [os.environ.get("AGB_FUSE_BIG_INTERPRETED", "0") == "0"]   # see BIG   # sums of a pending chain in the chain's own launch
 stats = {"fused_launches": 0, "fused_nodes": 0, "fallback_nodes": 0, "splits": 0}
 trace = None            # set to a list to record (n elements, full-array inputs, outputs, program) of every fused launch
@@ -262,6 +263,36 @@ def reduce(x, inner, red, outer, mapname):
     return out
 
 
+def reduce_deferred(x, inner, red, outer, mapname, out_shape):
+    """sum(map, x; dims) of a CONCRETE x as a pending value (kind "rs"): it is evaluated when something touches it, and
+    then together with every other pending reduction of the same layout in ONE launch (ag_sum_dim_batch) -- the bias
+    gradients `unbroadcast(b, dy)` of the four LSTM gates over many timesteps wait in the accumulation chain of
+    `addto!` until that chain is evaluated.  Returns None when reductions are not deferred."""
+    if not (enabled[0] and reduce_fusion[0] and batch_reductions[0]) or is_pending(x) or x.tr:
+        return None
+    return LazyArray(out_shape, x.dtype, "rs", (int(inner), int(red), int(outer), mapname), (x,), 1)
+
+
+def _force_reductions(root):
+    """Evaluate the pending reduction `root` and every other pending reduction of its layout (latest first)."""
+    batch = [root]
+    for k in sorted(_pending.keys(), reverse=True):
+        n = _pending.get(k)
+        if n is not None and n is not root and n.kind == "rs" and n.op == root.op and n.dtype == root.dtype:
+            batch.append(n)
+        n = None
+    inner, red, outer, mapname = root.op
+    outs = [D.DArray.empty(n.shape, n.dtype) for n in batch]
+    cnt = len(batch)
+    xs = (C.c_void_p * cnt)(*[n.args[0].ptr for n in batch])
+    os_ = (C.c_void_p * cnt)(*[o.ptr for o in outs])
+    check(D.lib.ag_sum_dim_batch(D.R[mapname], D._DT[np.dtype(root.dtype)], cnt, xs, inner, red, outer, os_))
+    stats["batched_reductions"] = stats.get("batched_reductions", 0) + cnt
+    stats["reduction_batches"] = stats.get("reduction_batches", 0) + 1
+    for n, o in zip(batch, outs):
+        n._set_storage(o)
+
+
 class _TooBig(Exception):
     """The DAG needs more inputs / outputs / instructions / slots than one launch has: evaluate arguments first."""
 
@@ -343,10 +374,23 @@ def force(root):
         if root.kind == "mm":
             root._set_storage(D._matmul_eager(root.args[0], root.args[1], root.op, root.shape, root.dtype))
             return
+        if root.kind == "rs":
+            _force_reductions(root)
+            return
         order = _topo(root)
         if _resolve_products(order, root):
             order = None
             continue                        # some nodes got their storage from a fused product: walk the rest again
+        rs = None
+        for i in range(len(order)):
+            if order[i].kind == "rs":
+                rs = order[i]
+                break
+        if rs is not None:                  # deferred reductions below the root: evaluate them (batched), walk again
+            order = None
+            _force_reductions(rs)
+            rs = None
+            continue
         action, ext = None, None
         if col_fusion[0] and _mixed_order(order):
             ok = False
@@ -487,6 +531,10 @@ def _run_eager(order):
             r = D._full_like_shape_eager(n.shape, n.dtype, a[0])
         elif k == "mm":
             r = D._matmul_eager(a[0], a[1], n.op, n.shape, n.dtype)
+        elif k == "rs":
+            _force_reductions(n)
+            stats["fallback_nodes"] += 1
+            continue
         elif k == "cr":
             r = D.DArray.empty(n.shape, n.dtype)
             check(D.lib.ag_sum_dim(D.R["id"], D._DT[np.dtype(n.dtype)], C.c_void_p(a[0].ptr), 1, a[0].shape[0], a[0].shape[1],

@@ -292,6 +292,12 @@ ag_status ag_sum_all(int32_t map, int32_t dtype, const void* x, int64_t n, void*
  * unbroadcast (src/unbroadcast.jl:17-24). */
 ag_status ag_sum_dim(int32_t map, int32_t dtype, const void* x, int64_t inner, int64_t red,
                      int64_t outer, void* out);
+/* The same reduction for n arrays of ONE layout, handed over together so that the library can run them as one launch
+ * (up to 32 arrays per launch for the row sums of a tall matrix with a short reduced extent: the bias gradients
+ * `unbroadcast(b, dy)` = sum(dy, dims=2) of the four LSTM gates over many timesteps, src/unbroadcast.jl:17-24;
+ * other layouts run one by one).  Values are those of n ag_sum_dim calls, bit for bit. */
+ag_status ag_sum_dim_batch(int32_t map, int32_t dtype, int32_t n, const void* const* xs, int64_t inner, int64_t red,
+                           int64_t outer, void* const* outs);
 
 /* out[i,o] = op over r of x[i,r,o], op: 0 = maximum, 1 = minimum, 2 = prod (forward of the rules at
  * src/base.jl:202-206,221; their gradients `dy.*(y.==x)` / `dy.*(y./x)` go through ag_binary_bwd / ag_binary_fwd). */

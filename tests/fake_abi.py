@@ -425,6 +425,15 @@ class FakeLib:
     def ag_sum_all(self, m, dtype, x, n, out):
         return self.ag_sum_dim(m, dtype, x, 1, n, 1, out)
 
+    def ag_sum_dim_batch(self, m, dtype, n, xs, inner, red, outer, outs):
+        for k in range(n):
+            st = self.ag_sum_dim(m, dtype, xs[k], inner, red, outer, outs[k])
+            if st:
+                return st
+        if n > 1:
+            self.launches -= n - 1          # one launch for the batch
+        return 0
+
     def ag_sum_dim(self, m, dtype, x, inner, red, outer, out):
         self.launches += 1
         T = _DT[dtype]
