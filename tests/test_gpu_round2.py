@@ -351,3 +351,51 @@ def test_flat_concatenations_use_batched_copies(ag):
     got = sp.full().to_numpy()
     assert ag.launch_count() - l0 <= 14, ag.launch_count() - l0       # 3 + 3 batched copies, sort, reduce, zero fill
     assert np.max(np.abs(got - ref.T)) <= 1e-5 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("inner,red,outer,n", [(512, 256, 1, 7), (512, 256, 1, 40), (300, 64, 1, 3), (64, 4096, 1, 3),
+                                               (1, 128, 256, 4), (16, 10, 3, 5)])
+def test_sum_dim_batch_equals_separate_reductions_bitwise(ag, dtype, inner, red, outer, n):
+    """ag_sum_dim_batch: n reductions of one layout handed over together (one launch per 32 for the tile layout of the
+    LSTM bias gradients, one by one otherwise) give exactly the values of n ag_sum_dim calls."""
+    lib, check = ag._lib.lib, ag._lib.check
+    rng = np.random.default_rng(inner + red + n)
+    xs = [ag.DArray.from_numpy(rng.standard_normal(inner * red * outer).astype(dtype)) for _ in range(n)]
+    one = [ag.DArray.empty((inner * outer,), dtype) for _ in range(n)]
+    for x, o in zip(xs, one):
+        check(lib.ag_sum_dim(0, x.dt, _vp(x), inner, red, outer, _vp(o)))
+    many = [ag.DArray.empty((inner * outer,), dtype) for _ in range(n)]
+    px = (C.c_void_p * n)(*[x.ptr for x in xs])
+    po = (C.c_void_p * n)(*[o.ptr for o in many])
+    l0 = ag.launch_count()
+    check(lib.ag_sum_dim_batch(0, xs[0].dt, n, px, inner, red, outer, po))
+    nl = ag.launch_count() - l0
+    if (inner, red) == (512, 256):
+        assert nl == (n + 31) // 32
+    for a, b, x in zip(one, many, xs):
+        assert np.array_equal(a.to_numpy(), b.to_numpy())
+        ref = x.to_numpy().astype(np.float64).reshape((inner, red, outer), order="F").sum(axis=1).reshape(-1, order="F")
+        assert np.max(np.abs(b.to_numpy() - ref)) <= (1e-5 if dtype == np.float32 else 1e-12) * max(np.max(np.abs(ref)), 1)
+
+
+def test_stand_alone_reductions_are_deferred_and_batched(ag):
+    """sum(x; dims) of stored arrays stays pending (lazy kind "rs") and many of them are evaluated by one launch when
+    the first is touched; an in-place update of an operand first evaluates what is pending (program order holds)."""
+    import sys
+    L = sys.modules["agb200.lazy"]
+    rng = np.random.default_rng(12)
+    arrs = [rng.standard_normal((512, 256)).astype(np.float32) for _ in range(12)]
+    devs = [ag.DArray.from_numpy(np.asfortranarray(a)) for a in arrs]
+    b0 = L.stats.get("reduction_batches", 0)
+    sums = [ag.sum_(d, dims=1) for d in devs]
+    assert all(L.is_pending(s) for s in sums)
+    acc = sums[0]
+    for s in sums[1:]:
+        acc = ag.add(acc, s)                                        # the accumulation chain of addto!
+    ag.axpy(1.0, devs[1], devs[0])                                  # in-place update of an operand: flushes first
+    got = acc.to_numpy()
+    assert L.stats.get("reduction_batches", 0) == b0 + 1
+    ref = sum(a.astype(np.float64).sum(axis=1, keepdims=True) for a in arrs)
+    assert np.max(np.abs(got - ref)) <= 1e-5 * np.max(np.abs(ref))
+    assert np.allclose(sums[0].to_numpy(), arrs[0].sum(axis=1, keepdims=True), rtol=1e-5, atol=1e-4)

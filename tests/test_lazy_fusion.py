@@ -401,3 +401,26 @@ def test_column_program_fallback_when_it_does_not_fit(lz):
         assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)
     finally:
         L.set_col_fusion(prev)
+
+
+def test_deferred_reductions_keep_program_order(lz):
+    """A stand-alone sum(x; dims) is deferred (kind "rs"); mutating x in place afterwards must not change it."""
+    ag, L, D = lz
+    rng = np.random.default_rng(4)
+    x = dev(ag, rng.standard_normal((300, 20)))
+    y = dev(ag, rng.standard_normal((300, 20)))
+    xn = x.to_numpy().copy()
+    s = ag.sum_(x, dims=1)
+    assert L.is_pending(s) and s.kind == "rs"
+    t = ag.sum_(y, dims=1)
+    b0 = L.stats.get("reduction_batches", 0)
+    ag.axpy(2.0, y, x)                                  # flushes: both reductions run (one batch) on the old x
+    assert L.stats.get("reduction_batches", 0) == b0 + 1
+    assert not L.is_pending(s) and not L.is_pending(t)
+    assert np.allclose(s.to_numpy(), xn.sum(axis=1, keepdims=True), rtol=1e-12, atol=1e-12)
+    prev = L.batch_reductions[0]
+    L.batch_reductions[0] = False
+    try:
+        assert not L.is_pending(ag.sum_(y, dims=1))
+    finally:
+        L.batch_reductions[0] = prev
