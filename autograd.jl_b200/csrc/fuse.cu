@@ -1096,7 +1096,16 @@ static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, c
   a.zero = 0;
   Context& c = ctx();
   const int N = dtype == AG_F32 ? 4 : 2;
-  vec = vec && (n % N == 0);
+  // A chain over fewer elements than one vector (the scalar tail of a loss: -(sum)/n) runs as ONE padded vector: every
+  // array of the chain is 16-byte aligned here, device allocations are at least 256-byte granular, so the lanes beyond
+  // n read and write padding of the arrays' own blocks.  That lets the specialised kernels take it (the interpreter
+  // costs a scattered 0.25 MB switch in instruction fetch for one element).  Not for fused sums (the padding lanes
+  // would be added) and not with row / column operands.
+  if (vec && n < N && !r_out && !a.has_bcast) {
+    a.n = N;
+    a.rows = N;
+  }
+  vec = vec && (a.n % N == 0);
   if (g_fused_static_enabled < 0) {
     const char* e = getenv("AGB_FUSED_STATIC");
     g_fused_static_enabled = (e && e[0] == '0') ? 0 : 1;
@@ -1149,7 +1158,7 @@ static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, c
       a.rlen = r_inner;
     }
   }
-  const int64_t nblk = cdiv(n, (int64_t)a.chunk);
+  const int64_t nblk = cdiv(a.n, (int64_t)a.chunk);
   double* part = nullptr;
   a.tickets = nullptr;
   a.lvl2 = nullptr;
@@ -1176,7 +1185,7 @@ static ag_status fused_impl(int32_t dtype, const int32_t* code, int32_t ncode, c
   if (done) ++g_fused_hits; else ++g_fused_misses;
   if (!done) {
     AG_CHECK(!r_out, AG_EUNSUPPORTED, "ag_ewise_fused_reduce: no specialised kernel for this program");
-    const int64_t items = vec ? n / N : n;
+    const int64_t items = vec ? a.n / N : a.n;
     const unsigned nb = (unsigned)cdiv(items, kThreads);
     if (vec) {
       if (dtype == AG_F32) launch_dynamic<float, true>(nin, ns_need, a, nb, c.stream);
