@@ -432,11 +432,82 @@ static ag_status ternary_dispatch(int which, MapArgs<3>& a) {
   return AG_EUNSUPPORTED;
 }
 
+// ---- special functions with an integer parameter (src/specialfunctions.jl:20,25 besselj / bessely of integer order;
+// :59 polygamma(m, x); :43 invdigamma): not in the unary table (they carry a parameter), so they run as their own
+// pass.  polygamma(m, x) = (-1)^(m+1) m! zeta(m+1, x) with the Hurwitz zeta function by Euler-Maclaurin summation
+// (x > 0; evaluated in double for both eltypes); invdigamma by Newton steps on digamma (Minka's start).
+enum { AG_SP_BESSELJ = 0, AG_SP_BESSELY = 1, AG_SP_POLYGAMMA = 2, AG_SP_INVDIGAMMA = 3 };
+
+__device__ __forceinline__ double hurwitz_zeta(int s, double q) {
+  // sum_{k<N} (q+k)^-s + tail at a = q + N >= 12
+  double sum = 0.0, a = q;
+  while (a < 12.0) { sum += pow(a, -(double)s); a += 1.0; }
+  const double ia = 1.0 / a, ia2 = ia * ia;
+  double t = pow(a, 1.0 - (double)s) / ((double)s - 1.0) + 0.5 * pow(a, -(double)s);
+  // B_2j / (2j)! * s (s+1) ... (s+2j-2) * a^(-s-2j+1)
+  const double B[7] = {1.0 / 6, -1.0 / 30, 1.0 / 42, -1.0 / 30, 5.0 / 66, -691.0 / 2730, 7.0 / 6};
+  double rising = (double)s, fact = 2.0, pw = pow(a, -(double)s - 1.0);
+  for (int j = 1; j <= 7; ++j) {
+    t += B[j - 1] / fact * rising * pw;
+    rising *= ((double)s + 2 * j - 1) * ((double)s + 2 * j);
+    fact *= (2.0 * j + 1) * (2.0 * j + 2);
+    pw *= ia2;
+  }
+  return sum + t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_special_param(int op, int m, const T* __restrict__ x, T* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T v = x[i];
+  T r;
+  if (op == AG_SP_BESSELJ || op == AG_SP_BESSELY) {
+    // negative integer order: f(-m, x) = (-1)^m f(m, x)   (the rule of order 0 asks for order -1)
+    const int am = m < 0 ? -m : m;
+    const T sgn = (m < 0 && (am & 1)) ? T(-1) : T(1);
+    if (op == AG_SP_BESSELJ) r = sizeof(T) == 4 ? (T)jnf(am, (float)v) : (T)jn(am, (double)v);
+    else r = sizeof(T) == 4 ? (T)ynf(am, (float)v) : (T)yn(am, (double)v);
+    r *= sgn;
+  } else if (op == AG_SP_POLYGAMMA) {
+    if (m == 0) r = digamma_<T>(v);
+    else if (m == 1) r = trigamma_<T>(v);
+    else if (!(v > T(0))) r = (T)NAN;                     // reflection for x <= 0 is not implemented
+    else {
+      double f = 1.0;
+      for (int k = 2; k <= m; ++k) f *= k;
+      const double z = hurwitz_zeta(m + 1, (double)v);
+      r = (T)(((m & 1) ? 1.0 : -1.0) * f * z);
+    }
+  } else {                                                // invdigamma
+    double yv = (double)v;
+    double xx = yv >= -2.22 ? exp(yv) + 0.5 : -1.0 / (yv + 0.5772156649015329);
+    for (int it = 0; it < 8; ++it) xx -= ((double)digamma_<double>(xx) - yv) / (double)trigamma_<double>(xx);
+    r = (T)xx;
+  }
+  y[i] = r;
+}
+
 }  // namespace agb
 
 using namespace agb;
 
 extern "C" {
+
+ag_status ag_special_param(int32_t op, int32_t dtype, int32_t m, const void* x, void* y, int64_t n) {
+  AG_REQUIRE_INIT();
+  if (n == 0) return AG_OK;
+  AG_CHECK(x && y && n > 0, AG_EINVAL, "ag_special_param: bad arguments");
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_special_param: dtype %d", dtype);
+  AG_CHECK(op >= AG_SP_BESSELJ && op <= AG_SP_INVDIGAMMA, AG_EUNSUPPORTED, "ag_special_param: op %d", op);
+  AG_CHECK(op != AG_SP_POLYGAMMA || (m >= 0 && m <= 20), AG_EUNSUPPORTED, "ag_special_param: polygamma order %d", m);
+  Context& c = ctx();
+  const unsigned nb = (unsigned)cdiv(n, (int64_t)256);
+  if (dtype == AG_F32) k_special_param<float><<<nb, 256, 0, c.stream>>>(op, m, (const float*)x, (float*)y, n);
+  else k_special_param<double><<<nb, 256, 0, c.stream>>>(op, m, (const double*)x, (double*)y, n);
+  AG_LAUNCHED();
+  return AG_OK;
+}
 
 ag_status ag_unary_fwd(int32_t op, int32_t dtype, const void* x, void* y, int64_t n) {
   AG_REQUIRE_INIT();

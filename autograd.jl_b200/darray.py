@@ -869,6 +869,18 @@ HOST_UNARY = dict(
     relu=lambda x: x if x > 0 else 0 * x, one=lambda x: type(x)(1))
 
 
+SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3)
+
+
+def special_param(name, m, x):
+    """besselj(m, x) / bessely(m, x) of integer order, polygamma(m, x), invdigamma(x) (ag_special_param): one pass."""
+    x = materialize(x)
+    out = DArray.empty(x.shape, x.dtype)
+    if x.size:
+        check(lib.ag_special_param(SP[name], x.dt, int(m), vptr(x), vptr(out), x.size))
+    return out
+
+
 def _special(name):
     """Host Numbers through scipy.special (the SpecialFunctions.jl counterpart); only when actually called."""
     def f(x):

@@ -394,6 +394,42 @@ besselj1 = _unary("besselj1", "besselj1", _no_order2("besselj1"), True, False)
 bessely1 = _unary("bessely1", "bessely1", _no_order2("bessely1"), True, False)
 
 
+# functions with an integer parameter (src/specialfunctions.jl:20,25,43,59): their own pass on the device
+# (ag_special_param); the order is not differentiated (`nothing` in the reference's rules)
+def _int_order(name, a):
+    if isinstance(a, bool) or int(a) != a:
+        raise UnsupportedOnDevice("%s: only integer orders are available on device (got %r)" % (name, a))
+    return int(a)
+
+
+def _sp_fwd(name):
+    def fwd(a, x):
+        if isinstance(x, DArray):
+            return D.special_param(name, _int_order(name, a), x)
+        import scipy.special as sp
+        return float({"besselj": sp.jv, "bessely": sp.yv, "polygamma": sp.polygamma}[name](a, x))
+    return fwd
+
+
+besselj = primitive("besselj", _sp_fwd("besselj"), None,
+                    lambda dy, y, a, x: mul(dy, div(sub(besselj(a - 1, x), besselj(a + 1, x)), 2)))
+bessely = primitive("bessely", _sp_fwd("bessely"), None,
+                    lambda dy, y, a, x: mul(dy, div(sub(bessely(a - 1, x), bessely(a + 1, x)), 2)))
+polygamma = primitive("polygamma", _sp_fwd("polygamma"), None,
+                      lambda dy, y, a, x: unbroadcast(x, mul(dy, polygamma(a + 1, x))))
+
+
+def _invdigamma_fwd(x):
+    if isinstance(x, DArray):
+        return D.special_param("invdigamma", 0, x)
+    import scipy.optimize as so
+    import scipy.special as sp
+    return float(so.newton(lambda t: sp.digamma(t) - x, math.exp(x) + 0.5 if x >= -2.22 else -1.0 / (x + 0.5772156649015329)))
+
+
+invdigamma = primitive("invdigamma", _invdigamma_fwd, lambda dy, y, x: mul(dy, div(1, trigamma(y))))
+
+
 def _copy_fwd(x):
     return D.copy(x) if isinstance(x, DArray) else x
 

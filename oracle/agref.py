@@ -690,6 +690,34 @@ bessely1 = primitive("bessely1", _np(_sp("y1")),
 bessely0 = primitive("bessely0", _np(_sp("y0")), lambda dy, y, x: mul(dy, neg(bessely1(x))))
 
 
+# functions with a (non-differentiated) order: src/specialfunctions.jl:20,25,43,59
+def _sp2(name):
+    def f(a, x):
+        import scipy.special as sp
+        return np.asarray(getattr(sp, name)(a, x), dtype=np.asarray(x).dtype) if isinstance(x, np.ndarray) else float(getattr(sp, name)(a, x))
+    return f
+
+
+besselj = primitive("besselj", _sp2("jv"), None,
+                    lambda dy, y, a, x: mul(dy, div(sub(besselj(a - 1, x), besselj(a + 1, x)), 2)))
+bessely = primitive("bessely", _sp2("yv"), None,
+                    lambda dy, y, a, x: mul(dy, div(sub(bessely(a - 1, x), bessely(a + 1, x)), 2)))
+polygamma = primitive("polygamma", _sp2("polygamma"), None,
+                      lambda dy, y, a, x: unbroadcast(x, mul(dy, polygamma(a + 1, x))))
+
+
+def _invdigamma_np(x):
+    import scipy.special as sp
+    xv = np.asarray(x, dtype=np.float64)
+    t = np.where(xv >= -2.22, np.exp(xv) + 0.5, -1.0 / (xv + 0.5772156649015329))
+    for _ in range(12):
+        t = t - (sp.digamma(t) - xv) / sp.polygamma(1, t)
+    return t.astype(np.asarray(x).dtype) if isinstance(x, np.ndarray) else float(t)
+
+
+invdigamma = primitive("invdigamma", _invdigamma_np, lambda dy, y, x: mul(dy, div(1, trigamma(y))))
+
+
 def _normback(x, p, dy, y):
     """src/linearalgebra.jl:222-238, branch for branch (raw arrays)."""
     if x.size == 0:

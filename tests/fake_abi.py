@@ -425,6 +425,23 @@ class FakeLib:
     def ag_sum_all(self, m, dtype, x, n, out):
         return self.ag_sum_dim(m, dtype, x, 1, n, 1, out)
 
+    def ag_special_param(self, op, dtype, m, x, y, n):
+        import scipy.special as sp
+        self.launches += 1
+        T = _DT[dtype]
+        v = _arr(x, n, T).astype(np.float64)
+        if op == 0: r = sp.jv(m, v)
+        elif op == 1: r = sp.yv(m, v)
+        elif op == 2: r = sp.polygamma(m, v)
+        elif op == 3:
+            r = np.where(v >= -2.22, np.exp(v) + 0.5, -1.0 / (v + 0.5772156649015329))
+            for _ in range(12):
+                r = r - (sp.digamma(r) - v) / sp.polygamma(1, r)
+        else:
+            return self._fail(5, "ag_special_param: op")
+        _arr(y, n, T)[:] = r.astype(T)
+        return 0
+
     def ag_sum_dim_batch(self, m, dtype, n, xs, inner, red, outer, outs):
         for k in range(n):
             st = self.ag_sum_dim(m, dtype, xs[k], inner, red, outer, outs[k])

@@ -355,3 +355,40 @@ def test_fused_expression_evaluator_rejects_bad_programs(ag):
         code = (C.c_int32 * len(prog))(*prog)
         st = lib.ag_ewise_vm(out.dt, code, len(prog), consts, 1, 1, ptrs, modes, imms, out.ptr, 8)
         assert st != 0, prog
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-5), (np.float64, 2e-11)])
+def test_special_functions_with_an_integer_parameter(ag, dtype, tol):
+    """besselj(m, x), bessely(m, x) of integer order, polygamma(m, x), invdigamma(x) (ag_special_param) against
+    scipy.special, and their gradients (src/specialfunctions.jl:20,25,43,59) against the closed forms."""
+    import scipy.special as sp
+    rng = np.random.default_rng(17)
+    x = rng.uniform(0.3, 25.0, 4001).astype(dtype)
+    xd = ag.DArray.from_numpy(x)
+    x64 = x.astype(np.float64)
+
+    def close(got, ref, t=tol):
+        return np.max(np.abs(got.astype(np.float64) - ref)) <= t * max(np.max(np.abs(ref)), 1.0)
+    for m in (-1, 0, 1, 2, 5):
+        assert close(ag.besselj(m, xd).to_numpy(), sp.jv(m, x64)), ("besselj", m)
+    for m in (0, 1, 3):
+        assert close(ag.bessely(m, xd).to_numpy(), sp.yv(m, x64), tol * 20), ("bessely", m)
+    for m in (0, 1, 2, 3, 6):
+        ref = sp.polygamma(m, x64)
+        got = ag.polygamma(m, xd).to_numpy().astype(np.float64)
+        floor = 1.0 if m <= 1 else 1e-30                  # digamma crosses zero: absolute there, relative elsewhere
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor)) <= (5e-6 if dtype == np.float32 else 1e-10), ("polygamma", m)
+    y = rng.uniform(-3.0, 4.0, 2001).astype(dtype)
+    inv = ag.invdigamma(ag.DArray.from_numpy(y)).to_numpy().astype(np.float64)
+    assert np.max(np.abs(sp.digamma(inv) - y.astype(np.float64))) <= (2e-5 if dtype == np.float32 else 1e-11)
+    # gradients
+    g = ag.grad(lambda v: ag.sum_(ag.besselj(2, v)))(xd).to_numpy()
+    assert close(g, (sp.jv(1, x64) - sp.jv(3, x64)) / 2)
+    g = ag.grad(lambda v: ag.sum_(ag.polygamma(1, v)))(xd).to_numpy().astype(np.float64)
+    ref = sp.polygamma(2, x64)
+    assert np.max(np.abs(g - ref) / np.maximum(np.abs(ref), 1e-30)) <= (5e-6 if dtype == np.float32 else 1e-10)
+    yd = ag.DArray.from_numpy(y)
+    g = ag.grad(lambda v: ag.sum_(ag.invdigamma(v)))(yd).to_numpy().astype(np.float64)
+    assert np.max(np.abs(g * sp.polygamma(1, inv) - 1.0)) <= (1e-4 if dtype == np.float32 else 1e-9)
+    with pytest.raises(ag.UnsupportedOnDevice):
+        ag.besselj(0.5, xd)

@@ -317,3 +317,19 @@ def test_timer_labels_follow_the_reference(hostlib):
     assert "[3]sum(abs2,·)[1]" in rows and "[3]addto![1]" in rows
     assert "[2]*[1]" in rows and "[2]addto![1]" in rows
     assert all(r[1] == 1 for r in rows.values())
+
+
+def test_parametrised_special_functions_host_rules(hostlib, oracle):
+    """besselj / bessely / polygamma / invdigamma: the host rules on the numpy stand-in against the oracle's."""
+    ag = hostlib
+    rng = np.random.default_rng(23)
+    x = rng.uniform(0.5, 9.0, (6, 5))
+    xd = ag.DArray.from_numpy(np.asfortranarray(x))
+    for name, m in (("besselj", 2), ("bessely", 1), ("polygamma", 1), ("polygamma", 3)):
+        go = oracle.grad(lambda v: oracle.sum_(getattr(oracle, name)(m, v)))(np.asfortranarray(x))
+        gd = ag.grad(lambda v: ag.sum_(getattr(ag, name)(m, v)))(xd).to_numpy()
+        assert np.allclose(gd, go, rtol=1e-10, atol=1e-12), (name, m)
+    y = rng.uniform(-2.0, 3.0, (4, 3))
+    go = oracle.grad(lambda v: oracle.sum_(oracle.invdigamma(v)))(np.asfortranarray(y))
+    gd = ag.grad(lambda v: ag.sum_(ag.invdigamma(v)))(ag.DArray.from_numpy(np.asfortranarray(y))).to_numpy()
+    assert np.allclose(gd, go, rtol=1e-8, atol=1e-10)
