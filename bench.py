@@ -129,7 +129,7 @@ class Clocks:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def bind_to_gpu_numa(local_rank, world):
+def bind_to_gpu_numa(local_rank, world, dev=None, stride=1):
     """Bind this rank's host threads to the CPUs local to its GPU (NVML's affinity mask = the GPU's NUMA node),
     split evenly among the ranks that share that mask, before any pinned staging buffer is allocated: the pages
     are then first-touched on the GPU's own node and the ranks' host loops do not migrate.  (Round 1: 8 ranks
@@ -138,7 +138,8 @@ def bind_to_gpu_numa(local_rank, world):
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        dev = local_rank if dev is None else dev
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev)
         ncpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
@@ -147,7 +148,7 @@ def bind_to_gpu_numa(local_rank, world):
             peers = []          # local ranks sharing this mask
             for r in range(world):
                 try:
-                    hw = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r), (ncpu + 63) // 64)
+                    hw = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r * stride), (ncpu + 63) // 64)
                     if list(hw) == list(words):
                         peers.append(r)
                 except Exception:
@@ -234,12 +235,29 @@ def main():
     K = args.steps
     B = args.batch
 
-    affinity = bind_to_gpu_numa(local, world)     # before any pinned allocation (first touch = this rank's node)
+    # Which GPU this rank drives.  With more GPUs visible than ranks (the driver's scaling run shows all eight at every
+    # N) the ranks are spread evenly over the box (N = 4: GPUs 0, 2, 4, 6) instead of packed onto the first N: the
+    # host-to-device paths are shared between neighbouring GPUs on this box (measured: 4 ranks on GPUs 0-3 get 28 GB/s
+    # each, 2 ranks 54 GB/s each), and NVSwitch makes every pair equally close for the allreduce.  AGB_SPREAD_DEVICES=0
+    # packs them (device = LOCAL_RANK).
+    dev, ndev, stride = local, None, 1
+    if world > 1 and os.environ.get("AGB_SPREAD_DEVICES", "1") != "0":
+        try:
+            import torch
+            ndev = torch.cuda.device_count()
+            if ndev > world and ndev % world == 0:
+                stride = ndev // world
+                dev = local * stride
+        except Exception:      # noqa: BLE001
+            pass
+    affinity = bind_to_gpu_numa(local, world, dev, stride)     # before any pinned allocation (first touch = this rank's node)
+    affinity["device"] = dev
+    affinity["visible_devices"] = ndev
     import __graft_entry__ as ge
     ag = ge.load_package()
-    ag.init(local)
+    ag.init(dev)
     Wl = ag.workloads
-    clocks = Clocks(local) if rank == 0 else None        # started early: nvidia-smi needs about a second before its first sample
+    clocks = Clocks(dev) if rank == 0 else None          # started early: nvidia-smi needs about a second before its first sample
 
     dist = None
     if world > 1:
