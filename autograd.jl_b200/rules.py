@@ -175,6 +175,12 @@ def _addto_fwd(a, b):
         assert a.shape == b.container.shape, "addto!: accumulator does not match the Sparse container"
         return b.addto_dense(a, inplace=not recording())   # copy first under an outer tape (:93)
     if isinstance(a, DArray) and isinstance(b, DArray):
+        if a.tr and b.tr and a.shape == b.shape and a.ndim == 2:
+            # two lazy adjoints (the gradients that reach an `adjoint` node's parent under an outer tape): a' + b' =
+            # (a + b)', one pass over the stored arrays instead of two materialised transposes and a sum
+            sa = DArray(a.buf, a.ptr, (a.shape[1], a.shape[0]), a.dtype)
+            sb = DArray(b.buf, b.ptr, (b.shape[1], b.shape[0]), b.dtype)
+            return D.adjoint(D.add(sa, sb))
         return D.add(a, b)                 # out of place: rules may alias dy (src/addto.jl:23)
     if isinstance(a, DArray) or isinstance(b, DArray):
         arr, num = (a, b) if isinstance(a, DArray) else (b, a)
