@@ -261,6 +261,9 @@ def main():
 
     dist = None
     if world > 1:
+        # NCCL's version banner goes to stdout (the image sets NCCL_DEBUG=VERSION): keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("gloo", rank=rank, world_size=world)
 
