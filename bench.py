@@ -261,9 +261,6 @@ def main():
 
     dist = None
     if world > 1:
-        # NCCL's version banner goes to stdout (the image sets NCCL_DEBUG=VERSION): keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("gloo", rank=rank, world_size=world)
 
@@ -276,7 +273,21 @@ def main():
             dist.all_gather_object(out, payload)
             return out
         use_p2p = os.environ.get("AGB_ALLREDUCE", "p2p") == "p2p"      # AGB_ALLREDUCE=nccl forces the NCCL path
-        dp = ag.DataParallel(rank, world, bcast, allgather if use_p2p else None)
+        # NCCL prints its version banner on the C stdout while the communicator is created: point fd 1 at stderr for
+        # that call (and flush the C buffer before switching back), so that stdout carries the one JSON line only
+        import ctypes as _ct
+        sys.stdout.flush()
+        _saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dp = ag.DataParallel(rank, world, bcast, allgather if use_p2p else None)
+        finally:
+            try:
+                _ct.CDLL(None).fflush(None)
+            except Exception:      # noqa: BLE001
+                pass
+            os.dup2(_saved, 1)
+            os.close(_saved)
         dist.barrier()
     else:
         dp = ag.DataParallel(0, 1)
