@@ -201,6 +201,18 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
                "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
+// tanh / sigm as CALLED functions for the unrolled epilogue loops: inlined, 64 copies of a 30-40 instruction sequence
+// are a 40 KB store path that runs once per tile -- paid for in instruction fetch (config 4 with the gate products
+// not split along K: +25 us per launch).  Same expressions as U<>::f, so the values do not change.
+__device__ __noinline__ float tc_tanh_call(float z) { return U<AG_U_TANH, float>::f(z); }
+__device__ __noinline__ float tc_sigm_call(float z) { return U<AG_U_SIGM, float>::f(z); }
+template <int ACT>
+__device__ __forceinline__ float tc_activation_compact(float z) {
+  if (ACT == TC_ACT_RELU) return relu(z);
+  if (ACT == TC_ACT_TANH) return tc_tanh_call(z);
+  if (ACT == TC_ACT_SIGM) return tc_sigm_call(z);
+  return z;
+}
 template <int ACT>
 __device__ __forceinline__ float tc_activation(float z) {
   if (ACT == TC_ACT_RELU) return relu(z);     // max.(0, z): same values as the FMax map jmax(0, z) of ewise_ops.cuh
@@ -226,7 +238,7 @@ __device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int6
       for (int e = 0; e < 8; ++e) {
         z[e] = p.alpha == 1.0f ? v[j + e] : __fmul_rn(p.alpha, v[j + e]);
         if (p.bias) z[e] = __fadd_rn(z[e], __ldg(p.bias + nn0 + j + e));
-        a[e] = tc_activation<ACT>(z[e]);
+        a[e] = tc_activation_compact<ACT>(z[e]);
       }
       if (dst2) {
         st_global_v8(dst + j, z);
@@ -246,7 +258,7 @@ __device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int6
       for (int e = 0; e < 4; ++e) {
         z[e] = p.alpha == 1.0f ? v[j + e] : __fmul_rn(p.alpha, v[j + e]);
         if (p.bias) z[e] = __fadd_rn(z[e], __ldg(p.bias + nn0 + j + e));
-        a[e] = tc_activation<ACT>(z[e]);
+        a[e] = tc_activation_compact<ACT>(z[e]);
       }
       if (dst2) {
         *reinterpret_cast<float4*>(dst + j) = make_float4(z[0], z[1], z[2], z[3]);
@@ -282,7 +294,7 @@ __device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int6
       if (j < nvalid) {
         float z = scale ? __fmul_rn(alpha, v[j]) : v[j];
         if (hb) z = __fadd_rn(z, b);
-        const float a = tc_activation<ACT>(z);
+        const float a = tc_activation_compact<ACT>(z);
         if (dst2) {
           *dst = z;
           *dst2 = a;
@@ -307,7 +319,7 @@ __device__ __forceinline__ void tc_store_row(const TcParams& p, int64_t mm, int6
       if (j < nvalid) {
         float z = scale ? __fmul_rn(alpha, v[j]) : v[j];
         if (hb) z = __fadd_rn(z, __ldg(bias + j));
-        const float a = tc_activation<ACT>(z);
+        const float a = tc_activation_compact<ACT>(z);
         if (dst2) {
           dst[j] = z;
           dst2[j] = a;
