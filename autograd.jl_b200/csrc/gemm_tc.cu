@@ -55,7 +55,8 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   //  8 KB
 constexpr int TC_RAW_BYTES = TC_A_BYTES + TC_B_BYTES;          // TMA stage: A and B as loaded (fp32)
 constexpr int TC_SPLIT_WARPS = 8;
-constexpr int TC_THREADS = 14 * 32;
+constexpr int TC_THREADS = 15 * 32;
+constexpr int TC_MMA2_WARP = 14;               // second MMA issuer (FLUSH = 1 kernels only)
 constexpr int TC_EPI_WARP0 = 10;                // warps 10..13
 constexpr int TC_NBARS = 3 * TC_STAGES + 4;
 constexpr int TC_SMEM_DATA = TC_STAGES * (TC_RAW_BYTES + TC_B_BYTES);
@@ -93,6 +94,21 @@ struct TcGroup {
   int work_start[TC_GROUP_MAX + 1];     // prefix sums of the problems' work items (tiles * splits)
   int nprob;
 };
+
+#ifdef AGB_TC_TRACE
+// Experiment build (tools/build_variant.sh ... "-DAGB_TC_TRACE"): block 0 records globaltimer stamps per k-block and
+// role: [0] producer issued the loads, [1] splitter saw the data, [2] splitter done, [3] MMA issued, [4] epilogue saw the
+// partial, [5] epilogue released the accumulator.  Read back with ag_gemm_trace (tests/probe_tc_trace.py).
+__device__ unsigned long long g_tc_trace[6][256];
+__device__ __forceinline__ unsigned long long tc_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_TRACE(ROLE, IDX) do { if (blockIdx.x == 0 && (IDX) < 256) g_tc_trace[ROLE][IDX] = tc_now(); } while (0)
+#else
+#define TC_TRACE(ROLE, IDX) do { } while (0)
+#endif
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -403,6 +419,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===== TMA producer (warp-uniform; one elected lane issues) =====
     int s = 0;
     uint32_t ph = 0;
+    int tr_i = 0;
+    (void)tr_i;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int q, mt, nt, kb0, kb1;
       decode(w, q, mt, nt, kb0, kb1);
@@ -434,11 +452,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
         __syncwarp();
+        if (lane == 0) TC_TRACE(0, tr_i);
+        ++tr_i;
         if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (FLUSH == 1 && warp == TC_MMA2_WARP)) {
     // ===== MMA issuer (warp-uniform; one elected lane issues) =====
+    // When the partial is promoted every k-block (FLUSH = 1) TWO warps issue, one per accumulator: warp 1 takes the
+    // even k-blocks (accumulator 0), warp 14 the odd ones (accumulator 1).  Measured with the k-block trace of the
+    // experiment build (round 2): one issuer needs 480 ns per k-block -- 200 ns blocked in the 12 tcgen05.mma (the
+    // issue of an MMA waits for the pipe) and 280 ns of barrier waits, fences, descriptors and commits during which
+    // the tensor pipe idles; with two issuers one warp's overhead runs under the other's MMAs.  No accumulator is
+    // shared between the issuers, so the order of the additions (and every bit of the result) is unchanged.
+    constexpr bool TWO = FLUSH == 1;
+    const int me = warp == 1 ? 0 : 1;
     // instruction descriptor: D=f32, A=B=tf32, A K-major (TMEM), B major, N, M
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_KMAJOR ? 0u : 1u) << 16) |
                            ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -452,12 +480,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t desc_lo_blo = ((blo_base >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
     int s = 0, ci = 0;   // stage, chunk counter (selects the TMEM accumulator)
     uint32_t ph = 0;
+    int tr_i = 0;
+    (void)tr_i;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int q, mt, nt, kb0, kb1;
       decode(w, q, mt, nt, kb0, kb1);
       for (int kc0 = kb0; kc0 < kb1; kc0 += FLUSH, ++ci) {
         const int kc1 = min(kc0 + FLUSH, kb1);
         const int acc = ci & 1;
+        const bool mine = !TWO || acc == me;
+        if (!mine) {                       // the other issuer's k-block: only the stage bookkeeping advances
+          if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+          ++tr_i;
+          continue;
+        }
         mbar_wait(tempty(acc), ((ci >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_BN;
@@ -487,6 +523,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             umma_commit(bar_e);               // stage (smem + TMEM) reusable when these MMAs retire
           }
           __syncwarp();
+          if (lane == 0) TC_TRACE(3, tr_i);
+          ++tr_i;
           if (++s == TC_STAGES) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit(tfull(acc));        // chunk partial complete
@@ -504,11 +542,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int row = lq * 32 + lane;             // tile row
     int s = 0;
     uint32_t ph = 0;
+    int tr_i = 0;
+    (void)tr_i;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int q, mt, nt, kb0, kb1;
       decode(w, q, mt, nt, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(s), ph);
+        if (threadIdx.x == 64) TC_TRACE(1, tr_i);
         tc_fence_after();                   // order the TMEM stores below after the stage hand-over
         const uint8_t* rawA = smem_gen + s * TC_RAW_BYTES;
         uint32_t v[16];
@@ -552,6 +593,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready_bar(s));
+        if (threadIdx.x == 64) TC_TRACE(2, tr_i);
+        ++tr_i;
         if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -570,6 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int kc0 = kb0; kc0 < kb1; kc0 += FLUSH, ++ci) {
         const int acc = ci & 1;
         mbar_wait(tfull(acc), (ci >> 1) & 1);
+        if (threadIdx.x == TC_EPI_WARP0 * 32) TC_TRACE(4, ci);
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
@@ -582,6 +626,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(acc));
+        if (threadIdx.x == TC_EPI_WARP0 * 32) TC_TRACE(5, ci);
       }
       // rows beyond the tile pitch belong to the next tile (which computes them itself)
       const int64_t mm = r_loc < p.mm_pitch ? (int64_t)mt * p.mm_pitch + r_loc : p.MM;
@@ -951,6 +996,13 @@ ag_status gemm_tc_group(int n, const TcJob* jobs) {
   }
   return AG_OK;
 }
+
+#ifdef AGB_TC_TRACE
+extern "C" int ag_gemm_trace(unsigned long long* out) {      // 6 x 256 stamps of the last launch's block 0
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 6 * 256) == cudaSuccess ? 0 : 3;
+}
+#endif
 
 ag_status gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha, const void* A,
                   int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc,
