@@ -998,6 +998,109 @@ ag_status gemm_tc_group(int n, const TcJob* jobs) {
 }
 
 #ifdef AGB_TC_TRACE
+// ---- experiment (trace build only): how fast can ONE SM take data in?  Every CTA streams 16 KB "A" tiles of a large
+// array by TMA through a 6-stage ring (as the product does) and, per tile, 8 KB of a small L2-resident "B" array
+//   mode 0: not at all      mode 1: by TMA into the same stage      mode 2: by 256 threads with ld.global -> st.shared
+// Reports ns per tile (block 0, %globaltimer).  tests/probe_tc_ingest.py.
+__global__ void __launch_bounds__(320, 1)
+    k_ingest(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ Bg,
+             int mode, int tiles_per_cta, int pattern, unsigned long long* out_ns) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int ST = 6, SB = 24576;
+  const uint32_t bars = smem_base + ST * SB;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (ST + s); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned long long t0 = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < tiles_per_cta; ++i) {
+      mbar_wait(empty(s), ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(full(s), 16384 + (mode == 1 ? 8192 : 0));
+        if (pattern == 0)       // 16 KB contiguous
+          tma_load_2d(smem_base + s * SB, &tmA, full(s), 0, (blockIdx.x * tiles_per_cta + i) * 128);
+        else                    // the layout of w1*x: 128 rows of 128 B at a 3136-byte pitch, 24 k-blocks per 128-row tile
+          tma_load_2d(smem_base + s * SB, &tmA, full(s), (i % 24) * 32, (blockIdx.x * (tiles_per_cta / 24) + i / 24) * 128);
+        if (mode == 1) tma_load_2d(smem_base + s * SB + 16384, &tmB, full(s), 0, (i % 8) * 64);
+      }
+      __syncwarp();
+      if (++s == ST) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= 2) {                    // 8 consumer warps (256 threads)
+    const int tid = threadIdx.x - 64;
+    int s = 0;
+    uint32_t ph = 0;
+    float acc = 0.f;
+    float4 pre[2];
+    if (mode == 2) {
+      pre[0] = __ldg(reinterpret_cast<const float4*>(Bg) + tid);
+      pre[1] = __ldg(reinterpret_cast<const float4*>(Bg) + tid + 256);
+    }
+    for (int i = 0; i < tiles_per_cta; ++i) {
+      mbar_wait(full(s), ph);
+      const float4* a4 = reinterpret_cast<const float4*>(smem_gen + s * SB);
+      float4 v = a4[tid], w = a4[tid + 256], u = a4[tid + 512], x = a4[tid + 768];      // read the 16 KB
+      acc += v.x + w.y + u.z + x.w;
+      if (mode == 2) {
+        float4* b4 = reinterpret_cast<float4*>(smem_gen + s * SB + 16384);
+        b4[tid] = pre[0];
+        b4[tid + 256] = pre[1];
+        const float4* src = reinterpret_cast<const float4*>(Bg) + (size_t)(((i + 1) % 8) * 512);
+        pre[0] = __ldg(src + tid);
+        pre[1] = __ldg(src + tid + 256);
+      } else if (mode == 1) {
+        const float4* b4 = reinterpret_cast<const float4*>(smem_gen + s * SB + 16384);
+        acc += b4[tid].x + b4[tid + 256].y;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty(s));
+      if (++s == ST) { s = 0; ph ^= 1; }
+    }
+    if (acc == 123.456f) out_ns[1] = 1;       // keep the reads
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    out_ns[0] = t1 - t0;
+  }
+}
+
+extern "C" int ag_debug_ingest(int mode, int tiles_per_cta, int pattern, const void* A, long long rowsA, const void* B,
+                               double* ns_per_tile) {
+  Context& c = ctx();
+  CUtensorMap ma, mb;
+  // A: rowsA rows of 32 floats (K-major rows, 128 B each, contiguous); B: 512 rows of 32 floats
+  const int kA = pattern == 0 ? 32 : 784;
+  if (!make_map(&ma, A, kA, rowsA, kA, 32, 128, true) || !make_map(&mb, B, 32, 512, 32, 32, 64, true)) return 3;
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, 16) != cudaSuccess) return 2;
+  cudaMemset(d, 0, 16);
+  cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 24576 + 2048);
+  const int grid = c.num_sms;
+  for (int rep = 0; rep < 3; ++rep)
+    k_ingest<<<grid, 320, 6 * 24576 + 2048, c.stream>>>(ma, mb, (const float*)B, mode, tiles_per_cta, pattern, d);
+  unsigned long long h[2] = {0, 0};
+  cudaStreamSynchronize(c.stream);
+  cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  *ns_per_tile = (double)h[0] / tiles_per_cta;
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+#endif
+
+#ifdef AGB_TC_TRACE
 extern "C" int ag_gemm_trace(unsigned long long* out) {      // 6 x 256 stamps of the last launch's block 0
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 6 * 256) == cudaSuccess ? 0 : 3;
