@@ -436,7 +436,8 @@ static ag_status ternary_dispatch(int which, MapArgs<3>& a) {
 // :59 polygamma(m, x); :43 invdigamma): not in the unary table (they carry a parameter), so they run as their own
 // pass.  polygamma(m, x) = (-1)^(m+1) m! zeta(m+1, x) with the Hurwitz zeta function by Euler-Maclaurin summation
 // (x > 0; evaluated in double for both eltypes); invdigamma by Newton steps on digamma (Minka's start).
-enum { AG_SP_BESSELJ = 0, AG_SP_BESSELY = 1, AG_SP_POLYGAMMA = 2, AG_SP_INVDIGAMMA = 3 };
+enum { AG_SP_BESSELJ = 0, AG_SP_BESSELY = 1, AG_SP_POLYGAMMA = 2, AG_SP_INVDIGAMMA = 3, AG_SP_DAWSON = 4, AG_SP_ERFI = 5,
+       AG_SP_AIRYAI = 6, AG_SP_AIRYAIPRIME = 7, AG_SP_AIRYBI = 8, AG_SP_AIRYBIPRIME = 9, AG_SP_COUNT = 10 };
 
 __device__ __forceinline__ double hurwitz_zeta(int s, double q) {
   // sum_{k<N} (q+k)^-s + tail at a = q + N >= 12
@@ -454,6 +455,137 @@ __device__ __forceinline__ double hurwitz_zeta(int s, double q) {
     pw *= ia2;
   }
   return sum + t;
+}
+
+
+// ---- dawson / erfi / Airy functions (src/specialfunctions.jl:5-8,33,39): CUDA's math library has none of them.
+// All evaluated in double for both eltypes.
+//  dawson: Rybicki's sampling sum, F(x) = pi^-1/2 sum_{n odd} exp(-(x - n h)^2) / n with h = 0.2 (sampling error
+//          exp(-(pi/2h)^2) ~ 1e-27), Maclaurin series below 0.2, asymptotic series above 100.
+//  erfi:   2/sqrt(pi) exp(x^2) dawson(x).
+//  Airy:   Maclaurin series for |x| < 2; beyond, the Laplace-type integral (DLMF 9.5.8)
+//            Ai(z) = exp(-zeta) zeta^-1/6 / (sqrt(pi) 48^1/6 Gamma(5/6)) int_0^inf exp(-t) t^-1/6 (2 + t/zeta)^-1/6 dt
+//          by generalised Gauss-Laguerre quadrature (alpha = -1/6, 40-point rule, nodes with weight > 1e-22 kept), its
+//          derivative from the same nodes; for x < 0 one complex evaluation A = Ai(|x| e^{i pi/3}) gives all four
+//          functions through the connection formulas Ai(-z) = 2 Re[e^{i pi/3} A], Bi(-z) = 2 Re[e^{-i pi/6} A];
+//          Bi, Bi' for x > 0: the series (all terms positive) up to 8.5, the asymptotic expansion (DLMF 9.7.7-8) above.
+constexpr int kAiryNQ = 28;
+__constant__ double kAiryT[kAiryNQ] = {
+    2.83891417994567609e-02, 1.70985378860034898e-01, 4.35871678341770485e-01, 8.23518257913030904e-01,
+    1.33452543254227374e+00, 1.96968293206435074e+00, 2.72998134002859949e+00, 3.61662161916100899e+00,
+    4.63102611052654112e+00, 5.77485171830547639e+00, 7.05000568630218716e+00, 8.45866437513237734e+00,
+    1.00032955242749395e+01, 1.16866845947722418e+01, 1.35119659344693552e+01, 1.54826596959377145e+01,
+    1.76027156808069130e+01, 1.98765656022785429e+01, 2.23091856773962789e+01, 2.49061720212974187e+01,
+    2.76738320739497183e+01, 3.06192963295084120e+01, 3.37506560850239978e+01, 3.70771349708391185e+01,
+    4.06093049694341346e+01, 4.43593619516066724e+01, 4.83414822434528233e+01, 5.25722917078504892e+01};
+__constant__ double kAiryW[kAiryNQ] = {
+    1.43720408803314909e-01, 2.30407559241880361e-01, 2.42253045521327898e-01, 2.03636639103440736e-01,
+    1.43760630622921298e-01, 8.69128834706077852e-02, 4.54175001832914579e-02, 2.06118031206068975e-02,
+    8.14278821268601093e-03, 2.80266075663376368e-03, 8.40337441621719040e-04, 2.19303732907765277e-04,
+    4.97401659009251131e-05, 9.78508095920972090e-06, 1.66542824603694159e-06, 2.44502736799656883e-07,
+    3.08537034236218771e-08, 3.33296072937279380e-09, 3.06781892365377496e-10, 2.39331309909008319e-11,
+    1.57294707676285316e-12, 8.64936013017882508e-14, 3.94819816700652301e-15, 1.48271173048109927e-16,
+    4.53390374815054902e-18, 1.11547980452036191e-19, 2.17766660589229045e-21, 3.31878891057973789e-23};
+
+__device__ double dawson_(double x) {
+  const double ax = fabs(x);
+  if (ax < 0.2) {
+    const double x2 = x * x;
+    return x * (1.0 - 2.0 / 3 * x2 * (1.0 - 2.0 / 5 * x2 * (1.0 - 2.0 / 7 * x2 * (1.0 - 2.0 / 9 * x2 * (1.0 - 2.0 / 11 * x2 *
+               (1.0 - 2.0 / 13 * x2 * (1.0 - 2.0 / 15 * x2)))))));
+  }
+  if (!(ax <= 100.0)) {        // also NaN
+    const double i2 = 1.0 / (2.0 * x * x);
+    return (1.0 / (2.0 * x)) * (1.0 + i2 * (1.0 + 3.0 * i2 * (1.0 + 5.0 * i2 * (1.0 + 7.0 * i2))));
+  }
+  const double H = 0.2;
+  const int n0 = 2 * (int)(0.5 * ax / H + 0.5);
+  const double xp = ax - n0 * H;
+  double e1 = exp(2.0 * xp * H);
+  const double e2 = e1 * e1;
+  double d1 = n0 + 1.0, d2 = d1 - 2.0, s = 0.0;
+  for (int i = 0; i < 18; ++i) {
+    const double a = (2 * i + 1) * H;
+    s += exp(-a * a) * (e1 / d1 + 1.0 / (d2 * e1));
+    d1 += 2.0; d2 -= 2.0; e1 *= e2;
+  }
+  const double r = 0.56418958354775628695 * exp(-xp * xp) * s;
+  return x < 0.0 ? -r : r;
+}
+
+struct Cx { double re, im; };
+__device__ __forceinline__ Cx cmul(Cx a, Cx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cx cpolar(double r, double th) { double s, c; sincos(th, &s, &c); return {r * c, r * s}; }
+
+// out[0..3] = Ai, Ai', Bi, Bi' at x
+__device__ void airy_all(double x, double* out) {
+  const double C1 = 0.355028053887817239, C2 = 0.258819403792806798, SQ3 = 1.7320508075688772935;
+  const double CQ = 0.26218399708832302;           // 1 / (sqrt(pi) 48^(1/6) Gamma(5/6))
+  const double ISP = 0.56418958354775628695;       // 1 / sqrt(pi)
+  const double PI = 3.14159265358979323846;
+  if (x != x) { out[0] = out[1] = out[2] = out[3] = x; return; }
+  const bool series = (x > -2.0 && x < 2.0);
+  if (series || (x >= 2.0 && x <= 8.5)) {
+    const double x3 = x * x * x;
+    double a = 1.0, f = 1.0, b = x, g = x, ck = 0.5 * x * x, fp = ck, d = 1.0, gp = 1.0;
+    for (int k = 0; k < 120; ++k) {
+      a *= x3 / ((3.0 * k + 2) * (3.0 * k + 3)); f += a;
+      b *= x3 / ((3.0 * k + 3) * (3.0 * k + 4)); g += b;
+      if (k > 0) { ck *= x3 / ((3.0 * k) * (3.0 * k + 2)); fp += ck; }
+      d *= x3 / ((3.0 * k + 1) * (3.0 * k + 3)); gp += d;
+      if (k > 2 && fabs(a) < 1e-17 * fabs(f) && fabs(b) <= 1e-17 * fabs(g) && fabs(d) < 1e-17 * fabs(gp)) break;
+    }
+    out[2] = SQ3 * (C1 * f + C2 * g);
+    out[3] = SQ3 * (C1 * fp + C2 * gp);
+    if (series) { out[0] = C1 * f - C2 * g; out[1] = C1 * fp - C2 * gp; return; }
+  }
+  if (x >= 2.0) {
+    const double sx = sqrt(x), z = (2.0 / 3) * x * sx;
+    double I = 0.0, J = 0.0;
+    for (int j = 0; j < kAiryNQ; ++j) {
+      const double w = 2.0 + kAiryT[j] / z, p = pow(w, -1.0 / 6);
+      I += kAiryW[j] * p;
+      J += kAiryW[j] * kAiryT[j] * p / w;
+    }
+    const double pre = CQ * exp(-z) * pow(z, -1.0 / 6);
+    out[0] = pre * I;
+    out[1] = pre * sx * (-I - I / (6.0 * z) + J / (6.0 * z * z));
+    if (x > 8.5) {                                  // Bi, Bi': asymptotic expansion
+      double u = 1.0, su = 1.0, sv = 1.0;
+      for (int k = 0; k < 40; ++k) {
+        const double un = u * ((6.0 * k + 5) * (6.0 * k + 3) * (6.0 * k + 1)) / (216.0 * (k + 1) * (2.0 * k + 1)) / z;
+        if (fabs(un) > fabs(u)) break;
+        u = un;
+        su += u;
+        sv += u * (6.0 * (k + 1) + 1) / (1.0 - 6.0 * (k + 1));
+        if (fabs(u) < 1e-17) break;
+      }
+      const double q = sqrt(sx), ez = exp(z);
+      out[2] = ISP * ez / q * su;
+      out[3] = ISP * ez * q * sv;
+    }
+    return;
+  }
+  // x <= -2: A = Ai(Z), Z = |x| e^{i pi/3}, zeta = i zr
+  const double zz = -x, sz = sqrt(zz), zr = (2.0 / 3) * zz * sz;
+  Cx I = {0.0, 0.0}, J = {0.0, 0.0};
+  for (int j = 0; j < kAiryNQ; ++j) {
+    const double im = -kAiryT[j] / zr, r2 = 4.0 + im * im, th = atan2(im, 2.0);
+    const Cx p = cpolar(pow(r2, -1.0 / 12), -th / 6);                 // w^(-1/6)
+    const Cx q = cmul(p, Cx{2.0 / r2, -im / r2});                     // w^(-7/6)
+    I.re += kAiryW[j] * p.re; I.im += kAiryW[j] * p.im;
+    const double wt = kAiryW[j] * kAiryT[j];
+    J.re += wt * q.re; J.im += wt * q.im;
+  }
+  const Cx pre = cpolar(CQ * pow(zr, -1.0 / 6), -zr - PI / 12);       // C e^{-i zr} zeta^(-1/6)
+  const Cx A = cmul(pre, I);
+  // -I - I/(6 zeta) + J/(6 zeta^2), zeta = i zr
+  const Cx br = {-I.re - I.im / (6.0 * zr) - J.re / (6.0 * zr * zr), -I.im + I.re / (6.0 * zr) - J.im / (6.0 * zr * zr)};
+  const Cx Ap = cmul(cmul(pre, cpolar(sz, PI / 6)), br);
+  out[0] = 2.0 * cmul(cpolar(1.0, PI / 3), A).re;
+  out[2] = 2.0 * cmul(cpolar(1.0, -PI / 6), A).re;
+  out[1] = -2.0 * cmul(cpolar(1.0, 2 * PI / 3), Ap).re;
+  out[3] = -2.0 * cmul(cpolar(1.0, PI / 6), Ap).re;
 }
 
 template <typename T>
@@ -479,6 +611,15 @@ __global__ void __launch_bounds__(256) k_special_param(int op, int m, const T* _
       const double z = hurwitz_zeta(m + 1, (double)v);
       r = (T)(((m & 1) ? 1.0 : -1.0) * f * z);
     }
+  } else if (op == AG_SP_DAWSON) {
+    r = (T)dawson_((double)v);
+  } else if (op == AG_SP_ERFI) {                          // 2/sqrt(pi) exp(x^2) dawson(x)
+    const double xv = (double)v;
+    r = (T)(1.12837916709551257390 * exp(xv * xv) * dawson_(xv));
+  } else if (op >= AG_SP_AIRYAI && op <= AG_SP_AIRYBIPRIME) {
+    double o[4];
+    airy_all((double)v, o);
+    r = (T)o[op - AG_SP_AIRYAI];
   } else {                                                // invdigamma
     double yv = (double)v;
     double xx = yv >= -2.22 ? exp(yv) + 0.5 : -1.0 / (yv + 0.5772156649015329);
@@ -499,7 +640,7 @@ ag_status ag_special_param(int32_t op, int32_t dtype, int32_t m, const void* x, 
   if (n == 0) return AG_OK;
   AG_CHECK(x && y && n > 0, AG_EINVAL, "ag_special_param: bad arguments");
   AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_special_param: dtype %d", dtype);
-  AG_CHECK(op >= AG_SP_BESSELJ && op <= AG_SP_INVDIGAMMA, AG_EUNSUPPORTED, "ag_special_param: op %d", op);
+  AG_CHECK(op >= AG_SP_BESSELJ && op < AG_SP_COUNT, AG_EUNSUPPORTED, "ag_special_param: op %d", op);
   AG_CHECK(op != AG_SP_POLYGAMMA || (m >= 0 && m <= 20), AG_EUNSUPPORTED, "ag_special_param: polygamma order %d", m);
   Context& c = ctx();
   const unsigned nb = (unsigned)cdiv(n, (int64_t)256);

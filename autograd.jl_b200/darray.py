@@ -869,11 +869,13 @@ HOST_UNARY = dict(
     relu=lambda x: x if x > 0 else 0 * x, one=lambda x: type(x)(1))
 
 
-SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3)
+SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3, dawson=4, erfi=5, airyai=6, airyaiprime=7, airybi=8,
+          airybiprime=9)
 
 
 def special_param(name, m, x):
-    """besselj(m, x) / bessely(m, x) of integer order, polygamma(m, x), invdigamma(x) (ag_special_param): one pass."""
+    """besselj(m, x) / bessely(m, x) of integer order, polygamma(m, x), invdigamma(x), dawson / erfi / the four Airy
+    functions (m ignored) (ag_special_param): one pass."""
     x = materialize(x)
     out = DArray.empty(x.shape, x.dtype)
     if x.size:

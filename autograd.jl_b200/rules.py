@@ -436,6 +436,27 @@ def _invdigamma_fwd(x):
 invdigamma = primitive("invdigamma", _invdigamma_fwd, lambda dy, y, x: mul(dy, div(1, trigamma(y))))
 
 
+# src/specialfunctions.jl:5-8 (Airy functions), :33 (dawson), :39 (erfi): not in CUDA's math library, so they run as
+# their own pass (ag_special_param, parameter ignored) instead of the unary table; rules as the reference writes them
+def _sp1_fwd(name):
+    def fwd(x):
+        if isinstance(x, DArray):
+            return D.special_param(name, 0, x)
+        import scipy.special as sp
+        host = dict(dawson=sp.dawsn, erfi=sp.erfi, airyai=lambda v: sp.airy(v)[0], airyaiprime=lambda v: sp.airy(v)[1],
+                    airybi=lambda v: sp.airy(v)[2], airybiprime=lambda v: sp.airy(v)[3])
+        return float(host[name](x))
+    return fwd
+
+
+airyai = primitive("airyai", _sp1_fwd("airyai"), lambda dy, y, x: mul(dy, airyaiprime(x)))
+airyaiprime = primitive("airyaiprime", _sp1_fwd("airyaiprime"), lambda dy, y, x: mul(dy, mul(x, airyai(x))))
+airybi = primitive("airybi", _sp1_fwd("airybi"), lambda dy, y, x: mul(dy, airybiprime(x)))
+airybiprime = primitive("airybiprime", _sp1_fwd("airybiprime"), lambda dy, y, x: mul(dy, mul(x, airybi(x))))
+dawson = primitive("dawson", _sp1_fwd("dawson"), lambda dy, y, x: mul(dy, add(mul(mul(-2, y), x), 1)))
+erfi = primitive("erfi", _sp1_fwd("erfi"), lambda dy, y, x: mul(dy, mul(exp(abs2(x)), _2SPI)))
+
+
 def _copy_fwd(x):
     return D.copy(x) if isinstance(x, DArray) else x
 

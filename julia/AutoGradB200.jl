@@ -286,6 +286,33 @@ end
 # the user primitives of the examples, defined here so that they have device rules out of the box
 AutoGrad.@primitive sigm(x),dy,y (dy .* y .* (1 .- y))        # examples/charlm.jl:46-47
 AutoGrad.@primitive relu(x),dy,y (dy .* (y .== x))            # max.(0,x): src/math.jl:54 with x1 = 0
+# special functions (src/specialfunctions.jl): forward methods only -- the reference's own `@primitive` rules
+# (:5-8,20-21,25,29-30,33-44,59,63-67) are broadcast expressions over these same functions, so they run on the device
+# through the methods below.  Ids 30-42 are in the unary table (CUDA's math library has them); the rest run as their own
+# pass (ag_special_param: integer-order Bessel functions, polygamma(m, x), invdigamma, dawson, erfi, Airy functions).
+import SpecialFunctions
+const SPECIAL_UNARY = Dict{Symbol,Int32}(
+    :erf => 30, :erfc => 31, :erfcx => 32, :erfinv => 33, :erfcinv => 34, :gamma => 35, :loggamma => 36, :digamma => 37,
+    :trigamma => 38, :besselj0 => 39, :besselj1 => 40, :bessely0 => 41, :bessely1 => 42)
+const SPECIAL_PARAM = Dict{Symbol,Int32}(
+    :besselj => 0, :bessely => 1, :polygamma => 2, :invdigamma => 3, :dawson => 4, :erfi => 5, :airyai => 6,
+    :airyaiprime => 7, :airybi => 8, :airybiprime => 9)
+function special_param(op::Integer, m::Integer, x::DArray{T}) where T
+    y = similar(x)
+    isempty(x) || check(ccall((:ag_special_param, LIB), Int32, (Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int64),
+                              op, dtcode(T), m, x.ptr, y.ptr, length(x)))
+    y
+end
+for (f, id) in SPECIAL_UNARY
+    isdefined(SpecialFunctions, f) || continue
+    @eval broadcasted(::typeof(SpecialFunctions.$f), x::DArray) = unary_fwd($id, x)
+end
+for f in (:invdigamma, :dawson, :erfi, :airyai, :airyaiprime, :airybi, :airybiprime)
+    @eval broadcasted(::typeof(SpecialFunctions.$f), x::DArray) = special_param($(SPECIAL_PARAM[f]), 0, x)
+end
+for f in (:besselj, :bessely, :polygamma)      # integer parameter only: other orders have no device function
+    @eval broadcasted(::typeof(SpecialFunctions.$f), m::Integer, x::DArray) = special_param($(SPECIAL_PARAM[f]), m, x)
+end
 # binary broadcasting rules: fused kernel + unbroadcast (src/base.jl:21-49, src/math.jl:24,48,54-55)
 for (f, id) in BINARY
     f in (:(==), :<, :<=, :>, :>=) && continue                # @zerograd (src/base.jl:52-60)

@@ -718,6 +718,23 @@ def _invdigamma_np(x):
 invdigamma = primitive("invdigamma", _invdigamma_np, lambda dy, y, x: mul(dy, div(1, trigamma(y))))
 
 
+# src/specialfunctions.jl:5-8 (Airy functions), :33 (dawson), :39 (erfi); gradient expressions as the reference writes them
+def _airy(k):
+    def f(a):
+        import scipy.special as sp
+        r = sp.airy(np.asarray(a, dtype=np.float64))[k]
+        return r.astype(a.dtype) if isinstance(a, np.ndarray) else float(r)
+    return f
+
+
+airyai = primitive("airyai", _airy(0), lambda dy, y, x: mul(dy, airyaiprime(x)))
+airyaiprime = primitive("airyaiprime", _airy(1), lambda dy, y, x: mul(dy, mul(x, airyai(x))))
+airybi = primitive("airybi", _airy(2), lambda dy, y, x: mul(dy, airybiprime(x)))
+airybiprime = primitive("airybiprime", _airy(3), lambda dy, y, x: mul(dy, mul(x, airybi(x))))
+dawson = primitive("dawson", _np(_sp("dawsn")), lambda dy, y, x: mul(dy, add(mul(mul(-2, y), x), 1)))
+erfi = primitive("erfi", _np(_sp("erfi")), lambda dy, y, x: mul(dy, mul(exp(abs2(x)), _2SPI)))
+
+
 def _normback(x, p, dy, y):
     """src/linearalgebra.jl:222-238, branch for branch (raw arrays)."""
     if x.size == 0:

@@ -437,6 +437,9 @@ class FakeLib:
             r = np.where(v >= -2.22, np.exp(v) + 0.5, -1.0 / (v + 0.5772156649015329))
             for _ in range(12):
                 r = r - (sp.digamma(r) - v) / sp.polygamma(1, r)
+        elif op == 4: r = sp.dawsn(v)
+        elif op == 5: r = sp.erfi(v)
+        elif 6 <= op <= 9: r = sp.airy(v)[op - 6]
         else:
             return self._fail(5, "ag_special_param: op")
         _arr(y, n, T)[:] = r.astype(T)

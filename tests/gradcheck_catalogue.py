@@ -22,6 +22,10 @@ def check_catalogue(ag):
                            "trigamma": (1.2, 3.0), "besselj0": (0.5, 3.0), "besselj1": (0.5, 3.0),
                            "bessely0": (0.5, 3.0), "bessely1": (0.5, 3.0)}.items():
         assert ag.gradcheck(getattr(ag, name), dev(rng.uniform(lo, hi, (3, 4)))), name
+    # src/specialfunctions.jl:5-8,33,39: Airy functions, dawson, erfi (their own pass on the device)
+    for name, (lo, hi) in {"airyai": (-3.0, 3.0), "airyaiprime": (-3.0, 3.0), "airybi": (-3.0, 2.5),
+                           "airybiprime": (-3.0, 2.5), "dawson": (-2.0, 2.0), "erfi": (-1.2, 1.2)}.items():
+        assert ag.gradcheck(getattr(ag, name), dev(rng.uniform(lo, hi, (3, 4)))), name
     a, b = dev(rng.uniform(0.5, 1.5, (3, 4))), dev(rng.uniform(0.5, 1.5, (3, 4)))
     row, col = dev(rng.uniform(0.5, 1.5, (1, 4))), dev(rng.uniform(0.5, 1.5, (3, 1)))
     for name in ["add", "sub", "mul", "div", "pow_", "atan2", "hypot"]:

@@ -392,3 +392,53 @@ def test_special_functions_with_an_integer_parameter(ag, dtype, tol):
     assert np.max(np.abs(g * sp.polygamma(1, inv) - 1.0)) <= (1e-4 if dtype == np.float32 else 1e-9)
     with pytest.raises(ag.UnsupportedOnDevice):
         ag.besselj(0.5, xd)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 3e-6), (np.float64, 2e-12)])
+def test_airy_dawson_erfi_on_device(ag, dtype, tol):
+    """airyai / airyaiprime / airybi / airybiprime, dawson, erfi (src/specialfunctions.jl:5-8,33,39; ag_special_param,
+    functions CUDA's math library does not have) against scipy.special over every branch of the device code (series,
+    quadrature on both sides, asymptotic expansion), the Wronskian Ai Bi' - Ai' Bi = 1/pi, and the reference's rules."""
+    import scipy.special as sp
+    rng = np.random.default_rng(29)
+    x = np.concatenate([rng.uniform(-40.0, 12.0, 6000), np.linspace(-2.5, 2.5, 501), [0.0, -2.0, 2.0, 8.5, 8.6],
+                        rng.uniform(12.0, 25.0, 200)]).astype(dtype)
+    xd = ag.DArray.from_numpy(x)
+    x64 = x.astype(np.float64)
+    ref = sp.airy(x64)
+    got = [getattr(ag, n)(xd).to_numpy().astype(np.float64) for n in ("airyai", "airyaiprime", "airybi", "airybiprime")]
+    z = np.maximum(np.abs(x64), 1.0)
+    env = [np.where(x64 < 0, z ** -0.25, np.abs(ref[0])), np.where(x64 < 0, z ** 0.25, np.abs(ref[1])),
+           np.where(x64 < 0, z ** -0.25, np.abs(ref[2])), np.where(x64 < 0, z ** 0.25, np.abs(ref[3]))]
+    for k in range(4):                       # relative to the function for x >= 0, to the oscillation envelope for x < 0
+        err = np.abs(got[k] - ref[k]) / np.maximum(env[k], 1e-300 if dtype == np.float64 else 1e-38)
+        ok = np.isfinite(ref[k]) & (np.abs(ref[k]) > (0 if dtype == np.float64 else 1e-30))
+        assert np.max(err[ok]) <= tol, (k, float(np.max(err[ok])), float(x64[ok][np.argmax(err[ok])]))
+    if dtype == np.float64:
+        w = got[0] * got[3] - got[1] * got[2]
+        near = np.abs(x64) < 6
+        assert np.max(np.abs(w[near] * np.pi - 1.0)) <= 1e-10
+    xs = np.concatenate([rng.uniform(-30.0, 30.0, 4000), rng.uniform(-0.3, 0.3, 300), [0.0, 0.2, -0.2, 150.0]]).astype(dtype)
+    xsd, xs64 = ag.DArray.from_numpy(xs), xs.astype(np.float64)
+    d = ag.dawson(xsd).to_numpy().astype(np.float64)
+    assert np.max(np.abs(d - sp.dawsn(xs64)) / np.maximum(np.abs(sp.dawsn(xs64)), 1e-30)) <= tol
+    xe = rng.uniform(-5.0, 5.0, 3000).astype(dtype)
+    e = ag.erfi(ag.DArray.from_numpy(xe)).to_numpy().astype(np.float64)
+    refe = sp.erfi(xe.astype(np.float64))
+    assert np.max(np.abs(e - refe) / np.maximum(np.abs(refe), 1e-30)) <= tol
+    # rules: (Ai)' = Ai', (Ai')' = x Ai, (Bi')' = x Bi, dawson' = 1 - 2 x dawson, erfi' = 2/sqrt(pi) exp(x^2)
+    xg = rng.uniform(-6.0, 4.0, 2000).astype(dtype)
+    xgd, xg64 = ag.DArray.from_numpy(xg), xg.astype(np.float64)
+    ra = sp.airy(xg64)
+    gtol = 2e-5 if dtype == np.float32 else 1e-11
+
+    def close(g, r):
+        return np.max(np.abs(g.astype(np.float64) - r)) <= gtol * max(np.max(np.abs(r)), 1.0)
+    assert close(ag.grad(lambda v: ag.sum_(ag.airyai(v)))(xgd).to_numpy(), ra[1])
+    assert close(ag.grad(lambda v: ag.sum_(ag.airyaiprime(v)))(xgd).to_numpy(), xg64 * ra[0])
+    assert close(ag.grad(lambda v: ag.sum_(ag.airybi(v)))(xgd).to_numpy(), ra[3])
+    assert close(ag.grad(lambda v: ag.sum_(ag.airybiprime(v)))(xgd).to_numpy(), xg64 * ra[2])
+    assert close(ag.grad(lambda v: ag.sum_(ag.dawson(v)))(xgd).to_numpy(), 1 - 2 * xg64 * sp.dawsn(xg64))
+    xe64 = xe.astype(np.float64)
+    assert close(ag.grad(lambda v: ag.sum_(ag.erfi(v)))(ag.DArray.from_numpy(xe)).to_numpy(),
+                 2 / np.sqrt(np.pi) * np.exp(xe64 * xe64))

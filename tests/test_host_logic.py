@@ -329,6 +329,13 @@ def test_parametrised_special_functions_host_rules(hostlib, oracle):
         go = oracle.grad(lambda v: oracle.sum_(getattr(oracle, name)(m, v)))(np.asfortranarray(x))
         gd = ag.grad(lambda v: ag.sum_(getattr(ag, name)(m, v)))(xd).to_numpy()
         assert np.allclose(gd, go, rtol=1e-10, atol=1e-12), (name, m)
+    xs = rng.uniform(-3.0, 2.5, (6, 5))
+    xsd = ag.DArray.from_numpy(np.asfortranarray(xs))
+    for name in ("airyai", "airyaiprime", "airybi", "airybiprime", "dawson", "erfi"):
+        go = oracle.grad(lambda v: oracle.sum_(getattr(oracle, name)(v)))(np.asfortranarray(xs))
+        gd = ag.grad(lambda v: ag.sum_(getattr(ag, name)(v)))(xsd).to_numpy()
+        assert np.allclose(gd, go, rtol=1e-12, atol=1e-14), name
+        assert getattr(ag, name)(0.7) == getattr(oracle, name)(0.7)          # host Numbers
     y = rng.uniform(-2.0, 3.0, (4, 3))
     go = oracle.grad(lambda v: oracle.sum_(oracle.invdigamma(v)))(np.asfortranarray(y))
     gd = ag.grad(lambda v: ag.sum_(ag.invdigamma(v)))(ag.DArray.from_numpy(np.asfortranarray(y))).to_numpy()

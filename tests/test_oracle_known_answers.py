@@ -248,6 +248,29 @@ def test_special_function_known_answers(oracle):
         assert oracle.gradcheck(getattr(oracle, name), np.asfortranarray([[pt, pt + 0.2], [pt + 0.35, pt + 0.1]])), name
 
 
+def test_airy_dawson_erfi_known_answers(oracle):
+    """src/specialfunctions.jl:5-8,33,39.  Exact values: Ai(0) = 3^(-2/3)/Gamma(2/3), Ai'(0) = -3^(-1/3)/Gamma(1/3),
+    Bi(0) = sqrt(3) Ai(0), Bi'(0) = -sqrt(3) Ai'(0); the Wronskian Ai Bi' - Ai' Bi = 1/pi at any x; the rules
+    (Ai)'' = x Ai; dawson'(x) = 1 - 2 x dawson(x) with dawson(0) = 0; erfi'(0) = 2/sqrt(pi)."""
+    g = oracle.grad
+    z = np.array([0.0])
+    ai0, aip0 = 3 ** (-2 / 3) / math.gamma(2 / 3), -(3 ** (-1 / 3)) / math.gamma(1 / 3)
+    assert abs(oracle.airyai(z)[0] - ai0) < 1e-15 and abs(oracle.airyaiprime(z)[0] - aip0) < 1e-15
+    assert abs(oracle.airybi(z)[0] - math.sqrt(3) * ai0) < 1e-15 and abs(oracle.airybiprime(z)[0] + math.sqrt(3) * aip0) < 1e-15
+    x = np.array([-4.3, -1.0, 0.4, 2.2])
+    w = oracle.airyai(x) * oracle.airybiprime(x) - oracle.airyaiprime(x) * oracle.airybi(x)
+    assert np.allclose(w, 1 / math.pi, rtol=1e-12)
+    assert np.allclose(g(lambda v: oracle.sum_(oracle.airyai(v)))(x), oracle.airyaiprime(x), rtol=1e-14)
+    assert np.allclose(g(lambda v: oracle.sum_(oracle.airyaiprime(v)))(x), x * oracle.airyai(x), rtol=1e-14)
+    assert np.allclose(g(lambda v: oracle.sum_(oracle.airybiprime(v)))(x), x * oracle.airybi(x), rtol=1e-14)
+    assert oracle.dawson(z)[0] == 0.0 and g(lambda v: oracle.sum_(oracle.dawson(v)))(z)[0] == 1.0
+    assert np.allclose(g(lambda v: oracle.sum_(oracle.dawson(v)))(x), 1 - 2 * x * oracle.dawson(x), rtol=1e-14)
+    assert abs(g(lambda v: oracle.sum_(oracle.erfi(v)))(z)[0] - 2 / math.sqrt(math.pi)) < 1e-15
+    for name, pt in [("airyai", -1.3), ("airyaiprime", 0.4), ("airybi", -2.1), ("airybiprime", 0.6), ("dawson", 0.8),
+                     ("erfi", 0.5)]:
+        assert oracle.gradcheck(getattr(oracle, name), np.asfortranarray([[pt, pt + 0.2], [pt + 0.35, pt + 0.1]])), name
+
+
 def test_norm_known_answers(oracle):
     """src/linearalgebra.jl:64-65,222-238 on a 3-4-5 triangle: norm = 5, gradient x/5; p = 1: 7, sign(x); p = Inf: 4,
     the gradient goes to the largest entry; p = 0 counts nonzeros and has a zero gradient."""
