@@ -437,7 +437,8 @@ static ag_status ternary_dispatch(int which, MapArgs<3>& a) {
 // pass.  polygamma(m, x) = (-1)^(m+1) m! zeta(m+1, x) with the Hurwitz zeta function by Euler-Maclaurin summation
 // (x > 0; evaluated in double for both eltypes); invdigamma by Newton steps on digamma (Minka's start).
 enum { AG_SP_BESSELJ = 0, AG_SP_BESSELY = 1, AG_SP_POLYGAMMA = 2, AG_SP_INVDIGAMMA = 3, AG_SP_DAWSON = 4, AG_SP_ERFI = 5,
-       AG_SP_AIRYAI = 6, AG_SP_AIRYAIPRIME = 7, AG_SP_AIRYBI = 8, AG_SP_AIRYBIPRIME = 9, AG_SP_COUNT = 10 };
+       AG_SP_AIRYAI = 6, AG_SP_AIRYAIPRIME = 7, AG_SP_AIRYBI = 8, AG_SP_AIRYBIPRIME = 9, AG_SP_BESSELI = 10, AG_SP_BESSELK = 11,
+       AG_SP_COUNT = 12 };
 
 __device__ __forceinline__ double hurwitz_zeta(int s, double q) {
   // sum_{k<N} (q+k)^-s + tail at a = q + N >= 12
@@ -588,6 +589,52 @@ __device__ void airy_all(double x, double* out) {
   out[3] = -2.0 * cmul(cpolar(1.0, PI / 6), Ap).re;
 }
 
+
+// ---- modified Bessel functions of integer order (src/specialfunctions.jl:13,24), in double.
+//  besseli(m, x): the ascending series sum_k (x/2)^(2k+m) / (k! (k+m)!) -- every term positive, so no cancellation at any
+//                 x up to the overflow of the function itself (x ~ 713); I_m(-x) = (-1)^m I_m(x), I_-m = I_m.
+//  besselk(m, x): K_0 and K_1 from K_m(x) = int_0^inf exp(-x cosh t) cosh(m t) dt by the trapezoid rule (the integrand is analytic and
+//                 decays double-exponentially: the rule converges geometrically), step min(1/4, 0.7/sqrt(x)) so that the
+//                 Gaussian peak of width 1/sqrt(x) at large x stays resolved, then the upward recurrence
+//                 K_(n+1) = K_(n-1) + (2n/x) K_n (stable for K); x > 0 only (NaN below, Inf at 0).
+__device__ double besseli_(int m, double x) {
+  if (x != x) return x;
+  if (m < 0) m = -m;
+  const double ax = fabs(x);
+  const double sgn = (x < 0.0 && (m & 1)) ? -1.0 : 1.0;
+  if (ax == 0.0) return m == 0 ? 1.0 : 0.0 * sgn;
+  if (ax > 745.0 + 0.5 * m) return sgn * INFINITY;
+  const double q = 0.25 * ax * ax;
+  double t = exp(m * log(0.5 * ax) - lgamma(m + 1.0)), s = t;
+  for (int k = 1; k < 1500; ++k) {
+    t *= q / ((double)k * (double)(k + m));
+    s += t;
+    if (t < 1e-17 * s) break;
+  }
+  return sgn * s;
+}
+
+__device__ double besselk_(int m, double x) {
+  if (!(x > 0.0)) return x == 0.0 ? INFINITY : NAN;
+  if (m < 0) m = -m;
+  const double h = fmin(0.25, 0.7 / sqrt(x));
+  double s0 = 0.5 * exp(-x), s1 = s0;          // t = 0 with half weight: K0 and K1 integrands
+  for (int k = 1; k < 4000; ++k) {
+    const double c = cosh(k * h), f = exp(-x * c);
+    s0 += f;
+    s1 += f * c;
+    if (f * c < 1e-18 * s0) break;
+  }
+  double km = h * s0, k = h * s1;              // K0, K1; upward recurrence (stable for K)
+  if (m == 0) return km;
+  for (int n = 1; n < m; ++n) {
+    const double kn = km + (2.0 * n / x) * k;
+    km = k;
+    k = kn;
+  }
+  return k;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_special_param(int op, int m, const T* __restrict__ x, T* __restrict__ y, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -611,6 +658,10 @@ __global__ void __launch_bounds__(256) k_special_param(int op, int m, const T* _
       const double z = hurwitz_zeta(m + 1, (double)v);
       r = (T)(((m & 1) ? 1.0 : -1.0) * f * z);
     }
+  } else if (op == AG_SP_BESSELI) {
+    r = (T)besseli_(m, (double)v);
+  } else if (op == AG_SP_BESSELK) {
+    r = (T)besselk_(m, (double)v);
   } else if (op == AG_SP_DAWSON) {
     r = (T)dawson_((double)v);
   } else if (op == AG_SP_ERFI) {                          // 2/sqrt(pi) exp(x^2) dawson(x)

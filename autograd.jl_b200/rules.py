@@ -413,7 +413,7 @@ def _sp_fwd(name):
         if isinstance(x, DArray):
             return D.special_param(name, _int_order(name, a), x)
         import scipy.special as sp
-        return float({"besselj": sp.jv, "bessely": sp.yv, "polygamma": sp.polygamma}[name](a, x))
+        return float({"besselj": sp.jv, "bessely": sp.yv, "polygamma": sp.polygamma, "besseli": sp.iv, "besselk": sp.kv}[name](a, x))
     return fwd
 
 
@@ -421,6 +421,11 @@ besselj = primitive("besselj", _sp_fwd("besselj"), None,
                     lambda dy, y, a, x: mul(dy, div(sub(besselj(a - 1, x), besselj(a + 1, x)), 2)))
 bessely = primitive("bessely", _sp_fwd("bessely"), None,
                     lambda dy, y, a, x: mul(dy, div(sub(bessely(a - 1, x), bessely(a + 1, x)), 2)))
+# src/specialfunctions.jl:13,24
+besseli = primitive("besseli", _sp_fwd("besseli"), None,
+                    lambda dy, y, a, x: mul(dy, div(add(besseli(a - 1, x), besseli(a + 1, x)), 2)))
+besselk = primitive("besselk", _sp_fwd("besselk"), None,
+                    lambda dy, y, a, x: mul(dy, div(add(besselk(a - 1, x), besselk(a + 1, x)), -2)))
 polygamma = primitive("polygamma", _sp_fwd("polygamma"), None,
                       lambda dy, y, a, x: unbroadcast(x, mul(dy, polygamma(a + 1, x))))
 

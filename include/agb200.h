@@ -190,7 +190,9 @@ ag_status ag_unary_fwd(int32_t op, int32_t dtype, const void* x, void* y, int64_
  * 2 = polygamma(m, x) for 0 <= m <= 20 (:59; m >= 2 needs x > 0, NaN otherwise: no reflection), 3 = invdigamma(x)
  * (:43; m ignored); m is also ignored by 4 = dawson(x) (:33), 5 = erfi(x) (:39), 6 = airyai(x), 7 = airyaiprime(x),
  * 8 = airybi(x), 9 = airybiprime(x) (:5-8), which CUDA's math library does not have (series / Gauss-Laguerre
- * quadrature / asymptotic expansion in double, csrc/ewise.cu).  One pass, y[i] = f(m, x[i]). */
+ * quadrature / asymptotic expansion in double, csrc/ewise.cu); 10 = besseli(m, x), 11 = besselk(m, x) of integer order
+ * (:13,24; ascending series / trapezoid rule for K0, K1 + upward recurrence; their rules (f(m-1,x) + f(m+1,x))/(+-2)
+ * are composed by the host).  One pass, y[i] = f(m, x[i]). */
 ag_status ag_special_param(int32_t op, int32_t dtype, int32_t m, const void* x, void* y, int64_t n);
 /* dx[i] = dy[i] * g(x[i], y[i]).  dy: device array (dy_mode 0), device scalar (1), or the
  * immediate dy_scalar (2).  x / y may be NULL when g does not use them.

@@ -296,7 +296,7 @@ const SPECIAL_UNARY = Dict{Symbol,Int32}(
     :trigamma => 38, :besselj0 => 39, :besselj1 => 40, :bessely0 => 41, :bessely1 => 42)
 const SPECIAL_PARAM = Dict{Symbol,Int32}(
     :besselj => 0, :bessely => 1, :polygamma => 2, :invdigamma => 3, :dawson => 4, :erfi => 5, :airyai => 6,
-    :airyaiprime => 7, :airybi => 8, :airybiprime => 9)
+    :airyaiprime => 7, :airybi => 8, :airybiprime => 9, :besseli => 10, :besselk => 11)
 function special_param(op::Integer, m::Integer, x::DArray{T}) where T
     y = similar(x)
     isempty(x) || check(ccall((:ag_special_param, LIB), Int32, (Int32, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int64),
@@ -310,7 +310,7 @@ end
 for f in (:invdigamma, :dawson, :erfi, :airyai, :airyaiprime, :airybi, :airybiprime)
     @eval broadcasted(::typeof(SpecialFunctions.$f), x::DArray) = special_param($(SPECIAL_PARAM[f]), 0, x)
 end
-for f in (:besselj, :bessely, :polygamma)      # integer parameter only: other orders have no device function
+for f in (:besselj, :bessely, :polygamma, :besseli, :besselk)      # integer parameter only: other orders have no device function
     @eval broadcasted(::typeof(SpecialFunctions.$f), m::Integer, x::DArray) = special_param($(SPECIAL_PARAM[f]), m, x)
 end
 # binary broadcasting rules: fused kernel + unbroadcast (src/base.jl:21-49, src/math.jl:24,48,54-55)

@@ -702,6 +702,10 @@ besselj = primitive("besselj", _sp2("jv"), None,
                     lambda dy, y, a, x: mul(dy, div(sub(besselj(a - 1, x), besselj(a + 1, x)), 2)))
 bessely = primitive("bessely", _sp2("yv"), None,
                     lambda dy, y, a, x: mul(dy, div(sub(bessely(a - 1, x), bessely(a + 1, x)), 2)))
+besseli = primitive("besseli", _sp2("iv"), None,                                       # src/specialfunctions.jl:13
+                    lambda dy, y, a, x: mul(dy, div(add(besseli(a - 1, x), besseli(a + 1, x)), 2)))
+besselk = primitive("besselk", _sp2("kv"), None,                                       # :24
+                    lambda dy, y, a, x: mul(dy, div(add(besselk(a - 1, x), besselk(a + 1, x)), -2)))
 polygamma = primitive("polygamma", _sp2("polygamma"), None,
                       lambda dy, y, a, x: unbroadcast(x, mul(dy, polygamma(a + 1, x))))
 

@@ -440,6 +440,8 @@ class FakeLib:
         elif op == 4: r = sp.dawsn(v)
         elif op == 5: r = sp.erfi(v)
         elif 6 <= op <= 9: r = sp.airy(v)[op - 6]
+        elif op == 10: r = sp.iv(m, v)
+        elif op == 11: r = sp.kv(m, v)
         else:
             return self._fail(5, "ag_special_param: op")
         _arr(y, n, T)[:] = r.astype(T)

@@ -395,6 +395,35 @@ def test_special_functions_with_an_integer_parameter(ag, dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float32, 3e-6), (np.float64, 2e-12)])
+def test_modified_bessel_functions_of_integer_order(ag, dtype, tol):
+    """besseli(m, x), besselk(m, x) for integer m (src/specialfunctions.jl:13,24; ag_special_param ops 10, 11) against
+    scipy.special, with the reference's rules (I(m-1) + I(m+1))/2 and -(K(m-1) + K(m+1))/2."""
+    import scipy.special as sp
+    rng = np.random.default_rng(31)
+    x = np.concatenate([rng.uniform(0.01, 60.0, 4000), np.logspace(-5, 0, 200), [7.8, 7.9]]).astype(dtype)
+    xd, x64 = ag.DArray.from_numpy(x), x.astype(np.float64)
+
+    def rel(got, ref):
+        ok = np.isfinite(ref) & (np.abs(ref) > 1e-30) & (np.abs(ref) < 1e30)
+        return np.max(np.abs(got.astype(np.float64)[ok] - ref[ok]) / np.abs(ref[ok]))
+    for m in (0, 1, 2, 5, -3, 12):
+        assert rel(ag.besseli(m, xd).to_numpy(), sp.iv(m, x64)) <= tol, ("besseli", m)
+        assert rel(ag.besselk(m, xd).to_numpy(), sp.kv(m, x64)) <= tol, ("besselk", m)
+    xn = -x[:500]
+    assert rel(ag.besseli(3, ag.DArray.from_numpy(xn)).to_numpy(), sp.iv(3, xn.astype(np.float64))) <= tol
+    bad = ag.besselk(1, ag.DArray.from_numpy(np.array([-1.0, 0.0], dtype=dtype))).to_numpy()
+    assert np.isnan(bad[0]) and np.isinf(bad[1])
+    xg = rng.uniform(0.3, 6.0, 1500).astype(dtype)
+    xgd, xg64 = ag.DArray.from_numpy(xg), xg.astype(np.float64)
+    g = ag.grad(lambda v: ag.sum_(ag.besseli(2, v)))(xgd).to_numpy()
+    assert rel(g, (sp.iv(1, xg64) + sp.iv(3, xg64)) / 2) <= 10 * tol
+    g = ag.grad(lambda v: ag.sum_(ag.besselk(0, v)))(xgd).to_numpy()
+    assert rel(g, -sp.kv(1, xg64)) <= 10 * tol
+    with pytest.raises(ag.UnsupportedOnDevice):
+        ag.besselk(0.5, xd)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 3e-6), (np.float64, 2e-12)])
 def test_airy_dawson_erfi_on_device(ag, dtype, tol):
     """airyai / airyaiprime / airybi / airybiprime, dawson, erfi (src/specialfunctions.jl:5-8,33,39; ag_special_param,
     functions CUDA's math library does not have) against scipy.special over every branch of the device code (series,

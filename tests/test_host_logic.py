@@ -325,7 +325,7 @@ def test_parametrised_special_functions_host_rules(hostlib, oracle):
     rng = np.random.default_rng(23)
     x = rng.uniform(0.5, 9.0, (6, 5))
     xd = ag.DArray.from_numpy(np.asfortranarray(x))
-    for name, m in (("besselj", 2), ("bessely", 1), ("polygamma", 1), ("polygamma", 3)):
+    for name, m in (("besselj", 2), ("bessely", 1), ("polygamma", 1), ("polygamma", 3), ("besseli", 2), ("besselk", 1), ("besselk", 0)):
         go = oracle.grad(lambda v: oracle.sum_(getattr(oracle, name)(m, v)))(np.asfortranarray(x))
         gd = ag.grad(lambda v: ag.sum_(getattr(ag, name)(m, v)))(xd).to_numpy()
         assert np.allclose(gd, go, rtol=1e-10, atol=1e-12), (name, m)
