@@ -438,7 +438,7 @@ static ag_status ternary_dispatch(int which, MapArgs<3>& a) {
 // (x > 0; evaluated in double for both eltypes); invdigamma by Newton steps on digamma (Minka's start).
 enum { AG_SP_BESSELJ = 0, AG_SP_BESSELY = 1, AG_SP_POLYGAMMA = 2, AG_SP_INVDIGAMMA = 3, AG_SP_DAWSON = 4, AG_SP_ERFI = 5,
        AG_SP_AIRYAI = 6, AG_SP_AIRYAIPRIME = 7, AG_SP_AIRYBI = 8, AG_SP_AIRYBIPRIME = 9, AG_SP_BESSELI = 10, AG_SP_BESSELK = 11,
-       AG_SP_COUNT = 12 };
+       AG_SP_FLOOR = 12, AG_SP_CEIL = 13, AG_SP_ROUND = 14, AG_SP_TRUNC = 15, AG_SP_COUNT = 16 };
 
 __device__ __forceinline__ double hurwitz_zeta(int s, double q) {
   // sum_{k<N} (q+k)^-s + tail at a = q + N >= 12
@@ -658,6 +658,8 @@ __global__ void __launch_bounds__(256) k_special_param(int op, int m, const T* _
       const double z = hurwitz_zeta(m + 1, (double)v);
       r = (T)(((m & 1) ? 1.0 : -1.0) * f * z);
     }
+  } else if (op >= AG_SP_FLOOR && op <= AG_SP_TRUNC) {    // @zerograd floor / ceil / round (ties to even) / trunc
+    r = op == AG_SP_FLOOR ? floor(v) : op == AG_SP_CEIL ? ceil(v) : op == AG_SP_ROUND ? rint(v) : trunc(v);
   } else if (op == AG_SP_BESSELI) {
     r = (T)besseli_(m, (double)v);
   } else if (op == AG_SP_BESSELK) {

@@ -870,7 +870,7 @@ HOST_UNARY = dict(
 
 
 SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3, dawson=4, erfi=5, airyai=6, airyaiprime=7, airybi=8,
-          airybiprime=9, besseli=10, besselk=11)
+          airybiprime=9, besseli=10, besselk=11, floor=12, ceil=13, round=14, trunc=15)
 
 
 def special_param(name, m, x):

@@ -373,6 +373,89 @@ log1p = _unary("log1p", "log1p", lambda dy, y, x: mul(dy, div(1, add(1, x))), Tr
 cbrt = _unary("cbrt", "cbrt", lambda dy, y, x: mul(dy, div(1, mul(3, abs2(y)))), False, True)
 
 
+# ---- the rest of src/math.jl: degree / reciprocal / pi-scaled trigonometric functions, sinc / cosc, clamp, ldexp,
+# log(b, x).  The forward is composed from the table's ops on the unboxed arrays (deferred evaluation runs the chain as
+# ONE fused launch, lazy.py); the gradient is the reference's own broadcast expression, line for line.
+_D, _R, _PI = 180.0 / math.pi, math.pi / 180.0, math.pi
+
+
+def _inv(x):
+    return div(1, x)
+
+
+def _comp(name, fwd, rule):
+    return primitive(name, fwd, rule)
+
+
+acosd = _comp("acosd", lambda x: mul(acos(x), _D), lambda dy, y, x: mul(dy, div(-_D, sqrt(sub(1, abs2(x))))))     # math.jl:10
+acot = _comp("acot", lambda x: atan(_inv(x)), lambda dy, y, x: mul(dy, div(-1, add(1, abs2(x)))))                  # :12
+acotd = _comp("acotd", lambda x: mul(atan(_inv(x)), _D), lambda dy, y, x: mul(dy, div(-_D, add(1, abs2(x)))))      # :13
+acoth = _comp("acoth", lambda x: atanh(_inv(x)), lambda dy, y, x: mul(dy, div(1, sub(1, abs2(x)))))                # :14
+acsc = _comp("acsc", lambda x: asin(_inv(x)),                                                                      # :15
+             lambda dy, y, x: mul(dy, div(-1, sqrt(mul(mul(abs2(x), sub(x, 1)), add(x, 1))))))
+acscd = _comp("acscd", lambda x: mul(asin(_inv(x)), _D),                                                           # :16
+              lambda dy, y, x: mul(dy, div(-_D, sqrt(mul(mul(abs2(x), sub(x, 1)), add(x, 1))))))
+acsch = _comp("acsch", lambda x: asinh(_inv(x)), lambda dy, y, x: mul(dy, div(-1, sqrt(add(abs2(abs2(x)), abs2(x))))))   # :17
+asec = _comp("asec", lambda x: acos(_inv(x)), lambda dy, y, x: mul(dy, div(1, sqrt(sub(abs2(abs2(x)), abs2(x))))))       # :18
+asecd = _comp("asecd", lambda x: mul(acos(_inv(x)), _D),                                                           # :19
+              lambda dy, y, x: mul(dy, div(_D, sqrt(sub(abs2(abs2(x)), abs2(x))))))
+asech = _comp("asech", lambda x: acosh(_inv(x)), lambda dy, y, x: mul(dy, div(-1, sqrt(sub(abs2(x), abs2(abs2(x)))))))   # :20
+asind = _comp("asind", lambda x: mul(asin(x), _D), lambda dy, y, x: mul(dy, div(_D, sqrt(sub(1, abs2(x))))))       # :22
+atand = _comp("atand", lambda x: mul(atan(x), _D), lambda dy, y, x: mul(dy, div(_D, add(1, abs2(x)))))             # :25
+cosd = _comp("cosd", lambda x: cos(mul(x, _R)), lambda dy, y, x: mul(dy, div(mul(neg(sind(x)), _PI), 180)))        # :32
+cospi = _comp("cospi", lambda x: cos(mul(x, _PI)), lambda dy, y, x: mul(dy, mul(neg(sinpi(x)), _PI)))              # :34
+cot = _comp("cot", lambda x: _inv(tan(x)), lambda dy, y, x: mul(dy, neg(abs2(csc(x)))))                            # :35
+cotd = _comp("cotd", lambda x: _inv(tan(mul(x, _R))), lambda dy, y, x: mul(dy, div(mul(neg(abs2(cscd(x))), _PI), 180)))  # :36
+coth = _comp("coth", lambda x: _inv(tanh(x)), lambda dy, y, x: mul(dy, neg(abs2(csch(x)))))                        # :37
+csc = _comp("csc", lambda x: _inv(sin(x)), lambda dy, y, x: mul(dy, mul(mul(-1, y), cot(x))))                      # :38
+cscd = _comp("cscd", lambda x: _inv(sin(mul(x, _R))),                                                              # :39
+             lambda dy, y, x: mul(dy, div(mul(mul(mul(-1, y), cotd(x)), _PI), 180)))
+csch = _comp("csch", lambda x: _inv(sinh(x)), lambda dy, y, x: mul(dy, mul(mul(-1, y), coth(x))))                  # :40
+deg2rad = _comp("deg2rad", lambda x: mul(x, _R), lambda dy, y, x: mul(dy, _R))                                     # :41
+rad2deg = _comp("rad2deg", lambda x: mul(x, _D), lambda dy, y, x: mul(dy, _D))                                     # :58
+sec = _comp("sec", lambda x: _inv(cos(x)), lambda dy, y, x: mul(dy, mul(y, tan(x))))                               # :60
+secd = _comp("secd", lambda x: _inv(cos(mul(x, _R))), lambda dy, y, x: mul(dy, div(mul(mul(y, tand(x)), _PI), 180)))     # :61
+sech = _comp("sech", lambda x: _inv(cosh(x)), lambda dy, y, x: mul(dy, mul(mul(-1, y), tanh(x))))                  # :62
+sind = _comp("sind", lambda x: sin(mul(x, _R)), lambda dy, y, x: mul(dy, div(mul(cosd(x), _PI), 180)))             # :67
+sinpi = _comp("sinpi", lambda x: sin(mul(x, _PI)), lambda dy, y, x: mul(dy, mul(cospi(x), _PI)))                   # :69
+tand = _comp("tand", lambda x: tan(mul(x, _R)), lambda dy, y, x: mul(dy, div(mul(add(1, abs2(y)), _PI), 180)))     # :73
+
+
+def _sinc_fwd(x):
+    e = eq(x, 0)                      # sinc(0) = 1 without a branch: sin(pi x) / (pi x + [x == 0]) + [x == 0]
+    return add(div(sin(mul(x, _PI)), add(mul(x, _PI), e)), e)
+
+
+def _cosc_fwd(x):
+    e = eq(x, 0)                      # cosc(0) = 0: (cos(pi x) - sinc(x)) / (x + [x == 0])
+    return div(sub(cos(mul(x, _PI)), _sinc_fwd(x)), add(x, e))
+
+
+sinc = _comp("sinc", _sinc_fwd, lambda dy, y, x: mul(dy, cosc(x)))                                                 # :65
+cosc = _comp("cosc", _cosc_fwd, lambda dy, y, x: mul(dy, sub(div(mul(-2, y), x), mul(sinc(x), _PI ** 2))))         # :31
+clamp = primitive("clamp", lambda x, lo, hi: min_(max_(x, lo), hi),                                                # :28
+                  lambda dy, y, x, lo, hi: unbroadcast(x, mul(dy, mul(le(lo, x), le(x, hi)))))
+ldexp = primitive("ldexp", lambda x, n: mul(x, 2.0 ** n), lambda dy, y, x, n: mul(dy, 2.0 ** n))                   # :47
+logb = primitive("log", lambda x1, x2: div(log(x2), log(x1)),                                                      # :48 log(b, x)
+                 lambda dy, y, x1, x2: unbroadcast(x1, mul(dy, div(neg(log(x2)), mul(x1, abs2(log(x1)))))),
+                 lambda dy, y, x1, x2: unbroadcast(x2, mul(dy, div(1, mul(x2, log(x1))))))
+
+
+def _round_fwd(name):
+    def fwd(x):
+        if isinstance(x, DArray):
+            return D.special_param(name, 0, x)
+        return float({"floor": math.floor, "ceil": math.ceil, "round": round, "trunc": math.trunc}[name](x))
+    return fwd
+
+
+# @zerograd floor / ceil / round / trunc (src/base.jl:79,100,145,151): forward only, their own pass (round: ties to even, like Julia)
+floor = zerograd("floor", _round_fwd("floor"))
+ceil = zerograd("ceil", _round_fwd("ceil"))
+round_ = zerograd("round", _round_fwd("round"))
+trunc = zerograd("trunc", _round_fwd("trunc"))
+
+
 # special functions (src/specialfunctions.jl:20-21,29-30,34-42,63-67): the ones CUDA's math library provides, plus
 # digamma / trigamma; composites are the reference's own gradient expressions (used under an outer tape)
 _2SPI, _SPI2 = 2.0 / math.sqrt(math.pi), math.sqrt(math.pi) / 2.0

@@ -313,6 +313,47 @@ end
 for f in (:besselj, :bessely, :polygamma, :besseli, :besselk)      # integer parameter only: other orders have no device function
     @eval broadcasted(::typeof(SpecialFunctions.$f), m::Integer, x::DArray) = special_param($(SPECIAL_PARAM[f]), m, x)
 end
+# the rest of src/math.jl: forward methods composed from the table's ops (the reference's rules for them, src/math.jl:10-73,
+# are broadcast expressions over these same functions and run on the device through the methods here); the @zerograd
+# rounding functions of src/base.jl:79,100,145,151 are ag_special_param ops 12-15
+const D180, R180 = 180 / pi, pi / 180
+rcp(x::DArray) = binary_fwd(BINARY[:/], 1.0, x)
+scal(x::DArray, c) = binary_fwd(BINARY[:*], x, Float64(c))
+for (f, inner) in ((:acot, :atan), (:acoth, :atanh), (:acsc, :asin), (:acsch, :asinh), (:asec, :acos), (:asech, :acosh))
+    @eval broadcasted(::typeof($f), x::DArray) = unary_fwd($(UNARY[inner]), rcp(x))
+end
+for (f, inner) in ((:acotd, :atan), (:acscd, :asin), (:asecd, :acos))
+    @eval broadcasted(::typeof($f), x::DArray) = scal(unary_fwd($(UNARY[inner]), rcp(x)), D180)
+end
+for (f, inner) in ((:acosd, :acos), (:asind, :asin), (:atand, :atan))
+    @eval broadcasted(::typeof($f), x::DArray) = scal(unary_fwd($(UNARY[inner]), x), D180)
+end
+for (f, inner, c) in ((:sind, :sin, R180), (:cosd, :cos, R180), (:tand, :tan, R180), (:sinpi, :sin, pi), (:cospi, :cos, pi))
+    @eval broadcasted(::typeof($f), x::DArray) = unary_fwd($(UNARY[inner]), scal(x, $c))
+end
+for (f, inner) in ((:sec, :cos), (:csc, :sin), (:cot, :tan), (:sech, :cosh), (:csch, :sinh), (:coth, :tanh))
+    @eval broadcasted(::typeof($f), x::DArray) = rcp(unary_fwd($(UNARY[inner]), x))
+end
+for (f, inner) in ((:secd, :cos), (:cscd, :sin), (:cotd, :tan))
+    @eval broadcasted(::typeof($f), x::DArray) = rcp(unary_fwd($(UNARY[inner]), scal(x, R180)))
+end
+broadcasted(::typeof(deg2rad), x::DArray) = scal(x, R180)
+broadcasted(::typeof(rad2deg), x::DArray) = scal(x, D180)
+function broadcasted(::typeof(sinc), x::DArray)            # sinc(0) = 1 without a branch
+    e = binary_fwd(BINARY[:(==)], x, 0.0)
+    px = scal(x, pi)
+    add(binary_fwd(BINARY[:/], unary_fwd(UNARY[:sin], px), add(px, e)), e)
+end
+function broadcasted(::typeof(cosc), x::DArray)            # cosc(0) = 0
+    e = binary_fwd(BINARY[:(==)], x, 0.0)
+    binary_fwd(BINARY[:/], binary_fwd(BINARY[:-], unary_fwd(UNARY[:cos], scal(x, pi)), broadcasted(sinc, x)), add(x, e))
+end
+broadcasted(::typeof(clamp), x::DArray, lo::Number, hi::Number) = binary_fwd(BINARY[:min], binary_fwd(BINARY[:max], x, lo), hi)
+broadcasted(::typeof(ldexp), x::DArray, n::Integer) = scal(x, 2.0^n)
+broadcasted(::typeof(log), b::Number, x::DArray) = scal(unary_fwd(UNARY[:log], x), 1 / log(b))
+for (f, id) in ((:floor, 12), (:ceil, 13), (:round, 14), (:trunc, 15))
+    @eval broadcasted(::typeof($f), x::DArray) = special_param($id, 0, x)
+end
 # binary broadcasting rules: fused kernel + unbroadcast (src/base.jl:21-49, src/math.jl:24,48,54-55)
 for (f, id) in BINARY
     f in (:(==), :<, :<=, :>, :>=) && continue                # @zerograd (src/base.jl:52-60)

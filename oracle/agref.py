@@ -661,6 +661,74 @@ copy = primitive("copy", lambda x: np.array(x, order="F", copy=True) if isinstan
                  lambda dy, y, x: dy)
 
 
+# ---- the rest of src/math.jl (degree / reciprocal / pi-scaled trigonometry, sinc / cosc, clamp, ldexp, log(b, x)):
+# forward by numpy's own functions, gradient expressions as the reference writes them (line numbers of src/math.jl)
+_D, _PI = 180.0 / np.pi, np.pi
+tan = primitive("tan", _np(np.tan), lambda dy, y, x: mul(dy, add(1, abs2(y))))                                                  # :72
+acosd = primitive("acosd", _np(lambda x: np.degrees(np.arccos(x))), lambda dy, y, x: mul(dy, div(-_D, sqrt(sub(1, abs2(x))))))   # :10
+acot = primitive("acot", _np(lambda x: np.arctan(1 / x)), lambda dy, y, x: mul(dy, div(-1, add(1, abs2(x)))))                   # :12
+acotd = primitive("acotd", _np(lambda x: np.degrees(np.arctan(1 / x))), lambda dy, y, x: mul(dy, div(-_D, add(1, abs2(x)))))    # :13
+acoth = primitive("acoth", _np(lambda x: np.arctanh(1 / x)), lambda dy, y, x: mul(dy, div(1, sub(1, abs2(x)))))                 # :14
+acsc = primitive("acsc", _np(lambda x: np.arcsin(1 / x)),                                                                       # :15
+                 lambda dy, y, x: mul(dy, div(-1, sqrt(mul(mul(abs2(x), sub(x, 1)), add(x, 1))))))
+acscd = primitive("acscd", _np(lambda x: np.degrees(np.arcsin(1 / x))),                                                         # :16
+                  lambda dy, y, x: mul(dy, div(-_D, sqrt(mul(mul(abs2(x), sub(x, 1)), add(x, 1))))))
+acsch = primitive("acsch", _np(lambda x: np.arcsinh(1 / x)), lambda dy, y, x: mul(dy, div(-1, sqrt(add(abs2(abs2(x)), abs2(x))))))   # :17
+asec = primitive("asec", _np(lambda x: np.arccos(1 / x)), lambda dy, y, x: mul(dy, div(1, sqrt(sub(abs2(abs2(x)), abs2(x))))))       # :18
+asecd = primitive("asecd", _np(lambda x: np.degrees(np.arccos(1 / x))),                                                         # :19
+                  lambda dy, y, x: mul(dy, div(_D, sqrt(sub(abs2(abs2(x)), abs2(x))))))
+asech = primitive("asech", _np(lambda x: np.arccosh(1 / x)), lambda dy, y, x: mul(dy, div(-1, sqrt(sub(abs2(x), abs2(abs2(x)))))))   # :20
+asind = primitive("asind", _np(lambda x: np.degrees(np.arcsin(x))), lambda dy, y, x: mul(dy, div(_D, sqrt(sub(1, abs2(x))))))   # :22
+atand = primitive("atand", _np(lambda x: np.degrees(np.arctan(x))), lambda dy, y, x: mul(dy, div(_D, add(1, abs2(x)))))         # :25
+cosd = primitive("cosd", _np(lambda x: np.cos(np.radians(x))), lambda dy, y, x: mul(dy, div(mul(neg(sind(x)), _PI), 180)))      # :32
+cospi = primitive("cospi", _np(lambda x: np.cos(np.pi * x)), lambda dy, y, x: mul(dy, mul(neg(sinpi(x)), _PI)))                 # :34
+cot = primitive("cot", _np(lambda x: 1 / np.tan(x)), lambda dy, y, x: mul(dy, neg(abs2(csc(x)))))                               # :35
+cotd = primitive("cotd", _np(lambda x: 1 / np.tan(np.radians(x))), lambda dy, y, x: mul(dy, div(mul(neg(abs2(cscd(x))), _PI), 180)))  # :36
+coth = primitive("coth", _np(lambda x: 1 / np.tanh(x)), lambda dy, y, x: mul(dy, neg(abs2(csch(x)))))                           # :37
+csc = primitive("csc", _np(lambda x: 1 / np.sin(x)), lambda dy, y, x: mul(dy, mul(mul(-1, y), cot(x))))                         # :38
+cscd = primitive("cscd", _np(lambda x: 1 / np.sin(np.radians(x))),                                                              # :39
+                 lambda dy, y, x: mul(dy, div(mul(mul(mul(-1, y), cotd(x)), _PI), 180)))
+csch = primitive("csch", _np(lambda x: 1 / np.sinh(x)), lambda dy, y, x: mul(dy, mul(mul(-1, y), coth(x))))                     # :40
+deg2rad = primitive("deg2rad", _np(np.radians), lambda dy, y, x: mul(dy, _PI / 180))                                            # :41
+rad2deg = primitive("rad2deg", _np(np.degrees), lambda dy, y, x: mul(dy, _D))                                                   # :58
+sec = primitive("sec", _np(lambda x: 1 / np.cos(x)), lambda dy, y, x: mul(dy, mul(y, tan(x))))                                  # :60
+secd = primitive("secd", _np(lambda x: 1 / np.cos(np.radians(x))), lambda dy, y, x: mul(dy, div(mul(mul(y, tand(x)), _PI), 180)))    # :61
+sech = primitive("sech", _np(lambda x: 1 / np.cosh(x)), lambda dy, y, x: mul(dy, mul(mul(-1, y), tanh(x))))                     # :62
+sind = primitive("sind", _np(lambda x: np.sin(np.radians(x))), lambda dy, y, x: mul(dy, div(mul(cosd(x), _PI), 180)))           # :67
+sinpi = primitive("sinpi", _np(lambda x: np.sin(np.pi * x)), lambda dy, y, x: mul(dy, mul(cospi(x), _PI)))                      # :69
+tand = primitive("tand", _np(lambda x: np.tan(np.radians(x))), lambda dy, y, x: mul(dy, div(mul(add(1, abs2(y)), _PI), 180)))   # :73
+
+
+def _cosc_np(x):
+    x = np.asarray(x)
+    safe = np.where(x == 0, 1.0, x)
+    return np.where(x == 0, 0.0, np.cos(np.pi * safe) / safe - np.sin(np.pi * safe) / (np.pi * safe * safe)).astype(x.dtype)
+
+
+sinc = primitive("sinc", _np(np.sinc), lambda dy, y, x: mul(dy, cosc(x)))                                                       # :65
+cosc = primitive("cosc", _np(_cosc_np), lambda dy, y, x: mul(dy, sub(div(mul(-2, y), x), mul(sinc(x), _PI ** 2))))             # :31
+
+
+def _lemask(a, b):
+    av, bv = value(a), value(b)
+    r = _bcast(lambda p, q: (p <= q), av, bv)
+    dt = av.dtype if isinstance(av, np.ndarray) else (bv.dtype if isinstance(bv, np.ndarray) else np.float64)
+    return r.astype(dt) if isinstance(r, np.ndarray) else float(r)
+
+
+clamp = primitive("clamp", lambda x, lo, hi: np.clip(x, lo, hi),                                                                # :28
+                  lambda dy, y, x, lo, hi: unbroadcast(x, mul(dy, mul(_lemask(lo, x), _lemask(x, hi)))))
+ldexp = primitive("ldexp", lambda x, n: np.ldexp(x, n), lambda dy, y, x, n: mul(dy, 2.0 ** n))                                  # :47
+logb = primitive("log", _np(lambda b, x: np.log(x) / np.log(b)),                                                                # :48 log(b, x)
+                 lambda dy, y, x1, x2: unbroadcast(x1, mul(dy, div(neg(log(x2)), mul(x1, abs2(log(x1)))))),
+                 lambda dy, y, x1, x2: unbroadcast(x2, mul(dy, div(1, mul(x2, log(x1))))))
+# @zerograd rounding functions (src/base.jl:79,100,145,151)
+floor = lambda x: np.floor(value(x))
+ceil = lambda x: np.ceil(value(x))
+round_ = lambda x: np.rint(value(x))
+trunc = lambda x: np.trunc(value(x))
+
+
 # special functions (src/specialfunctions.jl:20-21,29-30,34-42,63-67) through scipy.special, the counterpart of
 # SpecialFunctions.jl; gradient expressions exactly as the reference writes them
 def _sp(name, *pre):

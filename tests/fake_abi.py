@@ -442,6 +442,7 @@ class FakeLib:
         elif 6 <= op <= 9: r = sp.airy(v)[op - 6]
         elif op == 10: r = sp.iv(m, v)
         elif op == 11: r = sp.kv(m, v)
+        elif 12 <= op <= 15: r = (np.floor, np.ceil, np.rint, np.trunc)[op - 12](v)
         else:
             return self._fail(5, "ag_special_param: op")
         _arr(y, n, T)[:] = r.astype(T)

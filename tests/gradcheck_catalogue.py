@@ -3,6 +3,10 @@ test; the reference's instrument is test/gradcheck.jl:35-133, its per-primitive 
 import numpy as np
 
 
+MATH_REST = ("acosd acot acotd acoth acsc acscd acsch asec asecd asech asind atand cosd cospi cot cotd coth csc cscd csch "
+             "deg2rad rad2deg sec secd sech sind sinpi tand sinc cosc").split()
+MATH_REST_DOMAINS = {"acosd": (-0.8, 0.8), "asind": (-0.8, 0.8), "asech": (0.2, 0.8)}
+
 def check_catalogue(ag):
     rng = np.random.default_rng(18)
     dev = ag.DArray.from_numpy
@@ -22,6 +26,15 @@ def check_catalogue(ag):
                            "trigamma": (1.2, 3.0), "besselj0": (0.5, 3.0), "besselj1": (0.5, 3.0),
                            "bessely0": (0.5, 3.0), "bessely1": (0.5, 3.0)}.items():
         assert ag.gradcheck(getattr(ag, name), dev(rng.uniform(lo, hi, (3, 4)))), name
+    # the rest of src/math.jl: degree / reciprocal / pi-scaled trigonometry, sinc / cosc, clamp, ldexp, log(b, x)
+    for name in MATH_REST:
+        lo, hi = MATH_REST_DOMAINS.get(name, (1.2, 2.0))
+        assert ag.gradcheck(getattr(ag, name), dev(rng.uniform(lo, hi, (3, 4)))), name
+    away = dev(np.array([[1.25, 1.45, 1.62], [1.9, 1.31, 1.05]]))            # not within the step of a clamp bound
+    assert ag.gradcheck(lambda z: ag.clamp(z, 1.4, 1.7), away)
+    assert ag.gradcheck(lambda z: ag.ldexp(z, 3), away)
+    assert ag.gradcheck(ag.logb, away, dev(np.array([[2.5, 3.0, 1.5], [2.2, 4.0, 1.8]])))
+    assert ag.gradcheck(lambda z: ag.logb(z, 3.0), away) and ag.gradcheck(lambda z: ag.logb(2.0, z), away)
     # src/specialfunctions.jl:5-8,33,39: Airy functions, dawson, erfi (their own pass on the device)
     for name, (lo, hi) in {"airyai": (-3.0, 3.0), "airyaiprime": (-3.0, 3.0), "airybi": (-3.0, 2.5),
                            "airybiprime": (-3.0, 2.5), "dawson": (-2.0, 2.0), "erfi": (-1.2, 1.2)}.items():

@@ -394,6 +394,41 @@ def test_special_functions_with_an_integer_parameter(ag, dtype, tol):
         ag.besselj(0.5, xd)
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-5), (np.float64, 1e-12)])
+def test_math_rest_on_device(ag, oracle, dtype, tol):
+    """The remainder of src/math.jl on the device (composed forwards, reference rules): values and gradients against
+    the float64 oracle; sinc(0) / cosc(0); clamp, ldexp, log(b, x); the @zerograd rounding functions bit-exact."""
+    from gradcheck_catalogue import MATH_REST, MATH_REST_DOMAINS
+    rng = np.random.default_rng(43)
+    for name in MATH_REST:
+        lo, hi = MATH_REST_DOMAINS.get(name, (1.2, 2.0))
+        x = np.asfortranarray(rng.uniform(lo, hi, (33, 17)).astype(dtype))
+        xd, x64 = ag.DArray.from_numpy(x), np.asfortranarray(x.astype(np.float64))
+        fo, fd = getattr(oracle, name), getattr(ag, name)
+        ref = fo(x64)
+        got = fd(xd).to_numpy()
+        assert got.dtype == dtype and np.max(np.abs(got - ref)) <= tol * max(np.max(np.abs(ref)), 1.0), name
+        go = oracle.grad(lambda v: oracle.sum_(fo(v)))(x64)
+        gd = ag.grad(lambda v: ag.sum_(fd(v)))(xd).to_numpy()
+        assert np.max(np.abs(gd - go)) <= 5 * tol * max(np.max(np.abs(go)), 1.0), name
+    x = np.asfortranarray(rng.uniform(1.0, 2.0, (33, 17)).astype(dtype))
+    xd, x64 = ag.DArray.from_numpy(x), np.asfortranarray(x.astype(np.float64))
+    lo_, hi_ = float(dtype(1.3)), float(dtype(1.7))
+    for fo, fd in ((lambda v: oracle.clamp(v, lo_, hi_), lambda v: ag.clamp(v, lo_, hi_)),
+                   (lambda v: oracle.ldexp(v, -2), lambda v: ag.ldexp(v, -2)),
+                   (lambda v: oracle.logb(v, 3.0), lambda v: ag.logb(v, 3.0)),
+                   (lambda v: oracle.logb(1.7, v), lambda v: ag.logb(1.7, v))):
+        ref, go = fo(x64), oracle.grad(lambda v: oracle.sum_(fo(v)))(x64)
+        assert np.max(np.abs(fd(xd).to_numpy() - ref)) <= tol * max(np.max(np.abs(ref)), 1.0)
+        assert np.max(np.abs(ag.grad(lambda v: ag.sum_(fd(v)))(xd).to_numpy() - go)) <= 5 * tol * max(np.max(np.abs(go)), 1.0)
+    z = np.array([0.0, 0.5, -1.5, 2.5, -0.2, 1e-3, 7.49, -7.51], dtype=dtype)
+    zd = ag.DArray.from_numpy(z)
+    assert ag.sinc(zd).to_numpy()[0] == 1.0 and ag.cosc(zd).to_numpy()[0] == 0.0
+    assert np.allclose(ag.sinc(zd).to_numpy(), np.sinc(z.astype(np.float64)), atol=tol)
+    for f, r in ((ag.floor, np.floor), (ag.ceil, np.ceil), (ag.round_, np.rint), (ag.trunc, np.trunc)):
+        assert np.array_equal(f(zd).to_numpy(), r(z))
+
+
 @pytest.mark.parametrize("dtype,tol", [(np.float32, 3e-6), (np.float64, 2e-12)])
 def test_modified_bessel_functions_of_integer_order(ag, dtype, tol):
     """besseli(m, x), besselk(m, x) for integer m (src/specialfunctions.jl:13,24; ag_special_param ops 10, 11) against

@@ -319,6 +319,44 @@ def test_timer_labels_follow_the_reference(hostlib):
     assert all(r[1] == 1 for r in rows.values())
 
 
+def test_math_rest_host_rules_against_the_oracle(hostlib, oracle):
+    """The remainder of src/math.jl (degree / reciprocal / pi-scaled trigonometry, sinc / cosc, clamp, ldexp,
+    log(b, x)): values and gradients of the product's composed forwards + reference rules against the oracle's
+    (numpy's own functions + the same rules), first and second order."""
+    from gradcheck_catalogue import MATH_REST, MATH_REST_DOMAINS
+    ag = hostlib
+    rng = np.random.default_rng(41)
+    for name in MATH_REST:
+        lo, hi = MATH_REST_DOMAINS.get(name, (1.2, 2.0))
+        x = np.asfortranarray(rng.uniform(lo, hi, (5, 4)))
+        xd = ag.DArray.from_numpy(x)
+        fo, fd = getattr(oracle, name), getattr(ag, name)
+        assert np.allclose(fd(xd).to_numpy(), fo(x), rtol=1e-13, atol=1e-15), name
+        go = oracle.grad(lambda v: oracle.sum_(fo(v)))(x)
+        gd = ag.grad(lambda v: ag.sum_(fd(v)))(xd).to_numpy()
+        assert np.allclose(gd, go, rtol=1e-12, atol=1e-14), name
+        assert abs(fd(1.3 if lo > 1 else 0.4) - float(fo(np.array([1.3 if lo > 1 else 0.4]))[0])) < 1e-13, name
+    x = np.asfortranarray(rng.uniform(1.0, 2.0, (5, 4)))
+    xd = ag.DArray.from_numpy(x)
+    for fo, fd in ((lambda v: oracle.clamp(v, 1.3, 1.7), lambda v: ag.clamp(v, 1.3, 1.7)),
+                   (lambda v: oracle.ldexp(v, -2), lambda v: ag.ldexp(v, -2)),
+                   (lambda v: oracle.logb(v, 3.0), lambda v: ag.logb(v, 3.0)),
+                   (lambda v: oracle.logb(1.7, v), lambda v: ag.logb(1.7, v))):
+        assert np.allclose(fd(xd).to_numpy(), fo(x), rtol=1e-14)
+        assert np.allclose(ag.grad(lambda v: ag.sum_(fd(v)))(xd).to_numpy(), oracle.grad(lambda v: oracle.sum_(fo(v)))(x),
+                           rtol=1e-12)
+    # second order through the rules (they are compositions of recorded primitives): d2/dx2 sec = sec (tan^2 + sec^2)
+    g2 = ag.grad(lambda v: ag.sum_(ag.grad(lambda u: ag.sum_(ag.sec(u)))(v)))(xd).to_numpy()
+    assert np.allclose(g2, (np.tan(x) ** 2 + 1 / np.cos(x) ** 2) / np.cos(x), rtol=1e-11)
+    # sinc(0) = 1, cosc(0) = 0; rounding functions are @zerograd (ties to even for round)
+    z = ag.DArray.from_numpy(np.array([0.0, 0.5, -1.5, 2.5, -0.2]))
+    assert np.array_equal(ag.sinc(z).to_numpy()[:1], [1.0]) and np.array_equal(ag.cosc(z).to_numpy()[:1], [0.0])
+    assert np.array_equal(ag.round_(z).to_numpy(), [0.0, 0.0, -2.0, 2.0, -0.0])
+    assert np.array_equal(ag.floor(z).to_numpy(), np.floor(z.to_numpy())) and np.array_equal(ag.ceil(z).to_numpy(), np.ceil(z.to_numpy()))
+    assert np.array_equal(ag.trunc(z).to_numpy(), np.trunc(z.to_numpy()))
+    assert ag.grad(lambda v: ag.sum_(ag.mul(v, ag.floor(v))))(z).to_numpy().tolist() == np.floor(z.to_numpy()).tolist()
+
+
 def test_parametrised_special_functions_host_rules(hostlib, oracle):
     """besselj / bessely / polygamma / invdigamma: the host rules on the numpy stand-in against the oracle's."""
     ag = hostlib
