@@ -813,6 +813,67 @@ getindex = primitive("getindex", _getindex_fwd, lambda dxi, xi, x, *idx: ungetin
                      only_first=True)
 
 # ---------------------------------------------------------------------------------------------------
+# diag / diagm / tr / tril / triu / kron (src/linearalgebra.jl:19-20,46-48,86,90,92,176-186)
+# ---------------------------------------------------------------------------------------------------
+
+def _diag_positions(shape, k):
+    """0-based column-major positions of the k-th diagonal of an (m, n) matrix."""
+    m, n = shape
+    cnt = max(0, min(m, n - k) if k >= 0 else min(m + k, n))
+    j = np.arange(cnt, dtype=np.int64)
+    return (j + (j + k) * m) if k >= 0 else ((j - k) + j * m)
+
+
+def diag(x, k=0):
+    """`diag(x)`, `diag(x, k)`: the diagonal read through `getindex` with linear positions, so its gradient is
+    getindex's own (a Sparse block scattered into zeros = the reference's `diagm(k => dy)`, src/linearalgebra.jl:19-20,
+    without its square-matrices-only restriction)."""
+    shp = size(x)
+    if len(shp) != 2:
+        raise DimensionMismatch("diag: a matrix is required")
+    return getindex(x, _diag_positions(shp, int(k)))
+
+
+def _diagm_fwd(v, k=0):
+    n = v.size + abs(int(k))
+    return _ungetindex_dense(D.zeros((n, n), v.dtype), reshape(v, (v.size,)), (_diag_positions((n, n), int(k)),))
+
+
+diagm = primitive("diagm", _diagm_fwd, lambda dy, y, v, k=0: reshape(diag(dy, k), size(v)))   # :22 (commented there)
+
+
+def tr(x):
+    """`tr(x)` = sum of the diagonal; gradient dy * I (src/linearalgebra.jl:86) through sum and getindex."""
+    return sum_(diag(x))
+
+
+_TRI_MASKS = {}
+
+
+def _tri_mask(x, lower):
+    """`tril(fill!(similar(x), 1))` / `triu(...)` of the rules (src/linearalgebra.jl:90,92): uploaded once per shape."""
+    v = value(x)
+    key = (tuple(v.shape), np.dtype(v.dtype).str, lower)
+    m = _TRI_MASKS.get(key)
+    if m is None:
+        ones_ = np.ones(v.shape, dtype=v.dtype)
+        m = _TRI_MASKS[key] = DArray.from_numpy(np.asfortranarray(np.tril(ones_) if lower else np.triu(ones_)))
+    return m
+
+
+tril = primitive("tril", lambda x: mul(x, _tri_mask(x, True)), lambda dy, y, x: mul(dy, _tri_mask(x, True)))
+triu = primitive("triu", lambda x: mul(x, _tri_mask(x, False)), lambda dy, y, x: mul(dy, _tri_mask(x, False)))
+
+
+def kron(a, b):
+    """`_kron` (src/linearalgebra.jl:176-186): reshape, one broadcast product, reshape -- all recorded primitives."""
+    if ndims(a) != 2 or ndims(b) != 2:
+        raise DimensionMismatch("Only support matrices for the time being")
+    (m1, n1), (m2, n2) = size(a), size(b)
+    return reshape(mul(reshape(a, (1, m1, 1, n1)), reshape(b, (m2, 1, n2, 1))), (m1 * m2, n1 * n2))
+
+
+# ---------------------------------------------------------------------------------------------------
 # cat / uncat (src/cat.jl:27-31,46-92,122-123) and cat1d (src/cat.jl:150-182)
 # ---------------------------------------------------------------------------------------------------
 

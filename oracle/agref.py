@@ -807,6 +807,25 @@ dawson = primitive("dawson", _np(_sp("dawsn")), lambda dy, y, x: mul(dy, add(mul
 erfi = primitive("erfi", _np(_sp("erfi")), lambda dy, y, x: mul(dy, mul(exp(abs2(x)), _2SPI)))
 
 
+# src/linearalgebra.jl:19-20 (diag), :86 (tr), :90,92 (tril / triu), :176-186 (_kron), rules as the reference writes them
+def _diagm_np(v, k=0):
+    return np.asfortranarray(np.diag(np.asarray(v).reshape(-1), k))
+
+
+diag = primitive("diag", lambda x, k=0: np.diag(x, k).copy(), lambda dy, y, x, k=0: _diagm_np(value(dy), k))
+diagm = primitive("diagm", _diagm_np, lambda dy, y, v, k=0: reshape(diag(dy, k), np.shape(value(v))))
+tr = primitive("tr", lambda x: np.trace(x), lambda dy, y, x: mul(dy, np.asfortranarray(np.eye(*value(x).shape, dtype=value(x).dtype))))
+tril = primitive("tril", lambda x: np.asfortranarray(np.tril(x)),
+                 lambda dy, y, x: mul(dy, np.asfortranarray(np.tril(np.ones_like(value(x))))))
+triu = primitive("triu", lambda x: np.asfortranarray(np.triu(x)),
+                 lambda dy, y, x: mul(dy, np.asfortranarray(np.triu(np.ones_like(value(x))))))
+
+
+def kron(a, b):
+    (m1, n1), (m2, n2) = np.shape(value(a)), np.shape(value(b))
+    return reshape(mul(reshape(a, (1, m1, 1, n1)), reshape(b, (m2, 1, n2, 1))), (m1 * m2, n1 * n2))
+
+
 def _normback(x, p, dy, y):
     """src/linearalgebra.jl:222-238, branch for branch (raw arrays)."""
     if x.size == 0:

@@ -59,6 +59,12 @@ def check_catalogue(ag):
     for f in (ag.var, ag.std, ag.norm):
         assert ag.gradcheck(f, a), f
     assert ag.gradcheck(ag.dot, a, b)
+    # src/linearalgebra.jl:19-20,86,90,92,176-186
+    sq = dev(rng.standard_normal((4, 4)))
+    assert ag.gradcheck(ag.diag, sq) and ag.gradcheck(lambda z: ag.diag(z, 1), sq) and ag.gradcheck(lambda z: ag.diag(z, -2), sq)
+    assert ag.gradcheck(ag.diag, a) and ag.gradcheck(ag.tr, sq) and ag.gradcheck(ag.tril, sq) and ag.gradcheck(ag.triu, a)
+    assert ag.gradcheck(ag.diagm, dev(rng.standard_normal(3))) and ag.gradcheck(lambda z: ag.diagm(z, -1), dev(rng.standard_normal(3)))
+    assert ag.gradcheck(ag.kron, dev(rng.standard_normal((2, 3))), dev(rng.standard_normal((4, 5))))
     m1, m2 = dev(rng.standard_normal((4, 3))), dev(rng.standard_normal((3, 5)))
     assert ag.gradcheck(ag.matmul, m1, m2)
     assert ag.gradcheck(lambda p, q: ag.matmul(ag.adjoint(p), q), dev(rng.standard_normal((3, 4))), m2)

@@ -506,3 +506,51 @@ def test_airy_dawson_erfi_on_device(ag, dtype, tol):
     xe64 = xe.astype(np.float64)
     assert close(ag.grad(lambda v: ag.sum_(ag.erfi(v)))(ag.DArray.from_numpy(xe)).to_numpy(),
                  2 / np.sqrt(np.pi) * np.exp(xe64 * xe64))
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-12)])
+def test_linear_algebra_helpers_on_device(ag, oracle, dtype, tol):
+    """diag / diagm / tr / tril / triu / kron (src/linearalgebra.jl:19-20,86,90,92,176-186): values against numpy,
+    gradients against the oracle's (which carry the reference's rule expressions)."""
+    rng = np.random.default_rng(47)
+    sq = np.asfortranarray(rng.standard_normal((6, 6)).astype(dtype))
+    rect = np.asfortranarray(rng.standard_normal((4, 7)).astype(dtype))
+    sqd, rectd = ag.DArray.from_numpy(sq), ag.DArray.from_numpy(rect)
+    for k in (0, 1, -2, 5):
+        assert np.array_equal(ag.diag(sqd, k).to_numpy(), np.diag(sq, k)), k
+        assert np.array_equal(ag.diag(rectd, k).to_numpy(), np.diag(rect, k)), k
+    v = rng.standard_normal(5).astype(dtype)
+    vd = ag.DArray.from_numpy(v)
+    for k in (0, 2, -1):
+        assert np.array_equal(ag.diagm(vd, k).to_numpy(), np.diag(v, k)), k
+    assert np.array_equal(ag.tril(rectd).to_numpy(), np.tril(rect)) and np.array_equal(ag.triu(rectd).to_numpy(), np.triu(rect))
+    assert abs(float(ag.value(ag.tr(sqd))) - np.trace(sq.astype(np.float64))) <= tol
+    a, b = np.asfortranarray(rng.standard_normal((3, 4)).astype(dtype)), np.asfortranarray(rng.standard_normal((5, 2)).astype(dtype))
+    ad, bd = ag.DArray.from_numpy(a), ag.DArray.from_numpy(b)
+    assert np.array_equal(ag.kron(ad, bd).to_numpy(), np.kron(a, b))
+    w = np.asfortranarray(rng.standard_normal((6, 6)))
+    wd = ag.DArray.from_numpy(w.astype(dtype))
+    sq64 = np.asfortranarray(sq.astype(np.float64))
+    for fo, fd in ((lambda z: oracle.diag(z, 1), lambda z: ag.diag(z, 1)), (oracle.tr, ag.tr), (oracle.tril, ag.tril),
+                   (oracle.triu, ag.triu)):
+        def lo(z):
+            r = fo(z)
+            return oracle.sum_(oracle.mul(r, w[:np.shape(oracle.value(r))[0]] if np.ndim(oracle.value(r)) == 2 else (w[0, :np.size(oracle.value(r))] if np.ndim(oracle.value(r)) else 1.0)))
+        def ld(z):
+            r = fd(z)
+            shp = ag.size(r)
+            wt = wd if len(shp) == 2 else (ag.DArray.from_numpy(w[0, :shp[0]].astype(dtype)) if len(shp) else 1.0)
+            return ag.sum_(ag.mul(r, wt))
+        go = oracle.grad(lo)(sq64)
+        gd = ag.grad(ld)(sqd)
+        gd = gd.full().to_numpy() if hasattr(gd, "full") else gd.to_numpy()
+        assert np.max(np.abs(gd - go)) <= tol * 10, fd
+    a64, b64 = np.asfortranarray(a.astype(np.float64)), np.asfortranarray(b.astype(np.float64))
+    wk = np.asfortranarray(rng.standard_normal((15, 8)))
+    wkd = ag.DArray.from_numpy(wk.astype(dtype))
+    go = oracle.grad(lambda p: oracle.sum_(oracle.mul(oracle.kron(p, b64), wk)))(a64)
+    gd = ag.grad(lambda p: ag.sum_(ag.mul(ag.kron(p, bd), wkd)))(ad).to_numpy()
+    assert np.max(np.abs(gd - go)) <= tol * 20
+    go = oracle.grad(lambda q: oracle.sum_(oracle.mul(oracle.kron(a64, q), wk)))(b64)
+    gd = ag.grad(lambda q: ag.sum_(ag.mul(ag.kron(ad, q), wkd)))(bd).to_numpy()
+    assert np.max(np.abs(gd - go)) <= tol * 20

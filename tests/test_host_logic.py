@@ -378,3 +378,50 @@ def test_parametrised_special_functions_host_rules(hostlib, oracle):
     go = oracle.grad(lambda v: oracle.sum_(oracle.invdigamma(v)))(np.asfortranarray(y))
     gd = ag.grad(lambda v: ag.sum_(ag.invdigamma(v)))(ag.DArray.from_numpy(np.asfortranarray(y))).to_numpy()
     assert np.allclose(gd, go, rtol=1e-8, atol=1e-10)
+
+
+def test_linear_algebra_helpers_host_rules(hostlib, oracle):
+    """diag / diagm / tr / tril / triu / kron (src/linearalgebra.jl:19-20,86,90,92,176-186): values against numpy,
+    gradients against the oracle's (which carry the reference's rule expressions)."""
+    rng = np.random.default_rng(47)
+    sq = np.asfortranarray(rng.standard_normal((6, 6)).astype(np.float64))
+    rect = np.asfortranarray(rng.standard_normal((4, 7)).astype(np.float64))
+    sqd, rectd = hostlib.DArray.from_numpy(sq), hostlib.DArray.from_numpy(rect)
+    for k in (0, 1, -2, 5):
+        assert np.array_equal(hostlib.diag(sqd, k).to_numpy(), np.diag(sq, k)), k
+        assert np.array_equal(hostlib.diag(rectd, k).to_numpy(), np.diag(rect, k)), k
+    v = rng.standard_normal(5).astype(np.float64)
+    vd = hostlib.DArray.from_numpy(v)
+    for k in (0, 2, -1):
+        assert np.array_equal(hostlib.diagm(vd, k).to_numpy(), np.diag(v, k)), k
+    assert np.array_equal(hostlib.tril(rectd).to_numpy(), np.tril(rect)) and np.array_equal(hostlib.triu(rectd).to_numpy(), np.triu(rect))
+    assert abs(float(hostlib.value(hostlib.tr(sqd))) - np.trace(sq.astype(np.float64))) <= 1e-12
+    a, b = np.asfortranarray(rng.standard_normal((3, 4)).astype(np.float64)), np.asfortranarray(rng.standard_normal((5, 2)).astype(np.float64))
+    ad, bd = hostlib.DArray.from_numpy(a), hostlib.DArray.from_numpy(b)
+    assert np.array_equal(hostlib.kron(ad, bd).to_numpy(), np.kron(a, b))
+    w = np.asfortranarray(rng.standard_normal((6, 6)))
+    wd = hostlib.DArray.from_numpy(w.astype(np.float64))
+    sq64 = np.asfortranarray(sq.astype(np.float64))
+    for fo, fd in ((lambda z: oracle.diag(z, 1), lambda z: hostlib.diag(z, 1)), (oracle.tr, hostlib.tr), (oracle.tril, hostlib.tril),
+                   (oracle.triu, hostlib.triu)):
+        def lo(z):
+            r = fo(z)
+            return oracle.sum_(oracle.mul(r, w[:np.shape(oracle.value(r))[0]] if np.ndim(oracle.value(r)) == 2 else (w[0, :np.size(oracle.value(r))] if np.ndim(oracle.value(r)) else 1.0)))
+        def ld(z):
+            r = fd(z)
+            shp = hostlib.size(r)
+            wt = wd if len(shp) == 2 else (hostlib.DArray.from_numpy(w[0, :shp[0]].astype(np.float64)) if len(shp) else 1.0)
+            return hostlib.sum_(hostlib.mul(r, wt))
+        go = oracle.grad(lo)(sq64)
+        gd = hostlib.grad(ld)(sqd)
+        gd = gd.full().to_numpy() if hasattr(gd, "full") else gd.to_numpy()
+        assert np.max(np.abs(gd - go)) <= 1e-12 * 10, fd
+    a64, b64 = np.asfortranarray(a.astype(np.float64)), np.asfortranarray(b.astype(np.float64))
+    wk = np.asfortranarray(rng.standard_normal((15, 8)))
+    wkd = hostlib.DArray.from_numpy(wk.astype(np.float64))
+    go = oracle.grad(lambda p: oracle.sum_(oracle.mul(oracle.kron(p, b64), wk)))(a64)
+    gd = hostlib.grad(lambda p: hostlib.sum_(hostlib.mul(hostlib.kron(p, bd), wkd)))(ad).to_numpy()
+    assert np.max(np.abs(gd - go)) <= 1e-12 * 20
+    go = oracle.grad(lambda q: oracle.sum_(oracle.mul(oracle.kron(a64, q), wk)))(b64)
+    gd = hostlib.grad(lambda q: hostlib.sum_(hostlib.mul(hostlib.kron(ad, q), wkd)))(bd).to_numpy()
+    assert np.max(np.abs(gd - go)) <= 1e-12 * 20
