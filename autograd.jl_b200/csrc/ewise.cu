@@ -438,7 +438,8 @@ static ag_status ternary_dispatch(int which, MapArgs<3>& a) {
 // (x > 0; evaluated in double for both eltypes); invdigamma by Newton steps on digamma (Minka's start).
 enum { AG_SP_BESSELJ = 0, AG_SP_BESSELY = 1, AG_SP_POLYGAMMA = 2, AG_SP_INVDIGAMMA = 3, AG_SP_DAWSON = 4, AG_SP_ERFI = 5,
        AG_SP_AIRYAI = 6, AG_SP_AIRYAIPRIME = 7, AG_SP_AIRYBI = 8, AG_SP_AIRYBIPRIME = 9, AG_SP_BESSELI = 10, AG_SP_BESSELK = 11,
-       AG_SP_FLOOR = 12, AG_SP_CEIL = 13, AG_SP_ROUND = 14, AG_SP_TRUNC = 15, AG_SP_COUNT = 16 };
+       AG_SP_FLOOR = 12, AG_SP_CEIL = 13, AG_SP_ROUND = 14, AG_SP_TRUNC = 15, AG_SP_EXPONENT = 16, AG_SP_SIGNIFICAND = 17,
+       AG_SP_REM2PI = 18, AG_SP_COUNT = 19 };
 
 __device__ __forceinline__ double hurwitz_zeta(int s, double q) {
   // sum_{k<N} (q+k)^-s + tail at a = q + N >= 12
@@ -660,6 +661,17 @@ __global__ void __launch_bounds__(256) k_special_param(int op, int m, const T* _
     }
   } else if (op >= AG_SP_FLOOR && op <= AG_SP_TRUNC) {    // @zerograd floor / ceil / round (ties to even) / trunc
     r = op == AG_SP_FLOOR ? floor(v) : op == AG_SP_CEIL ? ceil(v) : op == AG_SP_ROUND ? rint(v) : trunc(v);
+  } else if (op == AG_SP_EXPONENT) {                      // src/math.jl:44 (@zerograd): floor(log2(|x|))
+    r = (T)ilogb((double)v);
+  } else if (op == AG_SP_SIGNIFICAND) {                   // :64  x / 2^exponent(x), in [1, 2)
+    const double xv = (double)v;
+    r = (xv == 0.0 || !isfinite(xv)) ? v : (T)scalbn(xv, -ilogb(xv));
+  } else if (op == AG_SP_REM2PI) {                        // :56,59  m: 0 RoundNearest, 1 RoundToZero, 2 RoundDown (= mod2pi), 3 RoundUp
+    const double P2 = 6.283185307179586476925, xv = (double)v;
+    double q = m == 0 ? remainder(xv, P2) : fmod(xv, P2);
+    if (m == 2 && q < 0.0) q += P2;
+    if (m == 3 && q > 0.0) q -= P2;
+    r = (T)q;
   } else if (op == AG_SP_BESSELI) {
     r = (T)besseli_(m, (double)v);
   } else if (op == AG_SP_BESSELK) {

@@ -870,7 +870,8 @@ HOST_UNARY = dict(
 
 
 SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3, dawson=4, erfi=5, airyai=6, airyaiprime=7, airybi=8,
-          airybiprime=9, besseli=10, besselk=11, floor=12, ceil=13, round=14, trunc=15)
+          airybiprime=9, besseli=10, besselk=11, floor=12, ceil=13, round=14, trunc=15,
+          exponent=16, significand=17, rem2pi=18)
 
 
 def special_param(name, m, x):

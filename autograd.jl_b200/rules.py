@@ -449,6 +449,30 @@ def _round_fwd(name):
     return fwd
 
 
+_RMODES = {"nearest": 0, "tozero": 1, "down": 2, "up": 3}
+
+
+def _sp_m_fwd(name, m=0):
+    def fwd(x, *rest):
+        mode = _RMODES[rest[0]] if rest else m
+        if isinstance(x, DArray):
+            return D.special_param(name, mode, x)
+        if name == "exponent":
+            return float(math.frexp(x)[1] - 1)
+        if name == "significand":
+            return x if x == 0 else math.frexp(x)[0] * 2.0
+        p2 = 2 * math.pi
+        return (math.remainder(x, p2) if mode == 0 else math.fmod(x, p2) if mode == 1 else
+                x - p2 * math.floor(x / p2) if mode == 2 else x - p2 * math.ceil(x / p2))
+    return fwd
+
+
+exponent = zerograd("exponent", _sp_m_fwd("exponent"))                                                             # :44
+significand = primitive("significand", _sp_m_fwd("significand"),                                                   # :64
+                        lambda dy, y, x: mul(dy, exp2(neg(exponent(x)))))
+mod2pi = primitive("mod2pi", _sp_m_fwd("rem2pi", 2), lambda dy, y, x: dy)                                          # :56
+rem2pi = primitive("rem2pi", _sp_m_fwd("rem2pi"), lambda dy, y, x, r: dy)                                          # :59  r: "nearest" | "tozero" | "down" | "up"
+
 # @zerograd floor / ceil / round / trunc (src/base.jl:79,100,145,151): forward only, their own pass (round: ties to even, like Julia)
 floor = zerograd("floor", _round_fwd("floor"))
 ceil = zerograd("ceil", _round_fwd("ceil"))

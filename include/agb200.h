@@ -193,7 +193,9 @@ ag_status ag_unary_fwd(int32_t op, int32_t dtype, const void* x, void* y, int64_
  * quadrature / asymptotic expansion in double, csrc/ewise.cu); 10 = besseli(m, x), 11 = besselk(m, x) of integer order
  * (:13,24; ascending series / trapezoid rule for K0, K1 + upward recurrence; their rules (f(m-1,x) + f(m+1,x))/(+-2)
  * are composed by the host); 12 = floor, 13 = ceil, 14 = round (ties to even), 15 = trunc (the @zerograd rounding
- * functions of src/base.jl:79,100,145,151; m ignored).  One pass, y[i] = f(m, x[i]). */
+ * functions of src/base.jl:79,100,145,151; m ignored); 16 = exponent(x), 17 = significand(x) (src/math.jl:44,64),
+ * 18 = rem2pi(x, mode m: 0 nearest, 1 to zero, 2 down = mod2pi(x), 3 up; :56,59; reduction by the double 2*pi).
+ * One pass, y[i] = f(m, x[i]). */
 ag_status ag_special_param(int32_t op, int32_t dtype, int32_t m, const void* x, void* y, int64_t n);
 /* dx[i] = dy[i] * g(x[i], y[i]).  dy: device array (dy_mode 0), device scalar (1), or the
  * immediate dy_scalar (2).  x / y may be NULL when g does not use them.

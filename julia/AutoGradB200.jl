@@ -354,6 +354,11 @@ broadcasted(::typeof(log), b::Number, x::DArray) = scal(unary_fwd(UNARY[:log], x
 for (f, id) in ((:floor, 12), (:ceil, 13), (:round, 14), (:trunc, 15))
     @eval broadcasted(::typeof($f), x::DArray) = special_param($id, 0, x)
 end
+broadcasted(::typeof(exponent), x::DArray) = special_param(16, 0, x)
+broadcasted(::typeof(significand), x::DArray) = special_param(17, 0, x)
+broadcasted(::typeof(mod2pi), x::DArray) = special_param(18, 2, x)
+rmode(::RoundingMode{:Nearest}) = 0; rmode(::RoundingMode{:ToZero}) = 1; rmode(::RoundingMode{:Down}) = 2; rmode(::RoundingMode{:Up}) = 3
+broadcasted(::typeof(rem2pi), x::DArray, r::RoundingMode) = special_param(18, rmode(r), x)
 # binary broadcasting rules: fused kernel + unbroadcast (src/base.jl:21-49, src/math.jl:24,48,54-55)
 for (f, id) in BINARY
     f in (:(==), :<, :<=, :>, :>=) && continue                # @zerograd (src/base.jl:52-60)

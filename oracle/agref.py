@@ -722,6 +722,13 @@ ldexp = primitive("ldexp", lambda x, n: np.ldexp(x, n), lambda dy, y, x, n: mul(
 logb = primitive("log", _np(lambda b, x: np.log(x) / np.log(b)),                                                                # :48 log(b, x)
                  lambda dy, y, x1, x2: unbroadcast(x1, mul(dy, div(neg(log(x2)), mul(x1, abs2(log(x1)))))),
                  lambda dy, y, x1, x2: unbroadcast(x2, mul(dy, div(1, mul(x2, log(x1))))))
+exponent = lambda x: (np.frexp(value(x))[1] - 1).astype(np.asarray(value(x)).dtype)                                           # :44 @zerograd
+significand = primitive("significand", lambda x: (np.frexp(x)[0] * 2).astype(np.asarray(x).dtype),                              # :64
+                        lambda dy, y, x: mul(dy, np.exp2(-exponent(x))))
+mod2pi = primitive("mod2pi", lambda x: np.remainder(x, 2 * np.pi), lambda dy, y, x: dy)                                         # :56
+_REM = {"nearest": lambda x: x - 2 * np.pi * np.rint(x / (2 * np.pi)), "tozero": lambda x: np.fmod(x, 2 * np.pi),
+        "down": lambda x: np.remainder(x, 2 * np.pi), "up": lambda x: -np.remainder(-x, 2 * np.pi)}
+rem2pi = primitive("rem2pi", lambda x, r: _REM[r](x), lambda dy, y, x, r: dy)                                                   # :59
 # @zerograd rounding functions (src/base.jl:79,100,145,151)
 floor = lambda x: np.floor(value(x))
 ceil = lambda x: np.ceil(value(x))

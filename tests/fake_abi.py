@@ -443,6 +443,11 @@ class FakeLib:
         elif op == 10: r = sp.iv(m, v)
         elif op == 11: r = sp.kv(m, v)
         elif 12 <= op <= 15: r = (np.floor, np.ceil, np.rint, np.trunc)[op - 12](v)
+        elif op == 16: r = np.frexp(v)[1] - 1.0
+        elif op == 17: r = np.where(v == 0, v, np.frexp(v)[0] * 2.0)
+        elif op == 18:
+            P2 = 2 * np.pi
+            r = np.remainder(v, P2) if m == 2 else (np.fmod(v, P2) if m == 1 else (v - P2 * np.rint(v / P2) if m == 0 else -np.remainder(-v, P2)))
         else:
             return self._fail(5, "ag_special_param: op")
         _arr(y, n, T)[:] = r.astype(T)

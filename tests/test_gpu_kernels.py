@@ -421,6 +421,15 @@ def test_math_rest_on_device(ag, oracle, dtype, tol):
         ref, go = fo(x64), oracle.grad(lambda v: oracle.sum_(fo(v)))(x64)
         assert np.max(np.abs(fd(xd).to_numpy() - ref)) <= tol * max(np.max(np.abs(ref)), 1.0)
         assert np.max(np.abs(ag.grad(lambda v: ag.sum_(fd(v)))(xd).to_numpy() - go)) <= 5 * tol * max(np.max(np.abs(go)), 1.0)
+    xs = np.concatenate([rng.uniform(-40.0, 40.0, 500), [0.75, 1.0, 2.0, -3.999, 1e-3]]).astype(dtype)
+    xsd, xs64 = ag.DArray.from_numpy(xs), xs.astype(np.float64)
+    assert np.array_equal(ag.exponent(xsd).to_numpy(), oracle.exponent(xs)) and np.array_equal(ag.significand(xsd).to_numpy(), oracle.significand(xs))
+    assert np.max(np.abs(ag.mod2pi(xsd).to_numpy() - oracle.mod2pi(xs64))) <= 10 * tol
+    for r in ("nearest", "tozero", "down", "up"):
+        assert np.max(np.abs(ag.rem2pi(xsd, r).to_numpy() - oracle.rem2pi(xs64, r))) <= 10 * tol, r
+    gd = ag.grad(lambda v: ag.sum_(ag.mul(ag.significand(v), v)))(xsd).to_numpy()
+    go = oracle.grad(lambda v: oracle.sum_(oracle.mul(oracle.significand(v), v)))(xs64)
+    assert np.max(np.abs(gd - go)) <= 10 * tol * np.max(np.abs(go))
     z = np.array([0.0, 0.5, -1.5, 2.5, -0.2, 1e-3, 7.49, -7.51], dtype=dtype)
     zd = ag.DArray.from_numpy(z)
     assert ag.sinc(zd).to_numpy()[0] == 1.0 and ag.cosc(zd).to_numpy()[0] == 0.0

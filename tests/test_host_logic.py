@@ -348,6 +348,20 @@ def test_math_rest_host_rules_against_the_oracle(hostlib, oracle):
     # second order through the rules (they are compositions of recorded primitives): d2/dx2 sec = sec (tan^2 + sec^2)
     g2 = ag.grad(lambda v: ag.sum_(ag.grad(lambda u: ag.sum_(ag.sec(u)))(v)))(xd).to_numpy()
     assert np.allclose(g2, (np.tan(x) ** 2 + 1 / np.cos(x) ** 2) / np.cos(x), rtol=1e-11)
+    # exponent (@zerograd) / significand / mod2pi / rem2pi (src/math.jl:44,56,59,64)
+    xs = np.asfortranarray(np.concatenate([rng.uniform(-40.0, 40.0, 37), [0.75, 1.0, 2.0, -3.999, 1e-3]]))
+    xsd = ag.DArray.from_numpy(xs)
+    assert np.array_equal(ag.exponent(xsd).to_numpy(), oracle.exponent(xs))
+    assert np.array_equal(ag.significand(xsd).to_numpy(), oracle.significand(xs))
+    assert np.allclose(ag.mod2pi(xsd).to_numpy(), oracle.mod2pi(xs), atol=1e-13)
+    for r in ("nearest", "tozero", "down", "up"):
+        assert np.allclose(ag.rem2pi(xsd, r).to_numpy(), oracle.rem2pi(xs, r), atol=1e-13), r
+        assert abs(ag.rem2pi(7.5, r) - float(oracle.rem2pi(np.array([7.5]), r)[0])) < 1e-14
+    for fo, fd in ((oracle.significand, ag.significand), (oracle.mod2pi, ag.mod2pi),
+                   (lambda v: oracle.rem2pi(v, "up"), lambda v: ag.rem2pi(v, "up"))):
+        go = oracle.grad(lambda v: oracle.sum_(oracle.mul(fo(v), v)))(xs)
+        gd = ag.grad(lambda v: ag.sum_(ag.mul(fd(v), v)))(xsd).to_numpy()
+        assert np.allclose(gd, go, rtol=1e-12, atol=1e-13)
     # sinc(0) = 1, cosc(0) = 0; rounding functions are @zerograd (ties to even for round)
     z = ag.DArray.from_numpy(np.array([0.0, 0.5, -1.5, 2.5, -0.2]))
     assert np.array_equal(ag.sinc(z).to_numpy()[:1], [1.0]) and np.array_equal(ag.cosc(z).to_numpy()[:1], [0.0])
