@@ -1,0 +1,102 @@
+// linalg.cu -- inverse and determinant of a small dense matrix (src/linearalgebra.jl:18,28,57-58: det, inv, logdet,
+// logabsdet and the inv(x)' their rules read).  The reference calls LAPACK (getrf / getri) on the host; here one
+// thread block runs Gauss-Jordan elimination with partial pivoting on a double-precision copy [A | I] in the
+// workspace: the matrices these rules see are parameter-sized (a few hundred rows at most), the work is O(n^3) on one
+// SM and latency-bound, so there is nothing to tile -- it exists so that the rules run without a host round trip of
+// the matrix.  n <= 1024.
+#include "common.cuh"
+
+namespace agb {
+
+constexpr int kLuThreads = 1024;
+
+// W: n x 2n doubles, column-major (leading dimension n): columns 0..n-1 = A, n..2n-1 = I on entry; on exit columns
+// n..2n-1 hold inv(A).  info[0] = det, info[1] = log|det|, info[2] = sign(det).
+template <typename T>
+__global__ void __launch_bounds__(kLuThreads) k_gauss_jordan(const T* __restrict__ A, int n, double* __restrict__ W,
+                                                             T* __restrict__ inv, T* __restrict__ info) {
+  __shared__ double s_val[kLuThreads];
+  __shared__ int s_idx[kLuThreads];
+  __shared__ double s_col[1024];
+  __shared__ double s_det[3];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t nn = (int64_t)n * n;
+  for (int64_t e = tid; e < nn; e += nt) {
+    W[e] = (double)A[e];
+    W[nn + e] = (e % n == e / n) ? 1.0 : 0.0;
+  }
+  if (tid == 0) { s_det[0] = 1.0; s_det[1] = 0.0; s_det[2] = 1.0; }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    // pivot: the largest |W[i,k]|, i >= k (lowest row on ties, like getrf)
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < n; i += nt) {
+      const double v = fabs(W[(int64_t)k * n + i]);
+      if (v > best) { best = v; bi = i; }
+    }
+    s_val[tid] = best;
+    s_idx[tid] = bi;
+    __syncthreads();
+    for (int s = nt / 2; s > 0; s >>= 1) {
+      if (tid < s) {
+        const double o = s_val[tid + s];
+        const int oi = s_idx[tid + s];
+        if (o > s_val[tid] || (o == s_val[tid] && oi < s_idx[tid])) { s_val[tid] = o; s_idx[tid] = oi; }
+      }
+      __syncthreads();
+    }
+    const int p = s_idx[0];
+    __syncthreads();
+    if (p != k) {
+      for (int j = tid; j < 2 * n; j += nt) {
+        const double t = W[(int64_t)j * n + k];
+        W[(int64_t)j * n + k] = W[(int64_t)j * n + p];
+        W[(int64_t)j * n + p] = t;
+      }
+    }
+    __syncthreads();
+    const double piv = W[(int64_t)k * n + k];
+    if (tid == 0) {
+      s_det[0] *= (p != k) ? -piv : piv;
+      s_det[1] += log(fabs(piv));
+      if ((piv < 0.0) != (p != k)) s_det[2] = -s_det[2];
+      if (piv == 0.0) s_det[2] = 0.0;
+    }
+    for (int i = tid; i < n; i += nt) s_col[i] = (i == k) ? 0.0 : W[(int64_t)k * n + i];   // elimination factors
+    __syncthreads();
+    const double ip = 1.0 / piv;
+    for (int j = tid; j < 2 * n; j += nt) W[(int64_t)j * n + k] *= ip;                      // scale the pivot row
+    __syncthreads();
+    // rows i != k: W[i,j] -= f_i * W[k,j] for the columns that are not yet (A side) or already (I side) non-trivial
+    const int j0 = k, ncols = 2 * n - j0;
+    for (int64_t e = tid; e < (int64_t)ncols * n; e += nt) {
+      const int j = j0 + (int)(e / n), i = (int)(e % n);
+      if (i != k) W[(int64_t)j * n + i] -= s_col[i] * W[(int64_t)j * n + k];
+    }
+    __syncthreads();
+  }
+  if (inv)
+    for (int64_t e = tid; e < nn; e += nt) inv[e] = (T)W[nn + e];
+  if (info && tid < 3) info[tid] = (T)s_det[tid];
+}
+
+}  // namespace agb
+
+using namespace agb;
+
+extern "C" ag_status ag_inv_det(int32_t dtype, const void* a, int64_t n, void* inv_out, void* info_out) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_inv_det: dtype %d", dtype);
+  AG_CHECK(a && n >= 1 && (inv_out || info_out), AG_EINVAL, "ag_inv_det: bad arguments");
+  AG_CHECK(n <= 1024, AG_EUNSUPPORTED, "ag_inv_det: n = %lld (one-block elimination, n <= 1024)", (long long)n);
+  Context& c = ctx();
+  double* W = (double*)workspace((size_t)(2 * n * n) * sizeof(double));
+  AG_CHECK(W, AG_ENOMEM, "ag_inv_det: workspace");
+  if (dtype == AG_F32)
+    k_gauss_jordan<float><<<1, kLuThreads, 0, c.stream>>>((const float*)a, (int)n, W, (float*)inv_out, (float*)info_out);
+  else
+    k_gauss_jordan<double><<<1, kLuThreads, 0, c.stream>>>((const double*)a, (int)n, W, (double*)inv_out, (double*)info_out);
+  AG_LAUNCHED();
+  return AG_OK;
+}

@@ -874,6 +874,20 @@ SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3, dawson=4, erfi=5, air
           exponent=16, significand=17, rem2pi=18)
 
 
+def inv_det(x, want_inv=True):
+    """(inv(x) or None, (det, log|det|, sign)) of a square matrix in one launch (ag_inv_det); the three scalars are
+    read back to the host."""
+    x = materialize(x)
+    if len(x.shape) != 2 or x.shape[0] != x.shape[1]:
+        raise L.DimensionMismatch("matrix is not square: dimensions are %r" % (tuple(x.shape),))
+    n = x.shape[0]
+    inv = DArray.empty(x.shape, x.dtype) if want_inv else None
+    info = DArray.empty((3,), x.dtype)
+    check(lib.ag_inv_det(x.dt, vptr(x), n, vptr(inv) if want_inv else None, vptr(info)))
+    d = info.to_numpy()
+    return inv, (float(d[0]), float(d[1]), float(d[2]))
+
+
 def special_param(name, m, x):
     """besselj(m, x) / bessely(m, x) of integer order, polygamma(m, x), invdigamma(x), dawson / erfi / the four Airy
     functions (m ignored) (ag_special_param): one pass."""

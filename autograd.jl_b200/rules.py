@@ -871,6 +871,52 @@ def tr(x):
     return sum_(diag(x))
 
 
+# det / inv / logdet / logabsdet (src/linearalgebra.jl:18,28,57-58): one-launch elimination (ag_inv_det); the rules are
+# the reference's expressions over inv, adjoint and the matrix product
+def _inv_fwd(x):
+    if not isinstance(x, DArray):
+        return 1.0 / x
+    return D.inv_det(x)[0]
+
+
+def _det_fwd(x):
+    return D.inv_det(x, want_inv=False)[1][0] if isinstance(x, DArray) else x
+
+
+def _logdet_fwd(x):
+    if not isinstance(x, DArray):
+        return math.log(x)
+    _, (_, lad, sign) = D.inv_det(x, want_inv=False)
+    if sign < 0:
+        raise ValueError("DomainError: logdet of a matrix with negative determinant")
+    return lad
+
+
+def _yt_dy_yt(dy, y):
+    yt = adjoint(y)
+    return neg(matmul(matmul(yt, dy), yt))
+
+
+inv = primitive("inv", _inv_fwd, lambda dy, y, x: _yt_dy_yt(dy, y))                                # :28  (yt=y'; -yt*dy*yt)
+det = primitive("det", _det_fwd, lambda dy, y, x: mul(mul(dy, y), adjoint(inv(x))))                # :18  dy*y*inv(x)'
+logdet = primitive("logdet", _logdet_fwd, lambda dy, y, x: mul(dy, adjoint(inv(x))))               # :58  dy*inv(x)'
+
+
+def logabsdet(x):
+    """`logabsdet(x)` -> (log|det|, sign); the gradient flows through the first element (src/linearalgebra.jl:57:
+    dy[1]*inv(x)'), the sign is a constant."""
+    v = value(x)
+    sign = D.inv_det(v, want_inv=False)[1][2] if isinstance(v, DArray) else (1.0 if v >= 0 else -1.0)
+    return _logabsdet1(x), sign
+
+
+def _lad_fwd(x):
+    return D.inv_det(x, want_inv=False)[1][1] if isinstance(x, DArray) else math.log(abs(x))
+
+
+_logabsdet1 = primitive("logabsdet", _lad_fwd, lambda dy, y, x: mul(dy, adjoint(inv(x))))
+
+
 _TRI_MASKS = {}
 
 

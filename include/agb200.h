@@ -197,6 +197,12 @@ ag_status ag_unary_fwd(int32_t op, int32_t dtype, const void* x, void* y, int64_
  * 18 = rem2pi(x, mode m: 0 nearest, 1 to zero, 2 down = mod2pi(x), 3 up; :56,59; reduction by the double 2*pi).
  * One pass, y[i] = f(m, x[i]). */
 ag_status ag_special_param(int32_t op, int32_t dtype, int32_t m, const void* x, void* y, int64_t n);
+/* inv(a) and the determinant of an n x n column-major matrix (n <= 1024) in one launch: Gauss-Jordan elimination with
+ * partial pivoting in double.  inv_out (n x n, may be NULL) receives inv(a); info_out (3 values of the matrix dtype, may
+ * be NULL) receives det(a), log|det(a)|, sign(det(a)).  A singular matrix gives det 0 and non-finite inverse entries.
+ * Replaces the LAPACK calls behind det / inv / logdet / logabsdet and the inv(x)' of their rules
+ * (src/linearalgebra.jl:18,28,57-58). */
+ag_status ag_inv_det(int32_t dtype, const void* a, int64_t n, void* inv_out, void* info_out);
 /* dx[i] = dy[i] * g(x[i], y[i]).  dy: device array (dy_mode 0), device scalar (1), or the
  * immediate dy_scalar (2).  x / y may be NULL when g does not use them.
  * Replaces the broadcast expression in each rule of src/math.jl:9-74. */

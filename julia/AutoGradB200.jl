@@ -359,6 +359,26 @@ broadcasted(::typeof(significand), x::DArray) = special_param(17, 0, x)
 broadcasted(::typeof(mod2pi), x::DArray) = special_param(18, 2, x)
 rmode(::RoundingMode{:Nearest}) = 0; rmode(::RoundingMode{:ToZero}) = 1; rmode(::RoundingMode{:Down}) = 2; rmode(::RoundingMode{:Up}) = 3
 broadcasted(::typeof(rem2pi), x::DArray, r::RoundingMode) = special_param(18, rmode(r), x)
+# det / inv / logdet / logabsdet (src/linearalgebra.jl:18,28,57-58): forward methods through ag_inv_det (one launch);
+# the reference's rules (dy*y*inv(x)', -y'*dy*y', dy*inv(x)') are matrix products over these
+import LinearAlgebra
+function inv_det(x::DArray{T,2}, want_inv::Bool) where T
+    n = size(x, 1)
+    n == size(x, 2) || throw(DimensionMismatch("matrix is not square: dimensions are $(size(x))"))
+    iv = want_inv ? similar(x) : nothing
+    info = DArray{T}(undef, (3,))
+    check(ccall((:ag_inv_det, LIB), Int32, (Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                dtcode(T), x.ptr, n, want_inv ? iv.ptr : C_NULL, info.ptr))
+    iv, Array(info)                                   # (inv or nothing, [det, log|det|, sign])
+end
+LinearAlgebra.inv(x::DArray{T,2}) where T = inv_det(x, true)[1]
+LinearAlgebra.det(x::DArray{T,2}) where T = inv_det(x, false)[2][1]
+LinearAlgebra.logabsdet(x::DArray{T,2}) where T = (d = inv_det(x, false)[2]; (d[2], d[3]))
+function LinearAlgebra.logdet(x::DArray{T,2}) where T
+    d = inv_det(x, false)[2]
+    d[3] < 0 && throw(DomainError(d[1], "determinant is negative"))
+    d[2]
+end
 # binary broadcasting rules: fused kernel + unbroadcast (src/base.jl:21-49, src/math.jl:24,48,54-55)
 for (f, id) in BINARY
     f in (:(==), :<, :<=, :>, :>=) && continue                # @zerograd (src/base.jl:52-60)

@@ -828,6 +828,13 @@ triu = primitive("triu", lambda x: np.asfortranarray(np.triu(x)),
                  lambda dy, y, x: mul(dy, np.asfortranarray(np.triu(np.ones_like(value(x))))))
 
 
+# src/linearalgebra.jl:18 (det), :28 (inv), :58 (logdet) through numpy.linalg (LAPACK, like the reference)
+inv = primitive("inv", lambda x: np.asfortranarray(np.linalg.inv(x)),
+                lambda dy, y, x: neg(matmul(matmul(adjoint(y), dy), adjoint(y))))
+det = primitive("det", lambda x: np.linalg.det(x), lambda dy, y, x: mul(mul(dy, y), adjoint(inv(x))))
+logdet = primitive("logdet", lambda x: np.linalg.slogdet(x)[1], lambda dy, y, x: mul(dy, adjoint(inv(x))))
+
+
 def kron(a, b):
     (m1, n1), (m2, n2) = np.shape(value(a)), np.shape(value(b))
     return reshape(mul(reshape(a, (1, m1, 1, n1)), reshape(b, (m2, 1, n2, 1))), (m1 * m2, n1 * n2))

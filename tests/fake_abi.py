@@ -425,6 +425,17 @@ class FakeLib:
     def ag_sum_all(self, m, dtype, x, n, out):
         return self.ag_sum_dim(m, dtype, x, 1, n, 1, out)
 
+    def ag_inv_det(self, dtype, a, n, inv_out, info_out):
+        self.launches += 1
+        T = _DT[dtype]
+        A = _arr(a, n * n, T).astype(np.float64).reshape(n, n, order="F")
+        if inv_out:
+            _arr(inv_out, n * n, T)[:] = np.linalg.inv(A).reshape(-1, order="F").astype(T)
+        if info_out:
+            sign, lad = np.linalg.slogdet(A)
+            _arr(info_out, 3, T)[:] = np.array([np.linalg.det(A), lad, sign]).astype(T)
+        return 0
+
     def ag_special_param(self, op, dtype, m, x, y, n):
         import scipy.special as sp
         self.launches += 1

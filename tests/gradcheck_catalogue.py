@@ -65,6 +65,8 @@ def check_catalogue(ag):
     assert ag.gradcheck(ag.diag, a) and ag.gradcheck(ag.tr, sq) and ag.gradcheck(ag.tril, sq) and ag.gradcheck(ag.triu, a)
     assert ag.gradcheck(ag.diagm, dev(rng.standard_normal(3))) and ag.gradcheck(lambda z: ag.diagm(z, -1), dev(rng.standard_normal(3)))
     assert ag.gradcheck(ag.kron, dev(rng.standard_normal((2, 3))), dev(rng.standard_normal((4, 5))))
+    wellc = dev(rng.standard_normal((4, 4)) * 0.3 + 2 * np.eye(4))
+    assert ag.gradcheck(ag.inv, wellc) and ag.gradcheck(ag.det, wellc) and ag.gradcheck(ag.logdet, wellc)
     m1, m2 = dev(rng.standard_normal((4, 3))), dev(rng.standard_normal((3, 5)))
     assert ag.gradcheck(ag.matmul, m1, m2)
     assert ag.gradcheck(lambda p, q: ag.matmul(ag.adjoint(p), q), dev(rng.standard_normal((3, 4))), m2)

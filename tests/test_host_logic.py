@@ -439,3 +439,43 @@ def test_linear_algebra_helpers_host_rules(hostlib, oracle):
     go = oracle.grad(lambda q: oracle.sum_(oracle.mul(oracle.kron(a64, q), wk)))(b64)
     gd = hostlib.grad(lambda q: hostlib.sum_(hostlib.mul(hostlib.kron(ad, q), wkd)))(bd).to_numpy()
     assert np.max(np.abs(gd - go)) <= 1e-12 * 20
+
+
+def test_inv_det_logdet_host_rules(hostlib, oracle):
+    ag = hostlib
+    """inv / det / logdet / logabsdet (src/linearalgebra.jl:18,28,57-58; ag_inv_det: one-launch Gauss-Jordan elimination
+    with partial pivoting): values against LAPACK (numpy.linalg), gradients against the oracle's rules, a matrix that
+    needs row exchanges, a singular one."""
+    rng = np.random.default_rng(53)
+    for n in (1, 2, 5, 33, 130):
+        A = np.asfortranarray((rng.standard_normal((n, n)) + (0.0 if n < 33 else 0.2) * np.eye(n)).astype(np.float64))
+        Ad, A64 = ag.DArray.from_numpy(A), A.astype(np.float64)
+        scale = np.linalg.cond(A64)
+        got = ag.inv(Ad).to_numpy()
+        assert got.dtype == np.float64 and np.max(np.abs(got - np.linalg.inv(A64))) <= 1e-12 * scale * max(np.max(np.abs(np.linalg.inv(A64))), 1.0), n
+        sign, lad = np.linalg.slogdet(A64)
+        assert abs(np.linalg.det(A64)) > 1e30 or abs(ag.det(Ad) - np.linalg.det(A64)) <= 1e-12 * scale * abs(np.linalg.det(A64)), n
+        l, s = ag.logabsdet(Ad)
+        assert abs(l - lad) <= 1e-12 * scale * max(abs(lad), 1.0) and s == sign, n
+    P = np.asfortranarray(np.array([[0.0, 2.0, 1.0], [1.0, 0.0, 3.0], [4.0, 1.0, 0.0]], dtype=np.float64))      # zero leading pivots
+    assert np.allclose(ag.inv(ag.DArray.from_numpy(P)).to_numpy(), np.linalg.inv(P.astype(np.float64)), atol=1e-12 * 10)
+    assert abs(ag.det(ag.DArray.from_numpy(P)) - 25.0) <= 1e-12 * 100
+    S = np.asfortranarray(np.array([[1.0, 2.0], [2.0, 4.0]], dtype=np.float64))
+    assert ag.det(ag.DArray.from_numpy(S)) == 0.0
+    spd = rng.standard_normal((6, 6))
+    spd = np.asfortranarray((spd @ spd.T + 6 * np.eye(6)).astype(np.float64))
+    spdd, spd64 = ag.DArray.from_numpy(spd), np.asfortranarray(spd.astype(np.float64))
+    assert abs(ag.logdet(spdd) - np.linalg.slogdet(spd64)[1]) <= 1e-12 * 100
+    w = np.asfortranarray(rng.standard_normal((6, 6)))
+    wd = ag.DArray.from_numpy(w.astype(np.float64))
+    go = oracle.grad(lambda z: oracle.sum_(oracle.mul(oracle.inv(z), w)))(spd64)
+    gd = ag.grad(lambda z: ag.sum_(ag.mul(ag.inv(z), wd)))(spdd).to_numpy()
+    assert np.max(np.abs(gd - go)) <= 1e-12 * 1e3 * np.max(np.abs(go))
+    for fo, fd in ((oracle.det, ag.det), (oracle.logdet, ag.logdet)):
+        go = oracle.grad(fo)(spd64)
+        gd = ag.grad(fd)(spdd).to_numpy()
+        assert np.max(np.abs(gd - go)) <= 1e-12 * 1e3 * np.max(np.abs(go)), fd
+    gd = ag.grad(lambda z: ag.logabsdet(z)[0])(spdd).to_numpy()
+    assert np.max(np.abs(gd - np.linalg.inv(spd64).T)) <= 1e-12 * 1e3
+    with pytest.raises(ag.DimensionMismatch):
+        ag.inv(ag.DArray.from_numpy(np.asfortranarray(np.ones((2, 3), dtype=np.float64))))
