@@ -837,6 +837,56 @@ getindex = primitive("getindex", _getindex_fwd, lambda dxi, xi, x, *idx: ungetin
                      only_first=True)
 
 # ---------------------------------------------------------------------------------------------------
+# the @zerograd helpers of src/base.jl:52-62,75-160 that touch array VALUES: predicates, counts, integer division.
+# Each unboxes, computes on the device with the table's ops, and is never recorded.
+# ---------------------------------------------------------------------------------------------------
+
+def _z(name, f):
+    return zerograd(name, f)
+
+
+ne = _z("!=", lambda a, b: sub(1, eq(a, b)))
+isnan = _z("isnan", lambda x: sub(1, eq(x, x)))
+isinf = _z("isinf", lambda x: eq(abs_(x), math.inf))
+isfinite = _z("isfinite", lambda x: lt(abs_(x), math.inf))
+isinteger = _z("isinteger", lambda x: mul(isfinite(x), eq(x, trunc(x))))
+signbit = _z("signbit", lambda x: lt(atan2(x, -1.0), 0))        # atan2(-0.0, -1) = -pi: the sign bit of zeros too
+
+
+def _count(m):
+    v = sum_(m)
+    return int(round(float(v.to_numpy()) if isinstance(v, DArray) else float(v)))
+
+
+count = _z("count", _count)                                     # count(mask): number of non-zero mask entries
+any_ = _z("any", lambda m: _count(m) > 0)
+all_ = _z("all", lambda m: _count(m) == length(m))
+isequal = _z("isequal", lambda a, b: size(a) == size(b) and _count(add(eq(a, b), mul(isnan(a), isnan(b)))) == length(a))
+isapprox = _z("isapprox", lambda a, b, rtol=None, atol=0.0: float(value(norm(sub(a, b)))) <= max(
+    atol, (math.sqrt(float(np.finfo(value(a).dtype if isinstance(value(a), DArray) else np.float64).eps)) if rtol is None else rtol)
+    * max(float(value(norm(a))), float(value(norm(b))))))
+div_ = _z("div", lambda a, b: trunc(div(a, b)))                  # div(x, y) = trunc(x / y)
+rem = _z("rem", lambda a, b: sub(a, mul(b, trunc(div(a, b)))))  # rem(x, y) = x - y * trunc(x / y)
+unsafe_trunc = trunc
+widemul = _z("widemul", lambda a, b: mul(a, b))
+float_ = _z("float", lambda x: x)                                # device arrays are Float32 / Float64 already
+eltype = _z("eltype", lambda x: x.dtype if isinstance(x, DArray) else type(x))
+eps = _z("eps", lambda x: float(np.finfo(x.dtype).eps) if isinstance(x, DArray) else float(np.spacing(x)))
+typemax = _z("typemax", lambda x: math.inf)
+typemin = _z("typemin", lambda x: -math.inf)
+sizeof = _z("sizeof", lambda x: x.size * np.dtype(x.dtype).itemsize if isinstance(x, DArray) else 8)
+isempty = _z("isempty", lambda x: length(x) == 0)
+axes = _z("axes", lambda x: tuple(range(n) for n in size(x)))
+eachindex = _z("eachindex", lambda x: range(length(x)))
+lastindex = _z("lastindex", lambda x: length(x) - 1)            # 0-based like every index on the Python side
+strides = _z("strides", lambda x: tuple(int(np.prod(size(x)[:d])) for d in range(ndims(x))))   # column-major
+stride = _z("stride", lambda x, d: int(np.prod(size(x)[:d])))
+similar = _z("similar", lambda x: DArray.empty(x.shape, x.dtype))
+zero = _z("zero", lambda x: D.zeros(x.shape, x.dtype) if isinstance(x, DArray) else type(x)(0))
+ones = _z("ones", lambda x: D.full_like_shape(x.shape, x.dtype, 1.0) if isinstance(x, DArray) else D.full_like_shape(tuple(x), np.float64, 1.0))
+
+
+# ---------------------------------------------------------------------------------------------------
 # diag / diagm / tr / tril / triu / kron (src/linearalgebra.jl:19-20,46-48,86,90,92,176-186)
 # ---------------------------------------------------------------------------------------------------
 

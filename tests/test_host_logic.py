@@ -479,3 +479,31 @@ def test_inv_det_logdet_host_rules(hostlib, oracle):
     assert np.max(np.abs(gd - np.linalg.inv(spd64).T)) <= 1e-12 * 1e3
     with pytest.raises(ag.DimensionMismatch):
         ag.inv(ag.DArray.from_numpy(np.asfortranarray(np.ones((2, 3), dtype=np.float64))))
+
+
+def test_zerograd_value_helpers_host(hostlib):
+    ag = hostlib
+    """The value-touching @zerograd helpers of src/base.jl (predicates, counts, integer division, array queries): device
+    results against numpy; a Value argument is unboxed and nothing is recorded."""
+    x = np.asfortranarray(np.array([[1.5, -2.0, np.nan, 0.0], [np.inf, -np.inf, -0.0, 7.0], [3.25, -3.0, 2.0, -7.5]], dtype=np.float64))
+    xd = ag.DArray.from_numpy(x)
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(ag.isnan(xd).to_numpy(), np.isnan(x).astype(np.float64)) and np.array_equal(ag.isinf(xd).to_numpy(), np.isinf(x).astype(np.float64))
+        assert np.array_equal(ag.isfinite(xd).to_numpy(), np.isfinite(x).astype(np.float64))
+        assert np.array_equal(ag.signbit(xd).to_numpy()[~np.isnan(x)], np.signbit(x)[~np.isnan(x)].astype(np.float64))
+        assert np.array_equal(ag.isinteger(xd).to_numpy(), (np.isfinite(x) & (x == np.trunc(x))).astype(np.float64))
+    assert ag.count(ag.isnan(xd)) == 1 and ag.any_(ag.isinf(xd)) and not ag.all_(ag.isfinite(xd)) and ag.all_(ag.eq(xd, xd)) is False
+    a = np.asfortranarray(np.array([[7.5, -7.5, 9.0], [2.0, 3.0, -4.0]], dtype=np.float64))
+    b = np.asfortranarray(np.array([[2.0, 2.0, -4.0], [0.5, 5.0, 3.0]], dtype=np.float64))
+    ad, bd = ag.DArray.from_numpy(a), ag.DArray.from_numpy(b)
+    assert np.array_equal(ag.div_(ad, bd).to_numpy(), np.trunc(a / b)) and np.array_equal(ag.rem(ad, bd).to_numpy(), np.fmod(a, b))
+    assert np.array_equal(ag.ne(ad, bd).to_numpy(), (a != b).astype(np.float64)) and np.array_equal(ag.widemul(ad, bd).to_numpy(), a * b)
+    assert ag.isequal(xd, ag.DArray.from_numpy(x.copy(order="F"))) and not ag.isequal(ad, bd) and not ag.isequal(ad, xd)
+    assert ag.isapprox(ad, ag.DArray.from_numpy(np.asfortranarray(a * (1 + 1e-9 if np.float64 == np.float64 else 1 + 1e-5)))) and not ag.isapprox(ad, bd)
+    assert ag.eltype(ad) == np.float64 and ag.eps(ad) == float(np.finfo(np.float64).eps) and ag.sizeof(ad) == a.nbytes and not ag.isempty(ad)
+    assert ag.strides(ad) == (1, 2) and ag.stride(ad, 1) == 2 and ag.lastindex(ad) == 5 and ag.axes(ad) == (range(2), range(3))
+    assert ag.similar(ad).shape == (2, 3) and not np.any(ag.zero(ad).to_numpy()) and np.all(ag.ones(ad).to_numpy() == 1)
+    assert ag.typemax(ad) == np.inf and ag.typemin(ad) == -np.inf and ag.float_(ad) is ad
+    # unboxing: inside a tape the helpers see the Param's value and contribute no gradient
+    g = ag.grad(lambda v: ag.sum_(ag.mul(v, ag.isfinite(v))))(ad).to_numpy()
+    assert np.array_equal(g, np.ones_like(a))
