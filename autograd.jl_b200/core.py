@@ -83,6 +83,16 @@ class Value:
     def __neg__(self): return _r().neg(self)
     def __getitem__(self, i): return _r().getindex(self, *(i if isinstance(i, tuple) else (i,)))
 
+    # iteration in terms of getindex, which does the tracking (src/iterate.jl:6-17): `for e in v`, `a, b = v`
+    def __len__(self): return _r().length(self)
+
+    def __iter__(self):
+        if isinstance(self.value, (int, float)):      # iterate(::Value{<:Number}) yields the Value itself once
+            yield self
+            return
+        for i in range(_r().length(self)):
+            yield self[i]
+
     @property
     def T(self): return _r().adjoint(self)
 

@@ -507,3 +507,24 @@ def test_zerograd_value_helpers_host(hostlib):
     # unboxing: inside a tape the helpers see the Param's value and contribute no gradient
     g = ag.grad(lambda v: ag.sum_(ag.mul(v, ag.isfinite(v))))(ad).to_numpy()
     assert np.array_equal(g, np.ones_like(a))
+
+
+def test_iterating_a_tracked_array_goes_through_getindex(hostlib, oracle):
+    """src/iterate.jl:6-17: `for e in v` and `a, b, c = v` on a tracked array are getindex calls, so the elements are
+    tracked and the gradient comes back through ungetindex."""
+    ag = hostlib
+    x = np.asfortranarray(np.array([1.5, -2.0, 0.5]))
+    xd = ag.DArray.from_numpy(x)
+
+    def f(v):
+        a, b, c = v
+        t = ag.mul(a, b)
+        for e in v:
+            t = ag.add(t, ag.mul(e, c))
+        return t
+    g = ag.grad(f)(xd)
+    g = g.full().to_numpy() if hasattr(g, "full") else g.to_numpy()
+    # f = a b + (a + b + c) c
+    assert np.allclose(g, [x[1] + x[2], x[0] + x[2], x[0] + x[1] + 2 * x[2]])
+    p = ag.Param(2.5)
+    assert [e is p for e in p] == [True]
