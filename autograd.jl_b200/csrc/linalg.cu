@@ -4,6 +4,7 @@
 // workspace: the matrices these rules see are parameter-sized (a few hundred rows at most), the work is O(n^3) on one
 // SM and latency-bound, so there is nothing to tile -- it exists so that the rules run without a host round trip of
 // the matrix.  n <= 1024.
+#include <algorithm>
 #include "common.cuh"
 
 namespace agb {
@@ -81,9 +82,67 @@ __global__ void __launch_bounds__(kLuThreads) k_gauss_jordan(const T* __restrict
   if (info && tid < 3) info[tid] = (T)s_det[tid];
 }
 
+// ---- argmax / argmin of the vectorised array (@zerograd in src/base.jl:60-61): first index of the extremum, a NaN wins
+// (Julia's order), two phases: one candidate per block, then one block over the candidates.
+struct Cand { double v; int64_t i; };
+
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b, bool want_max) {   // is a preferred over b?
+  if (b.i < 0) return a.i >= 0;
+  if (a.i < 0) return false;
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  if (an || bn) return an && (!bn || a.i < b.i);
+  if (a.v == b.v) return a.i < b.i;
+  return want_max ? a.v > b.v : a.v < b.v;
+}
+
+__device__ __forceinline__ Cand cand_block_reduce(Cand c, bool want_max) {
+  __shared__ Cand s[256];
+  s[threadIdx.x] = c;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w && cand_better(s[threadIdx.x + w], s[threadIdx.x], want_max)) s[threadIdx.x] = s[threadIdx.x + w];
+    __syncthreads();
+  }
+  return s[0];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_argext_blocks(const T* __restrict__ x, int64_t n, bool want_max, Cand* __restrict__ out) {
+  Cand best = {0.0, -1};
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const Cand c = {(double)x[i], i};
+    if (cand_better(c, best, want_max)) best = c;
+  }
+  best = cand_block_reduce(best, want_max);
+  if (threadIdx.x == 0) out[blockIdx.x] = best;
+}
+
+__global__ void __launch_bounds__(256) k_argext_final(const Cand* __restrict__ in, int nb, bool want_max, int64_t* __restrict__ idx) {
+  Cand best = {0.0, -1};
+  for (int b = threadIdx.x; b < nb; b += 256)
+    if (cand_better(in[b], best, want_max)) best = in[b];
+  best = cand_block_reduce(best, want_max);
+  if (threadIdx.x == 0) *idx = best.i;
+}
+
 }  // namespace agb
 
 using namespace agb;
+
+extern "C" ag_status ag_argext(int32_t dtype, const void* x, int64_t n, int32_t want_max, int64_t* idx_out) {
+  AG_REQUIRE_INIT();
+  AG_CHECK(dtype == AG_F32 || dtype == AG_F64, AG_EUNSUPPORTED, "ag_argext: dtype %d", dtype);
+  AG_CHECK(x && idx_out && n >= 1, AG_EINVAL, "ag_argext: bad arguments (an empty collection has no extremum)");
+  Context& c = ctx();
+  const int nb = (int)std::min<int64_t>(cdiv(n, (int64_t)256), 148 * 8);
+  Cand* part = (Cand*)workspace((size_t)nb * sizeof(Cand));
+  AG_CHECK(part, AG_ENOMEM, "ag_argext: workspace");
+  if (dtype == AG_F32) k_argext_blocks<float><<<nb, 256, 0, c.stream>>>((const float*)x, n, want_max != 0, part);
+  else k_argext_blocks<double><<<nb, 256, 0, c.stream>>>((const double*)x, n, want_max != 0, part);
+  k_argext_final<<<1, 256, 0, c.stream>>>(part, nb, want_max != 0, idx_out);
+  AG_LAUNCHED();
+  return AG_OK;
+}
 
 extern "C" ag_status ag_inv_det(int32_t dtype, const void* a, int64_t n, void* inv_out, void* info_out) {
   AG_REQUIRE_INIT();

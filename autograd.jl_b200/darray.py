@@ -874,6 +874,19 @@ SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3, dawson=4, erfi=5, air
           exponent=16, significand=17, rem2pi=18)
 
 
+def argext(x, want_max):
+    """0-based column-major position of the first maximum / minimum of x (ag_argext); read back to the host."""
+    x = materialize(x)
+    if x.size == 0:
+        raise ValueError("ArgumentError: collection must be non-empty")
+    out = _Buffer(8)
+    check(lib.ag_argext(x.dt, vptr(x), x.size, 1 if want_max else 0, C.c_void_p(out.ptr)))
+    host = np.zeros(1, dtype=np.int64)
+    check(lib.ag_copy_d2h(host.ctypes.data_as(C.c_void_p), C.c_void_p(out.ptr), 8))
+    sync()
+    return int(host[0])
+
+
 def inv_det(x, want_inv=True):
     """(inv(x) or None, (det, log|det|, sign)) of a square matrix in one launch (ag_inv_det); the three scalars are
     read back to the host."""

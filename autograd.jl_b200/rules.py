@@ -858,6 +858,8 @@ def _count(m):
     return int(round(float(v.to_numpy()) if isinstance(v, DArray) else float(v)))
 
 
+argmax = _z("argmax", lambda x: D.argext(x, True) if isinstance(x, DArray) else 0)      # 0-based linear (column-major) index
+argmin = _z("argmin", lambda x: D.argext(x, False) if isinstance(x, DArray) else 0)
 count = _z("count", _count)                                     # count(mask): number of non-zero mask entries
 any_ = _z("any", lambda m: _count(m) > 0)
 all_ = _z("all", lambda m: _count(m) == length(m))

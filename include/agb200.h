@@ -203,6 +203,9 @@ ag_status ag_special_param(int32_t op, int32_t dtype, int32_t m, const void* x, 
  * Replaces the LAPACK calls behind det / inv / logdet / logabsdet and the inv(x)' of their rules
  * (src/linearalgebra.jl:18,28,57-58). */
 ag_status ag_inv_det(int32_t dtype, const void* a, int64_t n, void* inv_out, void* info_out);
+/* *idx_out (device int64) = 0-based position of the first maximum (want_max != 0) or minimum of x[0..n); a NaN wins,
+ * like Julia's argmax / argmin (@zerograd, src/base.jl:60-61).  Two launches. */
+ag_status ag_argext(int32_t dtype, const void* x, int64_t n, int32_t want_max, int64_t* idx_out);
 /* dx[i] = dy[i] * g(x[i], y[i]).  dy: device array (dy_mode 0), device scalar (1), or the
  * immediate dy_scalar (2).  x / y may be NULL when g does not use them.
  * Replaces the broadcast expression in each rule of src/math.jl:9-74. */

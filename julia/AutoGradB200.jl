@@ -379,6 +379,18 @@ function LinearAlgebra.logdet(x::DArray{T,2}) where T
     d[3] < 0 && throw(DomainError(d[1], "determinant is negative"))
     d[2]
 end
+# argmax / argmin (@zerograd, src/base.jl:60-61): first position of the extremum, 1-based linear index on this side
+function argext(x::DArray{T}, want_max::Bool) where T
+    isempty(x) && throw(ArgumentError("collection must be non-empty"))
+    out = Buffer(8)
+    check(ccall((:ag_argext, LIB), Int32, (Int32, Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}), dtcode(T), x.ptr, length(x), want_max ? 1 : 0, out.ptr))
+    host = Ref{Int64}(0)
+    check(ccall((:ag_copy_d2h, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), host, out.ptr, 8))
+    sync()
+    host[] + 1
+end
+Base.argmax(x::DArray) = argext(x, true)
+Base.argmin(x::DArray) = argext(x, false)
 # binary broadcasting rules: fused kernel + unbroadcast (src/base.jl:21-49, src/math.jl:24,48,54-55)
 for (f, id) in BINARY
     f in (:(==), :<, :<=, :>, :>=) && continue                # @zerograd (src/base.jl:52-60)

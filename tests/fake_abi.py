@@ -425,6 +425,14 @@ class FakeLib:
     def ag_sum_all(self, m, dtype, x, n, out):
         return self.ag_sum_dim(m, dtype, x, 1, n, 1, out)
 
+    def ag_argext(self, dtype, x, n, want_max, idx_out):
+        self.launches += 2
+        v = _arr(x, n, _DT[dtype])
+        nan = np.isnan(v)
+        i = int(np.argmax(nan)) if nan.any() else int(np.argmax(v) if want_max else np.argmin(v))
+        _arr(idx_out, 1, np.int64)[0] = i
+        return 0
+
     def ag_inv_det(self, dtype, a, n, inv_out, info_out):
         self.launches += 1
         T = _DT[dtype]

@@ -504,6 +504,14 @@ def test_zerograd_value_helpers_host(hostlib):
     assert ag.strides(ad) == (1, 2) and ag.stride(ad, 1) == 2 and ag.lastindex(ad) == 5 and ag.axes(ad) == (range(2), range(3))
     assert ag.similar(ad).shape == (2, 3) and not np.any(ag.zero(ad).to_numpy()) and np.all(ag.ones(ad).to_numpy() == 1)
     assert ag.typemax(ad) == np.inf and ag.typemin(ad) == -np.inf and ag.float_(ad) is ad
+    big = np.asfortranarray(np.random.default_rng(59).standard_normal((257, 1031)).astype(np.float64))
+    big[5, 7] = big[200, 900] = 9.0
+    big[100, 3] = big[11, 1000] = -9.0
+    bigd = ag.DArray.from_numpy(big)
+    flat = big.reshape(-1, order="F")
+    assert ag.argmax(bigd) == int(np.argmax(flat)) == 5 + 7 * 257 and ag.argmin(bigd) == int(np.argmin(flat)) == 100 + 3 * 257
+    assert ag.argmax(xd) == ag.argmin(xd) == 2 * 3 + 0                   # the NaN at (0, 2) wins both, like Julia
+    assert ag.argmax(ag.Param(bigd)) == 5 + 7 * 257
     # unboxing: inside a tape the helpers see the Param's value and contribute no gradient
     g = ag.grad(lambda v: ag.sum_(ag.mul(v, ag.isfinite(v))))(ad).to_numpy()
     assert np.array_equal(g, np.ones_like(a))
