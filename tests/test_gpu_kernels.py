@@ -639,3 +639,25 @@ def test_zerograd_value_helpers_on_device(ag, dtype):
     # unboxing: inside a tape the helpers see the Param's value and contribute no gradient
     g = ag.grad(lambda v: ag.sum_(ag.mul(v, ag.isfinite(v))))(ad).to_numpy()
     assert np.array_equal(g, np.ones_like(a))
+
+
+def test_inv_det_limits_and_tracked_iteration(ag):
+    """ag_inv_det refuses n > 1024 loudly (no fallback); iterating a tracked device array goes through getindex
+    (src/iterate.jl:6-17) and the gradient comes back through the Sparse scatter."""
+    big = ag.DArray.from_numpy(np.asfortranarray(np.eye(1025, dtype=np.float32)))
+    with pytest.raises(ag.UnsupportedOnDevice):
+        ag.inv(big)
+    ok = ag.DArray.from_numpy(np.asfortranarray(2 * np.eye(1024, dtype=np.float32)))
+    assert np.array_equal(ag.inv(ok).to_numpy(), 0.5 * np.eye(1024, dtype=np.float32))
+    x = np.asfortranarray(np.array([1.5, -2.0, 0.5], dtype=np.float32))
+    xd = ag.DArray.from_numpy(x)
+
+    def f(v):
+        a, b, c = v
+        t = ag.mul(a, b)
+        for e in v:
+            t = ag.add(t, ag.mul(e, c))
+        return t
+    g = ag.grad(f)(xd)
+    g = g.full().to_numpy() if hasattr(g, "full") else g.to_numpy()
+    assert np.allclose(g, [x[1] + x[2], x[0] + x[2], x[0] + x[1] + 2 * x[2]])
