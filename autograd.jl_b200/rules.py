@@ -687,6 +687,29 @@ def _mean_fwd(x, dims=None):
 mean = primitive("mean", _mean_fwd,
                  lambda dy, y, x, dims=None: div(_sum_back(dy, y, x, dims), length(x) // length(dy)))
 
+def _meanmap_fwd(which):
+    def fwd(x, dims=None):
+        s = _sum_fwd_map(which)(x, dims)
+        return div.fwd(s, length(x) // max(length(s), 1))
+    return fwd
+
+
+# mean(abs, x; dims), mean(abs2, x; dims)  (src/statistics.jl:9-10)
+meanabs = primitive("mean(abs)", _meanmap_fwd("abs"),
+                    lambda dy, y, x, dims=None: div(mul(dy, sign(x)), length(x) // length(dy)))
+meanabs2 = primitive("mean(abs2)", _meanmap_fwd("abs2"),
+                     lambda dy, y, x, dims=None: div(mul(dy, mul(2, x)), length(x) // length(dy)))
+
+
+def varm(x, m, dims=None, corrected=True):
+    """varm(x, m; corrected, dims) (src/statistics.jl:27)."""
+    return var(x, dims=dims, corrected=corrected, mean_=m)
+
+
+def stdm(x, m, dims=None, corrected=True):
+    return sqrt(varm(x, m, dims=dims, corrected=corrected))
+
+
 def var(x, dims=None, corrected=True, mean_=None):
     """var as a composite over primitives (src/statistics.jl:24-35): sum(abs2, x .- m) / (n - corrected)."""
     m = mean(x, dims=dims) if mean_ is None else mean_

@@ -919,6 +919,10 @@ meanabs2 = primitive("mean(abs2,·)", lambda x, dims=None: _mean_fwd(x, dims, la
                      lambda dy, y, x, dims=None: div(mul(dy, mul(2, x)), length(x) // length(dy)))
 
 
+meanabs = primitive("mean(abs,·)", lambda x, dims=None: _mean_fwd(x, dims, np.abs),                                           # src/statistics.jl:9
+                    lambda dy, y, x, dims=None: div(mul(dy, sign(x)), length(x) // length(dy)))
+
+
 def _extremum(npf):
     def fwd(x, dims=None):
         if dims is None:

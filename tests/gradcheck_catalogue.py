@@ -58,6 +58,9 @@ def check_catalogue(ag):
         assert ag.gradcheck(f, distinct) and ag.gradcheck(lambda z: f(z, dims=0), distinct), f
     for f in (ag.var, ag.std, ag.norm):
         assert ag.gradcheck(f, a), f
+    for f in (ag.meanabs, ag.meanabs2):                                  # src/statistics.jl:9-10
+        assert ag.gradcheck(f, a) and ag.gradcheck(lambda z: f(z, dims=0), a) and ag.gradcheck(lambda z: f(z, dims=1), a), f
+    assert ag.gradcheck(lambda z: ag.varm(z, 0.9, dims=0), a) and ag.gradcheck(lambda z: ag.stdm(z, 0.9), a)
     assert ag.gradcheck(ag.dot, a, b)
     # src/linearalgebra.jl:19-20,86,90,92,176-186
     sq = dev(rng.standard_normal((4, 4)))

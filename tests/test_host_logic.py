@@ -536,3 +536,25 @@ def test_iterating_a_tracked_array_goes_through_getindex(hostlib, oracle):
     assert np.allclose(g, [x[1] + x[2], x[0] + x[2], x[0] + x[1] + 2 * x[2]])
     p = ag.Param(2.5)
     assert [e is p for e in p] == [True]
+
+
+def test_mean_of_abs_and_varm_host_rules(hostlib, oracle):
+    """mean(abs, x; dims), mean(abs2, x; dims), varm / stdm (src/statistics.jl:9-10,26-35) against the oracle / numpy."""
+    ag = hostlib
+    rng = np.random.default_rng(61)
+    x = np.asfortranarray(rng.standard_normal((5, 7)))
+    xd = ag.DArray.from_numpy(x)
+    for dims in (None, 0, 1):
+        for fo, fd in ((oracle.meanabs, ag.meanabs), (oracle.meanabs2, ag.meanabs2)):
+            assert np.allclose(float(ag.value(fd(xd, dims=dims))) if dims is None else fd(xd, dims=dims).to_numpy(), fo(x, dims=dims))
+            w = rng.standard_normal(np.shape(fo(x, dims=dims))) if dims is not None else 1.7
+            wd = ag.DArray.from_numpy(np.asfortranarray(w)) if dims is not None else w
+            go = oracle.grad(lambda v: oracle.sum_(oracle.mul(fo(v, dims=dims), w)))(x)
+            gd = ag.grad(lambda v: ag.sum_(ag.mul(fd(v, dims=dims), wd)))(xd).to_numpy()
+            assert np.allclose(gd, go, rtol=1e-12, atol=1e-14), (dims, fd)
+    m = x.mean(axis=0, keepdims=True) + 0.1
+    md = ag.DArray.from_numpy(np.asfortranarray(m))
+    ref = ((x - m) ** 2).sum(axis=0, keepdims=True) / (5 - 1)
+    assert np.allclose(ag.varm(xd, md, dims=0).to_numpy(), ref) and np.allclose(ag.stdm(xd, md, dims=0).to_numpy(), np.sqrt(ref))
+    g = ag.grad(lambda v: ag.sum_(ag.varm(v, md, dims=0)))(xd).to_numpy()
+    assert np.allclose(g, 2 * (x - m) / 4)
