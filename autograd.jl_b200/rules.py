@@ -663,6 +663,22 @@ def _extremum_back(dy, y, x, dims=None):
     return mul(dy, _mask(y, x))
 
 
+# maximum(abs, x; dims), minimum(abs, x; dims): dy.*(y.==abs.(x)).*sign.(x)  (src/base.jl:203,206)
+def _absext(op):
+    def fwd(x, dims=None):
+        if isnum(x):
+            return abs(x)
+        r = D.reduce_dims(abs_.fwd(x), _dims(dims), op)
+        return r.reshape(()) if dims is None else r
+    return fwd
+
+
+def _absext_back(dy, y, x, dims=None):
+    return mul(mul(dy, _mask(y, abs_(value(x)))), sign(x))
+
+
+maxabs = primitive("maximum(abs)", _absext("max"), _absext_back)
+minabs = primitive("minimum(abs)", _absext("min"), _absext_back)
 maximum = primitive("maximum", _extremum("max", max), _extremum_back)
 minimum = primitive("minimum", _extremum("min", min), _extremum_back)
 prod = primitive("prod", _extremum("prod", None), lambda dy, y, x, dims=None: mul(dy, div(y, x)))
@@ -890,11 +906,18 @@ isequal = _z("isequal", lambda a, b: size(a) == size(b) and _count(add(eq(a, b),
 isapprox = _z("isapprox", lambda a, b, rtol=None, atol=0.0: float(value(norm(sub(a, b)))) <= max(
     atol, (math.sqrt(float(np.finfo(value(a).dtype if isinstance(value(a), DArray) else np.float64).eps)) if rtol is None else rtol)
     * max(float(value(norm(a))), float(value(norm(b))))))
-div_ = _z("div", lambda a, b: trunc(div(a, b)))                  # div(x, y) = trunc(x / y)
-rem = _z("rem", lambda a, b: sub(a, mul(b, trunc(div(a, b)))))  # rem(x, y) = x - y * trunc(x / y)
+div_ = _z("div", lambda a, b: trunc(div(a, b)))                  # div(x, y) = trunc(x / y)  (@zerograd, src/base.jl:88)
+# rem is differentiable (src/base.jl:144): rem(x1, x2) = x1 - x2 * div(x1, x2);  dx1 = dy, dx2 = -dy .* div.(x1, x2)
+rem = primitive("rem", lambda a, b: sub(a, mul(b, trunc(div(a, b)))),
+                lambda dy, y, x1, x2: unbroadcast(x1, dy),
+                lambda dy, y, x1, x2: unbroadcast(x2, mul(neg(dy), div_(x1, x2))))
+# x1 .\ x2 = x2 ./ x1 (src/base.jl:39-42)
+ldiv = primitive("\\", lambda x1, x2: div(x2, x1),
+                 lambda dy, y, x1, x2: unbroadcast(x1, div(mul(neg(dy), x2), abs2(x1))),
+                 lambda dy, y, x1, x2: unbroadcast(x2, div(dy, x1)))
 unsafe_trunc = trunc
-widemul = _z("widemul", lambda a, b: mul(a, b))
-float_ = _z("float", lambda x: x)                                # device arrays are Float32 / Float64 already
+widemul = mul                                                    # src/base.jl:156: the rules of .*
+float_ = identity                                                # src/base.jl:98: dy passes through
 eltype = _z("eltype", lambda x: x.dtype if isinstance(x, DArray) else type(x))
 eps = _z("eps", lambda x: float(np.finfo(x.dtype).eps) if isinstance(x, DArray) else float(np.spacing(x)))
 typemax = _z("typemax", lambda x: math.inf)

@@ -931,6 +931,14 @@ def _extremum(npf):
     return fwd
 
 
+_absx = lambda npf: (lambda x, dims=None: _extremum(npf)(np.abs(x), dims))
+maxabs = primitive("maximum(abs,·)", _absx(np.max), lambda dy, y, x, dims=None: mul(mul(dy, _eqmask(y, np.abs(value(x)))), sign(x)))   # src/base.jl:203
+minabs = primitive("minimum(abs,·)", _absx(np.min), lambda dy, y, x, dims=None: mul(mul(dy, _eqmask(y, np.abs(value(x)))), sign(x)))   # :206
+rem = primitive("rem", _np(np.fmod), lambda dy, y, x1, x2: unbroadcast(x1, dy),                                                     # :144
+                lambda dy, y, x1, x2: unbroadcast(x2, mul(neg(dy), np.trunc(value(x1) / value(x2)))))
+ldiv = primitive("\\", _np(lambda a, b: b / a),                                                                                    # :39-42
+                 lambda dy, y, x1, x2: unbroadcast(x1, div(mul(neg(dy), x2), abs2(x1))),
+                 lambda dy, y, x1, x2: unbroadcast(x2, div(dy, x1)))
 maximum = primitive("maximum", _extremum(np.max), lambda dy, y, x, dims=None: mul(dy, _eqmask(y, x)))
 minimum = primitive("minimum", _extremum(np.min), lambda dy, y, x, dims=None: mul(dy, _eqmask(y, x)))
 prod = primitive("prod", lambda x, dims=None: (np.prod(x) if dims is None else

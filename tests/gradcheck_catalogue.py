@@ -58,6 +58,12 @@ def check_catalogue(ag):
         assert ag.gradcheck(f, distinct) and ag.gradcheck(lambda z: f(z, dims=0), distinct), f
     for f in (ag.var, ag.std, ag.norm):
         assert ag.gradcheck(f, a), f
+    spread = dev(rng.permutation(12).reshape(3, 4) / 7.0 - 0.8)          # distinct |values|, both signs
+    for f in (ag.maxabs, ag.minabs):                                     # src/base.jl:203,206
+        assert ag.gradcheck(f, spread) and ag.gradcheck(lambda z: f(z, dims=0), spread) and ag.gradcheck(lambda z: f(z, dims=1), spread), f
+    num, den = dev(rng.uniform(3.1, 8.9, (3, 4))), dev(rng.uniform(1.05, 1.95, (3, 4)))
+    assert ag.gradcheck(ag.ldiv, num, den) and ag.gradcheck(lambda z: ag.ldiv(z, 2.0), num) and ag.gradcheck(ag.widemul, num, den)
+    assert ag.gradcheck(ag.float_, num)
     for f in (ag.meanabs, ag.meanabs2):                                  # src/statistics.jl:9-10
         assert ag.gradcheck(f, a) and ag.gradcheck(lambda z: f(z, dims=0), a) and ag.gradcheck(lambda z: f(z, dims=1), a), f
     assert ag.gradcheck(lambda z: ag.varm(z, 0.9, dims=0), a) and ag.gradcheck(lambda z: ag.stdm(z, 0.9), a)

@@ -497,6 +497,12 @@ def test_zerograd_value_helpers_host(hostlib):
     b = np.asfortranarray(np.array([[2.0, 2.0, -4.0], [0.5, 5.0, 3.0]], dtype=np.float64))
     ad, bd = ag.DArray.from_numpy(a), ag.DArray.from_numpy(b)
     assert np.array_equal(ag.div_(ad, bd).to_numpy(), np.trunc(a / b)) and np.array_equal(ag.rem(ad, bd).to_numpy(), np.fmod(a, b))
+    # rem is differentiable (src/base.jl:144): dx1 = dy, dx2 = -dy .* div.(x1, x2); float / widemul pass gradients
+    g1 = ag.grad(lambda v: ag.sum_(ag.rem(v, bd)))(ad).to_numpy()
+    g2 = ag.grad(lambda v: ag.sum_(ag.rem(ad, v)))(bd).to_numpy()
+    assert np.array_equal(g1, np.ones_like(a)) and np.array_equal(g2, -np.trunc(a / b))
+    assert np.array_equal(ag.grad(lambda v: ag.sum_(ag.widemul(ag.float_(v), bd)))(ad).to_numpy(), b)
+    assert np.array_equal(ag.ldiv(ad, bd).to_numpy(), b / a)
     assert np.array_equal(ag.ne(ad, bd).to_numpy(), (a != b).astype(np.float64)) and np.array_equal(ag.widemul(ad, bd).to_numpy(), a * b)
     assert ag.isequal(xd, ag.DArray.from_numpy(x.copy(order="F"))) and not ag.isequal(ad, bd) and not ag.isequal(ad, xd)
     assert ag.isapprox(ad, ag.DArray.from_numpy(np.asfortranarray(a * (1 + 1e-9 if np.float64 == np.float64 else 1 + 1e-5)))) and not ag.isapprox(ad, bd)
