@@ -1041,6 +1041,10 @@ def kron(a, b):
     return reshape(mul(reshape(a, (1, m1, 1, n1)), reshape(b, (m2, 1, n2, 1))), (m1 * m2, n1 * n2))
 
 
+# view(x, i...) (src/getindex.jl:36): same rule as getindex.  Tracked buffers are never overwritten while recording
+# (src/getindex.jl:12-28), so a copy of the selection is indistinguishable from an aliasing view on this path.
+view = primitive("view", _getindex_fwd, lambda dxi, xi, x, *idx: ungetindex(x, dxi, idx), only_first=True)
+
 # ---------------------------------------------------------------------------------------------------
 # cat / uncat (src/cat.jl:27-31,46-92,122-123) and cat1d (src/cat.jl:150-182)
 # ---------------------------------------------------------------------------------------------------

@@ -86,3 +86,4 @@ def check_catalogue(ag):
     assert ag.gradcheck(lambda p, q: ag.cat1d(p, q), a, row)
     for idx in [(slice(None), [1, 1, 2]), ([0, 2],), (1, 2), (slice(0, 2), slice(1, 3))]:
         assert ag.gradcheck(lambda z: ag.getindex(z, *idx), a), idx
+        assert ag.gradcheck(lambda z: ag.view(z, *idx), a), ("view", idx)             # src/getindex.jl:36
