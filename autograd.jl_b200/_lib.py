@@ -66,6 +66,7 @@ _SIGS = {
     "ag_special_param": [i32, i32, i32, vp, vp, i64],
     "ag_inv_det": [i32, vp, i64, vp, vp],
     "ag_argext": [i32, vp, i64, i32, vp],
+    "ag_cast": [i32, i32, vp, vp, i64],
     "ag_unary_bwd": [i32, i32, vp, i32, dbl, vp, vp, vp, i64],
     "ag_binary_fwd": [i32, i32, vp, dbl, pi64, vp, dbl, pi64, vp, i32, pi64],
     "ag_binary_bwd": [i32, i32, i32, vp, pi64, vp, dbl, pi64, vp, dbl, pi64, vp, pi64, vp, i32, pi64],

@@ -5,6 +5,7 @@
 // SM and latency-bound, so there is nothing to tile -- it exists so that the rules run without a host round trip of
 // the matrix.  n <= 1024.
 #include <algorithm>
+#include <cstdint>
 #include "common.cuh"
 
 namespace agb {
@@ -125,9 +126,50 @@ __global__ void __launch_bounds__(256) k_argext_final(const Cand* __restrict__ i
   if (threadIdx.x == 0) *idx = best.i;
 }
 
+// ---- eltype conversion Float32 <-> Float64 (oftype / big / convert: src/base.jl:76,365): four elements per thread,
+// 128-bit accesses on the Float32 side, 2 x 128-bit on the Float64 side; HBM-bound, 12 bytes per element.
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) k_cast(const S* __restrict__ x, D* __restrict__ y, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 4 <= n) {
+    S v[4];
+    if constexpr (sizeof(S) == 4) {
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(x + i);
+    } else {
+      *reinterpret_cast<double2*>(v) = *reinterpret_cast<const double2*>(x + i);
+      *reinterpret_cast<double2*>(v + 2) = *reinterpret_cast<const double2*>(x + i + 2);
+    }
+    D o[4] = {(D)v[0], (D)v[1], (D)v[2], (D)v[3]};
+    if constexpr (sizeof(D) == 4) {
+      *reinterpret_cast<float4*>(y + i) = *reinterpret_cast<float4*>(o);
+    } else {
+      *reinterpret_cast<double2*>(y + i) = *reinterpret_cast<double2*>(o);
+      *reinterpret_cast<double2*>(y + i + 2) = *reinterpret_cast<double2*>(o + 2);
+    }
+  } else {
+    for (int64_t j = i; j < n; ++j) y[j] = (D)x[j];
+  }
+}
+
 }  // namespace agb
 
 using namespace agb;
+
+extern "C" ag_status ag_cast(int32_t src_dtype, int32_t dst_dtype, const void* x, void* y, int64_t n) {
+  AG_REQUIRE_INIT();
+  if (n == 0) return AG_OK;
+  AG_CHECK(x && y && n > 0, AG_EINVAL, "ag_cast: bad arguments");
+  AG_CHECK((src_dtype == AG_F32 && dst_dtype == AG_F64) || (src_dtype == AG_F64 && dst_dtype == AG_F32), AG_EUNSUPPORTED,
+           "ag_cast: %d -> %d (Float32 <-> Float64 only)", src_dtype, dst_dtype);
+  AG_CHECK(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), AG_EINVAL, "ag_cast: buffers must be 16-byte aligned");
+  Context& c = ctx();
+  const unsigned nb = (unsigned)cdiv(n, (int64_t)1024);
+  if (src_dtype == AG_F32) k_cast<float, double><<<nb, 256, 0, c.stream>>>((const float*)x, (double*)y, n);
+  else k_cast<double, float><<<nb, 256, 0, c.stream>>>((const double*)x, (float*)y, n);
+  AG_LAUNCHED();
+  return AG_OK;
+}
 
 extern "C" ag_status ag_argext(int32_t dtype, const void* x, int64_t n, int32_t want_max, int64_t* idx_out) {
   AG_REQUIRE_INIT();

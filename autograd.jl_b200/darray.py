@@ -874,6 +874,18 @@ SP = dict(besselj=0, bessely=1, polygamma=2, invdigamma=3, dawson=4, erfi=5, air
           exponent=16, significand=17, rem2pi=18)
 
 
+def astype(x, dtype):
+    """Float32 <-> Float64 copy of a device array (ag_cast); the same array when the eltype already matches."""
+    x = materialize(x)
+    dtype = np.dtype(dtype)
+    if np.dtype(x.dtype) == dtype:
+        return x
+    out = DArray.empty(x.shape, dtype.type)
+    if x.size:
+        check(lib.ag_cast(x.dt, out.dt, vptr(x), vptr(out), x.size))
+    return out
+
+
 def argext(x, want_max):
     """0-based column-major position of the first maximum / minimum of x (ag_argext); read back to the host."""
     x = materialize(x)

@@ -916,6 +916,22 @@ ldiv = primitive("\\", lambda x1, x2: div(x2, x1),
                  lambda dy, y, x1, x2: unbroadcast(x1, div(mul(neg(dy), x2), abs2(x1))),
                  lambda dy, y, x1, x2: unbroadcast(x2, div(dy, x1)))
 unsafe_trunc = trunc
+
+
+
+def _dtype_of(t):
+    t = value(t)
+    return np.dtype(t.dtype if isinstance(t, DArray) else (t if isinstance(t, (type, np.dtype)) else np.float64))
+
+
+def _oftype_fwd(t, x):
+    return D.astype(x, _dtype_of(t)) if isinstance(x, DArray) else x
+
+
+# oftype(t, x): x converted to t's eltype; the gradient is converted back to x's (src/base.jl:365).  `t` is an array,
+# an eltype (np.float32 / np.float64) or a Value of either.
+oftype = primitive("oftype", _oftype_fwd, None, lambda dy, y, t, x: oftype(x, dy))
+big = primitive("big", lambda x: _oftype_fwd(np.float64, x), lambda dy, y, x: oftype(x, dy))      # src/base.jl:76: widest eltype here is Float64
 widemul = mul                                                    # src/base.jl:156: the rules of .*
 float_ = identity                                                # src/base.jl:98: dy passes through
 eltype = _z("eltype", lambda x: x.dtype if isinstance(x, DArray) else type(x))

@@ -206,6 +206,9 @@ ag_status ag_inv_det(int32_t dtype, const void* a, int64_t n, void* inv_out, voi
 /* *idx_out (device int64) = 0-based position of the first maximum (want_max != 0) or minimum of x[0..n); a NaN wins,
  * like Julia's argmax / argmin (@zerograd, src/base.jl:60-61).  Two launches. */
 ag_status ag_argext(int32_t dtype, const void* x, int64_t n, int32_t want_max, int64_t* idx_out);
+/* y[i] = (dst eltype) x[i]: Float32 <-> Float64 conversion of a device array (oftype / big / Float64.(x),
+ * src/base.jl:76,365).  Buffers 16-byte aligned (pool blocks are). */
+ag_status ag_cast(int32_t src_dtype, int32_t dst_dtype, const void* x, void* y, int64_t n);
 /* dx[i] = dy[i] * g(x[i], y[i]).  dy: device array (dy_mode 0), device scalar (1), or the
  * immediate dy_scalar (2).  x / y may be NULL when g does not use them.
  * Replaces the broadcast expression in each rule of src/math.jl:9-74. */

@@ -391,6 +391,16 @@ function argext(x::DArray{T}, want_max::Bool) where T
 end
 Base.argmax(x::DArray) = argext(x, true)
 Base.argmin(x::DArray) = argext(x, false)
+# eltype conversion on the device (oftype / big / Float64.(x), src/base.jl:76,365)
+function cast(::Type{D}, x::DArray{S}) where {D<:DT,S}
+    D === S && return x
+    y = DArray{D}(undef, size(x))
+    isempty(x) || check(ccall((:ag_cast, LIB), Int32, (Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int64), dtcode(S), dtcode(D), x.ptr, y.ptr, length(x)))
+    y
+end
+Base.oftype(t::DArray{D}, x::DArray) where D = cast(D, x)
+Base.big(x::DArray) = cast(Float64, x)
+broadcasted(::Type{D}, x::DArray) where {D<:DT} = cast(D, x)
 # binary broadcasting rules: fused kernel + unbroadcast (src/base.jl:21-49, src/math.jl:24,48,54-55)
 for (f, id) in BINARY
     f in (:(==), :<, :<=, :>, :>=) && continue                # @zerograd (src/base.jl:52-60)

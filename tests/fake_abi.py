@@ -425,6 +425,11 @@ class FakeLib:
     def ag_sum_all(self, m, dtype, x, n, out):
         return self.ag_sum_dim(m, dtype, x, 1, n, 1, out)
 
+    def ag_cast(self, src, dst, x, y, n):
+        self.launches += 1
+        _arr(y, n, _DT[dst])[:] = _arr(x, n, _DT[src]).astype(_DT[dst])
+        return 0
+
     def ag_argext(self, dtype, x, n, want_max, idx_out):
         self.launches += 2
         v = _arr(x, n, _DT[dtype])

@@ -518,6 +518,15 @@ def test_zerograd_value_helpers_host(hostlib):
     assert ag.argmax(bigd) == int(np.argmax(flat)) == 5 + 7 * 257 and ag.argmin(bigd) == int(np.argmin(flat)) == 100 + 3 * 257
     assert ag.argmax(xd) == ag.argmin(xd) == 2 * 3 + 0                   # the NaN at (0, 2) wins both, like Julia
     assert ag.argmax(ag.Param(bigd)) == 5 + 7 * 257
+    # oftype / big (src/base.jl:76,365): eltype conversion on the device, the gradient comes back in x's eltype
+    other = np.float32 if np.float64 == np.float64 else np.float64
+    odd = np.asfortranarray(np.random.default_rng(67).standard_normal((7, 11)).astype(np.float64))          # 77 elements: tail path
+    oddd = ag.DArray.from_numpy(odd)
+    conv = ag.oftype(other, oddd)
+    assert conv.dtype == other and np.array_equal(conv.to_numpy(), odd.astype(other)) and ag.oftype(np.float64, oddd) is oddd
+    assert ag.big(oddd).dtype == np.float64 and np.array_equal(ag.big(oddd).to_numpy(), odd.astype(np.float64))
+    g = ag.grad(lambda v: ag.sum_(ag.abs2(ag.oftype(other, v))))(oddd)
+    assert g.dtype == np.float64 and np.allclose(g.to_numpy(), 2 * odd, rtol=1e-6)
     # unboxing: inside a tape the helpers see the Param's value and contribute no gradient
     g = ag.grad(lambda v: ag.sum_(ag.mul(v, ag.isfinite(v))))(ad).to_numpy()
     assert np.array_equal(g, np.ones_like(a))
